@@ -1,0 +1,98 @@
+"""Shared helpers for the parity tests: build the reference-side / oracle-side objects from a
+distributions_b200.synth workload dict.  Test infrastructure (uses oracle/)."""
+import numpy as np
+
+from distributions_b200 import synth
+from oracle.pyoracle import BB, DD, DPD, GP, NICH
+
+MODEL_ID = {"dd": DD, "dpd": DPD, "bb": BB, "gp": GP, "nich": NICH}
+
+# The small configurations stored in tests/golden (seed, G, N).  G values are deliberately ragged
+# (not multiples of 32) and include G=1 (a single, empty group).
+SMALL = {
+    "nich": dict(seed=101, G=37, N=96),
+    "gp": dict(seed=102, G=21, N=96),
+    "bb": dict(seed=103, G=13, N=96),
+    "dd": dict(seed=104, G=29, N=96, dim=16),
+    "dpd": dict(seed=105, G=19, N=96, V=100, other_frac=0.1),
+}
+
+
+def make(model, **kw):
+    kw = dict(kw)
+    return getattr(synth, model)(kw.pop("seed"), kw.pop("G"), kw.pop("N"), **kw)
+
+
+def ref_add_feature(kind, w):
+    """Add workload w as a feature of a reference RefKind."""
+    m = w["model"]
+    if m == "nich":
+        return kind.add_nich(w["shared"], w["count"], w["mean"], w["ctv"])
+    if m == "gp":
+        return kind.add_gp(w["shared"], w["count"], w["sum"])
+    if m == "bb":
+        return kind.add_bb(w["shared"], w["heads"], w["tails"])
+    if m == "dd":
+        return kind.add_dd(w["alphas"], w["counts"])
+    if m == "dpd":
+        return kind.add_dpd(w["gamma"], w["alpha"], w["beta0"], w["keys"], w["betas"], w["counts"])
+    raise ValueError(m)
+
+
+def oracle_caches(o, w):
+    m = w["model"]
+    if m == "nich":
+        return o.nich_caches(w["shared"], w["count"], w["mean"], w["ctv"])
+    if m == "gp":
+        return o.gp_caches(w["shared"], w["count"], w["sum"])
+    if m == "bb":
+        return o.bb_caches(w["shared"], w["heads"], w["tails"])
+    if m == "dd":
+        return o.dd_caches(w["alphas"], w["counts"])
+    if m == "dpd":
+        return o.dpd_caches(w["alpha"], w["beta0"], w["betas"], w["counts"])
+    raise ValueError(m)
+
+
+def dpd_rows(w, values=None):
+    """dense table row of each dpd value: index into keys, or V for OTHER / unknown."""
+    values = w["values"] if values is None else values
+    keys = w["keys"]
+    order = np.argsort(keys)
+    pos = np.searchsorted(keys[order], values)
+    pos = np.clip(pos, 0, keys.size - 1)
+    hit = keys[order][pos] == values
+    return np.where(hit, order[pos], keys.size).astype(np.uint32)
+
+
+def oracle_scores(o, feats, n=None, prior=None):
+    """prior (or zeros) + sum over feature workloads, via the C restatement."""
+    G = feats[0]["sizes"].size
+    n = feats[0]["values"].shape[0] if n is None else n
+    scores = np.zeros((n, G), np.float32)
+    if prior is not None:
+        scores += prior[None, :]
+    for w in feats:
+        vals = w["values"][:n]
+        if w["model"] == "dpd":
+            vals = dpd_rows(w, vals)
+        o.score_rows(MODEL_ID[w["model"]], oracle_caches(o, w), vals, scores)
+    return scores
+
+
+def explained_mismatch(scores64, u, a, b, eps):
+    """True where indices a != b are explained by u*total lying within eps*total of a CDF
+    boundary between them (a 'near-tie', SURVEY.md §7 hard parts)."""
+    s = scores64 - scores64.max(axis=1, keepdims=True)
+    lik = np.exp(s)
+    cdf = np.cumsum(lik, axis=1)
+    total = cdf[:, -1]
+    t = u.astype(np.float64) * total
+    lo = np.minimum(a, b)
+    hi = np.maximum(a, b)
+    ok = np.ones(len(u), bool)
+    for i in np.nonzero(a != b)[0]:
+        # every boundary cdf[lo..hi-1] must be within eps*total of t
+        seg = cdf[i, lo[i]:hi[i]]
+        ok[i] = np.all(np.abs(seg - t[i]) <= eps * total[i])
+    return ok
