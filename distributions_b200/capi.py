@@ -1,0 +1,256 @@
+"""ctypes binding of the C-ABI in include/dist_b200.h (libdist_b200.so).
+
+The library is the only compute path: if it is missing or fails to load, importing this module
+raises -- there is no Python / CPU fallback for scoring or sampling.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdist_b200.so")
+
+DD, DPD, BB, GP, NICH, NIW = 0, 1, 2, 3, 4, 5
+MODEL_NAMES = {DD: "dd", DPD: "dpd", BB: "bb", GP: "gp", NICH: "nich", NIW: "niw"}
+COLUMN_DTYPE = {DD: np.int32, DPD: np.uint32, BB: np.uint8, GP: np.uint32, NICH: np.float32, NIW: np.float32}
+
+c_f, c_i, c_sz, c_p = ctypes.c_float, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p
+
+# every symbol include/dist_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "dist_b200_abi_version": (c_i, []),
+    "dist_b200_ctx_create": (c_i, [c_i, ctypes.POINTER(c_p)]),
+    "dist_b200_ctx_destroy": (None, [c_p]),
+    "dist_b200_last_error": (ctypes.c_char_p, [c_p]),
+    "dist_b200_sm_count": (c_i, [c_p]),
+    "dist_b200_feature_create": (c_i, [c_p, c_i, ctypes.POINTER(c_p)]),
+    "dist_b200_feature_destroy": (None, [c_p]),
+    "dist_b200_feature_model": (c_i, [c_p]),
+    "dist_b200_feature_groups": (c_i, [c_p]),
+    "dist_b200_nich_update_all": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, c_p]),
+    "dist_b200_gp_update_all": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p]),
+    "dist_b200_bb_update_all": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p]),
+    "dist_b200_dd_update_all": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p]),
+    "dist_b200_dpd_update_all": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_i, c_p, c_p]),
+    "dist_b200_niw_update_all": (c_i, [c_p, c_i, c_p, c_f, c_p, c_f, c_i, c_p, c_p, c_p, c_p]),
+    "dist_b200_feature_update_group": (c_i, [c_p, c_i, c_p, c_p]),
+    "dist_b200_feature_add_group": (c_i, [c_p, c_p]),
+    "dist_b200_feature_remove_group": (c_i, [c_p, c_i, c_p]),
+    "dist_b200_feature_download_caches": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
+    "dist_b200_prior_pitman_yor": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
+    "dist_b200_score_batch": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_i, c_p]),
+    "dist_b200_score_sample_batch": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_p, c_p, c_p]),
+    "dist_b200_sample_from_scores": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p, c_p]),
+    "dist_b200_score_sample_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_p, c_p]),
+    "dist_b200_score_value_host": (c_i, [c_p, c_p, c_p, c_p]),
+    "dist_b200_numerics_probe": (c_i, [c_p, c_i, c_sz, c_p, c_p, c_p]),
+    "dist_b200_pipe_peak": (c_i, [c_p, c_i, ctypes.POINTER(ctypes.c_double)]),
+}
+
+
+class DistB200Error(RuntimeError):
+    pass
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise DistB200Error(
+            "%s is missing: build it with `python -m distributions_b200.build` "
+            "(there is no CPU fallback for the scoring path)" % path)
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = load_library()
+    return _lib
+
+
+def _np_ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def _dev_ptr(t):
+    """device pointer of a torch tensor / raw int / None"""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = lib()
+        h = c_p()
+        rc = self.L.dist_b200_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise DistB200Error("dist_b200_ctx_create(device=%d) failed with status %d (no usable CUDA device?)" % (device, rc))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dist_b200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc, what):
+        if rc != 0:
+            msg = self.L.dist_b200_last_error(self.h)
+            raise DistB200Error("%s failed: status %d: %s" % (what, rc, msg.decode() if msg else ""))
+
+    @property
+    def sm_count(self):
+        return self.L.dist_b200_sm_count(self.h)
+
+    def feature(self, model):
+        return Feature(self, model)
+
+    # -- prior ----------------------------------------------------------------------------------
+    def prior_pitman_yor(self, alpha, d, group_sizes, prior_dev, stream=None):
+        sizes = np.ascontiguousarray(group_sizes, dtype=np.int32)
+        self.check(self.L.dist_b200_prior_pitman_yor(self.h, alpha, d, sizes.size, _np_ptr(sizes), _dev_ptr(prior_dev),
+                                                     stream), "prior_pitman_yor")
+
+    # -- hot path (device pointers) --------------------------------------------------------------
+    def _lists(self, features, columns):
+        F = len(features)
+        fa = (c_p * F)(*[f.h for f in features])
+        ca = (c_p * F)(*[_dev_ptr(c) for c in columns])
+        return F, fa, ca
+
+    def score_batch(self, features, columns, n_rows, prior, scores, accumulate=False, stream=None):
+        F, fa, ca = self._lists(features, columns)
+        self.check(self.L.dist_b200_score_batch(self.h, fa, F, ca, n_rows, _dev_ptr(prior), _dev_ptr(scores),
+                                                1 if accumulate else 0, stream), "score_batch")
+
+    def score_sample_batch(self, features, columns, n_rows, prior, u, assign, scores=None, stream=None):
+        F, fa, ca = self._lists(features, columns)
+        self.check(self.L.dist_b200_score_sample_batch(self.h, fa, F, ca, n_rows, _dev_ptr(prior), _dev_ptr(u),
+                                                       _dev_ptr(assign), _dev_ptr(scores), stream), "score_sample_batch")
+
+    def sample_from_scores(self, scores, n_rows, G, u, assign, stream=None):
+        self.check(self.L.dist_b200_sample_from_scores(self.h, _dev_ptr(scores), n_rows, G, _dev_ptr(u), _dev_ptr(assign),
+                                                       stream), "sample_from_scores")
+
+    # -- host-buffer forms -----------------------------------------------------------------------
+    def score_sample_batch_host(self, features, columns, prior, u, want_scores=False):
+        F = len(features)
+        cols = [np.ascontiguousarray(c, dtype=COLUMN_DTYPE[f.model]) for f, c in zip(features, columns)]
+        n = u.shape[0]
+        G = features[0].groups
+        fa = (c_p * F)(*[f.h for f in features])
+        ca = (c_p * F)(*[c.ctypes.data for c in cols])
+        prior = None if prior is None else np.ascontiguousarray(prior, dtype=np.float32)
+        u = np.ascontiguousarray(u, dtype=np.float32)
+        assign = np.empty(n, dtype=np.int32)
+        scores = np.empty((n, G), dtype=np.float32) if want_scores else None
+        self.check(self.L.dist_b200_score_sample_batch_host(self.h, fa, F, ca, n, _np_ptr(prior), _np_ptr(u), _np_ptr(assign),
+                                                            _np_ptr(scores)), "score_sample_batch_host")
+        return assign, scores
+
+    def score_value_host(self, feature, value, scores_accum):
+        v = np.ascontiguousarray(value, dtype=COLUMN_DTYPE[feature.model])
+        assert scores_accum.dtype == np.float32 and scores_accum.flags.c_contiguous
+        self.check(self.L.dist_b200_score_value_host(self.h, feature.h, _np_ptr(v), _np_ptr(scores_accum)), "score_value_host")
+        return scores_accum
+
+    def pipe_peak(self, which):
+        """lane-ops/s of the MUFU (0) or FP32-FMA (1) pipe, measured with a register-only kernel"""
+        out = ctypes.c_double()
+        self.check(self.L.dist_b200_pipe_peak(self.h, which, ctypes.byref(out)), "pipe_peak")
+        return out.value
+
+    def numerics_probe(self, fn, x_dev, out_dev, n, stream=None):
+        self.check(self.L.dist_b200_numerics_probe(self.h, fn, n, _dev_ptr(x_dev), _dev_ptr(out_dev), stream), "numerics_probe")
+
+
+class Feature:
+    """Device-side MixtureValueScorer of one Model::Mixture."""
+
+    def __init__(self, ctx, model):
+        self.ctx = ctx
+        self.model = model
+        h = c_p()
+        ctx.check(ctx.L.dist_b200_feature_create(ctx.h, model, ctypes.byref(h)), "feature_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.dist_b200_feature_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def groups(self):
+        return self.ctx.L.dist_b200_feature_groups(self.h)
+
+    def update_all(self, w, stream=None):
+        """w: a dict of group statistics in the layout of distributions_b200.synth workloads."""
+        L, c = self.ctx.L, self.ctx
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731
+        u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)  # noqa: E731
+        m = self.model
+        if m == NICH:
+            sh, cnt, mean, ctv = f32(w["shared"]), i32(w["count"]), f32(w["mean"]), f32(w["ctv"])
+            c.check(L.dist_b200_nich_update_all(self.h, _np_ptr(sh), cnt.size, _np_ptr(cnt), _np_ptr(mean), _np_ptr(ctv), stream), "nich_update_all")
+        elif m == GP:
+            sh, cnt, sm = f32(w["shared"]), u32(w["count"]), u32(w["sum"])
+            c.check(L.dist_b200_gp_update_all(self.h, _np_ptr(sh), cnt.size, _np_ptr(cnt), _np_ptr(sm), stream), "gp_update_all")
+        elif m == BB:
+            sh, h, t = f32(w["shared"]), i32(w["heads"]), i32(w["tails"])
+            c.check(L.dist_b200_bb_update_all(self.h, _np_ptr(sh), h.size, _np_ptr(h), _np_ptr(t), stream), "bb_update_all")
+        elif m == DD:
+            al, cnt = f32(w["alphas"]), i32(w["counts"])
+            c.check(L.dist_b200_dd_update_all(self.h, al.size, _np_ptr(al), cnt.shape[0], _np_ptr(cnt), stream), "dd_update_all")
+        elif m == DPD:
+            keys, betas, cnt = u32(w["keys"]), f32(w["betas"]), i32(w["counts"])
+            c.check(L.dist_b200_dpd_update_all(self.h, w["alpha"], w["beta0"], keys.size, _np_ptr(keys), _np_ptr(betas),
+                                               cnt.shape[0], _np_ptr(cnt), stream), "dpd_update_all")
+        elif m == NIW:
+            mu, psi, cnt, sx, sxx = f32(w["mu"]), f32(w["psi"]), i32(w["count"]), f32(w["sum_x"]), f32(w["sum_xxT"])
+            c.check(L.dist_b200_niw_update_all(self.h, mu.size, _np_ptr(mu), w["kappa"], _np_ptr(psi), w["nu"], cnt.size,
+                                               _np_ptr(cnt), _np_ptr(sx), _np_ptr(sxx), stream), "niw_update_all")
+        else:
+            raise ValueError(m)
+        return self
+
+    def update_group(self, groupid, stats, stream=None):
+        buf = np.ascontiguousarray(stats)
+        self.ctx.check(self.ctx.L.dist_b200_feature_update_group(self.h, groupid, _np_ptr(buf), stream), "update_group")
+
+    def add_group(self, stream=None):
+        self.ctx.check(self.ctx.L.dist_b200_feature_add_group(self.h, stream), "add_group")
+
+    def remove_group(self, groupid, stream=None):
+        self.ctx.check(self.ctx.L.dist_b200_feature_remove_group(self.h, groupid, stream), "remove_group")
+
+    def download_caches(self, rows, stream=None):
+        G = self.groups
+        out = np.empty((rows, G), dtype=np.float32)
+        n = c_sz()
+        self.ctx.check(self.ctx.L.dist_b200_feature_download_caches(self.h, _np_ptr(out), out.size, ctypes.byref(n), stream), "download_caches")
+        assert n.value == out.size, (n.value, out.size)
+        return out

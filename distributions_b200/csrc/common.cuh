@@ -1,0 +1,115 @@
+// common.cuh -- shared host/device declarations of the B200 mixture-scoring library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dist_b200.h"
+#include "numerics.cuh"
+
+namespace distb200 {
+
+constexpr int kMaxFeatures = 512;  // feature descriptors travel in kernel-parameter space (16 KB)
+
+// device view of one feature, consumed by the row-mapped score kernel
+struct FeatDesc {
+    const void *params;  // nich/gp/bb: float4[G]; dd: float[G][vdim]; dpd: float[(V+1)][G]
+    const void *column;  // value column, N entries
+    int kind;            // dist_b200_model
+    int vdim;            // dd: dim
+    int pad0, pad1;
+};
+
+struct FeatList {
+    int n;
+    FeatDesc f[kMaxFeatures];
+};
+
+}  // namespace distb200
+
+struct dist_b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string last_error;
+    distb200::NumericTables tables{};
+    float *tables_storage = nullptr;  // one allocation backing `tables`
+    // scratch for the host-buffer entry points
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    void *scratch_dev = nullptr;
+    size_t scratch_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+};
+
+struct dist_b200_feature {
+    dist_b200_ctx *ctx = nullptr;
+    int model = 0;
+    int G = 0;          // packed group count
+    int capacity = 0;   // allocated groups
+    int dim = 0;        // dd: dim, dpd: V, niw: d
+    // hyper-parameters of the last update_all (needed by update_group / add_group)
+    float shared[4] = {0, 0, 0, 0};
+    std::vector<float> alphas;        // dd alphas / dpd betas
+    std::vector<uint32_t> keys;       // dpd keys, sorted
+    std::vector<int> key_order;       // dpd: position in caller's key order of sorted key i
+    bool keys_dense = false;          // dpd: keys == 0..V-1
+    float alpha = 0, beta0 = 0;       // dpd
+    float alpha_sum = 0;              // dd
+    // device buffers
+    void *params = nullptr;           // hot layout (see FeatDesc::params)
+    size_t params_bytes = 0;
+    uint32_t *keys_dev = nullptr;     // dpd sorted keys
+    int *key_rows_dev = nullptr;      // dpd: table row of sorted key i
+    // niw
+    float *niw_buf = nullptr;
+    size_t niw_bytes = 0;
+    float kappa = 0, nu = 0;
+    std::vector<float> mu, psi;
+};
+
+namespace distb200 {
+
+inline int fail(dist_b200_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+#define DISTB200_CUDA(ctx, call)                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return ::distb200::fail((ctx), DIST_B200_ERR_CUDA,                                     \
+                                    std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+// ---- kernel launchers implemented in the .cu files --------------------------------------------
+// prep.cu
+int launch_nich_prep(dist_b200_ctx *ctx, const float shared[4], int G, int g0, int n, const int32_t *count_dev,
+                     const float *mean_dev, const float *ctv_dev, float4 *params, cudaStream_t s);
+int launch_gp_prep(dist_b200_ctx *ctx, const float shared[2], int g0, int n, const uint32_t *count_dev,
+                   const uint32_t *sum_dev, float4 *params, cudaStream_t s);
+int launch_bb_prep(dist_b200_ctx *ctx, const float shared[2], int g0, int n, const int32_t *heads_dev,
+                   const int32_t *tails_dev, float4 *params, cudaStream_t s);
+int launch_dd_prep(dist_b200_ctx *ctx, int dim, const float *alphas_dev, float alpha_sum, int g0, int n,
+                   const int32_t *counts_dev, float *table, cudaStream_t s);
+int launch_dpd_prep(dist_b200_ctx *ctx, float alpha, float beta0, int V, const float *betas_dev, int G,
+                    const int32_t *counts_dev, float *table, cudaStream_t s);
+int launch_prior_prep(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *sizes_dev, float *prior,
+                      cudaStream_t s);
+int launch_numerics_probe(dist_b200_ctx *ctx, int fn, size_t n, const float *in, float *out, cudaStream_t s);
+int launch_unpack_caches(dist_b200_ctx *ctx, const dist_b200_feature *f, float *out_dev, cudaStream_t s);
+
+// score_rows.cu: rows mapped to lanes, groups looped (nich / gp / bb / small-dim dd, any F)
+int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N, const float *prior,
+                      const float *u, int32_t *assign, float *scores, int accumulate, cudaStream_t s);
+// gather_rows.cu: one warp per row, groups mapped to lanes (value-major tables: dpd, wide dd) and the
+// stand-alone sampler over materialised scores
+int launch_gather_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *column, size_t N,
+                       const float *prior, const float *u, int32_t *assign, float *scores, int accumulate,
+                       cudaStream_t s);
+int launch_sample_scores(dist_b200_ctx *ctx, const float *scores, size_t N, int G, const float *u,
+                         int32_t *assign, cudaStream_t s);
+
+}  // namespace distb200

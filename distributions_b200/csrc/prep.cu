@@ -1,0 +1,292 @@
+// prep.cu -- cache rebuild kernels: raw group statistics -> the per-group caches the score kernels
+// read (MixtureValueScorer::update_all / update_group of every model), the Pitman-Yor prior vector,
+// and the numerics probe.  O(G * dim) work, once per batch: not the hot path.  This translation
+// unit is compiled with --fmad=false so that every expression keeps the reference's operation
+// order and rounding (the reference builds for SSE4.1, which has no FMA).
+#include "common.cuh"
+
+namespace distb200 {
+
+// ---------------------------------------------------------------------------------------------
+// NormalInverseChiSq: Shared::plus_group (nich.hpp:58-69) + Scorer::init (nich.hpp:239-250)
+// packed as float4 {mean, precision, log_coeff, score}
+__global__ void nich_prep_kernel(float mu, float kappa, float sigmasq, float nu, int g0, int n,
+                                 const int32_t *__restrict__ count, const float *__restrict__ mean,
+                                 const float *__restrict__ ctv, float4 *__restrict__ params,
+                                 NumericTables t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float cnt = static_cast<float>(count[i]);
+    const float mu_1 = mu - mean[i];
+    const float post_kappa = kappa + cnt;
+    const float post_mu = (kappa * mu + mean[i] * cnt) / post_kappa;
+    const float post_nu = nu + cnt;
+    const float post_sigmasq =
+        1.f / post_nu * (nu * sigmasq + ctv[i] + (cnt * kappa * mu_1 * mu_1) / post_kappa);
+    const float lambda = post_kappa / ((post_kappa + 1.f) * post_sigmasq);
+    const float score = fast_lgamma_nu(post_nu, t.lgamma_nu3) +
+                        0.5f * fast_log_table(lambda / (3.14159265358979f * post_nu), t.log2_table);
+    const float log_coeff = -0.5f * post_nu - 0.5f;
+    const float precision = lambda / post_nu;
+    params[g0 + i] = make_float4(post_mu, precision, log_coeff, score);
+}
+
+// GammaPoisson: plus_group (gp.hpp:56-61) + Scorer::init (gp.hpp:198-207); {post_alpha, score_coeff, score, 0}
+__global__ void gp_prep_kernel(float alpha, float inv_beta, int g0, int n, const uint32_t *__restrict__ count,
+                               const uint32_t *__restrict__ sum, float4 *__restrict__ params, NumericTables t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float post_alpha = alpha + static_cast<float>(sum[i]);
+    const float post_inv_beta = inv_beta + static_cast<float>(count[i]);
+    const float score_coeff = -fast_log_table(1.f + post_inv_beta, t.log2_table);
+    const float score = -fast_lgamma_exact(post_alpha, t.lgamma5) +
+                        post_alpha * (fast_log_table(post_inv_beta, t.log2_table) + score_coeff);
+    params[g0 + i] = make_float4(post_alpha, score_coeff, score, 0.f);
+}
+
+// BetaBernoulli: update_all (bb.hpp:276-292); {heads_score, tails_score, 0, 0}
+__global__ void bb_prep_kernel(float alpha, float beta, int g0, int n, const int32_t *__restrict__ heads,
+                               const int32_t *__restrict__ tails, float4 *__restrict__ params, NumericTables t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float h = alpha + static_cast<float>(heads[i]);
+    const float tl = beta + static_cast<float>(tails[i]);
+    params[g0 + i] = make_float4(fast_log_table(h / (h + tl), t.log2_table),
+                                 fast_log_table(tl / (h + tl), t.log2_table), 0.f, 0.f);
+}
+
+// DirichletDiscrete: update_all (dd.hpp:399-421) folded with score_value's subtraction
+// (dd.hpp:433-445 -> vector_math.cc:160-168): table[g][v] (stride_g, stride_v) =
+// fast_log(alphas[v] + counts[g][v]) - fast_log(alpha_sum + count_sum[g])
+__global__ void dd_prep_kernel(int dim, const float *__restrict__ alphas, float alpha_sum, int g0, int n,
+                               const int32_t *__restrict__ counts, float *__restrict__ table, size_t stride_g,
+                               size_t stride_v, NumericTables t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t *c = counts + static_cast<size_t>(i) * dim;
+    int32_t count_sum = 0;
+    for (int v = 0; v < dim; ++v) count_sum += c[v];
+    const float shift = fast_log_table(alpha_sum + static_cast<float>(count_sum), t.log2_table);
+    float *out = table + static_cast<size_t>(g0 + i) * stride_g;
+    for (int v = 0; v < dim; ++v) {
+        out[v * stride_v] = fast_log_table(alphas[v] + static_cast<float>(c[v]), t.log2_table) - shift;
+    }
+}
+
+// DirichletProcessDiscrete: update_all (dpd.hpp:471-497) folded with score_value (dpd.hpp:517-543):
+// value-major table[(V+1)][G]; row V is the OTHER / unseen row fast_log(alpha*beta0) - shift[g].
+__global__ void dpd_shift_kernel(float alpha, int V, int G, const int32_t *__restrict__ counts,
+                                 float *__restrict__ shift, NumericTables t) {
+    // one warp per group: total count over the V known values
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= G) return;
+    long long total = 0;
+    for (int v = lane; v < V; v += 32) total += counts[static_cast<size_t>(g) * V + v];
+    for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) shift[g] = fast_log_table(alpha + static_cast<float>(total), t.log2_table);
+}
+
+__global__ void dpd_table_kernel(float alpha, float beta0, int V, const float *__restrict__ betas, int G,
+                                 const int32_t *__restrict__ counts, const float *__restrict__ shift,
+                                 float *__restrict__ table, NumericTables t) {
+    // 32x32 tile transpose: counts are [G][V] (read along v), table is [V+1][G] (written along g)
+    __shared__ int32_t tile[32][33];
+    const int v0 = blockIdx.x * 32, g0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int g = g0 + r, v = v0 + threadIdx.x;
+        tile[r][threadIdx.x] = (g < G && v < V) ? counts[static_cast<size_t>(g) * V + v] : 0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int v = v0 + r, g = g0 + threadIdx.x;
+        if (g >= G || v > V) continue;
+        float s;
+        if (v < V) {
+            s = fast_log_table(alpha * betas[v] + static_cast<float>(tile[threadIdx.x][r]), t.log2_table);
+        } else {
+            s = fast_log_table(alpha * beta0, t.log2_table);
+        }
+        table[static_cast<size_t>(v) * G + g] = s - shift[g];
+    }
+}
+
+// Pitman-Yor prior vector: CachedMixture::init + score_value (clustering.hpp:151-161,195-230)
+__global__ void prior_prep_kernel(float alpha, float d, int G, const int32_t *__restrict__ sizes,
+                                  float *__restrict__ prior, NumericTables t) {
+    __shared__ long long s_total;
+    __shared__ int s_empty;
+    if (threadIdx.x == 0) {
+        s_total = 0;
+        s_empty = 0;
+    }
+    __syncthreads();
+    long long total = 0;
+    int empty = 0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        total += sizes[g];
+        empty += (sizes[g] == 0);
+    }
+    atomicAdd(reinterpret_cast<unsigned long long *>(&s_total), static_cast<unsigned long long>(total));
+    atomicAdd(&s_empty, empty);
+    __syncthreads();
+    const int nonempty = G - s_empty;
+    const float numer = alpha + d * static_cast<float>(nonempty);
+    const float denom = static_cast<float>(s_empty);
+    const float empty_score = fast_log_table(numer / denom, t.log2_table);
+    const float shift = -fast_log_table(static_cast<float>(s_total) + alpha, t.log2_table);
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const float shifted =
+            sizes[g] ? fast_log_table(static_cast<float>(sizes[g]) - d, t.log2_table) : empty_score;
+        prior[g] = shifted + shift;
+    }
+}
+
+// numerics probe (dist_b200_numerics_probe)
+__global__ void numerics_probe_kernel(int fn, size_t n, const float *__restrict__ in, float *__restrict__ out,
+                                      NumericTables t) {
+    __shared__ __align__(16) float coeff[33 * kLgammaRowStride];
+    for (int i = threadIdx.x; i < 33 * kLgammaRowStride; i += blockDim.x) coeff[i] = t.lgamma5[i];
+    __syncthreads();
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = in[i];
+    float y = 0.f;
+    switch (fn) {
+        case 0: y = fast_log_table(x, t.log2_table); break;
+        case 1: y = fast_exp_neg(x); break;
+        case 2: y = fast_lgamma_cell(x, coeff); break;
+        case 3: y = fast_lgamma_nu(x, t.lgamma_nu3); break;
+        case 4: y = fast_log_factorial(__float_as_uint(x), t.log_factorial, t.lgamma5); break;
+        case 5: y = fast_log_cell(x); break;
+        case 6: y = fast_lgamma_exact(x, t.lgamma5); break;
+    }
+    out[i] = y;
+}
+
+// hot layout -> the reference's struct-of-arrays cache layout (dist_b200_feature_download_caches)
+__global__ void unpack_float4_kernel(int model, int G, const float4 *__restrict__ params, float *__restrict__ out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const float4 p = params[g];
+    if (model == DIST_B200_NICH) {  // score_, log_coeff_, precision_, mean_
+        out[0 * G + g] = p.w;
+        out[1 * G + g] = p.z;
+        out[2 * G + g] = p.y;
+        out[3 * G + g] = p.x;
+    } else if (model == DIST_B200_GP) {  // score_, post_alpha_, score_coeff_
+        out[0 * G + g] = p.z;
+        out[1 * G + g] = p.x;
+        out[2 * G + g] = p.y;
+    } else {  // bb: heads_scores_, tails_scores_
+        out[0 * G + g] = p.x;
+        out[1 * G + g] = p.y;
+    }
+}
+
+__global__ void transpose_table_kernel(int G, int dim, const float *__restrict__ table_gv, float *__restrict__ out_vg) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    for (int v = 0; v < dim; ++v) out_vg[static_cast<size_t>(v) * G + g] = table_gv[static_cast<size_t>(g) * dim + v];
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline int blocks_for(size_t n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
+
+#define LAUNCH_CHECK(ctx)                                                                     \
+    do {                                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess)                                                               \
+            return fail((ctx), DIST_B200_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e__)); \
+    } while (0)
+
+int launch_nich_prep(dist_b200_ctx *ctx, const float sh[4], int G, int g0, int n, const int32_t *count,
+                     const float *mean, const float *ctv, float4 *params, cudaStream_t s) {
+    (void)G;
+    if (n <= 0) return DIST_B200_OK;
+    nich_prep_kernel<<<blocks_for(n, 128), 128, 0, s>>>(sh[0], sh[1], sh[2], sh[3], g0, n, count, mean, ctv,
+                                                        params, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+int launch_gp_prep(dist_b200_ctx *ctx, const float sh[2], int g0, int n, const uint32_t *count,
+                   const uint32_t *sum, float4 *params, cudaStream_t s) {
+    if (n <= 0) return DIST_B200_OK;
+    gp_prep_kernel<<<blocks_for(n, 128), 128, 0, s>>>(sh[0], sh[1], g0, n, count, sum, params, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+int launch_bb_prep(dist_b200_ctx *ctx, const float sh[2], int g0, int n, const int32_t *heads,
+                   const int32_t *tails, float4 *params, cudaStream_t s) {
+    if (n <= 0) return DIST_B200_OK;
+    bb_prep_kernel<<<blocks_for(n, 128), 128, 0, s>>>(sh[0], sh[1], g0, n, heads, tails, params, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+int launch_dd_prep(dist_b200_ctx *ctx, int dim, const float *alphas, float alpha_sum, int g0, int n,
+                   const int32_t *counts, float *table, cudaStream_t s) {
+    if (n <= 0) return DIST_B200_OK;
+    dd_prep_kernel<<<blocks_for(n, 128), 128, 0, s>>>(dim, alphas, alpha_sum, g0, n, counts, table,
+                                                      static_cast<size_t>(dim), 1, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+int launch_dpd_prep(dist_b200_ctx *ctx, float alpha, float beta0, int V, const float *betas, int G,
+                    const int32_t *counts, float *table, cudaStream_t s) {
+    if (G <= 0) return DIST_B200_OK;
+    // shift lives in the tail of the table allocation: rows [0, V] are the table, row V+1 is shift
+    float *shift = table + static_cast<size_t>(V + 1) * G;
+    dpd_shift_kernel<<<blocks_for(static_cast<size_t>(G) * 32, 256), 256, 0, s>>>(alpha, V, G, counts, shift,
+                                                                                 ctx->tables);
+    LAUNCH_CHECK(ctx);
+    dim3 grid((V + 1 + 31) / 32, (G + 31) / 32), block(32, 8);
+    dpd_table_kernel<<<grid, block, 0, s>>>(alpha, beta0, V, betas, G, counts, shift, table, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+int launch_prior_prep(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *sizes, float *prior,
+                      cudaStream_t s) {
+    prior_prep_kernel<<<1, 1024, 0, s>>>(alpha, d, G, sizes, prior, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+int launch_numerics_probe(dist_b200_ctx *ctx, int fn, size_t n, const float *in, float *out, cudaStream_t s) {
+    if (n == 0) return DIST_B200_OK;
+    numerics_probe_kernel<<<blocks_for(n, 256), 256, 0, s>>>(fn, n, in, out, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+int launch_unpack_caches(dist_b200_ctx *ctx, const dist_b200_feature *f, float *out, cudaStream_t s) {
+    const int G = f->G;
+    if (G <= 0) return DIST_B200_OK;
+    switch (f->model) {
+        case DIST_B200_NICH:
+        case DIST_B200_GP:
+        case DIST_B200_BB:
+            unpack_float4_kernel<<<blocks_for(G, 128), 128, 0, s>>>(f->model, G,
+                                                                    static_cast<const float4 *>(f->params), out);
+            break;
+        case DIST_B200_DD:
+            transpose_table_kernel<<<blocks_for(G, 128), 128, 0, s>>>(G, f->dim, static_cast<const float *>(f->params),
+                                                                      out);
+            break;
+        case DIST_B200_DPD: {
+            cudaError_t e = cudaMemcpyAsync(out, f->params, sizeof(float) * static_cast<size_t>(f->dim + 1) * G,
+                                            cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, cudaGetErrorString(e));
+        } break;
+        default:
+            return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "download_caches: model has no flat cache layout");
+    }
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+}  // namespace distb200

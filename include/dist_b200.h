@@ -1,0 +1,185 @@
+/* dist_b200.h -- C-ABI of the B200-native mixture-scoring hot path.
+ *
+ * Drop-in boundary for ONE path of forcedotcom/distributions (reference paths are relative to
+ * /root/reference): batched `Mixture::score_value` for every row against every group of the
+ * conjugate component models, plus the clustering prior's group-size term, followed by
+ * `sample_from_scores`.  The reference has no FFI of its own for this path: the
+ * seam is the C++ template contract `MixtureSlave<Model, DataScorer, ValueScorer>`
+ * (include/distributions/mixture.hpp:340-450) and its Cython mirror
+ * (distributions/lp/models/_nich.pyx:85-138).  Each entry point below names the reference
+ * interface it replaces; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every call returns a dist_b200_status (0 = ok) and never aborts or
+ *     throws across the boundary (the reference aborts / throws: common.hpp:49-67).
+ *   - `*_dev` pointers are CUDA device pointers on the context's device, `*_host` / unmarked
+ *     statistics pointers are host pointers.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream).  Calls taking a stream are asynchronous on it unless
+ *     they return data to the host.
+ *   - a "feature" is the device-side MixtureValueScorer of one Model::Mixture: the per-group
+ *     caches of one feature column for G groups.  Features that share a partition (one cross-cat
+ *     "kind") are scored together: scores[n][g] = prior[g] + sum_f score_f(x[n][f]; group g).
+ *   - there is NO CPU fallback: every scoring / sampling entry launches sm_100a kernels.
+ */
+#ifndef DIST_B200_H_
+#define DIST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIST_B200_ABI_VERSION 1
+
+typedef enum {
+    DIST_B200_OK = 0,
+    DIST_B200_ERR_INVALID = 1,     /* bad argument (null, size, range) */
+    DIST_B200_ERR_CUDA = 2,        /* a CUDA runtime call failed; see dist_b200_last_error */
+    DIST_B200_ERR_UNSUPPORTED = 3, /* valid request outside what this build implements */
+    DIST_B200_ERR_STATE = 4        /* feature not initialised / G mismatch between features */
+} dist_b200_status;
+
+/* component models, include/distributions/models/{dd,dpd,bb,gp,nich,niw}.hpp */
+typedef enum {
+    DIST_B200_DD = 0,   /* DirichletDiscrete<max_dim>   value: int32   */
+    DIST_B200_DPD = 1,  /* DirichletProcessDiscrete     value: uint32 (0xFFFFFFFF = OTHER, dpd.hpp:55) */
+    DIST_B200_BB = 2,   /* BetaBernoulli                value: uint8 (0 / non-0) */
+    DIST_B200_GP = 3,   /* GammaPoisson                 value: uint32  */
+    DIST_B200_NICH = 4, /* NormalInverseChiSq           value: float   */
+    DIST_B200_NIW = 5   /* NormalInverseWishart<d>      value: float[d], rows contiguous */
+} dist_b200_model;
+
+typedef struct dist_b200_ctx dist_b200_ctx;
+typedef struct dist_b200_feature dist_b200_feature;
+
+/* ---- context --------------------------------------------------------------------------------
+ * Owns the device-side numerics tables that replace src/special.cc's statics (FastLog table
+ * special.cc:35-44, lgamma_approx_coeff5 :144-211, log_factorial_table :213-230,
+ * lgamma_nu_func_approx_coeff3 :232-269) and scratch buffers.  One context per device/thread. */
+int dist_b200_abi_version(void);
+int dist_b200_ctx_create(int device, dist_b200_ctx **out);
+void dist_b200_ctx_destroy(dist_b200_ctx *ctx);
+const char *dist_b200_last_error(const dist_b200_ctx *ctx);
+int dist_b200_sm_count(const dist_b200_ctx *ctx);
+
+/* ---- features: MixtureValueScorer::{resize, update_all, update_group, add_group, remove_group}
+ * All statistics arrays are host pointers holding the reference's Group fields as
+ * struct-of-arrays over the G packed group ids. */
+int dist_b200_feature_create(dist_b200_ctx *ctx, int model, dist_b200_feature **out);
+void dist_b200_feature_destroy(dist_b200_feature *f);
+int dist_b200_feature_model(const dist_b200_feature *f);
+int dist_b200_feature_groups(const dist_b200_feature *f); /* G, 0 before the first update_all */
+
+/* NormalInverseChiSq::MixtureValueScorer::update_all (nich.hpp:344-352 -> Scorer::init :239-250,
+ * Shared::plus_group :58-69).  shared = {mu, kappa, sigmasq, nu}; Group = {count, mean,
+ * count_times_variance} (nich.hpp:98-101). */
+int dist_b200_nich_update_all(dist_b200_feature *f, const float shared[4], int G, const int32_t *count,
+                              const float *mean, const float *count_times_variance, void *stream);
+/* GammaPoisson (gp.hpp:293-301 -> :198-207, :56-61).  shared = {alpha, inv_beta};
+ * Group = {count, sum, log_prod} (gp.hpp:84-87; log_prod does not enter score_value). */
+int dist_b200_gp_update_all(dist_b200_feature *f, const float shared[2], int G, const uint32_t *count,
+                            const uint32_t *sum, void *stream);
+/* BetaBernoulli (bb.hpp:276-292).  shared = {alpha, beta}; Group = {heads, tails} (bb.hpp:79-81). */
+int dist_b200_bb_update_all(dist_b200_feature *f, const float shared[2], int G, const int32_t *heads,
+                            const int32_t *tails, void *stream);
+/* DirichletDiscrete<max_dim> (dd.hpp:399-421).  counts is [G][dim] row-major (Group::counts,
+ * dd.hpp:89-92; count_sum is recomputed). */
+int dist_b200_dd_update_all(dist_b200_feature *f, int dim, const float *alphas, int G,
+                            const int32_t *counts, void *stream);
+/* DirichletProcessDiscrete (dpd.hpp:471-497).  keys[V] are the values present in Shared::betas with
+ * weights betas[V]; counts is [G][V] dense (column v <-> keys[v]); beta0 scores OTHER / unseen
+ * values (dpd.hpp:533-537). */
+int dist_b200_dpd_update_all(dist_b200_feature *f, float alpha, float beta0, int V, const uint32_t *keys,
+                             const float *betas, int G, const int32_t *counts, void *stream);
+/* NormalInverseWishart<d> has no Mixture in the reference; this is the batched form of looping
+ * Group::score_value over groups (mixture.hpp:321-337 semantics; niw.hpp:82-103, :343-361,
+ * random.hpp:160-185).  psi and sum_xxT[g] are [d][d] row-major; Group = {count, sum_x, sum_xxT}
+ * (niw.hpp:187-190). */
+int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float kappa, const float *psi,
+                             float nu, int G, const int32_t *count, const float *sum_x,
+                             const float *sum_xxT, void *stream);
+
+/* MixtureValueScorer::update_group after Group::add_value / remove_value touched one group
+ * (nich.hpp:312-342, gp.hpp:262-291, bb.hpp:258-274, dd.hpp:381-397,458-467).  `stats` points at
+ * that single group's statistics in the same order as the update_all arguments:
+ *   nich {int32 count; float mean; float ctv}   gp {uint32 count; uint32 sum}
+ *   bb {int32 heads; int32 tails}               dd int32 counts[dim]
+ * The hyper-parameters are the ones given to the last update_all. */
+int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void *stats, void *stream);
+/* packed_add of a fresh empty group / packed_remove = swap-with-last (vector.hpp:39-61,
+ * mixture.hpp:361-375) on every per-group device array. */
+int dist_b200_feature_add_group(dist_b200_feature *f, void *stream);
+int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stream);
+
+/* Read the caches back in the reference's own struct-of-arrays layout (for parity tests):
+ *   nich [4][G] score_, log_coeff_, precision_, mean_   (nich.hpp:379-384)
+ *   gp   [3][G] score_, post_alpha_, score_coeff_       (gp.hpp:329-333)
+ *   bb   [2][G] heads_scores_, tails_scores_            (bb.hpp:321-324)
+ *   dd   [dim][G]  score_value_group(g, v) = scores_[v][g] - scores_shift_[g]  (dd.hpp:423-431)
+ *   dpd  [V+1][G]  the same for keys[v], last row = the OTHER / unseen row      (dpd.hpp:499-515)
+ * Synchronises the stream.  *n_floats receives the number of floats written. */
+int dist_b200_feature_download_caches(const dist_b200_feature *f, float *out_host, size_t capacity_floats,
+                                      size_t *n_floats, void *stream);
+
+/* ---- clustering prior: Clustering<int>::PitmanYor::Mixture::{init, score_value}
+ * (clustering.hpp:151-161, :195-230; CRP is d = 0).  Writes prior_dev[g] = shifted_scores_[g] -
+ * fast_log(sample_size + alpha) for g < G from the group sizes (host). */
+int dist_b200_prior_pitman_yor(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *group_sizes,
+                               float *prior_dev, void *stream);
+
+/* ---- the hot path -----------------------------------------------------------------------------
+ * columns_dev[f] is feature f's value column for the N rows, typed per model (see
+ * dist_b200_model); feature-major storage, i.e. one contiguous array per feature.
+ *
+ * dist_b200_score_batch: batched MixtureSlave::score_value (mixture.hpp:416-425).
+ *   accumulate != 0 : scores_dev[n][g] += sum_f ...        (the slave's ACCUMULATE semantic)
+ *   accumulate == 0 : scores_dev[n][g]  = prior_dev[g] + sum_f ... (prior_dev may be NULL = 0;
+ *                     this is clustering's OVERWRITE, clustering.hpp:195-208, followed by the slaves)
+ * scores_dev is [N][G] row-major float32. */
+int dist_b200_score_batch(dist_b200_ctx *ctx, const dist_b200_feature *const *features, int n_features,
+                          const void *const *columns_dev, size_t n_rows, const float *prior_dev,
+                          float *scores_dev, int accumulate, void *stream);
+
+/* dist_b200_score_sample_batch: the whole per-row assignment step of
+ * examples/mixture/main.py:236-244 for N rows against frozen statistics, fused:
+ * prior + features -> sample_from_scores_overwrite (random.hpp:360-366) with the caller's
+ * uniforms u_dev[n] in [0,1) in place of sample_unif01(rng).  assign_dev[n] receives the packed
+ * group id.  scores_dev (optional, may be NULL) also receives the [N][G] log scores. */
+int dist_b200_score_sample_batch(dist_b200_ctx *ctx, const dist_b200_feature *const *features,
+                                 int n_features, const void *const *columns_dev, size_t n_rows,
+                                 const float *prior_dev, const float *u_dev, int32_t *assign_dev,
+                                 float *scores_dev, void *stream);
+
+/* dist_b200_sample_from_scores: sample_from_scores (random.hpp:386-392; scores are not
+ * overwritten) for N rows of G materialised scores, e.g. after the feature-shard reduction. */
+int dist_b200_sample_from_scores(dist_b200_ctx *ctx, const float *scores_dev, size_t n_rows, int G,
+                                 const float *u_dev, int32_t *assign_dev, void *stream);
+
+/* ---- host-buffer forms: the call a reference-side binding makes.  Same
+ * semantics with HOST pointers; inputs are staged through pinned memory, copied to the device,
+ * scored there, and results copied back before returning. */
+int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_feature *const *features,
+                                      int n_features, const void *const *columns_host, size_t n_rows,
+                                      const float *prior_host, const float *u_host, int32_t *assign_host,
+                                      float *scores_host);
+/* per-value MixtureSlave::score_value (mixture.hpp:416-425): scores_accum_host[G] += model term. */
+int dist_b200_score_value_host(dist_b200_ctx *ctx, const dist_b200_feature *feature, const void *value_host,
+                               float *scores_accum_host);
+
+/* ---- numerics probes (parity tests of the device functions against special.hpp / fmath.hpp).
+ * fn: 0 fast_log (table form, as used by the cache rebuilds)   1 fast_exp (sampler form)
+ *     2 fast_lgamma   3 fast_lgamma_nu   4 fast_log_factorial (input bits as uint32)
+ *     5 fast_log (per-cell form: truncated mantissa + MUFU.LG2) */
+int dist_b200_numerics_probe(dist_b200_ctx *ctx, int fn, size_t n, const float *in_dev, float *out_dev,
+                             void *stream);
+
+/* Register-only pipe probes for roofline denominators that MEASURED_PEAKS.json does not carry:
+ * which = 0: MUFU (ex2/lg2) lane-ops per second, 1: FP32 FMA lane-ops per second, whole device. */
+int dist_b200_pipe_peak(dist_b200_ctx *ctx, int which, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIST_B200_H_ */

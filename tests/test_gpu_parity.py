@@ -1,0 +1,421 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the oracle restatement on the
+same seeded inputs, against the committed golden vectors of the compiled reference, and -- where
+oracle/_ref travelled to the box -- against the live unmodified reference.
+
+Stated tolerances (see tests/test_oracle.py for the measured origins):
+  scores  |cuda - oracle| <= 3e-6 * (1 + |ref|) + model envelope, where the envelope is
+          nich: 1e-6 * |log_coeff[g]|  (MUFU.LG2 vs the table entry: <= 2^-22 in log2)
+          gp  : 6e-7 * (1 + |score[g]|) (fp32 cancellation of score[g] + lgamma(post_alpha+v))
+          dd / dpd / bb: none (table gathers are bit-exact: tolerance 0)
+  vs the compiled reference add LOG_STEP * |log_coeff[g]| for nich (fast_log is a step function; the
+  -ffast-math build may evaluate its argument one ulp away).
+  assignments: identical to the oracle's for the same uniforms except near-ties, i.e. rows where
+          u * total lies within eps * total of a CDF boundary between the two indices, eps = 2e-5
+          (fast_exp's build envelope 5e-6 + summation order); the mismatch rate is also bounded.
+"""
+import numpy as np
+import pytest
+
+import cases
+from distributions_b200 import synth
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+LOG_STEP = 6.2e-5
+EPS_TIE = 2e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from distributions_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def model_id(name):
+    from distributions_b200 import capi
+    return {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH}[name]
+
+
+def envelope(oracle, w):
+    G = w["sizes"].size
+    if w["model"] == "nich":
+        return 1e-6 * np.abs(oracle.nich_caches(w["shared"], w["count"], w["mean"], w["ctv"])[1])
+    if w["model"] == "gp":
+        return 6e-7 * (1.0 + np.abs(oracle.gp_caches(w["shared"], w["count"], w["sum"])[0]))
+    return np.zeros(G)
+
+
+def run_cuda(ctx, feats_w, prior, u, n, want_scores=True, sample=True):
+    """score (+sample) the first n rows of the workloads through the device-pointer C-ABI."""
+    feats = [ctx.feature(model_id(w["model"])).update_all(w) for w in feats_w]
+    cols = [dev(w["values"][:n].astype(__import__("distributions_b200.capi", fromlist=["x"]).COLUMN_DTYPE[model_id(w["model"])])) for w in feats_w]
+    G = feats_w[0]["sizes"].size
+    prior_d = dev(prior.astype(np.float32)) if prior is not None else None
+    scores_d = torch.full((n, G), 777.0, device="cuda", dtype=torch.float32) if want_scores else None
+    if sample:
+        u_d = dev(u[:n].astype(np.float32))
+        assign_d = torch.full((n,), -5, device="cuda", dtype=torch.int32)
+        ctx.score_sample_batch(feats, cols, n, prior_d, u_d, assign_d, scores_d)
+        torch.cuda.synchronize()
+        return assign_d.cpu().numpy(), (scores_d.cpu().numpy() if want_scores else None)
+    ctx.score_batch(feats, cols, n, prior_d, scores_d)
+    torch.cuda.synchronize()
+    return None, scores_d.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------ numerics
+def test_numerics_device_functions(ctx, oracle):
+    sweeps = {
+        0: np.concatenate([np.logspace(-37, 38, 200001), -np.logspace(-5, 5, 1001), [0.0, np.inf]]),
+        2: np.logspace(-3, 9.6, 200001),
+        3: np.logspace(-3, 9.6, 200001),
+        5: np.concatenate([np.logspace(0, 30, 200001), 1 + np.logspace(-7, 0, 50001)]),
+        6: np.logspace(-3, 9.6, 200001),
+    }
+    tol = {0: 0.0, 2: 1e-6, 3: 2e-6, 5: 5e-7, 6: 1e-6}
+    orc_fn = {0: 0, 2: 2, 3: 3, 5: 0, 6: 2}
+    for fn, x in sweeps.items():
+        x = x.astype(np.float32)
+        xd = dev(x)
+        out = torch.empty_like(xd)
+        ctx.numerics_probe(fn, xd, out, x.size)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().astype(np.float64)
+        want = oracle.vec(orc_fn[fn], x).astype(np.float64)
+        err = np.abs(got - want) / (1 + np.abs(want))
+        err = np.where(got == want, 0.0, err)
+        assert err.max() <= tol[fn], (fn, err.max(), x[np.argmax(err)])
+    # fast_exp on the sampler's domain: relative to the restated fmath::exp
+    x = np.linspace(-87.0, 0.0, 200001).astype(np.float32)
+    xd = dev(x)
+    out = torch.empty_like(xd)
+    ctx.numerics_probe(1, xd, out, x.size)
+    got = out.cpu().numpy().astype(np.float64)
+    want = oracle.fast_exp(x).astype(np.float64)
+    assert np.max(np.abs(got - want) / want) <= 2e-6
+    # log factorial
+    n = np.concatenate([np.arange(0, 300), [1000, 65535, 1 << 20]]).astype(np.uint32)
+    xd = dev(n.view(np.float32))
+    out = torch.empty_like(xd)
+    ctx.numerics_probe(4, xd, out, n.size)
+    np.testing.assert_allclose(out.cpu().numpy(), oracle.fast_log_factorial(n), rtol=1e-6)
+
+
+def test_prior(ctx, oracle, golden):
+    for j in range(5):
+        for empties in (1, 10):
+            key = "prior_%d_%d" % (j, empties)
+            sizes = golden[key + "_sizes"]
+            alpha, d = [float(v) for v in golden[key + "_alpha_d"]]
+            out = torch.zeros(sizes.size, device="cuda")
+            ctx.prior_pitman_yor(alpha, d, sizes, out)
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+            assert np.array_equal(got, oracle.py_prior(alpha, d, sizes))  # same table, same op order
+            np.testing.assert_allclose(got, golden[key + "_out"], atol=2e-6, rtol=0)
+
+
+CACHE_ROWS = {"nich": 4, "gp": 3, "bb": 2}
+
+
+@pytest.mark.parametrize("name", list(cases.SMALL))
+def test_caches(ctx, oracle, golden, name):
+    w = cases.make(name, **cases.SMALL[name])
+    f = ctx.feature(model_id(name)).update_all(w)
+    want = cases.oracle_caches(oracle, w)
+    if name in CACHE_ROWS:
+        got = f.download_caches(CACHE_ROWS[name])
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(got, golden["%s_caches" % name], rtol=3e-6, atol=3e-6)
+    elif name == "dd":
+        got = f.download_caches(w["alphas"].size)          # score_value_group table [dim][G]
+        assert np.array_equal(got, want[:-1] - want[-1][None, :])
+    else:
+        got = f.download_caches(w["keys"].size + 1)        # [V+1][G], last row = OTHER
+        assert np.array_equal(got, want[:-1] - want[-1][None, :])
+
+
+# ------------------------------------------------------------------------------ single features
+@pytest.mark.parametrize("name", list(cases.SMALL))
+def test_single_feature_golden_and_oracle(ctx, oracle, golden, name):
+    cfg = cases.SMALL[name]
+    w = cases.make(name, **cfg)
+    n = cfg["N"]
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    u = golden["%s_u" % name]
+    assign, scores = run_cuda(ctx, [w], prior, u, n)
+    want = cases.oracle_scores(oracle, [w], prior=prior)
+    env = envelope(oracle, w)[None, :]
+    if name in ("dd", "dpd", "bb"):
+        assert np.array_equal(scores, want)
+    else:
+        assert np.all(np.abs(scores - want) <= 3e-6 * (1 + np.abs(want)) + env)
+    # against the compiled reference's outputs
+    ref_scores = golden["%s_scores" % name]
+    step = LOG_STEP * np.abs(oracle.nich_caches(w["shared"], w["count"], w["mean"], w["ctv"])[1])[None, :] if name == "nich" else 0.0
+    assert np.all(np.abs(scores - ref_scores) <= 4e-6 * (1 + np.abs(ref_scores)) + env + step)
+    # assignments: vs the oracle sampler on the CUDA scores, and vs the reference's indices
+    a_orc = oracle.sample_rows(scores.copy(), u)
+    assert cases.explained_mismatch(scores.astype(np.float64), u, assign, a_orc, EPS_TIE).all()
+    a_ref = golden["%s_assign" % name]
+    ok = cases.explained_mismatch(ref_scores.astype(np.float64), u, assign, a_ref, 2e-3 if name == "nich" else EPS_TIE)
+    assert ok.all()
+    assert np.mean(assign == a_ref) > 0.95
+    # fused (no materialised scores) gives the same indices as the materialising launch
+    assign2, _ = run_cuda(ctx, [w], prior, u, n, want_scores=False)
+    assert np.array_equal(assign, assign2)
+
+
+@pytest.mark.parametrize("name", list(cases.SMALL))
+def test_accumulate_semantic(ctx, oracle, golden, name):
+    """Mixture.score_value ADDS into the buffer (reference test_models.py:552-557)."""
+    from distributions_b200 import capi
+    w = cases.make(name, **cases.SMALL[name])
+    noise = golden["%s_noise" % name]
+    f = ctx.feature(model_id(name)).update_all(w)
+    col = dev(w["values"][:8].astype(capi.COLUMN_DTYPE[model_id(name)]))
+    sc = dev(noise)
+    ctx.score_batch([f], [col], 8, None, sc, accumulate=True)
+    torch.cuda.synchronize()
+    got = sc.cpu().numpy()
+    want = golden["%s_accum" % name]
+    env = envelope(oracle, w)[None, :]
+    step = LOG_STEP * np.abs(oracle.nich_caches(w["shared"], w["count"], w["mean"], w["ctv"])[1])[None, :] if name == "nich" else 0.0
+    assert np.all(np.abs(got - want) <= 4e-6 * (1 + np.abs(want)) + env + step)
+    # == per-group Group::score_value at the reference's own tolerance
+    row0 = got[0] - noise[0]
+    gs = golden["%s_group_scores" % name]
+    assert np.all(np.abs(row0 - gs) <= 1e-3 * (1 + np.abs(row0) + np.abs(gs)))
+    # per-value host entry (MixtureSlave::score_value drop-in)
+    acc = noise[0].copy()
+    ctx.score_value_host(f, w["values"][:1], acc)
+    np.testing.assert_array_equal(acc, got[0])
+
+
+@pytest.mark.parametrize("G", [1, 2, 31, 32, 33, 64, 100, 128, 129, 257, 1000])
+@pytest.mark.parametrize("name", ["nich", "gp", "bb", "dd"])
+def test_group_count_tiers(ctx, oracle, name, G):
+    """ragged group counts across every register-tile / multi-chunk tier, ragged row counts"""
+    n = 517
+    w = cases.make(name, seed=1000 + G, G=G, N=n)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    assign, scores = run_cuda(ctx, [w], prior, w["u"], n)
+    want = cases.oracle_scores(oracle, [w], prior=prior)
+    env = envelope(oracle, w)[None, :]
+    assert np.all(np.abs(scores - want) <= 3e-6 * (1 + np.abs(want)) + env)
+    a_orc = oracle.sample_rows(scores.copy(), w["u"])
+    assert cases.explained_mismatch(scores.astype(np.float64), w["u"], assign, a_orc, EPS_TIE).all()
+    assert np.mean(assign == a_orc) > 0.98
+    assign2, _ = run_cuda(ctx, [w], prior, w["u"], n, want_scores=False)
+    assert np.array_equal(assign, assign2)
+    assert assign.min() >= 0 and assign.max() < G
+
+
+@pytest.mark.parametrize("G,V", [(19, 100), (512, 4096), (77, 1000)])
+def test_dpd_tiers(ctx, oracle, G, V):
+    n = 1031
+    w = synth.dpd(2000 + G, G, n, V=V, other_frac=0.05)
+    if V == 1000:  # sparse, shuffled keys: device-side key search
+        rng = np.random.default_rng(1)
+        keys = rng.choice(1 << 20, V, replace=False).astype(np.uint32)
+        known = w["values"] != 0xFFFFFFFF
+        w["values"][known] = keys[w["values"][known]]
+        w["keys"] = keys
+        w["values"][:5] = [3, 5, 7, 11, 13][:5]  # (almost surely) unknown values -> the OTHER row
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    assign, scores = run_cuda(ctx, [w], prior, w["u"], n)
+    want = cases.oracle_scores(oracle, [w], prior=prior)
+    assert np.array_equal(scores, want)
+    a_orc = oracle.sample_rows(scores.copy(), w["u"])
+    assert cases.explained_mismatch(scores.astype(np.float64), w["u"], assign, a_orc, EPS_TIE).all()
+    assign2, _ = run_cuda(ctx, [w], prior, w["u"], n, want_scores=False)
+    assert np.array_equal(assign, assign2)
+
+
+# ------------------------------------------------------------------------------------ cross-cat
+def _crosscat_small():
+    G, N = 17, 64
+    cc = synth.crosscat(201, G, N, n_gp=3, n_bb=3)
+    extra = []
+    for f in range(2):
+        w = synth.nich(300 + f, G, N)
+        w["count"] = cc["sizes"].copy()
+        w["mean"][cc["sizes"] == 0] = 0
+        w["ctv"][cc["sizes"] == 0] = 0
+        extra.append(w)
+    return cc, cc["features"] + extra
+
+
+def test_crosscat_golden(ctx, oracle, golden):
+    cc, feats = _crosscat_small()
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, cc["sizes"])
+    u = golden["crosscat_u"]
+    assign, scores = run_cuda(ctx, feats, prior, u, 64)
+    want = cases.oracle_scores(oracle, feats, prior=prior)
+    env = sum(envelope(oracle, w) for w in feats)[None, :]
+    assert np.all(np.abs(scores - want) <= 4e-6 * (1 + np.abs(want)) + env)
+    ref_scores = golden["crosscat_scores"]
+    step = sum(LOG_STEP * np.abs(oracle.nich_caches(w["shared"], w["count"], w["mean"], w["ctv"])[1]) for w in feats[-2:])[None, :]
+    assert np.all(np.abs(scores - ref_scores) <= 5e-6 * (1 + np.abs(ref_scores)) + env + step)
+    a_orc = oracle.sample_rows(scores.copy(), u)
+    assert cases.explained_mismatch(scores.astype(np.float64), u, assign, a_orc, EPS_TIE).all()
+
+
+@pytest.mark.parametrize("G,F", [(128, 24), (200, 10)])
+def test_crosscat_streaming(ctx, oracle, G, F):
+    """enough features that the group caches do not fit in shared memory (double-buffered staging)"""
+    n = 700
+    cc = synth.crosscat(500 + G, G, n, n_gp=F // 2, n_bb=F // 2)
+    feats = cc["features"]
+    # widen the caches with dd features so the resident budget is exceeded
+    for k in range(6):
+        w = synth.dd(900 + k, G, n, dim=32)
+        feats.append(w)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, cc["sizes"])
+    assign, scores = run_cuda(ctx, feats, prior, cc["u"], n)
+    want = cases.oracle_scores(oracle, feats, prior=prior)
+    env = sum(envelope(oracle, w) for w in feats)[None, :]
+    assert np.all(np.abs(scores - want) <= 5e-6 * (1 + np.abs(want)) + env)
+    a_orc = oracle.sample_rows(scores.copy(), cc["u"])
+    assert cases.explained_mismatch(scores.astype(np.float64), cc["u"], assign, a_orc, EPS_TIE).all()
+    assign2, _ = run_cuda(ctx, feats, prior, cc["u"], n, want_scores=False)
+    assert np.array_equal(assign, assign2)
+
+
+def test_mixed_dpd_and_rows(ctx, oracle):
+    """a dpd feature next to row-mapped features: materialise + accumulate + stand-alone sampler"""
+    G, n = 40, 333
+    w1 = synth.nich(71, G, n)
+    w2 = synth.dpd(72, G, n, V=64, other_frac=0.1)
+    w2["sizes"] = w1["sizes"]
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w1["sizes"])
+    assign, scores = run_cuda(ctx, [w1, w2], prior, w1["u"], n)
+    want = cases.oracle_scores(oracle, [w1, w2], prior=prior)
+    assert np.all(np.abs(scores - want) <= 4e-6 * (1 + np.abs(want)) + envelope(oracle, w1)[None, :])
+    a_orc = oracle.sample_rows(scores.copy(), w1["u"])
+    assert cases.explained_mismatch(scores.astype(np.float64), w1["u"], assign, a_orc, EPS_TIE).all()
+
+
+# -------------------------------------------------------------------------------------- sampler
+@pytest.mark.parametrize("G", [1, 2, 5, 100, 1024])
+def test_sampler_golden(ctx, golden, G):
+    s = golden["sampler_%d_scores" % G]
+    u = golden["sampler_%d_u" % G]
+    want = golden["sampler_%d_assign" % G]
+    out = torch.full((s.shape[0],), -1, device="cuda", dtype=torch.int32)
+    ctx.sample_from_scores(dev(s), s.shape[0], G, dev(u), out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert cases.explained_mismatch(s.astype(np.float64), u, got, want, EPS_TIE).all()
+    assert np.mean(got == want) >= 0.95
+
+
+def test_sampler_large_vs_oracle_and_distribution(ctx, oracle):
+    rng = np.random.default_rng(9)
+    n, G = 200000, 333
+    s = (rng.standard_normal((n, G)) * 2).astype(np.float32)
+    s[:, :] = s[:1000].repeat(200, axis=0)  # 1000 distinct rows x 200 draws each
+    u = rng.random(n, dtype=np.float32)
+    out = torch.empty(n, device="cuda", dtype=torch.int32)
+    ctx.sample_from_scores(dev(s), n, G, dev(u), out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    want = oracle.sample_rows(s.copy(), u)
+    assert cases.explained_mismatch(s.astype(np.float64), u, got, want, EPS_TIE).all()
+    assert np.mean(got != want) < 2e-4
+    # the draws follow softmax(scores): chi-square style check on one row's 200 draws pooled over rows
+    p = np.exp(s[:1000].astype(np.float64) - s[:1000].max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    hits = np.zeros(1000)
+    for r in range(1000):
+        hits[r] = p[r, got[r * 200:(r + 1) * 200]].mean()
+    assert abs(hits.mean() - (p ** 2).sum(1).mean()) < 5e-3
+
+
+# ----------------------------------------------------------------------------------- properties
+def test_full_size_properties_nich(ctx, oracle):
+    """BASELINE config 2 at full size (1M rows x 1024 groups): size-independent properties --
+    indices in range; a shifted prior (+c on every group) leaves every index unchanged; rows with a
+    dominant group pick it; a spot-check block against the oracle."""
+    from distributions_b200 import capi
+    G, n = 1024, 1_000_000
+    w = synth.nich(20242, G, n)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    f = ctx.feature(capi.NICH).update_all(w)
+    col, u_d = dev(w["values"]), dev(w["u"])
+    a1 = torch.empty(n, device="cuda", dtype=torch.int32)
+    a2 = torch.empty(n, device="cuda", dtype=torch.int32)
+    ctx.score_sample_batch([f], [col], n, dev(prior), u_d, a1)
+    ctx.score_sample_batch([f], [col], n, dev(prior + np.float32(0.5)), u_d, a2)
+    torch.cuda.synchronize()
+    a1, a2 = a1.cpu().numpy(), a2.cpu().numpy()
+    assert a1.min() >= 0 and a1.max() < G
+    assert np.mean(a1 != a2) < 1e-4  # softmax shift invariance (up to rounding near-ties)
+    blk = slice(500000, 500000 + 2048)
+    sc = cases.oracle_scores(oracle, [dict(w, values=w["values"][blk])], prior=prior)
+    want = oracle.sample_rows(sc.copy(), w["u"][blk])
+    ok = cases.explained_mismatch(sc.astype(np.float64), w["u"][blk], a1[blk], want, 1e-4)
+    assert ok.all()
+    assert np.mean(a1[blk] == want) > 0.99
+
+
+def test_host_entry(ctx, oracle):
+    n, G = 3000, 50
+    w = synth.nich(5, G, n)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    from distributions_b200 import capi
+    f = ctx.feature(capi.NICH).update_all(w)
+    assign, scores = ctx.score_sample_batch_host([f], [w["values"]], prior, w["u"], want_scores=True)
+    a_dev, s_dev = run_cuda(ctx, [w], prior, w["u"], n)
+    assert np.array_equal(assign, a_dev) and np.array_equal(scores, s_dev)
+
+
+def test_update_group_add_remove_group(ctx, oracle):
+    """update_group / add_group / remove_group keep the device caches equal to a fresh update_all
+    (MixtureSlave::add_value / add_group / remove_group choreography, mixture.hpp:361-398)."""
+    from distributions_b200 import capi
+    G = 9
+    w = synth.nich(11, G, 10)
+    f = ctx.feature(capi.NICH).update_all(w)
+    # mutate group 3 on the host (Group::add_value restated in the oracle), refresh just that group
+    c, m, v = oracle.nich_group_update(+1, int(w["count"][3]), float(w["mean"][3]), float(w["ctv"][3]), [1.25, -0.5])
+    rec = np.zeros(1, dtype=[("c", np.int32), ("m", np.float32), ("v", np.float32)])
+    rec[0] = (c, m, v)
+    f.update_group(3, rec)
+    w2 = dict(w, count=w["count"].copy(), mean=w["mean"].copy(), ctv=w["ctv"].copy())
+    w2["count"][3], w2["mean"][3], w2["ctv"][3] = c, m, v
+    want = oracle.nich_caches(w2["shared"], w2["count"], w2["mean"], w2["ctv"])
+    np.testing.assert_allclose(f.download_caches(4), want, rtol=2e-6, atol=2e-6)
+    # add an empty group, then remove group 2 (swap-with-last)
+    f.add_group()
+    assert f.groups == G + 1
+    w3 = dict(w2, count=np.append(w2["count"], 0).astype(np.int32), mean=np.append(w2["mean"], 0).astype(np.float32),
+              ctv=np.append(w2["ctv"], 0).astype(np.float32))
+    np.testing.assert_allclose(f.download_caches(4), oracle.nich_caches(w3["shared"], w3["count"], w3["mean"], w3["ctv"]), rtol=2e-6, atol=2e-6)
+    f.remove_group(2)
+    assert f.groups == G
+    for k in ("count", "mean", "ctv"):
+        a = w3[k].copy()
+        a[2] = a[-1]
+        w3[k] = a[:-1]
+    np.testing.assert_allclose(f.download_caches(4), oracle.nich_caches(w3["shared"], w3["count"], w3["mean"], w3["ctv"]), rtol=2e-6, atol=2e-6)
+
+
+def test_error_codes(ctx):
+    from distributions_b200 import capi
+    f = ctx.feature(capi.NICH)
+    with pytest.raises(capi.DistB200Error):  # no update_all yet -> ERR_STATE, not a crash
+        ctx.score_batch([f], [torch.zeros(4, device="cuda")], 4, None, torch.zeros(4, device="cuda"))
+    w1, w2 = synth.nich(1, 5, 4), synth.nich(2, 6, 4)
+    f1, f2 = ctx.feature(capi.NICH).update_all(w1), ctx.feature(capi.NICH).update_all(w2)
+    with pytest.raises(capi.DistB200Error):  # features disagree on G
+        ctx.score_batch([f1, f2], [dev(w1["values"]), dev(w2["values"])], 4, None, torch.zeros(4 * 5, device="cuda"))
