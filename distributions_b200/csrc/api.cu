@@ -78,6 +78,16 @@ int ensure_params(dist_b200_feature *f, int G, bool keep) {
     f->params = fresh;
     f->params_bytes = want;
     f->capacity = f->model == DIST_B200_DPD ? G : static_cast<int>(want / (sizeof(float) * group_floats(f)));
+    if (f->model == DIST_B200_NICH) {
+        float *aux = nullptr;
+        DISTB200_CUDA(ctx, cudaMalloc(&aux, sizeof(float) * f->capacity));
+        DISTB200_CUDA(ctx, cudaMemset(aux, 0, sizeof(float) * f->capacity));
+        if (f->aux) {
+            if (keep) DISTB200_CUDA(ctx, cudaMemcpy(aux, f->aux, sizeof(float) * std::min(f->capacity, f->G), cudaMemcpyDeviceToDevice));
+            DISTB200_CUDA(ctx, cudaFree(f->aux));
+        }
+        f->aux = aux;
+    }
     return DIST_B200_OK;
 }
 
@@ -181,6 +191,7 @@ void dist_b200_feature_destroy(dist_b200_feature *f) {
     if (!f) return;
     cudaDeviceSynchronize();
     if (f->params) cudaFree(f->params);
+    if (f->aux) cudaFree(f->aux);
     if (f->keys_dev) cudaFree(f->keys_dev);
     if (f->key_rows_dev) cudaFree(f->key_rows_dev);
     if (f->niw_buf) cudaFree(f->niw_buf);
@@ -204,7 +215,7 @@ int dist_b200_nich_update_all(dist_b200_feature *f, const float shared[4], int G
     const float *v = up.put(ctv, G);
     if (up.err) return up.err;
     f->G = G;
-    return launch_nich_prep(ctx, f->shared, G, 0, G, c, m, v, static_cast<float4 *>(f->params), as_stream(stream));
+    return launch_nich_prep(ctx, f->shared, G, 0, G, c, m, v, static_cast<float4 *>(f->params), f->aux, as_stream(stream));
 }
 
 int dist_b200_gp_update_all(dist_b200_feature *f, const float shared[2], int G, const uint32_t *count,
@@ -339,7 +350,7 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             const float *m = up.put(reinterpret_cast<const float *>(p + 4), 1);
             const float *v = up.put(reinterpret_cast<const float *>(p + 8), 1);
             if (up.err) return up.err;
-            return launch_nich_prep(ctx, f->shared, f->G, groupid, 1, c, m, v, static_cast<float4 *>(f->params), s);
+            return launch_nich_prep(ctx, f->shared, f->G, groupid, 1, c, m, v, static_cast<float4 *>(f->params), f->aux, s);
         }
         case DIST_B200_GP: {
             const uint32_t *p = static_cast<const uint32_t *>(stats);
@@ -392,6 +403,8 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
     if (groupid != last)  // packed_remove: move the last group into the hole (vector.hpp:47-51)
         DISTB200_CUDA(ctx, cudaMemcpyAsync(base + gb * groupid, base + gb * last, gb, cudaMemcpyDeviceToDevice, as_stream(stream)));
     DISTB200_CUDA(ctx, cudaMemsetAsync(base + gb * last, 0, gb, as_stream(stream)));
+    if (f->aux && groupid != last)
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(f->aux + groupid, f->aux + last, sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
     f->G = last;
     return DIST_B200_OK;
 }

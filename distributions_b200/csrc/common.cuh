@@ -60,6 +60,7 @@ struct dist_b200_feature {
     // device buffers
     void *params = nullptr;           // hot layout (see FeatDesc::params)
     size_t params_bytes = 0;
+    float *aux = nullptr;             // nich: unscaled log_coeff_ per group (capacity floats)
     uint32_t *keys_dev = nullptr;     // dpd sorted keys
     int *key_rows_dev = nullptr;      // dpd: table row of sorted key i
     // niw
@@ -87,7 +88,7 @@ inline int fail(dist_b200_ctx *ctx, int code, const std::string &msg) {
 // ---- kernel launchers implemented in the .cu files --------------------------------------------
 // prep.cu
 int launch_nich_prep(dist_b200_ctx *ctx, const float shared[4], int G, int g0, int n, const int32_t *count_dev,
-                     const float *mean_dev, const float *ctv_dev, float4 *params, cudaStream_t s);
+                     const float *mean_dev, const float *ctv_dev, float4 *params, float *aux, cudaStream_t s);
 int launch_gp_prep(dist_b200_ctx *ctx, const float shared[2], int g0, int n, const uint32_t *count_dev,
                    const uint32_t *sum_dev, float4 *params, cudaStream_t s);
 int launch_bb_prep(dist_b200_ctx *ctx, const float shared[2], int g0, int n, const int32_t *heads_dev,

@@ -31,7 +31,7 @@ struct NumericTables {
 
 __device__ __forceinline__ float mufu_lg2(float x) {
     float y;
-    asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // ftz: no denormal fix-up code around the MUFU
     return y;
 }
 __device__ __forceinline__ float mufu_ex2(float x) {
@@ -48,10 +48,12 @@ __device__ __forceinline__ float fast_log_table(float x, const float *__restrict
     return __fmul_rn(__fadd_rn(static_cast<float>(e), __ldg(log2_table + man)), kLn2);
 }
 
-// per-cell form; x must be positive, finite, normal
-__device__ __forceinline__ float fast_log_cell(float x) {
-    return mufu_lg2(__uint_as_float(__float_as_uint(x) & 0xFFFFFE00u)) * kLn2;
+// per-cell form; x must be positive, finite, normal.  fast_log2_cell is the table's log2 part; the
+// hot loops fold the trailing `* ln 2` into the per-group coefficient (one FMUL less per cell).
+__device__ __forceinline__ float fast_log2_cell(float x) {
+    return mufu_lg2(__uint_as_float(__float_as_uint(x) & 0xFFFFFE00u));
 }
+__device__ __forceinline__ float fast_log_cell(float x) { return fast_log2_cell(x) * kLn2; }
 
 // fast_exp as used by scores_to_likelihoods (random.cc:94-106): argument = score - max <= 0.
 // fmath::exp is exp() to 4e-7 (source) / 5e-6 (the -ffast-math build); MUFU.EX2 of x*log2(e) is

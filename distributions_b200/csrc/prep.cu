@@ -9,11 +9,12 @@ namespace distb200 {
 
 // ---------------------------------------------------------------------------------------------
 // NormalInverseChiSq: Shared::plus_group (nich.hpp:58-69) + Scorer::init (nich.hpp:239-250)
-// packed as float4 {mean, precision, log_coeff, score}
+// packed as float4 {mean, precision, log_coeff * ln 2, score}: the hot loop multiplies the coefficient
+// with MUFU.LG2's base-2 logarithm directly.  The unscaled log_coeff_ is kept in `aux` for read-back.
 __global__ void nich_prep_kernel(float mu, float kappa, float sigmasq, float nu, int g0, int n,
                                  const int32_t *__restrict__ count, const float *__restrict__ mean,
                                  const float *__restrict__ ctv, float4 *__restrict__ params,
-                                 NumericTables t) {
+                                 float *__restrict__ aux, NumericTables t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float cnt = static_cast<float>(count[i]);
@@ -28,7 +29,8 @@ __global__ void nich_prep_kernel(float mu, float kappa, float sigmasq, float nu,
                         0.5f * fast_log_table(lambda / (3.14159265358979f * post_nu), t.log2_table);
     const float log_coeff = -0.5f * post_nu - 0.5f;
     const float precision = lambda / post_nu;
-    params[g0 + i] = make_float4(post_mu, precision, log_coeff, score);
+    params[g0 + i] = make_float4(post_mu, precision, log_coeff * kLn2, score);
+    aux[g0 + i] = log_coeff;
 }
 
 // GammaPoisson: plus_group (gp.hpp:56-61) + Scorer::init (gp.hpp:198-207); {post_alpha, score_coeff, score, 0}
@@ -165,13 +167,14 @@ __global__ void numerics_probe_kernel(int fn, size_t n, const float *__restrict_
 }
 
 // hot layout -> the reference's struct-of-arrays cache layout (dist_b200_feature_download_caches)
-__global__ void unpack_float4_kernel(int model, int G, const float4 *__restrict__ params, float *__restrict__ out) {
+__global__ void unpack_float4_kernel(int model, int G, const float4 *__restrict__ params,
+                                     const float *__restrict__ aux, float *__restrict__ out) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
     const float4 p = params[g];
     if (model == DIST_B200_NICH) {  // score_, log_coeff_, precision_, mean_
         out[0 * G + g] = p.w;
-        out[1 * G + g] = p.z;
+        out[1 * G + g] = aux[g];
         out[2 * G + g] = p.y;
         out[3 * G + g] = p.x;
     } else if (model == DIST_B200_GP) {  // score_, post_alpha_, score_coeff_
@@ -201,11 +204,11 @@ static inline int blocks_for(size_t n, int threads) { return static_cast<int>((n
     } while (0)
 
 int launch_nich_prep(dist_b200_ctx *ctx, const float sh[4], int G, int g0, int n, const int32_t *count,
-                     const float *mean, const float *ctv, float4 *params, cudaStream_t s) {
+                     const float *mean, const float *ctv, float4 *params, float *aux, cudaStream_t s) {
     (void)G;
     if (n <= 0) return DIST_B200_OK;
     nich_prep_kernel<<<blocks_for(n, 128), 128, 0, s>>>(sh[0], sh[1], sh[2], sh[3], g0, n, count, mean, ctv,
-                                                        params, ctx->tables);
+                                                        params, aux, ctx->tables);
     LAUNCH_CHECK(ctx);
     return DIST_B200_OK;
 }
@@ -271,7 +274,7 @@ int launch_unpack_caches(dist_b200_ctx *ctx, const dist_b200_feature *f, float *
         case DIST_B200_GP:
         case DIST_B200_BB:
             unpack_float4_kernel<<<blocks_for(G, 128), 128, 0, s>>>(f->model, G,
-                                                                    static_cast<const float4 *>(f->params), out);
+                                                                    static_cast<const float4 *>(f->params), f->aux, out);
             break;
         case DIST_B200_DD:
             transpose_table_kernel<<<blocks_for(G, 128), 128, 0, s>>>(G, f->dim, static_cast<const float *>(f->params),

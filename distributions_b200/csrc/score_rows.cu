@@ -63,7 +63,7 @@ __device__ __forceinline__ float cell_score(int kind, uint32_t xb, const float *
             const float4 q = *reinterpret_cast<const float4 *>(p);
             const float d = __uint_as_float(xb) - q.x;
             const float z = __fadd_rn(1.f, __fmul_rn(q.y, __fmul_rn(d, d)));
-            return fmaf(q.z, fast_log_cell(z), q.w);
+            return fmaf(q.z, fast_log2_cell(z), q.w);  // q.z = log_coeff * ln 2
         }
         case DIST_B200_GP: {
             const float4 q = *reinterpret_cast<const float4 *>(p);
@@ -99,7 +99,7 @@ __device__ __forceinline__ void accumulate_feature(int kind, const uint32_t (&xb
                 for (int r = 0; r < R; ++r) {
                     const float d = __uint_as_float(xb[r]) - q.x;
                     const float z = __fadd_rn(1.f, __fmul_rn(q.y, __fmul_rn(d, d)));
-                    acc[r][j] += fmaf(q.z, fast_log_cell(z), q.w);
+                    acc[r][j] += fmaf(q.z, fast_log2_cell(z), q.w);  // q.z = log_coeff * ln 2
                 }
             }
         } break;
@@ -162,17 +162,17 @@ template <int CHUNK, int R, bool kSample, bool kScores>
 __global__ void __launch_bounds__(kThreads)
 score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     extern __shared__ __align__(16) float smem[];
-    // layout: coeff[33*8] | logfact[64] | prior[CHUNK] | tile[8 warps][32][33] (kScores) |
+    // layout: coeff[33*8] | logfact[64] | prior[Gpad] | tile[8 warps][32][33] (kScores) |
     //         slots[kSlots][R][kThreads] float2 (kSample, multi-chunk) | caches
-    float *coeff = smem;
-    float *logfact = coeff + 33 * kLgammaRowStride;
-    float *prior_s = logfact + 64;
-    float *cursor = prior_s + CHUNK;
-    float *tile = cursor;
-    if (kScores) cursor += (kThreads / 32) * 32 * 33;
     const int G = a.G;
     const int nchunks = (G + CHUNK - 1) / CHUNK;
     const bool multi = nchunks > 1;
+    float *coeff = smem;
+    float *logfact = coeff + 33 * kLgammaRowStride;
+    float *prior_s = logfact + 64;
+    float *cursor = prior_s + nchunks * CHUNK;
+    float *tile = cursor;
+    if (kScores) cursor += (kThreads / 32) * 32 * 33;
     float2 *slots = reinterpret_cast<float2 *>(cursor);
     if (kSample && multi) cursor += 2 * kSlots * R * kThreads;
     float *caches = cursor;
@@ -183,6 +183,9 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
 
     for (int i = tid; i < 33 * kLgammaRowStride; i += kThreads) coeff[i] = a.t.lgamma5[i];
     if (tid < 64) logfact[tid] = a.t.log_factorial[tid];
+    // the prior vector (clustering's overwrite) seeds every accumulator; padded groups get -inf
+    for (int g = tid; g < Gpad; g += kThreads)
+        prior_s[g] = g < G ? ((a.prior && !a.accumulate) ? a.prior[g] : 0.f) : -INFINITY;
     if (a.resident) {
         size_t off = 0;
         for (int f = 0; f < F; ++f) {
@@ -213,33 +216,32 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
         float slot_m[R], slot_s[R];  // slot being merged (multi-chunk sampling)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            slot_m[r] = -INFINITY;
+            slot_m[r] = INFINITY;  // negated scaled maximum of the slot so far
             slot_s[r] = 0.f;
         }
         int result[R];
 
         for (int c = 0; c < nchunks; ++c) {
             const int g0 = c * CHUNK;
-            __syncthreads();  // prior_s / staging buffers of the previous chunk are no longer read
-            if (tid < CHUNK) {
-                const int g = g0 + tid;
-                prior_s[tid] = g < G ? ((a.prior && !a.accumulate) ? a.prior[g] : 0.f) : -INFINITY;
-            }
-            if (!a.resident) {  // stage feature 0 of this chunk
+            if (!a.resident) {  // stage feature 0 of this chunk (buffer 0 was released by the last sync)
                 const FeatDesc &fd = feats.f[0];
                 const int st = kind_stride(fd);
                 const float *src = static_cast<const float *>(fd.params) + static_cast<size_t>(g0) * st;
                 for (int i = tid * 4; i < CHUNK * st; i += kThreads * 4) cp_async16(caches + i, src + i);
                 cp_async_commit();
             }
-            __syncthreads();
 
             float acc[R][CHUNK];
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-                const float p = prior_s[j];
+            for (int j = 0; j < CHUNK; j += 4) {
+                const float4 p = *reinterpret_cast<const float4 *>(prior_s + g0 + j);
 #pragma unroll
-                for (int r = 0; r < R; ++r) acc[r][j] = p;
+                for (int r = 0; r < R; ++r) {
+                    acc[r][j] = p.x;
+                    acc[r][j + 1] = p.y;
+                    acc[r][j + 2] = p.z;
+                    acc[r][j + 3] = p.w;
+                }
             }
 
             uint32_t xb[R];
@@ -281,6 +283,18 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                 }
             }
 
+            if (g0 + CHUNK > G) {
+                // ragged last tile: padded groups carry zeroed caches, whose model terms may be inf/NaN
+                // (lgamma(0)); pin them to -inf so they vanish from max / exp / the walk
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) {
+                    if (g0 + j >= G) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r][j] = -INFINITY;
+                    }
+                }
+            }
+
             if (kScores) {
                 // [32 rows][32 groups] transposes through a padded per-warp tile -> coalesced rows
                 float *tw = tile + warp * 32 * 33;
@@ -315,10 +329,11 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                         float m = acc[r][0];
 #pragma unroll
                         for (int j = 1; j < CHUNK; ++j) m = fmaxf(m, acc[r][j]);
+                        const float nm = -m * kLog2e;  // exp(s - m) = 2^(s*log2e + nm): one FFMA + MUFU.EX2
                         float total = 0.f;
 #pragma unroll
                         for (int j = 0; j < CHUNK; ++j) {
-                            acc[r][j] = fast_exp_neg(acc[r][j] - m);
+                            acc[r][j] = mufu_ex2(fmaf(acc[r][j], kLog2e, nm));
                             total += acc[r][j];
                         }
                         float t = total * a.u[row[r]];
@@ -336,16 +351,19 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                         float m = acc[r][0];
 #pragma unroll
                         for (int j = 1; j < CHUNK; ++j) m = fmaxf(m, acc[r][j]);
+                        // slots carry nm = -(max * log2 e), rounded ONCE: every later rescale is a
+                        // difference of these rounded values, so chunk sums stay mutually consistent
+                        const float nm = -m * kLog2e;
                         float s = 0.f;
 #pragma unroll
-                        for (int j = 0; j < CHUNK; ++j) s += fast_exp_neg(acc[r][j] - m);
+                        for (int j = 0; j < CHUNK; ++j) s += mufu_ex2(fmaf(acc[r][j], kLog2e, nm));
                         // merge into the running slot
-                        const float mn = fmaxf(slot_m[r], m);
-                        slot_s[r] = slot_s[r] * fast_exp_neg(slot_m[r] - mn) + s * fast_exp_neg(m - mn);
-                        slot_m[r] = mn;
+                        const float nn = fminf(slot_m[r], nm);
+                        slot_s[r] = slot_s[r] * mufu_ex2(nn - slot_m[r]) + s * mufu_ex2(nn - nm);
+                        slot_m[r] = nn;
                         if ((c + 1) % chunks_per_slot == 0 || c + 1 == nchunks) {
                             slots[((c / chunks_per_slot) * R + r) * kThreads + tid] = make_float2(slot_m[r], slot_s[r]);
-                            slot_m[r] = -INFINITY;
+                            slot_m[r] = INFINITY;
                             slot_s[r] = 0.f;
                         }
                     }
@@ -359,18 +377,18 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
             int slot_sel[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float mm = -INFINITY;
-                for (int k = 0; k < nslots; ++k) mm = fmaxf(mm, slots[(k * R + r) * kThreads + tid].x);
+                float mm = INFINITY;  // = -(row maximum) * log2 e
+                for (int k = 0; k < nslots; ++k) mm = fminf(mm, slots[(k * R + r) * kThreads + tid].x);
                 float total = 0.f;
                 for (int k = 0; k < nslots; ++k) {
                     const float2 ms = slots[(k * R + r) * kThreads + tid];
-                    total += ms.y * fast_exp_neg(ms.x - mm);
+                    total += ms.y * mufu_ex2(mm - ms.x);
                 }
                 float t = total * a.u[row[r]];
                 int sel = nslots - 1;
                 for (int k = 0; k < nslots; ++k) {
                     const float2 ms = slots[(k * R + r) * kThreads + tid];
-                    const float w = ms.y * fast_exp_neg(ms.x - mm);
+                    const float w = ms.y * mufu_ex2(mm - ms.x);
                     if (t <= w) {
                         sel = k;
                         break;
@@ -404,7 +422,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                                                 static_cast<const float *>(fd.params) + static_cast<size_t>(g) * st,
                                                 fd.vdim, coeff, logfact);
                             }
-                            l = fast_exp_neg(s - Mi);
+                            l = mufu_ex2(fmaf(s, kLog2e, Mi));
                         }
                         float scan = l;
 #pragma unroll
@@ -445,7 +463,7 @@ static int launch_variant(dist_b200_ctx *ctx, const FeatList &feats, RowsArgs a,
         cache_floats += static_cast<size_t>(Gpad) * st;
         if (st > max_stride) max_stride = st;
     }
-    size_t fixed = (33 * kLgammaRowStride + 64 + CHUNK) * sizeof(float);
+    size_t fixed = (33 * kLgammaRowStride + 64 + Gpad) * sizeof(float);
     if (kScores) fixed += (kThreads / 32) * 32 * 33 * sizeof(float);
     if (kSample && nchunks > 1) fixed += sizeof(float2) * kSlots * R * kThreads;
     a.resident = cache_floats * sizeof(float) <= kResidentBudget ? 1 : 0;
@@ -493,7 +511,7 @@ int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N
     if (G <= 32) return launch_modes<32, 1>(ctx, feats, a, s);
     if (G <= 64) return launch_modes<64, 1>(ctx, feats, a, s);
     if (G <= 128) return launch_modes<128, 1>(ctx, feats, a, s);
-    return launch_modes<32, 1>(ctx, feats, a, s);
+    return launch_modes<32, 2>(ctx, feats, a, s);
 }
 
 }  // namespace distb200

@@ -101,7 +101,9 @@ def test_numerics_device_functions(ctx, oracle):
     ctx.numerics_probe(1, xd, out, x.size)
     got = out.cpu().numpy().astype(np.float64)
     want = oracle.fast_exp(x).astype(np.float64)
-    assert np.max(np.abs(got - want) / want) <= 2e-6
+    # x * log2(e) is rounded once at magnitude |x| * 1.44: the relative error grows with |x| (the
+    # reference's own (x + 1) - r*b re-association has the same shape, 5e-6 at x = -87)
+    assert np.all(np.abs(got - want) / want <= 5e-7 + 1.2e-7 * np.abs(x))
     # log factorial
     n = np.concatenate([np.arange(0, 300), [1000, 65535, 1 << 20]]).astype(np.uint32)
     xd = dev(n.view(np.float32))
@@ -322,8 +324,8 @@ def test_sampler_golden(ctx, golden, G):
 def test_sampler_large_vs_oracle_and_distribution(ctx, oracle):
     rng = np.random.default_rng(9)
     n, G = 200000, 333
-    s = (rng.standard_normal((n, G)) * 2).astype(np.float32)
-    s[:, :] = s[:1000].repeat(200, axis=0)  # 1000 distinct rows x 200 draws each
+    base = (rng.standard_normal((1000, G)) * 2).astype(np.float32)
+    s = np.ascontiguousarray(base.repeat(200, axis=0))  # 1000 distinct rows x 200 draws each
     u = rng.random(n, dtype=np.float32)
     out = torch.empty(n, device="cuda", dtype=torch.int32)
     ctx.sample_from_scores(dev(s), n, G, dev(u), out)
@@ -333,7 +335,7 @@ def test_sampler_large_vs_oracle_and_distribution(ctx, oracle):
     assert cases.explained_mismatch(s.astype(np.float64), u, got, want, EPS_TIE).all()
     assert np.mean(got != want) < 2e-4
     # the draws follow softmax(scores): chi-square style check on one row's 200 draws pooled over rows
-    p = np.exp(s[:1000].astype(np.float64) - s[:1000].max(1, keepdims=True))
+    p = np.exp(base.astype(np.float64) - base.max(1, keepdims=True))
     p /= p.sum(1, keepdims=True)
     hits = np.zeros(1000)
     for r in range(1000):
