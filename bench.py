@@ -32,6 +32,7 @@ WORKLOADS = {
     "c2_nich": dict(model="nich", G=1024, N=1_000_000, seed=20242),
     "c3_crosscat": dict(model="crosscat", G=128, N=1_000_000, seed=20243, n_gp=128, n_bb=128),
     "c4_dpd": dict(model="dpd", G=512, N=10_000_000, seed=20244, V=4096),
+    "c5_niw": dict(model="niw", G=256, N=1_000_000, seed=20245, d=32),
 }
 
 
@@ -107,7 +108,7 @@ def make_workload(name, rank=0):
 
 
 def model_id(capi, name):
-    return {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH}[name]
+    return {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH, "niw": capi.NIW}[name]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -273,7 +274,7 @@ def run_b200(args):
     # the binding limit of this kernel is not HBM: report the measured pipe it is bound by as well
     mufu = ctx.pipe_peak(0)
     fma = ctx.pipe_peak(1)
-    mufu_per_cell = {"nich": 2.0, "dd": 1.0, "dpd": 1.0, "gp": 1.0, "bb": 1.0}[wl["feats"][0]["model"]]
+    mufu_per_cell = {"nich": 2.0, "dd": 1.0, "dpd": 1.0, "gp": 1.0, "bb": 1.0, "niw": 2.0}[wl["feats"][0]["model"]]
     if wl["name"] == "c3_crosscat":
         mufu_per_cell = 1.0 / F
     cells_rank = float(N) * F * G
@@ -308,6 +309,92 @@ def run_b200(args):
     return 0
 
 
+def run_b200_feature_sharded(args):
+    """c3 at N > 1: the features of one cross-cat kind are sharded over the ranks; one NCCL
+    reduce-scatter(sum) of per-row, per-group partial scores over NVLink, each rank samples its row
+    block (distributions_b200.sharding).  Strong scaling: the 1M x 256 x 128 table is fixed."""
+    import torch
+    import torch.distributed as dist
+    from distributions_b200 import capi, sharding, synth
+
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    wl = make_workload(args.workload, 0)  # the same table on every rank; each rank keeps its features
+    G, N = wl["G"], wl["N"]
+    F = len(wl["feats"])
+    mine = sharding.feature_shard(F, rank, world)
+    ctx = capi.Context(local_rank)
+    feats = [ctx.feature(model_id(capi, wl["feats"][f]["model"])).update_all(wl["feats"][f]) for f in mine]
+    cols = [torch.from_numpy(np.ascontiguousarray(wl["feats"][f]["values"],
+                                                  dtype=capi.COLUMN_DTYPE[model_id(capi, wl["feats"][f]["model"])])).to(dev)
+            for f in mine]
+    u = torch.from_numpy(wl["u"]).to(dev)
+    prior = torch.empty(G, device=dev, dtype=torch.float32)
+    ctx.prior_pitman_yor(synth.PY_ALPHA, synth.PY_D, wl["sizes"], prior)
+    stream = torch.cuda.current_stream().cuda_stream
+    comm = torch.cuda.Stream(device=dev)
+    launches = [0]
+
+    def score_partial(lo, hi, out):
+        if feats:
+            ctx.score_batch(feats, [c[lo:hi] for c in cols], hi - lo, prior if rank == 0 else None, out, stream=stream)
+            launches[0] += 1
+        else:
+            out.zero_()
+
+    def sample_block(scores, ub, out):
+        ctx.sample_from_scores(scores, scores.shape[0], G, ub, out, stream=stream)
+        launches[0] += 1
+
+    def step():
+        return sharding.feature_sharded_score_sample(score_partial, sample_block, N, G, u, dev, tile_rows=args.tile_rows,
+                                                     comm_stream=comm)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches[0] = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s0, s1 in ev:
+        s0.record()
+        step()
+        s1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([float(sum(a.elapsed_time(b) for a, b in ev))], device=dev, dtype=torch.float64)
+    dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    if rank == 0:
+        value = float(N) * F * G / (ms_per_step * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "rows": N, "groups": G, "features": F,
+                       "parallelism": "feature shards (%d per rank) + NCCL reduce-scatter(sum) of [rows][G] partials, "
+                                      "tiles of %d rows overlapped on a second stream" % (len(mine), args.tile_rows),
+                       "l2": "inputs (640 MB of columns + 512 MB of partial scores per step) exceed the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": launches[0],
+            "nvlink_bytes_per_step_per_rank": int(4 * N * G * (world - 1) / world),
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -316,9 +403,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2_nich", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tile-rows", type=int, default=65536, help="row tile of the feature-sharded reduce-scatter")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c3_crosscat" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_b200_feature_sharded(args)
     return run_b200(args)
 
 

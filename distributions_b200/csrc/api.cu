@@ -30,6 +30,19 @@ int ensure_scratch(dist_b200_ctx *ctx, size_t bytes) {
     return DIST_B200_OK;
 }
 
+int ensure_scores_scratch(dist_b200_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->scores_scratch_bytes) return DIST_B200_OK;
+    if (ctx->scores_scratch) {
+        DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+        DISTB200_CUDA(ctx, cudaFree(ctx->scores_scratch));
+        ctx->scores_scratch = nullptr;
+        ctx->scores_scratch_bytes = 0;
+    }
+    DISTB200_CUDA(ctx, cudaMalloc(&ctx->scores_scratch, bytes));
+    ctx->scores_scratch_bytes = bytes;
+    return DIST_B200_OK;
+}
+
 int ensure_pinned(dist_b200_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->pinned_bytes) return DIST_B200_OK;
     if (ctx->pinned) {
@@ -167,6 +180,7 @@ void dist_b200_ctx_destroy(dist_b200_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->tables_storage) cudaFree(ctx->tables_storage);
     if (ctx->scratch_dev) cudaFree(ctx->scratch_dev);
+    if (ctx->scores_scratch) cudaFree(ctx->scores_scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -330,9 +344,39 @@ int dist_b200_dpd_update_all(dist_b200_feature *f, float alpha, float beta0, int
 int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float kappa, const float *psi,
                              float nu, int G, const int32_t *count, const float *sum_x, const float *sum_xxT,
                              void *stream) {
-    (void)d; (void)mu; (void)kappa; (void)psi; (void)nu; (void)G; (void)count; (void)sum_x; (void)sum_xxT; (void)stream;
-    if (!check_feature(f, DIST_B200_NIW)) return DIST_B200_ERR_INVALID;
-    return fail(f->ctx, DIST_B200_ERR_UNSUPPORTED, "niw: not built yet");
+    if (!check_feature(f, DIST_B200_NIW) || d < 1 || !mu || !psi || G < 0 || (G && (!count || !sum_x || !sum_xxT)))
+        return DIST_B200_ERR_INVALID;
+    dist_b200_ctx *ctx = f->ctx;
+    if (d > 32) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "niw: d > 32");
+    if (!(kappa > 0.f) || !(nu > static_cast<float>(d) - 1.f))
+        return fail(ctx, DIST_B200_ERR_INVALID, "niw: need kappa > 0 and nu > d - 1 (niw.hpp:121,132)");
+    const size_t rec = static_cast<size_t>(niw_padded_dim(d)) * (niw_padded_dim(d) + 1) + 4;
+    const size_t bytes = sizeof(float) * rec * std::max(G, 1);
+    if (bytes > f->niw_bytes) {
+        if (f->niw_buf) {
+            DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+            DISTB200_CUDA(ctx, cudaFree(f->niw_buf));
+            f->niw_buf = nullptr;
+        }
+        DISTB200_CUDA(ctx, cudaMalloc(&f->niw_buf, bytes));
+        f->niw_bytes = bytes;
+    }
+    const size_t dd = static_cast<size_t>(d) * d;
+    int rc = ensure_scratch(ctx, round_up(4 * d, 256) + round_up(4 * dd, 256) + round_up(4 * static_cast<size_t>(G), 256) +
+                                     round_up(4 * static_cast<size_t>(G) * d, 256) + round_up(4 * G * dd, 256) + 256);
+    if (rc) return rc;
+    Upload up{ctx, as_stream(stream)};
+    const float *mu_d = up.put(mu, d);
+    const float *psi_d = up.put(psi, dd);
+    const int32_t *cnt_d = up.put(count, G);
+    const float *sx_d = up.put(sum_x, static_cast<size_t>(G) * d);
+    const float *sxx_d = up.put(sum_xxT, static_cast<size_t>(G) * dd);
+    if (up.err) return up.err;
+    f->dim = d;
+    f->G = G;
+    f->kappa = kappa;
+    f->nu = nu;
+    return launch_niw_prep(ctx, d, mu_d, kappa, psi_d, nu, G, cnt_d, sx_d, sxx_d, f->niw_buf, as_stream(stream));
 }
 
 int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void *stats, void *stream) {
@@ -462,12 +506,13 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
         if (features[f]->G != G) return fail(ctx, DIST_B200_ERR_STATE, "score: features disagree on the number of groups");
     }
     if (N == 0) return DIST_B200_OK;
-    // value-major table features (dpd) take the warp-per-row kernel, one feature per launch
-    bool any_table = false;
-    for (int f = 0; f < F; ++f) any_table = any_table || features[f]->model == DIST_B200_DPD;
-    for (int f = 0; f < F; ++f)
-        if (features[f]->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score: niw not built yet");
-    if (!any_table) {
+    // Row-mapped models (nich/gp/bb/dd) fuse into one launch.  dpd (value-major table, warp per row) and
+    // niw (dense contraction) have their own kernels: alone they run directly, in mixed lists the scores
+    // are materialised, every feature accumulates, and the stand-alone sampler finishes.
+    auto solo = [](const dist_b200_feature *f) { return f->model == DIST_B200_DPD || f->model == DIST_B200_NIW; };
+    int n_solo = 0;
+    for (int f = 0; f < F; ++f) n_solo += solo(features[f]) ? 1 : 0;
+    if (n_solo == 0) {
         if (F > kMaxFeatures) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score: more than 512 features in one call");
         FeatList fl;
         fl.n = F;
@@ -480,19 +525,19 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
         }
         return launch_score_rows(ctx, fl, G, N, prior, u, assign, scores, accumulate, s);
     }
-    if (F == 1) return launch_gather_rows(ctx, features[0], columns[0], N, prior, u, assign, scores, accumulate, s);
-    // mixed lists: materialise.  Row-mapped features first (prior folded in), then each table feature
-    // accumulates, then the stand-alone sampler.
+    if (F == 1 && features[0]->model == DIST_B200_DPD)
+        return launch_gather_rows(ctx, features[0], columns[0], N, prior, u, assign, scores, accumulate, s);
     float *buf = scores;
     if (!buf) {
-        int rc = ensure_scratch(ctx, sizeof(float) * N * G);
+        int rc = ensure_scores_scratch(ctx, sizeof(float) * N * G);
         if (rc) return rc;
-        buf = static_cast<float *>(ctx->scratch_dev);
+        buf = static_cast<float *>(ctx->scores_scratch);
     }
     FeatList fl;
     fl.n = 0;
     for (int f = 0; f < F; ++f) {
-        if (features[f]->model == DIST_B200_DPD) continue;
+        if (solo(features[f])) continue;
+        if (fl.n >= kMaxFeatures) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score: more than 512 features in one call");
         FeatDesc &d = fl.f[fl.n++];
         d.params = features[f]->params;
         d.column = columns[f];
@@ -507,10 +552,13 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
         started = true;
     }
     for (int f = 0; f < F; ++f) {
-        if (features[f]->model != DIST_B200_DPD) continue;
-        if ((rc = launch_gather_rows(ctx, features[f], columns[f], N, started ? nullptr : prior, nullptr, nullptr, buf,
-                                     started ? 1 : 0, s)))
-            return rc;
+        if (!solo(features[f])) continue;
+        if (features[f]->model == DIST_B200_DPD)
+            rc = launch_gather_rows(ctx, features[f], columns[f], N, started ? nullptr : prior, nullptr, nullptr, buf,
+                                    started ? 1 : 0, s);
+        else
+            rc = launch_niw_scores(ctx, features[f], columns[f], N, started ? nullptr : prior, buf, started ? 1 : 0, s);
+        if (rc) return rc;
         started = true;
     }
     if (assign) return launch_sample_scores(ctx, buf, N, G, u, assign, s);
@@ -587,14 +635,6 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
     std::vector<const void *> cols(F);
     for (int f = 0; f < F; ++f) cols[f] = dev + col_off[f];
     float *scores_dev = scores_host ? reinterpret_cast<float *>(dev + scores_off) : nullptr;
-    bool any_table = false, any_rows = false;
-    for (int f = 0; f < F; ++f) (features[f]->model == DIST_B200_DPD ? any_table : any_rows) = true;
-    if (any_table && F > 1 && !scores_dev) {
-        // mixed list without a caller buffer: give the dispatcher an explicit [N][G] region
-        if ((rc = ensure_scratch(ctx, off + round_up(sizeof(float) * N * G, 256) + 256))) return rc;
-        return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_sample_host: mixed dpd + other features need scores_host");
-    }
-    (void)any_rows;
     rc = score_dispatch(ctx, features, F, cols.data(), N, prior_host ? reinterpret_cast<const float *>(dev + prior_off) : nullptr,
                         reinterpret_cast<const float *>(dev + u_off), reinterpret_cast<int32_t *>(dev + assign_off),
                         scores_dev, 0, s);

@@ -40,6 +40,8 @@ struct dist_b200_ctx {
     size_t pinned_bytes = 0;
     void *scratch_dev = nullptr;
     size_t scratch_bytes = 0;
+    void *scores_scratch = nullptr;   // [N][G] buffer of the materialising dispatch paths
+    size_t scores_scratch_bytes = 0;
     cudaStream_t own_stream = nullptr;
 };
 
@@ -112,5 +114,11 @@ int launch_gather_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const voi
                        cudaStream_t s);
 int launch_sample_scores(dist_b200_ctx *ctx, const float *scores, size_t N, int G, const float *u,
                          int32_t *assign, cudaStream_t s);
+// niw.cu
+int niw_padded_dim(int d);
+int launch_niw_prep(dist_b200_ctx *ctx, int d, const float *mu, float kappa, const float *psi, float nu, int G,
+                    const int32_t *count, const float *sum_x, const float *sum_xxT, float *recs, cudaStream_t s);
+int launch_niw_scores(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *values, size_t N,
+                      const float *prior, float *scores, int accumulate, cudaStream_t s);
 
 }  // namespace distb200

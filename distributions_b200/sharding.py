@@ -1,0 +1,121 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed for the plumbing).
+
+Two partitionings:
+
+* row shards  -- rows are independent given frozen statistics (examples/mixture/main.py:143-160):
+  caches and prior are replicated, each rank scores + samples its own contiguous row range.
+  NO data-path collective.
+* feature shards of one cross-cat kind -- scores[n][g] = prior[g] + sum_f s_f[n][g] is a sum over
+  features: rank k scores its features into a partial [rows][G] (the prior is added by exactly one
+  rank), ONE reduce-scatter(sum) over row blocks leaves rank k with the fully reduced rows of block k,
+  which it samples with the stand-alone sampler.  Rows are processed in tiles so that the
+  reduce-scatter of tile i (NCCL, its own stream) overlaps the scoring of tile i+1.
+
+The compute is injected as callables so the same orchestration runs on CUDA (C-ABI kernels) and in the
+world_size=2 gloo tests on CPU.
+"""
+import torch
+import torch.distributed as dist
+
+
+def row_shard(n_rows, rank, world):
+    """contiguous [lo, hi) row range of `rank`; ranges differ by at most one row"""
+    base, rem = divmod(n_rows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def feature_shard(n_features, rank, world):
+    """indices of the features owned by `rank` (round-robin keeps model kinds balanced)"""
+    return list(range(rank, n_features, world))
+
+
+def block_rows(n_rows, world):
+    """rows per reduce-scatter block: every rank's block has the same (padded) size"""
+    return (n_rows + world - 1) // world
+
+
+def reduce_scatter_rows(partial, out_block, group=None):
+    """partial: [world * block][G] (this rank's partial scores, zero-padded), out_block: [block][G]
+    receives sum over ranks of block `rank`.  Uses reduce_scatter_tensor where the backend has it
+    (NCCL), all_reduce + slice otherwise (gloo)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    block = out_block.shape[0]
+    assert partial.shape[0] == world * block
+    try:
+        if dist.get_backend(group) == "gloo":
+            raise RuntimeError("gloo: no reduce_scatter_tensor")
+        dist.reduce_scatter_tensor(out_block, partial, op=dist.ReduceOp.SUM, group=group)
+    except RuntimeError:
+        tmp = partial.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        out_block.copy_(tmp[rank * block:(rank + 1) * block])
+    return out_block
+
+
+def feature_sharded_score_sample(score_partial, sample_block, n_rows, n_groups, u, device, tile_rows=65536, group=None,
+                                 comm_stream=None):
+    """Score + sample `n_rows` rows whose FEATURES are sharded over the ranks of `group`.
+
+    score_partial(lo, hi, out)   writes this rank's partial scores of rows [lo, hi) into out[(hi-lo)][G]
+                                 (prior included on exactly one rank)
+    sample_block(scores, u, out) samples rows of a fully reduced [b][G] block with uniforms u[b]
+    u                            [n_rows] uniforms (replicated)
+
+    Returns (assign_local, (lo, hi)): the indices of the rows this rank owns.  Row tiles of
+    world * block rows are reduce-scattered so that rank k owns rows [t0 + k*block, t0 + (k+1)*block) of
+    every tile.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    tile_rows = max(world, min(tile_rows, n_rows))
+    block = block_rows(tile_rows, world)
+    tile_rows = block * world
+    owned_rows, owned_assign = [], []
+    use_cuda = device.type == "cuda"
+    cur = torch.cuda.current_stream(device) if use_cuda else None
+    bufs = [torch.zeros((tile_rows, n_groups), dtype=torch.float32, device=device) for _ in range(2)]
+    outs = [torch.zeros((block, n_groups), dtype=torch.float32, device=device) for _ in range(2)]
+    pending = None  # (buffer index, t0, event)
+    t0 = 0
+    it = 0
+
+    def finish(p):
+        bi, pt0, ev = p
+        if use_cuda and ev is not None:
+            cur.wait_event(ev)
+        lo = min(pt0 + rank * block, n_rows)
+        hi = min(lo + block, min(pt0 + tile_rows, n_rows))
+        if hi > lo:
+            a = torch.empty(hi - lo, dtype=torch.int32, device=device)
+            sample_block(outs[bi][:hi - lo], u[lo:hi], a)
+            owned_rows.append((lo, hi))
+            owned_assign.append(a)
+
+    while t0 < n_rows:
+        bi = it & 1
+        hi = min(t0 + tile_rows, n_rows)
+        buf = bufs[bi]
+        if hi - t0 < tile_rows:
+            buf.zero_()
+        score_partial(t0, hi, buf[:hi - t0])
+        if use_cuda and comm_stream is not None:
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ready)
+                reduce_scatter_rows(buf, outs[bi], group)
+                done = torch.cuda.Event()
+                done.record(comm_stream)
+        else:
+            reduce_scatter_rows(buf, outs[bi], group)
+            done = None
+        if pending is not None:
+            finish(pending)  # sample the previous tile while this tile's reduce-scatter is in flight
+        pending = (bi, t0, done)
+        t0 = hi
+        it += 1
+    if pending is not None:
+        finish(pending)
+    return owned_assign, owned_rows

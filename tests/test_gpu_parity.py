@@ -421,3 +421,76 @@ def test_error_codes(ctx):
     f1, f2 = ctx.feature(capi.NICH).update_all(w1), ctx.feature(capi.NICH).update_all(w2)
     with pytest.raises(capi.DistB200Error):  # features disagree on G
         ctx.score_batch([f1, f2], [dev(w1["values"]), dev(w2["values"])], 4, None, torch.zeros(4 * 5, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------ NIW
+def _niw_cuda(ctx, w, n, prior, sample=True, extra=None):
+    from distributions_b200 import capi
+    f = ctx.feature(capi.NIW).update_all(w)
+    feats, cols = [f], [dev(np.ascontiguousarray(w["values"][:n], dtype=np.float32))]
+    if extra is not None:
+        feats.append(ctx.feature(model_id(extra["model"])).update_all(extra))
+        cols.append(dev(extra["values"][:n].astype(capi.COLUMN_DTYPE[model_id(extra["model"])])))
+    G = w["sizes"].size
+    scores = torch.full((n, G), 555.0, device="cuda")
+    assign = torch.full((n,), -3, device="cuda", dtype=torch.int32)
+    ctx.score_sample_batch(feats, cols, n, dev(prior), dev(w["u"][:n]), assign, scores)
+    torch.cuda.synchronize()
+    return assign.cpu().numpy(), scores.cpu().numpy()
+
+
+def _niw_tol(w, want):
+    d = w["mu"].size
+    dof = w["nu"] + w["count"].astype(np.float64) - d + 1.0
+    coef3 = 0.5 * (dof + d)
+    # fast_log step envelope (the argument 1 + q/dof is built from a whitened sum of squares here, from
+    # sigma^-1 in the oracle: last-bit differences move it across table steps) + fp32 accumulation
+    return 2e-5 * (1 + np.abs(want)) + LOG_STEP * coef3[None, :]
+
+
+@pytest.mark.parametrize("d,G", [(2, 9), (3, 40), (8, 33), (32, 9), (32, 70)])
+def test_niw_vs_oracle(ctx, oracle, d, G):
+    n = 301
+    w = synth.niw(600 + d + G, G, n, d=d)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    assign, scores = _niw_cuda(ctx, w, n, prior)
+    want = np.tile(prior, (n, 1)).astype(np.float32)
+    oracle.niw_score_rows(w["mu"], w["kappa"], w["psi"], w["nu"], w["count"], w["sum_x"], w["sum_xxT"], w["values"][:n], want)
+    assert np.all(np.abs(scores - want) <= _niw_tol(w, want))
+    assert np.mean(np.abs(scores - want) <= 2e-5 * (1 + np.abs(want))) > 0.9
+    a_orc = oracle.sample_rows(scores.copy(), w["u"][:n])
+    assert cases.explained_mismatch(scores.astype(np.float64), w["u"][:n], assign, a_orc, EPS_TIE).all()
+    assert assign.min() >= 0 and assign.max() < G
+
+
+def test_niw_1d_reference_kat(ctx, ref):
+    """reference KAT test_normal_models.py:34-84: NIW(d=1) == NICH(sigmasq = psi/nu), vs the REFERENCE's
+    nich output at the reference's tolerance 1e-3"""
+    from distributions_b200 import capi
+    data = np.array([4.0, 3.0, 7.0, 10.0])
+    vals = np.array([32.0, -0.1], np.float32)
+    k = ref.kind(1, None)
+    k.add_nich([30.0, 0.3, 2.0 / 3.0, 3.0], [len(data)], [np.float32(data.mean())], [np.float32(((data - data.mean()) ** 2).sum())])
+    want = k.score_rows([vals], 2, with_prior=False)
+    w = dict(mu=[30.0], kappa=0.3, psi=[[2.0]], nu=3.0, count=[len(data)], sum_x=np.float32([[data.sum()]]),
+             sum_xxT=np.float32([[[(data ** 2).sum()]]]))
+    f = ctx.feature(capi.NIW).update_all(w)
+    sc = torch.zeros((2, 1), device="cuda")
+    ctx.score_batch([f], [dev(vals.reshape(2, 1))], 2, None, sc)
+    torch.cuda.synchronize()
+    got = sc.cpu().numpy()
+    assert np.all(np.abs(got - want) <= 1e-3 * (1 + np.abs(got) + np.abs(want)))
+
+
+def test_niw_mixed_with_nich(ctx, oracle):
+    G, n, d = 21, 200, 8
+    w = synth.niw(77, G, n, d=d)
+    w2 = synth.nich(78, G, n)
+    w2["sizes"] = w["sizes"]
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    assign, scores = _niw_cuda(ctx, w, n, prior, extra=w2)
+    want = cases.oracle_scores(oracle, [w2], prior=prior)
+    oracle.niw_score_rows(w["mu"], w["kappa"], w["psi"], w["nu"], w["count"], w["sum_x"], w["sum_xxT"], w["values"][:n], want)
+    assert np.all(np.abs(scores - want) <= _niw_tol(w, want) + envelope(oracle, w2)[None, :])
+    a_orc = oracle.sample_rows(scores.copy(), w["u"][:n])
+    assert cases.explained_mismatch(scores.astype(np.float64), w["u"][:n], assign, a_orc, EPS_TIE).all()
