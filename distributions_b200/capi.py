@@ -150,7 +150,9 @@ class Context:
                                                        stream), "sample_from_scores")
 
     # -- host-buffer forms -----------------------------------------------------------------------
-    def score_sample_batch_host(self, features, columns, prior, u, want_scores=False):
+    def score_sample_batch_host(self, features, columns, prior, u, want_scores=False, assign_out=None):
+        """Host-buffer entry.  Arrays that are already page-locked (e.g. numpy views of
+        torch.Tensor.pin_memory()) are copied from directly; pageable ones are staged by the library."""
         F = len(features)
         cols = [np.ascontiguousarray(c, dtype=COLUMN_DTYPE[f.model]) for f, c in zip(features, columns)]
         n = u.shape[0]
@@ -159,7 +161,8 @@ class Context:
         ca = (c_p * F)(*[c.ctypes.data for c in cols])
         prior = None if prior is None else np.ascontiguousarray(prior, dtype=np.float32)
         u = np.ascontiguousarray(u, dtype=np.float32)
-        assign = np.empty(n, dtype=np.int32)
+        assign = assign_out if assign_out is not None else np.empty(n, dtype=np.int32)
+        assert assign.dtype == np.int32 and assign.size == n and assign.flags.c_contiguous
         scores = np.empty((n, G), dtype=np.float32) if want_scores else None
         self.check(self.L.dist_b200_score_sample_batch_host(self.h, fa, F, ca, n, _np_ptr(prior), _np_ptr(u), _np_ptr(assign),
                                                             _np_ptr(scores)), "score_sample_batch_host")

@@ -161,6 +161,8 @@ int dist_b200_ctx_create(int device, dist_b200_ctx **out) {
     e = cudaMalloc(&ctx->tables_storage, host.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->tables_storage, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         if (ctx->tables_storage) cudaFree(ctx->tables_storage);
         delete ctx;
@@ -183,6 +185,8 @@ void dist_b200_ctx_destroy(dist_b200_ctx *ctx) {
     if (ctx->scores_scratch) cudaFree(ctx->scores_scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->own_stream2) cudaStreamDestroy(ctx->own_stream2);
+    if (ctx->ev) cudaEventDestroy(ctx->ev);
     delete ctx;
 }
 
@@ -621,29 +625,80 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
     off += round_up(sizeof(int32_t) * N, 256);
     const size_t scores_off = off;
     if (scores_host) off += round_up(sizeof(float) * N * G, 256);
+    (void)in_bytes;
     int rc;
-    if ((rc = ensure_pinned(ctx, scores_host ? scores_off : off))) return rc;
+    if ((rc = ensure_pinned(ctx, scores_off))) return rc;
     if ((rc = ensure_scratch(ctx, off + 256))) return rc;
     char *pin = static_cast<char *>(ctx->pinned);
-    // the mixed-list dispatch may use the head of scratch for its own [N][G] buffer: keep ours behind it
     char *dev = static_cast<char *>(ctx->scratch_dev);
-    for (int f = 0; f < F; ++f) std::memcpy(pin + col_off[f], columns_host[f], value_bytes(features[f]) * N);
-    if (prior_host) std::memcpy(pin + prior_off, prior_host, sizeof(float) * G);
-    std::memcpy(pin + u_off, u_host, sizeof(float) * N);
-    cudaStream_t s = ctx->own_stream;
-    DISTB200_CUDA(ctx, cudaMemcpyAsync(dev, pin, in_bytes, cudaMemcpyHostToDevice, s));
+    // A caller buffer that is already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+    // is copied from / to directly; pageable buffers go through the context's pinned staging area.
+    auto is_pinned = [](const void *p) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost;
+    };
+    std::vector<char> col_pinned(F);
+    for (int f = 0; f < F; ++f) col_pinned[f] = is_pinned(columns_host[f]) ? 1 : 0;
+    const bool u_pinned = is_pinned(u_host), assign_pinned = is_pinned(assign_host);
+    const bool scores_pinned = scores_host && is_pinned(scores_host);
+
+    // Row chunks are pipelined over two streams: the H2D copy of chunk k+1 and the D2H copy of chunk
+    // k-1 overlap the kernels of chunk k (rows are independent given frozen statistics).
+    cudaStream_t st[2] = {ctx->own_stream, ctx->own_stream2};
+    const float *prior_dev = nullptr;
+    if (prior_host) {
+        std::memcpy(pin + prior_off, prior_host, sizeof(float) * G);
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(dev + prior_off, pin + prior_off, sizeof(float) * G, cudaMemcpyHostToDevice, st[0]));
+        DISTB200_CUDA(ctx, cudaEventRecord(ctx->ev, st[0]));
+        DISTB200_CUDA(ctx, cudaStreamWaitEvent(st[1], ctx->ev, 0));
+        prior_dev = reinterpret_cast<const float *>(dev + prior_off);
+    }
+    const size_t min_chunk = 32768;
+    size_t nchunks = std::min<size_t>(8, std::max<size_t>(1, N / min_chunk));
+    for (int f = 0; f < F; ++f)  // paths that materialise through the context's single scores buffer: no overlap
+        if (features[f]->model == DIST_B200_NIW || (features[f]->model == DIST_B200_DPD && F > 1)) nchunks = 1;
+    const size_t chunk = round_up((N + nchunks - 1) / nchunks, 256);
     std::vector<const void *> cols(F);
-    for (int f = 0; f < F; ++f) cols[f] = dev + col_off[f];
     float *scores_dev = scores_host ? reinterpret_cast<float *>(dev + scores_off) : nullptr;
-    rc = score_dispatch(ctx, features, F, cols.data(), N, prior_host ? reinterpret_cast<const float *>(dev + prior_off) : nullptr,
-                        reinterpret_cast<const float *>(dev + u_off), reinterpret_cast<int32_t *>(dev + assign_off),
-                        scores_dev, 0, s);
-    if (rc) return rc;
-    DISTB200_CUDA(ctx, cudaMemcpyAsync(pin + assign_off, dev + assign_off, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s));
-    if (scores_host)
-        DISTB200_CUDA(ctx, cudaMemcpyAsync(scores_host, scores_dev, sizeof(float) * N * G, cudaMemcpyDeviceToHost, s));
-    DISTB200_CUDA(ctx, cudaStreamSynchronize(s));
-    std::memcpy(assign_host, pin + assign_off, sizeof(int32_t) * N);
+    size_t k = 0;
+    for (size_t lo = 0; lo < N; lo += chunk, ++k) {
+        const size_t n = std::min(chunk, N - lo);
+        cudaStream_t s = st[k & 1];
+        for (int f = 0; f < F; ++f) {
+            const size_t vb = value_bytes(features[f]);
+            const char *src = static_cast<const char *>(columns_host[f]) + vb * lo;
+            if (!col_pinned[f]) {
+                std::memcpy(pin + col_off[f] + vb * lo, src, vb * n);
+                src = pin + col_off[f] + vb * lo;
+            }
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(dev + col_off[f] + vb * lo, src, vb * n, cudaMemcpyHostToDevice, s));
+            cols[f] = dev + col_off[f] + vb * lo;
+        }
+        {
+            const char *src = reinterpret_cast<const char *>(u_host + lo);
+            if (!u_pinned) {
+                std::memcpy(pin + u_off + 4 * lo, src, 4 * n);
+                src = pin + u_off + 4 * lo;
+            }
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(dev + u_off + 4 * lo, src, 4 * n, cudaMemcpyHostToDevice, s));
+        }
+        rc = score_dispatch(ctx, features, F, cols.data(), n, prior_dev, reinterpret_cast<const float *>(dev + u_off) + lo,
+                            reinterpret_cast<int32_t *>(dev + assign_off) + lo, scores_dev ? scores_dev + lo * G : nullptr, 0, s);
+        if (rc) return rc;
+        int32_t *adst = assign_pinned ? assign_host + lo : reinterpret_cast<int32_t *>(pin + assign_off) + lo;
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(adst, dev + assign_off + 4 * lo, 4 * n, cudaMemcpyDeviceToHost, s));
+        if (scores_host)
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(scores_host + lo * G, scores_dev + lo * G, sizeof(float) * n * G,
+                                               cudaMemcpyDeviceToHost, s));
+    }
+    (void)scores_pinned;
+    DISTB200_CUDA(ctx, cudaStreamSynchronize(st[0]));
+    DISTB200_CUDA(ctx, cudaStreamSynchronize(st[1]));
+    if (!assign_pinned) std::memcpy(assign_host, pin + assign_off, sizeof(int32_t) * N);
     return DIST_B200_OK;
 }
 

@@ -42,7 +42,8 @@ struct dist_b200_ctx {
     size_t scratch_bytes = 0;
     void *scores_scratch = nullptr;   // [N][G] buffer of the materialising dispatch paths
     size_t scores_scratch_bytes = 0;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
+    cudaEvent_t ev = nullptr;
 };
 
 struct dist_b200_feature {

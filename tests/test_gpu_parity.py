@@ -494,3 +494,21 @@ def test_niw_mixed_with_nich(ctx, oracle):
     assert np.all(np.abs(scores - want) <= _niw_tol(w, want) + envelope(oracle, w2)[None, :])
     a_orc = oracle.sample_rows(scores.copy(), w["u"][:n])
     assert cases.explained_mismatch(scores.astype(np.float64), w["u"][:n], assign, a_orc, EPS_TIE).all()
+
+
+def test_host_entry_pinned_and_chunked(ctx, oracle):
+    """host-buffer entry with page-locked caller buffers (direct copies) and enough rows to exercise
+    the two-stream chunk pipeline: identical to the device-pointer path"""
+    from distributions_b200 import capi
+    n, G = 300_000, 70
+    w = synth.nich(15, G, n)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    f = ctx.feature(capi.NICH).update_all(w)
+    a_dev, _ = run_cuda(ctx, [w], prior, w["u"], n, want_scores=False)
+    pv = torch.from_numpy(w["values"]).pin_memory()
+    pu = torch.from_numpy(w["u"]).pin_memory()
+    pa = torch.empty(n, dtype=torch.int32).pin_memory()
+    assign, _ = ctx.score_sample_batch_host([f], [pv.numpy()], prior, pu.numpy(), assign_out=pa.numpy())
+    assert np.array_equal(assign, a_dev)
+    assign2, _ = ctx.score_sample_batch_host([f], [w["values"]], prior, w["u"])  # pageable: staged
+    assert np.array_equal(assign2, a_dev)
