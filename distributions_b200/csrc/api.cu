@@ -210,6 +210,7 @@ void dist_b200_feature_destroy(dist_b200_feature *f) {
     cudaDeviceSynchronize();
     if (f->params) cudaFree(f->params);
     if (f->aux) cudaFree(f->aux);
+    if (f->gp_table) cudaFree(f->gp_table);
     if (f->keys_dev) cudaFree(f->keys_dev);
     if (f->key_rows_dev) cudaFree(f->key_rows_dev);
     if (f->niw_buf) cudaFree(f->niw_buf);
@@ -250,6 +251,7 @@ int dist_b200_gp_update_all(dist_b200_feature *f, const float shared[2], int G, 
     const uint32_t *sm = up.put(sum, G);
     if (up.err) return up.err;
     f->G = G;
+    f->gp_table_dirty = true;
     return launch_gp_prep(ctx, f->shared, 0, G, c, sm, static_cast<float4 *>(f->params), as_stream(stream));
 }
 
@@ -405,6 +407,7 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             const uint32_t *c = up.put(p, 1);
             const uint32_t *sm = up.put(p + 1, 1);
             if (up.err) return up.err;
+            f->gp_table_dirty = true;
             return launch_gp_prep(ctx, f->shared, groupid, 1, c, sm, static_cast<float4 *>(f->params), s);
         }
         case DIST_B200_BB: {
@@ -451,6 +454,7 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
     if (groupid != last)  // packed_remove: move the last group into the hole (vector.hpp:47-51)
         DISTB200_CUDA(ctx, cudaMemcpyAsync(base + gb * groupid, base + gb * last, gb, cudaMemcpyDeviceToDevice, as_stream(stream)));
     DISTB200_CUDA(ctx, cudaMemsetAsync(base + gb * last, 0, gb, as_stream(stream)));
+    f->gp_table_dirty = true;
     if (f->aux && groupid != last)
         DISTB200_CUDA(ctx, cudaMemcpyAsync(f->aux + groupid, f->aux + last, sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
     f->G = last;
@@ -495,6 +499,40 @@ int dist_b200_prior_pitman_yor(dist_b200_ctx *ctx, float alpha, float d, int G, 
 }
 
 // ---- the hot path ---------------------------------------------------------------------------
+// Describe one row-mapped feature for the score kernel.  In multi-feature lists GammaPoisson goes through
+// its per-(group, value) table (rebuilt lazily, stream-ordered, after any cache update).
+static int fill_desc(dist_b200_ctx *ctx, const dist_b200_feature *cf, const void *column, bool multi, FeatDesc &d,
+                     cudaStream_t s) {
+    dist_b200_feature *f = const_cast<dist_b200_feature *>(cf);
+    d.params = f->params;
+    d.column = column;
+    d.kind = f->model;
+    d.vdim = f->dim;
+    d.aux = nullptr;
+    if (multi && f->model == DIST_B200_GP) {
+        if (f->gp_table_cap < f->capacity) {
+            if (f->gp_table) {
+                DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+                DISTB200_CUDA(ctx, cudaFree(f->gp_table));
+                f->gp_table = nullptr;
+            }
+            DISTB200_CUDA(ctx, cudaMalloc(&f->gp_table, sizeof(float) * kGpTableX * f->capacity));
+            f->gp_table_cap = f->capacity;
+            f->gp_table_dirty = true;
+        }
+        if (f->gp_table_dirty) {
+            int rc = launch_gp_table(ctx, f->capacity, static_cast<const float4 *>(f->params), f->gp_table, s);
+            if (rc) return rc;
+            f->gp_table_dirty = false;
+        }
+        d.params = f->gp_table;
+        d.kind = kKindGpTable;
+        d.vdim = kGpTableX;
+        d.aux = f->params;
+    }
+    return DIST_B200_OK;
+}
+
 static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *features, int F,
                           const void *const *columns, size_t N, const float *prior, const float *u,
                           int32_t *assign, float *scores, int accumulate, cudaStream_t s) {
@@ -521,11 +559,8 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
         FeatList fl;
         fl.n = F;
         for (int f = 0; f < F; ++f) {
-            fl.f[f].params = features[f]->params;
-            fl.f[f].column = columns[f];
-            fl.f[f].kind = features[f]->model;
-            fl.f[f].vdim = features[f]->dim;
-            fl.f[f].pad0 = fl.f[f].pad1 = 0;
+            int rc = fill_desc(ctx, features[f], columns[f], F > 1, fl.f[f], s);
+            if (rc) return rc;
         }
         return launch_score_rows(ctx, fl, G, N, prior, u, assign, scores, accumulate, s);
     }
@@ -542,12 +577,8 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
     for (int f = 0; f < F; ++f) {
         if (solo(features[f])) continue;
         if (fl.n >= kMaxFeatures) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score: more than 512 features in one call");
-        FeatDesc &d = fl.f[fl.n++];
-        d.params = features[f]->params;
-        d.column = columns[f];
-        d.kind = features[f]->model;
-        d.vdim = features[f]->dim;
-        d.pad0 = d.pad1 = 0;
+        int rc = fill_desc(ctx, features[f], columns[f], true, fl.f[fl.n++], s);
+        if (rc) return rc;
     }
     bool started = accumulate != 0;
     int rc;

@@ -17,10 +17,14 @@ constexpr int kMaxFeatures = 512;  // feature descriptors travel in kernel-param
 struct FeatDesc {
     const void *params;  // nich/gp/bb: float4[G]; dd: float[G][vdim]; dpd: float[(V+1)][G]
     const void *column;  // value column, N entries
-    int kind;            // dist_b200_model
-    int vdim;            // dd: dim
-    int pad0, pad1;
+    int kind;            // dist_b200_model, or kKindGpTable
+    int vdim;            // dd: dim; gp table: kGpTableX
+    const void *aux;     // gp table: the float4 caches, for values >= kGpTableX
 };
+
+// internal kind: GammaPoisson scored through a per-(group, value) table for small counts
+constexpr int kKindGpTable = 6;
+constexpr int kGpTableX = 32;
 
 struct FeatList {
     int n;
@@ -64,6 +68,9 @@ struct dist_b200_feature {
     void *params = nullptr;           // hot layout (see FeatDesc::params)
     size_t params_bytes = 0;
     float *aux = nullptr;             // nich: unscaled log_coeff_ per group (capacity floats)
+    float *gp_table = nullptr;        // gp: [capacity][kGpTableX] tabulated terms for values < kGpTableX
+    int gp_table_cap = 0;
+    bool gp_table_dirty = true;
     uint32_t *keys_dev = nullptr;     // dpd sorted keys
     int *key_rows_dev = nullptr;      // dpd: table row of sorted key i
     // niw
@@ -108,6 +115,7 @@ int launch_unpack_caches(dist_b200_ctx *ctx, const dist_b200_feature *f, float *
 // score_rows.cu: rows mapped to lanes, groups looped (nich / gp / bb / small-dim dd, any F)
 int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N, const float *prior,
                       const float *u, int32_t *assign, float *scores, int accumulate, cudaStream_t s);
+int launch_gp_table(dist_b200_ctx *ctx, int n_groups, const float4 *params, float *table, cudaStream_t s);
 // gather_rows.cu: one warp per row, groups mapped to lanes (value-major tables: dpd, wide dd) and the
 // stand-alone sampler over materialised scores
 int launch_gather_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *column, size_t N,

@@ -45,7 +45,17 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 __host__ __device__ __forceinline__ int kind_stride(int kind, int vdim) {  // floats of cache per group
-    return kind == DIST_B200_DD ? vdim : 4;
+    return (kind == DIST_B200_DD || kind == kKindGpTable) ? vdim : 4;
+}
+
+// GammaPoisson term of one (value, group) cell -- the single definition shared by the direct path, the
+// table builder and the out-of-table fallback, so all three produce the same bits  (gp.cc:56-66)
+__device__ __forceinline__ float gp_term(const float4 q, uint32_t xb, const float *__restrict__ coeff,
+                                         const float *__restrict__ logfact) {
+    const float xf = static_cast<float>(xb);
+    const float lf = xb < 64 ? logfact[xb] : fast_lgamma_cell(static_cast<float>(xb + 1u), coeff);
+    const float lg = fast_lgamma_cell(q.x + xf, coeff);
+    return fmaf(q.y, xf, (q.z + lg) - lf);
 }
 
 // raw 32-bit value of row `row` of a feature column
@@ -64,17 +74,14 @@ __device__ __forceinline__ float cell_score(int kind, uint32_t xb, const float *
             const float z = __fadd_rn(1.f, __fmul_rn(q.y, __fmul_rn(d, d)));
             return fmaf(q.z, fast_log2_cell(z), q.w);  // q.z = log_coeff * ln 2
         }
-        case DIST_B200_GP: {
-            const float4 q = *reinterpret_cast<const float4 *>(p);
-            const float xf = static_cast<float>(xb);
-            const float lf = xb < 64 ? logfact[xb] : fast_lgamma_cell(static_cast<float>(xb + 1u), coeff);
-            const float lg = fast_lgamma_cell(q.x + xf, coeff);
-            return fmaf(q.y, xf, (q.z + lg) - lf);
-        }
+        case DIST_B200_GP:
+            return gp_term(*reinterpret_cast<const float4 *>(p), xb, coeff, logfact);
         case DIST_B200_BB: {
             const float2 q = *reinterpret_cast<const float2 *>(p);
             return xb ? q.x : q.y;
         }
+        case kKindGpTable:  // p points at this group's table row; out-of-table values handled by the caller
+            return p[min(xb, static_cast<uint32_t>(kGpTableX - 1))];
         default: {  // DD
             const int v = min(static_cast<int>(xb), vdim - 1);
             return p[v];
@@ -87,8 +94,28 @@ __device__ __forceinline__ float cell_score(int kind, uint32_t xb, const float *
 template <int CHUNK, bool kAssign>
 __device__ __forceinline__ void accumulate_feature(int kind, uint32_t xb, const float *__restrict__ pb, int vdim,
                                                    float (&acc)[CHUNK], const float *__restrict__ coeff,
-                                                   const float *__restrict__ logfact) {
+                                                   const float *__restrict__ logfact,
+                                                   const float4 *__restrict__ aux = nullptr) {
     switch (kind) {
+        case kKindGpTable: {
+            // tabulated GammaPoisson: one conflict-free gather per cell (lanes differ only in the value
+            // column of a 32-wide row).  Counts beyond the table take the direct formula from `aux`.
+            if (xb < static_cast<uint32_t>(kGpTableX)) {
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) {
+                    const float v = pb[j * kGpTableX + xb];
+                    acc[j] = kAssign ? v : acc[j] + v;
+                }
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < CHUNK; ++j) {
+                    const float v = gp_term(aux[j], xb, coeff, logfact);
+#pragma unroll
+                    for (int jj = 0; jj < CHUNK; ++jj)
+                        if (jj == j) acc[jj] = kAssign ? v : acc[jj] + v;
+                }
+            }
+        } break;
         case DIST_B200_NICH: {
             // score + log_coeff * fast_log(1 + precision * (v - mean)^2)   (nich.cc:59-65)
             const float4 *p4 = reinterpret_cast<const float4 *>(pb);
@@ -105,13 +132,9 @@ __device__ __forceinline__ void accumulate_feature(int kind, uint32_t xb, const 
         case DIST_B200_GP: {
             // score + fast_lgamma(post_alpha + v) - fast_log_factorial(v) + score_coeff * v  (gp.cc:56-66)
             const float4 *p4 = reinterpret_cast<const float4 *>(pb);
-            const float xf = static_cast<float>(xb);
-            const float lf = xb < 64 ? logfact[xb] : fast_lgamma_cell(static_cast<float>(xb + 1u), coeff);
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j) {
-                const float4 q = p4[j];
-                const float lg = fast_lgamma_cell(q.x + xf, coeff);
-                const float v = fmaf(q.y, xf, (q.z + lg) - lf);
+                const float v = gp_term(p4[j], xb, coeff, logfact);
                 acc[j] = kAssign ? v : acc[j] + v;
             }
         } break;
@@ -281,7 +304,8 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                         __syncthreads();
                         pb = caches + (f & 1) * a.stage_floats;
                     }
-                    accumulate_feature<CHUNK, false>(fd.kind, xb, pb, fd.vdim, acc, coeff, logfact);
+                    accumulate_feature<CHUNK, false>(fd.kind, xb, pb, fd.vdim, acc, coeff, logfact,
+                                                     static_cast<const float4 *>(fd.aux) + g0);
                     if (!resident) __syncthreads();  // buffer (f&1) is rewritten two features from now
                     xb = xn;
                 }
@@ -405,10 +429,14 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                     float s = prior_s[g];
                     for (int f = 0; f < F; ++f) {
                         const FeatDesc &fd = feats.f[f];
-                        s += cell_score(fd.kind, load_value(fd.kind, fd.column, row),
-                                        static_cast<const float *>(fd.params) +
-                                            static_cast<size_t>(g) * kind_stride(fd.kind, fd.vdim),
-                                        fd.vdim, coeff, logfact);
+                        const uint32_t xv = load_value(fd.kind, fd.column, row);
+                        if (fd.kind == kKindGpTable && xv >= static_cast<uint32_t>(kGpTableX))
+                            s += gp_term(static_cast<const float4 *>(fd.aux)[g], xv, coeff, logfact);
+                        else
+                            s += cell_score(fd.kind, xv,
+                                            static_cast<const float *>(fd.params) +
+                                                static_cast<size_t>(g) * kind_stride(fd.kind, fd.vdim),
+                                            fd.vdim, coeff, logfact);
                     }
                     t -= mufu_ex2(fmaf(s, kLog2e, nmax));
                     if (t <= 0.f) {
@@ -421,6 +449,30 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
         }
         if (kSample && valid) a.assign[row] = result;
     }  // row tiles
+}
+
+// table[g][x] = GammaPoisson term of value x for group g, x < kGpTableX: built with gp_term itself (this
+// translation unit, same flags) so the tabulated and the direct path agree bit for bit
+__global__ void gp_table_kernel(int n_groups, const float4 *__restrict__ params, float *__restrict__ table,
+                                NumericTables t) {
+    __shared__ __align__(16) float coeff[33 * kLgammaRowStride];
+    __shared__ float logfact[64];
+    for (int i = threadIdx.x; i < 33 * kLgammaRowStride; i += blockDim.x) coeff[i] = t.lgamma5[i];
+    if (threadIdx.x < 64) logfact[threadIdx.x] = t.log_factorial[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_groups * kGpTableX) return;
+    const int g = i / kGpTableX, x = i % kGpTableX;
+    table[i] = gp_term(params[g], static_cast<uint32_t>(x), coeff, logfact);
+}
+
+int launch_gp_table(dist_b200_ctx *ctx, int n_groups, const float4 *params, float *table, cudaStream_t s) {
+    if (n_groups <= 0) return DIST_B200_OK;
+    const int n = n_groups * kGpTableX;
+    gp_table_kernel<<<(n + 255) / 256, 256, 0, s>>>(n_groups, params, table, ctx->tables);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("gp_table launch: ") + cudaGetErrorString(e));
+    return DIST_B200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -512,3 +512,25 @@ def test_host_entry_pinned_and_chunked(ctx, oracle):
     assert np.array_equal(assign, a_dev)
     assign2, _ = ctx.score_sample_batch_host([f], [w["values"]], prior, w["u"])  # pageable: staged
     assert np.array_equal(assign2, a_dev)
+
+
+def test_crosscat_gp_table_and_fallback(ctx, oracle):
+    """multi-feature lists score GammaPoisson through the per-(group, value) table; counts beyond the
+    table (>= 32, >= 64) take the direct formula -- both must equal the oracle"""
+    G, n = 45, 400
+    cc = synth.crosscat(640, G, n, n_gp=5, n_bb=2)
+    feats = cc["features"]
+    for k, w in enumerate(feats[:5]):
+        w["values"][k::7] = [31, 32, 33, 63, 64, 65, 200, 5000][k % 8]
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, cc["sizes"])
+    assign, scores = run_cuda(ctx, feats, prior, cc["u"], n)
+    want = cases.oracle_scores(oracle, feats, prior=prior)
+    env = sum(envelope(oracle, w) for w in feats)[None, :]
+    assert np.all(np.abs(scores - want) <= 5e-6 * (1 + np.abs(want)) + env)
+    a_orc = oracle.sample_rows(scores.copy(), cc["u"])
+    assert cases.explained_mismatch(scores.astype(np.float64), cc["u"], assign, a_orc, EPS_TIE).all()
+    # the single-feature (direct) kernel and the table path agree bit for bit on one feature
+    _, s_direct = run_cuda(ctx, [feats[0]], None, cc["u"], n, sample=False)
+    _, s_both = run_cuda(ctx, [feats[0], feats[5]], None, cc["u"], n, sample=False)
+    _, s_bb = run_cuda(ctx, [feats[5]], None, cc["u"], n, sample=False)
+    assert np.array_equal(s_both, s_direct + s_bb)
