@@ -30,13 +30,17 @@
 
 namespace distb200 {
 
-constexpr int kThreads = 256;
 constexpr int kSlots = 16;
+constexpr int kStages = 3;  // cp.async ring depth of the streaming mode
 constexpr size_t kResidentBudget = 96 * 1024;  // bytes of group caches kept resident in smem
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -172,9 +176,10 @@ struct RowsArgs {
     NumericTables t;
 };
 
-template <int CHUNK, int KIND, bool kSample, bool kScores>
-__global__ void __launch_bounds__(kThreads)
+template <int CHUNK, int KIND, bool kSample, bool kScores, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : (CHUNK <= 32 ? 3 : (CHUNK <= 64 ? 2 : 1)))
 score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
+    constexpr int kThreads = THREADS;  // block size of this instantiation
     extern __shared__ __align__(16) float smem[];
     // layout: coeff[33*8] | logfact[64] | prior[Gpad] | tile[8 warps][32][33] (kScores) |
     //         slots[kSlots][kThreads] float2 (kSample, multi-tile) | caches
@@ -253,11 +258,25 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
             // group offset of this thread's tile: uniform in the main pass, per lane when finalising
             int g0 = it * CHUNK;
             if (fin) g0 = min((sel * chunks_per_slot + (it - nchunks)) * CHUNK, Gpad - CHUNK);
-            if (!resident) {  // stage feature 0 of this tile (buffer 0 was released by the last sync)
-                const int st = kind_stride(feats.f[0].kind, feats.f[0].vdim);
-                const float *src = static_cast<const float *>(feats.f[0].params) + static_cast<size_t>(g0) * st;
-                for (int i = tid * 4; i < CHUNK * st; i += kThreads * 4) cp_async16(caches + i, src + i);
-                cp_async_commit();
+            // streaming mode: a kStages-deep cp.async ring; stage (f % kStages) holds feature f's caches for
+            // this tile of groups followed by this block's row values of feature f (one word per thread),
+            // so both arrive kStages-1 features ahead of their use
+            const int ring_floats = a.stage_floats + kThreads;
+            auto issue = [&](int f) {
+                const FeatDesc &fd = feats.f[f];
+                const int st = kind_stride(fd.kind, fd.vdim);
+                const float *src = static_cast<const float *>(fd.params) + static_cast<size_t>(g0) * st;
+                float *dst = caches + (f % kStages) * ring_floats;
+                for (int i = tid * 4; i < CHUNK * st; i += kThreads * 4) cp_async16(dst + i, src + i);
+                const char *xp = static_cast<const char *>(fd.column) + (fd.kind == DIST_B200_BB ? row : 4 * row);
+                cp_async4(dst + a.stage_floats + tid, reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(xp) & ~uintptr_t(3)));
+            };
+            if (!resident) {
+#pragma unroll
+                for (int f = 0; f < kStages - 1; ++f) {
+                    if (f < F) issue(f);
+                    cp_async_commit();
+                }
             }
 
             float acc[CHUNK];
@@ -278,37 +297,36 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                 accumulate_feature<CHUNK, true>(KIND, xb, caches + static_cast<size_t>(g0) * kind_stride(KIND, vdim), vdim,
                                                 acc, coeff, logfact);
             } else {
-                uint32_t xb = load_value(feats.f[0].kind, feats.f[0].column, row);
+                uint32_t xb = resident ? load_value(feats.f[0].kind, feats.f[0].column, row) : 0u;
                 size_t res_off = 0;
                 for (int f = 0; f < F; ++f) {
                     const FeatDesc &fd = feats.f[f];
                     const int st = kind_stride(fd.kind, fd.vdim);
                     uint32_t xn = 0;
-                    if (f + 1 < F) xn = load_value(feats.f[f + 1].kind, feats.f[f + 1].column, row);
                     const float *pb;
                     if (resident) {
+                        if (f + 1 < F) xn = load_value(feats.f[f + 1].kind, feats.f[f + 1].column, row);
                         pb = caches + res_off + static_cast<size_t>(g0) * st;
                         res_off += static_cast<size_t>(Gpad) * st;
                     } else {
-                        if (f + 1 < F) {  // prefetch the next feature's caches behind this feature's math
-                            const FeatDesc &fn = feats.f[f + 1];
-                            const int sn = kind_stride(fn.kind, fn.vdim);
-                            const float *src = static_cast<const float *>(fn.params) + static_cast<size_t>(g0) * sn;
-                            float *dst = caches + ((f + 1) & 1) * a.stage_floats;
-                            for (int i = tid * 4; i < CHUNK * sn; i += kThreads * 4) cp_async16(dst + i, src + i);
-                            cp_async_commit();
-                            cp_async_wait<1>();
+                        cp_async_wait<kStages - 2>();  // this thread's copies of feature f have landed
+                        __syncthreads();               // ... everyone's have, and stage (f-1) % kStages is free
+                        if (f + kStages - 1 < F) issue(f + kStages - 1);
+                        cp_async_commit();
+                        pb = caches + (f % kStages) * ring_floats;
+                        const uint32_t word = reinterpret_cast<const uint32_t *>(pb + a.stage_floats)[tid];
+                        if (fd.kind == DIST_B200_BB) {
+                            const uintptr_t addr = reinterpret_cast<uintptr_t>(fd.column) + row;
+                            xb = (word >> (8 * (addr & 3))) & 0xffu;
                         } else {
-                            cp_async_wait<0>();
+                            xb = word;
                         }
-                        __syncthreads();
-                        pb = caches + (f & 1) * a.stage_floats;
                     }
                     accumulate_feature<CHUNK, false>(fd.kind, xb, pb, fd.vdim, acc, coeff, logfact,
                                                      static_cast<const float4 *>(fd.aux) + g0);
-                    if (!resident) __syncthreads();  // buffer (f&1) is rewritten two features from now
-                    xb = xn;
+                    if (resident) xb = xn;
                 }
+                if (!resident) __syncthreads();  // the ring is refilled by the next tile's prologue
             }
 
             if (g0 + CHUNK > G) {
@@ -478,6 +496,9 @@ int launch_gp_table(dist_b200_ctx *ctx, int n_groups, const float4 *params, floa
 // ---------------------------------------------------------------------------------------------
 template <int CHUNK, int KIND, bool kSample, bool kScores>
 static int launch_variant(dist_b200_ctx *ctx, const FeatList &feats, RowsArgs a, cudaStream_t s) {
+    // the cross-cat kernel at the widest register tile runs 128-thread blocks, three per SM (12 warps);
+    // everything else 256-thread blocks
+    constexpr int kThreads = (KIND < 0 && CHUNK == 128) ? 128 : 256;
     const int G = a.G;
     const int nchunks = (G + CHUNK - 1) / CHUNK;
     const int Gpad = nchunks * CHUNK;
@@ -494,9 +515,9 @@ static int launch_variant(dist_b200_ctx *ctx, const FeatList &feats, RowsArgs a,
     a.resident = cache_floats * sizeof(float) <= kResidentBudget ? 1 : 0;
     if (KIND >= 0 && !a.resident) return DIST_B200_ERR_UNSUPPORTED;  // caller falls back to the generic kernel
     a.stage_floats = CHUNK * max_stride;
-    const size_t smem = fixed + (a.resident ? cache_floats : 2 * static_cast<size_t>(a.stage_floats)) * sizeof(float);
+    const size_t smem = fixed + (a.resident ? cache_floats : kStages * (static_cast<size_t>(a.stage_floats) + kThreads)) * sizeof(float);
     if (smem > 227 * 1024) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_rows: group caches exceed shared memory");
-    auto kern = score_rows_kernel<CHUNK, KIND, kSample, kScores>;
+    auto kern = score_rows_kernel<CHUNK, KIND, kSample, kScores, kThreads>;
     DISTB200_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
     DISTB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
