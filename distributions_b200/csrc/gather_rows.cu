@@ -117,8 +117,107 @@ __global__ void __launch_bounds__(kGatherThreadsMax) gather_rows_kernel(const Ga
     }
 }
 
+// Register-tiled form for G <= 32 * K (K = 1..32 cells per lane, compile time): the row is held striped
+// in registers (g = 32 k + lane) through max / exp / sum with fully unrolled loops; only the likelihoods
+// cross shared memory once (skewed, conflict-free both ways) so that each lane can sum a CONTIGUOUS
+// segment; the segment holding u * total is then resolved by a K-lane prefix scan instead of a serial
+// walk.  Sampling only (the materialising variants stay on the generic kernel above).
+constexpr int kFastWarps = 8;
+
+template <int K>
+__global__ void __launch_bounds__(kFastWarps * 32) gather_rows_fast_kernel(const GatherArgs a) {
+    __shared__ float lik_all[kFastWarps][33 * K + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = a.G;
+    float *lik = lik_all[warp];
+    float prior[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int g = 32 * k + lane;
+        prior[k] = (a.table && a.prior && g < G) ? a.prior[g] : 0.f;
+    }
+    // this lane's contiguous segment [lane*K, lane*K + K) in skewed coordinates
+    const unsigned full = 0xffffffffu;
+    for (size_t n = static_cast<size_t>(blockIdx.x) * kFastWarps + warp; n < a.N;
+         n += static_cast<size_t>(gridDim.x) * kFastWarps) {
+        const float *src = a.table ? a.table + static_cast<size_t>(table_row(a, a.values[n])) * G
+                                   : a.scores_in + n * G;
+        float s[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int g = 32 * k + lane;
+            s[k] = g < G ? src[g] + prior[k] : -INFINITY;   // prior + (scores_[v][g] - shift[g])
+        }
+        float m = s[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) m = fmaxf(m, s[k]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(full, m, o));
+        const float nm = -m * kLog2e;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) lik[33 * k + lane] = mufu_ex2(fmaf(s[k], kLog2e, nm));  // skew(32k + lane)
+        __syncwarp();
+        float part = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+            const int i = lane * K + kk;
+            part += lik[i + (i >> 5)];
+        }
+        float incl = part;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const float total = __shfl_sync(full, incl, 31);
+        const float t0 = total * a.u[n];
+        const unsigned hit = __ballot_sync(full, incl >= t0 && lane * K < G);
+        int idx = G - 1;
+        if (hit) {
+            const int owner = __ffs(hit) - 1;
+            const float resid = t0 - __shfl_sync(full, incl - part, owner);  // draw left inside the segment
+            // K-lane inclusive scan over the owner's segment: first element reaching the residual
+            const int i = owner * K + (lane < K ? lane : K - 1);
+            float c = (lane < K && i < G) ? lik[i + (i >> 5)] : 0.f;
+#pragma unroll
+            for (int o = 1; o < K; o <<= 1) {
+                const float v = __shfl_up_sync(full, c, o);
+                if (lane >= o) c += v;
+            }
+            const unsigned h2 = __ballot_sync(full, lane < K && c >= resid);
+            const int last = min(G, owner * K + K) - 1;
+            idx = h2 ? min(owner * K + __ffs(h2) - 1, last) : last;
+        }
+        if (lane == 0) a.assign[n] = idx;
+    }
+}
+
+template <int K>
+static int launch_gather_fast(dist_b200_ctx *ctx, const GatherArgs &a, cudaStream_t s) {
+    auto kern = gather_rows_fast_kernel<K>;
+    int per_sm = 0;
+    DISTB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFastWarps * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    const size_t want = (a.N + kFastWarps - 1) / kFastWarps;
+    const size_t cap = static_cast<size_t>(ctx->sm_count) * per_sm;
+    kern<<<static_cast<unsigned>(want < cap ? want : cap), kFastWarps * 32, 0, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("gather_rows_fast launch: ") + cudaGetErrorString(e));
+    return DIST_B200_OK;
+}
+
 static int launch_gather(dist_b200_ctx *ctx, const GatherArgs &a, cudaStream_t s) {
     if (a.N == 0 || a.G == 0) return DIST_B200_OK;
+    if (a.assign && !a.scores_out && !a.accumulate && a.G <= 1024) {
+        const int k = (a.G + 31) / 32;
+        if (k <= 1) return launch_gather_fast<1>(ctx, a, s);
+        if (k <= 2) return launch_gather_fast<2>(ctx, a, s);
+        if (k <= 4) return launch_gather_fast<4>(ctx, a, s);
+        if (k <= 8) return launch_gather_fast<8>(ctx, a, s);
+        if (k <= 16) return launch_gather_fast<16>(ctx, a, s);
+        return launch_gather_fast<32>(ctx, a, s);
+    }
     const int seg = (a.G + 31) / 32;
     const size_t row_bytes = sizeof(float) * (static_cast<size_t>(32 * seg) + seg + 1);
     int threads = kGatherThreadsMax;
