@@ -39,6 +39,7 @@ SIGNATURES = {
     "dist_b200_feature_remove_group": (c_i, [c_p, c_i, c_p]),
     "dist_b200_feature_download_caches": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
     "dist_b200_prior_pitman_yor": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
+    "dist_b200_prior_pitman_yor_host": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p]),
     "dist_b200_score_batch": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_i, c_p]),
     "dist_b200_score_sample_batch": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_p, c_p, c_p]),
     "dist_b200_sample_from_scores": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p, c_p]),

@@ -126,6 +126,22 @@ struct Upload {
 
 bool check_feature(const dist_b200_feature *f, int model) { return f && f->ctx && f->model == model; }
 
+// cache mutations are asynchronous on the caller's stream: mark their completion ...
+int mark_ready(dist_b200_feature *f, int rc, cudaStream_t s) {
+    if (rc != DIST_B200_OK) return rc;
+    DISTB200_CUDA(f->ctx, cudaEventRecord(f->ready, s));
+    // the statistics were staged through the context's scratch buffer: drain the stream so the next
+    // host-side upload (possibly on another stream) cannot overwrite it under the prep kernel
+    DISTB200_CUDA(f->ctx, cudaStreamSynchronize(s));
+    return DIST_B200_OK;
+}
+// ... and make a scoring stream wait for them (no-op when it is the same stream)
+int wait_ready(dist_b200_ctx *ctx, const dist_b200_feature *const *features, int F, cudaStream_t s) {
+    for (int f = 0; f < F; ++f)
+        if (features[f] && features[f]->ready) DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, features[f]->ready, 0));
+    return DIST_B200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -201,6 +217,10 @@ int dist_b200_feature_create(dist_b200_ctx *ctx, int model, dist_b200_feature **
     if (!f) return fail(ctx, DIST_B200_ERR_CUDA, "out of host memory");
     f->ctx = ctx;
     f->model = model;
+    if (cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming) != cudaSuccess) {
+        delete f;
+        return fail(ctx, DIST_B200_ERR_CUDA, "cudaEventCreate failed");
+    }
     *out = f;
     return DIST_B200_OK;
 }
@@ -214,6 +234,7 @@ void dist_b200_feature_destroy(dist_b200_feature *f) {
     if (f->keys_dev) cudaFree(f->keys_dev);
     if (f->key_rows_dev) cudaFree(f->key_rows_dev);
     if (f->niw_buf) cudaFree(f->niw_buf);
+    if (f->ready) cudaEventDestroy(f->ready);
     delete f;
 }
 
@@ -234,7 +255,7 @@ int dist_b200_nich_update_all(dist_b200_feature *f, const float shared[4], int G
     const float *v = up.put(ctv, G);
     if (up.err) return up.err;
     f->G = G;
-    return launch_nich_prep(ctx, f->shared, G, 0, G, c, m, v, static_cast<float4 *>(f->params), f->aux, as_stream(stream));
+    return mark_ready(f, launch_nich_prep(ctx, f->shared, G, 0, G, c, m, v, static_cast<float4 *>(f->params), f->aux, as_stream(stream)), as_stream(stream));
 }
 
 int dist_b200_gp_update_all(dist_b200_feature *f, const float shared[2], int G, const uint32_t *count,
@@ -252,7 +273,7 @@ int dist_b200_gp_update_all(dist_b200_feature *f, const float shared[2], int G, 
     if (up.err) return up.err;
     f->G = G;
     f->gp_table_dirty = true;
-    return launch_gp_prep(ctx, f->shared, 0, G, c, sm, static_cast<float4 *>(f->params), as_stream(stream));
+    return mark_ready(f, launch_gp_prep(ctx, f->shared, 0, G, c, sm, static_cast<float4 *>(f->params), as_stream(stream)), as_stream(stream));
 }
 
 int dist_b200_bb_update_all(dist_b200_feature *f, const float shared[2], int G, const int32_t *heads,
@@ -269,7 +290,7 @@ int dist_b200_bb_update_all(dist_b200_feature *f, const float shared[2], int G, 
     const int32_t *t = up.put(tails, G);
     if (up.err) return up.err;
     f->G = G;
-    return launch_bb_prep(ctx, f->shared, 0, G, h, t, static_cast<float4 *>(f->params), as_stream(stream));
+    return mark_ready(f, launch_bb_prep(ctx, f->shared, 0, G, h, t, static_cast<float4 *>(f->params), as_stream(stream)), as_stream(stream));
 }
 
 int dist_b200_dd_update_all(dist_b200_feature *f, int dim, const float *alphas, int G, const int32_t *counts,
@@ -299,7 +320,7 @@ int dist_b200_dd_update_all(dist_b200_feature *f, int dim, const float *alphas, 
     const int32_t *c = up.put(counts, static_cast<size_t>(G) * dim);
     if (up.err) return up.err;
     f->G = G;
-    return launch_dd_prep(ctx, dim, a, alpha_sum, 0, G, c, static_cast<float *>(f->params), as_stream(stream));
+    return mark_ready(f, launch_dd_prep(ctx, dim, a, alpha_sum, 0, G, c, static_cast<float *>(f->params), as_stream(stream)), as_stream(stream));
 }
 
 int dist_b200_dpd_update_all(dist_b200_feature *f, float alpha, float beta0, int V, const uint32_t *keys,
@@ -344,7 +365,7 @@ int dist_b200_dpd_update_all(dist_b200_feature *f, float alpha, float beta0, int
     const int32_t *c = up.put(counts, static_cast<size_t>(G) * V);
     if (up.err) return up.err;
     f->G = G;
-    return launch_dpd_prep(ctx, alpha, beta0, V, b, G, c, static_cast<float *>(f->params), as_stream(stream));
+    return mark_ready(f, launch_dpd_prep(ctx, alpha, beta0, V, b, G, c, static_cast<float *>(f->params), as_stream(stream)), as_stream(stream));
 }
 
 int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float kappa, const float *psi,
@@ -382,7 +403,7 @@ int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float
     f->G = G;
     f->kappa = kappa;
     f->nu = nu;
-    return launch_niw_prep(ctx, d, mu_d, kappa, psi_d, nu, G, cnt_d, sx_d, sxx_d, f->niw_buf, as_stream(stream));
+    return mark_ready(f, launch_niw_prep(ctx, d, mu_d, kappa, psi_d, nu, G, cnt_d, sx_d, sxx_d, f->niw_buf, as_stream(stream)), as_stream(stream));
 }
 
 int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void *stats, void *stream) {
@@ -392,6 +413,7 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
     int rc = ensure_scratch(ctx, 4096 + sizeof(int32_t) * 256);
     if (rc) return rc;
     cudaStream_t s = as_stream(stream);
+    DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
     Upload up{ctx, s};
     switch (f->model) {
         case DIST_B200_NICH: {
@@ -400,7 +422,7 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             const float *m = up.put(reinterpret_cast<const float *>(p + 4), 1);
             const float *v = up.put(reinterpret_cast<const float *>(p + 8), 1);
             if (up.err) return up.err;
-            return launch_nich_prep(ctx, f->shared, f->G, groupid, 1, c, m, v, static_cast<float4 *>(f->params), f->aux, s);
+            return mark_ready(f, launch_nich_prep(ctx, f->shared, f->G, groupid, 1, c, m, v, static_cast<float4 *>(f->params), f->aux, s), s);
         }
         case DIST_B200_GP: {
             const uint32_t *p = static_cast<const uint32_t *>(stats);
@@ -408,20 +430,20 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             const uint32_t *sm = up.put(p + 1, 1);
             if (up.err) return up.err;
             f->gp_table_dirty = true;
-            return launch_gp_prep(ctx, f->shared, groupid, 1, c, sm, static_cast<float4 *>(f->params), s);
+            return mark_ready(f, launch_gp_prep(ctx, f->shared, groupid, 1, c, sm, static_cast<float4 *>(f->params), s), s);
         }
         case DIST_B200_BB: {
             const int32_t *p = static_cast<const int32_t *>(stats);
             const int32_t *h = up.put(p, 1);
             const int32_t *t = up.put(p + 1, 1);
             if (up.err) return up.err;
-            return launch_bb_prep(ctx, f->shared, groupid, 1, h, t, static_cast<float4 *>(f->params), s);
+            return mark_ready(f, launch_bb_prep(ctx, f->shared, groupid, 1, h, t, static_cast<float4 *>(f->params), s), s);
         }
         case DIST_B200_DD: {
             const float *a = up.put(f->alphas.data(), f->dim);
             const int32_t *c = up.put(static_cast<const int32_t *>(stats), f->dim);
             if (up.err) return up.err;
-            return launch_dd_prep(ctx, f->dim, a, f->alpha_sum, groupid, 1, c, static_cast<float *>(f->params), s);
+            return mark_ready(f, launch_dd_prep(ctx, f->dim, a, f->alpha_sum, groupid, 1, c, static_cast<float *>(f->params), s), s);
         }
         default:
             return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "update_group: use update_all for this model");
@@ -458,7 +480,7 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
     if (f->aux && groupid != last)
         DISTB200_CUDA(ctx, cudaMemcpyAsync(f->aux + groupid, f->aux + last, sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
     f->G = last;
-    return DIST_B200_OK;
+    return mark_ready(f, DIST_B200_OK, as_stream(stream));
 }
 
 int dist_b200_feature_download_caches(const dist_b200_feature *f, float *out_host, size_t capacity_floats,
@@ -495,7 +517,26 @@ int dist_b200_prior_pitman_yor(dist_b200_ctx *ctx, float alpha, float d, int G, 
     Upload up{ctx, as_stream(stream)};
     const int32_t *sz = up.put(group_sizes, G);
     if (up.err) return up.err;
-    return launch_prior_prep(ctx, alpha, d, G, sz, prior_dev, as_stream(stream));
+    int rc2 = launch_prior_prep(ctx, alpha, d, G, sz, prior_dev, as_stream(stream));
+    if (rc2) return rc2;
+    DISTB200_CUDA(ctx, cudaStreamSynchronize(as_stream(stream)));  // scratch (group sizes) is free again
+    return DIST_B200_OK;
+}
+
+int dist_b200_prior_pitman_yor_host(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *group_sizes,
+                                    float *prior_host) {
+    if (!ctx || G < 1 || !group_sizes || !prior_host) return DIST_B200_ERR_INVALID;
+    int rc = ensure_scratch(ctx, round_up(sizeof(int32_t) * G, 256) + sizeof(float) * G + 256);
+    if (rc) return rc;
+    cudaStream_t s = ctx->own_stream;
+    Upload up{ctx, s};
+    const int32_t *sz = up.put(group_sizes, G);
+    if (up.err) return up.err;
+    float *out = reinterpret_cast<float *>(static_cast<char *>(ctx->scratch_dev) + up.off);
+    if ((rc = launch_prior_prep(ctx, alpha, d, G, sz, out, s))) return rc;
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(prior_host, out, sizeof(float) * G, cudaMemcpyDeviceToHost, s));
+    DISTB200_CUDA(ctx, cudaStreamSynchronize(s));
+    return DIST_B200_OK;
 }
 
 // ---- the hot path ---------------------------------------------------------------------------
@@ -548,6 +589,10 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
         if (features[f]->G != G) return fail(ctx, DIST_B200_ERR_STATE, "score: features disagree on the number of groups");
     }
     if (N == 0) return DIST_B200_OK;
+    {
+        int rcw = wait_ready(ctx, features, F, s);
+        if (rcw) return rcw;
+    }
     // Row-mapped models (nich/gp/bb/dd) fuse into one launch.  dpd (value-major table, warp per row) and
     // niw (dense contraction) have their own kernels: alone they run directly, in mixed lists the scores
     // are materialised, every feature accumulates, and the stand-alone sampler finishes.
@@ -680,6 +725,7 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
     // Row chunks are pipelined over two streams: the H2D copy of chunk k+1 and the D2H copy of chunk
     // k-1 overlap the kernels of chunk k (rows are independent given frozen statistics).
     cudaStream_t st[2] = {ctx->own_stream, ctx->own_stream2};
+    if ((rc = wait_ready(ctx, features, F, st[0])) || (rc = wait_ready(ctx, features, F, st[1]))) return rc;
     const float *prior_dev = nullptr;
     if (prior_host) {
         std::memcpy(pin + prior_off, prior_host, sizeof(float) * G);
@@ -744,6 +790,7 @@ int dist_b200_score_value_host(dist_b200_ctx *ctx, const dist_b200_feature *feat
     char *dev = static_cast<char *>(ctx->scratch_dev);
     float *sc = reinterpret_cast<float *>(dev + round_up(vb, 256));
     cudaStream_t s = ctx->own_stream;
+    if ((rc = wait_ready(ctx, &feature, 1, s))) return rc;
     DISTB200_CUDA(ctx, cudaMemcpyAsync(dev, value_host, vb, cudaMemcpyHostToDevice, s));
     DISTB200_CUDA(ctx, cudaMemcpyAsync(sc, scores_accum_host, sizeof(float) * G, cudaMemcpyHostToDevice, s));
     const void *col = dev;

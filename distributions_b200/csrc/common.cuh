@@ -71,6 +71,7 @@ struct dist_b200_feature {
     float *gp_table = nullptr;        // gp: [capacity][kGpTableX] tabulated terms for values < kGpTableX
     int gp_table_cap = 0;
     bool gp_table_dirty = true;
+    cudaEvent_t ready = nullptr;      // recorded after every cache mutation; scoring streams wait on it
     uint32_t *keys_dev = nullptr;     // dpd sorted keys
     int *key_rows_dev = nullptr;      // dpd: table row of sorted key i
     // niw

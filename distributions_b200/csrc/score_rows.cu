@@ -183,7 +183,10 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     extern __shared__ __align__(16) float smem[];
     // layout: coeff[33*8] | logfact[64] | prior[Gpad] | tile[8 warps][32][33] (kScores) |
     //         slots[kSlots][kThreads] float2 (kSample, multi-tile) | caches
-    constexpr bool kSingle = KIND >= 0;  // one feature of a known model; caches resident, prior folded in
+    constexpr bool kSingle = KIND >= 0;  // one feature of a known model; caches resident
+    // prior folded into the resident caches (first feature ASSIGNS): not for gp, whose score[g] cancels
+    // against lgamma(post_alpha + v) -- adding the prior before that cancellation would cost ~1e-5
+    constexpr bool kFold = kSingle && KIND != DIST_B200_GP;
     const int G = a.G;
     const int nchunks = (G + CHUNK - 1) / CHUNK;
     const int Gpad = nchunks * CHUNK;
@@ -219,7 +222,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
         cp_async_wait<0>();
     }
     __syncthreads();
-    if (kSingle) {
+    if (kFold) {
         // fold the prior into this block's private copy of the caches: the first (only) feature then
         // ASSIGNS prior + term in one FFMA instead of seeding accumulators and adding
         const int vdim = feats.f[0].vdim;
@@ -280,7 +283,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
             }
 
             float acc[CHUNK];
-            if (!kSingle) {
+            if (!kFold) {
 #pragma unroll
                 for (int j = 0; j < CHUNK; j += 4) {
                     const float4 p = *reinterpret_cast<const float4 *>(prior_s + g0 + j);
@@ -294,8 +297,8 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
             if (kSingle) {
                 const uint32_t xb = load_value(KIND, feats.f[0].column, row);
                 const int vdim = feats.f[0].vdim;
-                accumulate_feature<CHUNK, true>(KIND, xb, caches + static_cast<size_t>(g0) * kind_stride(KIND, vdim), vdim,
-                                                acc, coeff, logfact);
+                accumulate_feature<CHUNK, kFold>(KIND, xb, caches + static_cast<size_t>(g0) * kind_stride(KIND, vdim), vdim,
+                                                 acc, coeff, logfact);
             } else {
                 uint32_t xb = resident ? load_value(feats.f[0].kind, feats.f[0].column, row) : 0u;
                 size_t res_off = 0;

@@ -129,6 +129,11 @@ int dist_b200_feature_download_caches(const dist_b200_feature *f, float *out_hos
 int dist_b200_prior_pitman_yor(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *group_sizes,
                                float *prior_dev, void *stream);
 
+/* Same with a HOST result buffer: the per-value CachedMixture::score_value(model, scores) drop-in
+ * (clustering.hpp:195-208; overwrites prior_host[0..G)). */
+int dist_b200_prior_pitman_yor_host(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *group_sizes,
+                                    float *prior_host);
+
 /* ---- the hot path -----------------------------------------------------------------------------
  * columns_dev[f] is feature f's value column for the N rows, typed per model (see
  * dist_b200_model); feature-major storage, i.e. one contiguous array per feature.

@@ -1,0 +1,386 @@
+// distributions_b200/mixture.hpp -- host-side C++ mirror of the reference's Shared / Group / Mixture
+// interface for the mixture-scoring hot path, on top of the C-ABI (dist_b200.h).
+//
+// What is mirrored (paths relative to /root/reference):
+//   MixtureSlave<Model, DataScorer, ValueScorer>            include/distributions/mixture.hpp:340-450
+//     groups(), init, add_group, remove_group, add_value, remove_value, score_value (ACCUMULATES into
+//     the caller's buffer), score_value_group                (same names, argument meaning, order)
+//   Model::Shared / Model::Group {init, add_value, remove_value}
+//     NormalInverseChiSq  models/nich.hpp:52-165      GammaPoisson   models/gp.hpp:52-135
+//     BetaBernoulli       models/bb.hpp:52-122        DirichletDiscrete<max_dim>  models/dd.hpp:55-149
+//   Clustering<int>::PitmanYor::Mixture (CachedMixture over MixtureDriver)
+//                                                            clustering.hpp:126-234, mixture.hpp:48-163
+//     counts(), empty_groupids(), sample_size(), init, add_value / remove_value (return whether a group
+//     was added / removed), score_value (OVERWRITES the caller's buffer)
+// What is new: Mixture::score_values / CrossCat::score_sample_values -- the batched entry that scores
+// N rows against frozen statistics and samples a group per row.
+//
+// Group statistics live and mutate on the host exactly as in the reference (integer / float
+// bookkeeping); every score -- per value or batched -- is computed by the sm_100a
+// kernels behind the C-ABI.  There is no CPU scoring path here: a failed C-ABI call throws
+// std::runtime_error (the reference's DIST_THROW_ON_ERROR behaviour, common.hpp:49-67).
+// Not mirrored (off the path): Sampler, sample_value, score_data, protobuf, Group::merge, gp log_prod.
+#pragma once
+
+#include <dist_b200.h>
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_set>
+#include <utility>
+#include <vector>
+
+namespace distributions_b200 {
+
+// borrowed (pointer, size) view, the reference's AlignedFloats (vector.hpp:63-90) without the
+// 32-byte alignment requirement
+struct Floats {
+    float * ptr;
+    size_t n;
+    Floats(float * p, size_t size) : ptr(p), n(size) {}
+    Floats(std::vector<float> & v) : ptr(v.data()), n(v.size()) {}  // NOLINT(runtime/explicit)
+    float * data() { return ptr; }
+    size_t size() const { return n; }
+    float & operator[](size_t i) { return ptr[i]; }
+};
+
+namespace detail {
+// value type as it travels in a column (dist_b200_model): bool -> uint8
+template <class V> struct WireValue { typedef V type; };
+template <> struct WireValue<bool> { typedef uint8_t type; };
+}  // namespace detail
+
+struct rng_t {};  // scoring never draws (doc/overview.rst:213-220); kept so signatures match
+
+class Context {
+  public:
+    explicit Context(int device = 0) {
+        if (dist_b200_ctx_create(device, &ctx_) != DIST_B200_OK)
+            throw std::runtime_error("dist_b200_ctx_create failed: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Context() { dist_b200_ctx_destroy(ctx_); }
+    Context(const Context &) = delete;
+    Context & operator=(const Context &) = delete;
+    dist_b200_ctx * get() const { return ctx_; }
+    void check(int rc, const char * what) const {
+        if (rc != DIST_B200_OK)
+            throw std::runtime_error(std::string(what) + ": " + dist_b200_last_error(ctx_));
+    }
+
+  private:
+    dist_b200_ctx * ctx_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------
+// component models: Shared, Group and how a group list is uploaded
+
+struct NormalInverseChiSq {
+    typedef float Value;
+    enum { model_id = DIST_B200_NICH };
+    struct Shared {
+        float mu, kappa, sigmasq, nu;
+        static Shared EXAMPLE() { return Shared{0.f, 1.f, 1.f, 1.f}; }  // nich.hpp:87-94
+    };
+    struct Group {
+        int32_t count;
+        float mean;
+        float count_times_variance;
+        void init(const Shared &, rng_t &) { count = 0; mean = 0.f; count_times_variance = 0.f; }
+        void add_value(const Shared &, const Value & value, rng_t &) {  // nich.hpp:125-133
+            ++count;
+            float delta = value - mean;
+            mean += delta / count;
+            count_times_variance += delta * (value - mean);
+        }
+        void remove_value(const Shared &, const Value & value, rng_t &) {  // nich.hpp:146-165
+            float total = mean * count;
+            float delta = value - mean;
+            --count;
+            mean = (count == 0) ? 0.f : (total - value) / count;
+            if (count <= 1) count_times_variance = 0.f;
+            else count_times_variance -= delta * (value - mean);
+        }
+    };
+    static int update_all(dist_b200_feature * f, const Shared & s, const std::vector<Group> & groups) {
+        const size_t G = groups.size();
+        std::vector<int32_t> count(G);
+        std::vector<float> mean(G), ctv(G);
+        for (size_t g = 0; g < G; ++g) {
+            count[g] = groups[g].count; mean[g] = groups[g].mean; ctv[g] = groups[g].count_times_variance;
+        }
+        const float sh[4] = {s.mu, s.kappa, s.sigmasq, s.nu};
+        return dist_b200_nich_update_all(f, sh, static_cast<int>(G), count.data(), mean.data(), ctv.data(), nullptr);
+    }
+    static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
+        struct { int32_t count; float mean; float ctv; } st = {g.count, g.mean, g.count_times_variance};
+        return dist_b200_feature_update_group(f, static_cast<int>(groupid), &st, nullptr);
+    }
+};
+
+struct GammaPoisson {
+    typedef uint32_t Value;
+    enum { model_id = DIST_B200_GP };
+    struct Shared {
+        float alpha, inv_beta;
+        static Shared EXAMPLE() { return Shared{1.f, 1.f}; }  // gp.hpp:75-80
+    };
+    struct Group {
+        uint32_t count;
+        uint32_t sum;
+        void init(const Shared &, rng_t &) { count = 0; sum = 0; }
+        void add_value(const Shared &, const Value & value, rng_t &) { ++count; sum += value; }     // gp.hpp:109-116
+        void remove_value(const Shared &, const Value & value, rng_t &) { --count; sum -= value; }  // gp.hpp:128-135
+    };
+    static int update_all(dist_b200_feature * f, const Shared & s, const std::vector<Group> & groups) {
+        const size_t G = groups.size();
+        std::vector<uint32_t> count(G), sum(G);
+        for (size_t g = 0; g < G; ++g) { count[g] = groups[g].count; sum[g] = groups[g].sum; }
+        const float sh[2] = {s.alpha, s.inv_beta};
+        return dist_b200_gp_update_all(f, sh, static_cast<int>(G), count.data(), sum.data(), nullptr);
+    }
+    static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
+        const uint32_t st[2] = {g.count, g.sum};
+        return dist_b200_feature_update_group(f, static_cast<int>(groupid), st, nullptr);
+    }
+};
+
+struct BetaBernoulli {
+    typedef bool Value;
+    enum { model_id = DIST_B200_BB };
+    struct Shared {
+        float alpha, beta;
+        static Shared EXAMPLE() { return Shared{0.5f, 2.f}; }  // bb.hpp:70-75
+    };
+    struct Group {
+        int32_t heads, tails;
+        void init(const Shared &, rng_t &) { heads = 0; tails = 0; }
+        void add_value(const Shared &, const Value & value, rng_t &) { (value ? heads : tails) += 1; }     // bb.hpp:102-107
+        void remove_value(const Shared &, const Value & value, rng_t &) { (value ? heads : tails) -= 1; }  // bb.hpp:117-122
+    };
+    static int update_all(dist_b200_feature * f, const Shared & s, const std::vector<Group> & groups) {
+        const size_t G = groups.size();
+        std::vector<int32_t> h(G), t(G);
+        for (size_t g = 0; g < G; ++g) { h[g] = groups[g].heads; t[g] = groups[g].tails; }
+        const float sh[2] = {s.alpha, s.beta};
+        return dist_b200_bb_update_all(f, sh, static_cast<int>(G), h.data(), t.data(), nullptr);
+    }
+    static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
+        const int32_t st[2] = {g.heads, g.tails};
+        return dist_b200_feature_update_group(f, static_cast<int>(groupid), st, nullptr);
+    }
+};
+
+template <int max_dim_>
+struct DirichletDiscrete {
+    typedef int Value;
+    enum { model_id = DIST_B200_DD, max_dim = max_dim_ };
+    struct Shared {
+        int dim;
+        float alphas[max_dim_];
+        static Shared EXAMPLE() {  // dd.hpp:78-85
+            Shared s;
+            s.dim = max_dim_;
+            for (int i = 0; i < max_dim_; ++i) s.alphas[i] = 0.5f;
+            return s;
+        }
+    };
+    struct Group {
+        int dim;
+        int count_sum;
+        int counts[max_dim_];
+        void init(const Shared & shared, rng_t &) {
+            dim = shared.dim;
+            count_sum = 0;
+            for (int v = 0; v < dim; ++v) counts[v] = 0;
+        }
+        void add_value(const Shared &, const Value & value, rng_t &) { count_sum += 1; counts[value] += 1; }     // dd.hpp:123-130
+        void remove_value(const Shared &, const Value & value, rng_t &) { count_sum -= 1; counts[value] -= 1; }  // dd.hpp:142-149
+    };
+    static int update_all(dist_b200_feature * f, const Shared & s, const std::vector<Group> & groups) {
+        const size_t G = groups.size();
+        std::vector<int32_t> counts(G * s.dim);
+        for (size_t g = 0; g < G; ++g)
+            for (int v = 0; v < s.dim; ++v) counts[g * s.dim + v] = groups[g].counts[v];
+        return dist_b200_dd_update_all(f, s.dim, s.alphas, static_cast<int>(G), counts.data(), nullptr);
+    }
+    static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
+        return dist_b200_feature_update_group(f, static_cast<int>(groupid), g.counts, nullptr);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Mixture: MixtureSlave with the device-side value scorer
+
+template <class Model>
+class Mixture {
+  public:
+    typedef typename Model::Value Value;
+    typedef typename Model::Shared Shared;
+    typedef typename Model::Group Group;
+
+    explicit Mixture(std::shared_ptr<Context> ctx) : ctx_(std::move(ctx)) {
+        ctx_->check(dist_b200_feature_create(ctx_->get(), Model::model_id, &f_), "feature_create");
+    }
+    ~Mixture() { dist_b200_feature_destroy(f_); }
+    Mixture(const Mixture &) = delete;
+    Mixture & operator=(const Mixture &) = delete;
+
+    std::vector<Group> & groups() { return groups_; }
+    const std::vector<Group> & groups() const { return groups_; }
+    Group & groups(size_t i) { return groups_[i]; }
+    const Group & groups(size_t i) const { return groups_[i]; }
+    const dist_b200_feature * feature() const { return f_; }
+
+    // mixture.hpp:354-359: value_scorer_.resize + update_all
+    void init(const Shared & shared, rng_t &) {
+        ctx_->check(Model::update_all(f_, shared, groups_), "update_all");
+    }
+    // mixture.hpp:361-369
+    void add_group(const Shared & shared, rng_t & rng) {
+        groups_.emplace_back();
+        groups_.back().init(shared, rng);
+        ctx_->check(dist_b200_feature_add_group(f_, nullptr), "add_group");
+    }
+    // mixture.hpp:371-375: packed_remove = swap with last (vector.hpp:47-51)
+    void remove_group(const Shared &, size_t groupid) {
+        groups_[groupid] = std::move(groups_.back());
+        groups_.pop_back();
+        ctx_->check(dist_b200_feature_remove_group(f_, static_cast<int>(groupid), nullptr), "remove_group");
+    }
+    // mixture.hpp:377-398
+    void add_value(const Shared & shared, size_t groupid, const Value & value, rng_t & rng) {
+        groups_[groupid].add_value(shared, value, rng);
+        ctx_->check(Model::update_group(f_, shared, groupid, groups_[groupid]), "update_group");
+    }
+    void remove_value(const Shared & shared, size_t groupid, const Value & value, rng_t & rng) {
+        groups_[groupid].remove_value(shared, value, rng);
+        ctx_->check(Model::update_group(f_, shared, groupid, groups_[groupid]), "update_group");
+    }
+    // mixture.hpp:416-425: scores_accum[g] += score of `value` under group g
+    void score_value(const Shared &, const Value & value, Floats scores_accum, rng_t &) const {
+        if (scores_accum.size() != groups_.size()) throw std::runtime_error("score_value: size mismatch");
+        const typename detail::WireValue<Value>::type wire = static_cast<typename detail::WireValue<Value>::type>(value);
+        ctx_->check(dist_b200_score_value_host(ctx_->get(), f_, &wire, scores_accum.data()), "score_value");
+    }
+    // mixture.hpp:400-414
+    float score_value_group(const Shared & shared, size_t groupid, const Value & value, rng_t & rng) const {
+        std::vector<float> tmp(groups_.size(), 0.f);
+        score_value(shared, value, Floats(tmp), rng);
+        return tmp[groupid];
+    }
+
+    // NEW: batched score (+ sample).  values[n] are rows of this feature, prior[G] the clustering
+    // prior vector (or null), u[n] uniforms in [0,1); assign[n] receives the sampled packed group ids,
+    // scores (optional) the [n][G] log scores.  Host buffers.
+    template <class T>
+    void score_values(const Shared &, const T * values, size_t n, const float * prior, const float * u,
+                      int32_t * assign, float * scores = nullptr) const {
+        std::vector<typename detail::WireValue<Value>::type> wire(values, values + n);
+        const dist_b200_feature * feats[1] = {f_};
+        const void * cols[1] = {wire.data()};
+        ctx_->check(dist_b200_score_sample_batch_host(ctx_->get(), feats, 1, cols, n, prior, u, assign, scores),
+                    "score_values");
+    }
+
+  private:
+    std::shared_ptr<Context> ctx_;
+    dist_b200_feature * f_ = nullptr;
+    std::vector<Group> groups_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Clustering<int>::PitmanYor and its Mixture (CachedMixture over MixtureDriver)
+
+struct PitmanYor {
+    float alpha;
+    float d;
+
+    class Mixture {
+      public:
+        typedef std::unordered_set<size_t> IdSet;
+        explicit Mixture(std::shared_ptr<Context> ctx) : ctx_(std::move(ctx)) {}
+
+        std::vector<int32_t> & counts() { return counts_; }
+        const std::vector<int32_t> & counts() const { return counts_; }
+        int32_t counts(size_t groupid) const { return counts_[groupid]; }
+        const IdSet & empty_groupids() const { return empty_groupids_; }
+        size_t sample_size() const { return sample_size_; }
+
+        void init(const PitmanYor &) {  // mixture.hpp:63-75
+            empty_groupids_.clear();
+            sample_size_ = 0;
+            for (size_t i = 0; i < counts_.size(); ++i) {
+                sample_size_ += counts_[i];
+                if (counts_[i] == 0) empty_groupids_.insert(i);
+            }
+        }
+        bool add_value(const PitmanYor &, size_t groupid, int32_t count = 1) {  // mixture.hpp:77-93
+            const bool add_group = (counts_[groupid] == 0);
+            counts_[groupid] += count;
+            sample_size_ += count;
+            if (add_group) {
+                empty_groupids_.erase(groupid);
+                empty_groupids_.insert(counts_.size());
+                counts_.push_back(0);
+            }
+            return add_group;
+        }
+        bool remove_value(const PitmanYor &, size_t groupid, int32_t count = 1) {  // mixture.hpp:95-122
+            counts_[groupid] -= count;
+            sample_size_ -= count;
+            const bool remove_group = (counts_[groupid] == 0);
+            if (remove_group) {
+                const size_t last = counts_.size() - 1;
+                if (groupid != last) {
+                    counts_[groupid] = counts_.back();
+                    if (counts_.back() == 0) {
+                        empty_groupids_.erase(last);
+                        empty_groupids_.insert(groupid);
+                    }
+                }
+                counts_.pop_back();
+            }
+            return remove_group;
+        }
+        // clustering.hpp:195-208: OVERWRITES scores with the prior vector
+        void score_value(const PitmanYor & model, Floats scores) const {
+            if (scores.size() != counts_.size()) throw std::runtime_error("score_value: size mismatch");
+            ctx_->check(dist_b200_prior_pitman_yor_host(ctx_->get(), model.alpha, model.d, static_cast<int>(counts_.size()),
+                                                        counts_.data(), scores.data()),
+                        "prior_pitman_yor");
+        }
+
+      private:
+        std::shared_ptr<Context> ctx_;
+        std::vector<int32_t> counts_;
+        IdSet empty_groupids_;
+        size_t sample_size_ = 0;
+    };
+};
+
+// ---------------------------------------------------------------------------------------------
+// One cross-cat kind: a clustering mixture plus feature mixtures sharing its partition
+// (examples/mixture/main.py:59-123 in C++), with the batched row step.
+class CrossCat {
+  public:
+    explicit CrossCat(std::shared_ptr<Context> ctx) : ctx_(std::move(ctx)) {}
+    void add_feature(const dist_b200_feature * f, const void * column_host) {
+        feats_.push_back(f);
+        cols_.push_back(column_host);
+    }
+    // prior -> every feature -> sample, for n rows (the fused path of SURVEY.md §3.3)
+    void score_sample_values(size_t n, const float * prior, const float * u, int32_t * assign, float * scores = nullptr) {
+        ctx_->check(dist_b200_score_sample_batch_host(ctx_->get(), feats_.data(), static_cast<int>(feats_.size()), cols_.data(), n,
+                                                      prior, u, assign, scores),
+                    "score_sample_values");
+    }
+
+  private:
+    std::shared_ptr<Context> ctx_;
+    std::vector<const dist_b200_feature *> feats_;
+    std::vector<const void *> cols_;
+};
+
+}  // namespace distributions_b200

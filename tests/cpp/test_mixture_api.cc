@@ -1,0 +1,138 @@
+// Drives the C++ host mirror (include/distributions_b200/mixture.hpp) through the reference's
+// Mixture choreography (doc/overview.rst:130-202, tests/test_models.py:537-594): init, add_value,
+// remove_value, add_group, remove_group, per-value score_value (accumulate), PitmanYor prior
+// (overwrite), and the new batched entry.  Reads a script of operations, prints every score vector;
+// tests/test_cpp_api.py replays the same script with the oracle and compares.
+#include <distributions_b200/mixture.hpp>
+
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+using namespace distributions_b200;
+
+template <class T>
+static void print_vec(const char * tag, const std::vector<T> & v) {
+    std::printf("%s", tag);
+    for (auto x : v) std::printf(" %.9g", static_cast<double>(x));
+    std::printf("\n");
+}
+
+template <class Model, class Parse>
+static void run_script(std::shared_ptr<Context> ctx, std::istream & in, const typename Model::Shared & shared, Parse parse) {
+    rng_t rng;
+    Mixture<Model> mixture(ctx);
+    PitmanYor py{1.0f, 0.1f};
+    PitmanYor::Mixture driver(ctx);
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        std::string op;
+        ls >> op;
+        if (op == "end") break;
+        if (op == "groups") {  // groups <G>: start with G empty groups
+            size_t G;
+            ls >> G;
+            mixture.groups().resize(G);
+            for (auto & g : mixture.groups()) g.init(shared, rng);
+            driver.counts().assign(G, 0);
+        } else if (op == "fill") {  // fill <gid> <value>: Group::add_value before init (benchmarks/mixture.cc:88-99)
+            size_t gid;
+            ls >> gid;
+            auto v = parse(ls);
+            mixture.groups(gid).add_value(shared, v, rng);
+            driver.counts()[gid] += 1;
+        } else if (op == "init") {
+            mixture.init(shared, rng);
+            driver.init(py);
+        } else if (op == "add") {  // doc/overview.rst:185-195
+            size_t gid;
+            ls >> gid;
+            auto v = parse(ls);
+            const bool added = driver.add_value(py, gid);
+            mixture.add_value(shared, gid, v, rng);
+            if (added) mixture.add_group(shared, rng);
+        } else if (op == "remove") {  // doc/overview.rst:196-202
+            size_t gid;
+            ls >> gid;
+            auto v = parse(ls);
+            const bool removed = driver.remove_value(py, gid);
+            mixture.remove_value(shared, gid, v, rng);
+            if (removed) mixture.remove_group(shared, gid);
+        } else if (op == "score") {  // prior overwrite, then the slave accumulates
+            auto v = parse(ls);
+            std::vector<float> scores(mixture.groups().size(), 12345.f);
+            driver.score_value(py, Floats(scores));
+            print_vec("prior", scores);
+            mixture.score_value(shared, v, Floats(scores), rng);
+            print_vec("scores", scores);
+            std::vector<float> one(1, mixture.score_value_group(shared, 0, v, rng));
+            print_vec("group0", one);
+        } else if (op == "batch") {  // batch <n> then n values, then n uniforms
+            size_t n;
+            ls >> n;
+            std::vector<typename detail::WireValue<typename Model::Value>::type> vals(n);
+            std::vector<float> u(n);
+            std::getline(in, line);
+            std::istringstream vs(line);
+            for (auto & v : vals) v = parse(vs);
+            std::getline(in, line);
+            std::istringstream us(line);
+            for (auto & x : u) us >> x;
+            const size_t G = mixture.groups().size();
+            std::vector<float> prior(G), scores(n * G);
+            std::vector<int32_t> assign(n);
+            driver.score_value(py, Floats(prior));
+            mixture.score_values(shared, vals.data(), n, prior.data(), u.data(), assign.data(), scores.data());
+            print_vec("batch_assign", assign);
+            print_vec("batch_scores", scores);
+            // the batched entry must equal the per-value path row by row up to the association of the
+            // prior (the fused kernel folds it into the group cache: (prior + score) + c*L instead of
+            // prior + (score + c*L)), i.e. a couple of ulp
+            bool same = true;
+            for (size_t i = 0; i < n && i < 8; ++i) {
+                std::vector<float> row(prior);
+                mixture.score_value(shared, static_cast<typename Model::Value>(vals[i]), Floats(row), rng);
+                for (size_t g = 0; g < G; ++g) {
+                    const float a = row[g], b = scores[i * G + g];
+                    const float mag = (a < 0 ? -a : a) + 1.f;
+                    same = same && ((a > b ? a - b : b - a) <= 1e-6f * mag);
+                }
+            }
+            std::printf("batch_matches_per_value %d\n", same ? 1 : 0);
+        }
+    }
+}
+
+int main(int argc, char ** argv) {
+    if (argc < 2) return 2;
+    std::ifstream in(argv[1]);
+    try {
+        auto ctx = std::make_shared<Context>(0);
+        std::string line;
+        while (std::getline(in, line)) {
+            if (line == "model nich") {
+                std::printf("model nich\n");
+                run_script<NormalInverseChiSq>(ctx, in, NormalInverseChiSq::Shared::EXAMPLE(),
+                                               [](std::istream & s) { float v; s >> v; return v; });
+            } else if (line == "model gp") {
+                std::printf("model gp\n");
+                run_script<GammaPoisson>(ctx, in, GammaPoisson::Shared::EXAMPLE(),
+                                         [](std::istream & s) { uint32_t v; s >> v; return v; });
+            } else if (line == "model bb") {
+                std::printf("model bb\n");
+                run_script<BetaBernoulli>(ctx, in, BetaBernoulli::Shared::EXAMPLE(),
+                                          [](std::istream & s) { int v; s >> v; return v != 0; });
+            } else if (line == "model dd") {
+                std::printf("model dd\n");
+                run_script<DirichletDiscrete<16>>(ctx, in, DirichletDiscrete<16>::Shared::EXAMPLE(),
+                                                  [](std::istream & s) { int v; s >> v; return v; });
+            }
+        }
+    } catch (const std::exception & e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
