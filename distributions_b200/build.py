@@ -24,6 +24,7 @@ SOURCES = {
     "score_rows.cu": [],
     "gather_rows.cu": [],
     "niw.cu": [],
+    "niw_tc.cu": [],
     "microbench.cu": [],
 }
 

@@ -234,6 +234,7 @@ void dist_b200_feature_destroy(dist_b200_feature *f) {
     if (f->keys_dev) cudaFree(f->keys_dev);
     if (f->key_rows_dev) cudaFree(f->key_rows_dev);
     if (f->niw_buf) cudaFree(f->niw_buf);
+    if (f->niw_tc) cudaFree(f->niw_tc);
     if (f->ready) cudaEventDestroy(f->ready);
     delete f;
 }
@@ -403,7 +404,21 @@ int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float
     f->G = G;
     f->kappa = kappa;
     f->nu = nu;
-    return mark_ready(f, launch_niw_prep(ctx, d, mu_d, kappa, psi_d, nu, G, cnt_d, sx_d, sxx_d, f->niw_buf, as_stream(stream)), as_stream(stream));
+    int rc2 = launch_niw_prep(ctx, d, mu_d, kappa, psi_d, nu, G, cnt_d, sx_d, sxx_d, f->niw_buf, as_stream(stream));
+    if (rc2 == DIST_B200_OK && d == 32 && G > 0) {  // operand images for the tensor-core path
+        const size_t tc_bytes = sizeof(float) * niw_tc_floats(G);
+        if (tc_bytes > f->niw_tc_bytes) {
+            if (f->niw_tc) {
+                DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+                DISTB200_CUDA(ctx, cudaFree(f->niw_tc));
+                f->niw_tc = nullptr;
+            }
+            DISTB200_CUDA(ctx, cudaMalloc(&f->niw_tc, tc_bytes));
+            f->niw_tc_bytes = tc_bytes;
+        }
+        rc2 = launch_niw_tc_prep(ctx, G, f->niw_buf, f->niw_tc, as_stream(stream));
+    }
+    return mark_ready(f, rc2, as_stream(stream));
 }
 
 int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void *stats, void *stream) {

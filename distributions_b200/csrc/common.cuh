@@ -77,6 +77,8 @@ struct dist_b200_feature {
     // niw
     float *niw_buf = nullptr;
     size_t niw_bytes = 0;
+    float *niw_tc = nullptr;          // d = 32: tensor-core operand images, b vectors, constants
+    size_t niw_tc_bytes = 0;
     float kappa = 0, nu = 0;
     std::vector<float> mu, psi;
 };
@@ -130,5 +132,10 @@ int launch_niw_prep(dist_b200_ctx *ctx, int d, const float *mu, float kappa, con
                     const int32_t *count, const float *sum_x, const float *sum_xxT, float *recs, cudaStream_t s);
 int launch_niw_scores(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *values, size_t N,
                       const float *prior, float *scores, int accumulate, cudaStream_t s);
+// niw_tc.cu (tcgen05 / TMEM path, d = 32)
+size_t niw_tc_floats(int G);
+int launch_niw_tc_prep(dist_b200_ctx *ctx, int G, const float *recs, float *tc_buf, cudaStream_t s);
+int launch_niw_tc_scores(dist_b200_ctx *ctx, int G, const float *tc_buf, const void *values, size_t N, const float *prior,
+                         float *scores, int accumulate, bool split, cudaStream_t s);
 
 }  // namespace distb200

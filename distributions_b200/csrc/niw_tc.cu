@@ -1,0 +1,348 @@
+// niw_tc.cu -- NormalInverseWishart<32> quadratic forms on the 5th-generation tensor cores.
+//
+// The only dense contraction on the hot path: for every (row n, group g)
+//   y = W_g x_n   (W_g = L_g^-1, d x d),    q = |y - W_g mu'_g|^2,
+//   score = C_g - 0.5 (dof_g + d) fast_log(1 + q / dof_g)          (niw.hpp:353-360, random.hpp:160-185)
+// Stacking the W_g of 8 groups gives a B operand of 256 rows, so one tcgen05.mma tile is
+//   D[128 rows][256 = 8 groups x 32 dims] = X[128][32] * Wstack[256][32]^T        (kind::tf32, fp32 accum)
+// with the accumulator in TMEM (2 x 256 columns, double buffered).  A TMEM lane is a data row and a
+// 32-column slice is exactly one cell's y vector, so the epilogue is one tcgen05.ld (32x32b.x32) per
+// cell followed by 32 (y-b)^2 FMAs, MUFU.LG2 and the score FFMA, all in registers.
+//
+// Precision: one TF32 pass rounds x and W to 10 mantissa bits, and y - b cancels |W mu'| ~ 17 down to
+// |y - b| ~ 1: ~0.04 absolute on a score.  The default mode therefore splits both operands
+// (x = x_hi + x_lo, W = W_hi + W_lo with x_hi, W_hi exactly representable in TF32) and accumulates
+// x_hi W_hi + x_lo W_hi + x_hi W_lo in the same TMEM tile ("3xTF32", error ~2^-21), which keeps the
+// scores within the fp32 kernel's tolerance.  DIST_B200_NIW_MODE=tf32 selects the single pass.
+//
+// Pipeline per CTA (128 threads = 4 warps = the 128 TMEM lanes; one CTA per SM, persistent over row
+// tiles): the X tile is converted and laid out in shared memory once per row tile; the operand images
+// of 8-group blocks, pre-laid-out by niw_tc_prep_kernel in the canonical no-swizzle K-major core-matrix
+// order, stream in with cp.async.bulk + mbarrier (double buffered); one thread issues the MMAs and a
+// tcgen05.commit; the epilogue of block b-1 runs while the tensor pipe works on block b.
+#include "common.cuh"
+
+namespace distb200 {
+
+constexpr int kTcDim = 32;                 // d (K of the GEMM)
+constexpr int kTcGroupsPerBlock = 8;       // groups per B tile (N = 256)
+constexpr int kTcRows = 128;               // rows per tile (M)
+constexpr int kTcImageFloats = 256 * 32;   // one operand image of a block: 256 x 32 fp32 = 32 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// no-swizzle K-major canonical layout: core matrix = 8 rows x 16 bytes, rows 16 B apart;
+// core (row group j, k core c) at byte offset (c * n_row_groups + j) * 128
+__host__ __device__ __forceinline__ int core_offset_floats(int row, int k, int n_row_groups) {
+    return ((k >> 2) * n_row_groups + (row >> 3)) * 32 + (row & 7) * 4 + (k & 3);
+}
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading (K) byte offset, bits [16,30)
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride (M/N) byte offset, bits [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
+    return d;                                                      // layout type 0 = no swizzle
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();  // never hang the device on a protocol error
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Operand images.  From the group records of niw_prep_kernel (mu'[32] | W[32][32] | consts[4]) build, per
+// block of 8 groups: W_hi image (32 KB), W_lo image (32 KB) in core-matrix order; and per group
+// b = W mu' (32 floats) and the constants.
+__global__ void niw_tc_prep_kernel(int G, int n_blocks, const float *__restrict__ recs, float *__restrict__ images,
+                                   float *__restrict__ bvec, float *__restrict__ consts) {
+    constexpr int REC = kTcDim + kTcDim * kTcDim + 4;
+    const int blk = blockIdx.x;
+    for (int e = threadIdx.x; e < 256 * 32; e += blockDim.x) {
+        const int n = e >> 5, k = e & 31;          // B row n = (group in block) * 32 + i, column k
+        const int g = blk * kTcGroupsPerBlock + (n >> 5), i = n & 31;
+        const float w = g < G ? recs[static_cast<size_t>(g) * REC + kTcDim + i * kTcDim + k] : 0.f;
+        const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);  // exactly representable in TF32
+        const int off = core_offset_floats(n, k, 32);
+        images[static_cast<size_t>(blk) * 2 * kTcImageFloats + off] = hi;
+        images[static_cast<size_t>(blk) * 2 * kTcImageFloats + kTcImageFloats + off] = w - hi;
+    }
+    for (int e = threadIdx.x; e < 256; e += blockDim.x) {
+        const int g = blk * kTcGroupsPerBlock + (e >> 5), i = e & 31;
+        double b = 0.0;
+        if (g < G) {
+            const float *rec = recs + static_cast<size_t>(g) * REC;
+            for (int k = 0; k <= i; ++k) b += static_cast<double>(rec[kTcDim + i * kTcDim + k]) * static_cast<double>(rec[k]);
+        }
+        bvec[static_cast<size_t>(blk) * 256 + e] = static_cast<float>(b);
+    }
+    if (threadIdx.x < kTcGroupsPerBlock * 4) {
+        const int g = blk * kTcGroupsPerBlock + (threadIdx.x >> 2), c = threadIdx.x & 3;
+        consts[static_cast<size_t>(blk) * 32 + threadIdx.x] = g < G ? recs[static_cast<size_t>(g) * REC + kTcDim + kTcDim * kTcDim + c] : 0.f;
+    }
+    (void)n_blocks;
+}
+
+struct NiwTcArgs {
+    int G, n_blocks, accumulate;
+    size_t N;
+    const float *images;  // [n_blocks][2][256*32]
+    const float *bvec;    // [n_blocks][256]
+    const float *consts;  // [n_blocks][8][4]
+    const float *values;  // [N][32]
+    const float *prior;   // [G] or nullptr
+    float *scores;        // [N][G]
+};
+
+template <bool kSplit>
+__global__ void __launch_bounds__(kTcRows, 1) niw_tc_kernel(const NiwTcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int kImages = kSplit ? 2 : 1;
+    float *A_hi = reinterpret_cast<float *>(smem_raw);                       // 16 KB
+    float *A_lo = A_hi + kTcRows * kTcDim;                                    // 16 KB (split only)
+    float *B = A_lo + (kSplit ? kTcRows * kTcDim : 0);                        // [2][kImages][32 KB]
+    float *bs = B + 2 * kImages * kTcImageFloats;                             // [n_blocks][256]
+    float *cs = bs + a.n_blocks * 256;                                        // [n_blocks][32]
+    float *ps = cs + a.n_blocks * 32;                                         // [n_blocks*8] prior
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ps + a.n_blocks * 8);       // bfull[2], mma_done[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nb = a.n_blocks;
+    uint64_t *bfull = bars, *mma_done = bars + 2;
+
+    // per-CTA resident small tables
+    for (int i = tid; i < nb * 256; i += kTcRows) bs[i] = a.bvec[i];
+    for (int i = tid; i < nb * 32; i += kTcRows) cs[i] = a.consts[i];
+    for (int i = tid; i < nb * 8; i += kTcRows) ps[i] = (i < a.G && a.prior && !a.accumulate) ? a.prior[i] : 0.f;
+    if (tid == 0) {
+        mbar_init(&bfull[0], 1);
+        mbar_init(&bfull[1], 1);
+        mbar_init(&mma_done[0], 1);
+        mbar_init(&mma_done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t image_bytes = kTcImageFloats * sizeof(float);
+    uint32_t full_phase[2] = {0, 0}, done_phase[2] = {0, 0};
+
+    const size_t ntiles = (a.N + kTcRows - 1) / kTcRows;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t row_raw = tile * kTcRows + tid;
+        const bool valid = row_raw < a.N;
+        const size_t row = valid ? row_raw : a.N - 1;
+        // ---- A tile: this thread's row, 8 k-cores of 4 floats, hi / lo parts
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(a.values + row * kTcDim);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 x = src[c];
+                float4 hi;
+                hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                const int off = core_offset_floats(tid, c * 4, kTcRows / 8);
+                *reinterpret_cast<float4 *>(A_hi + off) = kSplit ? hi : x;
+                if (kSplit) *reinterpret_cast<float4 *>(A_lo + off) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy stores -> visible to the MMA
+        __syncthreads();
+        if (tid == 0) {  // operand images of block 0
+            mbar_expect_tx(&bfull[0], kImages * image_bytes);
+            for (int im = 0; im < kImages; ++im)
+                bulk_g2s(B + im * kTcImageFloats, a.images + im * kTcImageFloats, image_bytes, &bfull[0]);
+        }
+
+        for (int gb = 0; gb <= nb; ++gb) {
+            const int buf = gb & 1;
+            if (gb >= 1) {  // MMA of block gb-1 finished: its B buffer is free, its accumulator is ready
+                mbar_wait(&mma_done[buf ^ 1], done_phase[buf ^ 1]);
+                done_phase[buf ^ 1] ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            }
+            if (tid == 0 && gb < nb) {
+                if (gb + 1 < nb) {  // prefetch the next block's images into the buffer just freed
+                    float *dst = B + (buf ^ 1) * kImages * kTcImageFloats;
+                    const float *src = a.images + static_cast<size_t>(gb + 1) * 2 * kTcImageFloats;
+                    mbar_expect_tx(&bfull[buf ^ 1], kImages * image_bytes);
+                    for (int im = 0; im < kImages; ++im) bulk_g2s(dst + im * kTcImageFloats, src + im * kTcImageFloats, image_bytes, &bfull[buf ^ 1]);
+                }
+                mbar_wait(&bfull[buf], full_phase[buf]);
+                full_phase[buf] ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t d_addr = tmem_base + buf * 256;
+                const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
+                const uint32_t b_hi = smem_u32(B + buf * kImages * kTcImageFloats), b_lo = b_hi + image_bytes;
+                // per k-step of 8 (two k-cores): A cores are 16 row-groups apart, B cores 32 row-groups apart
+                uint32_t acc = 0;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ao = ks * 2 * (kTcRows / 8) * 128, bo = ks * 2 * 32 * 128;
+                    umma_tf32(d_addr, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, acc);
+                    acc = 1;
+                    if (kSplit) {
+                        umma_tf32(d_addr, make_smem_desc(a_lo + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, 1);
+                        umma_tf32(d_addr, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_lo + bo, 32 * 128, 128), idesc, 1);
+                    }
+                }
+                umma_commit(&mma_done[buf]);
+            }
+            __syncwarp();  // warp 0 reconverges before the warp-collective tcgen05.ld below
+            if (gb >= 1) {
+                // ---- epilogue of block gb-1: TMEM lane = row, 32 columns = one group's y vector
+                const int pb = gb - 1, pbuf = buf ^ 1;
+                float out[kTcGroupsPerBlock];
+#pragma unroll
+                for (int j = 0; j < kTcGroupsPerBlock; ++j) {
+                    float y[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + pbuf * 256 + j * 32, y);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bs + pb * 256 + j * 32);
+                    float q = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = b4[i];
+                        float t;
+                        t = y[4 * i] - b.x; q = fmaf(t, t, q);
+                        t = y[4 * i + 1] - b.y; q = fmaf(t, t, q);
+                        t = y[4 * i + 2] - b.z; q = fmaf(t, t, q);
+                        t = y[4 * i + 3] - b.w; q = fmaf(t, t, q);
+                    }
+                    const float4 c = *reinterpret_cast<const float4 *>(cs + pb * 32 + j * 4);
+                    const float arg = __fadd_rn(1.f, __fmul_rn(c.z, q));
+                    out[j] = fmaf(c.y, fast_log2_cell(arg), c.x) + ps[pb * 8 + j];
+                }
+                if (valid) {
+                    float *dst = a.scores + row * a.G + pb * kTcGroupsPerBlock;
+                    if (pb * kTcGroupsPerBlock + kTcGroupsPerBlock <= a.G && (a.G & 3) == 0) {
+                        float4 o0 = make_float4(out[0], out[1], out[2], out[3]), o1 = make_float4(out[4], out[5], out[6], out[7]);
+                        if (a.accumulate) {
+                            const float4 p0 = *reinterpret_cast<float4 *>(dst), p1 = *reinterpret_cast<float4 *>(dst + 4);
+                            o0 = make_float4(o0.x + p0.x, o0.y + p0.y, o0.z + p0.z, o0.w + p0.w);
+                            o1 = make_float4(o1.x + p1.x, o1.y + p1.y, o1.z + p1.z, o1.w + p1.w);
+                        }
+                        *reinterpret_cast<float4 *>(dst) = o0;
+                        *reinterpret_cast<float4 *>(dst + 4) = o1;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kTcGroupsPerBlock; ++j)
+                            if (pb * kTcGroupsPerBlock + j < a.G) dst[j] = a.accumulate ? dst[j] + out[j] : out[j];
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            }
+            __syncthreads();  // accumulator (gb-1)&1 drained by every warp before block gb+1 overwrites it
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t niw_tc_floats(int G) {
+    const size_t nb = (G + kTcGroupsPerBlock - 1) / kTcGroupsPerBlock;
+    return nb * (2 * kTcImageFloats + 256 + 32);
+}
+
+int launch_niw_tc_prep(dist_b200_ctx *ctx, int G, const float *recs, float *tc_buf, cudaStream_t s) {
+    const int nb = (G + kTcGroupsPerBlock - 1) / kTcGroupsPerBlock;
+    if (nb == 0) return DIST_B200_OK;
+    float *images = tc_buf, *bvec = images + static_cast<size_t>(nb) * 2 * kTcImageFloats, *consts = bvec + static_cast<size_t>(nb) * 256;
+    niw_tc_prep_kernel<<<nb, 256, 0, s>>>(G, nb, recs, images, bvec, consts);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("niw_tc_prep launch: ") + cudaGetErrorString(e));
+    return DIST_B200_OK;
+}
+
+int launch_niw_tc_scores(dist_b200_ctx *ctx, int G, const float *tc_buf, const void *values, size_t N, const float *prior,
+                         float *scores, int accumulate, bool split, cudaStream_t s) {
+    if (N == 0 || G == 0) return DIST_B200_OK;
+    const int nb = (G + kTcGroupsPerBlock - 1) / kTcGroupsPerBlock;
+    NiwTcArgs a{};
+    a.G = G;
+    a.n_blocks = nb;
+    a.accumulate = accumulate;
+    a.N = N;
+    a.images = tc_buf;
+    a.bvec = tc_buf + static_cast<size_t>(nb) * 2 * kTcImageFloats;
+    a.consts = a.bvec + static_cast<size_t>(nb) * 256;
+    a.values = static_cast<const float *>(values);
+    a.prior = prior;
+    a.scores = scores;
+    const int images = split ? 2 : 1;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(kTcRows) * kTcDim * images + 2 * images * kTcImageFloats +
+                                         static_cast<size_t>(nb) * (256 + 32 + 8)) + 64 + 1024;
+    if (smem > 227 * 1024) return DIST_B200_ERR_UNSUPPORTED;  // too many groups for the resident b / consts tables
+    const size_t ntiles = (N + kTcRows - 1) / kTcRows;
+    const unsigned grid = static_cast<unsigned>(ntiles < static_cast<size_t>(ctx->sm_count) ? ntiles : ctx->sm_count);
+    cudaError_t e;
+    if (split) {
+        e = cudaFuncSetAttribute(niw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e == cudaSuccess) niw_tc_kernel<true><<<grid, kTcRows, smem, s>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(niw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e == cudaSuccess) niw_tc_kernel<false><<<grid, kTcRows, smem, s>>>(a);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("niw_tc launch: ") + cudaGetErrorString(e));
+    return DIST_B200_OK;
+}
+
+}  // namespace distb200
