@@ -27,6 +27,7 @@ namespace distb200 {
 constexpr int kTcDim = 32;                 // d (K of the GEMM)
 constexpr int kTcGroupsPerBlock = 8;       // groups per B tile (N = 256)
 constexpr int kTcRows = 128;               // rows per tile (M)
+constexpr int kTcThreads = 256;            // two warpgroups: both see all 128 TMEM lanes, each drains half the columns
 constexpr int kTcImageFloats = 256 * 32;   // one operand image of a block: 256 x 32 fp32 = 32 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -95,10 +96,51 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 64 columns = two cells per instruction, results left in flight (the caller issues tcgen05.wait::ld once)
+__device__ __forceinline__ void tmem_ld64_nowait(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+}
+
+// Blackwell packed fp32 pairs: one instruction, two lanes of the FMA pipe (halves the epilogue's issue count)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float sum2(uint64_t a) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+    return lo + hi;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Operand images.  From the group records of niw_prep_kernel (mu'[32] | W[32][32] | consts[4]) build, per
 // block of 8 groups: W_hi image (32 KB), W_lo image (32 KB) in core-matrix order; and per group
-// b = W mu' (32 floats) and the constants.
+// -b = -(W mu') (32 floats) and the constants.
 __global__ void niw_tc_prep_kernel(int G, int n_blocks, const float *__restrict__ recs, float *__restrict__ images,
                                    float *__restrict__ bvec, float *__restrict__ consts) {
     constexpr int REC = kTcDim + kTcDim * kTcDim + 4;
@@ -119,7 +161,7 @@ __global__ void niw_tc_prep_kernel(int G, int n_blocks, const float *__restrict_
             const float *rec = recs + static_cast<size_t>(g) * REC;
             for (int k = 0; k <= i; ++k) b += static_cast<double>(rec[kTcDim + i * kTcDim + k]) * static_cast<double>(rec[k]);
         }
-        bvec[static_cast<size_t>(blk) * 256 + e] = static_cast<float>(b);
+        bvec[static_cast<size_t>(blk) * 256 + e] = static_cast<float>(-b);  // negated: the epilogue adds
     }
     if (threadIdx.x < kTcGroupsPerBlock * 4) {
         const int g = blk * kTcGroupsPerBlock + (threadIdx.x >> 2), c = threadIdx.x & 3;
@@ -139,30 +181,34 @@ struct NiwTcArgs {
     float *scores;        // [N][G]
 };
 
+// W-stationary schedule.  A work item is (block of 8 groups, chunk of row tiles): the CTA loads that
+// block's operand images once (64 KB in split mode), then streams the chunk's row tiles through a
+// double-buffered A tile and a double-buffered TMEM accumulator.  Items are ordered chunk-major so the
+// CTAs running at the same time share a 1 MB chunk of rows in L2 while each keeps its own W block in
+// shared memory: L2->SM traffic is n_blocks x |X| instead of n_row_tiles x |W|.
+constexpr int kTcChunkTiles = 64;  // row tiles per work item (8192 rows)
+
 template <bool kSplit>
-__global__ void __launch_bounds__(kTcRows, 1) niw_tc_kernel(const NiwTcArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) niw_tc_kernel(const NiwTcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr int kImages = kSplit ? 2 : 1;
-    float *A_hi = reinterpret_cast<float *>(smem_raw);                       // 16 KB
-    float *A_lo = A_hi + kTcRows * kTcDim;                                    // 16 KB (split only)
-    float *B = A_lo + (kSplit ? kTcRows * kTcDim : 0);                        // [2][kImages][32 KB]
-    float *bs = B + 2 * kImages * kTcImageFloats;                             // [n_blocks][256]
-    float *cs = bs + a.n_blocks * 256;                                        // [n_blocks][32]
-    float *ps = cs + a.n_blocks * 32;                                         // [n_blocks*8] prior
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ps + a.n_blocks * 8);       // bfull[2], mma_done[2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+    constexpr int kAFloats = kTcRows * kTcDim;                                // one A image: 16 KB
+    float *As = reinterpret_cast<float *>(smem_raw);                          // [2 buffers][kImages][16 KB]
+    float *Bs = As + 2 * kImages * kAFloats;                                  // [kImages][32 KB]
+    float *bs = Bs + kImages * kTcImageFloats;                                // [256] -b = -(W mu')
+    float *cs = bs + 256;                                                     // [8][4] constants
+    float *ps = cs + 32;                                                      // [8] prior
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ps + 8);                    // bfull, mma_done[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int r_in_tile = tid & (kTcRows - 1);  // this thread's row of the tile = its TMEM lane
+    const int wg = tid >> 7;                     // warpgroup: k-cores [4 wg, 4 wg + 4) of A, groups [4 wg, 4 wg + 4) of D
     const int nb = a.n_blocks;
-    uint64_t *bfull = bars, *mma_done = bars + 2;
+    uint64_t *bfull = bars, *mma_done = bars + 1;
 
-    // per-CTA resident small tables
-    for (int i = tid; i < nb * 256; i += kTcRows) bs[i] = a.bvec[i];
-    for (int i = tid; i < nb * 32; i += kTcRows) cs[i] = a.consts[i];
-    for (int i = tid; i < nb * 8; i += kTcRows) ps[i] = (i < a.G && a.prior && !a.accumulate) ? a.prior[i] : 0.f;
     if (tid == 0) {
-        mbar_init(&bfull[0], 1);
-        mbar_init(&bfull[1], 1);
+        mbar_init(bfull, 1);
         mbar_init(&mma_done[0], 1);
         mbar_init(&mma_done[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -179,61 +225,85 @@ __global__ void __launch_bounds__(kTcRows, 1) niw_tc_kernel(const NiwTcArgs a) {
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t image_bytes = kTcImageFloats * sizeof(float);
-    uint32_t full_phase[2] = {0, 0}, done_phase[2] = {0, 0};
+    uint32_t full_phase = 0, done_phase[2] = {0, 0};
 
     const size_t ntiles = (a.N + kTcRows - 1) / kTcRows;
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t row_raw = tile * kTcRows + tid;
-        const bool valid = row_raw < a.N;
-        const size_t row = valid ? row_raw : a.N - 1;
-        // ---- A tile: this thread's row, 8 k-cores of 4 floats, hi / lo parts
-        {
-            const float4 *src = reinterpret_cast<const float4 *>(a.values + row * kTcDim);
+    const size_t nchunks = (ntiles + kTcChunkTiles - 1) / kTcChunkTiles;
+    const size_t nitems = nchunks * nb;
+
+    // this thread's half row of a tile: global -> registers
+    auto load_x = [&](size_t tile, float4 (&x)[4]) {
+        size_t row = tile * kTcRows + r_in_tile;
+        if (row >= a.N) row = a.N - 1;
+        const float4 *src = reinterpret_cast<const float4 *>(a.values + row * kTcDim) + 4 * wg;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float4 x = src[c];
-                float4 hi;
-                hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-                hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-                const int off = core_offset_floats(tid, c * 4, kTcRows / 8);
-                *reinterpret_cast<float4 *>(A_hi + off) = kSplit ? hi : x;
-                if (kSplit) *reinterpret_cast<float4 *>(A_lo + off) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
-            }
+        for (int c = 0; c < 4; ++c) x[c] = __ldg(src + c);
+    };
+    // registers -> A buffer `ab` in core-matrix order, split into TF32-exact hi and the remainder
+    auto store_x = [&](int ab, const float4 (&x)[4]) {
+        float *A_hi = As + ab * kImages * kAFloats, *A_lo = A_hi + kAFloats;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float4 hi;
+            hi.x = __uint_as_float(__float_as_uint(x[c].x) & 0xFFFFE000u);
+            hi.y = __uint_as_float(__float_as_uint(x[c].y) & 0xFFFFE000u);
+            hi.z = __uint_as_float(__float_as_uint(x[c].z) & 0xFFFFE000u);
+            hi.w = __uint_as_float(__float_as_uint(x[c].w) & 0xFFFFE000u);
+            const int off = core_offset_floats(r_in_tile, (4 * wg + c) * 4, kTcRows / 8);
+            *reinterpret_cast<float4 *>(A_hi + off) = kSplit ? hi : x[c];
+            if (kSplit)
+                *reinterpret_cast<float4 *>(A_lo + off) = make_float4(x[c].x - hi.x, x[c].y - hi.y, x[c].z - hi.z, x[c].w - hi.w);
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy stores -> visible to the MMA
-        __syncthreads();
-        if (tid == 0) {  // operand images of block 0
-            mbar_expect_tx(&bfull[0], kImages * image_bytes);
-            for (int im = 0; im < kImages; ++im)
-                bulk_g2s(B + im * kTcImageFloats, a.images + im * kTcImageFloats, image_bytes, &bfull[0]);
-        }
+    };
 
-        for (int gb = 0; gb <= nb; ++gb) {
-            const int buf = gb & 1;
-            if (gb >= 1) {  // MMA of block gb-1 finished: its B buffer is free, its accumulator is ready
+    for (size_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int blk = static_cast<int>(item % nb);
+        const size_t chunk = item / nb;
+        const size_t t0 = chunk * kTcChunkTiles, t1 = t0 + kTcChunkTiles < ntiles ? t0 + kTcChunkTiles : ntiles;
+        const int nt = static_cast<int>(t1 - t0);
+        // ---- per-item setup: W images (bulk, async), b / constants / prior of this block, A tile 0
+        if (tid == 0) {
+            mbar_expect_tx(bfull, kImages * image_bytes);
+            for (int im = 0; im < kImages; ++im)
+                bulk_g2s(Bs + im * kTcImageFloats, a.images + (static_cast<size_t>(blk) * 2 + im) * kTcImageFloats, image_bytes, bfull);
+        }
+        bs[tid] = a.bvec[static_cast<size_t>(blk) * 256 + tid];
+        if (tid < 32) cs[tid] = a.consts[static_cast<size_t>(blk) * 32 + tid];
+        if (tid < 8) {
+            const int g = blk * kTcGroupsPerBlock + tid;
+            ps[tid] = (g < a.G && a.prior && !a.accumulate) ? a.prior[g] : 0.f;
+        }
+        {
+            float4 x[4];
+            load_x(t0, x);
+            store_x(0, x);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(bfull, full_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        }
+        full_phase ^= 1;
+        __syncwarp();
+
+        for (int t = 0; t <= nt; ++t) {
+            const int buf = t & 1;
+            float4 xn[4];
+            const bool have_next = t + 1 < nt;
+            if (have_next) load_x(t0 + t + 1, xn);  // in flight across the wait and the epilogue below
+            if (t >= 1) {  // MMA of tile t-1 finished: accumulator ready, A buffer (t-1)&1 reusable
                 mbar_wait(&mma_done[buf ^ 1], done_phase[buf ^ 1]);
                 done_phase[buf ^ 1] ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
-            if (tid == 0 && gb < nb) {
-                if (gb + 1 < nb) {  // prefetch the next block's images into the buffer just freed
-                    float *dst = B + (buf ^ 1) * kImages * kTcImageFloats;
-                    const float *src = a.images + static_cast<size_t>(gb + 1) * 2 * kTcImageFloats;
-                    mbar_expect_tx(&bfull[buf ^ 1], kImages * image_bytes);
-                    for (int im = 0; im < kImages; ++im) bulk_g2s(dst + im * kTcImageFloats, src + im * kTcImageFloats, image_bytes, &bfull[buf ^ 1]);
-                }
-                mbar_wait(&bfull[buf], full_phase[buf]);
-                full_phase[buf] ^= 1;
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (tid == 0 && t < nt) {
                 const uint32_t d_addr = tmem_base + buf * 256;
-                const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
-                const uint32_t b_hi = smem_u32(B + buf * kImages * kTcImageFloats), b_lo = b_hi + image_bytes;
-                // per k-step of 8 (two k-cores): A cores are 16 row-groups apart, B cores 32 row-groups apart
+                const uint32_t a_hi = smem_u32(As + buf * kImages * kAFloats), a_lo = a_hi + kAFloats * sizeof(float);
+                const uint32_t b_hi = smem_u32(Bs), b_lo = b_hi + image_bytes;
                 uint32_t acc = 0;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
+                for (int ks = 0; ks < 4; ++ks) {  // k-step of 8 = two k-cores
                     const uint32_t ao = ks * 2 * (kTcRows / 8) * 128, bo = ks * 2 * 32 * 128;
                     umma_tf32(d_addr, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, acc);
                     acc = 1;
@@ -245,49 +315,60 @@ __global__ void __launch_bounds__(kTcRows, 1) niw_tc_kernel(const NiwTcArgs a) {
                 umma_commit(&mma_done[buf]);
             }
             __syncwarp();  // warp 0 reconverges before the warp-collective tcgen05.ld below
-            if (gb >= 1) {
-                // ---- epilogue of block gb-1: TMEM lane = row, 32 columns = one group's y vector
-                const int pb = gb - 1, pbuf = buf ^ 1;
-                float out[kTcGroupsPerBlock];
+            if (t >= 1) {
+                // ---- epilogue of tile t-1: TMEM lane = row, 32 columns = one group's y vector
+                const int pbuf = buf ^ 1;
+                const size_t row = (t0 + t - 1) * kTcRows + r_in_tile;
+                constexpr int kPer = kTcGroupsPerBlock / 2;  // groups per warpgroup
+                float out[kPer];
+                // all four cells of this thread are pulled out of TMEM up front (2 loads of 64 columns,
+                // one wait): the TMEM latency is paid once per tile, and the four sums of squares below
+                // are independent instruction streams
+                uint32_t yr[2][64];
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + pbuf * 256 + wg * kPer * 32;
+                tmem_ld64_nowait(t_row, yr[0]);
+                tmem_ld64_nowait(t_row + 64, yr[1]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < kTcGroupsPerBlock; ++j) {
-                    float y[32];
-                    tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + pbuf * 256 + j * 32, y);
-                    const float4 *b4 = reinterpret_cast<const float4 *>(bs + pb * 256 + j * 32);
-                    float q = 0.f;
+                for (int jj = 0; jj < kPer; ++jj) {
+                    const int j = wg * kPer + jj;
+                    const uint32_t *y = &yr[jj >> 1][(jj & 1) * 32];
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bs + j * 32);
+                    // |y - b|^2 with packed fp32x2 adds / fmas, four independent chains
+                    uint64_t qa = 0ull, qb = 0ull;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 b = b4[i];
-                        float t;
-                        t = y[4 * i] - b.x; q = fmaf(t, t, q);
-                        t = y[4 * i + 1] - b.y; q = fmaf(t, t, q);
-                        t = y[4 * i + 2] - b.z; q = fmaf(t, t, q);
-                        t = y[4 * i + 3] - b.w; q = fmaf(t, t, q);
+                        const float4 nb4 = b4[i];  // holds -b
+                        const uint64_t d0 = add2(pack2(__uint_as_float(y[4 * i]), __uint_as_float(y[4 * i + 1])), pack2(nb4.x, nb4.y));
+                        const uint64_t d1 = add2(pack2(__uint_as_float(y[4 * i + 2]), __uint_as_float(y[4 * i + 3])), pack2(nb4.z, nb4.w));
+                        qa = fma2(d0, d0, qa);
+                        qb = fma2(d1, d1, qb);
                     }
-                    const float4 c = *reinterpret_cast<const float4 *>(cs + pb * 32 + j * 4);
+                    const float q = sum2(qa) + sum2(qb);
+                    const float4 c = *reinterpret_cast<const float4 *>(cs + j * 4);
                     const float arg = __fadd_rn(1.f, __fmul_rn(c.z, q));
-                    out[j] = fmaf(c.y, fast_log2_cell(arg), c.x) + ps[pb * 8 + j];
+                    out[jj] = fmaf(c.y, fast_log2_cell(arg), c.x) + ps[j];
                 }
-                if (valid) {
-                    float *dst = a.scores + row * a.G + pb * kTcGroupsPerBlock;
-                    if (pb * kTcGroupsPerBlock + kTcGroupsPerBlock <= a.G && (a.G & 3) == 0) {
-                        float4 o0 = make_float4(out[0], out[1], out[2], out[3]), o1 = make_float4(out[4], out[5], out[6], out[7]);
+                if (row < a.N) {
+                    const int gbase = blk * kTcGroupsPerBlock + wg * kPer;
+                    float *dst = a.scores + row * a.G + gbase;
+                    if (gbase + kPer <= a.G && (a.G & 3) == 0) {
+                        float4 o0 = make_float4(out[0], out[1], out[2], out[3]);
                         if (a.accumulate) {
-                            const float4 p0 = *reinterpret_cast<float4 *>(dst), p1 = *reinterpret_cast<float4 *>(dst + 4);
+                            const float4 p0 = *reinterpret_cast<float4 *>(dst);
                             o0 = make_float4(o0.x + p0.x, o0.y + p0.y, o0.z + p0.z, o0.w + p0.w);
-                            o1 = make_float4(o1.x + p1.x, o1.y + p1.y, o1.z + p1.z, o1.w + p1.w);
                         }
                         *reinterpret_cast<float4 *>(dst) = o0;
-                        *reinterpret_cast<float4 *>(dst + 4) = o1;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < kTcGroupsPerBlock; ++j)
-                            if (pb * kTcGroupsPerBlock + j < a.G) dst[j] = a.accumulate ? dst[j] + out[j] : out[j];
+                        for (int jj = 0; jj < kPer; ++jj)
+                            if (gbase + jj < a.G) dst[jj] = a.accumulate ? dst[jj] + out[jj] : out[jj];
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             }
-            __syncthreads();  // accumulator (gb-1)&1 drained by every warp before block gb+1 overwrites it
+            if (have_next) store_x(buf ^ 1, xn);  // A buffer (t+1)&1 was last read by MMA(t-1), complete above
+            __syncthreads();  // accumulator (t-1)&1 drained and A tile t+1 visible before the next issue
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -327,18 +408,18 @@ int launch_niw_tc_scores(dist_b200_ctx *ctx, int G, const float *tc_buf, const v
     a.prior = prior;
     a.scores = scores;
     const int images = split ? 2 : 1;
-    const size_t smem = sizeof(float) * (static_cast<size_t>(kTcRows) * kTcDim * images + 2 * images * kTcImageFloats +
-                                         static_cast<size_t>(nb) * (256 + 32 + 8)) + 64 + 1024;
-    if (smem > 227 * 1024) return DIST_B200_ERR_UNSUPPORTED;  // too many groups for the resident b / consts tables
+    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(images) * kTcRows * kTcDim + static_cast<size_t>(images) * kTcImageFloats +
+                                         256 + 32 + 8) + 64 + 1024;
     const size_t ntiles = (N + kTcRows - 1) / kTcRows;
-    const unsigned grid = static_cast<unsigned>(ntiles < static_cast<size_t>(ctx->sm_count) ? ntiles : ctx->sm_count);
+    const size_t nitems = ((ntiles + kTcChunkTiles - 1) / kTcChunkTiles) * static_cast<size_t>(nb);
+    const unsigned grid = static_cast<unsigned>(nitems < static_cast<size_t>(ctx->sm_count) ? nitems : ctx->sm_count);
     cudaError_t e;
     if (split) {
         e = cudaFuncSetAttribute(niw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess) niw_tc_kernel<true><<<grid, kTcRows, smem, s>>>(a);
+        if (e == cudaSuccess) niw_tc_kernel<true><<<grid, kTcThreads, smem, s>>>(a);
     } else {
         e = cudaFuncSetAttribute(niw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess) niw_tc_kernel<false><<<grid, kTcRows, smem, s>>>(a);
+        if (e == cudaSuccess) niw_tc_kernel<false><<<grid, kTcThreads, smem, s>>>(a);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("niw_tc launch: ") + cudaGetErrorString(e));
