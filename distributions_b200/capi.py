@@ -43,6 +43,12 @@ SIGNATURES = {
     "dist_b200_score_batch": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_i, c_p]),
     "dist_b200_score_sample_batch": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_p, c_p, c_p]),
     "dist_b200_sample_from_scores": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p, c_p]),
+    "dist_b200_peer_alloc": (c_i, [c_p, c_sz, ctypes.POINTER(c_p), c_p]),
+    "dist_b200_peer_open": (c_i, [c_p, c_p, ctypes.POINTER(c_p)]),
+    "dist_b200_peer_close": (c_i, [c_p, c_p]),
+    "dist_b200_peer_free": (c_i, [c_p, c_p]),
+    "dist_b200_score_push_batch": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_sz, c_p, c_p, c_i, c_sz, c_p]),
+    "dist_b200_sample_from_slots": (c_i, [c_p, c_p, c_i, c_sz, c_sz, c_i, c_p, c_p, c_p]),
     "dist_b200_score_sample_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_p, c_p]),
     "dist_b200_score_value_host": (c_i, [c_p, c_p, c_p, c_p]),
     "dist_b200_numerics_probe": (c_i, [c_p, c_i, c_sz, c_p, c_p, c_p]),
@@ -149,6 +155,36 @@ class Context:
     def sample_from_scores(self, scores, n_rows, G, u, assign, stream=None):
         self.check(self.L.dist_b200_sample_from_scores(self.h, _dev_ptr(scores), n_rows, G, _dev_ptr(u), _dev_ptr(assign),
                                                        stream), "sample_from_scores")
+
+    # -- feature shards over peer memory ---------------------------------------------------------
+    def peer_alloc(self, nbytes):
+        """cudaMalloc a buffer and return (device pointer, 64-byte IPC handle)"""
+        ptr = c_p()
+        handle = (ctypes.c_ubyte * 64)()
+        self.check(self.L.dist_b200_peer_alloc(self.h, nbytes, ctypes.byref(ptr), handle), "peer_alloc")
+        return ptr.value, bytes(handle)
+
+    def peer_open(self, handle):
+        ptr = c_p()
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        self.check(self.L.dist_b200_peer_open(self.h, buf, ctypes.byref(ptr)), "peer_open")
+        return ptr.value
+
+    def peer_close(self, ptr):
+        self.check(self.L.dist_b200_peer_close(self.h, ptr), "peer_close")
+
+    def peer_free(self, ptr):
+        self.check(self.L.dist_b200_peer_free(self.h, ptr), "peer_free")
+
+    def score_push_batch(self, features, columns, n_rows, row0, prior, slot_ptrs, block_rows, stream=None):
+        F, fa, ca = self._lists(features, columns)
+        sp = (c_p * len(slot_ptrs))(*slot_ptrs)
+        self.check(self.L.dist_b200_score_push_batch(self.h, fa, F, ca, n_rows, row0, _dev_ptr(prior), sp, len(slot_ptrs),
+                                                     block_rows, stream), "score_push_batch")
+
+    def sample_from_slots(self, slots, n_slots, slot_stride, n_rows, G, u, assign, stream=None):
+        self.check(self.L.dist_b200_sample_from_slots(self.h, _dev_ptr(slots), n_slots, slot_stride, n_rows, G, _dev_ptr(u),
+                                                      _dev_ptr(assign), stream), "sample_from_slots")
 
     # -- host-buffer forms -----------------------------------------------------------------------
     def score_sample_batch_host(self, features, columns, prior, u, want_scores=False, assign_out=None):

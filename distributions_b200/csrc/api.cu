@@ -682,6 +682,78 @@ int dist_b200_sample_from_scores(dist_b200_ctx *ctx, const float *scores_dev, si
     return launch_sample_scores(ctx, scores_dev, n_rows, G, u_dev, assign_dev, as_stream(stream));
 }
 
+int dist_b200_peer_alloc(dist_b200_ctx *ctx, size_t bytes, void **dev_ptr, unsigned char handle_out[64]) {
+    if (!ctx || !dev_ptr || !handle_out || bytes == 0) return DIST_B200_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DISTB200_CUDA(ctx, cudaMalloc(dev_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dev_ptr);
+        *dev_ptr = nullptr;
+        return fail(ctx, DIST_B200_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    std::memcpy(handle_out, &h, 64);
+    return DIST_B200_OK;
+}
+
+int dist_b200_peer_open(dist_b200_ctx *ctx, const unsigned char handle[64], void **dev_ptr) {
+    if (!ctx || !handle || !dev_ptr) return DIST_B200_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    DISTB200_CUDA(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DIST_B200_OK;
+}
+
+int dist_b200_peer_close(dist_b200_ctx *ctx, void *dev_ptr) {
+    if (!ctx || !dev_ptr) return DIST_B200_ERR_INVALID;
+    DISTB200_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return DIST_B200_OK;
+}
+
+int dist_b200_peer_free(dist_b200_ctx *ctx, void *dev_ptr) {
+    if (!ctx || !dev_ptr) return DIST_B200_ERR_INVALID;
+    DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+    DISTB200_CUDA(ctx, cudaFree(dev_ptr));
+    return DIST_B200_OK;
+}
+
+int dist_b200_score_push_batch(dist_b200_ctx *ctx, const dist_b200_feature *const *features, int F,
+                               const void *const *columns_dev, size_t n_rows, size_t row0, const float *prior_dev,
+                               void *const *slot_ptrs, int n_owners, size_t block_rows, void *stream) {
+    if (!ctx || !features || !columns_dev || F < 1 || !slot_ptrs || n_owners < 1 || block_rows == 0) return DIST_B200_ERR_INVALID;
+    if (n_owners > kMaxPushOwners) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_push: more than 16 owners");
+    if (F > kMaxFeatures) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_push: more than 512 features in one call");
+    const int G = features[0] ? features[0]->G : 0;
+    if (G < 1) return fail(ctx, DIST_B200_ERR_STATE, "score_push: feature 0 has no groups");
+    if ((row0 + n_rows + block_rows - 1) / block_rows > static_cast<size_t>(n_owners))
+        return fail(ctx, DIST_B200_ERR_INVALID, "score_push: rows extend past the last owner's block");
+    cudaStream_t s = as_stream(stream);
+    int rc = wait_ready(ctx, features, F, s);
+    if (rc) return rc;
+    FeatList fl;
+    fl.n = F;
+    for (int f = 0; f < F; ++f) {
+        if (!features[f] || !columns_dev[f] || features[f]->ctx != ctx || features[f]->G != G)
+            return fail(ctx, DIST_B200_ERR_INVALID, "score_push: bad feature list");
+        if (features[f]->model == DIST_B200_DPD || features[f]->model == DIST_B200_NIW)
+            return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_push: row-mapped models only");
+        if ((rc = fill_desc(ctx, features[f], columns_dev[f], true, fl.f[f], s))) return rc;
+    }
+    PushTargets pt{};
+    pt.n = n_owners;
+    pt.row0 = row0;
+    pt.block_rows = block_rows;
+    for (int i = 0; i < n_owners; ++i) pt.ptr[i] = static_cast<float *>(slot_ptrs[i]);
+    return launch_score_rows(ctx, fl, G, n_rows, prior_dev, nullptr, nullptr, nullptr, 0, s, &pt);
+}
+
+int dist_b200_sample_from_slots(dist_b200_ctx *ctx, const float *slots_dev, int n_slots, size_t slot_stride,
+                                size_t n_rows, int G, const float *u_dev, int32_t *assign_dev, void *stream) {
+    if (!ctx || !slots_dev || n_slots < 1 || !u_dev || !assign_dev || G < 1) return DIST_B200_ERR_INVALID;
+    return launch_sample_scores(ctx, slots_dev, n_rows, G, u_dev, assign_dev, as_stream(stream), n_slots, slot_stride);
+}
+
 static size_t value_bytes(const dist_b200_feature *f) {
     switch (f->model) {
         case DIST_B200_BB: return 1;

@@ -11,6 +11,7 @@
 
 namespace distb200 {
 
+constexpr int kMaxPushOwners = 16;  // ranks of one NVLink domain a feature-sharded launch can push to
 constexpr int kMaxFeatures = 512;  // feature descriptors travel in kernel-parameter space (16 KB)
 
 // device view of one feature, consumed by the row-mapped score kernel
@@ -25,6 +26,13 @@ struct FeatDesc {
 // internal kind: GammaPoisson scored through a per-(group, value) table for small counts
 constexpr int kKindGpTable = 6;
 constexpr int kGpTableX = 32;
+
+// destinations of a peer-push launch (see RowsArgs)
+struct PushTargets {
+    int n;
+    size_t row0, block_rows;
+    float *ptr[kMaxPushOwners];
+};
 
 struct FeatList {
     int n;
@@ -117,7 +125,8 @@ int launch_unpack_caches(dist_b200_ctx *ctx, const dist_b200_feature *f, float *
 
 // score_rows.cu: rows mapped to lanes, groups looped (nich / gp / bb / small-dim dd, any F)
 int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N, const float *prior,
-                      const float *u, int32_t *assign, float *scores, int accumulate, cudaStream_t s);
+                      const float *u, int32_t *assign, float *scores, int accumulate, cudaStream_t s,
+                      const PushTargets *push = nullptr);
 int launch_gp_table(dist_b200_ctx *ctx, int n_groups, const float4 *params, float *table, cudaStream_t s);
 // gather_rows.cu: one warp per row, groups mapped to lanes (value-major tables: dpd, wide dd) and the
 // stand-alone sampler over materialised scores
@@ -125,7 +134,7 @@ int launch_gather_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const voi
                        const float *prior, const float *u, int32_t *assign, float *scores, int accumulate,
                        cudaStream_t s);
 int launch_sample_scores(dist_b200_ctx *ctx, const float *scores, size_t N, int G, const float *u,
-                         int32_t *assign, cudaStream_t s);
+                         int32_t *assign, cudaStream_t s, int n_slots = 1, size_t slot_stride = 0);
 // niw.cu
 int niw_padded_dim(int d);
 int launch_niw_prep(dist_b200_ctx *ctx, int d, const float *mu, float kappa, const float *psi, float nu, int G,

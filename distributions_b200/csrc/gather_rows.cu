@@ -33,6 +33,8 @@ struct GatherArgs {
     const int *key_rows;     // table row of sorted key i
     const float *prior;      // [G] or nullptr
     const float *scores_in;  // scores mode: [N][G]
+    int n_slots;             // scores mode: the row is the sum of n_slots partial rows ...
+    size_t slot_stride;      // ... slot_stride floats apart (feature-shard slots, summed in slot order)
     const float *u;
     int32_t *assign;         // nullable
     float *scores_out;       // nullable ([N][G])
@@ -66,6 +68,7 @@ __global__ void __launch_bounds__(kGatherThreadsMax) gather_rows_kernel(const Ga
         float m = -INFINITY;
         for (int g = lane; g < G; g += 32) {
             float s = src[g];
+            for (int k = 1; k < a.n_slots; ++k) s += src[k * a.slot_stride + g];
             if (a.table) {
                 if (a.accumulate) s += out[g];          // slave semantic: accumulate onto the buffer
                 else if (a.prior) s = a.prior[g] + s;   // clustering overwrite, then the slave adds
@@ -146,7 +149,13 @@ __global__ void __launch_bounds__(kFastWarps * 32) gather_rows_fast_kernel(const
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int g = 32 * k + lane;
-            s[k] = g < G ? src[g] + prior[k] : -INFINITY;   // prior + (scores_[v][g] - shift[g])
+            float v = -INFINITY;
+            if (g < G) {
+                v = src[g];
+                for (int sl = 1; sl < a.n_slots; ++sl) v += src[sl * a.slot_stride + g];  // fixed slot order
+                v += prior[k];  // prior + (scores_[v][g] - shift[g])
+            }
+            s[k] = v;
         }
         float m = s[0];
 #pragma unroll
@@ -256,15 +265,18 @@ int launch_gather_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const voi
     a.u = u;
     a.assign = assign;
     a.scores_out = scores;
+    a.n_slots = 1;
     return launch_gather(ctx, a, s);
 }
 
 int launch_sample_scores(dist_b200_ctx *ctx, const float *scores, size_t N, int G, const float *u,
-                         int32_t *assign, cudaStream_t s) {
+                         int32_t *assign, cudaStream_t s, int n_slots, size_t slot_stride) {
     GatherArgs a{};
     a.G = G;
     a.N = N;
     a.scores_in = scores;
+    a.n_slots = n_slots;
+    a.slot_stride = slot_stride;
     a.u = u;
     a.assign = assign;
     return launch_gather(ctx, a, s);

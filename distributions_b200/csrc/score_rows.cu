@@ -174,10 +174,16 @@ struct RowsArgs {
     int32_t *assign;
     float *scores;
     NumericTables t;
+    // peer push (feature shards): row r of this launch is global row row0 + r; it belongs to owner
+    // (row0 + r) / block_rows and is stored into that owner's slot for this rank, push[owner] (a peer
+    // device pointer mapped over NVLink), at local row (row0 + r) % block_rows
+    int n_push;
+    size_t row0, block_rows;
+    float *push[kMaxPushOwners];
 };
 
 template <int CHUNK, int KIND, bool kSample, bool kScores, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : (CHUNK <= 32 ? 3 : (CHUNK <= 64 ? 2 : 1)))
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : (CHUNK <= 32 ? (KIND >= 0 ? 4 : 3) : (CHUNK <= 64 ? 2 : 1)))
 score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     constexpr int kThreads = THREADS;  // block size of this instantiation
     extern __shared__ __align__(16) float smem[];
@@ -355,7 +361,13 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                         for (int i = 0; i < 32; ++i) {
                             const size_t rr = wrow0 + i;
                             if (rr >= a.N) break;
-                            float *dst = a.scores + rr * G + g;
+                            float *dst;
+                            if (a.n_push) {
+                                const size_t grow = a.row0 + rr;
+                                dst = a.push[grow / a.block_rows] + (grow % a.block_rows) * G + g;
+                            } else {
+                                dst = a.scores + rr * G + g;
+                            }
                             const float v = tw[i * 33 + lane];
                             *dst = a.accumulate ? *dst + v : v;
                         }
@@ -558,9 +570,17 @@ static int launch_tiers(dist_b200_ctx *ctx, const FeatList &feats, const RowsArg
 }
 
 int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N, const float *prior,
-                      const float *u, int32_t *assign, float *scores, int accumulate, cudaStream_t s) {
+                      const float *u, int32_t *assign, float *scores, int accumulate, cudaStream_t s,
+                      const PushTargets *push) {
     if (N == 0 || G == 0) return DIST_B200_OK;
     RowsArgs a{};
+    if (push) {
+        a.n_push = push->n;
+        a.row0 = push->row0;
+        a.block_rows = push->block_rows;
+        for (int i = 0; i < push->n; ++i) a.push[i] = push->ptr[i];
+        scores = push->ptr[0];  // selects the score-materialising kernel variants
+    }
     a.G = G;
     a.N = N;
     a.prior = prior;

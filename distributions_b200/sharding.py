@@ -119,3 +119,52 @@ def feature_sharded_score_sample(score_partial, sample_block, n_rows, n_groups, 
     if pending is not None:
         finish(pending)
     return owned_assign, owned_rows
+
+
+class PeerFeatureShards:
+    """Feature shards with the reduction fused into the score kernel over NVLink peer memory.
+
+    Every rank owns the contiguous row block `rank` (block_rows(n_rows, world) rows) and holds `world`
+    slots [block][G]; rank r's score kernel stores its partial rows straight into slot r of the owning
+    rank (CUDA IPC mapping, dist_b200_score_push_batch), so the transfer overlaps the math tile by tile
+    and no partial [N][G] tile is written to local HBM.  The owner samples the fixed-order sum of its
+    slots (dist_b200_sample_from_slots).  Needs one process per GPU on one NVLink domain.
+    """
+
+    def __init__(self, ctx, n_rows, n_groups, group=None):
+        self.ctx, self.group = ctx, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_rows, self.G = n_rows, n_groups
+        self.block = block_rows(n_rows, self.world)
+        self.slot_floats = self.block * n_groups
+        self.mine, handle = ctx.peer_alloc(4 * self.world * self.slot_floats)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self.bases = [self.mine if r == self.rank else ctx.peer_open(h) for r, h in enumerate(handles)]
+        # this rank's slot inside every owner's buffer
+        self.slot_ptrs = [b + 4 * self.rank * self.slot_floats for b in self.bases]
+
+    def owned(self):
+        lo = min(self.rank * self.block, self.n_rows)
+        return lo, min(lo + self.block, self.n_rows)
+
+    def step(self, features, columns, prior, u, assign_out, stream=None):
+        """features / columns: this rank's shard (>= 1 feature); prior: device [G], applied by rank 0;
+        u: device [n_rows]; assign_out: device int32 [rows owned].  Returns the owned row range."""
+        assert len(features) >= 1, "every rank needs at least one feature of the kind"
+        self.ctx.score_push_batch(features, columns, self.n_rows, 0, prior if self.rank == 0 else None,
+                                  self.slot_ptrs, self.block, stream=stream)
+        dist.barrier(group=self.group)  # every rank's pushes have landed in the owners' slots
+        lo, hi = self.owned()
+        if hi > lo:
+            self.ctx.sample_from_slots(self.mine, self.world, self.slot_floats, hi - lo, self.G, u[lo:hi], assign_out,
+                                       stream=stream)
+        dist.barrier(group=self.group)  # owners are done reading before the next step overwrites the slots
+        return lo, hi
+
+    def close(self):
+        for r, b in enumerate(self.bases):
+            if r != self.rank:
+                self.ctx.peer_close(b)
+        self.ctx.peer_free(self.mine)

@@ -162,6 +162,27 @@ int dist_b200_score_sample_batch(dist_b200_ctx *ctx, const dist_b200_feature *co
 int dist_b200_sample_from_scores(dist_b200_ctx *ctx, const float *scores_dev, size_t n_rows, int G,
                                  const float *u_dev, int32_t *assign_dev, void *stream);
 
+/* ---- feature shards over NVLink peer memory (one process per GPU) ----------------------------------
+ * scores[n][g] = prior[g] + sum_f s_f[n][g] is a sum over features.  With the features of
+ * a kind sharded over K ranks, each rank scores its features for every row and stores the partial row
+ * DIRECTLY into the owning rank's memory -- owner = row / block_rows -- from inside the score kernel, so
+ * the NVLink transfer overlaps the math tile by tile and the partial [N][G] tile never touches local HBM.
+ * Every owner holds K slots [block_rows][G] (slot r written by rank r) and samples the fixed-order sum of
+ * its slots (deterministic, unlike atomics).  Buffers are exchanged as CUDA IPC handles. */
+int dist_b200_peer_alloc(dist_b200_ctx *ctx, size_t bytes, void **dev_ptr, unsigned char handle_out[64]);
+int dist_b200_peer_open(dist_b200_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+int dist_b200_peer_close(dist_b200_ctx *ctx, void *dev_ptr);
+int dist_b200_peer_free(dist_b200_ctx *ctx, void *dev_ptr);
+/* Partial scores of rows [row0, row0 + n_rows) for this rank's features, pushed to the owners' slots:
+ * slot_ptrs[o] is the (peer-mapped) base of THIS rank's slot in owner o's buffer.  prior_dev is passed
+ * by exactly one rank.  Row-mapped models only (nich / gp / bb / dd). */
+int dist_b200_score_push_batch(dist_b200_ctx *ctx, const dist_b200_feature *const *features, int n_features,
+                               const void *const *columns_dev, size_t n_rows, size_t row0, const float *prior_dev,
+                               void *const *slot_ptrs, int n_owners, size_t block_rows, void *stream);
+/* sample_from_scores over the sum of n_slots partial score blocks, slot_stride floats apart. */
+int dist_b200_sample_from_slots(dist_b200_ctx *ctx, const float *slots_dev, int n_slots, size_t slot_stride,
+                                size_t n_rows, int G, const float *u_dev, int32_t *assign_dev, void *stream);
+
 /* ---- host-buffer forms: the call a reference-side binding makes.  Same
  * semantics with HOST pointers; inputs are staged through pinned memory, copied to the device,
  * scored there, and results copied back before returning. */

@@ -1,0 +1,85 @@
+"""Two-GPU tests of the feature-shard paths (NCCL reduce-scatter and the fused NVLink peer push).
+Needs >= 2 CUDA devices: skipped on single-GPU boxes (run with `gpurun --gpus 2`)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n, G, F, out_dir):
+    import torch.distributed as dist
+    from distributions_b200 import capi, sharding, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    cc = synth.crosscat(911, G, n, n_gp=F // 2, n_bb=F - F // 2)
+    ids = {"gp": capi.GP, "bb": capi.BB}
+    ctx = capi.Context(rank)
+    mine = sharding.feature_shard(F, rank, world)
+    feats = [ctx.feature(ids[cc["features"][f]["model"]]).update_all(cc["features"][f]) for f in mine]
+    cols = [torch.from_numpy(np.ascontiguousarray(cc["features"][f]["values"],
+                                                  dtype=capi.COLUMN_DTYPE[ids[cc["features"][f]["model"]]])).to(dev) for f in mine]
+    u = torch.from_numpy(cc["u"]).to(dev)
+    prior = torch.empty(G, device=dev)
+    ctx.prior_pitman_yor(synth.PY_ALPHA, synth.PY_D, cc["sizes"], prior)
+    # (1) fused peer push
+    shards = sharding.PeerFeatureShards(ctx, n, G)
+    lo, hi = shards.owned()
+    a_push = torch.full((hi - lo,), -1, device=dev, dtype=torch.int32)
+    for _ in range(2):  # twice: slots are reused across steps
+        shards.step(feats, cols, prior, u, a_push)
+    torch.cuda.synchronize()
+
+    # (2) NCCL reduce-scatter orchestration
+    def score_partial(l, h, out):
+        ctx.score_batch(feats, [c[l:h] for c in cols], h - l, prior if rank == 0 else None, out)
+
+    def sample_block(scores, ub, out):
+        ctx.sample_from_scores(scores, scores.shape[0], G, ub, out)
+
+    assigns, rows = sharding.feature_sharded_score_sample(score_partial, sample_block, n, G, u, dev, tile_rows=1024,
+                                                          comm_stream=torch.cuda.Stream(device=dev))
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), lo=lo, hi=hi, a_push=a_push.cpu().numpy(), rows=np.array(rows),
+             a_rs=np.concatenate([a.cpu().numpy() for a in assigns]))
+    shards.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_feature_shards_two_gpus(tmp_path, oracle):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    import torch.multiprocessing as mp
+    import cases
+    from distributions_b200 import synth
+    world, n, G, F = 2, 5000, 40, 6
+    port = 29600 + os.getpid() % 1000
+    mp.spawn(_worker, args=(world, port, n, G, F, str(tmp_path)), nprocs=world, join=True)
+    cc = synth.crosscat(911, G, n, n_gp=F // 2, n_bb=F - F // 2)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, cc["sizes"])
+    full = cases.oracle_scores(oracle, cc["features"], prior=prior)
+    want = oracle.sample_rows(full.copy(), cc["u"])
+    got_push = np.full(n, -1, np.int32)
+    got_rs = np.full(n, -1, np.int32)
+    for r in range(world):
+        d = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        got_push[int(d["lo"]):int(d["hi"])] = d["a_push"]
+        off = 0
+        for lo, hi in d["rows"]:
+            got_rs[lo:hi] = d["a_rs"][off:off + hi - lo]
+            off += hi - lo
+    for got in (got_push, got_rs):
+        assert got.min() >= 0
+        assert cases.explained_mismatch(full.astype(np.float64), cc["u"], got, want, 2e-5).all()
+        assert np.mean(got == want) > 0.995
