@@ -356,7 +356,14 @@ def run_b200_feature_sharded(args):
         ctx.sample_from_scores(scores, scores.shape[0], G, ub, out, stream=stream)
         launches[0] += 1
 
+    peer = sharding.PeerFeatureShards(ctx, N, G) if args.shard_mode == "push" else None
+    lo_own, hi_own = peer.owned() if peer else (0, 0)
+    assign_own = torch.empty(max(hi_own - lo_own, 1), device=dev, dtype=torch.int32)
+
     def step():
+        if peer is not None:  # reduction fused into the score kernel over NVLink peer memory
+            launches[0] += 2
+            return peer.step(feats, cols, prior, u, assign_own, stream=stream)
         return sharding.feature_sharded_score_sample(score_partial, sample_block, N, G, u, dev, tile_rows=args.tile_rows,
                                                      comm_stream=comm)
 
@@ -390,8 +397,11 @@ def run_b200_feature_sharded(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "rows": N, "groups": G, "features": F,
-                       "parallelism": "feature shards (%d per rank) + NCCL reduce-scatter(sum) of [rows][G] partials, "
-                                      "tiles of %d rows overlapped on a second stream" % (len(mine), args.tile_rows),
+                       "parallelism": ("feature shards (%d per rank), partial rows pushed into the owner's slot over NVLink "
+                                       "peer memory from inside the score kernel, owner samples the slot sum" % len(mine))
+                       if peer is not None else
+                       ("feature shards (%d per rank) + NCCL reduce-scatter(sum) of [rows][G] partials, "
+                        "tiles of %d rows overlapped on a second stream" % (len(mine), args.tile_rows)),
                        "l2": "inputs (640 MB of columns + 512 MB of partial scores per step) exceed the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches[0],
             "nvlink_bytes_per_step_per_rank": int(4 * N * G * (world - 1) / world),
@@ -410,6 +420,8 @@ def main():
     ap.add_argument("--workload", default="c2_nich", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--tile-rows", type=int, default=65536, help="row tile of the feature-sharded reduce-scatter")
+    ap.add_argument("--shard-mode", default="push", choices=["push", "rs"],
+                    help="c3 at N>1: fused NVLink peer push (default) or NCCL reduce-scatter")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
