@@ -147,15 +147,17 @@ __global__ void __launch_bounds__(kFastWarps * 32) gather_rows_fast_kernel(const
                                    : a.scores_in + n * G;
         float s[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
+        for (int k = 0; k < K; ++k) {  // K independent loads in flight
             const int g = 32 * k + lane;
-            float v = -INFINITY;
-            if (g < G) {
-                v = src[g];
-                for (int sl = 1; sl < a.n_slots; ++sl) v += src[sl * a.slot_stride + g];  // fixed slot order
-                v += prior[k];  // prior + (scores_[v][g] - shift[g])
+            s[k] = g < G ? src[g] + prior[k] : -INFINITY;  // prior + (scores_[v][g] - shift[g])
+        }
+        for (int sl = 1; sl < a.n_slots; ++sl) {  // feature-shard slots, summed in fixed slot order
+            const float *ss = src + sl * a.slot_stride;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int g = 32 * k + lane;
+                if (g < G) s[k] += ss[g];
             }
-            s[k] = v;
         }
         float m = s[0];
 #pragma unroll
