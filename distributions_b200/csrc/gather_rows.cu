@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(kFastWarps * 32) gather_rows_fast_kernel(const
         const int g = 32 * k + lane;
         prior[k] = (a.table && a.prior && g < G) ? a.prior[g] : 0.f;
     }
-    // this lane's contiguous segment [lane*K, lane*K + K) in skewed coordinates
+    // this lane's contiguous segment [lane*K, lane*K + K) in skewed coordinates: K divides 32, so the
+    // segment never crosses a 32-boundary and skew(lane*K + kk) = seg0 + kk
+    const int seg0 = lane * K + ((lane * K) >> 5);
     const unsigned full = 0xffffffffu;
     for (size_t n = static_cast<size_t>(blockIdx.x) * kFastWarps + warp; n < a.N;
          n += static_cast<size_t>(gridDim.x) * kFastWarps) {
@@ -171,10 +173,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) gather_rows_fast_kernel(const
         __syncwarp();
         float part = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < K; ++kk) {
-            const int i = lane * K + kk;
-            part += lik[i + (i >> 5)];
-        }
+        for (int kk = 0; kk < K; ++kk) part += lik[seg0 + kk];
         float incl = part;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
