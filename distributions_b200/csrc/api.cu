@@ -199,6 +199,7 @@ void dist_b200_ctx_destroy(dist_b200_ctx *ctx) {
     if (ctx->tables_storage) cudaFree(ctx->tables_storage);
     if (ctx->scratch_dev) cudaFree(ctx->scratch_dev);
     if (ctx->scores_scratch) cudaFree(ctx->scores_scratch);
+    if (ctx->xpack) cudaFree(ctx->xpack);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->own_stream2) cudaStreamDestroy(ctx->own_stream2);

@@ -52,6 +52,8 @@ struct dist_b200_ctx {
     size_t pinned_bytes = 0;
     void *scratch_dev = nullptr;
     size_t scratch_bytes = 0;
+    void *xpack = nullptr;            // niw tensor path: rows packed into A-operand images
+    size_t xpack_bytes = 0;
     void *scores_scratch = nullptr;   // [N][G] buffer of the materialising dispatch paths
     size_t scores_scratch_bytes = 0;
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;

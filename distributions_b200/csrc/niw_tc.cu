@@ -20,6 +20,8 @@
 // of 8-group blocks, pre-laid-out by niw_tc_prep_kernel in the canonical no-swizzle K-major core-matrix
 // order, stream in with cp.async.bulk + mbarrier (double buffered); one thread issues the MMAs and a
 // tcgen05.commit; the epilogue of block b-1 runs while the tensor pipe works on block b.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace distb200 {
@@ -377,6 +379,232 @@ __global__ void __launch_bounds__(kTcThreads, 1) niw_tc_kernel(const NiwTcArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-specialised form.  The row tiles are first packed once into the A-operand images
+// (niw_tc_pack_x_kernel: TF32-exact hi part + remainder, core-matrix order, zero padded), so that the
+// main kernel moves EVERY operand with cp.async.bulk and no thread touches operand data:
+//   warp 0 (one lane)  : loader  -- W images of the item, then the A images of its row tiles through a
+//                                   kAStages-deep ring (a_full / a_empty mbarriers)
+//   warp 1 (one lane)  : issuer  -- tcgen05.mma for tile t into TMEM buffer t & 1; tcgen05.commit frees
+//                                   the A stage (a_empty) and publishes the accumulator (t_full)
+//   warps 2..9         : epilogue -- tcgen05.ld, release the TMEM buffer (t_empty) as soon as the loads
+//                                   have landed, then sums of squares / MUFU.LG2 / score stores
+// so the tensor pipe runs tile t+1 while the epilogue drains tile t, with no block-wide barrier.
+constexpr int kAStages = 3;
+constexpr int kWsThreads = 320;
+
+template <bool kSplit>
+__global__ void niw_tc_pack_x_kernel(size_t N, size_t ntiles, const float *__restrict__ values, float *__restrict__ xpack) {
+    constexpr int kImages = kSplit ? 2 : 1;
+    constexpr int kAFloats = kTcRows * kTcDim;
+    // one thread per (row, k-core): 4 floats
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= ntiles * kTcRows * 8) return;
+    const size_t row = i >> 3;
+    const int c = static_cast<int>(i & 7);
+    const size_t tile = row / kTcRows;
+    const int r = static_cast<int>(row % kTcRows);
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < N) x = __ldg(reinterpret_cast<const float4 *>(values + row * kTcDim) + c);
+    float4 hi;
+    hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+    hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+    hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+    hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+    float *base = xpack + tile * kImages * kAFloats;
+    const int off = core_offset_floats(r, c * 4, kTcRows / 8);
+    *reinterpret_cast<float4 *>(base + off) = kSplit ? hi : x;
+    if (kSplit) *reinterpret_cast<float4 *>(base + kAFloats + off) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+}
+
+template <bool kSplit>
+__global__ void __launch_bounds__(kWsThreads, 1) niw_tc_ws_kernel(const NiwTcArgs a, const float *__restrict__ xpack) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int kImages = kSplit ? 2 : 1;
+    constexpr int kAFloats = kTcRows * kTcDim;
+    float *As = reinterpret_cast<float *>(smem_raw);                          // [kAStages][kImages][16 KB]
+    float *Bs = As + kAStages * kImages * kAFloats;                           // [kImages][32 KB]
+    float *bs = Bs + kImages * kTcImageFloats;                                // [256] -b
+    float *cs = bs + 256;                                                     // [8][4]
+    float *ps = cs + 32;                                                      // [8]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ps + 8);
+    uint64_t *a_full = bars, *a_empty = bars + kAStages, *t_full = bars + 2 * kAStages, *t_empty = t_full + 2;
+    uint64_t *b_full = t_empty + 2, *b_empty = b_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = a.n_blocks;
+    if (tid == 0) {
+        for (int i = 0; i < kAStages; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], 8);  // one arrival per epilogue warp
+        }
+        mbar_init(b_full, 1);
+        mbar_init(b_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t image_bytes = kTcImageFloats * sizeof(float), a_bytes = kAFloats * sizeof(float);
+
+    const size_t ntiles = (a.N + kTcRows - 1) / kTcRows;
+    const size_t nchunks = (ntiles + kTcChunkTiles - 1) / kTcChunkTiles;
+    const size_t nitems = nchunks * nb;
+
+    if (warp == 0) {
+        // ===================== loader =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, bphase = 0;
+            for (size_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int blk = static_cast<int>(item % nb);
+                const size_t t0 = (item / nb) * kTcChunkTiles, t1 = t0 + kTcChunkTiles < ntiles ? t0 + kTcChunkTiles : ntiles;
+                mbar_wait(b_empty, bphase ^ 1);  // every MMA of the previous item has finished reading Bs
+                mbar_expect_tx(b_full, kImages * image_bytes);
+                for (int im = 0; im < kImages; ++im)
+                    bulk_g2s(Bs + im * kTcImageFloats, a.images + (static_cast<size_t>(blk) * 2 + im) * kTcImageFloats, image_bytes, b_full);
+                bphase ^= 1;
+                for (size_t t = t0; t < t1; ++t) {
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&a_full[stage], kImages * a_bytes);
+                    bulk_g2s(As + stage * kImages * kAFloats, xpack + t * kImages * kAFloats, kImages * a_bytes, &a_full[stage]);
+                    if (++stage == kAStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, bphase = 0, tphase[2] = {0, 0};
+            int tb = 0;
+            for (size_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const size_t t0 = (item / nb) * kTcChunkTiles, t1 = t0 + kTcChunkTiles < ntiles ? t0 + kTcChunkTiles : ntiles;
+                mbar_wait(b_full, bphase);
+                bphase ^= 1;
+                for (size_t t = t0; t < t1; ++t) {
+                    mbar_wait(&a_full[stage], phase);
+                    mbar_wait(&t_empty[tb], tphase[tb] ^ 1);  // epilogue has drained this accumulator
+                    tphase[tb] ^= 1;
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t d_addr = tmem_base + tb * 256;
+                    const uint32_t a_hi = smem_u32(As + stage * kImages * kAFloats), a_lo = a_hi + a_bytes;
+                    const uint32_t b_hi = smem_u32(Bs), b_lo = b_hi + image_bytes;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t ao = ks * 2 * (kTcRows / 8) * 128, bo = ks * 2 * 32 * 128;
+                        umma_tf32(d_addr, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, acc);
+                        acc = 1;
+                        if (kSplit) {
+                            umma_tf32(d_addr, make_smem_desc(a_lo + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, 1);
+                            umma_tf32(d_addr, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_lo + bo, 32 * 128, 128), idesc, 1);
+                        }
+                    }
+                    umma_commit(&a_empty[stage]);  // A stage reusable once these MMAs retire
+                    umma_commit(&t_full[tb]);      // accumulator ready for the epilogue
+                    if (++stage == kAStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    tb ^= 1;
+                }
+                umma_commit(b_empty);  // all MMAs of this item retired -> Bs may be overwritten
+            }
+        }
+    } else {
+        // ===================== epilogue (8 warps) =====================
+        const int e = warp - 2;        // 0..7
+        const int q = warp & 3;        // TMEM lane quarter this warp may access
+        const int h = e >> 2;          // column half: groups [4h, 4h + 4)
+        const int r_in_tile = q * 32 + lane;
+        constexpr int kPer = kTcGroupsPerBlock / 2;
+        uint32_t fphase[2] = {0, 0};
+        int tb = 0;
+        for (size_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int blk = static_cast<int>(item % nb);
+            const size_t t0 = (item / nb) * kTcChunkTiles, t1 = t0 + kTcChunkTiles < ntiles ? t0 + kTcChunkTiles : ntiles;
+            // per-block tables (the previous item's epilogue must be finished in all 8 warps first)
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            const int et = tid - 64;
+            bs[et] = a.bvec[static_cast<size_t>(blk) * 256 + et];
+            if (et < 32) cs[et] = a.consts[static_cast<size_t>(blk) * 32 + et];
+            if (et < 8) {
+                const int g = blk * kTcGroupsPerBlock + et;
+                ps[et] = (g < a.G && a.prior && !a.accumulate) ? a.prior[g] : 0.f;
+            }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            for (size_t t = t0; t < t1; ++t) {
+                mbar_wait(&t_full[tb], fphase[tb]);
+                fphase[tb] ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                uint32_t yr[2][64];
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tb * 256 + h * kPer * 32;
+                tmem_ld64_nowait(t_row, yr[0]);
+                tmem_ld64_nowait(t_row + 64, yr[1]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                if (lane == 0) {  // accumulator drained by this warp: one of the 8 arrivals
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&t_empty[tb])) : "memory");
+                }
+                tb ^= 1;
+                float out[kPer];
+#pragma unroll
+                for (int jj = 0; jj < kPer; ++jj) {
+                    const int j = h * kPer + jj;
+                    const uint32_t *y = &yr[jj >> 1][(jj & 1) * 32];
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bs + j * 32);
+                    uint64_t qa = 0ull, qb = 0ull;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 nb4 = b4[i];  // holds -b
+                        const uint64_t d0 = add2(pack2(__uint_as_float(y[4 * i]), __uint_as_float(y[4 * i + 1])), pack2(nb4.x, nb4.y));
+                        const uint64_t d1 = add2(pack2(__uint_as_float(y[4 * i + 2]), __uint_as_float(y[4 * i + 3])), pack2(nb4.z, nb4.w));
+                        qa = fma2(d0, d0, qa);
+                        qb = fma2(d1, d1, qb);
+                    }
+                    const float qq = sum2(qa) + sum2(qb);
+                    const float4 c = *reinterpret_cast<const float4 *>(cs + j * 4);
+                    const float arg = __fadd_rn(1.f, __fmul_rn(c.z, qq));
+                    out[jj] = fmaf(c.y, fast_log2_cell(arg), c.x) + ps[j];
+                }
+                const size_t row = t * kTcRows + r_in_tile;
+                if (row < a.N) {
+                    const int gbase = blk * kTcGroupsPerBlock + h * kPer;
+                    float *dst = a.scores + row * a.G + gbase;
+                    if (gbase + kPer <= a.G && (a.G & 3) == 0) {
+                        float4 o0 = make_float4(out[0], out[1], out[2], out[3]);
+                        if (a.accumulate) {
+                            const float4 p0 = *reinterpret_cast<float4 *>(dst);
+                            o0 = make_float4(o0.x + p0.x, o0.y + p0.y, o0.z + p0.z, o0.w + p0.w);
+                        }
+                        *reinterpret_cast<float4 *>(dst) = o0;
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < kPer; ++jj)
+                            if (gbase + jj < a.G) dst[jj] = a.accumulate ? dst[jj] + out[jj] : out[jj];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 size_t niw_tc_floats(int G) {
     const size_t nb = (G + kTcGroupsPerBlock - 1) / kTcGroupsPerBlock;
     return nb * (2 * kTcImageFloats + 256 + 32);
@@ -408,18 +636,51 @@ int launch_niw_tc_scores(dist_b200_ctx *ctx, int G, const float *tc_buf, const v
     a.prior = prior;
     a.scores = scores;
     const int images = split ? 2 : 1;
-    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(images) * kTcRows * kTcDim + static_cast<size_t>(images) * kTcImageFloats +
-                                         256 + 32 + 8) + 64 + 1024;
     const size_t ntiles = (N + kTcRows - 1) / kTcRows;
     const size_t nitems = ((ntiles + kTcChunkTiles - 1) / kTcChunkTiles) * static_cast<size_t>(nb);
     const unsigned grid = static_cast<unsigned>(nitems < static_cast<size_t>(ctx->sm_count) ? nitems : ctx->sm_count);
+    static const bool use_ws = [] {
+        const char *e = getenv("DIST_B200_NIW_WS");
+        return !(e && e[0] == '0');
+    }();
     cudaError_t e;
-    if (split) {
-        e = cudaFuncSetAttribute(niw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess) niw_tc_kernel<true><<<grid, kTcThreads, smem, s>>>(a);
+    if (use_ws) {
+        // pack the rows into A-operand images once, then the warp-specialised pipeline
+        const size_t xbytes = sizeof(float) * ntiles * images * kTcRows * kTcDim;
+        if (xbytes > ctx->xpack_bytes) {
+            if (ctx->xpack) {
+                DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+                DISTB200_CUDA(ctx, cudaFree(ctx->xpack));
+                ctx->xpack = nullptr;
+                ctx->xpack_bytes = 0;
+            }
+            DISTB200_CUDA(ctx, cudaMalloc(&ctx->xpack, xbytes));
+            ctx->xpack_bytes = xbytes;
+        }
+        float *xpack = static_cast<float *>(ctx->xpack);
+        const size_t nthreads = ntiles * kTcRows * 8;
+        const unsigned pgrid = static_cast<unsigned>((nthreads + 255) / 256);
+        const size_t smem = sizeof(float) * (static_cast<size_t>(kAStages) * images * kTcRows * kTcDim +
+                                             static_cast<size_t>(images) * kTcImageFloats + 256 + 32 + 8) + 256 + 1024;
+        if (split) {
+            niw_tc_pack_x_kernel<true><<<pgrid, 256, 0, s>>>(N, ntiles, a.values, xpack);
+            e = cudaFuncSetAttribute(niw_tc_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e == cudaSuccess) niw_tc_ws_kernel<true><<<grid, kWsThreads, smem, s>>>(a, xpack);
+        } else {
+            niw_tc_pack_x_kernel<false><<<pgrid, 256, 0, s>>>(N, ntiles, a.values, xpack);
+            e = cudaFuncSetAttribute(niw_tc_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e == cudaSuccess) niw_tc_ws_kernel<false><<<grid, kWsThreads, smem, s>>>(a, xpack);
+        }
     } else {
-        e = cudaFuncSetAttribute(niw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess) niw_tc_kernel<false><<<grid, kTcThreads, smem, s>>>(a);
+        const size_t smem = sizeof(float) * (2 * static_cast<size_t>(images) * kTcRows * kTcDim + static_cast<size_t>(images) * kTcImageFloats +
+                                             256 + 32 + 8) + 64 + 1024;
+        if (split) {
+            e = cudaFuncSetAttribute(niw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e == cudaSuccess) niw_tc_kernel<true><<<grid, kTcThreads, smem, s>>>(a);
+        } else {
+            e = cudaFuncSetAttribute(niw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e == cudaSuccess) niw_tc_kernel<false><<<grid, kTcThreads, smem, s>>>(a);
+        }
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("niw_tc launch: ") + cudaGetErrorString(e));
