@@ -3,6 +3,7 @@
 // every scoring / sampling call ends in a kernel launch or an error code.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -823,7 +824,11 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
         prior_dev = reinterpret_cast<const float *>(dev + prior_off);
     }
     const size_t min_chunk = 32768;
-    size_t nchunks = std::min<size_t>(8, std::max<size_t>(1, N / min_chunk));
+    static const size_t max_chunks = [] {
+        const char *e = getenv("DIST_B200_HOST_CHUNKS");
+        return e ? static_cast<size_t>(std::max(1, atoi(e))) : static_cast<size_t>(6);  // measured optimum at 1M rows
+    }();
+    size_t nchunks = std::min<size_t>(max_chunks, std::max<size_t>(1, N / min_chunk));
     for (int f = 0; f < F; ++f)  // paths that materialise through the context's single scores buffer: no overlap
         if (features[f]->model == DIST_B200_NIW || (features[f]->model == DIST_B200_DPD && F > 1)) nchunks = 1;
     const size_t chunk = round_up((N + nchunks - 1) / nchunks, 256);
