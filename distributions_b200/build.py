@@ -26,6 +26,7 @@ SOURCES = {
     "niw.cu": [],
     "niw_tc.cu": [],
     "microbench.cu": [],
+    "stats.cu": [],
 }
 
 

@@ -37,6 +37,10 @@ SIGNATURES = {
     "dist_b200_feature_update_group": (c_i, [c_p, c_i, c_p, c_p]),
     "dist_b200_feature_add_group": (c_i, [c_p, c_p]),
     "dist_b200_feature_remove_group": (c_i, [c_p, c_i, c_p]),
+    "dist_b200_feature_add_rows": (c_i, [c_p, c_p, c_p, c_sz, c_p]),
+    "dist_b200_feature_download_stats": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
+    "dist_b200_count_assignments": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_i, c_p]),
+    "dist_b200_prior_pitman_yor_dev": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
     "dist_b200_feature_download_caches": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
     "dist_b200_prior_pitman_yor": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
     "dist_b200_prior_pitman_yor_host": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p]),
@@ -134,6 +138,14 @@ class Context:
         sizes = np.ascontiguousarray(group_sizes, dtype=np.int32)
         self.check(self.L.dist_b200_prior_pitman_yor(self.h, alpha, d, sizes.size, _np_ptr(sizes), _dev_ptr(prior_dev),
                                                      stream), "prior_pitman_yor")
+
+    def count_assignments(self, assign_dev, n_rows, G, counts_dev, accumulate=False, stream=None):
+        self.check(self.L.dist_b200_count_assignments(self.h, _dev_ptr(assign_dev), n_rows, G, _dev_ptr(counts_dev),
+                                                      1 if accumulate else 0, stream), "count_assignments")
+
+    def prior_pitman_yor_dev(self, alpha, d, G, sizes_dev, prior_dev, stream=None):
+        self.check(self.L.dist_b200_prior_pitman_yor_dev(self.h, alpha, d, G, _dev_ptr(sizes_dev), _dev_ptr(prior_dev), stream),
+                   "prior_pitman_yor_dev")
 
     # -- hot path (device pointers) --------------------------------------------------------------
     def _lists(self, features, columns):
@@ -286,6 +298,18 @@ class Feature:
 
     def remove_group(self, groupid, stream=None):
         self.ctx.check(self.ctx.L.dist_b200_feature_remove_group(self.h, groupid, stream), "remove_group")
+
+    def add_rows(self, column_dev, assign_dev, n_rows, stream=None):
+        """batched Group::add_value: fold rows into their assigned groups on the device, rebuild the caches"""
+        self.ctx.check(self.ctx.L.dist_b200_feature_add_rows(self.h, _dev_ptr(column_dev), _dev_ptr(assign_dev), n_rows, stream),
+                       "add_rows")
+
+    def download_stats(self, nbytes, stream=None):
+        out = np.empty(nbytes, dtype=np.uint8)
+        n = c_sz()
+        self.ctx.check(self.ctx.L.dist_b200_feature_download_stats(self.h, _np_ptr(out), out.size, ctypes.byref(n), stream),
+                       "download_stats")
+        return out[:n.value]
 
     def download_caches(self, rows, stream=None):
         G = self.groups

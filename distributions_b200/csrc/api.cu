@@ -68,6 +68,57 @@ size_t group_floats(const dist_b200_feature *f) {
     }
 }
 
+// device-side raw statistics: number of arrays and 4-byte elements per group of array a
+int stat_arrays(const dist_b200_feature *f) {
+    switch (f->model) {
+        case DIST_B200_NICH: return 3;
+        case DIST_B200_GP: case DIST_B200_BB: return 2;
+        case DIST_B200_DD: return 1;
+        default: return 0;
+    }
+}
+size_t stat_elems(const dist_b200_feature *f, int) { return f->model == DIST_B200_DD ? static_cast<size_t>(f->dim) : 1; }
+uint32_t *stat_ptr(const dist_b200_feature *f, int a) {
+    size_t off = 0;
+    for (int b = 0; b < a; ++b) off += stat_elems(f, b) * f->capacity;
+    return f->stats + off;
+}
+// (re)allocate the statistics arrays for the feature's current capacity, keeping the first old_G groups
+int ensure_stats(dist_b200_feature *f, int old_capacity, int old_G, bool keep) {
+    dist_b200_ctx *ctx = f->ctx;
+    const int na = stat_arrays(f);
+    if (na == 0) return DIST_B200_OK;
+    size_t words = 0;
+    for (int a = 0; a < na; ++a) words += stat_elems(f, a) * f->capacity;
+    if (f->stats && old_capacity == f->capacity && words <= f->stats_words) return DIST_B200_OK;
+    uint32_t *fresh = nullptr;
+    DISTB200_CUDA(ctx, cudaMalloc(&fresh, words * 4));
+    DISTB200_CUDA(ctx, cudaMemset(fresh, 0, words * 4));
+    if (f->stats) {
+        if (keep && old_capacity > 0) {
+            size_t off_old = 0, off_new = 0;
+            for (int a = 0; a < na; ++a) {
+                const size_t e = stat_elems(f, a);
+                DISTB200_CUDA(ctx, cudaMemcpy(fresh + off_new, f->stats + off_old, e * std::min(old_G, f->capacity) * 4, cudaMemcpyDeviceToDevice));
+                off_old += e * old_capacity;
+                off_new += e * f->capacity;
+            }
+        }
+        DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+        DISTB200_CUDA(ctx, cudaFree(f->stats));
+    }
+    f->stats = fresh;
+    f->stats_words = words;
+    return DIST_B200_OK;
+}
+// copy `n` groups of statistics (device pointer, e.g. the freshly uploaded scratch) into array a from group g0
+int mirror_stats(dist_b200_feature *f, int a, const void *src_dev, int g0, int n, cudaStream_t s) {
+    if (!f->stats || n <= 0) return DIST_B200_OK;
+    const size_t e = stat_elems(f, a);
+    DISTB200_CUDA(f->ctx, cudaMemcpyAsync(stat_ptr(f, a) + e * g0, src_dev, e * n * 4, cudaMemcpyDeviceToDevice, s));
+    return DIST_B200_OK;
+}
+
 // (re)allocate the hot-layout buffer for `G` groups, zero-filled, padded to 128 groups so that the
 // score kernel may stage whole register tiles
 int ensure_params(dist_b200_feature *f, int G, bool keep) {
@@ -79,7 +130,9 @@ int ensure_params(dist_b200_feature *f, int G, bool keep) {
     } else {
         bytes = sizeof(float) * group_floats(f) * cap;
     }
-    if (bytes <= f->params_bytes && (f->model == DIST_B200_DPD || cap <= f->capacity)) return DIST_B200_OK;
+    const int old_capacity = f->capacity, old_G = f->G;
+    if (bytes <= f->params_bytes && (f->model == DIST_B200_DPD || cap <= f->capacity))
+        return ensure_stats(f, f->stats ? old_capacity : 0, old_G, keep);
     void *fresh = nullptr;
     const size_t want = f->model == DIST_B200_DPD ? bytes : sizeof(float) * group_floats(f) * round_up(cap + cap / 2, 128);
     DISTB200_CUDA(ctx, cudaMalloc(&fresh, want));
@@ -102,7 +155,7 @@ int ensure_params(dist_b200_feature *f, int G, bool keep) {
         }
         f->aux = aux;
     }
-    return DIST_B200_OK;
+    return ensure_stats(f, old_capacity, old_G, keep);
 }
 
 // copy host arrays into consecutive, 256-byte aligned regions of the context scratch
@@ -237,6 +290,7 @@ void dist_b200_feature_destroy(dist_b200_feature *f) {
     if (f->key_rows_dev) cudaFree(f->key_rows_dev);
     if (f->niw_buf) cudaFree(f->niw_buf);
     if (f->niw_tc) cudaFree(f->niw_tc);
+    if (f->stats) cudaFree(f->stats);
     if (f->ready) cudaEventDestroy(f->ready);
     delete f;
 }
@@ -258,6 +312,9 @@ int dist_b200_nich_update_all(dist_b200_feature *f, const float shared[4], int G
     const float *v = up.put(ctv, G);
     if (up.err) return up.err;
     f->G = G;
+    if ((rc = mirror_stats(f, 0, c, 0, G, as_stream(stream))) || (rc = mirror_stats(f, 1, m, 0, G, as_stream(stream))) ||
+        (rc = mirror_stats(f, 2, v, 0, G, as_stream(stream))))
+        return rc;
     return mark_ready(f, launch_nich_prep(ctx, f->shared, G, 0, G, c, m, v, static_cast<float4 *>(f->params), f->aux, as_stream(stream)), as_stream(stream));
 }
 
@@ -276,6 +333,7 @@ int dist_b200_gp_update_all(dist_b200_feature *f, const float shared[2], int G, 
     if (up.err) return up.err;
     f->G = G;
     f->gp_table_dirty = true;
+    if ((rc = mirror_stats(f, 0, c, 0, G, as_stream(stream))) || (rc = mirror_stats(f, 1, sm, 0, G, as_stream(stream)))) return rc;
     return mark_ready(f, launch_gp_prep(ctx, f->shared, 0, G, c, sm, static_cast<float4 *>(f->params), as_stream(stream)), as_stream(stream));
 }
 
@@ -293,6 +351,7 @@ int dist_b200_bb_update_all(dist_b200_feature *f, const float shared[2], int G, 
     const int32_t *t = up.put(tails, G);
     if (up.err) return up.err;
     f->G = G;
+    if ((rc = mirror_stats(f, 0, h, 0, G, as_stream(stream))) || (rc = mirror_stats(f, 1, t, 0, G, as_stream(stream)))) return rc;
     return mark_ready(f, launch_bb_prep(ctx, f->shared, 0, G, h, t, static_cast<float4 *>(f->params), as_stream(stream)), as_stream(stream));
 }
 
@@ -323,6 +382,7 @@ int dist_b200_dd_update_all(dist_b200_feature *f, int dim, const float *alphas, 
     const int32_t *c = up.put(counts, static_cast<size_t>(G) * dim);
     if (up.err) return up.err;
     f->G = G;
+    if ((rc = mirror_stats(f, 0, c, 0, G, as_stream(stream)))) return rc;
     return mark_ready(f, launch_dd_prep(ctx, dim, a, alpha_sum, 0, G, c, static_cast<float *>(f->params), as_stream(stream)), as_stream(stream));
 }
 
@@ -368,6 +428,20 @@ int dist_b200_dpd_update_all(dist_b200_feature *f, float alpha, float beta0, int
     const int32_t *c = up.put(counts, static_cast<size_t>(G) * V);
     if (up.err) return up.err;
     f->G = G;
+    {   // device-resident statistics: counts[G][V] | betas[V]
+        const size_t words = static_cast<size_t>(G) * V + V;
+        if (words > f->stats_words) {
+            if (f->stats) {
+                DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+                DISTB200_CUDA(ctx, cudaFree(f->stats));
+                f->stats = nullptr;
+            }
+            DISTB200_CUDA(ctx, cudaMalloc(&f->stats, words * 4));
+            f->stats_words = words;
+        }
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(f->stats, c, sizeof(int32_t) * static_cast<size_t>(G) * V, cudaMemcpyDeviceToDevice, as_stream(stream)));
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(f->stats + static_cast<size_t>(G) * V, b, sizeof(float) * V, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    }
     return mark_ready(f, launch_dpd_prep(ctx, alpha, beta0, V, b, G, c, static_cast<float *>(f->params), as_stream(stream)), as_stream(stream));
 }
 
@@ -439,6 +513,9 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             const float *m = up.put(reinterpret_cast<const float *>(p + 4), 1);
             const float *v = up.put(reinterpret_cast<const float *>(p + 8), 1);
             if (up.err) return up.err;
+            if ((rc = mirror_stats(f, 0, c, groupid, 1, s)) || (rc = mirror_stats(f, 1, m, groupid, 1, s)) ||
+                (rc = mirror_stats(f, 2, v, groupid, 1, s)))
+                return rc;
             return mark_ready(f, launch_nich_prep(ctx, f->shared, f->G, groupid, 1, c, m, v, static_cast<float4 *>(f->params), f->aux, s), s);
         }
         case DIST_B200_GP: {
@@ -447,6 +524,7 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             const uint32_t *sm = up.put(p + 1, 1);
             if (up.err) return up.err;
             f->gp_table_dirty = true;
+            if ((rc = mirror_stats(f, 0, c, groupid, 1, s)) || (rc = mirror_stats(f, 1, sm, groupid, 1, s))) return rc;
             return mark_ready(f, launch_gp_prep(ctx, f->shared, groupid, 1, c, sm, static_cast<float4 *>(f->params), s), s);
         }
         case DIST_B200_BB: {
@@ -454,12 +532,14 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             const int32_t *h = up.put(p, 1);
             const int32_t *t = up.put(p + 1, 1);
             if (up.err) return up.err;
+            if ((rc = mirror_stats(f, 0, h, groupid, 1, s)) || (rc = mirror_stats(f, 1, t, groupid, 1, s))) return rc;
             return mark_ready(f, launch_bb_prep(ctx, f->shared, groupid, 1, h, t, static_cast<float4 *>(f->params), s), s);
         }
         case DIST_B200_DD: {
             const float *a = up.put(f->alphas.data(), f->dim);
             const int32_t *c = up.put(static_cast<const int32_t *>(stats), f->dim);
             if (up.err) return up.err;
+            if ((rc = mirror_stats(f, 0, c, groupid, 1, s))) return rc;
             return mark_ready(f, launch_dd_prep(ctx, f->dim, a, f->alpha_sum, groupid, 1, c, static_cast<float *>(f->params), s), s);
         }
         default:
@@ -494,10 +574,101 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
         DISTB200_CUDA(ctx, cudaMemcpyAsync(base + gb * groupid, base + gb * last, gb, cudaMemcpyDeviceToDevice, as_stream(stream)));
     DISTB200_CUDA(ctx, cudaMemsetAsync(base + gb * last, 0, gb, as_stream(stream)));
     f->gp_table_dirty = true;
+    if (f->stats && groupid != last) {
+        for (int a = 0; a < stat_arrays(f); ++a) {
+            const size_t e = stat_elems(f, a);
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(stat_ptr(f, a) + e * groupid, stat_ptr(f, a) + e * last, e * 4, cudaMemcpyDeviceToDevice,
+                                               as_stream(stream)));
+        }
+    }
     if (f->aux && groupid != last)
         DISTB200_CUDA(ctx, cudaMemcpyAsync(f->aux + groupid, f->aux + last, sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
     f->G = last;
     return mark_ready(f, DIST_B200_OK, as_stream(stream));
+}
+
+int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, const int32_t *assign_dev, size_t n_rows,
+                               void *stream) {
+    if (!f || !f->ctx || !column_dev || !assign_dev) return DIST_B200_ERR_INVALID;
+    dist_b200_ctx *ctx = f->ctx;
+    if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: niw statistics stay on the host");
+    if (f->G < 1 || !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: call update_all first");
+    cudaStream_t s = as_stream(stream);
+    DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
+    const size_t sb = add_rows_scratch_bytes(f) + round_up(sizeof(float) * 256, 256) + 256;
+    int rc = ensure_scratch(ctx, sb);
+    if (rc) return rc;
+    if ((rc = launch_add_rows(ctx, f, column_dev, assign_dev, n_rows, ctx->scratch_dev, add_rows_scratch_bytes(f), s))) return rc;
+    // rebuild the caches from the updated statistics (update_all on device-resident Groups)
+    const int G = f->G;
+    switch (f->model) {
+        case DIST_B200_NICH:
+            rc = launch_nich_prep(ctx, f->shared, G, 0, G, reinterpret_cast<const int32_t *>(stat_ptr(f, 0)),
+                                  reinterpret_cast<const float *>(stat_ptr(f, 1)), reinterpret_cast<const float *>(stat_ptr(f, 2)),
+                                  static_cast<float4 *>(f->params), f->aux, s);
+            break;
+        case DIST_B200_GP:
+            f->gp_table_dirty = true;
+            rc = launch_gp_prep(ctx, f->shared, 0, G, stat_ptr(f, 0), stat_ptr(f, 1), static_cast<float4 *>(f->params), s);
+            break;
+        case DIST_B200_BB:
+            rc = launch_bb_prep(ctx, f->shared, 0, G, reinterpret_cast<const int32_t *>(stat_ptr(f, 0)),
+                                reinterpret_cast<const int32_t *>(stat_ptr(f, 1)), static_cast<float4 *>(f->params), s);
+            break;
+        case DIST_B200_DD: {
+            float *a_dev = reinterpret_cast<float *>(static_cast<char *>(ctx->scratch_dev) + add_rows_scratch_bytes(f));
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(a_dev, f->alphas.data(), sizeof(float) * f->dim, cudaMemcpyHostToDevice, s));
+            rc = launch_dd_prep(ctx, f->dim, a_dev, f->alpha_sum, 0, G, reinterpret_cast<const int32_t *>(stat_ptr(f, 0)),
+                                static_cast<float *>(f->params), s);
+        } break;
+        case DIST_B200_DPD:
+            rc = launch_dpd_prep(ctx, f->alpha, f->beta0, f->dim, reinterpret_cast<const float *>(f->stats + static_cast<size_t>(G) * f->dim),
+                                 G, reinterpret_cast<const int32_t *>(f->stats), static_cast<float *>(f->params), s);
+            break;
+        default: rc = DIST_B200_ERR_UNSUPPORTED;
+    }
+    return mark_ready(f, rc, s);
+}
+
+int dist_b200_feature_download_stats(const dist_b200_feature *f, void *out_host, size_t capacity_bytes, size_t *n_bytes,
+                                     void *stream) {
+    if (!f || !f->ctx || !out_host) return DIST_B200_ERR_INVALID;
+    dist_b200_ctx *ctx = f->ctx;
+    if (!f->stats) return fail(ctx, DIST_B200_ERR_STATE, "download_stats: no device statistics (update_all first)");
+    cudaStream_t s = as_stream(stream);
+    DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
+    char *out = static_cast<char *>(out_host);
+    size_t total = 0;
+    if (f->model == DIST_B200_DPD) {
+        total = sizeof(int32_t) * static_cast<size_t>(f->G) * f->dim;
+        if (n_bytes) *n_bytes = total;
+        if (total > capacity_bytes) return fail(ctx, DIST_B200_ERR_INVALID, "download_stats: buffer too small");
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(out, f->stats, total, cudaMemcpyDeviceToHost, s));
+    } else {
+        for (int a = 0; a < stat_arrays(f); ++a) total += stat_elems(f, a) * f->G * 4;
+        if (n_bytes) *n_bytes = total;
+        if (total > capacity_bytes) return fail(ctx, DIST_B200_ERR_INVALID, "download_stats: buffer too small");
+        size_t off = 0;
+        for (int a = 0; a < stat_arrays(f); ++a) {
+            const size_t b = stat_elems(f, a) * f->G * 4;
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(out + off, stat_ptr(f, a), b, cudaMemcpyDeviceToHost, s));
+            off += b;
+        }
+    }
+    DISTB200_CUDA(ctx, cudaStreamSynchronize(s));
+    return DIST_B200_OK;
+}
+
+int dist_b200_count_assignments(dist_b200_ctx *ctx, const int32_t *assign_dev, size_t n_rows, int G, int32_t *counts_dev,
+                                int accumulate, void *stream) {
+    if (!ctx || !assign_dev || !counts_dev || G < 1) return DIST_B200_ERR_INVALID;
+    return launch_count_assignments(ctx, assign_dev, n_rows, G, counts_dev, accumulate, as_stream(stream));
+}
+
+int dist_b200_prior_pitman_yor_dev(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *group_sizes_dev,
+                                   float *prior_dev, void *stream) {
+    if (!ctx || G < 1 || !group_sizes_dev || !prior_dev) return DIST_B200_ERR_INVALID;
+    return launch_prior_prep(ctx, alpha, d, G, group_sizes_dev, prior_dev, as_stream(stream));
 }
 
 int dist_b200_feature_download_caches(const dist_b200_feature *f, float *out_host, size_t capacity_floats,

@@ -82,6 +82,12 @@ struct dist_b200_feature {
     int gp_table_cap = 0;
     bool gp_table_dirty = true;
     cudaEvent_t ready = nullptr;      // recorded after every cache mutation; scoring streams wait on it
+    // device-resident raw group statistics (mirror of the host Groups; the state that batched
+    // add_value updates in place): arrays of `capacity` groups, 4-byte elements
+    //   nich: count | mean | count_times_variance     gp: count | sum     bb: heads | tails
+    //   dd: counts[capacity][dim]                      dpd: counts[G][V] | betas[V]
+    uint32_t *stats = nullptr;
+    size_t stats_words = 0;
     uint32_t *keys_dev = nullptr;     // dpd sorted keys
     int *key_rows_dev = nullptr;      // dpd: table row of sorted key i
     // niw
@@ -130,6 +136,12 @@ int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N
                       const float *u, int32_t *assign, float *scores, int accumulate, cudaStream_t s,
                       const PushTargets *push = nullptr);
 int launch_gp_table(dist_b200_ctx *ctx, int n_groups, const float4 *params, float *table, cudaStream_t s);
+// stats.cu: batched Group::add_value (segmented reduction of assigned rows into the device-side statistics)
+int launch_add_rows(dist_b200_ctx *ctx, dist_b200_feature *f, const void *column, const int32_t *assign, size_t N,
+                    void *scratch, size_t scratch_bytes, cudaStream_t s);
+size_t add_rows_scratch_bytes(const dist_b200_feature *f);
+int launch_count_assignments(dist_b200_ctx *ctx, const int32_t *assign, size_t N, int G, int32_t *counts, int accumulate,
+                             cudaStream_t s);
 // gather_rows.cu: one warp per row, groups mapped to lanes (value-major tables: dpd, wide dd) and the
 // stand-alone sampler over materialised scores
 int launch_gather_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *column, size_t N,

@@ -113,6 +113,28 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
 int dist_b200_feature_add_group(dist_b200_feature *f, void *stream);
 int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stream);
 
+/* ---- batched Group::add_value on the device (next row of the path: score -> sample -> UPDATE) -----
+ * Folds n_rows values into the groups given by assign_dev[n] (packed ids; negative = skip) with one
+ * segmented reduction, merges into the device-resident statistics (the arrays last given to update_all /
+ * update_group) and rebuilds the caches, without a host round trip.  Reference, per value:
+ * Group::add_value + MixtureValueScorer::add_value (nich.hpp:125-133,326-333; gp.hpp:109-116,275-282;
+ * bb.hpp:102-107,258-265; dd.hpp:123-130,381-388; dpd.hpp:188-196,430-447).  Counts are exact; nich's
+ * mean / count_times_variance use the pairwise merge of Group::merge (nich.hpp:167-179) instead of N
+ * sequential Welford steps (agreement ~1e-6 relative).  niw: not supported (statistics stay on the host). */
+int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, const int32_t *assign_dev, size_t n_rows,
+                               void *stream);
+/* Device-resident statistics back to the host, arrays in update_all's argument order, G entries each
+ * (nich: count,int32 | mean,f32 | ctv,f32; gp: count | sum; bb: heads | tails; dd: counts[G][dim];
+ * dpd: counts[G][V]).  Synchronises the stream. */
+int dist_b200_feature_download_stats(const dist_b200_feature *f, void *out_host, size_t capacity_bytes, size_t *n_bytes,
+                                     void *stream);
+/* MixtureDriver::counts() for a batch: counts_dev[g] (+)= #{n : assign_dev[n] == g}  (mixture.hpp:77-93). */
+int dist_b200_count_assignments(dist_b200_ctx *ctx, const int32_t *assign_dev, size_t n_rows, int G, int32_t *counts_dev,
+                                int accumulate, void *stream);
+/* dist_b200_prior_pitman_yor with the group sizes already on the device. */
+int dist_b200_prior_pitman_yor_dev(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *group_sizes_dev,
+                                   float *prior_dev, void *stream);
+
 /* Read the caches back in the reference's own struct-of-arrays layout (for parity tests):
  *   nich [4][G] score_, log_coeff_, precision_, mean_   (nich.hpp:379-384)
  *   gp   [3][G] score_, post_alpha_, score_coeff_       (gp.hpp:329-333)

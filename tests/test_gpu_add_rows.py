@@ -1,0 +1,134 @@
+"""Batched Group::add_value on the device (the first 'next' row of SURVEY.md §8f): the statistics and
+caches after dist_b200_feature_add_rows must equal the reference's one-value-at-a-time add_value
+(restated in the oracle / simple integer sums) followed by update_all; counts exactly, nich's float
+statistics within the pairwise-vs-sequential rounding (1e-5 relative)."""
+import numpy as np
+import pytest
+
+import cases
+from distributions_b200 import synth
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from distributions_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _expected_after_add(oracle, w, assign):
+    """apply Group::add_value for every (value, group) pair sequentially, the reference's way"""
+    w2 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in w.items()}
+    m, vals = w["model"], w["values"]
+    G = w["sizes"].size
+    if m == "nich":
+        for g in range(G):
+            xs = vals[assign == g]
+            if len(xs):
+                c, mean, ctv = oracle.nich_group_update(+1, int(w["count"][g]), float(w["mean"][g]), float(w["ctv"][g]), xs)
+                w2["count"][g], w2["mean"][g], w2["ctv"][g] = c, mean, ctv
+    elif m == "gp":
+        w2["count"] = w["count"] + np.bincount(assign, minlength=G).astype(np.uint32)
+        w2["sum"] = w["sum"] + np.bincount(assign, weights=vals.astype(np.float64), minlength=G).astype(np.uint32)
+    elif m == "bb":
+        w2["heads"] = w["heads"] + np.bincount(assign[vals != 0], minlength=G).astype(np.int32)
+        w2["tails"] = w["tails"] + np.bincount(assign[vals == 0], minlength=G).astype(np.int32)
+    elif m == "dd":
+        np.add.at(w2["counts"], (assign, vals), 1)
+    elif m == "dpd":
+        known = vals != 0xFFFFFFFF
+        np.add.at(w2["counts"], (assign[known], vals[known].astype(np.int64)), 1)
+    return w2
+
+
+@pytest.mark.parametrize("name,G,n", [("nich", 37, 5000), ("nich", 3000, 20000), ("gp", 21, 5000), ("bb", 13, 5000),
+                                      ("dd", 29, 5000), ("dpd", 19, 5000)])
+def test_add_rows_matches_sequential_add_value(ctx, oracle, name, G, n):
+    from distributions_b200 import capi
+    ids = {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH}
+    kw = dict(dim=16) if name == "dd" else (dict(V=100, other_frac=0.05) if name == "dpd" else {})
+    w = getattr(synth, name)(4000 + G, G, n, **kw)
+    rng = np.random.default_rng(G)
+    assign = rng.integers(0, G, n).astype(np.int32)
+    assign[::17] = -1  # rows left unassigned are skipped
+    f = ctx.feature(ids[name]).update_all(w)
+    col = dev(w["values"].astype(capi.COLUMN_DTYPE[ids[name]]))
+    f.add_rows(col, dev(assign), n)
+    keep = assign >= 0
+    want = _expected_after_add(oracle, dict(w, values=w["values"][keep]), assign[keep])
+    # statistics
+    if name == "nich":
+        raw = f.download_stats(12 * G)
+        cnt = raw[:4 * G].view(np.int32)
+        mean = raw[4 * G:8 * G].view(np.float32)
+        ctv = raw[8 * G:].view(np.float32)
+        assert np.array_equal(cnt, want["count"])
+        np.testing.assert_allclose(mean, want["mean"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(ctv, want["ctv"], rtol=2e-4, atol=1e-3)
+    elif name == "gp":
+        raw = f.download_stats(8 * G).view(np.uint32)
+        assert np.array_equal(raw[:G], want["count"]) and np.array_equal(raw[G:], want["sum"])
+    elif name == "bb":
+        raw = f.download_stats(8 * G).view(np.int32)
+        assert np.array_equal(raw[:G], want["heads"]) and np.array_equal(raw[G:], want["tails"])
+    elif name == "dd":
+        raw = f.download_stats(4 * G * 16).view(np.int32).reshape(G, 16)
+        assert np.array_equal(raw, want["counts"])
+    else:
+        raw = f.download_stats(4 * G * 100).view(np.int32).reshape(G, 100)
+        assert np.array_equal(raw, want["counts"])
+    # caches == update_all on the reference-side statistics
+    rows = {"nich": 4, "gp": 3, "bb": 2, "dd": 16, "dpd": 101}[name]
+    got = f.download_caches(rows)
+    exp = cases.oracle_caches(oracle, want)
+    if name in ("dd", "dpd"):
+        exp = exp[:-1] - exp[-1][None, :]
+        assert np.array_equal(got, exp)
+    elif name == "nich":
+        np.testing.assert_allclose(got, exp, rtol=3e-4, atol=3e-4)
+    else:
+        np.testing.assert_allclose(got, exp, rtol=2e-6, atol=2e-6)
+
+
+def test_device_side_sweep(ctx, oracle):
+    """score -> sample -> add_value -> prior update -> score again, all on the device; the second pass
+    must equal the oracle's scores for the statistics the first pass produced."""
+    from distributions_b200 import capi
+    G, n = 50, 4000
+    w = synth.nich(77, G, n)
+    f = ctx.feature(capi.NICH).update_all(w)
+    col, u = dev(w["values"]), dev(w["u"])
+    sizes = dev(w["sizes"].astype(np.int32))
+    prior = torch.empty(G, device="cuda")
+    ctx.prior_pitman_yor_dev(synth.PY_ALPHA, synth.PY_D, G, sizes, prior)
+    assign = torch.empty(n, device="cuda", dtype=torch.int32)
+    ctx.score_sample_batch([f], [col], n, prior, u, assign)
+    f.add_rows(col, assign, n)
+    ctx.count_assignments(assign, n, G, sizes, accumulate=True)
+    ctx.prior_pitman_yor_dev(synth.PY_ALPHA, synth.PY_D, G, sizes, prior)
+    scores = torch.empty((n, G), device="cuda")
+    assign2 = torch.empty(n, device="cuda", dtype=torch.int32)
+    ctx.score_sample_batch([f], [col], n, prior, u, assign2, scores)
+    torch.cuda.synchronize()
+    a1 = assign.cpu().numpy()
+    want = _expected_after_add(oracle, w, a1)
+    sizes2 = w["sizes"] + np.bincount(a1, minlength=G).astype(np.int32)
+    assert np.array_equal(sizes.cpu().numpy(), sizes2)
+    prior2 = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, sizes2)
+    np.testing.assert_allclose(prior.cpu().numpy(), prior2, atol=2e-6)
+    exp = cases.oracle_scores(oracle, [want], prior=prior2)
+    got = scores.cpu().numpy()
+    coeff = np.abs(oracle.nich_caches(want["shared"], want["count"], want["mean"], want["ctv"])[1])[None, :]
+    # statistics agree to ~1e-5 (pairwise vs sequential); a perturbed argument can cross a fast_log step
+    assert np.all(np.abs(got - exp) <= 2e-4 * (1 + np.abs(exp)) + 6.2e-5 * coeff)
+    assert np.median(np.abs(got - exp)) < 1e-4
