@@ -38,6 +38,7 @@ SIGNATURES = {
     "dist_b200_feature_add_group": (c_i, [c_p, c_p]),
     "dist_b200_feature_remove_group": (c_i, [c_p, c_i, c_p]),
     "dist_b200_feature_add_rows": (c_i, [c_p, c_p, c_p, c_sz, c_p]),
+    "dist_b200_add_rows_batch": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz, c_p]),
     "dist_b200_feature_download_stats": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
     "dist_b200_count_assignments": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_i, c_p]),
     "dist_b200_prior_pitman_yor_dev": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
@@ -138,6 +139,11 @@ class Context:
         sizes = np.ascontiguousarray(group_sizes, dtype=np.int32)
         self.check(self.L.dist_b200_prior_pitman_yor(self.h, alpha, d, sizes.size, _np_ptr(sizes), _dev_ptr(prior_dev),
                                                      stream), "prior_pitman_yor")
+
+    def add_rows_batch(self, features, columns, assign_dev, n_rows, stream=None):
+        """batched Group::add_value for all features of one kind; nothing is drained, later calls order behind it"""
+        F, fa, ca = self._lists(features, columns)
+        self.check(self.L.dist_b200_add_rows_batch(self.h, fa, F, ca, _dev_ptr(assign_dev), n_rows, stream), "add_rows_batch")
 
     def count_assignments(self, assign_dev, n_rows, G, counts_dev, accumulate=False, stream=None):
         self.check(self.L.dist_b200_count_assignments(self.h, _dev_ptr(assign_dev), n_rows, G, _dev_ptr(counts_dev),

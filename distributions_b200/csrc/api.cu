@@ -252,6 +252,8 @@ void dist_b200_ctx_destroy(dist_b200_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->tables_storage) cudaFree(ctx->tables_storage);
     if (ctx->scratch_dev) cudaFree(ctx->scratch_dev);
+    if (ctx->add_acc) cudaFree(ctx->add_acc);
+    if (ctx->add_done) cudaEventDestroy(ctx->add_done);
     if (ctx->scores_scratch) cudaFree(ctx->scores_scratch);
     if (ctx->xpack) cudaFree(ctx->xpack);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -291,6 +293,7 @@ void dist_b200_feature_destroy(dist_b200_feature *f) {
     if (f->niw_buf) cudaFree(f->niw_buf);
     if (f->niw_tc) cudaFree(f->niw_tc);
     if (f->stats) cudaFree(f->stats);
+    if (f->alphas_dev) cudaFree(f->alphas_dev);
     if (f->ready) cudaEventDestroy(f->ready);
     delete f;
 }
@@ -382,6 +385,8 @@ int dist_b200_dd_update_all(dist_b200_feature *f, int dim, const float *alphas, 
     const int32_t *c = up.put(counts, static_cast<size_t>(G) * dim);
     if (up.err) return up.err;
     f->G = G;
+    if (!f->alphas_dev) DISTB200_CUDA(ctx, cudaMalloc(&f->alphas_dev, sizeof(float) * 256));
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(f->alphas_dev, a, sizeof(float) * dim, cudaMemcpyDeviceToDevice, as_stream(stream)));
     if ((rc = mirror_stats(f, 0, c, 0, G, as_stream(stream)))) return rc;
     return mark_ready(f, launch_dd_prep(ctx, dim, a, alpha_sum, 0, G, c, static_cast<float *>(f->params), as_stream(stream)), as_stream(stream));
 }
@@ -587,47 +592,99 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
     return mark_ready(f, DIST_B200_OK, as_stream(stream));
 }
 
+// batched Group::add_value over many features of one kind.  Everything is enqueued on `stream`: the
+// accumulators live in a dedicated context buffer guarded by an event (not the upload scratch), so the
+// call returns without draining the stream; later scoring calls order themselves behind the features'
+// `ready` events.
+int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                             const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, void *stream) {
+    if (!ctx) return DIST_B200_ERR_INVALID;
+    if (n_features < 0 || (n_features && (!features || !columns_dev)) || !assign_dev)
+        return fail(ctx, DIST_B200_ERR_INVALID, "add_rows: null argument");
+    cudaStream_t s = as_stream(stream);
+    size_t acc_need = 0;
+    for (int i = 0; i < n_features; ++i) {
+        dist_b200_feature *f = features[i];
+        if (!f || f->ctx != ctx || !columns_dev[i]) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows: bad feature / column");
+        if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: niw statistics stay on the host");
+        if (f->G < 1 || !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: call update_all first");
+        if (f->model == DIST_B200_NICH || f->model == DIST_B200_GP || f->model == DIST_B200_BB)
+            acc_need = std::max(acc_need, add_rows_acc_bytes(f->G) * std::min(n_features, kAddBatch));
+    }
+    if (acc_need > ctx->add_acc_bytes) {
+        if (ctx->add_acc) {
+            DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+            DISTB200_CUDA(ctx, cudaFree(ctx->add_acc));
+            ctx->add_acc = nullptr;
+            ctx->add_acc_bytes = 0;
+        }
+        DISTB200_CUDA(ctx, cudaMalloc(&ctx->add_acc, acc_need));
+        ctx->add_acc_bytes = acc_need;
+    }
+    if (!ctx->add_done) DISTB200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->add_done, cudaEventDisableTiming));
+    DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, ctx->add_done, 0));  // the previous batch may have run on another stream
+    int rc = wait_ready(ctx, features, n_features, s);
+    if (rc) return rc;
+
+    AddBatch b{};
+    b.N = n_rows;
+    b.assign = assign_dev;
+    b.acc = static_cast<char *>(ctx->add_acc);
+    auto flush = [&]() -> int {
+        if (b.n == 0) return DIST_B200_OK;
+        b.acc_stride = add_rows_acc_bytes(b.G);
+        int r = launch_add_rows_pooled(ctx, b, s);
+        if (!r) r = launch_merge_prep_batch(ctx, b, s);
+        b.n = 0;
+        return r;
+    };
+    for (int i = 0; i < n_features; ++i) {
+        dist_b200_feature *f = features[i];
+        const int G = f->G;
+        switch (f->model) {
+            case DIST_B200_NICH:
+            case DIST_B200_GP:
+            case DIST_B200_BB: {
+                if (b.n == kAddBatch || (b.n && b.G != G))
+                    if ((rc = flush())) return rc;
+                b.G = G;
+                AddDesc &d = b.d[b.n++];
+                d.column = columns_dev[i];
+                d.st0 = stat_ptr(f, 0);
+                d.st1 = stat_ptr(f, 1);
+                d.st2 = f->model == DIST_B200_NICH ? stat_ptr(f, 2) : nullptr;
+                d.params = static_cast<float4 *>(f->params);
+                d.aux = f->aux;
+                for (int k = 0; k < 4; ++k) d.shared[k] = f->shared[k];
+                d.model = f->model;
+                if (f->model == DIST_B200_GP) f->gp_table_dirty = true;
+            } break;
+            case DIST_B200_DD:
+                if (!f->alphas_dev) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: dd alphas not resident (update_all first)");
+                if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, s))) return rc;
+                if ((rc = launch_dd_prep(ctx, f->dim, f->alphas_dev, f->alpha_sum, 0, G, reinterpret_cast<const int32_t *>(stat_ptr(f, 0)),
+                                         static_cast<float *>(f->params), s)))
+                    return rc;
+                break;
+            case DIST_B200_DPD:
+                if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, s))) return rc;
+                if ((rc = launch_dpd_prep(ctx, f->alpha, f->beta0, f->dim, reinterpret_cast<const float *>(f->stats + static_cast<size_t>(G) * f->dim),
+                                          G, reinterpret_cast<const int32_t *>(f->stats), static_cast<float *>(f->params), s)))
+                    return rc;
+                break;
+            default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: unsupported model");
+        }
+    }
+    if ((rc = flush())) return rc;
+    for (int i = 0; i < n_features; ++i) DISTB200_CUDA(ctx, cudaEventRecord(features[i]->ready, s));
+    DISTB200_CUDA(ctx, cudaEventRecord(ctx->add_done, s));
+    return DIST_B200_OK;
+}
+
 int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, const int32_t *assign_dev, size_t n_rows,
                                void *stream) {
-    if (!f || !f->ctx || !column_dev || !assign_dev) return DIST_B200_ERR_INVALID;
-    dist_b200_ctx *ctx = f->ctx;
-    if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: niw statistics stay on the host");
-    if (f->G < 1 || !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: call update_all first");
-    cudaStream_t s = as_stream(stream);
-    DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
-    const size_t sb = add_rows_scratch_bytes(f) + round_up(sizeof(float) * 256, 256) + 256;
-    int rc = ensure_scratch(ctx, sb);
-    if (rc) return rc;
-    if ((rc = launch_add_rows(ctx, f, column_dev, assign_dev, n_rows, ctx->scratch_dev, add_rows_scratch_bytes(f), s))) return rc;
-    // rebuild the caches from the updated statistics (update_all on device-resident Groups)
-    const int G = f->G;
-    switch (f->model) {
-        case DIST_B200_NICH:
-            rc = launch_nich_prep(ctx, f->shared, G, 0, G, reinterpret_cast<const int32_t *>(stat_ptr(f, 0)),
-                                  reinterpret_cast<const float *>(stat_ptr(f, 1)), reinterpret_cast<const float *>(stat_ptr(f, 2)),
-                                  static_cast<float4 *>(f->params), f->aux, s);
-            break;
-        case DIST_B200_GP:
-            f->gp_table_dirty = true;
-            rc = launch_gp_prep(ctx, f->shared, 0, G, stat_ptr(f, 0), stat_ptr(f, 1), static_cast<float4 *>(f->params), s);
-            break;
-        case DIST_B200_BB:
-            rc = launch_bb_prep(ctx, f->shared, 0, G, reinterpret_cast<const int32_t *>(stat_ptr(f, 0)),
-                                reinterpret_cast<const int32_t *>(stat_ptr(f, 1)), static_cast<float4 *>(f->params), s);
-            break;
-        case DIST_B200_DD: {
-            float *a_dev = reinterpret_cast<float *>(static_cast<char *>(ctx->scratch_dev) + add_rows_scratch_bytes(f));
-            DISTB200_CUDA(ctx, cudaMemcpyAsync(a_dev, f->alphas.data(), sizeof(float) * f->dim, cudaMemcpyHostToDevice, s));
-            rc = launch_dd_prep(ctx, f->dim, a_dev, f->alpha_sum, 0, G, reinterpret_cast<const int32_t *>(stat_ptr(f, 0)),
-                                static_cast<float *>(f->params), s);
-        } break;
-        case DIST_B200_DPD:
-            rc = launch_dpd_prep(ctx, f->alpha, f->beta0, f->dim, reinterpret_cast<const float *>(f->stats + static_cast<size_t>(G) * f->dim),
-                                 G, reinterpret_cast<const int32_t *>(f->stats), static_cast<float *>(f->params), s);
-            break;
-        default: rc = DIST_B200_ERR_UNSUPPORTED;
-    }
-    return mark_ready(f, rc, s);
+    if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
+    return dist_b200_add_rows_batch(f->ctx, &f, 1, &column_dev, assign_dev, n_rows, stream);
 }
 
 int dist_b200_feature_download_stats(const dist_b200_feature *f, void *out_host, size_t capacity_bytes, size_t *n_bytes,

@@ -39,6 +39,26 @@ struct FeatList {
     FeatDesc f[kMaxFeatures];
 };
 
+// batched Group::add_value over the pooled-statistics models (nich / gp / bb) of one kind: up to
+// kAddBatch features per launch, descriptors in kernel-parameter space
+constexpr int kAddBatch = 128;
+struct AddDesc {
+    const void *column;          // value column, N entries
+    uint32_t *st0, *st1, *st2;   // stored statistics (nich: count|mean|ctv, gp: count|sum, bb: heads|tails)
+    float4 *params;              // hot caches, rebuilt after the merge
+    float *aux;                  // nich: unscaled log_coeff_
+    float shared[4];             // hyper-parameters
+    int model, pad;
+};
+struct AddBatch {
+    int n, G;
+    size_t N;
+    const int32_t *assign;
+    char *acc;                   // per feature: cnt_a[G] | cnt_b[G] (int) | sum_x[G] | sum_xx[G] (double)
+    size_t acc_stride;           // bytes per feature
+    AddDesc d[kAddBatch];
+};
+
 }  // namespace distb200
 
 struct dist_b200_ctx {
@@ -58,6 +78,9 @@ struct dist_b200_ctx {
     size_t scores_scratch_bytes = 0;
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
     cudaEvent_t ev = nullptr;
+    void *add_acc = nullptr;          // batched add_value: per-feature accumulators (stats.cu)
+    size_t add_acc_bytes = 0;
+    cudaEvent_t add_done = nullptr;   // recorded after the last merge that read add_acc
 };
 
 struct dist_b200_feature {
@@ -88,6 +111,7 @@ struct dist_b200_feature {
     //   dd: counts[capacity][dim]                      dpd: counts[G][V] | betas[V]
     uint32_t *stats = nullptr;
     size_t stats_words = 0;
+    float *alphas_dev = nullptr;      // dd: alphas, resident for device-side cache rebuilds
     uint32_t *keys_dev = nullptr;     // dpd sorted keys
     int *key_rows_dev = nullptr;      // dpd: table row of sorted key i
     // niw
@@ -137,9 +161,13 @@ int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N
                       const PushTargets *push = nullptr);
 int launch_gp_table(dist_b200_ctx *ctx, int n_groups, const float4 *params, float *table, cudaStream_t s);
 // stats.cu: batched Group::add_value (segmented reduction of assigned rows into the device-side statistics)
-int launch_add_rows(dist_b200_ctx *ctx, dist_b200_feature *f, const void *column, const int32_t *assign, size_t N,
-                    void *scratch, size_t scratch_bytes, cudaStream_t s);
-size_t add_rows_scratch_bytes(const dist_b200_feature *f);
+// pooled models: accumulate `b.n` features in one launch (b.acc zeroed by the launcher), then merge + rebuild caches
+int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s);
+int launch_merge_prep_batch(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s);  // prep.cu
+// dd / dpd: counts updated in place
+int launch_add_rows_counts(dist_b200_ctx *ctx, dist_b200_feature *f, const void *column, const int32_t *assign, size_t N,
+                           cudaStream_t s);
+size_t add_rows_acc_bytes(int G);
 int launch_count_assignments(dist_b200_ctx *ctx, const int32_t *assign, size_t N, int G, int32_t *counts, int accumulate,
                              cudaStream_t s);
 // gather_rows.cu: one warp per row, groups mapped to lanes (value-major tables: dpd, wide dd) and the

@@ -11,50 +11,108 @@ namespace distb200 {
 // NormalInverseChiSq: Shared::plus_group (nich.hpp:58-69) + Scorer::init (nich.hpp:239-250)
 // packed as float4 {mean, precision, log_coeff * ln 2, score}: the hot loop multiplies the coefficient
 // with MUFU.LG2's base-2 logarithm directly.  The unscaled log_coeff_ is kept in `aux` for read-back.
+__device__ __forceinline__ void nich_prep_one(float mu, float kappa, float sigmasq, float nu, int32_t count, float mean,
+                                              float ctv, float4 *params, float *aux, const NumericTables &t) {
+    const float cnt = static_cast<float>(count);
+    const float mu_1 = mu - mean;
+    const float post_kappa = kappa + cnt;
+    const float post_mu = (kappa * mu + mean * cnt) / post_kappa;
+    const float post_nu = nu + cnt;
+    const float post_sigmasq =
+        1.f / post_nu * (nu * sigmasq + ctv + (cnt * kappa * mu_1 * mu_1) / post_kappa);
+    const float lambda = post_kappa / ((post_kappa + 1.f) * post_sigmasq);
+    const float score = fast_lgamma_nu(post_nu, t.lgamma_nu3) +
+                        0.5f * fast_log_table(lambda / (3.14159265358979f * post_nu), t.log2_table);
+    const float log_coeff = -0.5f * post_nu - 0.5f;
+    const float precision = lambda / post_nu;
+    *params = make_float4(post_mu, precision, log_coeff * kLn2, score);
+    *aux = log_coeff;
+}
+
 __global__ void nich_prep_kernel(float mu, float kappa, float sigmasq, float nu, int g0, int n,
                                  const int32_t *__restrict__ count, const float *__restrict__ mean,
                                  const float *__restrict__ ctv, float4 *__restrict__ params,
                                  float *__restrict__ aux, NumericTables t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float cnt = static_cast<float>(count[i]);
-    const float mu_1 = mu - mean[i];
-    const float post_kappa = kappa + cnt;
-    const float post_mu = (kappa * mu + mean[i] * cnt) / post_kappa;
-    const float post_nu = nu + cnt;
-    const float post_sigmasq =
-        1.f / post_nu * (nu * sigmasq + ctv[i] + (cnt * kappa * mu_1 * mu_1) / post_kappa);
-    const float lambda = post_kappa / ((post_kappa + 1.f) * post_sigmasq);
-    const float score = fast_lgamma_nu(post_nu, t.lgamma_nu3) +
-                        0.5f * fast_log_table(lambda / (3.14159265358979f * post_nu), t.log2_table);
-    const float log_coeff = -0.5f * post_nu - 0.5f;
-    const float precision = lambda / post_nu;
-    params[g0 + i] = make_float4(post_mu, precision, log_coeff * kLn2, score);
-    aux[g0 + i] = log_coeff;
+    nich_prep_one(mu, kappa, sigmasq, nu, count[i], mean[i], ctv[i], params + g0 + i, aux + g0 + i, t);
 }
 
 // GammaPoisson: plus_group (gp.hpp:56-61) + Scorer::init (gp.hpp:198-207); {post_alpha, score_coeff, score, 0}
+__device__ __forceinline__ float4 gp_prep_one(float alpha, float inv_beta, uint32_t count, uint32_t sum, const NumericTables &t) {
+    const float post_alpha = alpha + static_cast<float>(sum);
+    const float post_inv_beta = inv_beta + static_cast<float>(count);
+    const float score_coeff = -fast_log_table(1.f + post_inv_beta, t.log2_table);
+    const float score = -fast_lgamma_exact(post_alpha, t.lgamma5) +
+                        post_alpha * (fast_log_table(post_inv_beta, t.log2_table) + score_coeff);
+    return make_float4(post_alpha, score_coeff, score, 0.f);
+}
+
 __global__ void gp_prep_kernel(float alpha, float inv_beta, int g0, int n, const uint32_t *__restrict__ count,
                                const uint32_t *__restrict__ sum, float4 *__restrict__ params, NumericTables t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float post_alpha = alpha + static_cast<float>(sum[i]);
-    const float post_inv_beta = inv_beta + static_cast<float>(count[i]);
-    const float score_coeff = -fast_log_table(1.f + post_inv_beta, t.log2_table);
-    const float score = -fast_lgamma_exact(post_alpha, t.lgamma5) +
-                        post_alpha * (fast_log_table(post_inv_beta, t.log2_table) + score_coeff);
-    params[g0 + i] = make_float4(post_alpha, score_coeff, score, 0.f);
+    params[g0 + i] = gp_prep_one(alpha, inv_beta, count[i], sum[i], t);
 }
 
 // BetaBernoulli: update_all (bb.hpp:276-292); {heads_score, tails_score, 0, 0}
+__device__ __forceinline__ float4 bb_prep_one(float alpha, float beta, int32_t heads, int32_t tails, const NumericTables &t) {
+    const float h = alpha + static_cast<float>(heads);
+    const float tl = beta + static_cast<float>(tails);
+    return make_float4(fast_log_table(h / (h + tl), t.log2_table), fast_log_table(tl / (h + tl), t.log2_table), 0.f, 0.f);
+}
+
 __global__ void bb_prep_kernel(float alpha, float beta, int g0, int n, const int32_t *__restrict__ heads,
                                const int32_t *__restrict__ tails, float4 *__restrict__ params, NumericTables t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float h = alpha + static_cast<float>(heads[i]);
-    const float tl = beta + static_cast<float>(tails[i]);
-    params[g0 + i] = make_float4(fast_log_table(h / (h + tl), t.log2_table),
-                                 fast_log_table(tl / (h + tl), t.log2_table), 0.f, 0.f);
+    params[g0 + i] = bb_prep_one(alpha, beta, heads[i], tails[i], t);
+}
+
+// Batched add_value, second half: fold the per-feature batch accumulators (stats.cu) into the stored
+// statistics and rebuild that group's cache entry, for every pooled feature of the launch.
+//   nich: (m, sum x, sum x^2) in double -> (m, mean_b, ctv_b), merged by the pairwise formula of Group::merge
+//         (nich.hpp:167-179) in double;  gp: count += m, sum += sum x (uint32 wrap-around, as gp.hpp:109-116);
+//   bb: heads / tails += counts (bb.hpp:102-107)
+__global__ void merge_prep_batch_kernel(const AddBatch b, NumericTables t) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= b.G) return;
+    const AddDesc &d = b.d[blockIdx.y];
+    const char *acc = b.acc + b.acc_stride * blockIdx.y;
+    const size_t ci = (static_cast<size_t>(b.G) * 4 + 255) / 256 * 256, di = (static_cast<size_t>(b.G) * 8 + 255) / 256 * 256;
+    const int *cnt_a = reinterpret_cast<const int *>(acc);
+    const int *cnt_b = reinterpret_cast<const int *>(acc + ci);
+    const double *sum_x = reinterpret_cast<const double *>(acc + 2 * ci);
+    const double *sum_xx = reinterpret_cast<const double *>(acc + 2 * ci + di);
+    if (d.model == DIST_B200_NICH) {
+        int32_t *count = reinterpret_cast<int32_t *>(d.st0);
+        float *mean = reinterpret_cast<float *>(d.st1), *ctv = reinterpret_cast<float *>(d.st2);
+        const int m = cnt_a[g];
+        if (m != 0) {
+            const double mean_b = sum_x[g] / m;
+            const double ctv_b = fmax(sum_xx[g] - m * mean_b * mean_b, 0.0);
+            const double n = count[g], tot = n + m;
+            const double delta = mean_b - static_cast<double>(mean[g]);
+            const double source_part = static_cast<double>(m) / tot;
+            const double cross_part = n * source_part;
+            count[g] = static_cast<int32_t>(tot);
+            mean[g] = static_cast<float>(static_cast<double>(mean[g]) + source_part * delta);
+            ctv[g] = static_cast<float>(static_cast<double>(ctv[g]) + ctv_b + cross_part * delta * delta);
+        }
+        nich_prep_one(d.shared[0], d.shared[1], d.shared[2], d.shared[3], count[g], mean[g], ctv[g], d.params + g, d.aux + g, t);
+    } else if (d.model == DIST_B200_GP) {
+        const uint32_t c = d.st0[g] + static_cast<uint32_t>(cnt_a[g]);
+        const uint32_t sm = d.st1[g] + static_cast<uint32_t>(cnt_b[g]);
+        d.st0[g] = c;
+        d.st1[g] = sm;
+        d.params[g] = gp_prep_one(d.shared[0], d.shared[1], c, sm, t);
+    } else {  // bb
+        int32_t *heads = reinterpret_cast<int32_t *>(d.st0), *tails = reinterpret_cast<int32_t *>(d.st1);
+        const int32_t h = heads[g] + cnt_a[g], tl = tails[g] + cnt_b[g];
+        heads[g] = h;
+        tails[g] = tl;
+        d.params[g] = bb_prep_one(d.shared[0], d.shared[1], h, tl, t);
+    }
 }
 
 // DirichletDiscrete: update_all (dd.hpp:399-421) folded with score_value's subtraction
@@ -114,6 +172,7 @@ __global__ void dpd_table_kernel(float alpha, float beta0, int V, const float *_
 }
 
 // Pitman-Yor prior vector: CachedMixture::init + score_value (clustering.hpp:151-161,195-230)
+// every block reduces all G sizes itself (G is small) and writes its own slice of the vector
 __global__ void prior_prep_kernel(float alpha, float d, int G, const int32_t *__restrict__ sizes,
                                   float *__restrict__ prior, NumericTables t) {
     __shared__ long long s_total;
@@ -129,15 +188,21 @@ __global__ void prior_prep_kernel(float alpha, float d, int G, const int32_t *__
         total += sizes[g];
         empty += (sizes[g] == 0);
     }
-    atomicAdd(reinterpret_cast<unsigned long long *>(&s_total), static_cast<unsigned long long>(total));
-    atomicAdd(&s_empty, empty);
+    for (int o = 16; o; o >>= 1) {
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+        empty += __shfl_xor_sync(0xffffffffu, empty, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&s_total), static_cast<unsigned long long>(total));
+        atomicAdd(&s_empty, empty);
+    }
     __syncthreads();
     const int nonempty = G - s_empty;
     const float numer = alpha + d * static_cast<float>(nonempty);
     const float denom = static_cast<float>(s_empty);
     const float empty_score = fast_log_table(numer / denom, t.log2_table);
     const float shift = -fast_log_table(static_cast<float>(s_total) + alpha, t.log2_table);
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
         const float shifted =
             sizes[g] ? fast_log_table(static_cast<float>(sizes[g]) - d, t.log2_table) : empty_score;
         prior[g] = shifted + shift;
@@ -229,6 +294,13 @@ int launch_bb_prep(dist_b200_ctx *ctx, const float sh[2], int g0, int n, const i
     return DIST_B200_OK;
 }
 
+int launch_merge_prep_batch(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s) {
+    if (b.n <= 0 || b.G <= 0) return DIST_B200_OK;
+    merge_prep_batch_kernel<<<dim3(blocks_for(b.G, 128), b.n), 128, 0, s>>>(b, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
 int launch_dd_prep(dist_b200_ctx *ctx, int dim, const float *alphas, float alpha_sum, int g0, int n,
                    const int32_t *counts, float *table, cudaStream_t s) {
     if (n <= 0) return DIST_B200_OK;
@@ -254,7 +326,8 @@ int launch_dpd_prep(dist_b200_ctx *ctx, float alpha, float beta0, int V, const f
 
 int launch_prior_prep(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *sizes, float *prior,
                       cudaStream_t s) {
-    prior_prep_kernel<<<1, 1024, 0, s>>>(alpha, d, G, sizes, prior, ctx->tables);
+    const int blocks = G <= 256 ? 1 : (G + 255) / 256 < 64 ? (G + 255) / 256 : 64;
+    prior_prep_kernel<<<blocks, 256, 0, s>>>(alpha, d, G, sizes, prior, ctx->tables);
     LAUNCH_CHECK(ctx);
     return DIST_B200_OK;
 }

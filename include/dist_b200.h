@@ -123,6 +123,12 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
  * sequential Welford steps (agreement ~1e-6 relative).  niw: not supported (statistics stay on the host). */
 int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, const int32_t *assign_dev, size_t n_rows,
                                void *stream);
+/* The same for all features of one cross-cat kind at once (the reference loops the features of a kind per
+ * row, loom-style kinds over ProductModel): one accumulate launch and one merge + cache-rebuild launch per 128
+ * nich / gp / bb features, everything enqueued on `stream` without draining it.  features[i] reads
+ * columns_dev[i]; all share assign_dev. */
+int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                             const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, void *stream);
 /* Device-resident statistics back to the host, arrays in update_all's argument order, G entries each
  * (nich: count,int32 | mean,f32 | ctv,f32; gp: count | sum; bb: heads | tails; dd: counts[G][dim];
  * dpd: counts[G][V]).  Synchronises the stream. */

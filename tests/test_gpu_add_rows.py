@@ -132,3 +132,40 @@ def test_device_side_sweep(ctx, oracle):
     # statistics agree to ~1e-5 (pairwise vs sequential); a perturbed argument can cross a fast_log step
     assert np.all(np.abs(got - exp) <= 2e-4 * (1 + np.abs(exp)) + 6.2e-5 * coeff)
     assert np.median(np.abs(got - exp)) < 1e-4
+
+
+def test_add_rows_batch_mixed_kind(ctx, oracle):
+    """all features of a kind in one call (more than one 128-feature launch, mixed models)"""
+    from distributions_b200 import capi
+    G, n = 24, 3000
+    ids = {"bb": capi.BB, "gp": capi.GP, "nich": capi.NICH, "dd": capi.DD}
+    names = ["gp", "bb", "nich"] * 50 + ["dd"]
+    ws = [getattr(synth, m)(900 + i, G, n, **(dict(dim=8) if m == "dd" else {})) for i, m in enumerate(names)]
+    rng = np.random.default_rng(5)
+    assign = rng.integers(0, G, n).astype(np.int32)
+    feats = [ctx.feature(ids[m]).update_all(w) for m, w in zip(names, ws)]
+    cols = [dev(w["values"].astype(capi.COLUMN_DTYPE[ids[m]])) for m, w in zip(names, ws)]
+    ctx.add_rows_batch(feats, cols, dev(assign), n)
+    for m, w, f in zip(names, ws, feats):
+        want = _expected_after_add(oracle, w, assign)
+        rows = {"nich": 4, "gp": 3, "bb": 2, "dd": 8}[m]
+        got = f.download_caches(rows)
+        exp = cases.oracle_caches(oracle, want)
+        if m == "dd":
+            assert np.array_equal(got, exp[:-1] - exp[-1][None, :])
+        elif m == "nich":
+            np.testing.assert_allclose(got, exp, rtol=3e-4, atol=3e-4)
+        else:
+            np.testing.assert_allclose(got, exp, rtol=2e-6, atol=2e-6)
+    # scoring after the batched update sees the new caches (stream ordering through the ready events)
+    sizes = ws[0]["sizes"]
+    prior = dev(oracle.py_prior(synth.PY_ALPHA, synth.PY_D, sizes))
+    scores = torch.empty((n, G), device="cuda")
+    sel = [0, 1, 3, 4]  # gp, bb features only: exact statistics, tight comparison
+    ctx.score_batch([feats[i] for i in sel], [cols[i] for i in sel], n, prior, scores)
+    after = [_expected_after_add(oracle, ws[i], assign) for i in sel]
+    exp = cases.oracle_scores(oracle, after, prior=prior.cpu().numpy())
+    got = scores.cpu().numpy()
+    # the gp envelope of tests/test_gpu_parity.py: one ulp of the cached score[g] survives the cancellation
+    env = sum(6e-7 * (1.0 + np.abs(oracle.gp_caches(w["shared"], w["count"], w["sum"])[0])) for w in after if w["model"] == "gp")
+    assert np.all(np.abs(got - exp) <= 3e-6 * (1 + np.abs(exp)) + env[None, :])
