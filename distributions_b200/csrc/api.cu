@@ -787,8 +787,23 @@ int dist_b200_prior_pitman_yor_host(dist_b200_ctx *ctx, float alpha, float d, in
 // ---- the hot path ---------------------------------------------------------------------------
 // Describe one row-mapped feature for the score kernel.  In multi-feature lists GammaPoisson goes through
 // its per-(group, value) table (rebuilt lazily, stream-ordered, after any cache update).
+static int queue_gp_table(dist_b200_ctx *ctx, dist_b200_feature *f, GpTableBatch &tb, cudaStream_t s) {
+    if (tb.n == kGpTableBatch) {
+        int rc = launch_gp_table_batch(ctx, tb, s);
+        if (rc) return rc;
+        tb.n = 0;
+    }
+    tb.n_groups[tb.n] = f->capacity;
+    tb.params[tb.n] = static_cast<const float4 *>(f->params);
+    tb.table[tb.n] = f->gp_table;
+    ++tb.n;
+    f->gp_table_dirty = false;
+    return DIST_B200_OK;
+}
+
+// stale tables are queued in `tb`; the caller launches the remainder before the score kernel
 static int fill_desc(dist_b200_ctx *ctx, const dist_b200_feature *cf, const void *column, bool multi, FeatDesc &d,
-                     cudaStream_t s) {
+                     GpTableBatch &tb, cudaStream_t s) {
     dist_b200_feature *f = const_cast<dist_b200_feature *>(cf);
     d.params = f->params;
     d.column = column;
@@ -807,15 +822,37 @@ static int fill_desc(dist_b200_ctx *ctx, const dist_b200_feature *cf, const void
             f->gp_table_dirty = true;
         }
         if (f->gp_table_dirty) {
-            int rc = launch_gp_table(ctx, f->capacity, static_cast<const float4 *>(f->params), f->gp_table, s);
+            int rc = queue_gp_table(ctx, f, tb, s);
             if (rc) return rc;
-            f->gp_table_dirty = false;
         }
         d.params = f->gp_table;
         d.kind = kKindGpTable;
         d.vdim = kGpTableX;
         d.aux = f->params;
     }
+    return DIST_B200_OK;
+}
+
+// rebuild every stale GammaPoisson value table of a multi-feature list on `s` (one launch per 128) and
+// re-record the features' ready events, so that other streams order themselves behind the rebuild
+static int refresh_gp_tables(dist_b200_ctx *ctx, const dist_b200_feature *const *features, int F, cudaStream_t s) {
+    if (F < 2) return DIST_B200_OK;
+    GpTableBatch tb;
+    tb.n = 0;
+    FeatDesc scratch_desc;
+    bool any = false;
+    for (int f = 0; f < F; ++f) {
+        if (!features[f] || features[f]->model != DIST_B200_GP) continue;
+        const bool stale = features[f]->gp_table_dirty || features[f]->gp_table_cap < features[f]->capacity;
+        int rc = fill_desc(ctx, features[f], nullptr, true, scratch_desc, tb, s);
+        if (rc) return rc;
+        any = any || stale;
+    }
+    if (!any) return DIST_B200_OK;
+    int rc = launch_gp_table_batch(ctx, tb, s);
+    if (rc) return rc;
+    for (int f = 0; f < F; ++f)
+        if (features[f] && features[f]->model == DIST_B200_GP) DISTB200_CUDA(ctx, cudaEventRecord(features[f]->ready, s));
     return DIST_B200_OK;
 }
 
@@ -848,10 +885,13 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
         if (F > kMaxFeatures) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score: more than 512 features in one call");
         FeatList fl;
         fl.n = F;
+        GpTableBatch tb;
+        tb.n = 0;
         for (int f = 0; f < F; ++f) {
-            int rc = fill_desc(ctx, features[f], columns[f], F > 1, fl.f[f], s);
+            int rc = fill_desc(ctx, features[f], columns[f], F > 1, fl.f[f], tb, s);
             if (rc) return rc;
         }
+        if (int rc = launch_gp_table_batch(ctx, tb, s)) return rc;
         return launch_score_rows(ctx, fl, G, N, prior, u, assign, scores, accumulate, s);
     }
     if (F == 1 && features[0]->model == DIST_B200_DPD)
@@ -864,14 +904,17 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
     }
     FeatList fl;
     fl.n = 0;
+    GpTableBatch tb;
+    tb.n = 0;
     for (int f = 0; f < F; ++f) {
         if (solo(features[f])) continue;
         if (fl.n >= kMaxFeatures) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score: more than 512 features in one call");
-        int rc = fill_desc(ctx, features[f], columns[f], true, fl.f[fl.n++], s);
+        int rc = fill_desc(ctx, features[f], columns[f], true, fl.f[fl.n++], tb, s);
         if (rc) return rc;
     }
     bool started = accumulate != 0;
     int rc;
+    if ((rc = launch_gp_table_batch(ctx, tb, s))) return rc;
     if (fl.n) {
         if ((rc = launch_score_rows(ctx, fl, G, N, prior, nullptr, nullptr, buf, accumulate, s))) return rc;
         started = true;
@@ -963,13 +1006,16 @@ int dist_b200_score_push_batch(dist_b200_ctx *ctx, const dist_b200_feature *cons
     if (rc) return rc;
     FeatList fl;
     fl.n = F;
+    GpTableBatch tb;
+    tb.n = 0;
     for (int f = 0; f < F; ++f) {
         if (!features[f] || !columns_dev[f] || features[f]->ctx != ctx || features[f]->G != G)
             return fail(ctx, DIST_B200_ERR_INVALID, "score_push: bad feature list");
         if (features[f]->model == DIST_B200_DPD || features[f]->model == DIST_B200_NIW)
             return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_push: row-mapped models only");
-        if ((rc = fill_desc(ctx, features[f], columns_dev[f], true, fl.f[f], s))) return rc;
+        if ((rc = fill_desc(ctx, features[f], columns_dev[f], true, fl.f[f], tb, s))) return rc;
     }
+    if ((rc = launch_gp_table_batch(ctx, tb, s))) return rc;
     PushTargets pt{};
     pt.n = n_owners;
     pt.row0 = row0;
@@ -1042,7 +1088,9 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
     // Row chunks are pipelined over two streams: the H2D copy of chunk k+1 and the D2H copy of chunk
     // k-1 overlap the kernels of chunk k (rows are independent given frozen statistics).
     cudaStream_t st[2] = {ctx->own_stream, ctx->own_stream2};
-    if ((rc = wait_ready(ctx, features, F, st[0])) || (rc = wait_ready(ctx, features, F, st[1]))) return rc;
+    if ((rc = wait_ready(ctx, features, F, st[0]))) return rc;
+    if ((rc = refresh_gp_tables(ctx, features, F, st[0]))) return rc;  // before the second stream starts reading them
+    if ((rc = wait_ready(ctx, features, F, st[1]))) return rc;
     const float *prior_dev = nullptr;
     if (prior_host) {
         std::memcpy(pin + prior_off, prior_host, sizeof(float) * G);

@@ -39,6 +39,15 @@ struct FeatList {
     FeatDesc f[kMaxFeatures];
 };
 
+// GammaPoisson value tables of many features rebuilt in one launch (grid.y = feature)
+constexpr int kGpTableBatch = 128;
+struct GpTableBatch {
+    int n;
+    int n_groups[kGpTableBatch];
+    const float4 *params[kGpTableBatch];
+    float *table[kGpTableBatch];
+};
+
 // batched Group::add_value over the pooled-statistics models (nich / gp / bb) of one kind: up to
 // kAddBatch features per launch, descriptors in kernel-parameter space
 constexpr int kAddBatch = 128;
@@ -159,7 +168,7 @@ int launch_unpack_caches(dist_b200_ctx *ctx, const dist_b200_feature *f, float *
 int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N, const float *prior,
                       const float *u, int32_t *assign, float *scores, int accumulate, cudaStream_t s,
                       const PushTargets *push = nullptr);
-int launch_gp_table(dist_b200_ctx *ctx, int n_groups, const float4 *params, float *table, cudaStream_t s);
+int launch_gp_table_batch(dist_b200_ctx *ctx, const GpTableBatch &b, cudaStream_t s);
 // stats.cu: batched Group::add_value (segmented reduction of assigned rows into the device-side statistics)
 // pooled models: accumulate `b.n` features in one launch (b.acc zeroed by the launcher), then merge + rebuild caches
 int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s);

@@ -486,23 +486,24 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
 
 // table[g][x] = GammaPoisson term of value x for group g, x < kGpTableX: built with gp_term itself (this
 // translation unit, same flags) so the tabulated and the direct path agree bit for bit
-__global__ void gp_table_kernel(int n_groups, const float4 *__restrict__ params, float *__restrict__ table,
-                                NumericTables t) {
+__global__ void gp_table_kernel(const GpTableBatch b, NumericTables t) {
     __shared__ __align__(16) float coeff[33 * kLgammaRowStride];
     __shared__ float logfact[64];
     for (int i = threadIdx.x; i < 33 * kLgammaRowStride; i += blockDim.x) coeff[i] = t.lgamma5[i];
     if (threadIdx.x < 64) logfact[threadIdx.x] = t.log_factorial[threadIdx.x];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_groups * kGpTableX) return;
+    if (i >= b.n_groups[blockIdx.y] * kGpTableX) return;
     const int g = i / kGpTableX, x = i % kGpTableX;
-    table[i] = gp_term(params[g], static_cast<uint32_t>(x), coeff, logfact);
+    b.table[blockIdx.y][i] = gp_term(b.params[blockIdx.y][g], static_cast<uint32_t>(x), coeff, logfact);
 }
 
-int launch_gp_table(dist_b200_ctx *ctx, int n_groups, const float4 *params, float *table, cudaStream_t s) {
-    if (n_groups <= 0) return DIST_B200_OK;
-    const int n = n_groups * kGpTableX;
-    gp_table_kernel<<<(n + 255) / 256, 256, 0, s>>>(n_groups, params, table, ctx->tables);
+int launch_gp_table_batch(dist_b200_ctx *ctx, const GpTableBatch &b, cudaStream_t s) {
+    int most = 0;
+    for (int i = 0; i < b.n; ++i) most = b.n_groups[i] > most ? b.n_groups[i] : most;
+    if (b.n <= 0 || most <= 0) return DIST_B200_OK;
+    const int n = most * kGpTableX;
+    gp_table_kernel<<<dim3((n + 255) / 256, b.n), 256, 0, s>>>(b, ctx->tables);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("gp_table launch: ") + cudaGetErrorString(e));
     return DIST_B200_OK;

@@ -29,8 +29,66 @@ size_t add_rows_acc_bytes(int G) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row streaming shared by the kernels below: every thread takes groups of four consecutive rows with
+// 16-byte (assign, 4-byte columns) / 4-byte (uint8 columns) loads, two groups in flight before the first
+// atomic, so the loop is bound by the atomics and not by two dependent DRAM latencies per row.  kVec
+// needs 16-byte aligned assign / column pointers (the launcher checks); the scalar form takes anything.
+template <typename T>
+__device__ __forceinline__ void load4(const T *p, size_t q, T (&v)[4]) {
+    if constexpr (sizeof(T) == 4) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p) + q);
+        v[0] = reinterpret_cast<const T &>(r.x);
+        v[1] = reinterpret_cast<const T &>(r.y);
+        v[2] = reinterpret_cast<const T &>(r.z);
+        v[3] = reinterpret_cast<const T &>(r.w);
+    } else {
+        static_assert(sizeof(T) == 1, "4- or 1-byte columns");
+        const uint32_t r = __ldg(reinterpret_cast<const uint32_t *>(p) + q);
+        v[0] = static_cast<T>(r & 0xff);
+        v[1] = static_cast<T>((r >> 8) & 0xff);
+        v[2] = static_cast<T>((r >> 16) & 0xff);
+        v[3] = static_cast<T>(r >> 24);
+    }
+}
+
+template <bool kVec, typename T, typename Fn>
+__device__ __forceinline__ void for_each_row(const int32_t *__restrict__ assign, const T *__restrict__ col, size_t N, int threads,
+                                             Fn &&fn) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * threads;
+    const size_t first = static_cast<size_t>(blockIdx.x) * threads + threadIdx.x;
+    if constexpr (kVec) {
+        const size_t n4 = N / 4;
+        size_t q = first;
+        for (; q + stride < n4; q += 2 * stride) {
+            int32_t g0[4], g1[4];
+            T x0[4], x1[4];
+            load4(assign, q, g0);
+            load4(assign, q + stride, g1);
+            load4(col, q, x0);
+            load4(col, q + stride, x1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fn(g0[k], x0[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fn(g1[k], x1[k]);
+        }
+        if (q < n4) {
+            int32_t g0[4];
+            T x0[4];
+            load4(assign, q, g0);
+            load4(col, q, x0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fn(g0[k], x0[k]);
+        }
+        const size_t n = 4 * n4 + first;  // the last N % 4 rows
+        if (n < N) fn(assign[n], col[n]);
+    } else {
+        for (size_t n = first; n < N; n += stride) fn(assign[n], col[n]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // pooled models: grid (row tiles, features)
-template <bool kSmem>
+template <bool kSmem, bool kVec>
 __global__ void __launch_bounds__(kAddThreads) add_rows_pooled_kernel(const AddBatch b) {
     extern __shared__ __align__(8) unsigned char add_smem[];
     const int G = b.G;
@@ -57,33 +115,25 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_pooled_kernel(const AddB
     }
     int *ca = kSmem ? s_ca : g_ca, *cb = kSmem ? s_cb : g_cb;
     double *ax = kSmem ? s_x : g_x, *axx = kSmem ? s_xx : g_xx;
-    const size_t stride = static_cast<size_t>(gridDim.x) * kAddThreads;
-    const size_t first = static_cast<size_t>(blockIdx.x) * kAddThreads + threadIdx.x;
     if (model == DIST_B200_NICH) {
-        const float *col = static_cast<const float *>(d.column);
-        for (size_t n = first; n < b.N; n += stride) {
-            const int g = b.assign[n];
-            if (g < 0 || g >= G) continue;
-            const double x = static_cast<double>(col[n]);
+        for_each_row<kVec>(b.assign, static_cast<const float *>(d.column), b.N, kAddThreads, [&](int g, float xf) {
+            if (g < 0 || g >= G) return;
+            const double x = static_cast<double>(xf);
             atomicAdd(&ca[g], 1);
             atomicAdd(&ax[g], x);
             atomicAdd(&axx[g], x * x);
-        }
+        });
     } else if (model == DIST_B200_GP) {
-        const uint32_t *col = static_cast<const uint32_t *>(d.column);
-        for (size_t n = first; n < b.N; n += stride) {
-            const int g = b.assign[n];
-            if (g < 0 || g >= G) continue;
+        for_each_row<kVec>(b.assign, static_cast<const uint32_t *>(d.column), b.N, kAddThreads, [&](int g, uint32_t x) {
+            if (g < 0 || g >= G) return;
             atomicAdd(&ca[g], 1);
-            atomicAdd(reinterpret_cast<unsigned int *>(&cb[g]), col[n]);
-        }
+            atomicAdd(reinterpret_cast<unsigned int *>(&cb[g]), x);
+        });
     } else {  // bb
-        const uint8_t *col = static_cast<const uint8_t *>(d.column);
-        for (size_t n = first; n < b.N; n += stride) {
-            const int g = b.assign[n];
-            if (g < 0 || g >= G) continue;
-            atomicAdd(col[n] != 0 ? &ca[g] : &cb[g], 1);
-        }
+        for_each_row<kVec>(b.assign, static_cast<const uint8_t *>(d.column), b.N, kAddThreads, [&](int g, uint8_t x) {
+            if (g < 0 || g >= G) return;
+            atomicAdd(x != 0 ? &ca[g] : &cb[g], 1);
+        });
     }
     if (kSmem) {
         __syncthreads();
@@ -121,7 +171,7 @@ __device__ __forceinline__ int dpd_row(const CountArgs &a, uint32_t value) {
     return (lo < a.dim && a.keys[lo] == value) ? a.key_rows[lo] : -1;
 }
 
-template <bool kSmem>
+template <bool kSmem, bool kVec>
 __global__ void __launch_bounds__(kAddThreads) add_rows_counts_kernel(const CountArgs a) {
     extern __shared__ int32_t bins[];
     const int cells = a.G * a.dim;
@@ -130,20 +180,19 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_counts_kernel(const Coun
         __syncthreads();
     }
     int32_t *dst = kSmem ? bins : a.counts;
-    for (size_t n = static_cast<size_t>(blockIdx.x) * kAddThreads + threadIdx.x; n < a.N;
-         n += static_cast<size_t>(gridDim.x) * kAddThreads) {
-        const int g = a.assign[n];
-        if (g < 0 || g >= a.G) continue;
+    // dd values are int32 ids, dpd values uint32 keys: both stream as uint32
+    for_each_row<kVec>(a.assign, static_cast<const uint32_t *>(a.column), a.N, kAddThreads, [&](int g, uint32_t x) {
+        if (g < 0 || g >= a.G) return;
         int r;
         if (a.model == DIST_B200_DD) {
-            r = static_cast<const int32_t *>(a.column)[n];
-            if (r < 0 || r >= a.dim) continue;
+            if (x >= static_cast<uint32_t>(a.dim)) return;
+            r = static_cast<int>(x);
         } else {
-            r = dpd_row(a, static_cast<const uint32_t *>(a.column)[n]);
-            if (r < 0) continue;
+            r = dpd_row(a, x);
+            if (r < 0) return;
         }
         atomicAdd(&dst[static_cast<size_t>(g) * a.dim + r], 1);
-    }
+    });
     if (kSmem) {
         __syncthreads();
         for (int i = threadIdx.x; i < cells; i += kAddThreads)
@@ -151,27 +200,28 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_counts_kernel(const Coun
     }
 }
 
-template <bool kSmem>
-__global__ void __launch_bounds__(256) count_assignments_kernel(const int32_t *__restrict__ assign, size_t N, int G,
-                                                                int32_t *__restrict__ counts) {
+template <bool kSmem, bool kVec>
+__global__ void __launch_bounds__(kAddThreads) count_assignments_kernel(const int32_t *__restrict__ assign, size_t N, int G,
+                                                                        int32_t *__restrict__ counts) {
     extern __shared__ int32_t bins[];
     if (kSmem) {
-        for (int i = threadIdx.x; i < G; i += 256) bins[i] = 0;
+        for (int i = threadIdx.x; i < G; i += kAddThreads) bins[i] = 0;
         __syncthreads();
     }
     int32_t *dst = kSmem ? bins : counts;
-    for (size_t n = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; n < N; n += static_cast<size_t>(gridDim.x) * 256) {
-        const int g = assign[n];
+    for_each_row<kVec>(assign, assign, N, kAddThreads, [&](int g, int) {
         if (g >= 0 && g < G) atomicAdd(&dst[g], 1);
-    }
+    });
     if (kSmem) {
         __syncthreads();
-        for (int i = threadIdx.x; i < G; i += 256)
+        for (int i = threadIdx.x; i < G; i += kAddThreads)
             if (bins[i]) atomicAdd(&counts[i], bins[i]);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 static unsigned row_tiles(const dist_b200_ctx *ctx, size_t N, int per_sm, int split) {
     // enough blocks to fill the machine, few enough that the per-block flush stays negligible
     const size_t want = (N + kAddThreads - 1) / kAddThreads;
@@ -183,12 +233,15 @@ static unsigned row_tiles(const dist_b200_ctx *ctx, size_t N, int per_sm, int sp
 int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s) {
     if (b.N == 0 || b.G == 0 || b.n == 0) return DIST_B200_OK;
     DISTB200_CUDA(ctx, cudaMemsetAsync(b.acc, 0, b.acc_stride * b.n, s));
-    const dim3 grid(row_tiles(ctx, b.N, 8, b.n), b.n);
-    if (b.G <= kAddSmemGroups) {
-        add_rows_pooled_kernel<true><<<grid, kAddThreads, static_cast<size_t>(b.G) * 24, s>>>(b);
-    } else {
-        add_rows_pooled_kernel<false><<<grid, kAddThreads, 0, s>>>(b);
-    }
+    const dim3 grid(row_tiles(ctx, (b.N + 3) / 4, 8, b.n), b.n);
+    bool vec = aligned16(b.assign);
+    for (int i = 0; i < b.n; ++i) vec = vec && aligned16(b.d[i].column);
+    const bool smem = b.G <= kAddSmemGroups;
+    const size_t sb = smem ? static_cast<size_t>(b.G) * 24 : 0;
+    if (smem && vec) add_rows_pooled_kernel<true, true><<<grid, kAddThreads, sb, s>>>(b);
+    else if (smem) add_rows_pooled_kernel<true, false><<<grid, kAddThreads, sb, s>>>(b);
+    else if (vec) add_rows_pooled_kernel<false, true><<<grid, kAddThreads, 0, s>>>(b);
+    else add_rows_pooled_kernel<false, false><<<grid, kAddThreads, 0, s>>>(b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("add_rows launch: ") + cudaGetErrorString(e));
     return DIST_B200_OK;
@@ -209,10 +262,15 @@ int launch_add_rows_counts(dist_b200_ctx *ctx, dist_b200_feature *f, const void 
     a.keys = f->keys_dev;
     a.key_rows = f->key_rows_dev;
     const size_t cells = static_cast<size_t>(f->G) * f->dim;
+    const bool vec = aligned16(assign) && aligned16(column);
     if (cells <= kCountSmemBins) {
-        add_rows_counts_kernel<true><<<row_tiles(ctx, N, 4, 1), kAddThreads, cells * 4, s>>>(a);
+        const unsigned grid = row_tiles(ctx, (N + 3) / 4, 4, 1);
+        if (vec) add_rows_counts_kernel<true, true><<<grid, kAddThreads, cells * 4, s>>>(a);
+        else add_rows_counts_kernel<true, false><<<grid, kAddThreads, cells * 4, s>>>(a);
     } else {
-        add_rows_counts_kernel<false><<<row_tiles(ctx, N, 8, 1), kAddThreads, 0, s>>>(a);
+        const unsigned grid = row_tiles(ctx, (N + 3) / 4, 8, 1);
+        if (vec) add_rows_counts_kernel<false, true><<<grid, kAddThreads, 0, s>>>(a);
+        else add_rows_counts_kernel<false, false><<<grid, kAddThreads, 0, s>>>(a);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("add_rows launch: ") + cudaGetErrorString(e));
@@ -223,11 +281,13 @@ int launch_count_assignments(dist_b200_ctx *ctx, const int32_t *assign, size_t N
                              cudaStream_t s) {
     if (!accumulate) DISTB200_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int32_t) * G, s));
     if (N == 0) return DIST_B200_OK;
-    const size_t want = (N + 255) / 256;
-    const size_t cap = static_cast<size_t>(ctx->sm_count) * 4;
-    const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
-    if (G <= kCountSmemBins) count_assignments_kernel<true><<<grid, 256, static_cast<size_t>(G) * 4, s>>>(assign, N, G, counts);
-    else count_assignments_kernel<false><<<grid, 256, 0, s>>>(assign, N, G, counts);
+    const unsigned grid = row_tiles(ctx, (N + 3) / 4, 4, 1);
+    const bool vec = aligned16(assign), smem = G <= kCountSmemBins;
+    const size_t sb = smem ? static_cast<size_t>(G) * 4 : 0;
+    if (smem && vec) count_assignments_kernel<true, true><<<grid, kAddThreads, sb, s>>>(assign, N, G, counts);
+    else if (smem) count_assignments_kernel<true, false><<<grid, kAddThreads, sb, s>>>(assign, N, G, counts);
+    else if (vec) count_assignments_kernel<false, true><<<grid, kAddThreads, 0, s>>>(assign, N, G, counts);
+    else count_assignments_kernel<false, false><<<grid, kAddThreads, 0, s>>>(assign, N, G, counts);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("count_assignments launch: ") + cudaGetErrorString(e));
     return DIST_B200_OK;
