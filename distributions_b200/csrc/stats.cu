@@ -115,24 +115,65 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_pooled_kernel(const AddB
     }
     int *ca = kSmem ? s_ca : g_ca, *cb = kSmem ? s_cb : g_cb;
     double *ax = kSmem ? s_x : g_x, *axx = kSmem ? s_xx : g_xx;
+    // Assignments under a CRP prior are skewed: many lanes of a warp hit the same group.  Lanes with equal g
+    // are combined in registers first (match.any + redux for integers, a masked butterfly for the double
+    // sums of groups with >= 3 lanes), so an atomic's cost does not grow with the skew.
     if (model == DIST_B200_NICH) {
         for_each_row<kVec>(b.assign, static_cast<const float *>(d.column), b.N, kAddThreads, [&](int g, float xf) {
-            if (g < 0 || g >= G) return;
-            const double x = static_cast<double>(xf);
-            atomicAdd(&ca[g], 1);
-            atomicAdd(&ax[g], x);
-            atomicAdd(&axx[g], x * x);
+            const unsigned active = __activemask();
+            const bool ok = g >= 0 && g < G;
+            const int key = ok ? g : -1;
+            const unsigned peers = __match_any_sync(active, key);
+            const int lane = threadIdx.x & 31;
+            double x = static_cast<double>(xf), xx = x * x;
+            const bool heavy = ok && __popc(peers) >= 3;
+            unsigned todo = __ballot_sync(active, heavy);
+            bool done = !ok;
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const unsigned grp = __shfl_sync(active, peers, leader);
+                const bool mine = (grp >> lane) & 1u;
+                double sx = mine ? x : 0.0, sxx = mine ? xx : 0.0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    sx += __shfl_xor_sync(active, sx, o);
+                    sxx += __shfl_xor_sync(active, sxx, o);
+                }
+                // with a partial warp (loop tail) the butterfly reads lanes outside `active`: fall back below
+                if (active == 0xffffffffu) {
+                    if (lane == leader) {
+                        atomicAdd(&ca[g], __popc(grp));
+                        atomicAdd(&ax[g], sx);
+                        atomicAdd(&axx[g], sxx);
+                    }
+                    if (mine) done = true;
+                }
+                todo &= ~grp;
+            }
+            if (!done) {
+                atomicAdd(&ca[g], 1);
+                atomicAdd(&ax[g], x);
+                atomicAdd(&axx[g], xx);
+            }
         });
     } else if (model == DIST_B200_GP) {
         for_each_row<kVec>(b.assign, static_cast<const uint32_t *>(d.column), b.N, kAddThreads, [&](int g, uint32_t x) {
-            if (g < 0 || g >= G) return;
-            atomicAdd(&ca[g], 1);
-            atomicAdd(reinterpret_cast<unsigned int *>(&cb[g]), x);
+            const unsigned active = __activemask();
+            const bool ok = g >= 0 && g < G;
+            const unsigned peers = __match_any_sync(active, ok ? g : -1);
+            const uint32_t sum = __reduce_add_sync(peers, x);
+            if (ok && (threadIdx.x & 31) == __ffs(peers) - 1) {
+                atomicAdd(&ca[g], __popc(peers));
+                atomicAdd(reinterpret_cast<unsigned int *>(&cb[g]), sum);
+            }
         });
     } else {  // bb
         for_each_row<kVec>(b.assign, static_cast<const uint8_t *>(d.column), b.N, kAddThreads, [&](int g, uint8_t x) {
-            if (g < 0 || g >= G) return;
-            atomicAdd(x != 0 ? &ca[g] : &cb[g], 1);
+            const unsigned active = __activemask();
+            const bool ok = g >= 0 && g < G;
+            const int key = ok ? 2 * g + (x != 0 ? 1 : 0) : -1;
+            const unsigned peers = __match_any_sync(active, key);
+            if (ok && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(x != 0 ? &ca[g] : &cb[g], __popc(peers));
         });
     }
     if (kSmem) {
@@ -191,6 +232,7 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_counts_kernel(const Coun
             r = dpd_row(a, x);
             if (r < 0) return;
         }
+        // equal cells within the warp are combined by the compiler's constant-increment aggregation
         atomicAdd(&dst[static_cast<size_t>(g) * a.dim + r], 1);
     });
     if (kSmem) {

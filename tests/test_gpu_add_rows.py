@@ -51,15 +51,18 @@ def _expected_after_add(oracle, w, assign):
     return w2
 
 
-@pytest.mark.parametrize("name,G,n", [("nich", 37, 5000), ("nich", 3000, 20000), ("gp", 21, 5000), ("bb", 13, 5000),
-                                      ("dd", 29, 5000), ("dpd", 19, 5000)])
-def test_add_rows_matches_sequential_add_value(ctx, oracle, name, G, n):
+@pytest.mark.parametrize("skew", [0.0, 0.85])
+@pytest.mark.parametrize("name,G,n", [("nich", 37, 5003), ("nich", 3000, 20000), ("gp", 21, 5001), ("bb", 13, 5002),
+                                      ("dd", 29, 5000), ("dpd", 19, 4999)])
+def test_add_rows_matches_sequential_add_value(ctx, oracle, name, G, n, skew):
     from distributions_b200 import capi
     ids = {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH}
     kw = dict(dim=16) if name == "dd" else (dict(V=100, other_frac=0.05) if name == "dpd" else {})
     w = getattr(synth, name)(4000 + G, G, n, **kw)
     rng = np.random.default_rng(G)
     assign = rng.integers(0, G, n).astype(np.int32)
+    # a CRP-like skew: most rows in two groups, so that many lanes of a warp share a group
+    assign = np.where(rng.random(n) < skew, np.where(rng.random(n) < 0.7, 3, 5), assign).astype(np.int32)
     assign[::17] = -1  # rows left unassigned are skipped
     f = ctx.feature(ids[name]).update_all(w)
     col = dev(w["values"].astype(capi.COLUMN_DTYPE[ids[name]]))
