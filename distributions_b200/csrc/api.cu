@@ -681,6 +681,38 @@ int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *featu
     return DIST_B200_OK;
 }
 
+// host buffers: stage columns + assignments through the context scratch, run the device batch, drain
+int dist_b200_add_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                                  const void *const *columns_host, const int32_t *assign_host, size_t n_rows) {
+    if (!ctx) return DIST_B200_ERR_INVALID;
+    if (n_features < 1 || !features || !columns_host || !assign_host) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows_host: null argument");
+    if (n_rows == 0) return DIST_B200_OK;
+    std::vector<size_t> off(n_features);
+    size_t total = 0;
+    for (int i = 0; i < n_features; ++i) {
+        if (!features[i] || !columns_host[i]) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows_host: null feature / column");
+        if (features[i]->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: niw statistics stay on the host");
+        off[i] = total;
+        total += round_up((features[i]->model == DIST_B200_BB ? 1 : 4) * n_rows, 256);
+    }
+    const size_t assign_off = total;
+    total += round_up(sizeof(int32_t) * n_rows, 256);
+    int rc = ensure_scratch(ctx, total + 256);
+    if (rc) return rc;
+    cudaStream_t s = ctx->own_stream;
+    char *dev = static_cast<char *>(ctx->scratch_dev);
+    std::vector<const void *> cols(n_features);
+    for (int i = 0; i < n_features; ++i) {
+        const size_t vb = features[i]->model == DIST_B200_BB ? 1 : 4;
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(dev + off[i], columns_host[i], vb * n_rows, cudaMemcpyHostToDevice, s));
+        cols[i] = dev + off[i];
+    }
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(dev + assign_off, assign_host, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, s));
+    rc = dist_b200_add_rows_batch(ctx, features, n_features, cols.data(), reinterpret_cast<const int32_t *>(dev + assign_off), n_rows, s);
+    DISTB200_CUDA(ctx, cudaStreamSynchronize(s));  // the scratch is free for the next upload
+    return rc;
+}
+
 int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, const int32_t *assign_dev, size_t n_rows,
                                void *stream) {
     if (!f || !f->ctx) return DIST_B200_ERR_INVALID;

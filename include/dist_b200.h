@@ -129,6 +129,10 @@ int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, con
  * columns_dev[i]; all share assign_dev. */
 int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
                              const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, void *stream);
+/* Host-buffer form (the call a reference-side binding makes): columns_host[i] holds n_rows values of
+ * features[i] (float / uint32 / int32, bool as uint8), assign_host the packed group ids.  Synchronous. */
+int dist_b200_add_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                                  const void *const *columns_host, const int32_t *assign_host, size_t n_rows);
 /* Device-resident statistics back to the host, arrays in update_all's argument order, G entries each
  * (nich: count,int32 | mean,f32 | ctv,f32; gp: count | sum; bb: heads | tails; dd: counts[G][dim];
  * dpd: counts[G][V]).  Synchronises the stream. */

@@ -113,6 +113,15 @@ struct NormalInverseChiSq {
         const float sh[4] = {s.mu, s.kappa, s.sigmasq, s.nu};
         return dist_b200_nich_update_all(f, sh, static_cast<int>(G), count.data(), mean.data(), ctv.data(), nullptr);
     }
+    // arrays as dist_b200_feature_download_stats returns them: count | mean | count_times_variance
+    static void load_groups(const unsigned char * raw, const Shared &, std::vector<Group> & groups) {
+        const size_t G = groups.size();
+        const int32_t * c = reinterpret_cast<const int32_t *>(raw);
+        const float * m = reinterpret_cast<const float *>(raw + 4 * G);
+        const float * v = reinterpret_cast<const float *>(raw + 8 * G);
+        for (size_t g = 0; g < G; ++g) { groups[g].count = c[g]; groups[g].mean = m[g]; groups[g].count_times_variance = v[g]; }
+    }
+    static size_t stats_bytes(const Shared &, size_t G) { return 12 * G; }
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         struct { int32_t count; float mean; float ctv; } st = {g.count, g.mean, g.count_times_variance};
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), &st, nullptr);
@@ -140,6 +149,12 @@ struct GammaPoisson {
         const float sh[2] = {s.alpha, s.inv_beta};
         return dist_b200_gp_update_all(f, sh, static_cast<int>(G), count.data(), sum.data(), nullptr);
     }
+    static void load_groups(const unsigned char * raw, const Shared &, std::vector<Group> & groups) {  // count | sum
+        const size_t G = groups.size();
+        const uint32_t * c = reinterpret_cast<const uint32_t *>(raw);
+        for (size_t g = 0; g < G; ++g) { groups[g].count = c[g]; groups[g].sum = c[G + g]; }
+    }
+    static size_t stats_bytes(const Shared &, size_t G) { return 8 * G; }
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         const uint32_t st[2] = {g.count, g.sum};
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), st, nullptr);
@@ -166,6 +181,12 @@ struct BetaBernoulli {
         const float sh[2] = {s.alpha, s.beta};
         return dist_b200_bb_update_all(f, sh, static_cast<int>(G), h.data(), t.data(), nullptr);
     }
+    static void load_groups(const unsigned char * raw, const Shared &, std::vector<Group> & groups) {  // heads | tails
+        const size_t G = groups.size();
+        const int32_t * c = reinterpret_cast<const int32_t *>(raw);
+        for (size_t g = 0; g < G; ++g) { groups[g].heads = c[g]; groups[g].tails = c[G + g]; }
+    }
+    static size_t stats_bytes(const Shared &, size_t G) { return 8 * G; }
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         const int32_t st[2] = {g.heads, g.tails};
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), st, nullptr);
@@ -205,6 +226,14 @@ struct DirichletDiscrete {
             for (int v = 0; v < s.dim; ++v) counts[g * s.dim + v] = groups[g].counts[v];
         return dist_b200_dd_update_all(f, s.dim, s.alphas, static_cast<int>(G), counts.data(), nullptr);
     }
+    static void load_groups(const unsigned char * raw, const Shared & s, std::vector<Group> & groups) {  // counts[G][dim]
+        const int32_t * c = reinterpret_cast<const int32_t *>(raw);
+        for (size_t g = 0; g < groups.size(); ++g) {
+            groups[g].count_sum = 0;
+            for (int v = 0; v < s.dim; ++v) { groups[g].counts[v] = c[g * s.dim + v]; groups[g].count_sum += c[g * s.dim + v]; }
+        }
+    }
+    static size_t stats_bytes(const Shared & s, size_t G) { return 4 * G * s.dim; }
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), g.counts, nullptr);
     }
@@ -269,6 +298,23 @@ class Mixture {
         std::vector<float> tmp(groups_.size(), 0.f);
         score_value(shared, value, Floats(tmp), rng);
         return tmp[groupid];
+    }
+
+    // NEW: batched add_value.  values[n] join groups assign[n] (packed ids, negative = skip): one segmented
+    // reduction on the device replaces n add_value calls (n cache refreshes); the host Groups are read back
+    // so that groups() stays the source of truth for dump / remove_value.  nich statistics come from the
+    // pairwise merge (nich.hpp:167-179), ~1e-6 relative from n sequential Welford steps.
+    template <class T>
+    void add_values(const Shared & shared, const T * values, const int32_t * assign, size_t n) {
+        std::vector<typename detail::WireValue<Value>::type> wire(values, values + n);
+        dist_b200_feature * feats[1] = {f_};
+        const void * cols[1] = {wire.data()};
+        ctx_->check(dist_b200_add_rows_batch_host(ctx_->get(), feats, 1, cols, assign, n), "add_values");
+        std::vector<unsigned char> raw(Model::stats_bytes(shared, groups_.size()));
+        size_t got = 0;
+        ctx_->check(dist_b200_feature_download_stats(f_, raw.data(), raw.size(), &got, nullptr), "download_stats");
+        if (got != raw.size()) throw std::runtime_error("add_values: statistics size mismatch");
+        Model::load_groups(raw.data(), shared, groups_);
     }
 
     // NEW: batched score (+ sample).  values[n] are rows of this feature, prior[G] the clustering

@@ -101,6 +101,19 @@ static void run_script(std::shared_ptr<Context> ctx, std::istream & in, const ty
                 }
             }
             std::printf("batch_matches_per_value %d\n", same ? 1 : 0);
+        } else if (op == "addbatch") {  // addbatch <n> then n values, then n packed group ids (non-empty groups)
+            size_t n;
+            ls >> n;
+            std::vector<typename detail::WireValue<typename Model::Value>::type> vals(n);
+            std::vector<int32_t> gids(n);
+            std::getline(in, line);
+            std::istringstream vs(line);
+            for (auto & v : vals) v = parse(vs);
+            std::getline(in, line);
+            std::istringstream gs(line);
+            for (auto & g : gids) gs >> g;
+            for (auto g : gids) driver.add_value(py, static_cast<size_t>(g));
+            mixture.add_values(shared, vals.data(), gids.data(), n);
         }
     }
 }

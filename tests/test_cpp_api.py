@@ -156,6 +156,17 @@ def test_cpp_mixture_choreography(tmp_path, oracle):
         lines.append(" ".join(repr(v) for v in vals))
         lines.append(" ".join(repr(float(x)) for x in u))
         expected.append((model, "batch", (vals, u), rp.scores(vals)))
+        # batched add_value into non-empty groups, then the per-value score sees the merged statistics
+        n = 60
+        vals = [_value(rng, model) for _ in range(n)]
+        live = [g for g, c in enumerate(rp.counts) if c > 0]
+        gids = [int(rng.choice(live)) for _ in range(n)]
+        lines.append("addbatch %d" % n)
+        lines.append(" ".join(repr(v) for v in vals))
+        lines.append(" ".join(str(g) for g in gids))
+        for g, v in zip(gids, vals):
+            rp.add(g, v)
+        score()
         lines.append("end")
         replays[model] = rp
     script = tmp_path / "script.txt"

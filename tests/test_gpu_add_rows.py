@@ -172,3 +172,19 @@ def test_add_rows_batch_mixed_kind(ctx, oracle):
     # the gp envelope of tests/test_gpu_parity.py: one ulp of the cached score[g] survives the cancellation
     env = sum(6e-7 * (1.0 + np.abs(oracle.gp_caches(w["shared"], w["count"], w["sum"])[0])) for w in after if w["model"] == "gp")
     assert np.all(np.abs(got - exp) <= 3e-6 * (1 + np.abs(exp)) + env[None, :])
+
+
+def test_add_rows_batch_host_buffers(ctx, oracle):
+    """the host-buffer entry a reference-side binding calls: same result as the device-pointer entry"""
+    from distributions_b200 import capi
+    G, n = 17, 2500
+    ws = [synth.gp(31, G, n), synth.bb(32, G, n), synth.nich(33, G, n)]
+    ids = [capi.GP, capi.BB, capi.NICH]
+    assign = np.random.default_rng(9).integers(0, G, n).astype(np.int32)
+    a = [ctx.feature(i).update_all(w) for i, w in zip(ids, ws)]
+    b = [ctx.feature(i).update_all(w) for i, w in zip(ids, ws)]
+    ctx.add_rows_batch_host(a, [w["values"] for w in ws], assign)
+    ctx.add_rows_batch(b, [dev(w["values"].astype(capi.COLUMN_DTYPE[i])) for i, w in zip(ids, ws)], dev(assign), n)
+    for fa, fb, nb, rows in zip(a, b, (8 * G, 8 * G, 12 * G), (3, 2, 4)):
+        assert np.array_equal(fa.download_stats(nb)[:4 * G], fb.download_stats(nb)[:4 * G])  # integer arrays exact
+        np.testing.assert_allclose(fa.download_caches(rows), fb.download_caches(rows), rtol=1e-6, atol=1e-6)
