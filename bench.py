@@ -208,14 +208,23 @@ def run_b200(args):
 
     scores_buf = torch.empty((N, G), device=dev, dtype=torch.float32) if args.materialise else None
 
-    sizes_dev = torch.from_numpy(wl["sizes"].astype(np.int32)).to(dev)
+    base_sizes = torch.from_numpy(wl["sizes"].astype(np.int32)).to(dev)
+    sizes_dev = base_sizes.clone()
+    in_groups = [False]
 
     def step():
+        # --sweep: one blocked Gibbs pass over the rows, all on the device -- the rows leave their groups
+        # (remove_value), are scored against the rest and resampled, join their new groups (add_value), and
+        # the clustering prior is refreshed from the new group sizes
+        if args.sweep and in_groups[0]:
+            ctx.remove_rows_batch(feats, cols, assign, N, stream=stream)
         ctx.score_sample_batch(feats, cols, N, prior, u, assign, scores_buf, stream=stream)
-        if args.sweep:  # the rest of one Gibbs-style pass: fold the sampled rows in, refresh caches + prior
+        if args.sweep:
             ctx.add_rows_batch(feats, cols, assign, N, stream=stream)
+            sizes_dev.copy_(base_sizes)
             ctx.count_assignments(assign, N, G, sizes_dev, accumulate=True, stream=stream)
             ctx.prior_pitman_yor_dev(synth.PY_ALPHA, synth.PY_D, G, sizes_dev, prior, stream=stream)
+            in_groups[0] = True
 
     def barrier():
         torch.cuda.synchronize()
@@ -318,9 +327,10 @@ def run_b200(args):
                    "l2": "flushed between timed steps (256 MB memset outside the event pairs)",
                    "mode": ("score+prior+sample with the [N][G] scores also written to HBM" if args.materialise else
                             "fused score+prior+sample, scores not materialised") +
-                           (" + batched add_value, cache rebuild and prior refresh on the device" if args.sweep else ""), "wall_s_timed_region": t_wall,
+                           (" + batched remove_value / add_value, cache rebuild and prior refresh on the device "
+                            "(one blocked Gibbs pass per step)" if args.sweep else ""), "wall_s_timed_region": t_wall,
                    "e2e_matches_device_assign": same},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * ((1 if F == 1 or wl["name"] == "c3_crosscat" else F) + ((2 * ((F + 127) // 128) + 2) if args.sweep else 0)),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * ((1 if F == 1 or wl["name"] == "c3_crosscat" else F) + ((4 * ((F + 127) // 128) + 2) if args.sweep else 0)),
         "roofline": roofline, "roofline_binding": roofline_binding, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
@@ -435,7 +445,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--materialise", action="store_true", help="also write the [N][G] log scores (HBM-write-bound mode)")
     ap.add_argument("--sweep", action="store_true",
-                    help="each step also folds the sampled rows into the groups on the device (add_value + cache/prior refresh)")
+                    help="each step is a blocked Gibbs pass on the device: remove_value, score+sample, add_value, cache/prior refresh")
     ap.add_argument("--tile-rows", type=int, default=65536, help="row tile of the feature-sharded reduce-scatter")
     ap.add_argument("--shard-mode", default="push", choices=["push", "rs"],
                     help="c3 at N>1: fused NVLink peer push (default) or NCCL reduce-scatter")

@@ -40,6 +40,8 @@ SIGNATURES = {
     "dist_b200_feature_add_rows": (c_i, [c_p, c_p, c_p, c_sz, c_p]),
     "dist_b200_add_rows_batch": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz, c_p]),
     "dist_b200_add_rows_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz]),
+    "dist_b200_remove_rows_batch": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz, c_p]),
+    "dist_b200_remove_rows_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz]),
     "dist_b200_feature_download_stats": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
     "dist_b200_count_assignments": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_i, c_p]),
     "dist_b200_prior_pitman_yor_dev": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
@@ -145,6 +147,19 @@ class Context:
         """batched Group::add_value for all features of one kind; nothing is drained, later calls order behind it"""
         F, fa, ca = self._lists(features, columns)
         self.check(self.L.dist_b200_add_rows_batch(self.h, fa, F, ca, _dev_ptr(assign_dev), n_rows, stream), "add_rows_batch")
+
+    def remove_rows_batch(self, features, columns, assign_dev, n_rows, stream=None):
+        """batched Group::remove_value: the rows leave the groups assign_dev names"""
+        F, fa, ca = self._lists(features, columns)
+        self.check(self.L.dist_b200_remove_rows_batch(self.h, fa, F, ca, _dev_ptr(assign_dev), n_rows, stream), "remove_rows_batch")
+
+    def remove_rows_batch_host(self, features, columns, assign):
+        F = len(features)
+        cols = [np.ascontiguousarray(c, dtype=COLUMN_DTYPE[f.model]) for f, c in zip(features, columns)]
+        assign = np.ascontiguousarray(assign, dtype=np.int32)
+        fa = (c_p * F)(*[f.h for f in features])
+        ca = (c_p * F)(*[_np_ptr(c) for c in cols])
+        self.check(self.L.dist_b200_remove_rows_batch_host(self.h, fa, F, ca, _np_ptr(assign), assign.size), "remove_rows_batch_host")
 
     def add_rows_batch_host(self, features, columns, assign):
         """host arrays: columns[i] numpy array of COLUMN_DTYPE[model], assign int32"""

@@ -596,8 +596,8 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
 // accumulators live in a dedicated context buffer guarded by an event (not the upload scratch), so the
 // call returns without draining the stream; later scoring calls order themselves behind the features'
 // `ready` events.
-int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
-                             const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, void *stream) {
+static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                      const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, int sign, void *stream) {
     if (!ctx) return DIST_B200_ERR_INVALID;
     if (n_features < 0 || (n_features && (!features || !columns_dev)) || !assign_dev)
         return fail(ctx, DIST_B200_ERR_INVALID, "add_rows: null argument");
@@ -627,6 +627,7 @@ int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *featu
     if (rc) return rc;
 
     AddBatch b{};
+    b.sign = sign;
     b.N = n_rows;
     b.assign = assign_dev;
     b.acc = static_cast<char *>(ctx->add_acc);
@@ -661,13 +662,13 @@ int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *featu
             } break;
             case DIST_B200_DD:
                 if (!f->alphas_dev) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: dd alphas not resident (update_all first)");
-                if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, s))) return rc;
+                if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, sign, s))) return rc;
                 if ((rc = launch_dd_prep(ctx, f->dim, f->alphas_dev, f->alpha_sum, 0, G, reinterpret_cast<const int32_t *>(stat_ptr(f, 0)),
                                          static_cast<float *>(f->params), s)))
                     return rc;
                 break;
             case DIST_B200_DPD:
-                if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, s))) return rc;
+                if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, sign, s))) return rc;
                 if ((rc = launch_dpd_prep(ctx, f->alpha, f->beta0, f->dim, reinterpret_cast<const float *>(f->stats + static_cast<size_t>(G) * f->dim),
                                           G, reinterpret_cast<const int32_t *>(f->stats), static_cast<float *>(f->params), s)))
                     return rc;
@@ -681,9 +682,19 @@ int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *featu
     return DIST_B200_OK;
 }
 
+int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                             const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, void *stream) {
+    return rows_batch(ctx, features, n_features, columns_dev, assign_dev, n_rows, +1, stream);
+}
+
+int dist_b200_remove_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                                const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, void *stream) {
+    return rows_batch(ctx, features, n_features, columns_dev, assign_dev, n_rows, -1, stream);
+}
+
 // host buffers: stage columns + assignments through the context scratch, run the device batch, drain
-int dist_b200_add_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
-                                  const void *const *columns_host, const int32_t *assign_host, size_t n_rows) {
+static int rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                           const void *const *columns_host, const int32_t *assign_host, size_t n_rows, int sign) {
     if (!ctx) return DIST_B200_ERR_INVALID;
     if (n_features < 1 || !features || !columns_host || !assign_host) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows_host: null argument");
     if (n_rows == 0) return DIST_B200_OK;
@@ -708,9 +719,19 @@ int dist_b200_add_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *
         cols[i] = dev + off[i];
     }
     DISTB200_CUDA(ctx, cudaMemcpyAsync(dev + assign_off, assign_host, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, s));
-    rc = dist_b200_add_rows_batch(ctx, features, n_features, cols.data(), reinterpret_cast<const int32_t *>(dev + assign_off), n_rows, s);
+    rc = rows_batch(ctx, features, n_features, cols.data(), reinterpret_cast<const int32_t *>(dev + assign_off), n_rows, sign, s);
     DISTB200_CUDA(ctx, cudaStreamSynchronize(s));  // the scratch is free for the next upload
     return rc;
+}
+
+int dist_b200_add_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                                  const void *const *columns_host, const int32_t *assign_host, size_t n_rows) {
+    return rows_batch_host(ctx, features, n_features, columns_host, assign_host, n_rows, +1);
+}
+
+int dist_b200_remove_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                                     const void *const *columns_host, const int32_t *assign_host, size_t n_rows) {
+    return rows_batch_host(ctx, features, n_features, columns_host, assign_host, n_rows, -1);
 }
 
 int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, const int32_t *assign_dev, size_t n_rows,

@@ -61,6 +61,7 @@ struct AddDesc {
 };
 struct AddBatch {
     int n, G;
+    int sign;                    // +1: add_value, -1: remove_value
     size_t N;
     const int32_t *assign;
     char *acc;                   // per feature: cnt_a[G] | cnt_b[G] (int) | sum_x[G] | sum_xx[G] (double)
@@ -175,7 +176,7 @@ int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s
 int launch_merge_prep_batch(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s);  // prep.cu
 // dd / dpd: counts updated in place
 int launch_add_rows_counts(dist_b200_ctx *ctx, dist_b200_feature *f, const void *column, const int32_t *assign, size_t N,
-                           cudaStream_t s);
+                           int sign, cudaStream_t s);
 size_t add_rows_acc_bytes(int G);
 int launch_count_assignments(dist_b200_ctx *ctx, const int32_t *assign, size_t N, int G, int32_t *counts, int accumulate,
                              cudaStream_t s);

@@ -73,7 +73,8 @@ __global__ void bb_prep_kernel(float alpha, float beta, int g0, int n, const int
 // statistics and rebuild that group's cache entry, for every pooled feature of the launch.
 //   nich: (m, sum x, sum x^2) in double -> (m, mean_b, ctv_b), merged by the pairwise formula of Group::merge
 //         (nich.hpp:167-179) in double;  gp: count += m, sum += sum x (uint32 wrap-around, as gp.hpp:109-116);
-//   bb: heads / tails += counts (bb.hpp:102-107)
+//   bb: heads / tails += counts (bb.hpp:102-107).  b.sign = -1 is the batched remove_value (nich.hpp:146-165,
+//   gp.hpp:128-135, bb.hpp:117-122): the same accumulators subtracted, nich by inverting the merge.
 __global__ void merge_prep_batch_kernel(const AddBatch b, NumericTables t) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= b.G) return;
@@ -91,24 +92,41 @@ __global__ void merge_prep_batch_kernel(const AddBatch b, NumericTables t) {
         if (m != 0) {
             const double mean_b = sum_x[g] / m;
             const double ctv_b = fmax(sum_xx[g] - m * mean_b * mean_b, 0.0);
-            const double n = count[g], tot = n + m;
-            const double delta = mean_b - static_cast<double>(mean[g]);
-            const double source_part = static_cast<double>(m) / tot;
-            const double cross_part = n * source_part;
-            count[g] = static_cast<int32_t>(tot);
-            mean[g] = static_cast<float>(static_cast<double>(mean[g]) + source_part * delta);
-            ctv[g] = static_cast<float>(static_cast<double>(ctv[g]) + ctv_b + cross_part * delta * delta);
+            if (b.sign > 0) {
+                const double n = count[g], tot = n + m;
+                const double delta = mean_b - static_cast<double>(mean[g]);
+                const double source_part = static_cast<double>(m) / tot;
+                const double cross_part = n * source_part;
+                count[g] = static_cast<int32_t>(tot);
+                mean[g] = static_cast<float>(static_cast<double>(mean[g]) + source_part * delta);
+                ctv[g] = static_cast<float>(static_cast<double>(ctv[g]) + ctv_b + cross_part * delta * delta);
+            } else {
+                // the inverse of the merge: (count, mean, ctv) = merge(rest, batch) solved for `rest`; a group
+                // emptied by the batch is reset like Group::remove_value does (nich.hpp:146-165)
+                const double tot = count[g], n = tot - m;
+                if (n <= 0) {
+                    count[g] = 0;
+                    mean[g] = 0.f;
+                    ctv[g] = 0.f;
+                } else {
+                    const double mean_r = (tot * static_cast<double>(mean[g]) - m * mean_b) / n;
+                    const double delta = mean_b - mean_r;
+                    count[g] = static_cast<int32_t>(n);
+                    ctv[g] = static_cast<float>(static_cast<double>(ctv[g]) - ctv_b - (n * m / tot) * delta * delta);
+                    mean[g] = static_cast<float>(mean_r);
+                }
+            }
         }
         nich_prep_one(d.shared[0], d.shared[1], d.shared[2], d.shared[3], count[g], mean[g], ctv[g], d.params + g, d.aux + g, t);
     } else if (d.model == DIST_B200_GP) {
-        const uint32_t c = d.st0[g] + static_cast<uint32_t>(cnt_a[g]);
-        const uint32_t sm = d.st1[g] + static_cast<uint32_t>(cnt_b[g]);
+        const uint32_t c = d.st0[g] + static_cast<uint32_t>(b.sign * cnt_a[g]);
+        const uint32_t sm = d.st1[g] + static_cast<uint32_t>(b.sign) * static_cast<uint32_t>(cnt_b[g]);
         d.st0[g] = c;
         d.st1[g] = sm;
         d.params[g] = gp_prep_one(d.shared[0], d.shared[1], c, sm, t);
     } else {  // bb
         int32_t *heads = reinterpret_cast<int32_t *>(d.st0), *tails = reinterpret_cast<int32_t *>(d.st1);
-        const int32_t h = heads[g] + cnt_a[g], tl = tails[g] + cnt_b[g];
+        const int32_t h = heads[g] + b.sign * cnt_a[g], tl = tails[g] + b.sign * cnt_b[g];
         heads[g] = h;
         tails[g] = tl;
         d.params[g] = bb_prep_one(d.shared[0], d.shared[1], h, tl, t);

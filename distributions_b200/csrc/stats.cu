@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_pooled_kernel(const AddB
 // ---------------------------------------------------------------------------------------------
 // dd / dpd: counts[g][row] += 1 in place; a shared-memory histogram when the whole table fits
 struct CountArgs {
-    int model, G, dim, keys_dense;
+    int model, G, dim, keys_dense, sign;
     size_t N;
     const void *column;
     const int32_t *assign;
@@ -223,17 +223,18 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_counts_kernel(const Coun
     int32_t *dst = kSmem ? bins : a.counts;
     // dd values are int32 ids, dpd values uint32 keys: both stream as uint32
     for_each_row<kVec>(a.assign, static_cast<const uint32_t *>(a.column), a.N, kAddThreads, [&](int g, uint32_t x) {
-        if (g < 0 || g >= a.G) return;
-        int r;
-        if (a.model == DIST_B200_DD) {
-            if (x >= static_cast<uint32_t>(a.dim)) return;
-            r = static_cast<int>(x);
-        } else {
-            r = dpd_row(a, x);
-            if (r < 0) return;
+        int cell = -1;
+        if (g >= 0 && g < a.G) {
+            if (a.model == DIST_B200_DD) {
+                if (x < static_cast<uint32_t>(a.dim)) cell = g * a.dim + static_cast<int>(x);
+            } else {
+                const int r = dpd_row(a, x);
+                if (r >= 0) cell = g * a.dim + r;
+            }
         }
-        // equal cells within the warp are combined by the compiler's constant-increment aggregation
-        atomicAdd(&dst[static_cast<size_t>(g) * a.dim + r], 1);
+        // lanes hitting the same cell are combined: one atomic per distinct cell of the warp
+        const unsigned peers = __match_any_sync(__activemask(), cell);
+        if (cell >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&dst[cell], a.sign * __popc(peers));
     });
     if (kSmem) {
         __syncthreads();
@@ -290,13 +291,14 @@ int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s
 }
 
 int launch_add_rows_counts(dist_b200_ctx *ctx, dist_b200_feature *f, const void *column, const int32_t *assign, size_t N,
-                           cudaStream_t s) {
+                           int sign, cudaStream_t s) {
     if (N == 0 || f->G == 0) return DIST_B200_OK;
     CountArgs a{};
     a.model = f->model;
     a.G = f->G;
     a.dim = f->dim;
     a.keys_dense = f->keys_dense ? 1 : 0;
+    a.sign = sign;
     a.N = N;
     a.column = column;
     a.assign = assign;

@@ -129,6 +129,15 @@ int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, con
  * columns_dev[i]; all share assign_dev. */
 int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
                              const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, void *stream);
+/* Batched Group::remove_value (nich.hpp:146-165, gp.hpp:128-135, bb.hpp:117-122, dd.hpp:142-149,
+ * dpd.hpp:207-215): the rows leave the groups assign_dev[n] names -- the first half of a Gibbs sweep over a
+ * block of rows.  Integer statistics exact; nich inverts the pairwise merge in double (a group emptied by the
+ * batch is reset to count = mean = ctv = 0 as the reference does).  Emptied groups stay in place: removing
+ * them (dist_b200_feature_remove_group) is the mixture driver's decision, as in mixture.hpp:95-122. */
+int dist_b200_remove_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                                const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, void *stream);
+int dist_b200_remove_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                                     const void *const *columns_host, const int32_t *assign_host, size_t n_rows);
 /* Host-buffer form (the call a reference-side binding makes): columns_host[i] holds n_rows values of
  * features[i] (float / uint32 / int32, bool as uint8), assign_host the packed group ids.  Synchronous. */
 int dist_b200_add_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,

@@ -188,3 +188,77 @@ def test_add_rows_batch_host_buffers(ctx, oracle):
     for fa, fb, nb, rows in zip(a, b, (8 * G, 8 * G, 12 * G), (3, 2, 4)):
         assert np.array_equal(fa.download_stats(nb)[:4 * G], fb.download_stats(nb)[:4 * G])  # integer arrays exact
         np.testing.assert_allclose(fa.download_caches(rows), fb.download_caches(rows), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("skew", [0.0, 0.85])
+@pytest.mark.parametrize("name,G,n", [("nich", 37, 5003), ("gp", 21, 5001), ("bb", 13, 5002), ("dd", 29, 5000), ("dpd", 19, 4999)])
+def test_remove_rows_matches_sequential_remove_value(ctx, oracle, name, G, n, skew):
+    """batched Group::remove_value: start from groups that contain the rows, remove them, compare with the
+    reference's one-at-a-time remove_value (oracle restatement) and with the statistics before the add."""
+    from distributions_b200 import capi
+    ids = {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH}
+    kw = dict(dim=16) if name == "dd" else (dict(V=100, other_frac=0.05) if name == "dpd" else {})
+    w = getattr(synth, name)(6000 + G, G, n, **kw)
+    rng = np.random.default_rng(G + 1)
+    assign = rng.integers(0, G, n).astype(np.int32)
+    assign = np.where(rng.random(n) < skew, np.where(rng.random(n) < 0.7, 3, 5), assign).astype(np.int32)
+    assign[::13] = -1
+    keep = assign >= 0
+    full = _expected_after_add(oracle, dict(w, values=w["values"][keep]), assign[keep])  # groups holding the rows
+    full["values"] = w["values"]
+    f = ctx.feature(ids[name]).update_all(full)
+    col = dev(w["values"].astype(capi.COLUMN_DTYPE[ids[name]]))
+    ctx.remove_rows_batch([f], [col], dev(assign), n)
+    if name == "nich":
+        raw = f.download_stats(12 * G)
+        cnt, mean, ctv = raw[:4 * G].view(np.int32), raw[4 * G:8 * G].view(np.float32), raw[8 * G:].view(np.float32)
+        assert np.array_equal(cnt, w["count"])
+        # the reference's sequential removal, one value at a time
+        seq_mean, seq_ctv = np.empty(G, np.float32), np.empty(G, np.float32)
+        for g in range(G):
+            xs = w["values"][keep][assign[keep] == g]
+            c, m, v = oracle.nich_group_update(-1, int(full["count"][g]), float(full["mean"][g]), float(full["ctv"][g]), xs)
+            assert c == w["count"][g]
+            seq_mean[g], seq_ctv[g] = m, v
+        scale = 1.0 + np.abs(w["values"]).max()
+        # both are float32 subtractions of nearly equal sums: compare at the accuracy of the statistics held
+        assert np.all(np.abs(mean - seq_mean) <= 2e-5 * scale)
+        assert np.all(np.abs(ctv - seq_ctv) <= 1e-4 * (np.abs(full["ctv"]) + 1))
+        assert np.all(np.abs(mean - w["mean"]) <= 2e-5 * scale)
+        assert np.all(np.abs(ctv - w["ctv"]) <= 1e-4 * (np.abs(full["ctv"]) + 1))
+    elif name == "gp":
+        raw = f.download_stats(8 * G).view(np.uint32)
+        assert np.array_equal(raw[:G], w["count"]) and np.array_equal(raw[G:], w["sum"])
+    elif name == "bb":
+        raw = f.download_stats(8 * G).view(np.int32)
+        assert np.array_equal(raw[:G], w["heads"]) and np.array_equal(raw[G:], w["tails"])
+    else:
+        dim = 16 if name == "dd" else 100
+        raw = f.download_stats(4 * G * dim).view(np.int32).reshape(G, dim)
+        assert np.array_equal(raw, w["counts"])
+    if name != "nich":  # caches are a pure function of the (exact) integer statistics
+        rows = {"gp": 3, "bb": 2, "dd": 16, "dpd": 101}[name]
+        got = f.download_caches(rows)
+        exp = cases.oracle_caches(oracle, w)
+        if name in ("dd", "dpd"):
+            assert np.array_equal(got, exp[:-1] - exp[-1][None, :])
+        else:
+            np.testing.assert_allclose(got, exp, rtol=2e-6, atol=2e-6)
+
+
+def test_remove_rows_empties_group(ctx, oracle):
+    """a group emptied by the batch is reset exactly (count = mean = ctv = 0), as nich.hpp:152-156"""
+    from distributions_b200 import capi
+    G, n = 5, 64
+    w = synth.nich(3, G, n)
+    w["count"][:] = 0
+    w["mean"][:] = 0
+    w["ctv"][:] = 0
+    assign = (np.arange(n) % 2).astype(np.int32)  # groups 0 and 1 only
+    f = ctx.feature(capi.NICH).update_all(w)
+    col = dev(w["values"])
+    f.add_rows(col, dev(assign), n)
+    ctx.remove_rows_batch([f], [col], dev(assign), n)
+    raw = f.download_stats(12 * G)
+    assert not raw.any()
+    np.testing.assert_array_equal(f.download_caches(4), cases.oracle_caches(oracle, w))
