@@ -21,6 +21,7 @@ namespace distb200 {
 constexpr int kAddThreads = 256;
 constexpr int kAddSmemGroups = 2048;   // groups whose accumulators fit in shared memory (24 B / group)
 constexpr int kCountSmemBins = 12288;  // int bins of a shared-memory histogram (48 KB)
+constexpr int kPeelRounds = 4;         // popular groups combined in registers per warp row
 
 size_t add_rows_acc_bytes(int G) {
     // cnt_a | cnt_b | sum_x | sum_xx, each G entries, 256-byte aligned regions
@@ -115,42 +116,43 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_pooled_kernel(const AddB
     }
     int *ca = kSmem ? s_ca : g_ca, *cb = kSmem ? s_cb : g_cb;
     double *ax = kSmem ? s_x : g_x, *axx = kSmem ? s_xx : g_xx;
-    // Assignments under a CRP prior are skewed: many lanes of a warp hit the same group.  Lanes with equal g
-    // are combined in registers first (match.any + redux for integers, a masked butterfly for the double
-    // sums of groups with >= 3 lanes), so an atomic's cost does not grow with the skew.
+    // Assignments under a CRP prior are skewed: many lanes of a warp hit the same group.  Integer
+    // shared-memory atomics take that well (measured, profiles/experiments/add_rows_modes.txt: 1.1x for a
+    // Zipf assignment, 2x with 85% of the rows in two groups; match.any or ballot-based combining costs more
+    // than it saves), but the double sums are CAS loops that degrade 9-14x.  For nich the lanes of the
+    // warp's popular groups are therefore combined in registers first (masked butterfly, one atomic per
+    // peeled group); lanes of unpopular groups go direct.
     if (model == DIST_B200_NICH) {
         for_each_row<kVec>(b.assign, static_cast<const float *>(d.column), b.N, kAddThreads, [&](int g, float xf) {
             const unsigned active = __activemask();
-            const bool ok = g >= 0 && g < G;
-            const int key = ok ? g : -1;
-            const unsigned peers = __match_any_sync(active, key);
             const int lane = threadIdx.x & 31;
-            double x = static_cast<double>(xf), xx = x * x;
-            const bool heavy = ok && __popc(peers) >= 3;
-            unsigned todo = __ballot_sync(active, heavy);
-            bool done = !ok;
-            while (todo) {
-                const int leader = __ffs(todo) - 1;
-                const unsigned grp = __shfl_sync(active, peers, leader);
-                const bool mine = (grp >> lane) & 1u;
-                double sx = mine ? x : 0.0, sxx = mine ? xx : 0.0;
+            bool pending = g >= 0 && g < G;
+            const double x = static_cast<double>(xf), xx = x * x;
+            if (active == 0xffffffffu) {
+#pragma unroll 1
+                for (int round = 0; round < kPeelRounds; ++round) {
+                    const unsigned todo = __ballot_sync(active, pending);
+                    if (!todo) break;
+                    const int leader = __ffs(todo) - 1;
+                    const int gl = __shfl_sync(active, g, leader);
+                    const bool mine = pending && g == gl;
+                    const unsigned grp = __ballot_sync(active, mine);
+                    if (__popc(grp) < 4) break;  // the double butterfly costs ~20 shuffles: only for heavy groups
+                    double sx = mine ? x : 0.0, sxx = mine ? xx : 0.0;
 #pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    sx += __shfl_xor_sync(active, sx, o);
-                    sxx += __shfl_xor_sync(active, sxx, o);
-                }
-                // with a partial warp (loop tail) the butterfly reads lanes outside `active`: fall back below
-                if (active == 0xffffffffu) {
-                    if (lane == leader) {
-                        atomicAdd(&ca[g], __popc(grp));
-                        atomicAdd(&ax[g], sx);
-                        atomicAdd(&axx[g], sxx);
+                    for (int o = 16; o; o >>= 1) {
+                        sx += __shfl_xor_sync(active, sx, o);
+                        sxx += __shfl_xor_sync(active, sxx, o);
                     }
-                    if (mine) done = true;
+                    if (lane == leader) {
+                        atomicAdd(&ca[gl], __popc(grp));
+                        atomicAdd(&ax[gl], sx);
+                        atomicAdd(&axx[gl], sxx);
+                    }
+                    if (mine) pending = false;
                 }
-                todo &= ~grp;
             }
-            if (!done) {
+            if (pending) {
                 atomicAdd(&ca[g], 1);
                 atomicAdd(&ax[g], x);
                 atomicAdd(&axx[g], xx);
@@ -158,22 +160,14 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_pooled_kernel(const AddB
         });
     } else if (model == DIST_B200_GP) {
         for_each_row<kVec>(b.assign, static_cast<const uint32_t *>(d.column), b.N, kAddThreads, [&](int g, uint32_t x) {
-            const unsigned active = __activemask();
-            const bool ok = g >= 0 && g < G;
-            const unsigned peers = __match_any_sync(active, ok ? g : -1);
-            const uint32_t sum = __reduce_add_sync(peers, x);
-            if (ok && (threadIdx.x & 31) == __ffs(peers) - 1) {
-                atomicAdd(&ca[g], __popc(peers));
-                atomicAdd(reinterpret_cast<unsigned int *>(&cb[g]), sum);
-            }
+            if (g < 0 || g >= G) return;
+            atomicAdd(&ca[g], 1);
+            atomicAdd(reinterpret_cast<unsigned int *>(&cb[g]), x);
         });
     } else {  // bb
         for_each_row<kVec>(b.assign, static_cast<const uint8_t *>(d.column), b.N, kAddThreads, [&](int g, uint8_t x) {
-            const unsigned active = __activemask();
-            const bool ok = g >= 0 && g < G;
-            const int key = ok ? 2 * g + (x != 0 ? 1 : 0) : -1;
-            const unsigned peers = __match_any_sync(active, key);
-            if (ok && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(x != 0 ? &ca[g] : &cb[g], __popc(peers));
+            if (g < 0 || g >= G) return;
+            atomicAdd(x != 0 ? &ca[g] : &cb[g], 1);
         });
     }
     if (kSmem) {
@@ -232,9 +226,9 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_counts_kernel(const Coun
                 if (r >= 0) cell = g * a.dim + r;
             }
         }
-        // lanes hitting the same cell are combined: one atomic per distinct cell of the warp
-        const unsigned peers = __match_any_sync(__activemask(), cell);
-        if (cell >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&dst[cell], a.sign * __popc(peers));
+        if (cell < 0) return;
+        if (a.sign > 0) atomicAdd(&dst[cell], 1);
+        else atomicAdd(&dst[cell], -1);
     });
     if (kSmem) {
         __syncthreads();
@@ -273,8 +267,9 @@ static unsigned row_tiles(const dist_b200_ctx *ctx, size_t N, int per_sm, int sp
     return static_cast<unsigned>(want < cap ? want : cap);
 }
 
-int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s) {
-    if (b.N == 0 || b.G == 0 || b.n == 0) return DIST_B200_OK;
+int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b_in, cudaStream_t s) {
+    if (b_in.N == 0 || b_in.G == 0 || b_in.n == 0) return DIST_B200_OK;
+    const AddBatch &b = b_in;
     DISTB200_CUDA(ctx, cudaMemsetAsync(b.acc, 0, b.acc_stride * b.n, s));
     const dim3 grid(row_tiles(ctx, (b.N + 3) / 4, 8, b.n), b.n);
     bool vec = aligned16(b.assign);
