@@ -1155,17 +1155,33 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
     const size_t min_chunk = 32768;
     static const size_t max_chunks = [] {
         const char *e = getenv("DIST_B200_HOST_CHUNKS");
-        return e ? static_cast<size_t>(std::max(1, atoi(e))) : static_cast<size_t>(6);  // measured optimum at 1M rows
+        return e ? static_cast<size_t>(std::max(1, atoi(e))) : static_cast<size_t>(5);  // measured optimum at 1M rows
     }();
     size_t nchunks = std::min<size_t>(max_chunks, std::max<size_t>(1, N / min_chunk));
     for (int f = 0; f < F; ++f)  // paths that materialise through the context's single scores buffer: no overlap
         if (features[f]->model == DIST_B200_NIW || (features[f]->model == DIST_B200_DPD && F > 1)) nchunks = 1;
-    const size_t chunk = round_up((N + nchunks - 1) / nchunks, 256);
+    // chunk boundaries: equal interior chunks, half-size first and last ones -- the first H2D copy and the
+    // last D2H copy are the only transfers no kernel hides
+    std::vector<size_t> bounds(1, 0);
+    if (nchunks >= 4) {
+        const size_t unit = round_up((N + 2 * (nchunks - 1) - 1) / (2 * (nchunks - 1)), 256);  // half an interior chunk
+        size_t at = unit;
+        while (at < N && bounds.size() < nchunks - 1) {
+            bounds.push_back(at);
+            at += 2 * unit;
+        }
+        const size_t last = N > unit ? (N - unit) / 256 * 256 : 0;  // 256-row aligned like every other boundary
+        if (last > bounds.back()) bounds.push_back(last);
+    } else {
+        const size_t chunk = round_up((N + nchunks - 1) / nchunks, 256);
+        for (size_t at = chunk; at < N; at += chunk) bounds.push_back(at);
+    }
+    bounds.push_back(N);
     std::vector<const void *> cols(F);
     float *scores_dev = scores_host ? reinterpret_cast<float *>(dev + scores_off) : nullptr;
-    size_t k = 0;
-    for (size_t lo = 0; lo < N; lo += chunk, ++k) {
-        const size_t n = std::min(chunk, N - lo);
+    for (size_t k = 0; k + 1 < bounds.size(); ++k) {
+        const size_t lo = bounds[k], n = bounds[k + 1] - lo;
+        if (n == 0) continue;
         cudaStream_t s = st[k & 1];
         for (int f = 0; f < F; ++f) {
             const size_t vb = value_bytes(features[f]);

@@ -378,9 +378,12 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
             }
 
             if (kScores && !fin) {
-                // [32 rows][32 groups] transposes through a padded per-warp tile -> coalesced rows
+                // [32 rows][32 groups] transposes through a padded per-warp tile -> every store instruction
+                // writes one full 128-byte line of a row.  Everything row-invariant is hoisted: the loop body
+                // is one LDS, one STG and a pointer step.
                 float *tw = tile + warp * 32 * 33;
                 const size_t wrow0 = tile_base + warp * 32;
+                const int nrows = wrow0 < row_end ? static_cast<int>(row_end - wrow0 < 32 ? row_end - wrow0 : 32) : 0;
 #pragma unroll
                 for (int sb = 0; sb < CHUNK / 32; ++sb) {
                     __syncwarp();
@@ -388,19 +391,33 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                     for (int j = 0; j < 32; ++j) tw[lane * 33 + j] = acc[sb * 32 + j];
                     __syncwarp();
                     const int g = g0 + sb * 32 + lane;
-                    if (g < G) {
-                        for (int i = 0; i < 32; ++i) {
-                            const size_t rr = wrow0 + i;
-                            if (rr >= row_end) break;
-                            float *dst;
-                            if (a.n_push) {
-                                const size_t grow = a.row0 + rr;
-                                dst = a.push[grow / a.block_rows] + (grow % a.block_rows) * G + g;
-                            } else {
-                                dst = a.scores + rr * G + g;
+                    if (g >= G) continue;
+                    const float *src = tw + lane;
+                    if (a.n_push) {
+                        // rows of this warp tile land in at most two owners' slots
+                        const size_t grow0 = a.row0 + wrow0;
+                        int owner = static_cast<int>(grow0 / a.block_rows);
+                        size_t off = grow0 - static_cast<size_t>(owner) * a.block_rows;
+                        float *dst = a.push[owner] + off * G + g;
+                        for (int i = 0; i < nrows; ++i) {
+                            if (off == a.block_rows) {
+                                ++owner;
+                                off = 0;
+                                dst = a.push[owner] + g;
                             }
-                            const float v = tw[i * 33 + lane];
-                            *dst = a.accumulate ? *dst + v : v;
+                            *dst = src[i * 33];
+                            dst += G;
+                            ++off;
+                        }
+                    } else {
+                        float *dst = a.scores + wrow0 * G + g;
+                        if (a.accumulate) {
+                            for (int i = 0; i < nrows; ++i, dst += G) *dst += src[i * 33];
+                        } else if (nrows == 32) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i, dst += G) *dst = src[i * 33];
+                        } else {
+                            for (int i = 0; i < nrows; ++i, dst += G) *dst = src[i * 33];
                         }
                     }
                 }
