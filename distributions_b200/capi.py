@@ -42,6 +42,9 @@ SIGNATURES = {
     "dist_b200_add_rows_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz]),
     "dist_b200_remove_rows_batch": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz, c_p]),
     "dist_b200_remove_rows_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz]),
+    "dist_b200_gp_set_log_prod": (c_i, [c_p, c_p, c_p]),
+    "dist_b200_score_data_grid": (c_i, [c_p, c_p, c_sz, c_sz, c_p, c_p]),
+    "dist_b200_score_data_grid_host": (c_i, [c_p, c_p, c_sz, c_sz, c_p]),
     "dist_b200_feature_download_stats": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
     "dist_b200_count_assignments": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_i, c_p]),
     "dist_b200_prior_pitman_yor_dev": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
@@ -302,6 +305,8 @@ class Feature:
         elif m == GP:
             sh, cnt, sm = f32(w["shared"]), u32(w["count"]), u32(w["sum"])
             c.check(L.dist_b200_gp_update_all(self.h, _np_ptr(sh), cnt.size, _np_ptr(cnt), _np_ptr(sm), stream), "gp_update_all")
+            if w.get("log_prod") is not None and cnt.size:
+                self.set_log_prod(w["log_prod"], stream)
         elif m == BB:
             sh, h, t = f32(w["shared"]), i32(w["heads"]), i32(w["tails"])
             c.check(L.dist_b200_bb_update_all(self.h, _np_ptr(sh), h.size, _np_ptr(h), _np_ptr(t), stream), "bb_update_all")
@@ -334,6 +339,24 @@ class Feature:
         """batched Group::add_value: fold rows into their assigned groups on the device, rebuild the caches"""
         self.ctx.check(self.ctx.L.dist_b200_feature_add_rows(self.h, _dev_ptr(column_dev), _dev_ptr(assign_dev), n_rows, stream),
                        "add_rows")
+
+    def set_log_prod(self, log_prod, stream=None):
+        """gp only: Group::log_prod per group, read by score_data_grid"""
+        lp = np.ascontiguousarray(log_prod, dtype=np.float32)
+        self.ctx.check(self.ctx.L.dist_b200_gp_set_log_prod(self.h, _np_ptr(lp), stream), "gp_set_log_prod")
+        return self
+
+    def score_data_grid(self, shareds):
+        """log marginal likelihood of all groups under each packed Shared (host arrays): [n_grid] float32"""
+        sh = np.ascontiguousarray(np.atleast_2d(shareds), dtype=np.float32)
+        out = np.empty(sh.shape[0], dtype=np.float32)
+        self.ctx.check(self.ctx.L.dist_b200_score_data_grid_host(self.h, _np_ptr(sh), sh.shape[0], sh.shape[1], _np_ptr(out)),
+                       "score_data_grid")
+        return out
+
+    def score_data_grid_dev(self, shareds_dev, n_grid, stride, out_dev, stream=None):
+        self.ctx.check(self.ctx.L.dist_b200_score_data_grid(self.h, _dev_ptr(shareds_dev), n_grid, stride, _dev_ptr(out_dev), stream),
+                       "score_data_grid")
 
     def download_stats(self, nbytes, stream=None):
         out = np.empty(nbytes, dtype=np.uint8)

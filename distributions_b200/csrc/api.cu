@@ -294,6 +294,7 @@ void dist_b200_feature_destroy(dist_b200_feature *f) {
     if (f->niw_tc) cudaFree(f->niw_tc);
     if (f->stats) cudaFree(f->stats);
     if (f->alphas_dev) cudaFree(f->alphas_dev);
+    if (f->log_prod_dev) cudaFree(f->log_prod_dev);
     if (f->ready) cudaEventDestroy(f->ready);
     delete f;
 }
@@ -336,6 +337,7 @@ int dist_b200_gp_update_all(dist_b200_feature *f, const float shared[2], int G, 
     if (up.err) return up.err;
     f->G = G;
     f->gp_table_dirty = true;
+    f->log_prod_valid = false;
     if ((rc = mirror_stats(f, 0, c, 0, G, as_stream(stream))) || (rc = mirror_stats(f, 1, sm, 0, G, as_stream(stream)))) return rc;
     return mark_ready(f, launch_gp_prep(ctx, f->shared, 0, G, c, sm, static_cast<float4 *>(f->params), as_stream(stream)), as_stream(stream));
 }
@@ -529,6 +531,7 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             const uint32_t *sm = up.put(p + 1, 1);
             if (up.err) return up.err;
             f->gp_table_dirty = true;
+            f->log_prod_valid = false;
             if ((rc = mirror_stats(f, 0, c, groupid, 1, s)) || (rc = mirror_stats(f, 1, sm, groupid, 1, s))) return rc;
             return mark_ready(f, launch_gp_prep(ctx, f->shared, groupid, 1, c, sm, static_cast<float4 *>(f->params), s), s);
         }
@@ -579,6 +582,7 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
         DISTB200_CUDA(ctx, cudaMemcpyAsync(base + gb * groupid, base + gb * last, gb, cudaMemcpyDeviceToDevice, as_stream(stream)));
     DISTB200_CUDA(ctx, cudaMemsetAsync(base + gb * last, 0, gb, as_stream(stream)));
     f->gp_table_dirty = true;
+    f->log_prod_valid = false;
     if (f->stats && groupid != last) {
         for (int a = 0; a < stat_arrays(f); ++a) {
             const size_t e = stat_elems(f, a);
@@ -658,7 +662,10 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
                 d.aux = f->aux;
                 for (int k = 0; k < 4; ++k) d.shared[k] = f->shared[k];
                 d.model = f->model;
-                if (f->model == DIST_B200_GP) f->gp_table_dirty = true;
+                if (f->model == DIST_B200_GP) {
+                    f->gp_table_dirty = true;
+                    f->log_prod_valid = false;  // Group::log_prod is not maintained by the batched update
+                }
             } break;
             case DIST_B200_DD:
                 if (!f->alphas_dev) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: dd alphas not resident (update_all first)");
@@ -738,6 +745,100 @@ int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, con
                                void *stream) {
     if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
     return dist_b200_add_rows_batch(f->ctx, &f, 1, &column_dev, assign_dev, n_rows, stream);
+}
+
+// ---- score_data_grid (next row: hyper-parameter inference over the same device-resident statistics) ----
+static size_t shared_stride(const dist_b200_feature *f) {
+    switch (f->model) {
+        case DIST_B200_NICH: return 4;
+        case DIST_B200_GP: case DIST_B200_BB: return 2;
+        case DIST_B200_DD: return static_cast<size_t>(f->dim);
+        case DIST_B200_DPD: return 1;
+        default: return 0;
+    }
+}
+
+int dist_b200_gp_set_log_prod(dist_b200_feature *f, const float *log_prod_host, void *stream) {
+    if (!check_feature(f, DIST_B200_GP) || !log_prod_host) return DIST_B200_ERR_INVALID;
+    dist_b200_ctx *ctx = f->ctx;
+    if (f->G < 1) return fail(ctx, DIST_B200_ERR_STATE, "gp_set_log_prod: call update_all first");
+    if (f->log_prod_dev && f->log_prod_cap < f->capacity) {
+        DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+        DISTB200_CUDA(ctx, cudaFree(f->log_prod_dev));
+        f->log_prod_dev = nullptr;
+    }
+    if (!f->log_prod_dev) {
+        DISTB200_CUDA(ctx, cudaMalloc(&f->log_prod_dev, sizeof(float) * f->capacity));
+        f->log_prod_cap = f->capacity;
+    }
+    cudaStream_t s = as_stream(stream);
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(f->log_prod_dev, log_prod_host, sizeof(float) * f->G, cudaMemcpyHostToDevice, s));
+    DISTB200_CUDA(ctx, cudaStreamSynchronize(s));  // pageable source
+    f->log_prod_valid = true;
+    return DIST_B200_OK;
+}
+
+int dist_b200_score_data_grid(dist_b200_feature *f, const float *shareds_dev, size_t n_grid, size_t stride,
+                              float *out_dev, void *stream) {
+    if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
+    dist_b200_ctx *ctx = f->ctx;
+    if (!shareds_dev || !out_dev) return fail(ctx, DIST_B200_ERR_INVALID, "score_data_grid: null argument");
+    if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_data_grid: niw statistics stay on the host");
+    if (f->G < 1 || !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "score_data_grid: call update_all first");
+    if (stride < shared_stride(f)) return fail(ctx, DIST_B200_ERR_INVALID, "score_data_grid: stride shorter than the model's packed Shared");
+    if (f->model == DIST_B200_GP && !f->log_prod_valid)
+        return fail(ctx, DIST_B200_ERR_STATE, "score_data_grid: gp needs Group::log_prod (dist_b200_gp_set_log_prod) after the last statistics change");
+    if (n_grid == 0) return DIST_B200_OK;
+    cudaStream_t s = as_stream(stream);
+    DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
+    // the double accumulators live next to the add_value accumulators (same event guards both)
+    const size_t need = sizeof(double) * n_grid;
+    if (need > ctx->add_acc_bytes) {
+        if (ctx->add_acc) {
+            DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+            DISTB200_CUDA(ctx, cudaFree(ctx->add_acc));
+            ctx->add_acc = nullptr;
+            ctx->add_acc_bytes = 0;
+        }
+        DISTB200_CUDA(ctx, cudaMalloc(&ctx->add_acc, need));
+        ctx->add_acc_bytes = need;
+    }
+    if (!ctx->add_done) DISTB200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->add_done, cudaEventDisableTiming));
+    DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, ctx->add_done, 0));
+    const uint32_t *st0, *st1 = nullptr, *st2 = nullptr;
+    const float *betas = nullptr;
+    if (f->model == DIST_B200_DPD) {
+        st0 = f->stats;
+        betas = reinterpret_cast<const float *>(f->stats + static_cast<size_t>(f->G) * f->dim);
+    } else {
+        st0 = stat_ptr(f, 0);
+        if (stat_arrays(f) > 1) st1 = stat_ptr(f, 1);
+        if (stat_arrays(f) > 2) st2 = stat_ptr(f, 2);
+    }
+    int rc = launch_score_data(ctx, f, st0, st1, st2, betas, f->log_prod_dev, shareds_dev, n_grid, stride,
+                               static_cast<double *>(ctx->add_acc), out_dev, s);
+    if (rc) return rc;
+    DISTB200_CUDA(ctx, cudaEventRecord(ctx->add_done, s));
+    return DIST_B200_OK;
+}
+
+int dist_b200_score_data_grid_host(dist_b200_feature *f, const float *shareds_host, size_t n_grid, size_t stride,
+                                   float *out_host) {
+    if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
+    dist_b200_ctx *ctx = f->ctx;
+    if (!shareds_host || !out_host) return fail(ctx, DIST_B200_ERR_INVALID, "score_data_grid: null argument");
+    if (n_grid == 0) return DIST_B200_OK;
+    const size_t in_bytes = round_up(sizeof(float) * n_grid * stride, 256);
+    int rc = ensure_scratch(ctx, in_bytes + sizeof(float) * n_grid + 256);
+    if (rc) return rc;
+    cudaStream_t s = ctx->own_stream;
+    char *dev = static_cast<char *>(ctx->scratch_dev);
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(dev, shareds_host, sizeof(float) * n_grid * stride, cudaMemcpyHostToDevice, s));
+    rc = dist_b200_score_data_grid(f, reinterpret_cast<const float *>(dev), n_grid, stride, reinterpret_cast<float *>(dev + in_bytes), s);
+    if (rc == DIST_B200_OK)
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(out_host, dev + in_bytes, sizeof(float) * n_grid, cudaMemcpyDeviceToHost, s));
+    DISTB200_CUDA(ctx, cudaStreamSynchronize(s));
+    return rc;
 }
 
 int dist_b200_feature_download_stats(const dist_b200_feature *f, void *out_host, size_t capacity_bytes, size_t *n_bytes,

@@ -122,6 +122,9 @@ struct dist_b200_feature {
     uint32_t *stats = nullptr;
     size_t stats_words = 0;
     float *alphas_dev = nullptr;      // dd: alphas, resident for device-side cache rebuilds
+    float *log_prod_dev = nullptr;    // gp: Group::log_prod per group (read by score_data only)
+    int log_prod_cap = 0;
+    bool log_prod_valid = false;      // cleared by every statistics mutation that does not maintain it
     uint32_t *keys_dev = nullptr;     // dpd sorted keys
     int *key_rows_dev = nullptr;      // dpd: table row of sorted key i
     // niw
@@ -163,6 +166,10 @@ int launch_dpd_prep(dist_b200_ctx *ctx, float alpha, float beta0, int V, const f
 int launch_prior_prep(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *sizes_dev, float *prior,
                       cudaStream_t s);
 int launch_numerics_probe(dist_b200_ctx *ctx, int fn, size_t n, const float *in, float *out, cudaStream_t s);
+// score_data_grid: log marginal likelihood of all groups under n_grid packed Shareds (acc: n_grid doubles of scratch)
+int launch_score_data(dist_b200_ctx *ctx, const dist_b200_feature *f, const uint32_t *st0, const uint32_t *st1,
+                      const uint32_t *st2, const float *betas, const float *log_prod, const float *shareds_dev,
+                      size_t n_grid, size_t stride, double *acc, float *out_dev, cudaStream_t s);
 int launch_unpack_caches(dist_b200_ctx *ctx, const dist_b200_feature *f, float *out_dev, cudaStream_t s);
 
 // score_rows.cu: rows mapped to lanes, groups looped (nich / gp / bb / small-dim dd, any F)

@@ -3,6 +3,8 @@
 // and the numerics probe.  O(G * dim) work, once per batch: not the hot path.  This translation
 // unit is compiled with --fmad=false so that every expression keeps the reference's operation
 // order and rounding (the reference builds for SSE4.1, which has no FMA).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace distb200 {
@@ -227,6 +229,131 @@ __global__ void prior_prep_kernel(float alpha, float d, int G, const int32_t *__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// score_data_grid: MixtureSlave::score_data_grid (mixture.hpp:427-438) -- the log
+// marginal likelihood of ALL groups under each of n_grid hyper-parameter settings, from the device-resident
+// group statistics.  Terms are the reference's fp32 expressions operation by operation (this translation
+// unit is built without FMA contraction; fast_lgamma / fast_log through the reference's tables); only the
+// accumulation differs: the reference adds them in group order in fp32, here every term goes into a double
+// block reduction, one atomicAdd(double) per block.  grid = (blocks over cells, n_grid).
+struct ScoreDataArgs {
+    int model, G, dim;            // dim: dd dim / dpd V
+    size_t n_grid, stride;        // packed Shareds: n_grid x stride floats
+    const float *shareds;
+    const uint32_t *st0, *st1, *st2;   // statistics arrays (see dist_b200_feature::stats)
+    const float *betas;           // dpd
+    const float *log_prod;        // gp
+    double *acc;                  // [n_grid], zeroed
+};
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double warp_part[32];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_part[warp] = v;
+    __syncthreads();
+    v = (threadIdx.x < (blockDim.x >> 5)) ? warp_part[threadIdx.x] : 0.0;
+    if (warp == 0)
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256) score_data_kernel(const ScoreDataArgs a, NumericTables t) {
+    const float *sh = a.shareds + blockIdx.y * a.stride;
+    const int G = a.G;
+    double part = 0.0;
+    if (a.model == DIST_B200_NICH) {  // nich.hpp:262-288
+        const float mu = sh[0], kappa = sh[1], sigmasq = sh[2], nu = sh[3];
+        const float nu_part = fast_lgamma_exact(0.5f * nu, t.lgamma5);
+        const float kappa_part = 0.5f * fast_log_table(kappa, t.log2_table);
+        const float sigmasq_part = 0.5f * nu * fast_log_table(nu * sigmasq, t.log2_table);
+        const float log_pi = 1.1447298858493991f;
+        const int32_t *count = reinterpret_cast<const int32_t *>(a.st0);
+        const float *mean = reinterpret_cast<const float *>(a.st1), *ctv = reinterpret_cast<const float *>(a.st2);
+        for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+            if (!count[g]) continue;
+            const float n = static_cast<float>(count[g]);
+            const float mu_1 = mu - mean[g];
+            const float post_kappa = kappa + n;
+            const float post_nu = nu + n;
+            const float post_sigmasq = 1.f / post_nu * (nu * sigmasq + ctv[g] + (n * kappa * mu_1 * mu_1) / post_kappa);
+            part += static_cast<double>(fast_lgamma_exact(0.5f * post_nu, t.lgamma5) - nu_part);
+            part += static_cast<double>(kappa_part - 0.5f * fast_log_table(post_kappa, t.log2_table));
+            part += static_cast<double>(sigmasq_part - 0.5f * post_nu * fast_log_table(post_nu * post_sigmasq, t.log2_table));
+            part += static_cast<double>(-0.5f * log_pi * count[g]);
+        }
+    } else if (a.model == DIST_B200_GP) {  // gp.hpp:220-241
+        const float alpha = sh[0], inv_beta = sh[1];
+        const float alpha_part = fast_lgamma_exact(alpha, t.lgamma5);
+        const float beta_part = alpha * fast_log_table(inv_beta, t.log2_table);
+        for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+            if (!a.st0[g]) continue;
+            const float post_alpha = alpha + static_cast<float>(a.st1[g]);
+            const float post_inv_beta = inv_beta + static_cast<float>(a.st0[g]);
+            part += static_cast<double>(fast_lgamma_exact(post_alpha, t.lgamma5) - alpha_part);
+            part += static_cast<double>(beta_part - post_alpha * fast_log_table(post_inv_beta, t.log2_table));
+            part += static_cast<double>(-a.log_prod[g]);
+        }
+    } else if (a.model == DIST_B200_BB) {  // bb.hpp:207-229
+        const float alpha0 = sh[0], beta0 = sh[1];
+        const float shared_part = fast_lgamma_exact(alpha0 + beta0, t.lgamma5) - fast_lgamma_exact(alpha0, t.lgamma5) -
+                                  fast_lgamma_exact(beta0, t.lgamma5);
+        const int32_t *heads = reinterpret_cast<const int32_t *>(a.st0), *tails = reinterpret_cast<const int32_t *>(a.st1);
+        for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+            const float alpha = alpha0 + heads[g];
+            const float beta = beta0 + tails[g];
+            const float group_part = fast_lgamma_exact(alpha, t.lgamma5) + fast_lgamma_exact(beta, t.lgamma5) -
+                                     fast_lgamma_exact(alpha + beta, t.lgamma5);
+            part += static_cast<double>(shared_part + group_part);
+        }
+    } else if (a.model == DIST_B200_DD) {  // dd.hpp:291-324; one thread per (group, value) cell
+        const int dim = a.dim;
+        const int32_t *counts = reinterpret_cast<const int32_t *>(a.st0);
+        float alpha_sum = 0;  // dd.hpp:297-302, sequential
+        for (int v = 0; v < dim; ++v) alpha_sum += sh[v];
+        const float total_part = fast_lgamma_exact(alpha_sum, t.lgamma5);
+        const size_t cells = static_cast<size_t>(G) * dim;
+        for (size_t c = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < cells;
+             c += static_cast<size_t>(gridDim.x) * blockDim.x) {
+            const int g = static_cast<int>(c / dim), v = static_cast<int>(c % dim);
+            const int32_t *row = counts + static_cast<size_t>(g) * dim;
+            int32_t count_sum = 0;
+            for (int k = 0; k < dim; ++k) count_sum += row[k];
+            if (!count_sum) continue;
+            const float alpha = sh[v];
+            part += static_cast<double>(fast_lgamma_exact(alpha + row[v], t.lgamma5) - fast_lgamma_exact(alpha, t.lgamma5));
+            if (v == 0) part += static_cast<double>(total_part - fast_lgamma_exact(alpha_sum + count_sum, t.lgamma5));
+        }
+    } else {  // dpd: dpd.hpp:344-374; one warp per group, lanes over the V known values
+        const int V = a.dim;
+        const float alpha = sh[0];
+        const int32_t *counts = reinterpret_cast<const int32_t *>(a.st0);
+        const float shared_total = fast_lgamma_exact(alpha, t.lgamma5);
+        const int lane = threadIdx.x & 31;
+        const int warps = (gridDim.x * blockDim.x) >> 5;
+        for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < G; g += warps) {
+            const int32_t *row = counts + static_cast<size_t>(g) * V;
+            long long total = 0;
+            for (int v = lane; v < V; v += 32) {
+                const int32_t c = row[v];
+                total += c;
+                if (!c) continue;
+                const float prior_i = a.betas[v] * alpha;
+                part += static_cast<double>(fast_lgamma_exact(prior_i + c, t.lgamma5) - fast_lgamma_exact(alpha * a.betas[v], t.lgamma5));
+            }
+            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            if (lane == 0 && total) part += static_cast<double>(shared_total - fast_lgamma_exact(alpha + static_cast<float>(total), t.lgamma5));
+        }
+    }
+    const double sum = block_sum(part);
+    if (threadIdx.x == 0 && sum != 0.0) atomicAdd(&a.acc[blockIdx.y], sum);
+}
+
+__global__ void score_data_finish_kernel(size_t n, const double *__restrict__ acc, float *__restrict__ out) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = static_cast<float>(acc[i]);
+}
+
 // numerics probe (dist_b200_numerics_probe)
 __global__ void numerics_probe_kernel(int fn, size_t n, const float *__restrict__ in, float *__restrict__ out,
                                       NumericTables t) {
@@ -346,6 +473,45 @@ int launch_prior_prep(dist_b200_ctx *ctx, float alpha, float d, int G, const int
                       cudaStream_t s) {
     const int blocks = G <= 256 ? 1 : (G + 255) / 256 < 64 ? (G + 255) / 256 : 64;
     prior_prep_kernel<<<blocks, 256, 0, s>>>(alpha, d, G, sizes, prior, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+int launch_score_data(dist_b200_ctx *ctx, const dist_b200_feature *f, const uint32_t *st0, const uint32_t *st1,
+                      const uint32_t *st2, const float *betas, const float *log_prod, const float *shareds_dev,
+                      size_t n_grid, size_t stride, double *acc, float *out_dev, cudaStream_t s) {
+    if (n_grid == 0) return DIST_B200_OK;
+    ScoreDataArgs a{};
+    a.model = f->model;
+    a.G = f->G;
+    a.dim = f->dim;
+    a.n_grid = n_grid;
+    a.stride = stride;
+    a.shareds = shareds_dev;
+    a.st0 = st0;
+    a.st1 = st1;
+    a.st2 = st2;
+    a.betas = betas;
+    a.log_prod = log_prod;
+    a.acc = acc;
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * n_grid, s);
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, cudaGetErrorString(e));
+    size_t work = static_cast<size_t>(f->G);
+    if (f->model == DIST_B200_DD) work *= f->dim;
+    if (f->model == DIST_B200_DPD) work *= 32;  // one warp per group
+    size_t blocks = (work + 255) / 256;
+    const size_t cap = std::max<size_t>(1, static_cast<size_t>(ctx->sm_count) * 8 / std::min<size_t>(n_grid, 8));
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    for (size_t i0 = 0; i0 < n_grid; i0 += 65535) {  // grid.y limit
+        ScoreDataArgs b = a;
+        const size_t n = std::min<size_t>(65535, n_grid - i0);
+        b.shareds = shareds_dev + i0 * stride;
+        b.acc = acc + i0;
+        score_data_kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(n)), 256, 0, s>>>(b, ctx->tables);
+        LAUNCH_CHECK(ctx);
+    }
+    score_data_finish_kernel<<<blocks_for(n_grid, 256), 256, 0, s>>>(n_grid, acc, out_dev);
     LAUNCH_CHECK(ctx);
     return DIST_B200_OK;
 }

@@ -46,7 +46,10 @@ def gp(seed, G, N, lam=5.0):
     rates = rng.gamma(2.0, lam / 2.0, G)
     count = sizes.astype(np.uint32)
     sum_ = np.array([rng.poisson(rates[g], sizes[g]).sum() if sizes[g] else 0 for g in range(G)], np.uint32)
-    return dict(model="gp", shared=np.array([1.0, 1.0], np.float32), sizes=sizes, count=count, sum=sum_,
+    # Group::log_prod = sum of log(value!) over the group's values (gp.hpp:109-116); only score_data reads it.
+    # Synthesised from the sums without drawing from rng (the committed golden vectors pin the stream).
+    log_prod = (0.5 * count * np.log1p(sum_ / np.maximum(count, 1)) ** 2).astype(np.float32)
+    return dict(model="gp", shared=np.array([1.0, 1.0], np.float32), sizes=sizes, count=count, sum=sum_, log_prod=log_prod,
                 values=rng.poisson(lam, N).astype(np.uint32), u=rng.random(N, dtype=np.float32))
 
 

@@ -142,6 +142,21 @@ int dist_b200_remove_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *cons
  * features[i] (float / uint32 / int32, bool as uint8), assign_host the packed group ids.  Synchronous. */
 int dist_b200_add_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
                                   const void *const *columns_host, const int32_t *assign_host, size_t n_rows);
+/* ---- score_data_grid: hyper-parameter inference over the same statistics ---------------------------
+ * out[i] = log marginal likelihood of all groups of `f` under hyper-parameter setting i: the reference's
+ * MixtureSlave::score_data_grid / score_data (mixture.hpp:427-438; nich.hpp:262-288, gp.hpp:220-241,
+ * bb.hpp:207-229, dd.hpp:250-324, dpd.hpp:344-374) on the device-resident group statistics.  shareds:
+ * n_grid packed Shareds, `stride` floats apart -- nich (mu, kappa, sigmasq, nu); gp (alpha, inv_beta);
+ * bb (alpha, beta); dd alphas[dim]; dpd (alpha), with beta0 / betas of the last update_all.  Every term is
+ * the reference's fp32 expression; the sum over groups is accumulated in double (the reference: fp32, group
+ * order), so results agree to ~1e-6 of sum |term|.  gp reads Group::log_prod, which the hot path does not
+ * carry: set it with dist_b200_gp_set_log_prod after update_all / any statistics change (ERR_STATE otherwise).
+ * niw: unsupported. */
+int dist_b200_gp_set_log_prod(dist_b200_feature *f, const float *log_prod_host, void *stream);
+int dist_b200_score_data_grid(dist_b200_feature *f, const float *shareds_dev, size_t n_grid, size_t stride,
+                              float *out_dev, void *stream);
+int dist_b200_score_data_grid_host(dist_b200_feature *f, const float *shareds_host, size_t n_grid, size_t stride,
+                                   float *out_host);
 /* Device-resident statistics back to the host, arrays in update_all's argument order, G entries each
  * (nich: count,int32 | mean,f32 | ctv,f32; gp: count | sum; bb: heads | tails; dd: counts[G][dim];
  * dpd: counts[G][V]).  Synchronises the stream. */

@@ -198,6 +198,127 @@ void orc_py_prior(float alpha, float d, size_t G, const int32_t *sizes, float *o
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* score_data: MixtureDataScorer::score_data of every model -- the log marginal  */
+/* likelihood of all groups under one Shared, fp32, accumulated in group order like the reference.    */
+/* `abs_sum` (optional) receives sum |term|: the scale the fp32 accumulation error is relative to.    */
+
+/* abs_sum[0] += |term| (the scale of the accumulation error), abs_sum[1] += term (the same fp32 terms
+ * accumulated in double: what the device computes) */
+static float acc_term(float score, float term, double *abs_sum) {
+    if (abs_sum) {
+        abs_sum[0] += fabs((double)term);
+        abs_sum[1] += (double)term;
+    }
+    return score + term;
+}
+
+/* nich.hpp:262-288 (Shared::plus_group nich.hpp:58-69) */
+float orc_nich_score_data(const float sh[4], size_t G, const int32_t *count, const float *mean,
+                          const float *ctv, double *abs_sum) {
+    const float mu = sh[0], kappa = sh[1], sigmasq = sh[2], nu = sh[3];
+    const float nu_part = orc_fast_lgamma(0.5f * nu);
+    const float kappa_part = 0.5f * orc_fast_log(kappa);
+    const float sigmasq_part = 0.5f * nu * orc_fast_log(nu * sigmasq);
+    const float log_pi = 1.1447298858493991f;
+    float score = 0;
+    if (abs_sum) abs_sum[0] = abs_sum[1] = 0;
+    for (size_t g = 0; g < G; ++g) {
+        if (!count[g]) continue;
+        float n = (float)count[g];
+        float mu_1 = mu - mean[g];
+        float post_kappa = kappa + n;
+        float post_nu = nu + n;
+        float post_sigmasq =
+            1.f / post_nu * (nu * sigmasq + ctv[g] + (n * kappa * mu_1 * mu_1) / post_kappa);
+        score = acc_term(score, orc_fast_lgamma(0.5f * post_nu) - nu_part, abs_sum);
+        score = acc_term(score, kappa_part - 0.5f * orc_fast_log(post_kappa), abs_sum);
+        score = acc_term(score, sigmasq_part - 0.5f * post_nu * orc_fast_log(post_nu * post_sigmasq), abs_sum);
+        score = acc_term(score, -0.5f * log_pi * count[g], abs_sum);
+    }
+    return score;
+}
+
+/* gp.hpp:220-241 (plus_group gp.hpp:56-61) */
+float orc_gp_score_data(const float sh[2], size_t G, const uint32_t *count, const uint32_t *sum,
+                        const float *log_prod, double *abs_sum) {
+    const float alpha_part = orc_fast_lgamma(sh[0]);
+    const float beta_part = sh[0] * orc_fast_log(sh[1]);
+    float score = 0;
+    if (abs_sum) abs_sum[0] = abs_sum[1] = 0;
+    for (size_t g = 0; g < G; ++g) {
+        if (!count[g]) continue;
+        float post_alpha = sh[0] + (float)sum[g];
+        float post_inv_beta = sh[1] + (float)count[g];
+        score = acc_term(score, orc_fast_lgamma(post_alpha) - alpha_part, abs_sum);
+        score = acc_term(score, beta_part - post_alpha * orc_fast_log(post_inv_beta), abs_sum);
+        score = acc_term(score, -log_prod[g], abs_sum);
+    }
+    return score;
+}
+
+/* bb.hpp:207-229 */
+float orc_bb_score_data(const float sh[2], size_t G, const int32_t *heads, const int32_t *tails, double *abs_sum) {
+    const float shared_part = orc_fast_lgamma(sh[0] + sh[1]) - orc_fast_lgamma(sh[0]) - orc_fast_lgamma(sh[1]);
+    float score = 0;
+    if (abs_sum) abs_sum[0] = abs_sum[1] = 0;
+    for (size_t g = 0; g < G; ++g) {
+        float alpha = sh[0] + heads[g];
+        float beta = sh[1] + tails[g];
+        float group_part = orc_fast_lgamma(alpha) + orc_fast_lgamma(beta) - orc_fast_lgamma(alpha + beta);
+        score = acc_term(score, shared_part + group_part, abs_sum);
+    }
+    return score;
+}
+
+/* dd.hpp:250-256 = _init (291-320) + _eval (322-324): per-value partial sums over the groups, then the
+ * (dim + 1)-vector is summed (vector_math.cc:85-93) */
+float orc_dd_score_data(int dim, const float *alphas, size_t G, const int32_t *counts, double *abs_sum) {
+    float shared_part[257], scores[257];
+    float alpha_sum = 0;
+    for (int i = 0; i < dim; ++i) {
+        alpha_sum += alphas[i];
+        shared_part[i] = orc_fast_lgamma(alphas[i]);
+        scores[i] = 0;
+    }
+    shared_part[dim] = orc_fast_lgamma(alpha_sum);
+    scores[dim] = 0;
+    if (abs_sum) abs_sum[0] = abs_sum[1] = 0;
+    for (size_t g = 0; g < G; ++g) {
+        const int32_t *c = counts + g * dim;
+        int32_t count_sum = 0;
+        for (int i = 0; i < dim; ++i) count_sum += c[i];
+        if (!count_sum) continue;
+        for (int i = 0; i < dim; ++i)
+            scores[i] = acc_term(scores[i], orc_fast_lgamma(alphas[i] + c[i]) - shared_part[i], abs_sum);
+        scores[dim] = acc_term(scores[dim], shared_part[dim] - orc_fast_lgamma(alpha_sum + count_sum), abs_sum);
+    }
+    float total = 0;
+    for (int i = 0; i <= dim; ++i) total += scores[i];
+    return total;
+}
+
+/* dpd.hpp:344-374; counts dense [G][V] (the sparse counters hold exactly the non-zero entries; the
+ * reference iterates them in hash-map order, this restatement in value order) */
+float orc_dpd_score_data(float alpha, size_t V, const float *betas, size_t G, const int32_t *counts, double *abs_sum) {
+    const float shared_total = orc_fast_lgamma(alpha);
+    float score = 0;
+    if (abs_sum) abs_sum[0] = abs_sum[1] = 0;
+    for (size_t g = 0; g < G; ++g) {
+        const int32_t *c = counts + g * V;
+        long total = 0;
+        for (size_t v = 0; v < V; ++v) total += c[v];
+        if (!total) continue;
+        for (size_t v = 0; v < V; ++v) {
+            if (!c[v]) continue;
+            float prior_i = betas[v] * alpha;
+            score = acc_term(score, orc_fast_lgamma(prior_i + c[v]) - orc_fast_lgamma(alpha * betas[v]), abs_sum);
+        }
+        score = acc_term(score, shared_total - orc_fast_lgamma(alpha + total), abs_sum);
+    }
+    return score;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* cache rebuilds                                                                              */
 
 void orc_nich_caches(const float sh[4], size_t G, const int32_t *count, const float *mean,

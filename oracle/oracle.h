@@ -88,6 +88,17 @@ void orc_gp_group_update(int op, uint32_t *count, uint32_t *sum, float *log_prod
 double orc_bench_nich(size_t G, const float *cache, const float *prior, size_t n, const float *values,
                       const float *u, int32_t *assign, int n_threads);
 
+/* ---- score_data (log marginal likelihood of all groups): nich.hpp:262-288,
+ * gp.hpp:220-241, bb.hpp:207-229, dd.hpp:250-324, dpd.hpp:344-374.  Returns the reference's fp32 group-order
+ * accumulation; abs_sum (nullable, 2 doubles) receives sum |term| and the same fp32 terms summed in double. */
+float orc_nich_score_data(const float sh[4], size_t G, const int32_t *count, const float *mean,
+                          const float *ctv, double *abs_sum);
+float orc_gp_score_data(const float sh[2], size_t G, const uint32_t *count, const uint32_t *sum,
+                        const float *log_prod, double *abs_sum);
+float orc_bb_score_data(const float sh[2], size_t G, const int32_t *heads, const int32_t *tails, double *abs_sum);
+float orc_dd_score_data(int dim, const float *alphas, size_t G, const int32_t *counts, double *abs_sum);
+float orc_dpd_score_data(float alpha, size_t V, const float *betas, size_t G, const int32_t *counts, double *abs_sum);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,6 +177,38 @@ class Oracle:
         self.L.orc_gp_group_update(op, ctypes.byref(c), ctypes.byref(s), ctypes.byref(lp), _ptr(values), values.size)
         return c.value, s.value, lp.value
 
+    def score_data(self, w, shared=None):
+        """MixtureDataScorer::score_data of workload dict `w` (tests/cases.py layout) under `shared`
+        (default: the workload's own).  Returns (score, sum |term|, the same fp32 terms summed in double)."""
+        a = (ctypes.c_double * 2)(0, 0)
+        m = w["model"]
+        L = self.L
+        for fn in ("orc_nich_score_data", "orc_gp_score_data", "orc_bb_score_data", "orc_dd_score_data", "orc_dpd_score_data"):
+            getattr(L, fn).restype = c_f
+        if m == "nich":
+            sh = _f32(w["shared"] if shared is None else shared)
+            c, mean, ctv = _i32(w["count"]), _f32(w["mean"]), _f32(w["ctv"])
+            r = L.orc_nich_score_data(_ptr(sh), ctypes.c_size_t(c.size), _ptr(c), _ptr(mean), _ptr(ctv), a)
+        elif m == "gp":
+            sh = _f32(w["shared"] if shared is None else shared)
+            c, sm, lp = _u32(w["count"]), _u32(w["sum"]), _f32(w["log_prod"])
+            r = L.orc_gp_score_data(_ptr(sh), ctypes.c_size_t(c.size), _ptr(c), _ptr(sm), _ptr(lp), a)
+        elif m == "bb":
+            sh = _f32(w["shared"] if shared is None else shared)
+            h, t = _i32(w["heads"]), _i32(w["tails"])
+            r = L.orc_bb_score_data(_ptr(sh), ctypes.c_size_t(h.size), _ptr(h), _ptr(t), a)
+        elif m == "dd":
+            al = _f32(w["alphas"] if shared is None else shared)
+            c = _i32(w["counts"])
+            r = L.orc_dd_score_data(int(al.size), _ptr(al), ctypes.c_size_t(c.shape[0]), _ptr(c), a)
+        elif m == "dpd":
+            alpha = float(w["alpha"] if shared is None else np.ravel(shared)[0])
+            b, c = _f32(w["betas"]), _i32(w["counts"])
+            r = L.orc_dpd_score_data(c_f(alpha), ctypes.c_size_t(b.size), _ptr(b), ctypes.c_size_t(c.shape[0]), _ptr(c), a)
+        else:
+            raise ValueError(m)
+        return float(r), float(a[0]), float(a[1])
+
     def bench_nich(self, cache, prior, values, u, n_threads):
         cache, prior, values, u = _f32(cache), _f32(prior), _f32(values), _f32(u)
         assign = np.empty(values.size, dtype=np.int32)
@@ -201,6 +233,8 @@ class Ref:
         L.refshim_vec.argtypes = [c_i, c_sz, c_p, c_p]
         L.refshim_py_score_add_value.restype = c_f
         L.refshim_py_score_add_value.argtypes = [c_f, c_f, c_i32, c_i32, c_i32, c_i32]
+        L.refshim_kind_score_data_grid.restype = ctypes.c_int
+        L.refshim_kind_score_data_grid.argtypes = [c_p, ctypes.c_int, ctypes.c_size_t, c_p, ctypes.c_size_t, ctypes.c_int, c_p]
         L.refshim_kind_create.restype = c_p
         L.refshim_kind_create.argtypes = [c_sz, c_p, c_f, c_f]
         L.refshim_kind_destroy.argtypes = [c_p]
@@ -324,6 +358,15 @@ class RefKind:
             scores = np.zeros((n, self.G), dtype=np.float32)
         self.L.refshim_kind_score_rows(self.h, arr, row0, n, 1 if with_prior else 0, _ptr(scores))
         return scores
+
+    def score_data_grid(self, f, shareds, use_grid=True):
+        """reference Mixture::score_data_grid (or score_data per point) of feature f; shareds [n_grid][stride]"""
+        shareds = np.ascontiguousarray(np.atleast_2d(shareds), dtype=np.float32)
+        out = np.empty(shareds.shape[0], dtype=np.float32)
+        rc = self.L.refshim_kind_score_data_grid(self.h, f, ctypes.c_size_t(shareds.shape[0]), _ptr(shareds),
+                                                 ctypes.c_size_t(shareds.shape[1]), 1 if use_grid else 0, _ptr(out))
+        assert rc == 0
+        return out
 
     def group_scores(self, f, value, which=0):
         v = np.asarray([value], dtype=COL_DTYPE[self.models[f]])

@@ -437,6 +437,61 @@ double refshim_kind_bench(void * p, const void * const * cols, size_t n, int n_t
 }
 
 // ----------------------------------------------------------------------------------------------
+// MixtureSlave::score_data_grid / score_data (mixture.hpp:427-438) of feature f over n_grid hyper-parameter
+// settings.  shareds: n_grid packed Shareds, `stride` floats each -- nich (mu, kappa, sigmasq, nu); gp (alpha,
+// inv_beta); bb (alpha, beta); dd alphas[dim]; dpd (alpha) with gamma / beta0 / betas of the feature's Shared.
+// use_grid != 0 calls score_data_grid (dd: the incremental _update path, dd.hpp:259-289), else score_data per point.
+int refshim_kind_score_data_grid(void * p, int f, size_t n_grid, const float * shareds, size_t stride,
+                                 int use_grid, float * out) {
+    RefKind * k = K(p);
+    D::rng_t rng;
+    Feature & ft = *k->feats[f];
+    D::VectorFloat scores(n_grid);
+    switch (ft.kind) {
+        case K_NICH: {
+            std::vector<NICH::Shared> grid(n_grid, ft.nich_shared);
+            for (size_t i = 0; i < n_grid; ++i) {
+                const float * s = shareds + i * stride;
+                grid[i].mu = s[0]; grid[i].kappa = s[1]; grid[i].sigmasq = s[2]; grid[i].nu = s[3];
+            }
+            if (use_grid) ft.nich.score_data_grid(grid, scores, rng);
+            else for (size_t i = 0; i < n_grid; ++i) scores[i] = ft.nich.score_data(grid[i], rng);
+        } break;
+        case K_GP: {
+            std::vector<GP::Shared> grid(n_grid, ft.gp_shared);
+            for (size_t i = 0; i < n_grid; ++i) {
+                grid[i].alpha = shareds[i * stride]; grid[i].inv_beta = shareds[i * stride + 1];
+            }
+            if (use_grid) ft.gp.score_data_grid(grid, scores, rng);
+            else for (size_t i = 0; i < n_grid; ++i) scores[i] = ft.gp.score_data(grid[i], rng);
+        } break;
+        case K_BB: {
+            std::vector<BB::Shared> grid(n_grid, ft.bb_shared);
+            for (size_t i = 0; i < n_grid; ++i) {
+                grid[i].alpha = shareds[i * stride]; grid[i].beta = shareds[i * stride + 1];
+            }
+            if (use_grid) ft.bb.score_data_grid(grid, scores, rng);
+            else for (size_t i = 0; i < n_grid; ++i) scores[i] = ft.bb.score_data(grid[i], rng);
+        } break;
+        case K_DD: {
+            std::vector<DD::Shared> grid(n_grid, ft.dd_shared);
+            for (size_t i = 0; i < n_grid; ++i)
+                for (int v = 0; v < ft.dd_shared.dim; ++v) grid[i].alphas[v] = shareds[i * stride + v];
+            if (use_grid) ft.dd.score_data_grid(grid, scores, rng);
+            else for (size_t i = 0; i < n_grid; ++i) scores[i] = ft.dd.score_data(grid[i], rng);
+        } break;
+        case K_DPD: {
+            std::vector<DPD::Shared> grid(n_grid, ft.dpd_shared);
+            for (size_t i = 0; i < n_grid; ++i) grid[i].alpha = shareds[i * stride];
+            if (use_grid) ft.dpd.score_data_grid(grid, scores, rng);
+            else for (size_t i = 0; i < n_grid; ++i) scores[i] = ft.dpd.score_data(grid[i], rng);
+        } break;
+        default: return -1;
+    }
+    for (size_t i = 0; i < n_grid; ++i) out[i] = scores[i];
+    return 0;
+}
+
 // Group::add_value / remove_value (host-side bookkeeping the product mirrors)
 // op: +1 add, -1 remove; state arrays are in/out
 void refshim_nich_group_update(int op, int32_t * count, float * mean, float * ctv,

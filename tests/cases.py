@@ -29,7 +29,7 @@ def ref_add_feature(kind, w):
     if m == "nich":
         return kind.add_nich(w["shared"], w["count"], w["mean"], w["ctv"])
     if m == "gp":
-        return kind.add_gp(w["shared"], w["count"], w["sum"])
+        return kind.add_gp(w["shared"], w["count"], w["sum"], w.get("log_prod"))
     if m == "bb":
         return kind.add_bb(w["shared"], w["heads"], w["tails"])
     if m == "dd":
@@ -96,3 +96,59 @@ def explained_mismatch(scores64, u, a, b, eps):
         seg = cdf[i, lo[i]:hi[i]]
         ok[i] = np.all(np.abs(seg - t[i]) <= eps * total[i])
     return ok
+
+
+# score_data golden cases: model -> (seed, G, synth kwargs, grid points); tests/golden/make_golden_score_data.py
+SCORE_DATA = {
+    "nich": (9101, 70, {}, 12),
+    "gp": (9102, 45, {}, 12),
+    "bb": (9103, 33, {}, 12),
+    "dd": (9104, 52, dict(dim=16), 12),
+    "dpd": (9105, 14, dict(V=80, other_frac=0.05), 8),
+}
+
+
+def shared_grid(w, n_grid, seed=0):
+    """n_grid hyper-parameter settings around workload w's Shared, packed as score_data_grid takes them:
+    nich (mu, kappa, sigmasq, nu); gp (alpha, inv_beta); bb (alpha, beta); dd alphas[dim]; dpd (alpha).
+    Consecutive dd settings differ in a few alphas only (the reference's incremental _update path)."""
+    rng = np.random.default_rng(seed)
+    m = w["model"]
+    if m == "nich":
+        g = np.tile(np.asarray(w["shared"], np.float32), (n_grid, 1))
+        g[:, 0] += rng.normal(0, 1, n_grid)
+        g[:, 1] *= rng.uniform(0.3, 3, n_grid)
+        g[:, 2] *= rng.uniform(0.3, 3, n_grid)
+        g[:, 3] *= rng.uniform(0.3, 3, n_grid)
+    elif m in ("gp", "bb"):
+        g = np.tile(np.asarray(w["shared"], np.float32), (n_grid, 1)) * rng.uniform(0.3, 3, (n_grid, 2))
+    elif m == "dd":
+        g = np.tile(np.asarray(w["alphas"], np.float32), (n_grid, 1))
+        for i in range(1, n_grid):
+            g[i] = g[i - 1]
+            idx = rng.integers(0, g.shape[1], 2)
+            g[i, idx] = rng.uniform(0.1, 2.0, 2)
+    elif m == "dpd":
+        g = (w["alpha"] * rng.uniform(0.3, 3, (n_grid, 1)))
+    else:
+        raise ValueError(m)
+    return np.ascontiguousarray(g, dtype=np.float32)
+
+
+def score_data_terms(w):
+    """number of fp32 terms MixtureDataScorer::score_data adds for workload w"""
+    m = w["model"]
+    G = w["sizes"].size
+    if m == "nich":
+        return 4 * G
+    if m == "gp":
+        return 3 * G
+    if m == "bb":
+        return G
+    return (w["counts"].shape[1] + 1) * G
+
+
+def accum_tol(n_terms, scale):
+    """rounding of an fp32 accumulation of n_terms terms with sum |term| = scale, in whatever order:
+    2 eps32 * sqrt(n_terms) * scale (a random-walk bound; the worst case is n_terms * eps32 * scale)"""
+    return 2.4e-7 * np.sqrt(n_terms) * scale + 1e-5

@@ -33,3 +33,9 @@ def golden():
     import numpy as np
     path = os.path.join(ROOT, "tests", "golden", "hotpath_golden.npz")
     return np.load(path)
+
+
+@pytest.fixture(scope="session")
+def golden_score_data():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "score_data_golden.npz"))

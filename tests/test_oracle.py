@@ -300,3 +300,49 @@ def test_niw_1d_reference_kat(oracle, ref):
     got = oracle.niw_score_rows([30.0], 0.3, [[2.0]], 3.0, [n], np.float32([[data.sum()]]),
                                 np.float32([[[(data ** 2).sum()]]]), vals.reshape(2, 1), np.zeros((2, 1), np.float32))
     assert np.all(relerr(got, want) <= 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# score_data: the restatement against the compiled reference.  Both sum fp32 terms in
+# group order; the -ffast-math reference build may re-associate (dd sums a vector, dpd iterates a hash
+# map), so the comparison is relative to sum |term|.
+@pytest.mark.parametrize("name,G", [("nich", 50), ("gp", 37), ("bb", 21), ("dd", 40), ("dpd", 12)])
+def test_score_data_matches_reference(oracle, ref, name, G):
+    kw = dict(dim=16) if name == "dd" else (dict(V=60, other_frac=0.05) if name == "dpd" else {})
+    w = getattr(synth, name)(8100 + G, G, 10, **kw)
+    k = ref.kind(G, w["sizes"], synth.PY_ALPHA, synth.PY_D)
+    f = cases.ref_add_feature(k, w)
+    grid = cases.shared_grid(w, 9, seed=G)
+    per_point = k.score_data_grid(f, grid, use_grid=False)
+    gridded = k.score_data_grid(f, grid, use_grid=True)
+    for i in range(grid.shape[0]):
+        got, scale, got64 = oracle.score_data(w, grid[i])
+        tol = cases.accum_tol(cases.score_data_terms(w), scale)
+        assert abs(got - per_point[i]) <= tol, (name, i, got, per_point[i], scale)
+        assert abs(got64 - per_point[i]) <= tol, (name, i, got64, per_point[i], scale)
+        # score_data_grid == score_data up to the accumulation order (dd's incremental _update)
+        assert abs(got - gridded[i]) <= 4 * tol, (name, i, got, gridded[i], scale)
+
+
+def test_score_data_skips_empty_groups_and_own_shared(oracle, ref):
+    w = synth.nich(5, 9, 4)
+    w["count"][2] = 0
+    k = ref.kind(9, w["sizes"], synth.PY_ALPHA, synth.PY_D)
+    f = cases.ref_add_feature(k, w)
+    got, scale, _ = oracle.score_data(w)
+    want = k.score_data_grid(f, np.asarray(w["shared"], np.float32)[None, :], use_grid=False)[0]
+    assert abs(got - want) <= cases.accum_tol(cases.score_data_terms(w), scale)
+
+
+def test_score_data_oracle_matches_golden(oracle, golden_score_data):
+    """runs without the reference (GPU box / fresh checkout): the restatement against the committed outputs"""
+    gd = golden_score_data
+    for name, (seed, G, kw, n_grid) in cases.SCORE_DATA.items():
+        w = getattr(synth, name)(seed, G, 10, **kw)
+        grid = cases.shared_grid(w, n_grid, seed=seed)
+        assert np.array_equal(grid, gd["sd_%s_grid" % name])
+        for i in range(n_grid):
+            got, scale, got64 = oracle.score_data(w, grid[i])
+            tol = cases.accum_tol(cases.score_data_terms(w), scale)
+            assert abs(got - gd["sd_%s_out" % name][i]) <= tol, (name, i)
+            assert abs(got64 - gd["sd_%s_out" % name][i]) <= tol, (name, i)
