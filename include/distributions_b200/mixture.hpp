@@ -122,6 +122,9 @@ struct NormalInverseChiSq {
         for (size_t g = 0; g < G; ++g) { groups[g].count = c[g]; groups[g].mean = m[g]; groups[g].count_times_variance = v[g]; }
     }
     static size_t stats_bytes(const Shared &, size_t G) { return 12 * G; }
+    static void pack_shared(const Shared & s, std::vector<float> & out) {  // score_data_grid layout
+        out.push_back(s.mu); out.push_back(s.kappa); out.push_back(s.sigmasq); out.push_back(s.nu);
+    }
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         struct { int32_t count; float mean; float ctv; } st = {g.count, g.mean, g.count_times_variance};
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), &st, nullptr);
@@ -155,6 +158,7 @@ struct GammaPoisson {
         for (size_t g = 0; g < G; ++g) { groups[g].count = c[g]; groups[g].sum = c[G + g]; }
     }
     static size_t stats_bytes(const Shared &, size_t G) { return 8 * G; }
+    static void pack_shared(const Shared & s, std::vector<float> & out) { out.push_back(s.alpha); out.push_back(s.inv_beta); }
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         const uint32_t st[2] = {g.count, g.sum};
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), st, nullptr);
@@ -187,6 +191,7 @@ struct BetaBernoulli {
         for (size_t g = 0; g < G; ++g) { groups[g].heads = c[g]; groups[g].tails = c[G + g]; }
     }
     static size_t stats_bytes(const Shared &, size_t G) { return 8 * G; }
+    static void pack_shared(const Shared & s, std::vector<float> & out) { out.push_back(s.alpha); out.push_back(s.beta); }
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         const int32_t st[2] = {g.heads, g.tails};
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), st, nullptr);
@@ -234,6 +239,9 @@ struct DirichletDiscrete {
         }
     }
     static size_t stats_bytes(const Shared & s, size_t G) { return 4 * G * s.dim; }
+    static void pack_shared(const Shared & s, std::vector<float> & out) {
+        for (int v = 0; v < s.dim; ++v) out.push_back(s.alphas[v]);
+    }
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), g.counts, nullptr);
     }
@@ -298,6 +306,26 @@ class Mixture {
         std::vector<float> tmp(groups_.size(), 0.f);
         score_value(shared, value, Floats(tmp), rng);
         return tmp[groupid];
+    }
+
+    // mixture.hpp:427-438: log marginal likelihood of all groups under `shared` / under each of `shareds`,
+    // evaluated on the device-resident statistics (fp32 terms of the reference, summed in double).
+    // GammaPoisson needs Group::log_prod, which this mirror's Group does not carry: set it first with
+    // dist_b200_gp_set_log_prod(feature(), ...).
+    float score_data(const Shared & shared, rng_t & rng) const {
+        std::vector<Shared> one(1, shared);
+        float out = 0.f;
+        score_data_grid(one, Floats(&out, 1), rng);
+        return out;
+    }
+    void score_data_grid(const std::vector<Shared> & shareds, Floats scores_out, rng_t &) const {
+        if (shareds.size() != scores_out.size()) throw std::runtime_error("score_data_grid: size mismatch");
+        if (shareds.empty()) return;
+        std::vector<float> packed;
+        for (const Shared & s : shareds) Model::pack_shared(s, packed);
+        ctx_->check(dist_b200_score_data_grid_host(f_, packed.data(), shareds.size(), packed.size() / shareds.size(),
+                                                   scores_out.data()),
+                    "score_data_grid");
     }
 
     // NEW: batched add_value.  values[n] join groups assign[n] (packed ids, negative = skip): one segmented

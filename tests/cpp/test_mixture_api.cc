@@ -101,6 +101,9 @@ static void run_script(std::shared_ptr<Context> ctx, std::istream & in, const ty
                 }
             }
             std::printf("batch_matches_per_value %d\n", same ? 1 : 0);
+        } else if (op == "scoredata") {  // Mixture::score_data under the script's Shared
+            std::vector<float> one(1, mixture.score_data(shared, rng));
+            print_vec("score_data", one);
         } else if (op == "addbatch") {  // addbatch <n> then n values, then n packed group ids (non-empty groups)
             size_t n;
             ls >> n;

@@ -64,6 +64,23 @@ class Replay:
             self.counts.pop()
             self.groups.pop()
 
+    def score_data(self):
+        """oracle MixtureDataScorer::score_data of the current groups under the script's Shared:
+        (fp32 group-order sum, sum |term|, the same terms summed in double)"""
+        m, G = self.model, len(self.groups)
+        sizes = np.asarray(self.counts, np.int32)
+        if m == "nich":
+            st = np.array(self.groups, dtype=np.float64)
+            w = dict(model=m, sizes=sizes, shared=np.array([0, 1, 1, 1], np.float32), count=st[:, 0].astype(np.int32),
+                     mean=st[:, 1].astype(np.float32), ctv=st[:, 2].astype(np.float32))
+        elif m == "bb":
+            st = np.array(self.groups, dtype=np.int32)
+            w = dict(model=m, sizes=sizes, shared=np.array([0.5, 2.0], np.float32), heads=st[:, 0].copy(), tails=st[:, 1].copy())
+        else:
+            w = dict(model=m, sizes=sizes, alphas=np.full(16, 0.5, np.float32),
+                     counts=np.array(self.groups, dtype=np.int32).reshape(G, 16))
+        return self.o.score_data(w)
+
     def scores(self, values):
         import cases
         from oracle.pyoracle import BB, DD, GP, NICH
@@ -167,6 +184,9 @@ def test_cpp_mixture_choreography(tmp_path, oracle):
         for g, v in zip(gids, vals):
             rp.add(g, v)
         score()
+        if model != "gp":  # the mirror's GammaPoisson::Group carries no log_prod
+            lines.append("scoredata")
+            expected.append((model, "scoredata", None, (None, rp.score_data())))
         lines.append("end")
         replays[model] = rp
     script = tmp_path / "script.txt"
@@ -188,6 +208,12 @@ def test_cpp_mixture_choreography(tmp_path, oracle):
             cur = row[1]
             row = next(it)
         assert cur == model
+        if kind == "scoredata":
+            assert row[0] == "score_data"
+            want32, scale, want64 = want
+            # nich statistics after the batched add differ from the sequential ones by ~1e-6 relative
+            assert abs(float(row[1]) - want64) <= (2e-5 if model == "nich" else 2e-7) * scale + 1e-5, (model, row, want)
+            continue
         if kind == "score":
             assert row[0] == "prior"
             np.testing.assert_allclose(np.array(row[1:], np.float32), prior, atol=2e-6)
