@@ -259,31 +259,15 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     const int nslots = (nchunks + chunks_per_slot - 1) / chunks_per_slot;
     // the selected slot is re-scored in-thread through the main loop body when caches are resident
     const int extra = (kSample && multi && resident) ? chunks_per_slot : 0;
-    // Row tiles are strided over the blocks (neighbouring blocks stream neighbouring rows: DRAM / TLB
-    // locality for the many column streams of a cross-cat kind).  With resident caches the last, partial
-    // round is split at warp granularity so that every SM runs out of work together (measured A/B on one
-    // box: c2 0.7537 -> 0.7490 ms).  The streaming mode keeps whole tiles (its block-wide barriers make
-    // idle warps cost as much as busy ones).
+    // Row tiles are strided over the blocks: neighbouring blocks stream neighbouring rows (DRAM / TLB
+    // locality for the many column streams of a cross-cat kind).  Splitting the last, partial round at
+    // warp granularity was measured and dropped: same-box A/B at c2 0.7315 ms plain vs 0.7380 ms balanced
+    // (blocks that finish early free MUFU issue slots for their neighbours on the SM), and the extra loop
+    // state cost the register-capped cross-cat kernel 8%.
     const size_t ntiles = (a.N + kThreads - 1) / kThreads;
-    const size_t full_rounds = resident ? ntiles / gridDim.x : (ntiles + gridDim.x - 1) / gridDim.x;
-    const size_t tail_begin = full_rounds * gridDim.x * kThreads;  // first row of the balanced last round
-    size_t tail_rows_per_block = 0;
-    if (resident && tail_begin < a.N)
-        tail_rows_per_block = (((a.N - tail_begin + 31) / 32 + gridDim.x - 1) / gridDim.x) * 32;  // <= kThreads
-
-    for (size_t round = 0; round <= full_rounds; ++round) {
-        size_t tile_base, row_end;
-        if (round < full_rounds) {
-            tile_base = (round * gridDim.x + blockIdx.x) * kThreads;
-            row_end = a.N;
-        } else {
-            if (tail_rows_per_block == 0) break;
-            tile_base = tail_begin + blockIdx.x * tail_rows_per_block;
-            row_end = tile_base + tail_rows_per_block < a.N ? tile_base + tail_rows_per_block : a.N;
-        }
-        if (tile_base >= row_end) break;
-        // warps past the end of the range have nothing to do (no block-wide barrier below when resident)
-        if (resident && tile_base + static_cast<size_t>(warp) * 32 >= row_end) continue;
+    for (size_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+        const size_t tile_base = tile_id * kThreads;
+        const size_t row_end = a.N;
         size_t row = tile_base + tid;
         const bool valid = row < row_end;
         if (!valid) row = row_end - 1;  // clamp: compute on a real row, discard the result
