@@ -11,9 +11,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdist_b200.so")
 
-DD, DPD, BB, GP, NICH, NIW = 0, 1, 2, 3, 4, 5
-MODEL_NAMES = {DD: "dd", DPD: "dpd", BB: "bb", GP: "gp", NICH: "nich", NIW: "niw"}
-COLUMN_DTYPE = {DD: np.int32, DPD: np.uint32, BB: np.uint8, GP: np.uint32, NICH: np.float32, NIW: np.float32}
+DD, DPD, BB, GP, NICH, NIW, BNB = 0, 1, 2, 3, 4, 5, 6
+MODEL_NAMES = {DD: "dd", DPD: "dpd", BB: "bb", GP: "gp", NICH: "nich", NIW: "niw", BNB: "bnb"}
+COLUMN_DTYPE = {DD: np.int32, DPD: np.uint32, BB: np.uint8, GP: np.uint32, NICH: np.float32, NIW: np.float32, BNB: np.uint32}
 
 c_f, c_i, c_sz, c_p = ctypes.c_float, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p
 
@@ -31,6 +31,7 @@ SIGNATURES = {
     "dist_b200_nich_update_all": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, c_p]),
     "dist_b200_gp_update_all": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p]),
     "dist_b200_bb_update_all": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p]),
+    "dist_b200_bnb_update_all": (c_i, [c_p, c_p, ctypes.c_uint32, c_i, c_p, c_p, c_p]),
     "dist_b200_dd_update_all": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p]),
     "dist_b200_dpd_update_all": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_i, c_p, c_p]),
     "dist_b200_niw_update_all": (c_i, [c_p, c_i, c_p, c_f, c_p, c_f, c_i, c_p, c_p, c_p, c_p]),
@@ -48,6 +49,8 @@ SIGNATURES = {
     "dist_b200_feature_download_stats": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
     "dist_b200_count_assignments": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_i, c_p]),
     "dist_b200_prior_pitman_yor_dev": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
+    "dist_b200_prior_low_entropy_host": (c_i, [c_p, c_i, c_i, c_p, c_p]),
+    "dist_b200_prior_low_entropy_dev": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p]),
     "dist_b200_feature_download_caches": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
     "dist_b200_prior_pitman_yor": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
     "dist_b200_prior_pitman_yor_host": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p]),
@@ -176,6 +179,17 @@ class Context:
     def count_assignments(self, assign_dev, n_rows, G, counts_dev, accumulate=False, stream=None):
         self.check(self.L.dist_b200_count_assignments(self.h, _dev_ptr(assign_dev), n_rows, G, _dev_ptr(counts_dev),
                                                       1 if accumulate else 0, stream), "count_assignments")
+
+    def prior_low_entropy_host(self, dataset_size, sizes):
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        out = np.empty(sizes.size, dtype=np.float32)
+        self.check(self.L.dist_b200_prior_low_entropy_host(self.h, int(dataset_size), sizes.size, _np_ptr(sizes), _np_ptr(out)),
+                   "prior_low_entropy")
+        return out
+
+    def prior_low_entropy_dev(self, dataset_size, G, sizes_dev, prior_dev, stream=None):
+        self.check(self.L.dist_b200_prior_low_entropy_dev(self.h, int(dataset_size), G, _dev_ptr(sizes_dev), _dev_ptr(prior_dev), stream),
+                   "prior_low_entropy_dev")
 
     def prior_pitman_yor_dev(self, alpha, d, G, sizes_dev, prior_dev, stream=None):
         self.check(self.L.dist_b200_prior_pitman_yor_dev(self.h, alpha, d, G, _dev_ptr(sizes_dev), _dev_ptr(prior_dev), stream),
@@ -307,6 +321,10 @@ class Feature:
             c.check(L.dist_b200_gp_update_all(self.h, _np_ptr(sh), cnt.size, _np_ptr(cnt), _np_ptr(sm), stream), "gp_update_all")
             if w.get("log_prod") is not None and cnt.size:
                 self.set_log_prod(w["log_prod"], stream)
+        elif m == BNB:
+            sh, cnt, sm = f32(w["shared"][:2]), u32(w["count"]), u32(w["sum"])
+            c.check(L.dist_b200_bnb_update_all(self.h, _np_ptr(sh), int(w["shared"][2]), cnt.size, _np_ptr(cnt), _np_ptr(sm), stream),
+                    "bnb_update_all")
         elif m == BB:
             sh, h, t = f32(w["shared"]), i32(w["heads"]), i32(w["tails"])
             c.check(L.dist_b200_bb_update_all(self.h, _np_ptr(sh), h.size, _np_ptr(h), _np_ptr(t), stream), "bb_update_all")

@@ -72,7 +72,7 @@ size_t group_floats(const dist_b200_feature *f) {
 int stat_arrays(const dist_b200_feature *f) {
     switch (f->model) {
         case DIST_B200_NICH: return 3;
-        case DIST_B200_GP: case DIST_B200_BB: return 2;
+        case DIST_B200_GP: case DIST_B200_BB: case DIST_B200_BNB: return 2;
         case DIST_B200_DD: return 1;
         default: return 0;
     }
@@ -269,7 +269,7 @@ int dist_b200_sm_count(const dist_b200_ctx *ctx) { return ctx ? ctx->sm_count : 
 int dist_b200_feature_create(dist_b200_ctx *ctx, int model, dist_b200_feature **out) {
     if (!ctx || !out) return DIST_B200_ERR_INVALID;
     *out = nullptr;
-    if (model < DIST_B200_DD || model > DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_INVALID, "unknown model");
+    if (model < DIST_B200_DD || model > DIST_B200_BNB) return fail(ctx, DIST_B200_ERR_INVALID, "unknown model");
     dist_b200_feature *f = new (std::nothrow) dist_b200_feature();
     if (!f) return fail(ctx, DIST_B200_ERR_CUDA, "out of host memory");
     f->ctx = ctx;
@@ -340,6 +340,25 @@ int dist_b200_gp_update_all(dist_b200_feature *f, const float shared[2], int G, 
     f->log_prod_valid = false;
     if ((rc = mirror_stats(f, 0, c, 0, G, as_stream(stream))) || (rc = mirror_stats(f, 1, sm, 0, G, as_stream(stream)))) return rc;
     return mark_ready(f, launch_gp_prep(ctx, f->shared, 0, G, c, sm, static_cast<float4 *>(f->params), as_stream(stream)), as_stream(stream));
+}
+
+int dist_b200_bnb_update_all(dist_b200_feature *f, const float shared[2], uint32_t r, int G, const uint32_t *count,
+                             const uint32_t *sum, void *stream) {
+    if (!check_feature(f, DIST_B200_BNB) || !shared || G < 0 || (G && (!count || !sum))) return DIST_B200_ERR_INVALID;
+    dist_b200_ctx *ctx = f->ctx;
+    f->shared[0] = shared[0];
+    f->shared[1] = shared[1];
+    f->shared[2] = static_cast<float>(r);  // the reference converts r to float wherever it enters (bnb.hpp:59,208)
+    int rc = ensure_params(f, G, false);
+    if (rc) return rc;
+    if ((rc = ensure_scratch(ctx, 2 * round_up(sizeof(float) * G, 256) + 256))) return rc;
+    Upload up{ctx, as_stream(stream)};
+    const uint32_t *c = up.put(count, G);
+    const uint32_t *sm = up.put(sum, G);
+    if (up.err) return up.err;
+    f->G = G;
+    if ((rc = mirror_stats(f, 0, c, 0, G, as_stream(stream))) || (rc = mirror_stats(f, 1, sm, 0, G, as_stream(stream)))) return rc;
+    return mark_ready(f, launch_bnb_prep(ctx, f->shared, 0, G, c, sm, static_cast<float4 *>(f->params), as_stream(stream)), as_stream(stream));
 }
 
 int dist_b200_bb_update_all(dist_b200_feature *f, const float shared[2], int G, const int32_t *heads,
@@ -535,6 +554,14 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             if ((rc = mirror_stats(f, 0, c, groupid, 1, s)) || (rc = mirror_stats(f, 1, sm, groupid, 1, s))) return rc;
             return mark_ready(f, launch_gp_prep(ctx, f->shared, groupid, 1, c, sm, static_cast<float4 *>(f->params), s), s);
         }
+        case DIST_B200_BNB: {
+            const uint32_t *p = static_cast<const uint32_t *>(stats);
+            const uint32_t *c = up.put(p, 1);
+            const uint32_t *sm = up.put(p + 1, 1);
+            if (up.err) return up.err;
+            if ((rc = mirror_stats(f, 0, c, groupid, 1, s)) || (rc = mirror_stats(f, 1, sm, groupid, 1, s))) return rc;
+            return mark_ready(f, launch_bnb_prep(ctx, f->shared, groupid, 1, c, sm, static_cast<float4 *>(f->params), s), s);
+        }
         case DIST_B200_BB: {
             const int32_t *p = static_cast<const int32_t *>(stats);
             const int32_t *h = up.put(p, 1);
@@ -612,7 +639,7 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
         if (!f || f->ctx != ctx || !columns_dev[i]) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows: bad feature / column");
         if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: niw statistics stay on the host");
         if (f->G < 1 || !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: call update_all first");
-        if (f->model == DIST_B200_NICH || f->model == DIST_B200_GP || f->model == DIST_B200_BB)
+        if (f->model == DIST_B200_NICH || f->model == DIST_B200_GP || f->model == DIST_B200_BB || f->model == DIST_B200_BNB)
             acc_need = std::max(acc_need, add_rows_acc_bytes(f->G) * std::min(n_features, kAddBatch));
     }
     if (acc_need > ctx->add_acc_bytes) {
@@ -649,7 +676,8 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
         switch (f->model) {
             case DIST_B200_NICH:
             case DIST_B200_GP:
-            case DIST_B200_BB: {
+            case DIST_B200_BB:
+            case DIST_B200_BNB: {
                 if (b.n == kAddBatch || (b.n && b.G != G))
                     if ((rc = flush())) return rc;
                 b.G = G;
@@ -751,7 +779,7 @@ int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, con
 static size_t shared_stride(const dist_b200_feature *f) {
     switch (f->model) {
         case DIST_B200_NICH: return 4;
-        case DIST_B200_GP: case DIST_B200_BB: return 2;
+        case DIST_B200_GP: case DIST_B200_BB: case DIST_B200_BNB: return 2;
         case DIST_B200_DD: return static_cast<size_t>(f->dim);
         case DIST_B200_DPD: return 1;
         default: return 0;
@@ -890,6 +918,7 @@ int dist_b200_feature_download_caches(const dist_b200_feature *f, float *out_hos
     switch (f->model) {
         case DIST_B200_NICH: rows = 4; break;
         case DIST_B200_GP: rows = 3; break;
+        case DIST_B200_BNB: rows = 3; break;
         case DIST_B200_BB: rows = 2; break;
         case DIST_B200_DD: rows = f->dim; break;
         case DIST_B200_DPD: rows = f->dim + 1; break;
@@ -919,6 +948,29 @@ int dist_b200_prior_pitman_yor(dist_b200_ctx *ctx, float alpha, float d, int G, 
     int rc2 = launch_prior_prep(ctx, alpha, d, G, sz, prior_dev, as_stream(stream));
     if (rc2) return rc2;
     DISTB200_CUDA(ctx, cudaStreamSynchronize(as_stream(stream)));  // scratch (group sizes) is free again
+    return DIST_B200_OK;
+}
+
+// LowEntropy clustering prior (clustering.hpp:245-331 through MixtureDriver::score_value): overwrite semantics
+int dist_b200_prior_low_entropy_dev(dist_b200_ctx *ctx, int dataset_size, int G, const int32_t *sizes_dev,
+                                    float *prior_dev, void *stream) {
+    if (!ctx || G < 1 || !sizes_dev || !prior_dev || dataset_size < 1) return DIST_B200_ERR_INVALID;
+    return launch_low_entropy_prep(ctx, dataset_size, G, sizes_dev, prior_dev, as_stream(stream));
+}
+
+int dist_b200_prior_low_entropy_host(dist_b200_ctx *ctx, int dataset_size, int G, const int32_t *group_sizes,
+                                     float *prior_host) {
+    if (!ctx || G < 1 || !group_sizes || !prior_host || dataset_size < 1) return DIST_B200_ERR_INVALID;
+    int rc = ensure_scratch(ctx, round_up(sizeof(int32_t) * G, 256) + sizeof(float) * G + 256);
+    if (rc) return rc;
+    cudaStream_t s = ctx->own_stream;
+    Upload up{ctx, s};
+    const int32_t *sz = up.put(group_sizes, G);
+    if (up.err) return up.err;
+    float *out = reinterpret_cast<float *>(static_cast<char *>(ctx->scratch_dev) + up.off);
+    if ((rc = launch_low_entropy_prep(ctx, dataset_size, G, sz, out, s))) return rc;
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(prior_host, out, sizeof(float) * G, cudaMemcpyDeviceToHost, s));
+    DISTB200_CUDA(ctx, cudaStreamSynchronize(s));
     return DIST_B200_OK;
 }
 

@@ -24,7 +24,7 @@ struct FeatDesc {
 };
 
 // internal kind: GammaPoisson scored through a per-(group, value) table for small counts
-constexpr int kKindGpTable = 6;
+constexpr int kKindGpTable = 16;  // (6 is DIST_B200_BNB)
 constexpr int kGpTableX = 32;
 
 // destinations of a peer-push launch (see RowsArgs)
@@ -157,6 +157,8 @@ int launch_nich_prep(dist_b200_ctx *ctx, const float shared[4], int G, int g0, i
                      const float *mean_dev, const float *ctv_dev, float4 *params, float *aux, cudaStream_t s);
 int launch_gp_prep(dist_b200_ctx *ctx, const float shared[2], int g0, int n, const uint32_t *count_dev,
                    const uint32_t *sum_dev, float4 *params, cudaStream_t s);
+int launch_bnb_prep(dist_b200_ctx *ctx, const float shared[3], int g0, int n, const uint32_t *count_dev,
+                    const uint32_t *sum_dev, float4 *params, cudaStream_t s);
 int launch_bb_prep(dist_b200_ctx *ctx, const float shared[2], int g0, int n, const int32_t *heads_dev,
                    const int32_t *tails_dev, float4 *params, cudaStream_t s);
 int launch_dd_prep(dist_b200_ctx *ctx, int dim, const float *alphas_dev, float alpha_sum, int g0, int n,
@@ -165,6 +167,8 @@ int launch_dpd_prep(dist_b200_ctx *ctx, float alpha, float beta0, int V, const f
                     const int32_t *counts_dev, float *table, cudaStream_t s);
 int launch_prior_prep(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *sizes_dev, float *prior,
                       cudaStream_t s);
+int launch_low_entropy_prep(dist_b200_ctx *ctx, int dataset_size, int G, const int32_t *sizes_dev, float *prior,
+                            cudaStream_t s);
 int launch_numerics_probe(dist_b200_ctx *ctx, int fn, size_t n, const float *in, float *out, cudaStream_t s);
 // score_data_grid: log marginal likelihood of all groups under n_grid packed Shareds (acc: n_grid doubles of scratch)
 int launch_score_data(dist_b200_ctx *ctx, const dist_b200_feature *f, const uint32_t *st0, const uint32_t *st1,

@@ -57,6 +57,24 @@ __global__ void gp_prep_kernel(float alpha, float inv_beta, int g0, int n, const
     params[g0 + i] = gp_prep_one(alpha, inv_beta, count[i], sum[i], t);
 }
 
+// BetaNegativeBinomial: plus_group (bnb.hpp:57-63) + Scorer::init (bnb.hpp:200-211); {post_beta, alpha, score, 0}
+__device__ __forceinline__ float4 bnb_prep_one(float alpha, float beta, float r, uint32_t count, uint32_t sum,
+                                               const NumericTables &t) {
+    const float post_alpha = alpha + r * static_cast<float>(count);
+    const float post_beta = beta + static_cast<float>(sum);
+    const float a = post_alpha + r;
+    const float score = fast_lgamma_exact(post_alpha + post_beta, t.lgamma5) - fast_lgamma_exact(post_alpha, t.lgamma5) -
+                        fast_lgamma_exact(post_beta, t.lgamma5) + fast_lgamma_exact(a, t.lgamma5);
+    return make_float4(post_beta, a, score, 0.f);
+}
+
+__global__ void bnb_prep_kernel(float alpha, float beta, float r, int g0, int n, const uint32_t *__restrict__ count,
+                                const uint32_t *__restrict__ sum, float4 *__restrict__ params, NumericTables t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    params[g0 + i] = bnb_prep_one(alpha, beta, r, count[i], sum[i], t);
+}
+
 // BetaBernoulli: update_all (bb.hpp:276-292); {heads_score, tails_score, 0, 0}
 __device__ __forceinline__ float4 bb_prep_one(float alpha, float beta, int32_t heads, int32_t tails, const NumericTables &t) {
     const float h = alpha + static_cast<float>(heads);
@@ -120,12 +138,13 @@ __global__ void merge_prep_batch_kernel(const AddBatch b, NumericTables t) {
             }
         }
         nich_prep_one(d.shared[0], d.shared[1], d.shared[2], d.shared[3], count[g], mean[g], ctv[g], d.params + g, d.aux + g, t);
-    } else if (d.model == DIST_B200_GP) {
+    } else if (d.model == DIST_B200_GP || d.model == DIST_B200_BNB) {
         const uint32_t c = d.st0[g] + static_cast<uint32_t>(b.sign * cnt_a[g]);
         const uint32_t sm = d.st1[g] + static_cast<uint32_t>(b.sign) * static_cast<uint32_t>(cnt_b[g]);
         d.st0[g] = c;
         d.st1[g] = sm;
-        d.params[g] = gp_prep_one(d.shared[0], d.shared[1], c, sm, t);
+        d.params[g] = d.model == DIST_B200_GP ? gp_prep_one(d.shared[0], d.shared[1], c, sm, t)
+                                              : bnb_prep_one(d.shared[0], d.shared[1], d.shared[2], c, sm, t);
     } else {  // bb
         int32_t *heads = reinterpret_cast<int32_t *>(d.st0), *tails = reinterpret_cast<int32_t *>(d.st1);
         const int32_t h = heads[g] + b.sign * cnt_a[g], tl = tails[g] + b.sign * cnt_b[g];
@@ -229,6 +248,52 @@ __global__ void prior_prep_kernel(float alpha, float d, int G, const int32_t *__
     }
 }
 
+// LowEntropy clustering prior: LowEntropy::score_add_value (clustering.hpp:265-293, :318-327) for every
+// group, as the uncached MixtureDriver::score_value evaluates it (mixture.hpp:123-141); overwrites prior[G].
+__global__ void low_entropy_prep_kernel(int dataset_size, int G, const int32_t *__restrict__ sizes,
+                                        float *__restrict__ prior, NumericTables t) {
+    __shared__ int s_total, s_empty;
+    if (threadIdx.x == 0) {
+        s_total = 0;
+        s_empty = 0;
+    }
+    __syncthreads();
+    int total = 0, empty = 0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        total += sizes[g];
+        empty += (sizes[g] == 0);
+    }
+    for (int o = 16; o; o >>= 1) {
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+        empty += __shfl_xor_sync(0xffffffffu, empty, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_total, total);
+        atomicAdd(&s_empty, empty);
+    }
+    __syncthreads();
+    const int sample_size = s_total;
+    float empty_score = -fast_log_table(static_cast<float>(s_empty), t.log2_table);
+    if (sample_size + 1 < dataset_size) {
+        const float n = static_cast<float>(sample_size + 1);
+        const float exponent = 0.45f - 0.1f / n - 0.1f / dataset_size;
+        const float scale = dataset_size / n;
+        empty_score += fast_log_table(scale, t.log2_table) * exponent;
+    }
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+        const int group_size = sizes[g];
+        float score;
+        if (group_size == 0) {
+            score = empty_score;
+        } else {
+            const float bigger = 1.f + group_size;
+            if (group_size > 10000) score = 1.f + fast_log_table(bigger, t.log2_table);
+            else score = fast_log_table(bigger / group_size, t.log2_table) * group_size + fast_log_table(bigger, t.log2_table);
+        }
+        prior[g] = score;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // score_data_grid: MixtureSlave::score_data_grid (mixture.hpp:427-438) -- the log
 // marginal likelihood of ALL groups under each of n_grid hyper-parameter settings, from the device-resident
@@ -243,6 +308,7 @@ struct ScoreDataArgs {
     const uint32_t *st0, *st1, *st2;   // statistics arrays (see dist_b200_feature::stats)
     const float *betas;           // dpd
     const float *log_prod;        // gp
+    float r;                      // bnb
     double *acc;                  // [n_grid], zeroed
 };
 
@@ -293,6 +359,18 @@ __global__ void __launch_bounds__(256) score_data_kernel(const ScoreDataArgs a, 
             part += static_cast<double>(fast_lgamma_exact(post_alpha, t.lgamma5) - alpha_part);
             part += static_cast<double>(beta_part - post_alpha * fast_log_table(post_inv_beta, t.log2_table));
             part += static_cast<double>(-a.log_prod[g]);
+        }
+    } else if (a.model == DIST_B200_BNB) {  // bnb.hpp:221-243; packed (alpha, beta), r = a.r
+        const float alpha = sh[0], beta = sh[1];
+        const float shared_part = fast_lgamma_exact(alpha + beta, t.lgamma5) - fast_lgamma_exact(alpha, t.lgamma5) -
+                                  fast_lgamma_exact(beta, t.lgamma5);
+        for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+            if (!a.st0[g]) continue;
+            const float post_alpha = alpha + a.r * static_cast<float>(a.st0[g]);
+            const float post_beta = beta + static_cast<float>(a.st1[g]);
+            part += static_cast<double>(fast_lgamma_exact(post_alpha, t.lgamma5) + fast_lgamma_exact(post_beta, t.lgamma5) -
+                                        fast_lgamma_exact(post_alpha + post_beta, t.lgamma5));
+            part += static_cast<double>(shared_part);
         }
     } else if (a.model == DIST_B200_BB) {  // bb.hpp:207-229
         const float alpha0 = sh[0], beta0 = sh[1];
@@ -387,7 +465,7 @@ __global__ void unpack_float4_kernel(int model, int G, const float4 *__restrict_
         out[1 * G + g] = aux[g];
         out[2 * G + g] = p.y;
         out[3 * G + g] = p.x;
-    } else if (model == DIST_B200_GP) {  // score_, post_alpha_, score_coeff_
+    } else if (model == DIST_B200_GP || model == DIST_B200_BNB) {  // gp: score_, post_alpha_, score_coeff_; bnb: score_, post_beta_, alpha_
         out[0 * G + g] = p.z;
         out[1 * G + g] = p.x;
         out[2 * G + g] = p.y;
@@ -427,6 +505,14 @@ int launch_gp_prep(dist_b200_ctx *ctx, const float sh[2], int g0, int n, const u
                    const uint32_t *sum, float4 *params, cudaStream_t s) {
     if (n <= 0) return DIST_B200_OK;
     gp_prep_kernel<<<blocks_for(n, 128), 128, 0, s>>>(sh[0], sh[1], g0, n, count, sum, params, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+int launch_bnb_prep(dist_b200_ctx *ctx, const float sh[3], int g0, int n, const uint32_t *count,
+                    const uint32_t *sum, float4 *params, cudaStream_t s) {
+    if (n <= 0) return DIST_B200_OK;
+    bnb_prep_kernel<<<blocks_for(n, 128), 128, 0, s>>>(sh[0], sh[1], sh[2], g0, n, count, sum, params, ctx->tables);
     LAUNCH_CHECK(ctx);
     return DIST_B200_OK;
 }
@@ -493,6 +579,7 @@ int launch_score_data(dist_b200_ctx *ctx, const dist_b200_feature *f, const uint
     a.st2 = st2;
     a.betas = betas;
     a.log_prod = log_prod;
+    a.r = f->shared[2];
     a.acc = acc;
     cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * n_grid, s);
     if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, cudaGetErrorString(e));
@@ -516,6 +603,13 @@ int launch_score_data(dist_b200_ctx *ctx, const dist_b200_feature *f, const uint
     return DIST_B200_OK;
 }
 
+int launch_low_entropy_prep(dist_b200_ctx *ctx, int dataset_size, int G, const int32_t *sizes, float *prior, cudaStream_t s) {
+    const int blocks = G <= 256 ? 1 : (G + 255) / 256 < 64 ? (G + 255) / 256 : 64;
+    low_entropy_prep_kernel<<<blocks, 256, 0, s>>>(dataset_size, G, sizes, prior, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
 int launch_numerics_probe(dist_b200_ctx *ctx, int fn, size_t n, const float *in, float *out, cudaStream_t s) {
     if (n == 0) return DIST_B200_OK;
     numerics_probe_kernel<<<blocks_for(n, 256), 256, 0, s>>>(fn, n, in, out, ctx->tables);
@@ -530,6 +624,7 @@ int launch_unpack_caches(dist_b200_ctx *ctx, const dist_b200_feature *f, float *
         case DIST_B200_NICH:
         case DIST_B200_GP:
         case DIST_B200_BB:
+        case DIST_B200_BNB:
             unpack_float4_kernel<<<blocks_for(G, 128), 128, 0, s>>>(f->model, G,
                                                                     static_cast<const float4 *>(f->params), f->aux, out);
             break;

@@ -62,6 +62,12 @@ __device__ __forceinline__ float gp_term(const float4 q, uint32_t xb, const floa
     return fmaf(q.y, xf, (q.z + lg) - lf);
 }
 
+// BetaNegativeBinomial term (bnb.hpp:308-319): q = {post_beta, alpha, score, -}
+__device__ __forceinline__ float bnb_term(const float4 q, uint32_t xb, const float *__restrict__ coeff) {
+    const float beta = q.x + static_cast<float>(xb);
+    return (q.z + fast_lgamma_cell(beta, coeff)) - fast_lgamma_cell(beta + q.y, coeff);
+}
+
 // raw 32-bit value of row `row` of a feature column
 __device__ __forceinline__ uint32_t load_value(int kind, const void *column, size_t row) {
     if (kind == DIST_B200_BB) return static_cast<const uint8_t *>(column)[row];
@@ -80,6 +86,8 @@ __device__ __forceinline__ float cell_score(int kind, uint32_t xb, const float *
         }
         case DIST_B200_GP:
             return gp_term(*reinterpret_cast<const float4 *>(p), xb, coeff, logfact);
+        case DIST_B200_BNB:
+            return bnb_term(*reinterpret_cast<const float4 *>(p), xb, coeff);
         case DIST_B200_BB: {
             const float2 q = *reinterpret_cast<const float2 *>(p);
             return xb ? q.x : q.y;
@@ -142,6 +150,15 @@ __device__ __forceinline__ void accumulate_feature(int kind, uint32_t xb, const 
                 acc[j] = kAssign ? v : acc[j] + v;
             }
         } break;
+        case DIST_B200_BNB: {
+            // score + fast_lgamma(post_beta + v) - fast_lgamma(post_beta + v + alpha)   (bnb.hpp:308-319)
+            const float4 *p4 = reinterpret_cast<const float4 *>(pb);
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+                const float v = bnb_term(p4[j], xb, coeff);
+                acc[j] = kAssign ? v : acc[j] + v;
+            }
+        } break;
         case DIST_B200_BB: {
             // value ? heads[g] : tails[g]   (bb.hpp:303-313)
             const float4 *p4 = reinterpret_cast<const float4 *>(pb);
@@ -192,7 +209,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     constexpr bool kSingle = KIND >= 0;  // one feature of a known model; caches resident
     // prior folded into the resident caches (first feature ASSIGNS): not for gp, whose score[g] cancels
     // against lgamma(post_alpha + v) -- adding the prior before that cancellation would cost ~1e-5
-    constexpr bool kFold = kSingle && KIND != DIST_B200_GP;
+    constexpr bool kFold = kSingle && KIND != DIST_B200_GP && KIND != DIST_B200_BNB;
     const int G = a.G;
     const int nchunks = (G + CHUNK - 1) / CHUNK;
     const int Gpad = nchunks * CHUNK;
@@ -628,6 +645,7 @@ int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N
         switch (feats.f[0].kind) {
             case DIST_B200_NICH: rc = launch_tiers<DIST_B200_NICH>(ctx, feats, a, s); break;
             case DIST_B200_GP: rc = launch_tiers<DIST_B200_GP>(ctx, feats, a, s); break;
+            case DIST_B200_BNB: rc = launch_tiers<DIST_B200_BNB>(ctx, feats, a, s); break;
             case DIST_B200_BB: rc = launch_tiers<DIST_B200_BB>(ctx, feats, a, s); break;
             case DIST_B200_DD: rc = launch_tiers<DIST_B200_DD>(ctx, feats, a, s); break;
         }

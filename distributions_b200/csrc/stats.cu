@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kAddThreads) add_rows_pooled_kernel(const AddB
                 atomicAdd(&axx[g], xx);
             }
         });
-    } else if (model == DIST_B200_GP) {
+    } else if (model == DIST_B200_GP || model == DIST_B200_BNB) {
         for_each_row<kVec>(b.assign, static_cast<const uint32_t *>(d.column), b.N, kAddThreads, [&](int g, uint32_t x) {
             if (g < 0 || g >= G) return;
             atomicAdd(&ca[g], 1);

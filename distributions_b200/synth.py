@@ -53,6 +53,17 @@ def gp(seed, G, N, lam=5.0):
                 values=rng.poisson(lam, N).astype(np.uint32), u=rng.random(N, dtype=np.float32))
 
 
+def bnb(seed, G, N, r=3):
+    """BetaNegativeBinomial: alpha=1, beta=1 (EXAMPLE(), bnb.hpp:79-85) with r failures; values ~ NegBin(r, p_g)."""
+    rng = np.random.default_rng(seed)
+    sizes = _sizes(rng, G)
+    ps = rng.beta(2.0, 2.0, G) * 0.8 + 0.1
+    count = sizes.astype(np.uint32)
+    sum_ = np.array([rng.negative_binomial(r, ps[g], sizes[g]).sum() if sizes[g] else 0 for g in range(G)], np.uint32)
+    return dict(model="bnb", shared=np.array([1.0, 1.0, r], np.float32), sizes=sizes, count=count, sum=sum_,
+                values=rng.negative_binomial(r, 0.4, N).astype(np.uint32), u=rng.random(N, dtype=np.float32))
+
+
 def bb(seed, G, N, p=0.3):
     """BetaBernoulli: EXAMPLE() alpha=0.5, beta=2; values ~ Bernoulli(0.3)."""
     rng = np.random.default_rng(seed)

@@ -48,7 +48,8 @@ typedef enum {
     DIST_B200_BB = 2,   /* BetaBernoulli                value: uint8 (0 / non-0) */
     DIST_B200_GP = 3,   /* GammaPoisson                 value: uint32  */
     DIST_B200_NICH = 4, /* NormalInverseChiSq           value: float   */
-    DIST_B200_NIW = 5   /* NormalInverseWishart<d>      value: float[d], rows contiguous */
+    DIST_B200_NIW = 5,  /* NormalInverseWishart<d>      value: float[d], rows contiguous */
+    DIST_B200_BNB = 6   /* BetaNegativeBinomial         value: uint32  */
 } dist_b200_model;
 
 typedef struct dist_b200_ctx dist_b200_ctx;
@@ -81,6 +82,11 @@ int dist_b200_nich_update_all(dist_b200_feature *f, const float shared[4], int G
  * Group = {count, sum, log_prod} (gp.hpp:84-87; log_prod does not enter score_value). */
 int dist_b200_gp_update_all(dist_b200_feature *f, const float shared[2], int G, const uint32_t *count,
                             const uint32_t *sum, void *stream);
+/* BetaNegativeBinomial (bnb.hpp:285-293 -> Scorer::init :200-211, plus_group :57-63).  shared = {alpha, beta},
+ * r failures; Group = {count, sum} (bnb.hpp:89-91).  Caches {score, post_beta, alpha + r * count + r}; a cell
+ * is score + fast_lgamma(post_beta + v) - fast_lgamma(post_beta + v + alpha) (bnb.hpp:308-319). */
+int dist_b200_bnb_update_all(dist_b200_feature *f, const float shared[2], uint32_t r, int G, const uint32_t *count,
+                             const uint32_t *sum, void *stream);
 /* BetaBernoulli (bb.hpp:276-292).  shared = {alpha, beta}; Group = {heads, tails} (bb.hpp:79-81). */
 int dist_b200_bb_update_all(dist_b200_feature *f, const float shared[2], int G, const int32_t *heads,
                             const int32_t *tails, void *stream);
@@ -185,6 +191,14 @@ int dist_b200_feature_download_caches(const dist_b200_feature *f, float *out_hos
 int dist_b200_prior_pitman_yor(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *group_sizes,
                                float *prior_dev, void *stream);
 
+/* LowEntropy clustering prior (Clustering<int>::LowEntropy, clustering.hpp:245-331): prior[g] =
+ * score_add_value(group_sizes[g], nonempty, sample_size, empty) as the uncached MixtureDriver::score_value
+ * evaluates it (mixture.hpp:123-141).  OVERWRITES prior[G], like the Pitman-Yor vector; feed it to the same
+ * `prior` argument of the score entries. */
+int dist_b200_prior_low_entropy_host(dist_b200_ctx *ctx, int dataset_size, int G, const int32_t *group_sizes,
+                                     float *prior_host);
+int dist_b200_prior_low_entropy_dev(dist_b200_ctx *ctx, int dataset_size, int G, const int32_t *sizes_dev,
+                                    float *prior_dev, void *stream);
 /* Same with a HOST result buffer: the per-value CachedMixture::score_value(model, scores) drop-in
  * (clustering.hpp:195-208; overwrites prior_host[0..G)). */
 int dist_b200_prior_pitman_yor_host(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *group_sizes,

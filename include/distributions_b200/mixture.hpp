@@ -165,6 +165,41 @@ struct GammaPoisson {
     }
 };
 
+struct BetaNegativeBinomial {
+    typedef uint32_t Value;
+    enum { model_id = DIST_B200_BNB };
+    struct Shared {
+        float alpha, beta;
+        uint32_t r;
+        static Shared EXAMPLE() { return Shared{1.f, 1.f, 1u}; }  // bnb.hpp:79-85
+    };
+    struct Group {
+        uint32_t count;
+        uint32_t sum;
+        void init(const Shared &, rng_t &) { count = 0; sum = 0; }
+        void add_value(const Shared &, const Value & value, rng_t &) { ++count; sum += value; }     // bnb.hpp:107-113
+        void remove_value(const Shared &, const Value & value, rng_t &) { --count; sum -= value; }  // bnb.hpp:124-130
+    };
+    static int update_all(dist_b200_feature * f, const Shared & s, const std::vector<Group> & groups) {
+        const size_t G = groups.size();
+        std::vector<uint32_t> count(G), sum(G);
+        for (size_t g = 0; g < G; ++g) { count[g] = groups[g].count; sum[g] = groups[g].sum; }
+        const float sh[2] = {s.alpha, s.beta};
+        return dist_b200_bnb_update_all(f, sh, s.r, static_cast<int>(G), count.data(), sum.data(), nullptr);
+    }
+    static void load_groups(const unsigned char * raw, const Shared &, std::vector<Group> & groups) {  // count | sum
+        const size_t G = groups.size();
+        const uint32_t * c = reinterpret_cast<const uint32_t *>(raw);
+        for (size_t g = 0; g < G; ++g) { groups[g].count = c[g]; groups[g].sum = c[G + g]; }
+    }
+    static size_t stats_bytes(const Shared &, size_t G) { return 8 * G; }
+    static void pack_shared(const Shared & s, std::vector<float> & out) { out.push_back(s.alpha); out.push_back(s.beta); }
+    static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
+        const uint32_t st[2] = {g.count, g.sum};
+        return dist_b200_feature_update_group(f, static_cast<int>(groupid), st, nullptr);
+    }
+};
+
 struct BetaBernoulli {
     typedef bool Value;
     enum { model_id = DIST_B200_BB };
@@ -431,6 +466,48 @@ struct PitmanYor {
         std::vector<int32_t> counts_;
         IdSet empty_groupids_;
         size_t sample_size_ = 0;
+    };
+};
+
+// ---------------------------------------------------------------------------------------------
+// Clustering<int>::LowEntropy and its Mixture (the uncached MixtureDriver, clustering.hpp:245-303)
+
+struct LowEntropy {
+    int32_t dataset_size;
+
+    class Mixture {
+      public:
+        explicit Mixture(std::shared_ptr<Context> ctx) : ctx_(std::move(ctx)) {}
+        std::vector<int32_t> & counts() { return counts_; }
+        const std::vector<int32_t> & counts() const { return counts_; }
+        void init(const LowEntropy &) {}
+        // mixture.hpp:77-93 / 95-122: same bookkeeping as the Pitman-Yor driver
+        bool add_value(const LowEntropy &, size_t groupid, int32_t count = 1) {
+            const bool add_group = (counts_[groupid] == 0);
+            counts_[groupid] += count;
+            if (add_group) counts_.push_back(0);
+            return add_group;
+        }
+        bool remove_value(const LowEntropy &, size_t groupid, int32_t count = 1) {
+            counts_[groupid] -= count;
+            const bool remove_group = (counts_[groupid] == 0);
+            if (remove_group) {
+                counts_[groupid] = counts_.back();
+                counts_.pop_back();
+            }
+            return remove_group;
+        }
+        // mixture.hpp:123-141: OVERWRITES scores with score_add_value of every group
+        void score_value(const LowEntropy & model, Floats scores) const {
+            if (scores.size() != counts_.size()) throw std::runtime_error("score_value: size mismatch");
+            ctx_->check(dist_b200_prior_low_entropy_host(ctx_->get(), model.dataset_size, static_cast<int>(counts_.size()),
+                                                         counts_.data(), scores.data()),
+                        "prior_low_entropy");
+        }
+
+      private:
+        std::shared_ptr<Context> ctx_;
+        std::vector<int32_t> counts_;
     };
 };
 

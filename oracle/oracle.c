@@ -197,6 +197,37 @@ void orc_py_prior(float alpha, float d, size_t G, const int32_t *sizes, float *o
     }
 }
 
+/* LowEntropy clustering prior: score_add_value (clustering.hpp:265-293, _approximate_postpred_correction
+ * :318-327) evaluated for every group by the uncached MixtureDriver::score_value (mixture.hpp:123-141):
+ * an OVERWRITE of the [G] vector, like the Pitman-Yor one. */
+static float le_postpred_correction(int32_t dataset_size, float sample_size) {
+    float exponent = 0.45f - 0.1f / sample_size - 0.1f / dataset_size;
+    float scale = dataset_size / sample_size;
+    return orc_fast_log(scale) * exponent;
+}
+
+float orc_low_entropy_score_add_value(int32_t dataset_size, int32_t group_size, int32_t sample_size,
+                                      int32_t empty_group_count) {
+    if (group_size == 0) {
+        float score = -orc_fast_log((float)empty_group_count);
+        if (sample_size + 1 < dataset_size) score += le_postpred_correction(dataset_size, (float)(sample_size + 1));
+        return score;
+    }
+    const int32_t very_large = 10000;
+    float bigger = 1.f + group_size;
+    if (group_size > very_large) return 1.f + orc_fast_log(bigger);
+    return orc_fast_log(bigger / group_size) * group_size + orc_fast_log(bigger);
+}
+
+void orc_low_entropy_prior(int32_t dataset_size, size_t G, const int32_t *sizes, float *out) {
+    int32_t empty = 0, total = 0;
+    for (size_t g = 0; g < G; ++g) {
+        total += sizes[g];
+        empty += (sizes[g] == 0);
+    }
+    for (size_t g = 0; g < G; ++g) out[g] = orc_low_entropy_score_add_value(dataset_size, sizes[g], total, empty);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* score_data: MixtureDataScorer::score_data of every model -- the log marginal  */
 /* likelihood of all groups under one Shared, fp32, accumulated in group order like the reference.    */
@@ -266,6 +297,22 @@ float orc_bb_score_data(const float sh[2], size_t G, const int32_t *heads, const
         float beta = sh[1] + tails[g];
         float group_part = orc_fast_lgamma(alpha) + orc_fast_lgamma(beta) - orc_fast_lgamma(alpha + beta);
         score = acc_term(score, shared_part + group_part, abs_sum);
+    }
+    return score;
+}
+
+/* bnb.hpp:221-243 */
+float orc_bnb_score_data(float alpha, float beta, uint32_t r, size_t G, const uint32_t *count, const uint32_t *sum,
+                         double *abs_sum) {
+    const float shared_part = orc_fast_lgamma(alpha + beta) - orc_fast_lgamma(alpha) - orc_fast_lgamma(beta);
+    float score = 0;
+    if (abs_sum) abs_sum[0] = abs_sum[1] = 0;
+    for (size_t g = 0; g < G; ++g) {
+        if (!count[g]) continue;
+        float post_alpha = alpha + (float)r * count[g];
+        float post_beta = beta + sum[g];
+        score = acc_term(score, orc_fast_lgamma(post_alpha) + orc_fast_lgamma(post_beta) - orc_fast_lgamma(post_alpha + post_beta), abs_sum);
+        score = acc_term(score, shared_part, abs_sum);
     }
     return score;
 }
@@ -355,6 +402,20 @@ void orc_gp_caches(const float sh[2], size_t G, const uint32_t *count, const uin
     }
 }
 
+/* BetaNegativeBinomial: plus_group bnb.hpp:57-63, Scorer::init bnb.hpp:200-211; cache[3][G] = score, post_beta, alpha */
+void orc_bnb_caches(float alpha, float beta, uint32_t r, size_t G, const uint32_t *count, const uint32_t *sum,
+                    float *cache) {
+    for (size_t g = 0; g < G; ++g) {
+        float post_alpha = alpha + (float)r * count[g];
+        float post_beta = beta + sum[g];
+        float a = post_alpha + r;
+        cache[0 * G + g] = orc_fast_lgamma(post_alpha + post_beta) - orc_fast_lgamma(post_alpha) -
+                           orc_fast_lgamma(post_beta) + orc_fast_lgamma(a);
+        cache[1 * G + g] = post_beta;
+        cache[2 * G + g] = a;
+    }
+}
+
 void orc_bb_caches(const float sh[2], size_t G, const int32_t *heads, const int32_t *tails,
                    float *cache) {
     for (size_t g = 0; g < G; ++g) { /* bb.hpp:276-292 */
@@ -419,6 +480,17 @@ void orc_gp_score_rows(size_t G, const float *cache, size_t n, const uint32_t *v
         for (size_t g = 0; g < G; ++g) {
             float temp = orc_fast_lgamma(post_alpha[g] + v);
             acc[g] += score[g] + temp - lf + coeff[g] * v;
+        }
+    }
+}
+
+void orc_bnb_score_rows(size_t G, const float *cache, size_t n, const uint32_t *values, float *scores) {
+    const float *score = cache, *post_beta = cache + G, *alpha = cache + 2 * G;
+    for (size_t i = 0; i < n; ++i) { /* bnb.hpp:308-319 */
+        float *acc = scores + i * G;
+        for (size_t g = 0; g < G; ++g) {
+            float beta = post_beta[g] + values[i];
+            acc[g] += score[g] + orc_fast_lgamma(beta) - orc_fast_lgamma(beta + alpha[g]);
         }
     }
 }

@@ -48,6 +48,11 @@ void orc_nich_caches(const float shared[4], size_t G, const int32_t *count, cons
 void orc_gp_caches(const float shared[2], size_t G, const uint32_t *count, const uint32_t *sum,
                    float *cache);
 /* bb.hpp:276-292 ; cache = [2][G]: heads, tails */
+/* BetaNegativeBinomial: caches bnb.hpp:57-63,200-211 as cache[3][G] = score, post_beta,
+ * alpha; score_value bnb.hpp:308-319 (accumulates) */
+void orc_bnb_caches(float alpha, float beta, uint32_t r, size_t G, const uint32_t *count, const uint32_t *sum,
+                    float *cache);
+void orc_bnb_score_rows(size_t G, const float *cache, size_t n, const uint32_t *values, float *scores);
 void orc_bb_caches(const float shared[2], size_t G, const int32_t *heads, const int32_t *tails,
                    float *cache);
 /* dd.hpp:399-421 ; counts [G][dim] ; cache = [dim+1][G]: rows 0..dim-1 = scores_[v], row dim = shift */
@@ -88,6 +93,12 @@ void orc_gp_group_update(int op, uint32_t *count, uint32_t *sum, float *log_prod
 double orc_bench_nich(size_t G, const float *cache, const float *prior, size_t n, const float *values,
                       const float *u, int32_t *assign, int n_threads);
 
+/* ---- LowEntropy clustering prior: clustering.hpp:265-293,318-327 through MixtureDriver::score_value
+ * (mixture.hpp:123-141) */
+float orc_low_entropy_score_add_value(int32_t dataset_size, int32_t group_size, int32_t sample_size,
+                                      int32_t empty_group_count);
+void orc_low_entropy_prior(int32_t dataset_size, size_t G, const int32_t *sizes, float *out);
+
 /* ---- score_data (log marginal likelihood of all groups): nich.hpp:262-288,
  * gp.hpp:220-241, bb.hpp:207-229, dd.hpp:250-324, dpd.hpp:344-374.  Returns the reference's fp32 group-order
  * accumulation; abs_sum (nullable, 2 doubles) receives sum |term| and the same fp32 terms summed in double. */
@@ -95,6 +106,8 @@ float orc_nich_score_data(const float sh[4], size_t G, const int32_t *count, con
                           const float *ctv, double *abs_sum);
 float orc_gp_score_data(const float sh[2], size_t G, const uint32_t *count, const uint32_t *sum,
                         const float *log_prod, double *abs_sum);
+float orc_bnb_score_data(float alpha, float beta, uint32_t r, size_t G, const uint32_t *count, const uint32_t *sum,
+                         double *abs_sum); /* bnb.hpp:221-243 */
 float orc_bb_score_data(const float sh[2], size_t G, const int32_t *heads, const int32_t *tails, double *abs_sum);
 float orc_dd_score_data(int dim, const float *alphas, size_t G, const int32_t *counts, double *abs_sum);
 float orc_dpd_score_data(float alpha, size_t V, const float *betas, size_t G, const int32_t *counts, double *abs_sum);

@@ -18,8 +18,8 @@ c_p = ctypes.c_void_p
 c_u64 = ctypes.c_uint64
 c_i32 = ctypes.c_int32
 
-DD, DPD, BB, GP, NICH, NIW = 0, 1, 2, 3, 4, 5
-COL_DTYPE = {DD: np.int32, DPD: np.uint32, BB: np.uint8, GP: np.uint32, NICH: np.float32, NIW: np.float32}
+DD, DPD, BB, GP, NICH, NIW, BNB = 0, 1, 2, 3, 4, 5, 6
+COL_DTYPE = {DD: np.int32, DPD: np.uint32, BB: np.uint8, GP: np.uint32, NICH: np.float32, NIW: np.float32, BNB: np.uint32}
 
 
 def _ptr(a):
@@ -52,6 +52,10 @@ class Oracle:
         L.orc_nich_caches.argtypes = [c_p, c_sz, c_p, c_p, c_p, c_p]
         L.orc_gp_caches.argtypes = [c_p, c_sz, c_p, c_p, c_p]
         L.orc_bb_caches.argtypes = [c_p, c_sz, c_p, c_p, c_p]
+        L.orc_bnb_caches.argtypes = [c_f, c_f, ctypes.c_uint32, c_sz, c_p, c_p, c_p]
+        L.orc_bnb_score_rows.argtypes = [c_sz, c_p, c_sz, c_p, c_p]
+        L.orc_bnb_score_data.restype = c_f
+        L.orc_bnb_score_data.argtypes = [c_f, c_f, ctypes.c_uint32, c_sz, c_p, c_p, c_p]
         L.orc_dd_caches.argtypes = [c_i, c_p, c_sz, c_p, c_p]
         L.orc_dpd_caches.argtypes = [c_f, c_f, c_sz, c_p, c_sz, c_p, c_p]
         L.orc_nich_score_rows.argtypes = [c_sz, c_p, c_sz, c_p, c_p]
@@ -94,6 +98,12 @@ class Oracle:
         self.L.orc_py_prior(alpha, d, sizes.size, _ptr(sizes), _ptr(out))
         return out
 
+    def low_entropy_prior(self, dataset_size, sizes):
+        sizes = _i32(sizes)
+        out = np.empty(sizes.size, dtype=np.float32)
+        self.L.orc_low_entropy_prior(int(dataset_size), ctypes.c_size_t(sizes.size), _ptr(sizes), _ptr(out))
+        return out
+
     # caches --------------------------------------------------------------------------------
     def nich_caches(self, shared, count, mean, ctv):
         shared, count, mean, ctv = _f32(shared), _i32(count), _f32(mean), _f32(ctv)
@@ -105,6 +115,13 @@ class Oracle:
         shared, count, sum_ = _f32(shared), _u32(count), _u32(sum_)
         out = np.empty((3, count.size), dtype=np.float32)
         self.L.orc_gp_caches(_ptr(shared), count.size, _ptr(count), _ptr(sum_), _ptr(out))
+        return out
+
+    def bnb_caches(self, shared, count, sum_):
+        """shared = (alpha, beta, r); rows: score, post_beta, alpha"""
+        count, sum_ = _u32(count), _u32(sum_)
+        out = np.empty((3, count.size), dtype=np.float32)
+        self.L.orc_bnb_caches(float(shared[0]), float(shared[1]), int(shared[2]), count.size, _ptr(count), _ptr(sum_), _ptr(out))
         return out
 
     def bb_caches(self, shared, heads, tails):
@@ -139,6 +156,8 @@ class Oracle:
             self.L.orc_gp_score_rows(G, _ptr(cache), n, _ptr(values), _ptr(scores))
         elif model == BB:
             self.L.orc_bb_score_rows(G, _ptr(cache), n, _ptr(values), _ptr(scores))
+        elif model == BNB:
+            self.L.orc_bnb_score_rows(G, _ptr(cache), n, _ptr(values), _ptr(scores))
         elif model == DD:
             self.L.orc_dd_score_rows(cache.shape[0] - 1, G, _ptr(cache), n, _ptr(values), _ptr(scores))
         elif model == DPD:
@@ -193,6 +212,10 @@ class Oracle:
             sh = _f32(w["shared"] if shared is None else shared)
             c, sm, lp = _u32(w["count"]), _u32(w["sum"]), _f32(w["log_prod"])
             r = L.orc_gp_score_data(_ptr(sh), ctypes.c_size_t(c.size), _ptr(c), _ptr(sm), _ptr(lp), a)
+        elif m == "bnb":
+            sh = np.asarray(w["shared"] if shared is None else shared, np.float64)
+            c, sm = _u32(w["count"]), _u32(w["sum"])
+            r = L.orc_bnb_score_data(float(sh[0]), float(sh[1]), int(w["shared"][2]), c.size, _ptr(c), _ptr(sm), a)
         elif m == "bb":
             sh = _f32(w["shared"] if shared is None else shared)
             h, t = _i32(w["heads"]), _i32(w["tails"])
@@ -241,6 +264,7 @@ class Ref:
         L.refshim_kind_add_nich.argtypes = [c_p, c_p, c_p, c_p, c_p]
         L.refshim_kind_add_gp.argtypes = [c_p, c_p, c_p, c_p, c_p]
         L.refshim_kind_add_bb.argtypes = [c_p, c_p, c_p, c_p]
+        L.refshim_kind_add_bnb.argtypes = [c_p, c_f, c_f, ctypes.c_uint32, c_p, c_p]
         L.refshim_kind_add_dd.argtypes = [c_p, c_i, c_p, c_p]
         L.refshim_kind_add_dpd.argtypes = [c_p, c_f, c_f, c_f, c_sz, c_p, c_p, c_p]
         L.refshim_kind_prior.argtypes = [c_p, c_p]
@@ -292,6 +316,13 @@ class Ref:
         self.L.refshim_nich_group_update(op, ctypes.byref(c), ctypes.byref(m), ctypes.byref(v), _ptr(values), values.size)
         return c.value, m.value, v.value
 
+    def low_entropy_prior(self, dataset_size, sizes):
+        sizes = _i32(sizes)
+        out = np.empty(sizes.size, dtype=np.float32)
+        self.L.refshim_low_entropy_prior.argtypes = [ctypes.c_int32, ctypes.c_size_t, c_p, c_p]
+        self.L.refshim_low_entropy_prior(int(dataset_size), sizes.size, _ptr(sizes), _ptr(out))
+        return out
+
     def gp_group_update(self, op, count, sum_, log_prod, values):
         c, s, lp = ctypes.c_uint32(count), ctypes.c_uint32(sum_), c_f(log_prod)
         values = _u32(values)
@@ -324,6 +355,11 @@ class RefKind:
         lp = _f32(log_prod) if log_prod is not None else None
         self.models.append(GP)
         return self.L.refshim_kind_add_gp(self.h, _ptr(shared), _ptr(count), _ptr(sum_), _ptr(lp))
+
+    def add_bnb(self, shared, count, sum_):
+        count, sum_ = _u32(count), _u32(sum_)
+        self.models.append(BNB)
+        return self.L.refshim_kind_add_bnb(self.h, float(shared[0]), float(shared[1]), int(shared[2]), _ptr(count), _ptr(sum_))
 
     def add_bb(self, shared, heads, tails):
         shared, heads, tails = _f32(shared), _i32(heads), _i32(tails)
@@ -375,7 +411,7 @@ class RefKind:
         return out
 
     def scorer_caches(self, f):
-        rows = {NICH: 4, GP: 3, BB: 2}[self.models[f]]
+        rows = {NICH: 4, GP: 3, BB: 2, BNB: 3}[self.models[f]]
         out = np.empty((rows, self.G), dtype=np.float32)
         rc = self.L.refshim_kind_scorer_caches(self.h, f, _ptr(out))
         assert rc == 0

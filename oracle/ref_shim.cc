@@ -31,6 +31,7 @@
 #include <distributions/models/bb.hpp>
 #include <distributions/models/dd.hpp>
 #include <distributions/models/dpd.hpp>
+#include <distributions/models/bnb.hpp>
 #include <distributions/models/gp.hpp>
 #include <distributions/models/nich.hpp>
 #include <distributions/random.hpp>
@@ -44,10 +45,11 @@ typedef D::DirichletProcessDiscrete DPD;
 typedef D::BetaBernoulli BB;
 typedef D::GammaPoisson GP;
 typedef D::NormalInverseChiSq NICH;
+typedef D::BetaNegativeBinomial BNB;
 
 namespace {
 
-enum Kind { K_DD = 0, K_DPD = 1, K_BB = 2, K_GP = 3, K_NICH = 4 };
+enum Kind { K_DD = 0, K_DPD = 1, K_BB = 2, K_GP = 3, K_NICH = 4, K_BNB = 6 };
 
 struct Feature {
     int kind;
@@ -56,6 +58,7 @@ struct Feature {
     BB::Shared bb_shared;     BB::Mixture bb;
     GP::Shared gp_shared;     GP::Mixture gp;
     NICH::Shared nich_shared; NICH::Mixture nich;
+    BNB::Shared bnb_shared;   BNB::Mixture bnb;
 };
 
 struct RefKind {
@@ -93,6 +96,10 @@ struct RefKind {
                 case K_NICH: {
                     float v = static_cast<const float *>(cols[f])[row];
                     ft.nich.score_value(ft.nich_shared, v, scores, rng);
+                } break;
+                case K_BNB: {
+                    uint32_t v = static_cast<const uint32_t *>(cols[f])[row];
+                    ft.bnb.score_value(ft.bnb_shared, v, scores, rng);
                 } break;
             }
         }
@@ -149,6 +156,19 @@ float refshim_py_score_add_value(float alpha, float d, int32_t group_size, int32
 }
 
 // ----------------------------------------------------------------------------------------------
+// LowEntropy clustering: Mixture = MixtureDriver<LowEntropy> (clustering.hpp:303), score_value overwrites out[G]
+void refshim_low_entropy_prior(int32_t dataset_size, size_t G, const int32_t * group_sizes, float * out) {
+    typedef D::Clustering<int32_t>::LowEntropy LowEntropy;
+    LowEntropy model;
+    model.dataset_size = dataset_size;
+    LowEntropy::Mixture mixture;
+    mixture.counts().assign(group_sizes, group_sizes + G);
+    mixture.init(model);
+    D::VectorFloat scores(G);
+    mixture.score_value(model, scores);
+    for (size_t g = 0; g < G; ++g) out[g] = scores[g];
+}
+
 // a "kind": one partition (G groups) shared by F feature mixtures + a PitmanYor prior on its sizes
 
 void * refshim_kind_create(size_t G, const int32_t * group_sizes, float alpha, float d) {
@@ -204,6 +224,26 @@ int refshim_kind_add_gp(void * p, const float * shared2, const uint32_t * count,
         grp.log_prod = log_prod ? log_prod[g] : 0.f;
     }
     ft->gp.init(ft->gp_shared, rng);
+    k->feats.push_back(ft);
+    return static_cast<int>(k->feats.size()) - 1;
+}
+
+int refshim_kind_add_bnb(void * p, float alpha, float beta, uint32_t r, const uint32_t * count,
+                         const uint32_t * sum) {
+    RefKind * k = K(p);
+    D::rng_t rng;
+    auto ft = std::make_shared<Feature>();
+    ft->kind = K_BNB;
+    ft->bnb_shared.alpha = alpha;
+    ft->bnb_shared.beta = beta;
+    ft->bnb_shared.r = r;
+    ft->bnb.groups().resize(k->G);
+    for (size_t g = 0; g < k->G; ++g) {
+        auto & grp = ft->bnb.groups(g);
+        grp.count = count[g];
+        grp.sum = sum[g];
+    }
+    ft->bnb.init(ft->bnb_shared, rng);
     k->feats.push_back(ft);
     return static_cast<int>(k->feats.size()) - 1;
 }
@@ -332,6 +372,11 @@ void refshim_kind_group_scores(void * p, int f, const void * value, int which, f
                 out[g] = which ? ft.nich.score_value_group(ft.nich_shared, g, v, rng)
                                : ft.nich.groups(g).score_value(ft.nich_shared, v, rng);
             } break;
+            case K_BNB: {
+                uint32_t v = *static_cast<const uint32_t *>(value);
+                out[g] = which ? ft.bnb.score_value_group(ft.bnb_shared, g, v, rng)
+                               : ft.bnb.groups(g).score_value(ft.bnb_shared, v, rng);
+            } break;
         }
     }
 }
@@ -366,6 +411,13 @@ int refshim_kind_scorer_caches(void * p, int f, float * out) {
                 s.init(ft.bb_shared, ft.bb.groups(g), rng);
                 out[0 * G + g] = s.heads_score;
                 out[1 * G + g] = s.tails_score;
+            } break;
+            case K_BNB: {  // out[3][G] = score, post_beta, alpha
+                BNB::Scorer s;
+                s.init(ft.bnb_shared, ft.bnb.groups(g), rng);
+                out[0 * G + g] = s.score;
+                out[1 * G + g] = s.post_beta;
+                out[2 * G + g] = s.alpha;
             } break;
             default: return -1;
         }
@@ -479,6 +531,14 @@ int refshim_kind_score_data_grid(void * p, int f, size_t n_grid, const float * s
                 for (int v = 0; v < ft.dd_shared.dim; ++v) grid[i].alphas[v] = shareds[i * stride + v];
             if (use_grid) ft.dd.score_data_grid(grid, scores, rng);
             else for (size_t i = 0; i < n_grid; ++i) scores[i] = ft.dd.score_data(grid[i], rng);
+        } break;
+        case K_BNB: {  // packed (alpha, beta); r of the feature's Shared
+            std::vector<BNB::Shared> grid(n_grid, ft.bnb_shared);
+            for (size_t i = 0; i < n_grid; ++i) {
+                grid[i].alpha = shareds[i * stride]; grid[i].beta = shareds[i * stride + 1];
+            }
+            if (use_grid) ft.bnb.score_data_grid(grid, scores, rng);
+            else for (size_t i = 0; i < n_grid; ++i) scores[i] = ft.bnb.score_data(grid[i], rng);
         } break;
         case K_DPD: {
             std::vector<DPD::Shared> grid(n_grid, ft.dpd_shared);

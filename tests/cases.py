@@ -3,9 +3,9 @@ distributions_b200.synth workload dict.  Test infrastructure (uses oracle/)."""
 import numpy as np
 
 from distributions_b200 import synth
-from oracle.pyoracle import BB, DD, DPD, GP, NICH
+from oracle.pyoracle import BB, BNB, DD, DPD, GP, NICH
 
-MODEL_ID = {"dd": DD, "dpd": DPD, "bb": BB, "gp": GP, "nich": NICH}
+MODEL_ID = {"dd": DD, "dpd": DPD, "bb": BB, "gp": GP, "nich": NICH, "bnb": BNB}
 
 # The small configurations stored in tests/golden (seed, G, N).  G values are deliberately ragged
 # (not multiples of 32) and include G=1 (a single, empty group).
@@ -32,6 +32,8 @@ def ref_add_feature(kind, w):
         return kind.add_gp(w["shared"], w["count"], w["sum"], w.get("log_prod"))
     if m == "bb":
         return kind.add_bb(w["shared"], w["heads"], w["tails"])
+    if m == "bnb":
+        return kind.add_bnb(w["shared"], w["count"], w["sum"])
     if m == "dd":
         return kind.add_dd(w["alphas"], w["counts"])
     if m == "dpd":
@@ -47,6 +49,8 @@ def oracle_caches(o, w):
         return o.gp_caches(w["shared"], w["count"], w["sum"])
     if m == "bb":
         return o.bb_caches(w["shared"], w["heads"], w["tails"])
+    if m == "bnb":
+        return o.bnb_caches(w["shared"], w["count"], w["sum"])
     if m == "dd":
         return o.dd_caches(w["alphas"], w["counts"])
     if m == "dpd":
@@ -98,6 +102,9 @@ def explained_mismatch(scores64, u, a, b, eps):
     return ok
 
 
+# BetaNegativeBinomial golden cases: key -> (seed, G, N, r); tests/golden/make_golden_rank3.py
+BNB_GOLDEN = {"bnb_a": (9301, 23, 96, 1), "bnb_b": (9302, 70, 64, 4)}
+
 # score_data golden cases: model -> (seed, G, synth kwargs, grid points); tests/golden/make_golden_score_data.py
 SCORE_DATA = {
     "nich": (9101, 70, {}, 12),
@@ -122,6 +129,8 @@ def shared_grid(w, n_grid, seed=0):
         g[:, 3] *= rng.uniform(0.3, 3, n_grid)
     elif m in ("gp", "bb"):
         g = np.tile(np.asarray(w["shared"], np.float32), (n_grid, 1)) * rng.uniform(0.3, 3, (n_grid, 2))
+    elif m == "bnb":  # (alpha, beta); r stays the feature's
+        g = np.tile(np.asarray(w["shared"][:2], np.float32), (n_grid, 1)) * rng.uniform(0.3, 3, (n_grid, 2))
     elif m == "dd":
         g = np.tile(np.asarray(w["alphas"], np.float32), (n_grid, 1))
         for i in range(1, n_grid):
@@ -143,6 +152,8 @@ def score_data_terms(w):
         return 4 * G
     if m == "gp":
         return 3 * G
+    if m == "bnb":
+        return 2 * G
     if m == "bb":
         return G
     return (w["counts"].shape[1] + 1) * G

@@ -36,6 +36,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_rank3():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "rank3_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_score_data():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "score_data_golden.npz"))

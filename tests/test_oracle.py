@@ -346,3 +346,70 @@ def test_score_data_oracle_matches_golden(oracle, golden_score_data):
             tol = cases.accum_tol(cases.score_data_terms(w), scale)
             assert abs(got - gd["sd_%s_out" % name][i]) <= tol, (name, i)
             assert abs(got64 - gd["sd_%s_out" % name][i]) <= tol, (name, i)
+
+
+# ------------------------------------------------------------------------------------------------
+# LowEntropy clustering prior
+def _low_entropy_cases():
+    rng = np.random.default_rng(11)
+    for dataset_size, G, empties in [(1000, 17, 1), (1000, 40, 3), (100000, 64, 1), (50, 6, 2)]:
+        sizes = rng.integers(1, max(2, dataset_size // (2 * G)), G).astype(np.int32)
+        sizes[rng.choice(G, empties, replace=False)] = 0
+        yield dataset_size, sizes
+    yield 2000000, np.array([20000, 5, 0, 1, 12345], np.int32)  # group_size > very_large branch
+
+
+def test_low_entropy_prior_matches_reference(oracle, ref):
+    for dataset_size, sizes in _low_entropy_cases():
+        got = oracle.low_entropy_prior(dataset_size, sizes)
+        want = ref.low_entropy_prior(dataset_size, sizes)
+        np.testing.assert_allclose(got, want, rtol=0, atol=2e-6 * (1 + np.abs(want).max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# BetaNegativeBinomial: caches, score_value, score_data against the compiled reference
+@pytest.mark.parametrize("G,r", [(29, 1), (64, 3), (7, 40)])
+def test_bnb_matches_reference(oracle, ref, G, r):
+    n = 300
+    w = synth.bnb(7000 + G, G, n, r=r)
+    k = ref.kind(G, w["sizes"], synth.PY_ALPHA, synth.PY_D)
+    f = cases.ref_add_feature(k, w)
+    cache = oracle.bnb_caches(w["shared"], w["count"], w["sum"])
+    want_cache = k.scorer_caches(f)
+    # fast_lgamma's polynomial is evaluated in double in both: caches agree to an ulp of the summands
+    np.testing.assert_allclose(cache, want_cache, rtol=2e-6, atol=2e-6 * (1 + np.abs(want_cache[0]).max()))
+    got = cases.oracle_scores(oracle, [w], prior=oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"]))
+    want = k.score_rows([w["values"]], n)
+    # score[g] + lgamma(beta) - lgamma(beta + alpha[g]) cancels: envelope 6e-7 * (1 + |score[g]| + |lgamma terms|)
+    env = 6e-7 * (1 + np.abs(want_cache[0])[None, :] + 2 * np.abs(want).max())
+    assert np.all(np.abs(got - want) <= 3e-6 * (1 + np.abs(want)) + env)
+    grid = cases.shared_grid(w, 7, seed=G)
+    per_point = k.score_data_grid(f, grid, use_grid=False)
+    for i in range(grid.shape[0]):
+        sd, scale, sd64 = oracle.score_data(w, grid[i])
+        assert abs(sd - per_point[i]) <= cases.accum_tol(cases.score_data_terms(w), scale)
+
+
+def test_rank3_oracle_matches_golden(oracle, golden_rank3):
+    """bnb + LowEntropy restatements against committed reference outputs (no reference needed)"""
+    gd = golden_rank3
+    for key, (seed, G, N, rr) in cases.BNB_GOLDEN.items():
+        w = synth.bnb(seed, G, N, r=rr)
+        cache = oracle.bnb_caches(w["shared"], w["count"], w["sum"])
+        want_cache = gd[key + "_caches"]
+        np.testing.assert_allclose(cache, want_cache, rtol=2e-6, atol=2e-6 * (1 + np.abs(want_cache[0]).max()))
+        got = cases.oracle_scores(oracle, [w], prior=oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"]))
+        want = gd[key + "_scores"]
+        env = 6e-7 * (1 + np.abs(want_cache[0])[None, :] + 2 * np.abs(want).max())
+        assert np.all(np.abs(got - want) <= 3e-6 * (1 + np.abs(want)) + env)
+        a = oracle.sample_rows(want.copy(), gd[key + "_u"])
+        assert np.array_equal(a, gd[key + "_assign"])
+        # Mixture::score_value_group == Group::score_value up to the cached / uncached evaluation order
+        np.testing.assert_allclose(gd[key + "_group_scores"], gd[key + "_mixture_group_scores"], rtol=0, atol=2e-3)
+        for i, sh in enumerate(gd[key + "_sd_grid"]):
+            sd, scale, _ = oracle.score_data(w, sh)
+            assert abs(sd - gd[key + "_sd_out"][i]) <= cases.accum_tol(cases.score_data_terms(w), scale)
+    for i, (dataset_size, sizes) in enumerate(_low_entropy_cases()):
+        assert int(gd["le_%d_dataset_size" % i][0]) == dataset_size and np.array_equal(gd["le_%d_sizes" % i], sizes)
+        want = gd["le_%d_out" % i]
+        np.testing.assert_allclose(oracle.low_entropy_prior(dataset_size, sizes), want, rtol=0, atol=2e-6 * (1 + np.abs(want).max()))
