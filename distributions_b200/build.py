@@ -27,6 +27,7 @@ SOURCES = {
     "niw_tc.cu": [],
     "microbench.cu": [],
     "stats.cu": [],
+    "wire.cu": [],
 }
 
 

@@ -46,6 +46,9 @@ SIGNATURES = {
     "dist_b200_gp_set_log_prod": (c_i, [c_p, c_p, c_p]),
     "dist_b200_score_data_grid": (c_i, [c_p, c_p, c_sz, c_sz, c_p, c_p]),
     "dist_b200_score_data_grid_host": (c_i, [c_p, c_p, c_sz, c_sz, c_p]),
+    "dist_b200_update_all_wire": (c_i, [c_p, c_p, c_sz, c_p, c_p, c_i, c_p]),
+    "dist_b200_wire_decode": (c_i, [c_p, c_i, c_p, c_sz, c_p, c_p, c_i, c_p, c_sz, c_p, c_sz, c_p, c_sz, c_p]),
+    "dist_b200_prior_wire_host": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p]),
     "dist_b200_feature_download_stats": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
     "dist_b200_count_assignments": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_i, c_p]),
     "dist_b200_prior_pitman_yor_dev": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
@@ -110,6 +113,27 @@ def _dev_ptr(t):
     return t.data_ptr()
 
 
+def wire_decode(model, shared_msg, group_msgs):
+    """decode serialized Shared / Group messages into (shared floats, keys, stats words); needs no device"""
+    L = lib()
+    G = len(group_msgs)
+    bufs = [ctypes.create_string_buffer(m, len(m)) for m in group_msgs]
+    ptrs = (c_p * max(G, 1))(*[ctypes.addressof(b) for b in bufs])
+    lens = (c_sz * max(G, 1))(*[len(m) for m in group_msgs])
+    counts = (c_sz * 3)()
+    args = (None, model, shared_msg, len(shared_msg), ptrs, lens, G)
+    rc = L.dist_b200_wire_decode(*args, None, 0, None, 0, None, 0, counts)
+    if rc not in (0, 1) or (rc == 1 and not any(counts)):
+        raise ValueError("wire_decode: status %d" % rc)
+    sh = np.empty(counts[0], np.float32)
+    keys = np.empty(counts[1], np.uint32)
+    st = np.empty(counts[2], np.uint32)
+    rc = L.dist_b200_wire_decode(*args, _np_ptr(sh), sh.size, _np_ptr(keys), keys.size, _np_ptr(st), st.size, counts)
+    if rc != 0:
+        raise ValueError("wire_decode: status %d" % rc)
+    return sh, keys, st
+
+
 class Context:
     def __init__(self, device=0):
         self.L = lib()
@@ -149,6 +173,12 @@ class Context:
         self.check(self.L.dist_b200_prior_pitman_yor(self.h, alpha, d, sizes.size, _np_ptr(sizes), _dev_ptr(prior_dev),
                                                      stream), "prior_pitman_yor")
 
+    def prior_pitman_yor_host(self, alpha, d, group_sizes):
+        sizes = np.ascontiguousarray(group_sizes, dtype=np.int32)
+        out = np.empty(sizes.size, dtype=np.float32)
+        self.check(self.L.dist_b200_prior_pitman_yor_host(self.h, alpha, d, sizes.size, _np_ptr(sizes), _np_ptr(out)), "prior_pitman_yor_host")
+        return out
+
     def add_rows_batch(self, features, columns, assign_dev, n_rows, stream=None):
         """batched Group::add_value for all features of one kind; nothing is drained, later calls order behind it"""
         F, fa, ca = self._lists(features, columns)
@@ -179,6 +209,13 @@ class Context:
     def count_assignments(self, assign_dev, n_rows, G, counts_dev, accumulate=False, stream=None):
         self.check(self.L.dist_b200_count_assignments(self.h, _dev_ptr(assign_dev), n_rows, G, _dev_ptr(counts_dev),
                                                       1 if accumulate else 0, stream), "count_assignments")
+
+    def prior_wire_host(self, clustering_msg, sizes):
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        out = np.empty(sizes.size, dtype=np.float32)
+        self.check(self.L.dist_b200_prior_wire_host(self.h, clustering_msg, len(clustering_msg), sizes.size, _np_ptr(sizes), _np_ptr(out)),
+                   "prior_wire")
+        return out
 
     def prior_low_entropy_host(self, dataset_size, sizes):
         sizes = np.ascontiguousarray(sizes, dtype=np.int32)
@@ -375,6 +412,16 @@ class Feature:
     def score_data_grid_dev(self, shareds_dev, n_grid, stride, out_dev, stream=None):
         self.ctx.check(self.ctx.L.dist_b200_score_data_grid(self.h, _dev_ptr(shareds_dev), n_grid, stride, _dev_ptr(out_dev), stream),
                        "score_data_grid")
+
+    def update_all_wire(self, shared_msg, group_msgs, stream=None):
+        """Shared + Groups as serialized protobuf messages (bytes) of the reference's schema"""
+        G = len(group_msgs)
+        bufs = [ctypes.create_string_buffer(m, len(m)) for m in group_msgs]
+        ptrs = (c_p * max(G, 1))(*[ctypes.addressof(b) for b in bufs])
+        lens = (c_sz * max(G, 1))(*[len(m) for m in group_msgs])
+        self.ctx.check(self.ctx.L.dist_b200_update_all_wire(self.h, shared_msg, len(shared_msg), ptrs, lens, G, stream),
+                       "update_all_wire")
+        return self
 
     def download_stats(self, nbytes, stream=None):
         out = np.empty(nbytes, dtype=np.uint8)

@@ -869,6 +869,69 @@ int dist_b200_score_data_grid_host(dist_b200_feature *f, const float *shareds_ho
     return rc;
 }
 
+// ---- protobuf wire format (schema.proto) -> update_all --------------------------
+int dist_b200_wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg, size_t shared_len,
+                          const void *const *group_msgs, const size_t *group_lens, int G, float *shared_out,
+                          size_t shared_cap, uint32_t *keys_out, size_t keys_cap, uint32_t *stats_out, size_t stats_cap,
+                          size_t counts_out[3]) {
+    if (!counts_out) return DIST_B200_ERR_INVALID;  // ctx may be null: decoding needs no device
+    WireFeature w;
+    int rc = wire_decode(ctx, model, shared_msg, shared_len, group_msgs, group_lens, G, w);
+    if (rc) return rc;
+    counts_out[0] = w.shared.size();
+    counts_out[1] = w.keys.size();
+    counts_out[2] = w.stats.size();
+    if (w.shared.size() > shared_cap || w.keys.size() > keys_cap || w.stats.size() > stats_cap)
+        return fail(ctx, DIST_B200_ERR_INVALID, "wire_decode: output buffer too small (sizes returned in counts_out)");
+    if (shared_out && !w.shared.empty()) std::memcpy(shared_out, w.shared.data(), sizeof(float) * w.shared.size());
+    if (keys_out && !w.keys.empty()) std::memcpy(keys_out, w.keys.data(), sizeof(uint32_t) * w.keys.size());
+    if (stats_out && !w.stats.empty()) std::memcpy(stats_out, w.stats.data(), sizeof(uint32_t) * w.stats.size());
+    return DIST_B200_OK;
+}
+
+int dist_b200_update_all_wire(dist_b200_feature *f, const void *shared_msg, size_t shared_len,
+                              const void *const *group_msgs, const size_t *group_lens, int G, void *stream) {
+    if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
+    dist_b200_ctx *ctx = f->ctx;
+    WireFeature w;
+    int rc = wire_decode(ctx, f->model, shared_msg, shared_len, group_msgs, group_lens, G, w);
+    if (rc) return rc;
+    const size_t g = static_cast<size_t>(G);
+    const uint32_t *st = w.stats.data();
+    switch (f->model) {
+        case DIST_B200_NICH:
+            return dist_b200_nich_update_all(f, w.shared.data(), G, reinterpret_cast<const int32_t *>(st),
+                                             reinterpret_cast<const float *>(st + g), reinterpret_cast<const float *>(st + 2 * g), stream);
+        case DIST_B200_GP:
+            if ((rc = dist_b200_gp_update_all(f, w.shared.data(), G, st, st + g, stream))) return rc;
+            return G ? dist_b200_gp_set_log_prod(f, reinterpret_cast<const float *>(st + 2 * g), stream) : DIST_B200_OK;
+        case DIST_B200_BNB:
+            return dist_b200_bnb_update_all(f, w.shared.data(), w.keys[0], G, st, st + g, stream);
+        case DIST_B200_BB:
+            return dist_b200_bb_update_all(f, w.shared.data(), G, reinterpret_cast<const int32_t *>(st),
+                                           reinterpret_cast<const int32_t *>(st + g), stream);
+        case DIST_B200_DD:
+            return dist_b200_dd_update_all(f, w.dim, w.shared.data(), G, reinterpret_cast<const int32_t *>(st), stream);
+        case DIST_B200_DPD:
+            return dist_b200_dpd_update_all(f, w.shared[1], w.shared[2], w.dim, w.keys.data(), w.shared.data() + 3, G,
+                                            reinterpret_cast<const int32_t *>(st), stream);
+        default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "update_all_wire: unsupported model");
+    }
+}
+
+int dist_b200_prior_wire_host(dist_b200_ctx *ctx, const void *clustering_msg, size_t len, int G,
+                              const int32_t *group_sizes, float *prior_host) {
+    if (!ctx || !clustering_msg || !group_sizes || !prior_host || G < 1) return DIST_B200_ERR_INVALID;
+    int which = 0;
+    float alpha = 0, d = 0;
+    uint64_t dataset_size = 0;
+    int rc = wire_decode_clustering(ctx, clustering_msg, len, &which, &alpha, &d, &dataset_size);
+    if (rc) return rc;
+    if (which == 1) return dist_b200_prior_pitman_yor_host(ctx, alpha, d, G, group_sizes, prior_host);
+    if (dataset_size < 1 || dataset_size > 0x7FFFFFFFull) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: LowEntropy dataset_size out of range");
+    return dist_b200_prior_low_entropy_host(ctx, static_cast<int>(dataset_size), G, group_sizes, prior_host);
+}
+
 int dist_b200_feature_download_stats(const dist_b200_feature *f, void *out_host, size_t capacity_bytes, size_t *n_bytes,
                                      void *stream) {
     if (!f || !f->ctx || !out_host) return DIST_B200_ERR_INVALID;

@@ -210,4 +210,17 @@ int launch_niw_tc_prep(dist_b200_ctx *ctx, int G, const float *recs, float *tc_b
 int launch_niw_tc_scores(dist_b200_ctx *ctx, int G, const float *tc_buf, const void *values, size_t N, const float *prior,
                          float *scores, int accumulate, bool split, cudaStream_t s);
 
+// wire.cu: protobuf wire format of the reference (schema.proto) -> SoA.  Decoded feature: Shared floats
+// (+ dpd keys) and the statistics arrays in update_all's argument order.
+struct WireFeature {
+    std::vector<float> shared;     // nich 4; gp 2; bb 2; bnb 3 (alpha, beta, r); dd alphas[dim]; dpd gamma, alpha, beta0, betas[V]
+    std::vector<uint32_t> keys;    // dpd: Shared.values; bnb: r (exact)
+    std::vector<uint32_t> stats;   // arrays of G (x dim) 4-byte elements, floats as their bit patterns
+    int dim = 0;                   // dd dim / dpd V
+};
+int wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg, size_t shared_len, const void *const *group_msgs,
+                const size_t *group_lens, int G, WireFeature &out);
+int wire_decode_clustering(dist_b200_ctx *ctx, const void *msg, size_t len, int *which, float *alpha, float *d,
+                           uint64_t *dataset_size);
+
 }  // namespace distb200

@@ -1,0 +1,274 @@
+// wire.cu -- the reference's protobuf wire format (distributions/io/schema.proto:36-158) decoded straight
+// into the packed SoA arrays update_all takes: Shared + G serialized Group messages -> statistics on the
+// device, without materialising host object graphs.  Host code only.
+//
+// Only what the schema uses is implemented: varint (wire type 0), 64-bit (1), length-delimited (2, also
+// packed repeated scalars), 32-bit (5).  proto2 repeated scalars may arrive packed or unpacked; both are
+// accepted.  Unknown fields are skipped, as protobuf readers do.  Counts are uint64 on the wire and 32-bit
+// in the reference's Groups (e.g. nich.hpp:98-101, gp.hpp:84-87): a value that does not fit is an error.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace distb200 {
+namespace {
+
+struct Reader {
+    const uint8_t *p, *end;
+    bool ok = true;
+
+    bool done() const { return p >= end || !ok; }
+    uint64_t varint() {
+        uint64_t v = 0;
+        for (int shift = 0; shift < 64; shift += 7) {
+            if (p >= end) {
+                ok = false;
+                return 0;
+            }
+            const uint8_t b = *p++;
+            v |= static_cast<uint64_t>(b & 0x7f) << shift;
+            if (!(b & 0x80)) return v;
+        }
+        ok = false;  // more than 10 bytes
+        return 0;
+    }
+    float fixed32() {
+        if (end - p < 4) {
+            ok = false;
+            return 0.f;
+        }
+        float f;
+        std::memcpy(&f, p, 4);  // little-endian host (x86-64 / aarch64)
+        p += 4;
+        return f;
+    }
+    Reader sub() {  // length-delimited payload
+        const uint64_t n = varint();
+        if (!ok || n > static_cast<uint64_t>(end - p)) {
+            ok = false;
+            return Reader{p, p};
+        }
+        Reader r{p, p + n};
+        p += n;
+        return r;
+    }
+    void skip(int wire_type) {
+        switch (wire_type) {
+            case 0: varint(); break;
+            case 1: if (end - p < 8) ok = false; else p += 8; break;
+            case 2: sub(); break;
+            case 5: if (end - p < 4) ok = false; else p += 4; break;
+            default: ok = false;
+        }
+    }
+};
+
+// one field occurrence of a float / varint scalar, packed or not, appended to `out`
+void read_floats(Reader &r, int wire_type, std::vector<float> &out) {
+    if (wire_type == 5) out.push_back(r.fixed32());
+    else if (wire_type == 2) {
+        Reader s = r.sub();
+        while (!s.done()) out.push_back(s.fixed32());
+        if (!s.ok) r.ok = false;
+    } else r.ok = false;
+}
+void read_varints(Reader &r, int wire_type, std::vector<uint64_t> &out) {
+    if (wire_type == 0) out.push_back(r.varint());
+    else if (wire_type == 2) {
+        Reader s = r.sub();
+        while (!s.done()) out.push_back(s.varint());
+        if (!s.ok) r.ok = false;
+    } else r.ok = false;
+}
+
+struct Fields {  // up to 5 numbered fields of one message, everything the schema's model messages need
+    std::vector<float> f[6];
+    std::vector<uint64_t> v[6];
+};
+
+// kinds: 'f' float field, 'v' varint field, 0 = not present in this message (skipped)
+bool parse(const void *msg, size_t len, const char kinds[6], Fields &out) {
+    Reader r{static_cast<const uint8_t *>(msg), static_cast<const uint8_t *>(msg) + len};
+    while (!r.done()) {
+        const uint64_t key = r.varint();
+        if (!r.ok) break;
+        const int wt = static_cast<int>(key & 7);
+        const uint64_t num = key >> 3;
+        if (num >= 1 && num <= 5 && kinds[num] == 'f') read_floats(r, wt, out.f[num]);
+        else if (num >= 1 && num <= 5 && kinds[num] == 'v') read_varints(r, wt, out.v[num]);
+        else r.skip(wt);
+    }
+    return r.ok;
+}
+
+bool fits32(uint64_t v) { return v <= 0xFFFFFFFFull; }
+
+}  // namespace
+
+static uint32_t fbits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+
+int wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg, size_t shared_len, const void *const *group_msgs,
+                const size_t *group_lens, int G, WireFeature &out) {
+    auto bad = [&](const char *what) { return fail(ctx, DIST_B200_ERR_INVALID, std::string("wire: ") + what); };
+    if (!shared_msg && shared_len) return bad("null Shared message");
+    if (G < 0 || (G && (!group_msgs || !group_lens))) return bad("null Group messages");
+    Fields sh;
+    const size_t g = static_cast<size_t>(G);
+    switch (model) {
+        case DIST_B200_NICH: {  // schema.proto:131-145
+            if (!parse(shared_msg, shared_len, "\0ffff", sh)) return bad("malformed NormalInverseChiSq.Shared");
+            for (int k = 1; k <= 4; ++k)
+                if (sh.f[k].size() != 1) return bad("NormalInverseChiSq.Shared: missing required field");
+            out.shared = {sh.f[1][0], sh.f[2][0], sh.f[3][0], sh.f[4][0]};
+            out.stats.assign(3 * g, 0);
+            for (size_t i = 0; i < g; ++i) {
+                Fields m;
+                if (!parse(group_msgs[i], group_lens[i], "\0vff\0", m)) return bad("malformed NormalInverseChiSq.Group");
+                if (m.v[1].size() != 1 || m.f[2].size() != 1 || m.f[3].size() != 1) return bad("NormalInverseChiSq.Group: missing required field");
+                if (m.v[1][0] > 0x7FFFFFFFull) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                out.stats[i] = static_cast<uint32_t>(m.v[1][0]);
+                out.stats[g + i] = fbits(m.f[2][0]);
+                out.stats[2 * g + i] = fbits(m.f[3][0]);
+            }
+        } break;
+        case DIST_B200_GP: {  // schema.proto:105-116: count, sum, log_prod
+            if (!parse(shared_msg, shared_len, "\0ff\0\0", sh)) return bad("malformed GammaPoisson.Shared");
+            if (sh.f[1].size() != 1 || sh.f[2].size() != 1) return bad("GammaPoisson.Shared: missing required field");
+            out.shared = {sh.f[1][0], sh.f[2][0]};
+            out.stats.assign(3 * g, 0);
+            for (size_t i = 0; i < g; ++i) {
+                Fields m;
+                if (!parse(group_msgs[i], group_lens[i], "\0vvf\0", m)) return bad("malformed GammaPoisson.Group");
+                if (m.v[1].size() != 1 || m.v[2].size() != 1 || m.f[3].size() != 1) return bad("GammaPoisson.Group: missing required field");
+                if (!fits32(m.v[1][0]) || !fits32(m.v[2][0])) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                out.stats[i] = static_cast<uint32_t>(m.v[1][0]);
+                out.stats[g + i] = static_cast<uint32_t>(m.v[2][0]);
+                out.stats[2 * g + i] = fbits(m.f[3][0]);
+            }
+        } break;
+        case DIST_B200_BNB: {  // schema.proto:118-129
+            if (!parse(shared_msg, shared_len, "\0ffv\0", sh)) return bad("malformed BetaNegativeBinomial.Shared");
+            if (sh.f[1].size() != 1 || sh.f[2].size() != 1 || sh.v[3].size() != 1) return bad("BetaNegativeBinomial.Shared: missing required field");
+            if (!fits32(sh.v[3][0])) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: r exceeds 32 bits");
+            out.shared = {sh.f[1][0], sh.f[2][0], static_cast<float>(sh.v[3][0])};
+            out.keys = {static_cast<uint32_t>(sh.v[3][0])};  // r, exact
+            out.stats.assign(2 * g, 0);
+            for (size_t i = 0; i < g; ++i) {
+                Fields m;
+                if (!parse(group_msgs[i], group_lens[i], "\0vv\0\0", m)) return bad("malformed BetaNegativeBinomial.Group");
+                if (m.v[1].size() != 1 || m.v[2].size() != 1) return bad("BetaNegativeBinomial.Group: missing required field");
+                if (!fits32(m.v[1][0]) || !fits32(m.v[2][0])) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                out.stats[i] = static_cast<uint32_t>(m.v[1][0]);
+                out.stats[g + i] = static_cast<uint32_t>(m.v[2][0]);
+            }
+        } break;
+        case DIST_B200_BB: {  // schema.proto:55-65
+            if (!parse(shared_msg, shared_len, "\0ff\0\0", sh)) return bad("malformed BetaBernoulli.Shared");
+            if (sh.f[1].size() != 1 || sh.f[2].size() != 1) return bad("BetaBernoulli.Shared: missing required field");
+            out.shared = {sh.f[1][0], sh.f[2][0]};
+            out.stats.assign(2 * g, 0);
+            for (size_t i = 0; i < g; ++i) {
+                Fields m;
+                if (!parse(group_msgs[i], group_lens[i], "\0vv\0\0", m)) return bad("malformed BetaBernoulli.Group");
+                if (m.v[1].size() != 1 || m.v[2].size() != 1) return bad("BetaBernoulli.Group: missing required field");
+                if (m.v[1][0] > 0x7FFFFFFFull || m.v[2][0] > 0x7FFFFFFFull) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                out.stats[i] = static_cast<uint32_t>(m.v[1][0]);
+                out.stats[g + i] = static_cast<uint32_t>(m.v[2][0]);
+            }
+        } break;
+        case DIST_B200_DD: {  // schema.proto:67-75: repeated alphas / repeated counts
+            if (!parse(shared_msg, shared_len, "\0f\0\0\0", sh)) return bad("malformed DirichletDiscrete.Shared");
+            const size_t dim = sh.f[1].size();
+            if (dim < 1 || dim > 256) return bad("DirichletDiscrete.Shared: dim must be 1..256");
+            out.shared = sh.f[1];
+            out.dim = static_cast<int>(dim);
+            out.stats.assign(g * dim, 0);
+            for (size_t i = 0; i < g; ++i) {
+                Fields m;
+                if (!parse(group_msgs[i], group_lens[i], "\0v\0\0\0", m)) return bad("malformed DirichletDiscrete.Group");
+                if (m.v[1].size() != dim) return bad("DirichletDiscrete.Group: counts length differs from Shared.alphas (dd.hpp:104-111)");
+                for (size_t v = 0; v < dim; ++v) {
+                    if (m.v[1][v] > 0x7FFFFFFFull) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                    out.stats[i * dim + v] = static_cast<uint32_t>(m.v[1][v]);
+                }
+            }
+        } break;
+        case DIST_B200_DPD: {  // schema.proto:77-90; Shared::protobuf_load dpd.hpp:104-125
+            if (!parse(shared_msg, shared_len, "\0ffvfv", sh)) return bad("malformed DirichletProcessDiscrete.Shared");
+            if (sh.f[1].size() != 1 || sh.f[2].size() != 1) return bad("DirichletProcessDiscrete.Shared: missing required field");
+            const size_t V = sh.v[3].size();
+            if (V < 1 || sh.f[4].size() != V || sh.v[5].size() != V) return bad("DirichletProcessDiscrete.Shared: values / betas / counts lengths differ");
+            double beta_sum = 0;  // dpd.hpp:114-124
+            out.shared = {sh.f[1][0], sh.f[2][0], 0.f};
+            for (size_t v = 0; v < V; ++v) {
+                if (!fits32(sh.v[3][v])) return bad("DirichletProcessDiscrete.Shared: value exceeds 32 bits");
+                if (!(sh.f[4][v] > 0.f)) return bad("DirichletProcessDiscrete.Shared: beta must be positive");
+                out.keys.push_back(static_cast<uint32_t>(sh.v[3][v]));
+                out.shared.push_back(sh.f[4][v]);
+                beta_sum += sh.f[4][v];
+            }
+            if (beta_sum > 1 + 1e-4) return bad("DirichletProcessDiscrete.Shared: betas sum to more than 1");
+            out.shared[2] = static_cast<float>(std::max(0.0, 1.0 - beta_sum));
+            out.dim = static_cast<int>(V);
+            out.stats.assign(g * V, 0);
+            // key -> column of the dense [G][V] table, Shared's order
+            std::vector<std::pair<uint32_t, uint32_t>> index(V);
+            for (size_t v = 0; v < V; ++v) index[v] = {out.keys[v], static_cast<uint32_t>(v)};
+            std::sort(index.begin(), index.end());
+            for (size_t i = 0; i < g; ++i) {
+                Fields m;
+                if (!parse(group_msgs[i], group_lens[i], "\0vv\0\0", m)) return bad("malformed DirichletProcessDiscrete.Group");
+                if (m.v[1].size() != m.v[2].size()) return bad("DirichletProcessDiscrete.Group: keys / values lengths differ");
+                for (size_t k = 0; k < m.v[1].size(); ++k) {
+                    if (!fits32(m.v[1][k]) || m.v[2][k] > 0x7FFFFFFFull) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                    const uint32_t key = static_cast<uint32_t>(m.v[1][k]);
+                    auto it = std::lower_bound(index.begin(), index.end(), std::make_pair(key, 0u));
+                    if (it == index.end() || it->first != key) return bad("DirichletProcessDiscrete.Group: key absent from Shared.values");
+                    out.stats[i * V + it->second] += static_cast<uint32_t>(m.v[2][k]);
+                }
+            }
+        } break;
+        default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: model has no wire loader (niw statistics stay on the host)");
+    }
+    return DIST_B200_OK;
+}
+
+// Clustering message (schema.proto:36-53): which = 1 PitmanYor {alpha, d}, 2 LowEntropy {dataset_size}
+int wire_decode_clustering(dist_b200_ctx *ctx, const void *msg, size_t len, int *which, float *alpha, float *d,
+                           uint64_t *dataset_size) {
+    Reader r{static_cast<const uint8_t *>(msg), static_cast<const uint8_t *>(msg) + len};
+    *which = 0;
+    while (!r.done()) {
+        const uint64_t key = r.varint();
+        if (!r.ok) break;
+        const int wt = static_cast<int>(key & 7);
+        const uint64_t num = key >> 3;
+        if (wt == 2 && (num == 1 || num == 2)) {
+            Reader s = r.sub();
+            if (!r.ok) break;
+            Fields m;
+            if (num == 1) {
+                if (!parse(s.p, static_cast<size_t>(s.end - s.p), "\0ff\0\0", m) || m.f[1].size() != 1 || m.f[2].size() != 1)
+                    return fail(ctx, DIST_B200_ERR_INVALID, "wire: malformed Clustering.PitmanYor");
+                *alpha = m.f[1][0];
+                *d = m.f[2][0];
+            } else {
+                if (!parse(s.p, static_cast<size_t>(s.end - s.p), "\0v\0\0\0", m) || m.v[1].size() != 1)
+                    return fail(ctx, DIST_B200_ERR_INVALID, "wire: malformed Clustering.LowEntropy");
+                *dataset_size = m.v[1][0];
+            }
+            *which = static_cast<int>(num);
+        } else {
+            r.skip(wt);
+        }
+    }
+    if (!r.ok || *which == 0) return fail(ctx, DIST_B200_ERR_INVALID, "wire: malformed Clustering message");
+    return DIST_B200_OK;
+}
+
+}  // namespace distb200

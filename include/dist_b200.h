@@ -163,6 +163,27 @@ int dist_b200_score_data_grid(dist_b200_feature *f, const float *shareds_dev, si
                               float *out_dev, void *stream);
 int dist_b200_score_data_grid_host(dist_b200_feature *f, const float *shareds_host, size_t n_grid, size_t stride,
                                    float *out_host);
+/* ---- the reference's protobuf wire format (distributions/io/schema.proto:36-158) ----------------------
+ * Load a feature from its serialized Shared message and G serialized Group messages (the records of the
+ * reference's dumps / loom-style streams) without building host objects: the messages are decoded straight
+ * into the SoA arrays of the model's update_all (dpd: dense counts in Shared.values order, beta0 =
+ * max(0, 1 - sum betas) as Shared::protobuf_load, dpd.hpp:104-125; gp: log_prod is kept for score_data_grid).
+ * Packed and unpacked repeated scalars are accepted, unknown fields skipped; a malformed message is
+ * DIST_B200_ERR_INVALID, a uint64 count that does not fit the reference's 32-bit Group fields
+ * DIST_B200_ERR_UNSUPPORTED.  niw: unsupported. */
+int dist_b200_update_all_wire(dist_b200_feature *f, const void *shared_msg, size_t shared_len,
+                              const void *const *group_msgs, const size_t *group_lens, int G, void *stream);
+/* The decode step alone (no device): shared_out = Shared floats (nich 4; gp 2; bb 2; bnb alpha, beta, r;
+ * dd alphas; dpd gamma, alpha, beta0, betas[V]), keys_out = dpd Shared.values (bnb: r), stats_out = the
+ * update_all arrays back to back, floats as bit patterns (gp: count | sum | log_prod).  counts_out receives the
+ * three lengths (also when a buffer is too small).  ctx may be NULL (no error text is recorded then). */
+int dist_b200_wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg, size_t shared_len,
+                          const void *const *group_msgs, const size_t *group_lens, int G, float *shared_out,
+                          size_t shared_cap, uint32_t *keys_out, size_t keys_cap, uint32_t *stats_out, size_t stats_cap,
+                          size_t counts_out[3]);
+/* Clustering message (pitman_yor = 1 | low_entropy = 2, schema.proto:36-53) -> the prior vector */
+int dist_b200_prior_wire_host(dist_b200_ctx *ctx, const void *clustering_msg, size_t len, int G,
+                              const int32_t *group_sizes, float *prior_host);
 /* Device-resident statistics back to the host, arrays in update_all's argument order, G entries each
  * (nich: count,int32 | mean,f32 | ctv,f32; gp: count | sum; bb: heads | tails; dd: counts[G][dim];
  * dpd: counts[G][V]).  Synchronises the stream. */

@@ -105,6 +105,16 @@ def explained_mismatch(scores64, u, a, b, eps):
 # BetaNegativeBinomial golden cases: key -> (seed, G, N, r); tests/golden/make_golden_rank3.py
 BNB_GOLDEN = {"bnb_a": (9301, 23, 96, 1), "bnb_b": (9302, 70, 64, 4)}
 
+# protobuf wire fixtures: model -> (seed, G, synth kwargs); tests/golden/make_golden_wire.py
+WIRE = {
+    "nich": (9401, 9, {}),
+    "gp": (9402, 11, {}),
+    "bnb": (9403, 7, dict(r=3)),
+    "bb": (9404, 10, {}),
+    "dd": (9405, 8, dict(dim=16)),
+    "dpd": (9406, 6, dict(V=40, other_frac=0.05)),
+}
+
 # score_data golden cases: model -> (seed, G, synth kwargs, grid points); tests/golden/make_golden_score_data.py
 SCORE_DATA = {
     "nich": (9101, 70, {}, 12),
