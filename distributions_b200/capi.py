@@ -49,6 +49,8 @@ SIGNATURES = {
     "dist_b200_update_all_wire": (c_i, [c_p, c_p, c_sz, c_p, c_p, c_i, c_p]),
     "dist_b200_wire_decode": (c_i, [c_p, c_i, c_p, c_sz, c_p, c_p, c_i, c_p, c_sz, c_p, c_sz, c_p, c_sz, c_p]),
     "dist_b200_prior_wire_host": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p]),
+    "dist_b200_feature_dump_groups_wire": (c_i, [c_p, c_p, c_sz, c_p, c_p, c_p]),
+    "dist_b200_wire_encode_groups": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_sz, c_p, c_sz, c_p, c_p]),
     "dist_b200_feature_download_stats": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
     "dist_b200_count_assignments": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_i, c_p]),
     "dist_b200_prior_pitman_yor_dev": (c_i, [c_p, c_f, c_f, c_i, c_p, c_p, c_p]),
@@ -132,6 +134,31 @@ def wire_decode(model, shared_msg, group_msgs):
     if rc != 0:
         raise ValueError("wire_decode: status %d" % rc)
     return sh, keys, st
+
+
+def _split(buf, lens):
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    raw = buf.tobytes()
+    return [raw[offs[i]:offs[i + 1]] for i in range(len(lens))]
+
+
+def wire_encode_groups(model, G, dim, keys, stats):
+    """SoA statistics (the arrays wire_decode returns) -> list of serialized Group messages; needs no device"""
+    L = lib()
+    stats = np.ascontiguousarray(stats, dtype=np.uint32)
+    keys = np.ascontiguousarray(keys, dtype=np.uint32) if keys is not None else np.zeros(0, np.uint32)
+    n = c_sz()
+    lens = (c_sz * max(G, 1))()
+    rc = L.dist_b200_wire_encode_groups(None, model, G, dim, _np_ptr(keys) if keys.size else None, _np_ptr(stats), stats.size,
+                                        None, 0, lens, ctypes.byref(n))
+    if rc != 1 and not (rc == 0 and n.value == 0):
+        raise ValueError("wire_encode_groups: status %d" % rc)
+    buf = np.empty(n.value, np.uint8)
+    rc = L.dist_b200_wire_encode_groups(None, model, G, dim, _np_ptr(keys) if keys.size else None, _np_ptr(stats), stats.size,
+                                        _np_ptr(buf), buf.size, lens, ctypes.byref(n))
+    if rc != 0:
+        raise ValueError("wire_encode_groups: status %d" % rc)
+    return _split(buf, [lens[i] for i in range(G)])
 
 
 class Context:
@@ -422,6 +449,19 @@ class Feature:
         self.ctx.check(self.ctx.L.dist_b200_update_all_wire(self.h, shared_msg, len(shared_msg), ptrs, lens, G, stream),
                        "update_all_wire")
         return self
+
+    def dump_groups_wire(self, stream=None):
+        """the current device-resident statistics as serialized Group messages (list of bytes)"""
+        G = self.groups
+        n = c_sz()
+        lens = (c_sz * max(G, 1))()
+        L = self.ctx.L
+        rc = L.dist_b200_feature_dump_groups_wire(self.h, None, 0, lens, ctypes.byref(n), stream)
+        if rc not in (0, 1):
+            self.ctx.check(rc, "dump_groups_wire")
+        buf = np.empty(n.value, np.uint8)
+        self.ctx.check(L.dist_b200_feature_dump_groups_wire(self.h, _np_ptr(buf), buf.size, lens, ctypes.byref(n), stream), "dump_groups_wire")
+        return _split(buf, [lens[i] for i in range(G)])
 
     def download_stats(self, nbytes, stream=None):
         out = np.empty(nbytes, dtype=np.uint8)

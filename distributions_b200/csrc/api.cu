@@ -932,6 +932,57 @@ int dist_b200_prior_wire_host(dist_b200_ctx *ctx, const void *clustering_msg, si
     return dist_b200_prior_low_entropy_host(ctx, static_cast<int>(dataset_size), G, group_sizes, prior_host);
 }
 
+static int emit_messages(dist_b200_ctx *ctx, const std::vector<uint8_t> &bytes, const std::vector<size_t> &lens, void *out,
+                         size_t capacity, size_t *lens_out, size_t *n_bytes) {
+    if (n_bytes) *n_bytes = bytes.size();
+    if (bytes.size() > capacity) return fail(ctx, DIST_B200_ERR_INVALID, "wire: output buffer too small (size returned in n_bytes)");
+    if (!bytes.empty()) std::memcpy(out, bytes.data(), bytes.size());
+    if (lens_out) for (size_t i = 0; i < lens.size(); ++i) lens_out[i] = lens[i];
+    return DIST_B200_OK;
+}
+
+int dist_b200_wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint32_t *keys, const uint32_t *stats,
+                                 size_t stats_words, void *out, size_t capacity, size_t *lens_out, size_t *n_bytes) {
+    std::vector<uint8_t> bytes;
+    std::vector<size_t> lens;
+    int rc = wire_encode_groups(ctx, model, G, dim, keys, stats, stats_words, bytes, lens);
+    if (rc) return rc;
+    return emit_messages(ctx, bytes, lens, out, capacity, lens_out, n_bytes);
+}
+
+int dist_b200_feature_dump_groups_wire(dist_b200_feature *f, void *out, size_t capacity, size_t *lens_out, size_t *n_bytes,
+                                       void *stream) {
+    if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
+    dist_b200_ctx *ctx = f->ctx;
+    if (!f->stats || f->G < 1) return fail(ctx, DIST_B200_ERR_STATE, "dump_groups_wire: no device statistics (update_all first)");
+    const size_t g = static_cast<size_t>(f->G);
+    size_t words;
+    switch (f->model) {
+        case DIST_B200_NICH: case DIST_B200_GP: words = 3 * g; break;
+        case DIST_B200_BNB: case DIST_B200_BB: words = 2 * g; break;
+        case DIST_B200_DD: case DIST_B200_DPD: words = g * f->dim; break;
+        default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "dump_groups_wire: unsupported model");
+    }
+    std::vector<uint32_t> st(words, 0);
+    size_t got = 0;
+    int rc = dist_b200_feature_download_stats(f, st.data(), 4 * words, &got, stream);  // synchronises
+    if (rc) return rc;
+    if (f->model == DIST_B200_GP) {  // Group::log_prod is a required field of the message
+        if (!f->log_prod_valid) return fail(ctx, DIST_B200_ERR_STATE, "dump_groups_wire: gp log_prod is stale (dist_b200_gp_set_log_prod)");
+        DISTB200_CUDA(ctx, cudaMemcpy(st.data() + 2 * g, f->log_prod_dev, 4 * g, cudaMemcpyDeviceToHost));
+    }
+    // dpd: the caller's key order (update_all's), table rows are in that order too
+    std::vector<uint32_t> keys;
+    if (f->model == DIST_B200_DPD) {
+        keys.resize(f->dim);
+        for (int i = 0; i < f->dim; ++i) keys[f->key_order[i]] = f->keys[i];
+    }
+    std::vector<uint8_t> bytes;
+    std::vector<size_t> lens;
+    if ((rc = wire_encode_groups(ctx, f->model, f->G, f->dim, keys.data(), st.data(), words, bytes, lens))) return rc;
+    return emit_messages(ctx, bytes, lens, out, capacity, lens_out, n_bytes);
+}
+
 int dist_b200_feature_download_stats(const dist_b200_feature *f, void *out_host, size_t capacity_bytes, size_t *n_bytes,
                                      void *stream) {
     if (!f || !f->ctx || !out_host) return DIST_B200_ERR_INVALID;

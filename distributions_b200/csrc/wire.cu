@@ -271,4 +271,71 @@ int wire_decode_clustering(dist_b200_ctx *ctx, const void *msg, size_t len, int 
     return DIST_B200_OK;
 }
 
+// ---- encoder: SoA statistics -> Group messages, canonical proto2 output (fields in number order,
+// repeated scalars unpacked), i.e. byte-identical to what the reference's writer produces
+namespace {
+void put_varint(std::vector<uint8_t> &o, uint64_t v) {
+    while (v >= 0x80) {
+        o.push_back(static_cast<uint8_t>(v) | 0x80);
+        v >>= 7;
+    }
+    o.push_back(static_cast<uint8_t>(v));
+}
+void put_u(std::vector<uint8_t> &o, int field, uint64_t v) {
+    put_varint(o, static_cast<uint64_t>(field) << 3);
+    put_varint(o, v);
+}
+void put_f(std::vector<uint8_t> &o, int field, uint32_t bits) {
+    put_varint(o, (static_cast<uint64_t>(field) << 3) | 5);
+    for (int k = 0; k < 4; ++k) o.push_back(static_cast<uint8_t>(bits >> (8 * k)));
+}
+}  // namespace
+
+int wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint32_t *keys, const uint32_t *stats,
+                       size_t stats_words, std::vector<uint8_t> &out, std::vector<size_t> &lens) {
+    const size_t g = static_cast<size_t>(G);
+    size_t need = 0;
+    switch (model) {
+        case DIST_B200_NICH: case DIST_B200_GP: need = 3 * g; break;
+        case DIST_B200_BNB: case DIST_B200_BB: need = 2 * g; break;
+        case DIST_B200_DD: case DIST_B200_DPD: need = g * static_cast<size_t>(dim); break;
+        default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: model has no Group writer");
+    }
+    if (G < 0 || stats_words < need || (G && !stats) || (model == DIST_B200_DPD && G && !keys))
+        return fail(ctx, DIST_B200_ERR_INVALID, "wire_encode: statistics array too short");
+    out.clear();
+    lens.assign(g, 0);
+    for (size_t i = 0; i < g; ++i) {
+        const size_t start = out.size();
+        switch (model) {
+            case DIST_B200_NICH:  // count, mean, count_times_variance
+                put_u(out, 1, stats[i]);
+                put_f(out, 2, stats[g + i]);
+                put_f(out, 3, stats[2 * g + i]);
+                break;
+            case DIST_B200_GP:  // count, sum, log_prod
+                put_u(out, 1, stats[i]);
+                put_u(out, 2, stats[g + i]);
+                put_f(out, 3, stats[2 * g + i]);
+                break;
+            case DIST_B200_BNB:
+            case DIST_B200_BB:
+                put_u(out, 1, stats[i]);
+                put_u(out, 2, stats[g + i]);
+                break;
+            case DIST_B200_DD:
+                for (int v = 0; v < dim; ++v) put_u(out, 1, stats[i * dim + v]);
+                break;
+            default:  // dpd: sparse (keys, values), non-zero counts in Shared order
+                for (int v = 0; v < dim; ++v)
+                    if (stats[i * dim + v]) put_u(out, 1, keys[v]);
+                for (int v = 0; v < dim; ++v)
+                    if (stats[i * dim + v]) put_u(out, 2, stats[i * dim + v]);
+                break;
+        }
+        lens[i] = out.size() - start;
+    }
+    return DIST_B200_OK;
+}
+
 }  // namespace distb200

@@ -181,6 +181,16 @@ int dist_b200_wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg,
                           const void *const *group_msgs, const size_t *group_lens, int G, float *shared_out,
                           size_t shared_cap, uint32_t *keys_out, size_t keys_cap, uint32_t *stats_out, size_t stats_cap,
                           size_t counts_out[3]);
+/* The way back: the feature's current device-resident statistics as G serialized Group messages,
+ * concatenated into out[capacity]; lens_out[G] (nullable) the length of each, *n_bytes the total (also when
+ * out is too small).  Canonical proto2 output (fields in number order, repeated scalars unpacked): byte-
+ * identical to the reference's writer for the same Groups; dpd groups list their non-zero counts in
+ * Shared.values order.  gp needs a valid log_prod (ERR_STATE otherwise).  Synchronises the stream. */
+int dist_b200_feature_dump_groups_wire(dist_b200_feature *f, void *out, size_t capacity, size_t *lens_out, size_t *n_bytes,
+                                       void *stream);
+/* the encode step alone (no device; ctx may be NULL): stats = the arrays dist_b200_wire_decode returns */
+int dist_b200_wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint32_t *keys, const uint32_t *stats,
+                                 size_t stats_words, void *out, size_t capacity, size_t *lens_out, size_t *n_bytes);
 /* Clustering message (pitman_yor = 1 | low_entropy = 2, schema.proto:36-53) -> the prior vector */
 int dist_b200_prior_wire_host(dist_b200_ctx *ctx, const void *clustering_msg, size_t len, int G,
                               const int32_t *group_sizes, float *prior_host);
