@@ -36,6 +36,20 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(summary):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from a committed ncu --set full summary"""
+    path = os.path.join(ROOT, "profiles", summary)
+    if not os.path.exists(path):
+        return None, None
+    total = 0.0
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(path):
+        parts = line.split()
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(parts[1]) * unit.get(parts[2], 1.0)
+    return total, "profiles/" + summary
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -293,10 +307,13 @@ def run_b200(args):
     if wl["feats"][0]["model"] == "dpd":
         algo_bytes += 4 * (4096 + 1) * G  # the cache table once
     achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_src = (None, None)
+    if wl["name"] == "c2_nich" and not args.sweep:
+        traffic, traffic_src = ncu_traffic("r01_c2_nich_materialised_v2.txt" if args.materialise else "r01_c2_nich_v4_tile32.txt")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "note": "the fused kernel moves 12 B per ROW and is bound by the MUFU pipe, not HBM: the fraction that "
                         "measures kernel quality is roofline_binding.frac (measured MUFU peak)",
-                "traffic": None, "peak_source": peak_src, "kernel": "score_rows_kernel / gather_rows_kernel (fused)",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "score_rows_kernel / gather_rows_kernel (fused)",
                 "algorithmic_bytes_per_launch": int(algo_bytes)}
     # the binding limit of this kernel is not HBM: report the measured pipe it is bound by as well
     mufu = ctx.pipe_peak(0)
