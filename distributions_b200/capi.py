@@ -42,6 +42,8 @@ SIGNATURES = {
     "dist_b200_add_rows_batch": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz, c_p]),
     "dist_b200_add_rows_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz]),
     "dist_b200_remove_rows_batch": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz, c_p]),
+    "dist_b200_rows_accumulate": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz, c_p, c_p]),
+    "dist_b200_rows_merge": (c_i, [c_p, c_p, c_i, c_p, c_i, c_p]),
     "dist_b200_remove_rows_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz]),
     "dist_b200_gp_set_log_prod": (c_i, [c_p, c_p, c_p]),
     "dist_b200_score_data_grid": (c_i, [c_p, c_p, c_sz, c_sz, c_p, c_p]),
@@ -210,6 +212,17 @@ class Context:
         """batched Group::add_value for all features of one kind; nothing is drained, later calls order behind it"""
         F, fa, ca = self._lists(features, columns)
         self.check(self.L.dist_b200_add_rows_batch(self.h, fa, F, ca, _dev_ptr(assign_dev), n_rows, stream), "add_rows_batch")
+
+    def rows_accumulate(self, features, columns, assign_dev, n_rows, xchg_dev, stream=None):
+        """row shards: this rank's accumulators into xchg_dev [F][4][G] float64 (then all-reduce, then rows_merge)"""
+        F, fa, ca = self._lists(features, columns)
+        self.check(self.L.dist_b200_rows_accumulate(self.h, fa, F, ca, _dev_ptr(assign_dev), n_rows, _dev_ptr(xchg_dev), stream),
+                   "rows_accumulate")
+
+    def rows_merge(self, features, xchg_dev, sign=+1, stream=None):
+        F = len(features)
+        fa = (c_p * F)(*[f.h for f in features])
+        self.check(self.L.dist_b200_rows_merge(self.h, fa, F, _dev_ptr(xchg_dev), sign, stream), "rows_merge")
 
     def remove_rows_batch(self, features, columns, assign_dev, n_rows, stream=None):
         """batched Group::remove_value: the rows leave the groups assign_dev names"""

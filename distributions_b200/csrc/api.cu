@@ -627,16 +627,31 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
 // accumulators live in a dedicated context buffer guarded by an event (not the upload scratch), so the
 // call returns without draining the stream; later scoring calls order themselves behind the features'
 // `ready` events.
+// phase: kRowsBoth = accumulate + merge (single GPU); kRowsAccumulate = accumulate and pack into `xchg`
+// ([n_features][4][G] doubles) for an all-reduce; kRowsMerge = merge from the (all-reduced) `xchg`
+enum { kRowsBoth = 0, kRowsAccumulate = 1, kRowsMerge = 2 };
+
 static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
-                      const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, int sign, void *stream) {
+                      const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, int sign, void *stream,
+                      int phase = kRowsBoth, double *xchg = nullptr) {
     if (!ctx) return DIST_B200_ERR_INVALID;
-    if (n_features < 0 || (n_features && (!features || !columns_dev)) || !assign_dev)
+    if (n_features < 0 || (n_features && !features) || (phase != kRowsMerge && ((n_features && !columns_dev) || !assign_dev)))
         return fail(ctx, DIST_B200_ERR_INVALID, "add_rows: null argument");
+    if (phase != kRowsBoth) {
+        if (!xchg) return fail(ctx, DIST_B200_ERR_INVALID, "rows exchange: null exchange buffer");
+        for (int i = 0; i < n_features; ++i) {
+            const dist_b200_feature *f = features[i];
+            if (!f) return fail(ctx, DIST_B200_ERR_INVALID, "rows exchange: null feature");
+            if (f->model == DIST_B200_DD || f->model == DIST_B200_DPD || f->model == DIST_B200_NIW)
+                return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "rows exchange: pooled-statistics models only (nich / gp / bb / bnb)");
+            if (f->G != features[0]->G) return fail(ctx, DIST_B200_ERR_INVALID, "rows exchange: features disagree on the number of groups");
+        }
+    }
     cudaStream_t s = as_stream(stream);
     size_t acc_need = 0;
     for (int i = 0; i < n_features; ++i) {
         dist_b200_feature *f = features[i];
-        if (!f || f->ctx != ctx || !columns_dev[i]) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows: bad feature / column");
+        if (!f || f->ctx != ctx || (phase != kRowsMerge && !columns_dev[i])) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows: bad feature / column");
         if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: niw statistics stay on the host");
         if (f->G < 1 || !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: call update_all first");
         if (f->model == DIST_B200_NICH || f->model == DIST_B200_GP || f->model == DIST_B200_BB || f->model == DIST_B200_BNB)
@@ -662,11 +677,17 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
     b.N = n_rows;
     b.assign = assign_dev;
     b.acc = static_cast<char *>(ctx->add_acc);
+    int flushed = 0;  // pooled features already processed = index of b.d[0] in the exchange buffer
     auto flush = [&]() -> int {
         if (b.n == 0) return DIST_B200_OK;
         b.acc_stride = add_rows_acc_bytes(b.G);
-        int r = launch_add_rows_pooled(ctx, b, s);
-        if (!r) r = launch_merge_prep_batch(ctx, b, s);
+        b.xchg = phase == kRowsMerge ? xchg : nullptr;
+        b.xchg_first = flushed;
+        int r = DIST_B200_OK;
+        if (phase != kRowsMerge) r = launch_add_rows_pooled(ctx, b, s);
+        if (!r && phase == kRowsAccumulate) r = launch_pack_accumulators(ctx, b, xchg, s);
+        if (!r && phase != kRowsAccumulate) r = launch_merge_prep_batch(ctx, b, s);
+        flushed += b.n;
         b.n = 0;
         return r;
     };
@@ -682,7 +703,7 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
                     if ((rc = flush())) return rc;
                 b.G = G;
                 AddDesc &d = b.d[b.n++];
-                d.column = columns_dev[i];
+                d.column = columns_dev ? columns_dev[i] : nullptr;
                 d.st0 = stat_ptr(f, 0);
                 d.st1 = stat_ptr(f, 1);
                 d.st2 = f->model == DIST_B200_NICH ? stat_ptr(f, 2) : nullptr;
@@ -690,7 +711,7 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
                 d.aux = f->aux;
                 for (int k = 0; k < 4; ++k) d.shared[k] = f->shared[k];
                 d.model = f->model;
-                if (f->model == DIST_B200_GP) {
+                if (f->model == DIST_B200_GP && phase != kRowsAccumulate) {
                     f->gp_table_dirty = true;
                     f->log_prod_valid = false;  // Group::log_prod is not maintained by the batched update
                 }
@@ -712,9 +733,25 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
         }
     }
     if ((rc = flush())) return rc;
-    for (int i = 0; i < n_features; ++i) DISTB200_CUDA(ctx, cudaEventRecord(features[i]->ready, s));
+    if (phase != kRowsAccumulate)
+        for (int i = 0; i < n_features; ++i) DISTB200_CUDA(ctx, cudaEventRecord(features[i]->ready, s));
     DISTB200_CUDA(ctx, cudaEventRecord(ctx->add_done, s));
     return DIST_B200_OK;
+}
+
+// Row-sharded update (one process per GPU): every rank accumulates its own rows, the [n_features][4][G] double
+// buffers are summed over the ranks (NCCL all-reduce by the caller), every rank merges the global sums into
+// its replica of the statistics -- all replicas stay identical.
+int dist_b200_rows_accumulate(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                              const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, double *xchg_dev,
+                              void *stream) {
+    return rows_batch(ctx, features, n_features, columns_dev, assign_dev, n_rows, +1, stream, kRowsAccumulate, xchg_dev);
+}
+
+int dist_b200_rows_merge(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features, const double *xchg_dev,
+                         int sign, void *stream) {
+    if (sign != 1 && sign != -1) return ctx ? fail(ctx, DIST_B200_ERR_INVALID, "rows_merge: sign must be +1 or -1") : DIST_B200_ERR_INVALID;
+    return rows_batch(ctx, features, n_features, nullptr, nullptr, 0, sign, stream, kRowsMerge, const_cast<double *>(xchg_dev));
 }
 
 int dist_b200_add_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
@@ -971,11 +1008,11 @@ int dist_b200_feature_dump_groups_wire(dist_b200_feature *f, void *out, size_t c
         if (!f->log_prod_valid) return fail(ctx, DIST_B200_ERR_STATE, "dump_groups_wire: gp log_prod is stale (dist_b200_gp_set_log_prod)");
         DISTB200_CUDA(ctx, cudaMemcpy(st.data() + 2 * g, f->log_prod_dev, 4 * g, cudaMemcpyDeviceToHost));
     }
-    // dpd: the caller's key order (update_all's), table rows are in that order too
+    // dpd: f->keys is update_all's key array, in the caller's order like the mirrored counts
     std::vector<uint32_t> keys;
     if (f->model == DIST_B200_DPD) {
-        keys.resize(f->dim);
-        for (int i = 0; i < f->dim; ++i) keys[f->key_order[i]] = f->keys[i];
+        if (f->keys.size() != static_cast<size_t>(f->dim)) return fail(ctx, DIST_B200_ERR_STATE, "dump_groups_wire: dpd keys missing");
+        keys = f->keys;
     }
     std::vector<uint8_t> bytes;
     std::vector<size_t> lens;

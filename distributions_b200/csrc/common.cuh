@@ -66,6 +66,8 @@ struct AddBatch {
     const int32_t *assign;
     char *acc;                   // per feature: cnt_a[G] | cnt_b[G] (int) | sum_x[G] | sum_xx[G] (double)
     size_t acc_stride;           // bytes per feature
+    const double *xchg;          // merge from an exchanged [feature][4][G] double buffer instead of acc (multi-GPU)
+    int xchg_first;              // index of d[0] in that buffer
     AddDesc d[kAddBatch];
 };
 
@@ -102,8 +104,7 @@ struct dist_b200_feature {
     // hyper-parameters of the last update_all (needed by update_group / add_group)
     float shared[4] = {0, 0, 0, 0};
     std::vector<float> alphas;        // dd alphas / dpd betas
-    std::vector<uint32_t> keys;       // dpd keys, sorted
-    std::vector<int> key_order;       // dpd: position in caller's key order of sorted key i
+    std::vector<uint32_t> keys;       // dpd keys as given to update_all (the order of the counts columns)
     bool keys_dense = false;          // dpd: keys == 0..V-1
     float alpha = 0, beta0 = 0;       // dpd
     float alpha_sum = 0;              // dd
@@ -185,6 +186,7 @@ int launch_gp_table_batch(dist_b200_ctx *ctx, const GpTableBatch &b, cudaStream_
 // pooled models: accumulate `b.n` features in one launch (b.acc zeroed by the launcher), then merge + rebuild caches
 int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s);
 int launch_merge_prep_batch(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t s);  // prep.cu
+int launch_pack_accumulators(dist_b200_ctx *ctx, const AddBatch &b, double *xchg, cudaStream_t s);  // prep.cu
 // dd / dpd: counts updated in place
 int launch_add_rows_counts(dist_b200_ctx *ctx, dist_b200_feature *f, const void *column, const int32_t *assign, size_t N,
                            int sign, cudaStream_t s);

@@ -101,17 +101,29 @@ __global__ void merge_prep_batch_kernel(const AddBatch b, NumericTables t) {
     const AddDesc &d = b.d[blockIdx.y];
     const char *acc = b.acc + b.acc_stride * blockIdx.y;
     const size_t ci = (static_cast<size_t>(b.G) * 4 + 255) / 256 * 256, di = (static_cast<size_t>(b.G) * 8 + 255) / 256 * 256;
-    const int *cnt_a = reinterpret_cast<const int *>(acc);
-    const int *cnt_b = reinterpret_cast<const int *>(acc + ci);
-    const double *sum_x = reinterpret_cast<const double *>(acc + 2 * ci);
-    const double *sum_xx = reinterpret_cast<const double *>(acc + 2 * ci + di);
+    // accumulators of this (feature, group): the launch's own, or the all-reduced exchange buffer
+    // ([feature][4][G] doubles: integers are exact in a double, gp's wrapped uint32 partial sums add mod 2^32)
+    int acc_a, acc_b;
+    double acc_x, acc_xx;
+    if (b.xchg) {
+        const double *x = b.xchg + static_cast<size_t>(b.xchg_first + blockIdx.y) * 4 * b.G;
+        acc_a = static_cast<int>(static_cast<long long>(x[g]));
+        acc_b = static_cast<int>(static_cast<unsigned int>(static_cast<unsigned long long>(x[b.G + g])));
+        acc_x = x[2 * b.G + g];
+        acc_xx = x[3 * b.G + g];
+    } else {
+        acc_a = reinterpret_cast<const int *>(acc)[g];
+        acc_b = reinterpret_cast<const int *>(acc + ci)[g];
+        acc_x = reinterpret_cast<const double *>(acc + 2 * ci)[g];
+        acc_xx = reinterpret_cast<const double *>(acc + 2 * ci + di)[g];
+    }
     if (d.model == DIST_B200_NICH) {
         int32_t *count = reinterpret_cast<int32_t *>(d.st0);
         float *mean = reinterpret_cast<float *>(d.st1), *ctv = reinterpret_cast<float *>(d.st2);
-        const int m = cnt_a[g];
+        const int m = acc_a;
         if (m != 0) {
-            const double mean_b = sum_x[g] / m;
-            const double ctv_b = fmax(sum_xx[g] - m * mean_b * mean_b, 0.0);
+            const double mean_b = acc_x / m;
+            const double ctv_b = fmax(acc_xx - m * mean_b * mean_b, 0.0);
             if (b.sign > 0) {
                 const double n = count[g], tot = n + m;
                 const double delta = mean_b - static_cast<double>(mean[g]);
@@ -139,15 +151,15 @@ __global__ void merge_prep_batch_kernel(const AddBatch b, NumericTables t) {
         }
         nich_prep_one(d.shared[0], d.shared[1], d.shared[2], d.shared[3], count[g], mean[g], ctv[g], d.params + g, d.aux + g, t);
     } else if (d.model == DIST_B200_GP || d.model == DIST_B200_BNB) {
-        const uint32_t c = d.st0[g] + static_cast<uint32_t>(b.sign * cnt_a[g]);
-        const uint32_t sm = d.st1[g] + static_cast<uint32_t>(b.sign) * static_cast<uint32_t>(cnt_b[g]);
+        const uint32_t c = d.st0[g] + static_cast<uint32_t>(b.sign * acc_a);
+        const uint32_t sm = d.st1[g] + static_cast<uint32_t>(b.sign) * static_cast<uint32_t>(acc_b);
         d.st0[g] = c;
         d.st1[g] = sm;
         d.params[g] = d.model == DIST_B200_GP ? gp_prep_one(d.shared[0], d.shared[1], c, sm, t)
                                               : bnb_prep_one(d.shared[0], d.shared[1], d.shared[2], c, sm, t);
     } else {  // bb
         int32_t *heads = reinterpret_cast<int32_t *>(d.st0), *tails = reinterpret_cast<int32_t *>(d.st1);
-        const int32_t h = heads[g] + b.sign * cnt_a[g], tl = tails[g] + b.sign * cnt_b[g];
+        const int32_t h = heads[g] + b.sign * acc_a, tl = tails[g] + b.sign * acc_b;
         heads[g] = h;
         tails[g] = tl;
         d.params[g] = bb_prep_one(d.shared[0], d.shared[1], h, tl, t);
@@ -521,6 +533,29 @@ int launch_bb_prep(dist_b200_ctx *ctx, const float sh[2], int g0, int n, const i
                    const int32_t *tails, float4 *params, cudaStream_t s) {
     if (n <= 0) return DIST_B200_OK;
     bb_prep_kernel<<<blocks_for(n, 128), 128, 0, s>>>(sh[0], sh[1], g0, n, heads, tails, params, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
+// accumulators of one launch -> the exchange layout [feature][4][G] doubles (what an all-reduce can sum)
+__global__ void pack_accumulators_kernel(const AddBatch b, double *__restrict__ xchg) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= b.G) return;
+    const char *acc = b.acc + b.acc_stride * blockIdx.y;
+    const size_t ci = (static_cast<size_t>(b.G) * 4 + 255) / 256 * 256, di = (static_cast<size_t>(b.G) * 8 + 255) / 256 * 256;
+    double *x = xchg + static_cast<size_t>(b.xchg_first + blockIdx.y) * 4 * b.G;
+    const int model = b.d[blockIdx.y].model;
+    x[g] = static_cast<double>(reinterpret_cast<const int *>(acc)[g]);
+    const int cb = reinterpret_cast<const int *>(acc + ci)[g];
+    // gp / bnb: the sum accumulator is a wrapped uint32; bb: a plain count
+    x[b.G + g] = (model == DIST_B200_GP || model == DIST_B200_BNB) ? static_cast<double>(static_cast<unsigned int>(cb)) : static_cast<double>(cb);
+    x[2 * b.G + g] = reinterpret_cast<const double *>(acc + 2 * ci)[g];
+    x[3 * b.G + g] = reinterpret_cast<const double *>(acc + 2 * ci + di)[g];
+}
+
+int launch_pack_accumulators(dist_b200_ctx *ctx, const AddBatch &b, double *xchg, cudaStream_t s) {
+    if (b.n <= 0 || b.G <= 0) return DIST_B200_OK;
+    pack_accumulators_kernel<<<dim3(blocks_for(b.G, 128), b.n), 128, 0, s>>>(b, xchg);
     LAUNCH_CHECK(ctx);
     return DIST_B200_OK;
 }

@@ -5,6 +5,8 @@ Two partitionings:
 * row shards  -- rows are independent given frozen statistics (examples/mixture/main.py:143-160):
   caches and prior are replicated, each rank scores + samples its own contiguous row range.
   NO data-path collective.
+* row shards, update row -- batched add_value / remove_value: every rank accumulates its rows, ONE
+  all-reduce(sum) of the [F][4][G] accumulators, every rank merges the global sums (row_sharded_update).
 * feature shards of one cross-cat kind -- scores[n][g] = prior[g] + sum_f s_f[n][g] is a sum over
   features: rank k scores its features into a partial [rows][G] (the prior is added by exactly one
   rank), ONE reduce-scatter(sum) over row blocks leaves rank k with the fully reduced rows of block k,
@@ -119,6 +121,20 @@ def feature_sharded_score_sample(score_partial, sample_block, n_rows, n_groups, 
     if pending is not None:
         finish(pending)
     return owned_assign, owned_rows
+
+
+def row_sharded_update(accumulate, merge, xchg, sign=+1, group=None):
+    """The update row (batched add_value / remove_value) under ROW shards: statistics are replicated, every
+    rank holds a slice of the rows, so the per-group accumulators must be summed over the ranks before the merge.
+
+    accumulate(xchg)    writes this rank's accumulators of its own rows into xchg ([F][4][G] float64)
+    merge(xchg, sign)   merges summed accumulators into this rank's replica of the statistics
+    One all-reduce(sum) in between; afterwards all replicas hold the same statistics (integers exactly; the
+    float64 sums in the reduction order of the backend, identical on every rank)."""
+    accumulate(xchg)
+    dist.all_reduce(xchg, op=dist.ReduceOp.SUM, group=group)
+    merge(xchg, sign)
+    return xchg
 
 
 class PeerFeatureShards:

@@ -144,6 +144,17 @@ int dist_b200_remove_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *fe
                                 const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, void *stream);
 int dist_b200_remove_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
                                      const void *const *columns_host, const int32_t *assign_host, size_t n_rows);
+/* Row shards (one process per GPU, rows partitioned, statistics replicated): the update has a real exchange
+ * step.  Every rank accumulates its own rows into xchg_dev -- [n_features][4][G] doubles per feature:
+ * count-like a, count-like b, sum x, sum x^2 (integers exact) --, the caller sums the buffers over the ranks
+ * (one NCCL all-reduce of float64), and every rank merges the global sums into its replica (sign +1 add_value,
+ * -1 remove_value), leaving all replicas bit-identical.  Pooled-statistics models only (nich / gp / bb / bnb),
+ * all features with the same G. */
+int dist_b200_rows_accumulate(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
+                              const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, double *xchg_dev,
+                              void *stream);
+int dist_b200_rows_merge(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features, const double *xchg_dev,
+                         int sign, void *stream);
 /* Host-buffer form (the call a reference-side binding makes): columns_host[i] holds n_rows values of
  * features[i] (float / uint32 / int32, bool as uint8), assign_host the packed group ids.  Synchronous. */
 int dist_b200_add_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,

@@ -83,3 +83,63 @@ def test_feature_shards_two_gpus(tmp_path, oracle):
         assert got.min() >= 0
         assert cases.explained_mismatch(full.astype(np.float64), cc["u"], got, want, 2e-5).all()
         assert np.mean(got == want) > 0.995
+
+
+# ---- row shards: the update row (batched add_value) with its all-reduce -----------------------------
+def _update_worker(rank, world, port, n, G, out_dir):
+    import torch.distributed as dist
+    from distributions_b200 import capi, sharding, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ws = [synth.nich(701, G, n), synth.gp(702, G, n), synth.bb(703, G, n), synth.bnb(704, G, n, r=2)]
+    ids = [capi.NICH, capi.GP, capi.BB, capi.BNB]
+    assign = np.random.default_rng(12).integers(0, G, n).astype(np.int32)
+    lo, hi = sharding.row_shard(n, rank, world)
+    ctx = capi.Context(rank)
+    feats = [ctx.feature(i).update_all(w) for i, w in zip(ids, ws)]
+    cols = [torch.from_numpy(np.ascontiguousarray(w["values"][lo:hi], dtype=capi.COLUMN_DTYPE[i])).to(dev) for i, w in zip(ids, ws)]
+    a_dev = torch.from_numpy(assign[lo:hi].copy()).to(dev)
+    xchg = torch.zeros((len(feats), 4, G), dtype=torch.float64, device=dev)
+    sharding.row_sharded_update(lambda x: ctx.rows_accumulate(feats, cols, a_dev, hi - lo, x),
+                                lambda x, sign: ctx.rows_merge(feats, x, sign), xchg, +1)
+    torch.cuda.synchronize()
+    out = {}
+    for k, (f, nb, rows) in enumerate(zip(feats, (12 * G, 8 * G, 8 * G, 8 * G), (4, 3, 2, 3))):
+        out["stats%d" % k] = f.download_stats(nb)
+        out["caches%d" % k] = f.download_caches(rows)
+    np.savez(os.path.join(out_dir, "upd%d.npz" % rank), **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_update_two_gpus(tmp_path):
+    """two ranks, each with half of the rows: after accumulate -> all-reduce -> merge both replicas hold the
+    statistics a single GPU gets from all rows"""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    import torch.multiprocessing as mp
+    from distributions_b200 import capi, synth
+    world, n, G = 2, 6001, 33
+    port = 29700 + os.getpid() % 1000
+    mp.spawn(_update_worker, args=(world, port, n, G, str(tmp_path)), nprocs=world, join=True)
+    ws = [synth.nich(701, G, n), synth.gp(702, G, n), synth.bb(703, G, n), synth.bnb(704, G, n, r=2)]
+    ids = [capi.NICH, capi.GP, capi.BB, capi.BNB]
+    assign = np.random.default_rng(12).integers(0, G, n).astype(np.int32)
+    ctx = capi.Context(0)
+    feats = [ctx.feature(i).update_all(w) for i, w in zip(ids, ws)]
+    cols = [torch.from_numpy(np.ascontiguousarray(w["values"], dtype=capi.COLUMN_DTYPE[i])).cuda() for i, w in zip(ids, ws)]
+    ctx.add_rows_batch(feats, cols, torch.from_numpy(assign).cuda(), n)
+    d = [np.load(os.path.join(str(tmp_path), "upd%d.npz" % r)) for r in range(world)]
+    for k, (f, nb, rows) in enumerate(zip(feats, (12 * G, 8 * G, 8 * G, 8 * G), (4, 3, 2, 3))):
+        single = f.download_stats(nb)
+        assert np.array_equal(d[0]["stats%d" % k], d[1]["stats%d" % k])          # replicas bit-identical
+        assert np.array_equal(d[0]["caches%d" % k], d[1]["caches%d" % k])
+        if k == 0:  # nich: counts exact, float statistics up to the summation order of the double accumulators
+            assert np.array_equal(d[0]["stats0"][:4 * G], single[:4 * G])
+            np.testing.assert_allclose(d[0]["stats0"][4 * G:].view(np.float32), single[4 * G:].view(np.float32), rtol=1e-6, atol=1e-6)
+        else:
+            assert np.array_equal(d[0]["stats%d" % k], single)
+    ctx.close()

@@ -95,3 +95,43 @@ def test_feature_sharded_matches_single_process(tmp_path, n, tile_rows):
     ok = cases.explained_mismatch(full.astype(np.float64), cc["u"], got, want, 2e-5)
     assert ok.all()
     assert np.mean(got == want) > 0.99
+
+
+# ---- row-sharded update row (batched add_value): accumulate -> all-reduce -> merge -----------------
+def _update_worker(rank, world, port, n, G, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = synth.gp(515, G, n)
+    assign = np.random.default_rng(3).integers(0, G, n)
+    lo, hi = sharding.row_shard(n, rank, world)
+    stats = {"count": w["count"].astype(np.int64), "sum": w["sum"].astype(np.int64)}  # this rank's replica
+
+    def accumulate(xchg):  # stand-in for dist_b200_rows_accumulate: [F=1][4][G] float64
+        x = xchg.numpy()
+        x[:] = 0
+        x[0, 0] = np.bincount(assign[lo:hi], minlength=G)
+        x[0, 1] = np.bincount(assign[lo:hi], weights=w["values"][lo:hi].astype(np.float64), minlength=G)
+
+    def merge(xchg, sign):  # stand-in for dist_b200_rows_merge
+        x = xchg.numpy()
+        stats["count"] += sign * x[0, 0].astype(np.int64)
+        stats["sum"] += sign * x[0, 1].astype(np.int64)
+
+    xchg = torch.zeros((1, 4, G), dtype=torch.float64)
+    sharding.row_sharded_update(accumulate, merge, xchg, +1)
+    np.savez(os.path.join(out_dir, "upd%d.npz" % rank), count=stats["count"], sum=stats["sum"])
+    dist.destroy_process_group()
+
+
+def test_row_sharded_update_replicas_agree(tmp_path):
+    world, n, G = 2, 3001, 17
+    port = 29800 + os.getpid() % 1000
+    mp.spawn(_update_worker, args=(world, port, n, G, str(tmp_path)), nprocs=world, join=True)
+    w = synth.gp(515, G, n)
+    assign = np.random.default_rng(3).integers(0, G, n)
+    count = w["count"].astype(np.int64) + np.bincount(assign, minlength=G)
+    total = w["sum"].astype(np.int64) + np.bincount(assign, weights=w["values"].astype(np.float64), minlength=G).astype(np.int64)
+    for r in range(world):
+        d = np.load(os.path.join(str(tmp_path), "upd%d.npz" % r))
+        assert np.array_equal(d["count"], count) and np.array_equal(d["sum"], total)
