@@ -1,0 +1,63 @@
+"""Host-side Group bookkeeping of the Python mirror (distributions_b200/models.py) against the reference's
+Group::add_value / remove_value as restated by the oracle (pinned to the compiled reference in
+tests/test_oracle.py): the fp32 Welford updates of nich must match bit for bit, the integer models exactly.
+No device needed."""
+import numpy as np
+
+from distributions_b200 import models
+
+
+def test_nich_group_arithmetic_is_the_references(oracle):
+    rng = np.random.default_rng(0)
+    shared = models.nich.Shared()
+    g = models.nich.Group()
+    g.init(shared)
+    state = (0, 0.0, 0.0)
+    held = []
+    for step in range(400):
+        if held and rng.random() < 0.35:
+            v = held.pop(int(rng.integers(0, len(held))))
+            g.remove_value(shared, v)
+            state = oracle.nich_group_update(-1, state[0], state[1], state[2], [v])
+        else:
+            v = float(np.float32(rng.normal(3.0, 10.0)))
+            held.append(v)
+            g.add_value(shared, v)
+            state = oracle.nich_group_update(+1, state[0], state[1], state[2], [v])
+        assert g.count == state[0]
+        assert np.float32(g.mean).view(np.uint32) == np.float32(state[1]).view(np.uint32), (step, g.mean, state[1])
+        assert np.float32(g.count_times_variance).view(np.uint32) == np.float32(state[2]).view(np.uint32), (step,)
+
+
+def test_count_sum_groups_wrap_like_uint32(oracle):
+    shared = models.gp.Shared()
+    g = models.gp.Group()
+    g.init(shared)
+    state = (0, 0, 0.0)
+    for v in [5, 0, 4000000000, 4000000000, 17]:
+        g.add_value(shared, v)
+        state = oracle.gp_group_update(+1, state[0], state[1], state[2], [v])
+        assert (g.count, g.sum) == (state[0], state[1])
+    for v in [4000000000, 5]:
+        g.remove_value(shared, v)
+        state = oracle.gp_group_update(-1, state[0], state[1], state[2], [v])
+        assert (g.count, g.sum) == (state[0], state[1])
+
+
+def test_bb_dd_groups_and_containers():
+    sb = models.bb.Shared()
+    g = models.bb.Group()
+    g.init(sb)
+    for v in (True, False, False, True, True):
+        g.add_value(sb, v)
+    g.remove_value(sb, True)
+    assert (g.heads, g.tails) == (2, 2)
+    sd = models.dd.Shared(dim=4)
+    d = models.dd.Group()
+    d.init(sd)
+    for v in (0, 3, 3, 1):
+        d.add_value(sd, v)
+    d.remove_value(sd, 3)
+    assert d.counts.tolist() == [1, 1, 0, 1]
+    assert models.nich.Shared(mu=1.5).dump() == {"mu": 1.5, "kappa": 1.0, "sigmasq": 1.0, "nu": 1.0}
+    assert set(models.MODELS) == {"nich", "gp", "bnb", "bb", "dd"}
