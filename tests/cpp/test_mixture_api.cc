@@ -136,6 +136,25 @@ int main(int argc, char ** argv) {
                 std::printf("model gp\n");
                 run_script<GammaPoisson>(ctx, in, GammaPoisson::Shared::EXAMPLE(),
                                          [](std::istream & s) { uint32_t v; s >> v; return v; });
+            } else if (line == "model bnb") {
+                std::printf("model bnb\n");
+                BetaNegativeBinomial::Shared sh = BetaNegativeBinomial::Shared::EXAMPLE();
+                sh.r = 3;
+                run_script<BetaNegativeBinomial>(ctx, in, sh, [](std::istream & s) { uint32_t v; s >> v; return v; });
+            } else if (line == "lowentropy") {  // lowentropy <dataset_size> <G> then G group sizes: the prior vector
+                std::getline(in, line);
+                std::istringstream ls(line);
+                int32_t dataset_size;
+                size_t G;
+                ls >> dataset_size >> G;
+                LowEntropy model{dataset_size};
+                LowEntropy::Mixture driver(ctx);
+                driver.counts().resize(G);
+                for (auto & c : driver.counts()) ls >> c;
+                driver.init(model);
+                std::vector<float> scores(G, 0.f);
+                driver.score_value(model, Floats(scores));
+                print_vec("low_entropy", scores);
             } else if (line == "model bb") {
                 std::printf("model bb\n");
                 run_script<BetaBernoulli>(ctx, in, BetaBernoulli::Shared::EXAMPLE(),

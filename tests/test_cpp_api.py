@@ -35,13 +35,13 @@ class Replay:
         self.groups, self.counts = [], []
 
     def empty(self):
-        return {"nich": (0, 0.0, 0.0), "gp": (0, 0), "bb": [0, 0], "dd": [0] * 16}[self.model]
+        return {"nich": (0, 0.0, 0.0), "gp": (0, 0), "bnb": (0, 0), "bb": [0, 0], "dd": [0] * 16}[self.model]
 
     def upd(self, st, v, op):
         m = self.model
         if m == "nich":
             return self.o.nich_group_update(op, st[0], st[1], st[2], [v])
-        if m == "gp":
+        if m in ("gp", "bnb"):
             return (st[0] + op, st[1] + op * int(v))
         if m == "bb":
             st = list(st); st[0 if v else 1] += op; return st
@@ -73,6 +73,10 @@ class Replay:
             st = np.array(self.groups, dtype=np.float64)
             w = dict(model=m, sizes=sizes, shared=np.array([0, 1, 1, 1], np.float32), count=st[:, 0].astype(np.int32),
                      mean=st[:, 1].astype(np.float32), ctv=st[:, 2].astype(np.float32))
+        elif m == "bnb":
+            st = np.array(self.groups, dtype=np.int64)
+            w = dict(model=m, sizes=sizes, shared=np.array([1.0, 1.0, 3], np.float32), count=st[:, 0].astype(np.uint32),
+                     sum=st[:, 1].astype(np.uint32))
         elif m == "bb":
             st = np.array(self.groups, dtype=np.int32)
             w = dict(model=m, sizes=sizes, shared=np.array([0.5, 2.0], np.float32), heads=st[:, 0].copy(), tails=st[:, 1].copy())
@@ -83,7 +87,7 @@ class Replay:
 
     def scores(self, values):
         import cases
-        from oracle.pyoracle import BB, DD, GP, NICH
+        from oracle.pyoracle import BB, BNB, DD, GP, NICH
         o, m, G = self.o, self.model, len(self.groups)
         prior = o.py_prior(1.0, 0.1, self.counts)
         out = np.tile(prior, (len(values), 1)).astype(np.float32)
@@ -94,6 +98,9 @@ class Replay:
         elif m == "gp":
             st = np.array(self.groups, dtype=np.int64)
             o.score_rows(GP, o.gp_caches([1, 1], st[:, 0], st[:, 1]), np.asarray(values, np.uint32), out)
+        elif m == "bnb":
+            st = np.array(self.groups, dtype=np.int64)
+            o.score_rows(BNB, o.bnb_caches([1.0, 1.0, 3], st[:, 0], st[:, 1]), np.asarray(values, np.uint32), out)
         elif m == "bb":
             st = np.array(self.groups, dtype=np.int32)
             o.score_rows(BB, o.bb_caches([0.5, 2.0], st[:, 0], st[:, 1]), np.asarray(values, np.uint8), out)
@@ -106,7 +113,7 @@ class Replay:
 def _value(rng, model):
     if model == "nich":
         return float(np.float32(rng.normal(0, 3)))
-    if model == "gp":
+    if model in ("gp", "bnb"):
         return int(rng.poisson(6))
     if model == "bb":
         return int(rng.random() < 0.4)
@@ -122,7 +129,7 @@ def test_cpp_mixture_choreography(tmp_path, oracle):
     exe = _compile(str(tmp_path / "test_mixture_api"))
     rng = np.random.default_rng(42)
     lines, replays, expected = [], {}, []
-    for model in ("nich", "gp", "bb", "dd"):
+    for model in ("nich", "gp", "bb", "dd", "bnb"):
         rp = Replay(model, oracle)
         lines.append("model %s" % model)
         G0 = 6
@@ -189,6 +196,9 @@ def test_cpp_mixture_choreography(tmp_path, oracle):
             expected.append((model, "scoredata", None, (None, rp.score_data())))
         lines.append("end")
         replays[model] = rp
+    le_sizes = [3, 0, 17, 1, 250, 0, 42]
+    lines.append("lowentropy")
+    lines.append("5000 %d %s" % (len(le_sizes), " ".join(str(c) for c in le_sizes)))
     script = tmp_path / "script.txt"
     script.write_text("\n".join(lines) + "\n")
     out = subprocess.run([exe, str(script)], capture_output=True, text=True, timeout=300)
@@ -199,7 +209,7 @@ def test_cpp_mixture_choreography(tmp_path, oracle):
     LOG_STEP = 6.2e-5
 
     def tol(model, want):
-        extra = 25 * LOG_STEP if model == "nich" else (6e-5 if model == "gp" else 0.0)
+        extra = 25 * LOG_STEP if model == "nich" else (6e-5 if model in ("gp", "bnb") else 0.0)
         return 4e-6 * (1 + np.abs(want)) + extra
 
     for model, kind, payload, (prior, want) in expected:
@@ -237,3 +247,6 @@ def test_cpp_mixture_choreography(tmp_path, oracle):
             assert cases.explained_mismatch(got.astype(np.float64), u, assign, a_orc, 2e-5).all()
             row = next(it)
             assert row == ["batch_matches_per_value", "1"]
+    row = next(it)
+    assert row[0] == "low_entropy"
+    assert np.array_equal(np.array(row[1:], np.float32), oracle.low_entropy_prior(5000, le_sizes))
