@@ -455,9 +455,12 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                     float s = 0.f;
 #pragma unroll
                     for (int j = 0; j < CHUNK; ++j) s += mufu_ex2(fmaf(acc[j], kLog2e, nm));
-                    const float nn = fminf(slot_m, nm);
-                    slot_s = slot_s * mufu_ex2(nn - slot_m) + s * mufu_ex2(nn - nm);
-                    slot_m = nn;
+                    // rescale to the smaller nm (the larger maximum): one of the two factors is 2^0 = 1, so a
+                    // single EX2 of -|difference| serves (slot_m = +inf on a fresh slot gives e = 0, slot_s = 0)
+                    const float dlt = slot_m - nm;
+                    const float e = mufu_ex2(-fabsf(dlt));
+                    slot_s = dlt > 0.f ? fmaf(slot_s, e, s) : fmaf(s, e, slot_s);
+                    slot_m = fminf(slot_m, nm);
                     if ((it + 1) % chunks_per_slot == 0 || it + 1 == nchunks) {
                         slots[(it / chunks_per_slot) * kThreads + tid] = make_float2(slot_m, slot_s);
                         slot_m = INFINITY;
