@@ -473,13 +473,14 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                         float total = 0.f;
                         for (int k = 0; k < nslots; ++k) {
                             const float2 ms = slots[k * kThreads + tid];
-                            total += ms.y * mufu_ex2(mm - ms.x);
+                            const float w = ms.y * mufu_ex2(mm - ms.x);
+                            slots[k * kThreads + tid].y = w;  // the walk below reads the rescaled mass back: no second EX2
+                            total += w;
                         }
                         float t = total * urow;
                         sel = nslots - 1;
                         for (int k = 0; k < nslots; ++k) {
-                            const float2 ms = slots[k * kThreads + tid];
-                            const float w = ms.y * mufu_ex2(mm - ms.x);
+                            const float w = slots[k * kThreads + tid].y;
                             if (t <= w) {
                                 sel = k;
                                 break;
