@@ -143,3 +143,36 @@ def test_update_all_wire_equals_update_all(wire, oracle, name):
         assert np.array_equal(ctx.prior_wire_host(wire["clustering_le"].tobytes(), sizes), ctx.prior_low_entropy_host(100000, sizes))
     finally:
         ctx.close()
+
+
+def test_decoder_survives_garbage(wire):
+    """a parser of external bytes must reject, never crash: random strings, truncations and bit flips of valid
+    messages for every model (the process surviving this test is the assertion)"""
+    rng = np.random.default_rng(2024)
+    outcomes = {"ok": 0, "rejected": 0}
+    for name in sorted(cases.WIRE):
+        sh_msg, g_msgs = messages(wire, name)
+        variants = []
+        for _ in range(150):
+            variants.append((bytes(rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8)), g_msgs))          # random Shared
+            variants.append((sh_msg, [bytes(rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8))]))       # random Group
+            cut = int(rng.integers(0, len(sh_msg) + 1))
+            variants.append((sh_msg[:cut], g_msgs))                                                                  # truncated Shared
+            g = bytearray(g_msgs[int(rng.integers(0, len(g_msgs)))])
+            if g:
+                g[int(rng.integers(0, len(g)))] ^= 1 << int(rng.integers(0, 8))                                      # bit flip
+            variants.append((sh_msg, [bytes(g)] + g_msgs[1:]))
+            s = bytearray(sh_msg)
+            s[int(rng.integers(0, len(s)))] ^= 1 << int(rng.integers(0, 8))
+            variants.append((bytes(s), g_msgs))
+        variants.append((b"", []))
+        variants.append((b"\x0a" + b"\xff" * 9 + b"\x7f", g_msgs))   # absurd length prefix
+        variants.append((b"\xff" * 64, g_msgs))                        # endless varint
+        for s_msg, gs in variants:
+            try:
+                sh, keys, st = capi.wire_decode(IDS[name], s_msg, gs)
+                assert np.all(np.isfinite(sh) | ~np.isfinite(sh))  # touch the outputs
+                outcomes["ok"] += 1
+            except ValueError:
+                outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 1000 and outcomes["ok"] > 0
