@@ -51,6 +51,8 @@ SIGNATURES = {
     "dist_b200_update_all_wire": (c_i, [c_p, c_p, c_sz, c_p, c_p, c_i, c_p]),
     "dist_b200_wire_decode": (c_i, [c_p, c_i, c_p, c_sz, c_p, c_p, c_i, c_p, c_sz, c_p, c_sz, c_p, c_sz, c_p]),
     "dist_b200_prior_wire_host": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p]),
+    "dist_b200_update_all_stream": (c_i, [c_p, c_p, c_sz, c_p, c_sz, c_p]),
+    "dist_b200_wire_split_stream": (c_i, [c_p, c_p, c_sz, c_p, c_p, c_sz, c_p]),
     "dist_b200_feature_dump_groups_wire": (c_i, [c_p, c_p, c_sz, c_p, c_p, c_p]),
     "dist_b200_wire_encode_groups": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_sz, c_p, c_sz, c_p, c_p]),
     "dist_b200_feature_download_stats": (c_i, [c_p, c_p, c_sz, ctypes.POINTER(c_sz), c_p]),
@@ -142,6 +144,20 @@ def _split(buf, lens):
     offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     raw = buf.tobytes()
     return [raw[offs[i]:offs[i + 1]] for i in range(len(lens))]
+
+
+def wire_split_stream(stream_bytes):
+    """records of a [uint32 length][message] stream (the reference's protobuf_stream format): list of bytes"""
+    L = lib()
+    n = c_sz()
+    rc = L.dist_b200_wire_split_stream(None, stream_bytes, len(stream_bytes), None, None, 0, ctypes.byref(n))
+    if rc not in (0, 1) or (rc == 1 and n.value == 0):
+        raise ValueError("wire_split_stream: status %d" % rc)
+    offs, lens = (c_sz * max(n.value, 1))(), (c_sz * max(n.value, 1))()
+    rc = L.dist_b200_wire_split_stream(None, stream_bytes, len(stream_bytes), offs, lens, n.value, ctypes.byref(n))
+    if rc != 0:
+        raise ValueError("wire_split_stream: status %d" % rc)
+    return [stream_bytes[offs[i]:offs[i] + lens[i]] for i in range(n.value)]
 
 
 def wire_encode_groups(model, G, dim, keys, stats):
@@ -461,6 +477,12 @@ class Feature:
         lens = (c_sz * max(G, 1))(*[len(m) for m in group_msgs])
         self.ctx.check(self.ctx.L.dist_b200_update_all_wire(self.h, shared_msg, len(shared_msg), ptrs, lens, G, stream),
                        "update_all_wire")
+        return self
+
+    def update_all_stream(self, shared_msg, stream_bytes, stream=None):
+        """Groups as one [uint32 length][message] record stream (distributions.io.stream.protobuf_stream_dump)"""
+        self.ctx.check(self.ctx.L.dist_b200_update_all_stream(self.h, shared_msg, len(shared_msg), stream_bytes, len(stream_bytes), stream),
+                       "update_all_stream")
         return self
 
     def dump_groups_wire(self, stream=None):

@@ -956,6 +956,51 @@ int dist_b200_update_all_wire(dist_b200_feature *f, const void *shared_msg, size
     }
 }
 
+// the reference's record stream (distributions/io/stream.py:141-153): [uint32 little-endian length][message] ...
+static int split_stream(dist_b200_ctx *ctx, const void *bytes, size_t len, std::vector<const void *> &msgs,
+                        std::vector<size_t> &lens) {
+    const uint8_t *p = static_cast<const uint8_t *>(bytes), *end = p + len;
+    while (p < end) {
+        if (end - p < 4) return fail(ctx, DIST_B200_ERR_INVALID, "wire stream: truncated record length");
+        const size_t n = static_cast<size_t>(p[0]) | (static_cast<size_t>(p[1]) << 8) | (static_cast<size_t>(p[2]) << 16) |
+                         (static_cast<size_t>(p[3]) << 24);
+        p += 4;
+        if (n > static_cast<size_t>(end - p)) return fail(ctx, DIST_B200_ERR_INVALID, "wire stream: record runs past the end");
+        msgs.push_back(p);
+        lens.push_back(n);
+        p += n;
+    }
+    return DIST_B200_OK;
+}
+
+int dist_b200_wire_split_stream(dist_b200_ctx *ctx, const void *stream_bytes, size_t stream_len, size_t *offsets_out,
+                                size_t *lens_out, size_t capacity, size_t *n_records) {
+    if ((!stream_bytes && stream_len) || !n_records) return DIST_B200_ERR_INVALID;  // ctx may be null
+    std::vector<const void *> msgs;
+    std::vector<size_t> lens;
+    int rc = split_stream(ctx, stream_bytes, stream_len, msgs, lens);
+    if (rc) return rc;
+    *n_records = msgs.size();
+    if (msgs.size() > capacity) return fail(ctx, DIST_B200_ERR_INVALID, "wire_split_stream: output arrays too small (count returned)");
+    for (size_t i = 0; i < msgs.size(); ++i) {
+        if (offsets_out) offsets_out[i] = static_cast<size_t>(static_cast<const uint8_t *>(msgs[i]) - static_cast<const uint8_t *>(stream_bytes));
+        if (lens_out) lens_out[i] = lens[i];
+    }
+    return DIST_B200_OK;
+}
+
+int dist_b200_update_all_stream(dist_b200_feature *f, const void *shared_msg, size_t shared_len, const void *stream_bytes,
+                                size_t stream_len, void *stream) {
+    if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
+    if (!stream_bytes && stream_len) return fail(f->ctx, DIST_B200_ERR_INVALID, "update_all_stream: null stream");
+    std::vector<const void *> msgs;
+    std::vector<size_t> lens;
+    int rc = split_stream(f->ctx, stream_bytes, stream_len, msgs, lens);
+    if (rc) return rc;
+    if (msgs.size() > 0x7FFFFFFFull) return fail(f->ctx, DIST_B200_ERR_UNSUPPORTED, "update_all_stream: too many groups");
+    return dist_b200_update_all_wire(f, shared_msg, shared_len, msgs.data(), lens.data(), static_cast<int>(msgs.size()), stream);
+}
+
 int dist_b200_prior_wire_host(dist_b200_ctx *ctx, const void *clustering_msg, size_t len, int G,
                               const int32_t *group_sizes, float *prior_host) {
     if (!ctx || !clustering_msg || !group_sizes || !prior_host || G < 1) return DIST_B200_ERR_INVALID;

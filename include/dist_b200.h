@@ -184,6 +184,14 @@ int dist_b200_score_data_grid_host(dist_b200_feature *f, const float *shareds_ho
  * DIST_B200_ERR_UNSUPPORTED.  niw: unsupported. */
 int dist_b200_update_all_wire(dist_b200_feature *f, const void *shared_msg, size_t shared_len,
                               const void *const *group_msgs, const size_t *group_lens, int G, void *stream);
+/* The same with the Groups as one record stream of the reference's dumps (distributions/io/stream.py:141-153,
+ * after decompression): [uint32 little-endian length][Group message] repeated; G = the number of records. */
+int dist_b200_update_all_stream(dist_b200_feature *f, const void *shared_msg, size_t shared_len, const void *stream_bytes,
+                                size_t stream_len, void *stream);
+/* record boundaries of such a stream (no device; ctx may be NULL): offsets_out / lens_out[capacity] (nullable),
+ * *n_records the count (also when capacity is too small) */
+int dist_b200_wire_split_stream(dist_b200_ctx *ctx, const void *stream_bytes, size_t stream_len, size_t *offsets_out,
+                                size_t *lens_out, size_t capacity, size_t *n_records);
 /* The decode step alone (no device): shared_out = Shared floats (nich 4; gp 2; bb 2; bnb alpha, beta, r;
  * dd alphas; dpd gamma, alpha, beta0, betas[V]), keys_out = dpd Shared.values (bnb: r), stats_out = the
  * update_all arrays back to back, floats as bit patterns (gp: count | sum | log_prod).  counts_out receives the

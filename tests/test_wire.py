@@ -130,6 +130,9 @@ def test_update_all_wire_equals_update_all(wire, oracle, name):
         assert np.array_equal(a.download_caches(rows).view(np.uint32), b.download_caches(rows).view(np.uint32))
         nbytes = 4 * expected(name)[3].size if name != "gp" else 8 * w["count"].size
         assert np.array_equal(a.download_stats(nbytes), b.download_stats(nbytes))
+        import struct
+        c = ctx.feature(IDS[name]).update_all_stream(sh_msg, b"".join(struct.pack("<I", len(m)) + m for m in g_msgs))
+        assert np.array_equal(a.download_caches(rows).view(np.uint32), c.download_caches(rows).view(np.uint32))
         dumped = b.dump_groups_wire()
         if name == "dpd":
             assert np.array_equal(capi.wire_decode(IDS[name], sh_msg, dumped)[2], expected(name)[3])
@@ -143,6 +146,19 @@ def test_update_all_wire_equals_update_all(wire, oracle, name):
         assert np.array_equal(ctx.prior_wire_host(wire["clustering_le"].tobytes(), sizes), ctx.prior_low_entropy_host(100000, sizes))
     finally:
         ctx.close()
+
+
+def test_record_stream_split(wire):
+    """the reference's dump framing (io/stream.py:141-153): struct.pack('<I', len) + message"""
+    import struct
+    _, g_msgs = messages(wire, "gp")
+    blob = b"".join(struct.pack("<I", len(m)) + m for m in g_msgs)
+    assert capi.wire_split_stream(blob) == g_msgs
+    assert capi.wire_split_stream(b"") == []
+    with pytest.raises(ValueError):
+        capi.wire_split_stream(blob[:-1])         # last record cut short
+    with pytest.raises(ValueError):
+        capi.wire_split_stream(blob + b"\x01\x00")  # dangling length prefix
 
 
 def test_decoder_survives_garbage(wire):
