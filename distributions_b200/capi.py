@@ -52,6 +52,7 @@ SIGNATURES = {
     "dist_b200_wire_decode": (c_i, [c_p, c_i, c_p, c_sz, c_p, c_p, c_i, c_p, c_sz, c_p, c_sz, c_p, c_sz, c_p]),
     "dist_b200_prior_wire_host": (c_i, [c_p, c_p, c_sz, c_i, c_p, c_p]),
     "dist_b200_update_all_stream": (c_i, [c_p, c_p, c_sz, c_p, c_sz, c_p]),
+    "dist_b200_wire_encode_shared": (c_i, [c_p, c_i, c_p, c_sz, c_p, c_sz, c_p, c_sz, c_p]),
     "dist_b200_wire_split_stream": (c_i, [c_p, c_p, c_sz, c_p, c_p, c_sz, c_p]),
     "dist_b200_feature_dump_groups_wire": (c_i, [c_p, c_p, c_sz, c_p, c_p, c_p]),
     "dist_b200_wire_encode_groups": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_sz, c_p, c_sz, c_p, c_p]),
@@ -144,6 +145,20 @@ def _split(buf, lens):
     offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     raw = buf.tobytes()
     return [raw[offs[i]:offs[i + 1]] for i in range(len(lens))]
+
+
+def wire_encode_shared(model, shared, keys=None):
+    """packed Shared values (wire_decode's) -> the serialized Shared message; needs no device"""
+    L = lib()
+    shared = np.ascontiguousarray(shared, dtype=np.float32)
+    keys = np.ascontiguousarray(keys if keys is not None else [], dtype=np.uint32)
+    buf = np.empty(16 + 5 * shared.size, np.uint8)
+    n = c_sz()
+    rc = L.dist_b200_wire_encode_shared(None, model, _np_ptr(shared), shared.size, _np_ptr(keys) if keys.size else None, keys.size,
+                                        _np_ptr(buf), buf.size, ctypes.byref(n))
+    if rc != 0:
+        raise ValueError("wire_encode_shared: status %d" % rc)
+    return buf[:n.value].tobytes()
 
 
 def wire_split_stream(stream_bytes):

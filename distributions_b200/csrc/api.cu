@@ -1032,6 +1032,14 @@ int dist_b200_wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, 
     return emit_messages(ctx, bytes, lens, out, capacity, lens_out, n_bytes);
 }
 
+int dist_b200_wire_encode_shared(dist_b200_ctx *ctx, int model, const float *shared, size_t n_shared, const uint32_t *keys,
+                                 size_t n_keys, void *out, size_t capacity, size_t *n_bytes) {
+    std::vector<uint8_t> bytes;
+    int rc = wire_encode_shared(ctx, model, shared, n_shared, keys, n_keys, bytes);
+    if (rc) return rc;
+    return emit_messages(ctx, bytes, std::vector<size_t>(), out, capacity, nullptr, n_bytes);
+}
+
 int dist_b200_feature_dump_groups_wire(dist_b200_feature *f, void *out, size_t capacity, size_t *lens_out, size_t *n_bytes,
                                        void *stream) {
     if (!f || !f->ctx) return DIST_B200_ERR_INVALID;

@@ -224,6 +224,8 @@ int wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg, size_t sh
                 const size_t *group_lens, int G, WireFeature &out);
 int wire_decode_clustering(dist_b200_ctx *ctx, const void *msg, size_t len, int *which, float *alpha, float *d,
                            uint64_t *dataset_size);
+int wire_encode_shared(dist_b200_ctx *ctx, int model, const float *shared, size_t n_shared, const uint32_t *keys,
+                       size_t n_keys, std::vector<uint8_t> &out);
 int wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint32_t *keys, const uint32_t *stats,
                        size_t stats_words, std::vector<uint8_t> &out, std::vector<size_t> &lens);
 

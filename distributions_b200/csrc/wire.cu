@@ -338,4 +338,42 @@ int wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint
     return DIST_B200_OK;
 }
 
+// Shared message of a model from the packed floats wire_decode returns (dpd: not written -- its Shared also
+// carries per-value totals the feature does not track)
+int wire_encode_shared(dist_b200_ctx *ctx, int model, const float *shared, size_t n_shared, const uint32_t *keys,
+                       size_t n_keys, std::vector<uint8_t> &out) {
+    auto need = [&](size_t n) { return n_shared == n && shared; };
+    out.clear();
+    auto put_float = [&](int field, float f) {
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        put_f(out, field, u);
+    };
+    switch (model) {
+        case DIST_B200_NICH:
+            if (!need(4)) break;
+            for (int k = 0; k < 4; ++k) put_float(k + 1, shared[k]);
+            return DIST_B200_OK;
+        case DIST_B200_GP:
+        case DIST_B200_BB:
+            if (!need(2)) break;
+            put_float(1, shared[0]);
+            put_float(2, shared[1]);
+            return DIST_B200_OK;
+        case DIST_B200_BNB:
+            if (!need(3) || n_keys != 1 || !keys) break;
+            put_float(1, shared[0]);
+            put_float(2, shared[1]);
+            put_u(out, 3, keys[0]);
+            return DIST_B200_OK;
+        case DIST_B200_DD:
+            if (!shared || n_shared < 1 || n_shared > 256) break;
+            for (size_t v = 0; v < n_shared; ++v) put_float(1, shared[v]);
+            return DIST_B200_OK;
+        default:
+            return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: model has no Shared writer");
+    }
+    return fail(ctx, DIST_B200_ERR_INVALID, "wire_encode_shared: wrong number of Shared values for the model");
+}
+
 }  // namespace distb200

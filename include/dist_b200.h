@@ -210,6 +210,10 @@ int dist_b200_feature_dump_groups_wire(dist_b200_feature *f, void *out, size_t c
 /* the encode step alone (no device; ctx may be NULL): stats = the arrays dist_b200_wire_decode returns */
 int dist_b200_wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint32_t *keys, const uint32_t *stats,
                                  size_t stats_words, void *out, size_t capacity, size_t *lens_out, size_t *n_bytes);
+/* Shared message from the packed values dist_b200_wire_decode returns (nich, gp, bb, bnb with keys[0] = r,
+ * dd; dpd's Shared also carries per-value totals the library does not track: ERR_UNSUPPORTED) */
+int dist_b200_wire_encode_shared(dist_b200_ctx *ctx, int model, const float *shared, size_t n_shared, const uint32_t *keys,
+                                 size_t n_keys, void *out, size_t capacity, size_t *n_bytes);
 /* Clustering message (pitman_yor = 1 | low_entropy = 2, schema.proto:36-53) -> the prior vector */
 int dist_b200_prior_wire_host(dist_b200_ctx *ctx, const void *clustering_msg, size_t len, int G,
                               const int32_t *group_sizes, float *prior_host);

@@ -67,8 +67,12 @@ def test_encode_is_the_reference_writers_bytes(wire, name):
     if name == "dpd":
         _, _, again = capi.wire_decode(IDS[name], sh_msg, out)
         assert np.array_equal(again, stats)
+        with pytest.raises(ValueError):  # its Shared carries per-value totals the library does not track
+            capi.wire_encode_shared(IDS[name], [1.0, 0.5, 0.1], None)
     else:
         assert out == g_msgs
+        sh, keys, _ = capi.wire_decode(IDS[name], sh_msg, g_msgs)
+        assert capi.wire_encode_shared(IDS[name], sh, keys) == sh_msg
 
 
 def _varint(v):
