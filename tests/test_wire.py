@@ -196,3 +196,37 @@ def test_decoder_survives_garbage(wire):
             except ValueError:
                 outcomes["rejected"] += 1
     assert outcomes["rejected"] > 1000 and outcomes["ok"] > 0
+
+
+@pytest.mark.parametrize("name", ["nich", "gp", "bnb", "bb", "dd"])
+def test_encode_decode_round_trip_random_statistics(wire, name):
+    """size-independent property: decode(encode(stats)) == stats for random statistics, including the extremes
+    of the 32-bit fields and float bit patterns (inf, -0.0, denormals)"""
+    rng = np.random.default_rng(77)
+    sh_msg, _ = messages(wire, name)
+    G = 257
+    specials = np.array([0, 1, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF, 0x7F800000, 0x00000001], np.uint32)
+
+    def ints(n, signed):
+        x = rng.integers(0, 1 << 31 if signed else 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+        x[:3] = [0, 1, 0x7FFFFFFF if signed else 0xFFFFFFFF]
+        return x
+
+    def floats(n):
+        x = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+        x[:specials.size] = specials
+        return x
+
+    if name == "nich":
+        stats, dim = np.concatenate([ints(G, True), floats(G), floats(G)]), 0
+    elif name == "gp":
+        stats, dim = np.concatenate([ints(G, False), ints(G, False), floats(G)]), 0
+    elif name == "bnb":
+        stats, dim = np.concatenate([ints(G, False), ints(G, False)]), 0
+    elif name == "bb":
+        stats, dim = np.concatenate([ints(G, True), ints(G, True)]), 0
+    else:
+        stats, dim = ints(G * 16, True), 16
+    msgs = capi.wire_encode_groups(IDS[name], G, dim, None, stats)
+    _, _, back = capi.wire_decode(IDS[name], sh_msg, msgs)
+    assert np.array_equal(back, stats)
