@@ -1,6 +1,8 @@
 """The Python-3 mirror of the reference's lp Mixture classes (distributions_b200/models.py) driven through
 the reference's own test choreography (distributions/tests/test_models.py:498-594 test_mixture_runs /
 test_mixture_score, doc/overview.rst:185-202) and checked against the oracle."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -60,7 +62,7 @@ def _tol(name, want):
 @pytest.mark.parametrize("name", sorted(models.MODELS))
 def test_mixture_choreography(ctx, oracle, name):
     model = models.MODELS[name]
-    rng = np.random.default_rng(hash(name) % 1000)
+    rng = np.random.default_rng(zlib.crc32(name.encode()) % 1000)  # deterministic across processes (str hash is salted)
     shared = model.Shared(r=3) if name == "bnb" else model.Shared()
     mixture = model.Mixture(ctx)
     for _ in range(6):  # groups filled before init (benchmarks/mixture.cc:88-99)
