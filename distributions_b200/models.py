@@ -342,3 +342,81 @@ bnb = _Namespace("bnb", int, _BnbShared, _CountSumGroup, _BnbMixture)
 bb = _Namespace("bb", bool, _BbShared, _BbGroup, _BbMixture)
 dd = _Namespace("dd", int, _DdShared, _DdGroup, _DdMixture)
 MODELS = {m.__name__: m for m in (nich, gp, bnb, bb, dd)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# Clustering<int>::{PitmanYor, LowEntropy} and their Mixture drivers (clustering.hpp:45-331, mixture.hpp:48-163;
+# Python reference: distributions/lp/clustering.pyx:120-257)
+class _ClusteringMixture:
+    """MixtureDriver bookkeeping (mixture.hpp:59-122): group sizes, the set of empty groups, the sample size;
+    add_value / remove_value report whether a group was added / removed so that the feature mixtures follow
+    (doc/overview.rst:185-202).  score_value OVERWRITES scores with the prior vector, evaluated on the device."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.counts = []
+        self.empty_groupids = set()
+        self.sample_size = 0
+
+    def __len__(self):
+        return len(self.counts)
+
+    def init(self, model, counts=None):
+        if counts is not None:
+            self.counts = [int(c) for c in counts]
+        self.empty_groupids = {i for i, c in enumerate(self.counts) if c == 0}
+        self.sample_size = sum(self.counts)
+        assert self.empty_groupids, "missing empty groups"  # mixture.hpp:150
+
+    def add_value(self, model, groupid, count=1):  # mixture.hpp:77-93
+        assert count, "cannot add zero values"
+        add_group = self.counts[groupid] == 0
+        self.counts[groupid] += count
+        self.sample_size += count
+        if add_group:
+            self.empty_groupids.discard(groupid)
+            self.empty_groupids.add(len(self.counts))
+            self.counts.append(0)
+        return add_group
+
+    def remove_value(self, model, groupid, count=1):  # mixture.hpp:95-122
+        assert count and 0 < count <= self.counts[groupid], "cannot remove more values than are in group"
+        self.counts[groupid] -= count
+        self.sample_size -= count
+        remove_group = self.counts[groupid] == 0
+        if remove_group:
+            last = len(self.counts) - 1
+            if groupid != last:
+                self.counts[groupid] = self.counts[-1]
+                if self.counts[-1] == 0:
+                    self.empty_groupids.discard(last)
+                    self.empty_groupids.add(groupid)
+            self.counts.pop()
+        return remove_group
+
+    def score_value(self, model, scores):
+        assert len(scores) == len(self.counts) and scores.dtype == np.float32
+        scores[:] = self._prior(model)
+        return scores
+
+
+class PitmanYor:
+    """Clustering<int>::PitmanYor (clustering.hpp:45-240); EXAMPLES as lp/clustering.pyx:211-217"""
+
+    def __init__(self, alpha=1.0, d=0.0):
+        self.alpha, self.d = float(alpha), float(d)
+
+    class Mixture(_ClusteringMixture):
+        def _prior(self, model):
+            return self.ctx.prior_pitman_yor_host(model.alpha, model.d, self.counts)
+
+
+class LowEntropy:
+    """Clustering<int>::LowEntropy (clustering.hpp:245-331)"""
+
+    def __init__(self, dataset_size):
+        self.dataset_size = int(dataset_size)
+
+    class Mixture(_ClusteringMixture):
+        def _prior(self, model):
+            return self.ctx.prior_low_entropy_host(model.dataset_size, self.counts)

@@ -61,3 +61,22 @@ def test_bb_dd_groups_and_containers():
     assert d.counts.tolist() == [1, 1, 0, 1]
     assert models.nich.Shared(mu=1.5).dump() == {"mu": 1.5, "kappa": 1.0, "sigmasq": 1.0, "nu": 1.0}
     assert set(models.MODELS) == {"nich", "gp", "bnb", "bb", "dd"}
+
+
+def test_clustering_driver_bookkeeping():
+    """MixtureDriver semantics (mixture.hpp:59-122): there is always an empty group, adding to it appends a
+    fresh one, emptying a group swaps the last group into its place"""
+    m = models.PitmanYor.Mixture(ctx=None)
+    model = models.PitmanYor(alpha=1.0, d=0.1)
+    m.init(model, [3, 0, 2])
+    assert m.sample_size == 5 and m.empty_groupids == {1}
+    assert m.add_value(model, 0) is False and m.counts == [4, 0, 2]
+    assert m.add_value(model, 1) is True                      # the empty group got its first value ...
+    assert m.counts == [4, 1, 2, 0] and m.empty_groupids == {3}  # ... so a fresh empty group is appended
+    assert m.remove_value(model, 1) is True                   # emptied: the last group (the empty one) moves in
+    assert m.counts == [4, 0, 2] and m.empty_groupids == {1} and m.sample_size == 6
+    assert m.remove_value(model, 2, 2) is True                # emptied group is the last one: just dropped
+    assert m.counts == [4, 0] and m.empty_groupids == {1}
+    le = models.LowEntropy.Mixture(ctx=None)
+    le.init(models.LowEntropy(100), [0, 7])
+    assert le.add_value(models.LowEntropy(100), 0, 2) is True and le.counts == [2, 7, 0] and le.empty_groupids == {2}
