@@ -1135,6 +1135,7 @@ int dist_b200_feature_download_caches(const dist_b200_feature *f, float *out_hos
     int rc = ensure_scratch(ctx, n * sizeof(float));
     if (rc) return rc;
     cudaStream_t s = as_stream(stream);
+    DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));  // a batched add / remove may still be rebuilding the caches
     if ((rc = launch_unpack_caches(ctx, f, static_cast<float *>(ctx->scratch_dev), s))) return rc;
     DISTB200_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->scratch_dev, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     DISTB200_CUDA(ctx, cudaStreamSynchronize(s));

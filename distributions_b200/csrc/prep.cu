@@ -144,7 +144,10 @@ __global__ void merge_prep_batch_kernel(const AddBatch b, NumericTables t) {
                     const double mean_r = (tot * static_cast<double>(mean[g]) - m * mean_b) / n;
                     const double delta = mean_b - mean_r;
                     count[g] = static_cast<int32_t>(n);
-                    ctv[g] = static_cast<float>(static_cast<double>(ctv[g]) - ctv_b - (n * m / tot) * delta * delta);
+                    // one value left: its variance term is exactly 0, as Group::remove_value forces it
+                    // (nich.hpp:146-165); otherwise rounding may not push the remainder below 0
+                    ctv[g] = n <= 1 ? 0.f
+                                    : static_cast<float>(fmax(static_cast<double>(ctv[g]) - ctv_b - (n * m / tot) * delta * delta, 0.0));
                     mean[g] = static_cast<float>(mean_r);
                 }
             }

@@ -268,9 +268,12 @@ static unsigned row_tiles(const dist_b200_ctx *ctx, size_t N, int per_sm, int sp
 }
 
 int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b_in, cudaStream_t s) {
-    if (b_in.N == 0 || b_in.G == 0 || b_in.n == 0) return DIST_B200_OK;
+    if (b_in.G == 0 || b_in.n == 0) return DIST_B200_OK;
     const AddBatch &b = b_in;
+    // zeroed BEFORE the empty-batch early-out: the merge / pack that follows an empty batch (a rank whose row
+    // shard is empty) must see zeros, not the previous batch's sums
     DISTB200_CUDA(ctx, cudaMemsetAsync(b.acc, 0, b.acc_stride * b.n, s));
+    if (b.N == 0) return DIST_B200_OK;
     const dim3 grid(row_tiles(ctx, (b.N + 3) / 4, 8, b.n), b.n);
     bool vec = aligned16(b.assign);
     for (int i = 0; i < b.n; ++i) vec = vec && aligned16(b.d[i].column);

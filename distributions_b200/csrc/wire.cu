@@ -117,68 +117,72 @@ int wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg, size_t sh
     auto bad = [&](const char *what) { return fail(ctx, DIST_B200_ERR_INVALID, std::string("wire: ") + what); };
     if (!shared_msg && shared_len) return bad("null Shared message");
     if (G < 0 || (G && (!group_msgs || !group_lens))) return bad("null Group messages");
+    for (int i = 0; i < G; ++i)
+        if (!group_msgs[i] && group_lens[i]) return bad("null Group message with a non-zero length");
+    // non-repeated fields: a field that occurs more than once takes its LAST value, as protobuf readers
+    // (the reference's included) do -- hence .empty() / .back() below
     Fields sh;
     const size_t g = static_cast<size_t>(G);
     switch (model) {
         case DIST_B200_NICH: {  // schema.proto:131-145
             if (!parse(shared_msg, shared_len, "\0ffff", sh)) return bad("malformed NormalInverseChiSq.Shared");
             for (int k = 1; k <= 4; ++k)
-                if (sh.f[k].size() != 1) return bad("NormalInverseChiSq.Shared: missing required field");
-            out.shared = {sh.f[1][0], sh.f[2][0], sh.f[3][0], sh.f[4][0]};
+                if (sh.f[k].empty()) return bad("NormalInverseChiSq.Shared: missing required field");
+            out.shared = {sh.f[1].back(), sh.f[2].back(), sh.f[3].back(), sh.f[4].back()};
             out.stats.assign(3 * g, 0);
             for (size_t i = 0; i < g; ++i) {
                 Fields m;
                 if (!parse(group_msgs[i], group_lens[i], "\0vff\0", m)) return bad("malformed NormalInverseChiSq.Group");
-                if (m.v[1].size() != 1 || m.f[2].size() != 1 || m.f[3].size() != 1) return bad("NormalInverseChiSq.Group: missing required field");
-                if (m.v[1][0] > 0x7FFFFFFFull) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
-                out.stats[i] = static_cast<uint32_t>(m.v[1][0]);
-                out.stats[g + i] = fbits(m.f[2][0]);
-                out.stats[2 * g + i] = fbits(m.f[3][0]);
+                if (m.v[1].empty() || m.f[2].empty() || m.f[3].empty()) return bad("NormalInverseChiSq.Group: missing required field");
+                if (m.v[1].back() > 0x7FFFFFFFull) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                out.stats[i] = static_cast<uint32_t>(m.v[1].back());
+                out.stats[g + i] = fbits(m.f[2].back());
+                out.stats[2 * g + i] = fbits(m.f[3].back());
             }
         } break;
         case DIST_B200_GP: {  // schema.proto:105-116: count, sum, log_prod
             if (!parse(shared_msg, shared_len, "\0ff\0\0", sh)) return bad("malformed GammaPoisson.Shared");
-            if (sh.f[1].size() != 1 || sh.f[2].size() != 1) return bad("GammaPoisson.Shared: missing required field");
-            out.shared = {sh.f[1][0], sh.f[2][0]};
+            if (sh.f[1].empty() || sh.f[2].empty()) return bad("GammaPoisson.Shared: missing required field");
+            out.shared = {sh.f[1].back(), sh.f[2].back()};
             out.stats.assign(3 * g, 0);
             for (size_t i = 0; i < g; ++i) {
                 Fields m;
                 if (!parse(group_msgs[i], group_lens[i], "\0vvf\0", m)) return bad("malformed GammaPoisson.Group");
-                if (m.v[1].size() != 1 || m.v[2].size() != 1 || m.f[3].size() != 1) return bad("GammaPoisson.Group: missing required field");
-                if (!fits32(m.v[1][0]) || !fits32(m.v[2][0])) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
-                out.stats[i] = static_cast<uint32_t>(m.v[1][0]);
-                out.stats[g + i] = static_cast<uint32_t>(m.v[2][0]);
-                out.stats[2 * g + i] = fbits(m.f[3][0]);
+                if (m.v[1].empty() || m.v[2].empty() || m.f[3].empty()) return bad("GammaPoisson.Group: missing required field");
+                if (!fits32(m.v[1].back()) || !fits32(m.v[2].back())) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                out.stats[i] = static_cast<uint32_t>(m.v[1].back());
+                out.stats[g + i] = static_cast<uint32_t>(m.v[2].back());
+                out.stats[2 * g + i] = fbits(m.f[3].back());
             }
         } break;
         case DIST_B200_BNB: {  // schema.proto:118-129
             if (!parse(shared_msg, shared_len, "\0ffv\0", sh)) return bad("malformed BetaNegativeBinomial.Shared");
-            if (sh.f[1].size() != 1 || sh.f[2].size() != 1 || sh.v[3].size() != 1) return bad("BetaNegativeBinomial.Shared: missing required field");
-            if (!fits32(sh.v[3][0])) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: r exceeds 32 bits");
-            out.shared = {sh.f[1][0], sh.f[2][0], static_cast<float>(sh.v[3][0])};
-            out.keys = {static_cast<uint32_t>(sh.v[3][0])};  // r, exact
+            if (sh.f[1].empty() || sh.f[2].empty() || sh.v[3].empty()) return bad("BetaNegativeBinomial.Shared: missing required field");
+            if (!fits32(sh.v[3].back())) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: r exceeds 32 bits");
+            out.shared = {sh.f[1].back(), sh.f[2].back(), static_cast<float>(sh.v[3].back())};
+            out.keys = {static_cast<uint32_t>(sh.v[3].back())};  // r, exact
             out.stats.assign(2 * g, 0);
             for (size_t i = 0; i < g; ++i) {
                 Fields m;
                 if (!parse(group_msgs[i], group_lens[i], "\0vv\0\0", m)) return bad("malformed BetaNegativeBinomial.Group");
-                if (m.v[1].size() != 1 || m.v[2].size() != 1) return bad("BetaNegativeBinomial.Group: missing required field");
-                if (!fits32(m.v[1][0]) || !fits32(m.v[2][0])) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
-                out.stats[i] = static_cast<uint32_t>(m.v[1][0]);
-                out.stats[g + i] = static_cast<uint32_t>(m.v[2][0]);
+                if (m.v[1].empty() || m.v[2].empty()) return bad("BetaNegativeBinomial.Group: missing required field");
+                if (!fits32(m.v[1].back()) || !fits32(m.v[2].back())) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                out.stats[i] = static_cast<uint32_t>(m.v[1].back());
+                out.stats[g + i] = static_cast<uint32_t>(m.v[2].back());
             }
         } break;
         case DIST_B200_BB: {  // schema.proto:55-65
             if (!parse(shared_msg, shared_len, "\0ff\0\0", sh)) return bad("malformed BetaBernoulli.Shared");
-            if (sh.f[1].size() != 1 || sh.f[2].size() != 1) return bad("BetaBernoulli.Shared: missing required field");
-            out.shared = {sh.f[1][0], sh.f[2][0]};
+            if (sh.f[1].empty() || sh.f[2].empty()) return bad("BetaBernoulli.Shared: missing required field");
+            out.shared = {sh.f[1].back(), sh.f[2].back()};
             out.stats.assign(2 * g, 0);
             for (size_t i = 0; i < g; ++i) {
                 Fields m;
                 if (!parse(group_msgs[i], group_lens[i], "\0vv\0\0", m)) return bad("malformed BetaBernoulli.Group");
-                if (m.v[1].size() != 1 || m.v[2].size() != 1) return bad("BetaBernoulli.Group: missing required field");
-                if (m.v[1][0] > 0x7FFFFFFFull || m.v[2][0] > 0x7FFFFFFFull) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
-                out.stats[i] = static_cast<uint32_t>(m.v[1][0]);
-                out.stats[g + i] = static_cast<uint32_t>(m.v[2][0]);
+                if (m.v[1].empty() || m.v[2].empty()) return bad("BetaBernoulli.Group: missing required field");
+                if (m.v[1].back() > 0x7FFFFFFFull || m.v[2].back() > 0x7FFFFFFFull) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: count exceeds 32 bits");
+                out.stats[i] = static_cast<uint32_t>(m.v[1].back());
+                out.stats[g + i] = static_cast<uint32_t>(m.v[2].back());
             }
         } break;
         case DIST_B200_DD: {  // schema.proto:67-75: repeated alphas / repeated counts
@@ -200,11 +204,11 @@ int wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg, size_t sh
         } break;
         case DIST_B200_DPD: {  // schema.proto:77-90; Shared::protobuf_load dpd.hpp:104-125
             if (!parse(shared_msg, shared_len, "\0ffvfv", sh)) return bad("malformed DirichletProcessDiscrete.Shared");
-            if (sh.f[1].size() != 1 || sh.f[2].size() != 1) return bad("DirichletProcessDiscrete.Shared: missing required field");
+            if (sh.f[1].empty() || sh.f[2].empty()) return bad("DirichletProcessDiscrete.Shared: missing required field");
             const size_t V = sh.v[3].size();
             if (V < 1 || sh.f[4].size() != V || sh.v[5].size() != V) return bad("DirichletProcessDiscrete.Shared: values / betas / counts lengths differ");
             double beta_sum = 0;  // dpd.hpp:114-124
-            out.shared = {sh.f[1][0], sh.f[2][0], 0.f};
+            out.shared = {sh.f[1].back(), sh.f[2].back(), 0.f};
             for (size_t v = 0; v < V; ++v) {
                 if (!fits32(sh.v[3][v])) return bad("DirichletProcessDiscrete.Shared: value exceeds 32 bits");
                 if (!(sh.f[4][v] > 0.f)) return bad("DirichletProcessDiscrete.Shared: beta must be positive");
@@ -253,14 +257,14 @@ int wire_decode_clustering(dist_b200_ctx *ctx, const void *msg, size_t len, int 
             if (!r.ok) break;
             Fields m;
             if (num == 1) {
-                if (!parse(s.p, static_cast<size_t>(s.end - s.p), "\0ff\0\0", m) || m.f[1].size() != 1 || m.f[2].size() != 1)
+                if (!parse(s.p, static_cast<size_t>(s.end - s.p), "\0ff\0\0", m) || m.f[1].empty() || m.f[2].empty())
                     return fail(ctx, DIST_B200_ERR_INVALID, "wire: malformed Clustering.PitmanYor");
-                *alpha = m.f[1][0];
-                *d = m.f[2][0];
+                *alpha = m.f[1].back();
+                *d = m.f[2].back();
             } else {
-                if (!parse(s.p, static_cast<size_t>(s.end - s.p), "\0v\0\0\0", m) || m.v[1].size() != 1)
+                if (!parse(s.p, static_cast<size_t>(s.end - s.p), "\0v\0\0\0", m) || m.v[1].empty())
                     return fail(ctx, DIST_B200_ERR_INVALID, "wire: malformed Clustering.LowEntropy");
-                *dataset_size = m.v[1][0];
+                *dataset_size = m.v[1].back();
             }
             *which = static_cast<int>(num);
         } else {

@@ -173,3 +173,49 @@ def accum_tol(n_terms, scale):
     """rounding of an fp32 accumulation of n_terms terms with sum |term| = scale, in whatever order:
     2 eps32 * sqrt(n_terms) * scale (a random-walk bound; the worst case is n_terms * eps32 * scale)"""
     return 2.4e-7 * np.sqrt(n_terms) * scale + 1e-5
+
+
+# ---- NIW against the reference's own exact-math Python (tests/golden/make_golden_niw.py) --------------------
+NIW_GOLDEN_CASES = ("ex0", "ex1", "ex2", "d32", "d2b", "d3b")
+LOG_STEP = 6.2e-5  # fast_log's table step in the log (special.hpp:57-67)
+
+
+def niw_golden_case(gd, name):
+    """one fixture as the float32 arguments of the C-ABI / oracle + the float64 reference outputs"""
+    g = lambda k: gd["%s_%s" % (name, k)]  # noqa: E731
+    return dict(mu=g("mu").astype(np.float32), kappa=float(g("kappa")), psi=g("psi").astype(np.float32), nu=float(g("nu")),
+                count=g("count").astype(np.int32), sum_x=g("sum_x").astype(np.float32), sum_xxT=g("sum_xxT").astype(np.float32),
+                values=g("values").astype(np.float32), scores=g("scores"), post_mu=g("post_mu"), const_scores=g("const_scores"))
+
+
+def check_niw_golden(score_fn, o, c):
+    """score_fn(case, values[n][d] float32) -> scores [n][G] of the implementation under test (prior = 0).
+    `o` supplies the pinned fast_lgamma / fast_log (their deviation from lgamma / log is KNOWN, so the checks
+    below are tight on everything the golden pins: posterior, Sigma^-1, det Sigma).
+
+      1. absolute, at the reference's own cross-flavour bar 1e-3 * (1 + |a| + |b|) (test_model_flavors.py:56-116)
+      2. score at the posterior mean (quadratic form 0) == exact constant corrected by the known
+         fast_lgamma / fast_log(dof) deviations; what is left is -0.5 * (fast_log(det) - log det): one table step
+      3. differences between rows within a group cancel the constant: they pin (x - mu')^T Sigma^-1 (x - mu')
+         through coeff * [log(1 + q1/dof) - log(1 + q2/dof)] to two table steps
+    """
+    from scipy.special import gammaln
+    d = c["mu"].size
+    want = c["scores"]
+    got = np.asarray(score_fn(c, c["values"]), np.float64)
+    err = np.abs(got - want) / (1 + np.abs(got) + np.abs(want))
+    assert np.all(err <= 1e-3), ("absolute", err.max())
+    dof = (c["nu"] + c["count"] - d + 1.0).astype(np.float64)
+    a, b = 0.5 * (dof + d), 0.5 * dof
+    fl = lambda x: np.asarray(o.fast_lgamma(np.asarray(x, np.float32)), np.float64)  # noqa: E731
+    corr = (fl(a) - gammaln(a)) - (fl(b) - gammaln(b)) - 0.5 * d * (np.asarray(o.fast_log(dof.astype(np.float32)), np.float64) - np.log(dof))
+    got_c = np.asarray(score_fn(c, c["post_mu"].astype(np.float32)), np.float64)
+    got_c = np.diagonal(got_c)  # row g = group g's own posterior mean
+    # float32 posterior mean: q ~ |delta|^2 / sigma, negligible; det: float32 LU / Cholesky of a d x d matrix
+    tol_c = 0.5 * LOG_STEP + 2e-6 * d + 3e-6 * (np.abs(c["const_scores"]) + np.abs(gammaln(a)) + np.abs(gammaln(b)))
+    assert np.all(np.abs(got_c - (c["const_scores"] + corr)) <= tol_c), ("constant", np.abs(got_c - (c["const_scores"] + corr)).max())
+    coeff = 0.5 * (dof + d)
+    dg, dw = got - got[:1], want - want[:1]
+    # the quadratic form is evaluated in float32 from float32 statistics: relative 1e-5 of |coeff * log-term| each
+    tol_d = coeff[None, :] * 2 * LOG_STEP + 2e-5 * (np.abs(want + 0 * dw) * 0 + np.abs(dw)) + 4e-5 * coeff[None, :]
+    assert np.all(np.abs(dg - dw) <= tol_d), ("differences", (np.abs(dg - dw) - tol_d).max())

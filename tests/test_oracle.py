@@ -413,3 +413,31 @@ def test_rank3_oracle_matches_golden(oracle, golden_rank3):
         assert int(gd["le_%d_dataset_size" % i][0]) == dataset_size and np.array_equal(gd["le_%d_sizes" % i], sizes)
         want = gd["le_%d_out" % i]
         np.testing.assert_allclose(oracle.low_entropy_prior(dataset_size, sizes), want, rtol=0, atol=2e-6 * (1 + np.abs(want).max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# NIW pinned to the reference's own exact-math Python flavour (imported by tests/golden/make_golden_niw.py)
+@pytest.fixture(scope="module")
+def golden_niw():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "niw_golden.npz"))
+
+
+@pytest.mark.parametrize("name", cases.NIW_GOLDEN_CASES)
+def test_niw_oracle_matches_reference_python(oracle, golden_niw, name):
+    c = cases.niw_golden_case(golden_niw, name)
+
+    def score(c, values):
+        n = values.shape[0]
+        return oracle.niw_score_rows(c["mu"], c["kappa"], c["psi"], c["nu"], c["count"], c["sum_x"], c["sum_xxT"],
+                                     np.ascontiguousarray(values, np.float32), np.zeros((n, c["count"].size), np.float32))
+
+    cases.check_niw_golden(score, oracle, c)
+
+
+def test_niw_golden_covers_reference_examples(golden_niw):
+    """the fixtures include the reference's EXAMPLES verbatim (dbg/models/niw.py:39-102 = lp/models/niw.pyx EXAMPLES)"""
+    assert golden_niw["ex0_values"].shape == (7, 2) and golden_niw["ex1_values"].shape == (9, 3) and golden_niw["ex2_values"].shape == (9, 4)
+    np.testing.assert_array_equal(golden_niw["ex0_values"][0], [1.0, 2.0])
+    assert float(golden_niw["ex1_kappa"]) == 7.5 and float(golden_niw["ex2_nu"]) == 10.0
+    assert golden_niw["d32_values"].shape == (96, 32) and golden_niw["d32_count"][-1] == 0
