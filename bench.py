@@ -1,13 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- value-group scores/sec of the batched score_value + sample_from_scores hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2_nich]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload all|c2_nich|...]
 
 A "step" is one pass of the hot path (prior + Mixture::score_value for every row x group +
-sample_from_scores) over one batch of synthetic rows with frozen group statistics.  At N=1 the
-workload is BASELINE.json configs[1]: NormalInverseChiSq, 1M rows x 1024 groups, fp32.  For N>1 rows
-are sharded across ranks with no data-path collective (weak scaling: every rank scores its own
-1M-row shard).  Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md).
+sample_from_scores) over one batch of synthetic rows with frozen group statistics.
+
+Headline (top-level keys of the ONE JSON line rank 0 prints): BASELINE.json configs[1], NormalInverseChiSq
+1M rows x 1024 groups fp32; for N > 1 rows are sharded across ranks with no data-path collective (weak
+scaling: every rank scores its own 1M-row shard).
+
+`configs` (with --workload all, the default): one sub-record per remaining BASELINE shape, each with its own
+ms_per_step / value / binding roofline / e2e --
+  N = 1 : c1_dd (100k rows, launch-latency bound), c1_dd_steady (50M rows), c3_crosscat, c4_dpd, c5_niw
+  N > 1 : c4_dpd row-sharded (weak) and c3_crosscat FEATURE-sharded (strong: the 1M x 256 x 128 table is fixed)
+          in both implementations, "push" (partials stored into the owner's memory over NVLink from inside the
+          score kernel) and "rs" (NCCL reduce-scatter), each with the same table timed on one GPU in the same run.
+Single-feature table models (c1, c4) report the per-cell kernel as `value` (that is what the roofline measures)
+and the per-value CDF shortcut (the library's default for those calls) beside it, flagged.
 """
 import argparse
 import json
@@ -26,7 +36,6 @@ METRIC = "value-group scores/sec (score_value+sample)"
 UNIT = "value-group scores/s"
 
 WORKLOADS = {
-    # name: (builder, kwargs, description)
     "c1_dd": dict(model="dd", G=100, N=100_000, seed=20241, dim=16),
     "c1_dd_steady": dict(model="dd", G=100, N=50_000_000, seed=20241, dim=16),
     "c2_nich": dict(model="nich", G=1024, N=1_000_000, seed=20242),
@@ -34,12 +43,23 @@ WORKLOADS = {
     "c4_dpd": dict(model="dpd", G=512, N=10_000_000, seed=20244, V=4096),
     "c5_niw": dict(model="niw", G=256, N=1_000_000, seed=20245, d=32),
 }
+HEADLINE = "c2_nich"
+SUB_N1 = ["c1_dd", "c1_dd_steady", "c3_crosscat", "c4_dpd", "c5_niw"]
+
+# committed ncu --set full summaries: dram__bytes of one launch of the config's dominant kernel
+NCU_SUMMARY = {
+    "c2_nich": "r02_c2_nich_packed.txt",
+    "c1_dd_steady": "r02_c1_dd_steady.txt",
+    "c3_crosscat": "r02_c3_crosscat.txt",
+    "c4_dpd": "r02_c4_dpd_table_rows.txt",
+    "c5_niw": "r02_c5_niw_fused.txt",
+}
 
 
 def ncu_traffic(summary):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from a committed ncu --set full summary"""
-    path = os.path.join(ROOT, "profiles", summary)
-    if not os.path.exists(path):
+    path = os.path.join(ROOT, "profiles", summary or "")
+    if not summary or not os.path.exists(path):
         return None, None
     total = 0.0
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -47,19 +67,21 @@ def ncu_traffic(summary):
         parts = line.split()
         if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             total += float(parts[1]) * unit.get(parts[2], 1.0)
-    return total, "profiles/" + summary
+    return (total or None), "profiles/" + summary
 
 
-def peaks():
+def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tflops=float(p["bf16_tflops"]),
+                    bf16_tflops_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs"""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -72,10 +94,11 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            time.sleep(0.3)  # first sample before the timed region starts
         except Exception:
             self.proc = None
 
@@ -127,14 +150,31 @@ def model_id(capi, name):
 
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_arm(wl, seconds_target, threads=None):
-    """The reference's own CPU path (oracle/_ref, unmodified reference code) on a bounded sample of
-    the workload, all host threads; falls back to the C port when _ref is absent."""
+    """The reference's own CPU path (oracle/_ref, unmodified reference code) on a bounded sample of the workload,
+    all host threads; the C port where the reference cannot be compiled (NIW: Eigen is absent)."""
     from distributions_b200 import synth
     from oracle.pyoracle import Oracle, Ref
     threads = threads or os.cpu_count() or 1
     G = wl["G"]
     cols = [w["values"] for w in wl["feats"]]
     F = len(cols)
+    model = wl["feats"][0]["model"]
+    if model == "niw":
+        o = Oracle()
+        w = wl["feats"][0]
+        prior = o.py_prior(synth.PY_ALPHA, synth.PY_D, wl["sizes"])
+
+        def run_rows(rows):
+            t0 = time.perf_counter()
+            sc = np.tile(prior, (rows, 1)).astype(np.float32)
+            o.niw_score_rows(w["mu"], w["kappa"], w["psi"], w["nu"], w["count"], w["sum_x"], w["sum_xxT"],
+                             np.ascontiguousarray(w["values"][:rows]), sc)
+            o.sample_rows(sc, wl["u"][:rows])
+            return time.perf_counter() - t0
+        probe = 256
+        rate = probe / max(run_rows(probe), 1e-6)
+        rows = int(min(wl["N"], max(probe, rate * seconds_target)))
+        return (lambda: run_rows(rows)), rows, "port", 1
     if Ref.available():
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import cases
@@ -147,28 +187,39 @@ def cpu_reference_arm(wl, seconds_target, threads=None):
         rate = probe / max(secs, 1e-6)
         rows = int(min(wl["N"], max(probe, rate * seconds_target)))
         run = lambda: k.bench(cols, rows, threads)[0]  # noqa: E731
-        kind = "reference"
-    else:
-        if F != 1 or wl["feats"][0]["model"] != "nich":
-            raise RuntimeError("oracle/_ref is required for the CPU arm of this workload")
-        o = Oracle()
-        w = wl["feats"][0]
-        cache = o.nich_caches(w["shared"], w["count"], w["mean"], w["ctv"])
-        prior = o.py_prior(synth.PY_ALPHA, synth.PY_D, wl["sizes"])
-        probe = min(wl["N"], 2000)
-        secs, _ = o.bench_nich(cache, prior, w["values"][:probe], wl["u"][:probe], threads)
-        rate = probe / max(secs, 1e-6)
-        rows = int(min(wl["N"], max(probe, rate * seconds_target)))
-        run = lambda: o.bench_nich(cache, prior, w["values"][:rows], wl["u"][:rows], threads)[0]  # noqa: E731
-        kind = "port"
-    return run, rows, kind, threads
+        return run, rows, "reference", threads
+    if F != 1 or model != "nich":
+        raise RuntimeError("oracle/_ref is required for the CPU arm of this workload")
+    o = Oracle()
+    w = wl["feats"][0]
+    cache = o.nich_caches(w["shared"], w["count"], w["mean"], w["ctv"])
+    prior = o.py_prior(synth.PY_ALPHA, synth.PY_D, wl["sizes"])
+    probe = min(wl["N"], 2000)
+    secs, _ = o.bench_nich(cache, prior, w["values"][:probe], wl["u"][:probe], threads)
+    rate = probe / max(secs, 1e-6)
+    rows = int(min(wl["N"], max(probe, rate * seconds_target)))
+    run = lambda: o.bench_nich(cache, prior, w["values"][:rows], wl["u"][:rows], threads)[0]  # noqa: E731
+    return run, rows, "port", threads
+
+
+def cpu_baseline_record(wl, seconds_target):
+    F = len(wl["feats"])
+    try:
+        run, rows, kind, threads = cpu_reference_arm(wl, seconds_target=seconds_target)
+        secs = run()
+        return {"value": rows * F * wl["G"] / secs, "unit": UNIT, "cores": threads, "kind": kind,
+                "sample": "first %d of %d rows, one pass, %d thread%s%s" % (rows, wl["N"], threads, "s" if threads > 1 else "",
+                                                                           " (row shards)" if threads > 1 else "")}
+    except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(exc)[:200]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    wl = make_workload(args.workload)
+    name = HEADLINE if args.workload == "all" else args.workload
+    wl = make_workload(name)
     F = len(wl["feats"])
     run, rows, kind, threads = cpu_reference_arm(wl, seconds_target=3.0)
     for _ in range(args.warmup):
@@ -181,7 +232,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "rows_per_step": rows, "groups": wl["G"], "features": F},
+        "config": {"workload": name, "rows_per_gpu": wl["N"], "groups": wl["G"], "features": F, "sample_rows_per_step": rows},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -191,264 +242,386 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+class Peaks:
+    """roofline denominators: HBM / bf16 from MEASURED_PEAKS.json, MUFU / FP32 / L2-gather measured here"""
+
+    def __init__(self, ctx):
+        self.m = measured_peaks()
+        self.mufu = ctx.pipe_peak(0)
+        self.fma = ctx.pipe_peak(1)
+        self.l2_gather = ctx.pipe_peak(2)
+
+
+def binding_roofline(name, wl, ms, peaks, cdf_shortcut=False, materialise=False):
+    """t_roof = max over the resources the ALGORITHM needs per cell; frac = t_roof / t_measured."""
+    G, N, F = wl["G"], wl["N"], len(wl["feats"])
+    cells = float(N) * F * G
+    t = ms * 1e-3
+    cols_bytes = sum(w["values"].nbytes for w in wl["feats"])
+    hbm_bytes = cols_bytes + 4 * N + 4 * N + (4 * N * G if materialise else 0)  # values + u in, assign out
+    model = wl["feats"][0]["model"]
+    if model == "dpd":
+        hbm_bytes += 4 * (wl["feats"][0]["keys"].size + 1) * G
+    hbm = {"bound": "hbm", "algorithmic_bytes_per_launch": int(hbm_bytes), "achieved": hbm_bytes / t / 1e9, "peak": peaks.m["hbm_gbs"],
+           "unit": "GB/s", "frac": hbm_bytes / t / 1e9 / peaks.m["hbm_gbs"], "peak_source": peaks.m["source"]}
+    traffic, traffic_src = ncu_traffic(NCU_SUMMARY.get(name))
+    if cdf_shortcut or materialise:
+        r = dict(hbm)
+        r["kernel"] = ("value_cdf_build_kernel + value_cdf_sample_kernel (per-value CDF trees)" if cdf_shortcut
+                       else "score_rows_kernel (scores materialised)")
+    elif model in ("dd", "nich", "dpd"):
+        mufu_per_cell = 2.0 if model == "nich" else 1.0  # nich: lg2 + ex2; dd / dpd: ex2
+        t_sfu = cells * mufu_per_cell / peaks.mufu
+        r = {"bound": "sfu", "achieved": cells * mufu_per_cell / t / 1e9, "peak": peaks.mufu / 1e9, "unit": "G MUFU lane-ops/s",
+             "frac": t_sfu / t, "mufu_per_cell": mufu_per_cell, "t_roof_ms": t_sfu * 1e3,
+             "peak_source": "measured here (dist_b200_pipe_peak: register-only ex2 / lg2 chains)",
+             "kernel": {"dd": "score_rows_kernel<128, dd>", "nich": "score_rows_kernel<32, nich packed>", "dpd": "table_rows_kernel<4>"}[model]}
+        if model == "dpd":  # SURVEY 8(d): max(t_SFU, gathered bytes / measured L2 gather bandwidth)
+            t_l2 = 4.0 * cells / peaks.l2_gather
+            r["l2_gather"] = {"gathered_bytes": 4.0 * cells, "achieved_gbs": 4.0 * cells / t / 1e9, "peak_gbs": peaks.l2_gather / 1e9,
+                              "t_roof_ms": t_l2 * 1e3, "frac": t_l2 / t,
+                              "peak_source": "measured here (random 2 KB rows of an L2-resident 8 MB table, LDG.128)"}
+            if t_l2 > t_sfu:
+                r.update({"bound": "l2_gather", "achieved": 4.0 * cells / t / 1e9, "peak": peaks.l2_gather / 1e9, "unit": "GB/s",
+                          "frac": t_l2 / t, "t_roof_ms": t_l2 * 1e3})
+        r["hbm"] = hbm
+    elif model == "niw":
+        flops = cells * (2.0 * 32 * 32 + 2 * 32)  # 2 d^2 + 2 d per cell (random.hpp:182)
+        peak = peaks.m["bf16_tflops"]
+        r = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak,
+             "flop_per_cell": 2112, "t_roof_ms": flops / (peak * 1e12) * 1e3,
+             "peak_source": peaks.m["source"] + ": dense bf16 burst; the kernel runs 3 TF32 passes (half rate each) to keep fp32-level parity",
+             "kernel": "niw_tc_fused_kernel (tcgen05 kind::tf32, 3xTF32)", "hbm": hbm}
+    else:  # cross-cat gp + bb: FP32 pipe per SURVEY 8(d): 10 FMA per gp cell, 1 per bb cell
+        n_gp = sum(1 for w in wl["feats"] if w["model"] == "gp")
+        fma_ops = float(N) * G * (10.0 * n_gp + 1.0 * (F - n_gp))
+        t_fp = fma_ops / peaks.fma
+        r = {"bound": "fp32", "achieved": fma_ops / t / 1e9, "peak": peaks.fma / 1e9, "unit": "G FMA lane-ops/s", "frac": t_fp / t,
+             "t_roof_ms": t_fp * 1e3, "peak_source": "measured here (dist_b200_pipe_peak: register-only FFMA chains)",
+             "kernel": "score_rows_kernel<128, cross-cat>",
+             "kernel_limiter": "the kernel tabulates the GammaPoisson term per (group, value < 32), so a gp cell is one shared-memory "
+                               "gather + FADD instead of the 10-FMA polynomial: its own limiter is one LDS wavefront per warp-cell "
+                               "(N F G / 32 wavefronts at 1 / clk / SM)",
+             "lds_wavefront_t_roof_ms": cells / 32.0 / (148 * 1.965e9) * 1e3, "hbm": hbm}
+    r["traffic"] = traffic
+    r["traffic_source"] = traffic_src
+    return r
+
+
+def launches_per_step(wl, cdf_shortcut=False):
+    model = wl["feats"][0]["model"]
+    if cdf_shortcut:
+        return 2  # CDF build + per-row search
+    if model == "niw":
+        return 1
+    return 1
+
+
+class Bench:
+    """one process = one GPU; times workloads through the device-pointer and the host-buffer C-ABI entries"""
+
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        from distributions_b200 import capi, synth
+        self.capi, self.synth = capi, synth
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.ctx = capi.Context(self.local_rank)
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, device=self.dev, dtype=torch.float32)  # > 126 MB L2
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.peaks = Peaks(self.ctx)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], device=self.dev, dtype=self.torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, step, steps, warmup, flush=True, sampler=None):
+        """W untimed steps, then K steps each bracketed by CUDA events on the launching stream, the L2 flushed between
+        steps outside the event pairs; barrier + synchronize on both sides; ms per step = max over ranks"""
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            if flush:
+                self.flush.zero_()
+            step()
+        self.barrier()
+        if sampler is not None:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        t_wall = time.perf_counter()
+        for s0, s1 in ev:
+            if flush:
+                self.flush.zero_()
+            s0.record()
+            step()
+            s1.record()
+        self.barrier()
+        t_wall = time.perf_counter() - t_wall
+        clocks = sampler.stop() if sampler is not None else None
+        ms = self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
+        return ms, t_wall, clocks
+
+    def load(self, wl):
+        torch, capi, ctx = self.torch, self.capi, self.ctx
+        G, N = wl["G"], wl["N"]
+        feats = [ctx.feature(model_id(capi, w["model"])).update_all(w) for w in wl["feats"]]
+        cols_host = [np.ascontiguousarray(w["values"], dtype=capi.COLUMN_DTYPE[model_id(capi, w["model"])]) for w in wl["feats"]]
+        cols = [torch.from_numpy(c).to(self.dev) for c in cols_host]
+        u = torch.from_numpy(wl["u"]).to(self.dev)
+        prior = torch.empty(G, device=self.dev, dtype=torch.float32)
+        ctx.prior_pitman_yor(self.synth.PY_ALPHA, self.synth.PY_D, wl["sizes"], prior)
+        assign = torch.empty(N, device=self.dev, dtype=torch.int32)
+        return dict(feats=feats, cols_host=cols_host, cols=cols, u=u, prior=prior, assign=assign)
+
+    def e2e(self, wl, st, steps):
+        """the host-buffer C-ABI call a reference-side binding makes, H2D + D2H inside the timed region: once with the
+        caller's buffers page-locked (copied from / to directly), once with plain pageable numpy arrays (staged by the
+        library through its own pinned area)"""
+        torch, ctx = self.torch, self.ctx
+        G, N, F = wl["G"], wl["N"], len(wl["feats"])
+        cells = float(N) * F * G * self.world
+        prior_host = st["prior"].cpu().numpy()
+        h2d = sum(c.nbytes for c in st["cols_host"]) + wl["u"].nbytes + 4 * G
+        out = {}
+        pins = None
+        for mode in ("pinned", "pageable"):
+            if mode == "pinned":
+                pins = ([torch.from_numpy(c).pin_memory() for c in st["cols_host"]], torch.from_numpy(wl["u"]).pin_memory(),
+                        torch.empty(N, dtype=torch.int32).pin_memory())
+                cols, uu, aa = [c.numpy() for c in pins[0]], pins[1].numpy(), pins[2].numpy()
+            else:
+                pins = None
+                cols, uu, aa = st["cols_host"], wl["u"], np.empty(N, np.int32)
+            ctx.score_sample_batch_host(st["feats"], cols, prior_host, uu, assign_out=aa)  # warm (staging alloc)
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                a_host, _ = ctx.score_sample_batch_host(st["feats"], cols, prior_host, uu, assign_out=aa)
+            self.barrier()
+            dt = self.max_over_ranks((time.perf_counter() - t0) / steps)
+            out[mode] = (cells / dt, np.array(a_host, copy=True))
+        e2e = {"value": out["pinned"][0], "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(4 * N),
+               "buffers": "caller's buffers page-locked (torch pin_memory)",
+               "pageable": {"value": out["pageable"][0], "unit": UNIT,
+                            "buffers": "plain numpy arrays, staged through the library's pinned area (memcpy + H2D)"}}
+        return e2e, out["pinned"][1], out["pageable"][1]
+
+    # ---- one configuration, rows sharded over the ranks (weak scaling; N = 1: the whole configuration) ----------
+    def run_rows(self, name, steps, warmup, sampler=None, with_cpu=False, with_e2e=True):
+        torch, ctx, capi = self.torch, self.ctx, self.capi
+        args = self.args
+        wl = make_workload(name, self.rank)
+        G, N, F = wl["G"], wl["N"], len(wl["feats"])
+        st = self.load(wl)
+        model = wl["feats"][0]["model"]
+        table_model = F == 1 and model in ("dd", "dpd")
+        scores_buf = torch.empty((N, G), device=self.dev, dtype=torch.float32) if (args.materialise and name == HEADLINE) else None
+        flush = N * 12 < 200e6  # inputs of the big configurations exceed the L2 on their own
+
+        sweep = args.sweep and name == HEADLINE
+        base_sizes = torch.from_numpy(wl["sizes"].astype(np.int32)).to(self.dev)
+        sizes_dev = base_sizes.clone()
+        in_groups = [False]
+
+        def step():
+            # --sweep: one blocked Gibbs pass over the rows, all on the device -- the rows leave their groups
+            # (remove_value), are scored against the rest and resampled, join their new groups (add_value), and the
+            # clustering prior is refreshed from the new group sizes
+            if sweep and in_groups[0]:
+                ctx.remove_rows_batch(st["feats"], st["cols"], st["assign"], N, stream=self.stream)
+            ctx.score_sample_batch(st["feats"], st["cols"], N, st["prior"], st["u"], st["assign"], scores_buf, stream=self.stream)
+            if sweep:
+                ctx.add_rows_batch(st["feats"], st["cols"], st["assign"], N, stream=self.stream)
+                sizes_dev.copy_(base_sizes)
+                ctx.count_assignments(st["assign"], N, G, sizes_dev, accumulate=True, stream=self.stream)
+                ctx.prior_pitman_yor_dev(self.synth.PY_ALPHA, self.synth.PY_D, G, sizes_dev, st["prior"], stream=self.stream)
+                in_groups[0] = True
+
+        cells = float(N) * F * G * self.world
+        rec = {"workload": name, "rows_per_gpu": N, "groups": G, "features": F, "steps": steps,
+               "l2": "flushed between timed steps (256 MB memset outside the event pairs)" if flush else
+                     "inputs (%d MB per step) exceed the 126 MB L2" % ((sum(c.nbytes for c in st["cols_host"]) + 8 * N) >> 20)}
+        if table_model:
+            # per-cell kernel = the measured roofline; the library default (per-value CDF trees) beside it, flagged
+            ctx.set_option(capi.OPT_VALUE_CDF, 1)
+            ms, t_wall, clocks = self.timed(step, steps, warmup, flush, sampler)
+            a_cell = st["assign"].cpu().numpy()
+            ctx.set_option(capi.OPT_VALUE_CDF, 0)
+            ms_cdf, _, _ = self.timed(step, steps, warmup, flush)
+            a_cdf = st["assign"].cpu().numpy()
+            rec["value_cdf_shortcut"] = {
+                "flag": "ALGORITHMIC SHORTCUT (SURVEY.md 8d): one table feature with frozen statistics -- the likelihood vector is "
+                        "evaluated once per distinct VALUE, rows only search per-value CDF trees; N G / t is still reported. This is "
+                        "the library's default for such calls (DIST_B200_OPT_VALUE_CDF)",
+                "ms_per_step": ms_cdf, "value": cells / (ms_cdf * 1e-3),
+                "roofline": binding_roofline(name, wl, ms_cdf, self.peaks, cdf_shortcut=True),
+                "index_agreement_with_per_cell_kernel": float(np.mean(a_cell == a_cdf)), "gpu_launches_per_step": 2}
+        else:
+            ms, t_wall, clocks = self.timed(step, steps, warmup, flush, sampler)
+        rec.update({"ms_per_step": ms, "value": cells / (ms * 1e-3), "wall_s_timed_region": t_wall,
+                    "roofline": binding_roofline(name, wl, ms, self.peaks, materialise=scores_buf is not None),
+                    "gpu_launches_per_step": launches_per_step(wl)})
+        if table_model:
+            ctx.set_option(capi.OPT_VALUE_CDF, 1)  # e2e below through the same per-cell kernel as `value`
+        if with_e2e and not sweep:
+            a_dev = None
+            step()
+            torch.cuda.synchronize()
+            a_dev = st["assign"].cpu().numpy()
+            e2e, a_pin, a_page = self.e2e(wl, st, max(2, min(steps, 5)))
+            rec["e2e"] = e2e
+            rec["e2e_matches_device_assign"] = bool(np.array_equal(a_pin, a_dev) and np.array_equal(a_page, a_dev))
+        if table_model:
+            ctx.set_option(capi.OPT_VALUE_CDF, 0)
+        if with_cpu and self.world == 1 and self.rank == 0:
+            rec["cpu_baseline"] = cpu_baseline_record(wl, 12.0 if name == HEADLINE else 3.0)
+        del st, scores_buf
+        torch.cuda.empty_cache()
+        return rec, clocks
+
+    # ---- c3 at N > 1: the features of one cross-cat kind sharded over the ranks (strong scaling) -----------------
+    def run_feature_sharded(self, name, steps, warmup, mode):
+        torch, ctx, capi, dist = self.torch, self.ctx, self.capi, self.dist
+        from distributions_b200 import sharding
+        wl = make_workload(name, 0)  # the same table on every rank; each rank keeps its features
+        G, N, F = wl["G"], wl["N"], len(wl["feats"])
+        mine = sharding.feature_shard(F, self.rank, self.world)
+        feats = [ctx.feature(model_id(capi, wl["feats"][f]["model"])).update_all(wl["feats"][f]) for f in mine]
+        cols = [torch.from_numpy(np.ascontiguousarray(wl["feats"][f]["values"],
+                                                      dtype=capi.COLUMN_DTYPE[model_id(capi, wl["feats"][f]["model"])])).to(self.dev)
+                for f in mine]
+        u = torch.from_numpy(wl["u"]).to(self.dev)
+        prior = torch.empty(G, device=self.dev, dtype=torch.float32)
+        ctx.prior_pitman_yor(self.synth.PY_ALPHA, self.synth.PY_D, wl["sizes"], prior)
+        comm = torch.cuda.Stream(device=self.dev)
+        launches = [0]
+
+        def score_partial(lo, hi, out):
+            ctx.score_batch(feats, [c[lo:hi] for c in cols], hi - lo, prior if self.rank == 0 else None, out, stream=self.stream)
+            launches[0] += 1
+
+        def sample_block(scores, ub, out):
+            ctx.sample_from_scores(scores, scores.shape[0], G, ub, out, stream=self.stream)
+            launches[0] += 1
+
+        peer = sharding.PeerFeatureShards(ctx, N, G) if mode == "push" else None
+        lo_own, hi_own = peer.owned() if peer else (0, 0)
+        assign_own = torch.empty(max(hi_own - lo_own, 1), device=self.dev, dtype=torch.int32)
+
+        def step():
+            if peer is not None:
+                launches[0] += peer.launches_per_step
+                return peer.step(feats, cols, prior, u, assign_own, stream=self.stream)
+            return sharding.feature_sharded_score_sample(score_partial, sample_block, N, G, u, self.dev, tile_rows=self.args.tile_rows,
+                                                         comm_stream=comm)
+
+        ms, t_wall, _ = self.timed(step, steps, warmup, flush=False)
+        launches[0] = 0
+        step()
+        self.barrier()
+        per_step = launches[0]
+        if peer is not None:
+            peer.close()
+        cells = float(N) * F * G
+        rec = {"workload": name, "rows": N, "groups": G, "features": F, "features_per_rank": len(mine), "steps": steps,
+               "scaling": "strong", "ms_per_step": ms, "value": cells / (ms * 1e-3), "gpu_launches_per_step": per_step,
+               "parallelism": ("feature shards; partial rows stored into the owning rank's memory over NVLink from inside the score "
+                               "kernel, the owner samples the fixed-order sum of its slots" if mode == "push" else
+                               "feature shards + NCCL reduce-scatter(sum) of [rows][G] partials, tiles of %d rows overlapped on a "
+                               "second stream" % self.args.tile_rows),
+               "nvlink_bytes_per_step_per_rank": int(4 * N * G * (self.world - 1) / self.world),
+               "l2": "inputs (640 MB of columns + 512 MB of partial scores per step) exceed the 126 MB L2"}
+        del feats, cols
+        torch.cuda.empty_cache()
+        return rec
+
+
 def run_b200(args):
-    import torch
-    from distributions_b200 import capi, synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-
-    wl = make_workload(args.workload, rank)  # every rank: its own shard (weak scaling)
-    G, N = wl["G"], wl["N"]
-    F = len(wl["feats"])
-    ctx = capi.Context(local_rank)
-    feats = [ctx.feature(model_id(capi, w["model"])).update_all(w) for w in wl["feats"]]
-    cols_host = [np.ascontiguousarray(w["values"], dtype=capi.COLUMN_DTYPE[model_id(capi, w["model"])]) for w in wl["feats"]]
-    cols = [torch.from_numpy(c).to(dev) for c in cols_host]
-    u = torch.from_numpy(wl["u"]).to(dev)
-    prior = torch.empty(G, device=dev, dtype=torch.float32)
-    ctx.prior_pitman_yor(synth.PY_ALPHA, synth.PY_D, wl["sizes"], prior)
-    assign = torch.empty(N, device=dev, dtype=torch.int32)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)  # > 126 MB L2
-    stream = torch.cuda.current_stream().cuda_stream
-
-    scores_buf = torch.empty((N, G), device=dev, dtype=torch.float32) if args.materialise else None
-
-    base_sizes = torch.from_numpy(wl["sizes"].astype(np.int32)).to(dev)
-    sizes_dev = base_sizes.clone()
-    in_groups = [False]
-
-    def step():
-        # --sweep: one blocked Gibbs pass over the rows, all on the device -- the rows leave their groups
-        # (remove_value), are scored against the rest and resampled, join their new groups (add_value), and
-        # the clustering prior is refreshed from the new group sizes
-        if args.sweep and in_groups[0]:
-            ctx.remove_rows_batch(feats, cols, assign, N, stream=stream)
-        ctx.score_sample_batch(feats, cols, N, prior, u, assign, scores_buf, stream=stream)
-        if args.sweep:
-            ctx.add_rows_batch(feats, cols, assign, N, stream=stream)
-            sizes_dev.copy_(base_sizes)
-            ctx.count_assignments(assign, N, G, sizes_dev, accumulate=True, stream=stream)
-            ctx.prior_pitman_yor_dev(synth.PY_ALPHA, synth.PY_D, G, sizes_dev, prior, stream=stream)
-            in_groups[0] = True
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall = time.perf_counter()
-    for s0, s1 in ev:
-        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
-        s0.record()
-        step()
-        s1.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop() if rank == 0 else None
-    ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([float(sum(ms))], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
-    cells_per_step = float(N) * F * G * world
-    value = cells_per_step / (ms_per_step * 1e-3)
-
-    # e2e: the host-buffer C-ABI call a reference-side binding makes; H2D + D2H inside the timed region
-    # inputs live in pinned host memory (torch pin_memory), the result lands in a pinned host buffer
-    e2e_steps = max(2, min(args.steps, 5))
-    pin_cols = [torch.from_numpy(c).pin_memory() for c in cols_host]
-    pin_u = torch.from_numpy(wl["u"]).pin_memory()
-    pin_assign = torch.empty(N, dtype=torch.int32).pin_memory()
-    prior_host = prior.cpu().numpy()
-    np_cols, np_u, np_assign = [c.numpy() for c in pin_cols], pin_u.numpy(), pin_assign.numpy()
-    ctx.score_sample_batch_host(feats, np_cols, prior_host, np_u, assign_out=np_assign)  # warm (staging alloc)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        a_host, _ = ctx.score_sample_batch_host(feats, np_cols, prior_host, np_u, assign_out=np_assign)
-    barrier()
-    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    h2d = sum(c.nbytes for c in cols_host) + wl["u"].nbytes + 4 * G
-    d2h = 4 * N
-    e2e = {"value": cells_per_step / float(e2e_t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h)}
-    same = None if args.sweep else bool(np.array_equal(a_host, assign.cpu().numpy()))
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+    b = Bench(args)
+    torch = b.torch
+    if args.feature_sharded and b.world > 1:
+        r = b.run_feature_sharded("c3_crosscat", args.steps, args.warmup, args.feature_sharded)
+        if b.rank == 0:
+            print(json.dumps(r))
+        b.dist.destroy_process_group()
+        return 0
+    headline = HEADLINE if args.workload == "all" else args.workload
+    sampler = ClockSampler(b.local_rank) if b.rank == 0 else None
+    rec, clocks = b.run_rows(headline, args.steps, args.warmup, sampler=sampler, with_cpu=not args.no_cpu)
+    sub_steps = max(3, min(args.steps, 10))
+    configs = {}
+    if args.workload == "all":
+        if b.world == 1:
+            for name in SUB_N1:
+                r, _ = b.run_rows(name, sub_steps, args.warmup, with_cpu=not args.no_cpu)
+                configs[name] = r
+        else:
+            r, _ = b.run_rows("c4_dpd", sub_steps, args.warmup, with_e2e=False)
+            r["scaling"] = "weak"
+            r["parallelism"] = "row shards: caches and prior replicated, every rank scores its own 10M-row shard, no collective"
+            configs["c4_dpd_row_sharded"] = r
+            for mode in ("push", "rs"):
+                configs["c3_crosscat_feature_sharded_" + mode] = b.run_feature_sharded("c3_crosscat", sub_steps, args.warmup, mode)
+            # the same table on ONE GPU in the same run (rank 0 only, the others wait): the strong-scaling reference
+            t1 = torch.zeros(1, device=b.dev, dtype=torch.float64)
+            if b.rank == 0:
+                world, b.world, dist, b.dist = b.world, 1, b.dist, None
+                r1, _ = b.run_rows("c3_crosscat", sub_steps, args.warmup, with_e2e=False)
+                b.world, b.dist = world, dist
+                t1[0] = r1["ms_per_step"]
+            b.barrier()
+            b.dist.broadcast(t1, 0)
+            for mode in ("push", "rs"):
+                r = configs["c3_crosscat_feature_sharded_" + mode]
+                r["single_gpu_ms_same_run"] = float(t1.item())
+                r["strong_scaling_efficiency"] = float(t1.item()) / (b.world * r["ms_per_step"])
+    if b.rank != 0:
+        if b.dist is not None:
+            b.dist.destroy_process_group()
         return 0
 
-    hbm_peak, peak_src = peaks()
-    algo_bytes = sum(c.nbytes for c in cols_host) + wl["u"].nbytes + 4 * N  # values + u in, assign out
-    if args.materialise:
-        algo_bytes += 4 * N * G  # the [N][G] log scores written once
-    if wl["feats"][0]["model"] == "dpd":
-        algo_bytes += 4 * (4096 + 1) * G  # the cache table once
-    achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
-    traffic, traffic_src = (None, None)
-    if wl["name"] == "c2_nich" and not args.sweep:
-        traffic, traffic_src = ncu_traffic("r01_c2_nich_materialised_v2.txt" if args.materialise else "r01_c2_nich_v4_tile32.txt")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "note": "the fused kernel moves 12 B per ROW and is bound by the MUFU pipe, not HBM: the fraction that "
-                        "measures kernel quality is roofline_binding.frac (measured MUFU peak)",
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "score_rows_kernel / gather_rows_kernel (fused)",
-                "algorithmic_bytes_per_launch": int(algo_bytes)}
-    # the binding limit of this kernel is not HBM: report the measured pipe it is bound by as well
-    mufu = ctx.pipe_peak(0)
-    fma = ctx.pipe_peak(1)
-    mufu_per_cell = {"nich": 2.0, "dd": 1.0, "dpd": 1.0, "gp": 1.0, "bb": 1.0, "niw": 2.0}[wl["feats"][0]["model"]]
-    if wl["name"] == "c3_crosscat":
-        mufu_per_cell = 1.0 / F
-    cells_rank = float(N) * F * G
-    t_sfu = cells_rank * mufu_per_cell / mufu
-    roofline_binding = {"bound": "sfu", "mufu_lane_ops_per_s_measured": mufu, "ffma_lane_ops_per_s_measured": fma,
-                        "mufu_per_cell": mufu_per_cell, "t_roof_ms": t_sfu * 1e3, "frac": t_sfu / (ms_per_step * 1e-3)}
-
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu:
-        try:
-            run, rows, kind, threads = cpu_reference_arm(wl, seconds_target=12.0)
-            secs = run()
-            cpu_baseline = {"value": rows * F * G / secs, "unit": UNIT, "cores": threads, "kind": kind,
-                            "sample": "first %d of %d rows, one pass, %d threads (row shards)" % (rows, N, threads)}
-        except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
-            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(exc)[:200]}
-
+    roof = rec.pop("roofline")
+    e2e = rec.pop("e2e", None)
+    cpu = rec.pop("cpu_baseline", None)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": b.world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "rows_per_gpu": N, "groups": G, "features": F,
-                   "l2": "flushed between timed steps (256 MB memset outside the event pairs)",
+        "config": {"workload": headline, "rows_per_gpu": rec["rows_per_gpu"], "groups": rec["groups"], "features": rec["features"],
+                   "l2": rec["l2"],
                    "mode": ("score+prior+sample with the [N][G] scores also written to HBM" if args.materialise else
                             "fused score+prior+sample, scores not materialised") +
                            (" + batched remove_value / add_value, cache rebuild and prior refresh on the device "
-                            "(one blocked Gibbs pass per step)" if args.sweep else ""), "wall_s_timed_region": t_wall,
-                   "e2e_matches_device_assign": same},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * ((1 if F == 1 or wl["name"] == "c3_crosscat" else F) + ((4 * ((F + 127) // 128) + 2) if args.sweep else 0)),
-        "roofline": roofline, "roofline_binding": roofline_binding, "cpu_baseline": cpu_baseline,
+                            "(one blocked Gibbs pass per step)" if args.sweep else ""),
+                   "wall_s_timed_region": rec["wall_s_timed_region"], "e2e_matches_device_assign": rec.get("e2e_matches_device_assign")},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * rec["gpu_launches_per_step"],
+        "roofline": roof, "cpu_baseline": cpu,
     }
+    if "value_cdf_shortcut" in rec:
+        line["value_cdf_shortcut"] = rec["value_cdf_shortcut"]
+    if configs:
+        line["configs"] = configs
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
-
-
-def run_b200_feature_sharded(args):
-    """c3 at N > 1: the features of one cross-cat kind are sharded over the ranks; one NCCL
-    reduce-scatter(sum) of per-row, per-group partial scores over NVLink, each rank samples its row
-    block (distributions_b200.sharding).  Strong scaling: the 1M x 256 x 128 table is fixed."""
-    import torch
-    import torch.distributed as dist
-    from distributions_b200 import capi, sharding, synth
-
-    world = int(os.environ["WORLD_SIZE"])
-    rank = int(os.environ["RANK"])
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
-    wl = make_workload(args.workload, 0)  # the same table on every rank; each rank keeps its features
-    G, N = wl["G"], wl["N"]
-    F = len(wl["feats"])
-    mine = sharding.feature_shard(F, rank, world)
-    ctx = capi.Context(local_rank)
-    feats = [ctx.feature(model_id(capi, wl["feats"][f]["model"])).update_all(wl["feats"][f]) for f in mine]
-    cols = [torch.from_numpy(np.ascontiguousarray(wl["feats"][f]["values"],
-                                                  dtype=capi.COLUMN_DTYPE[model_id(capi, wl["feats"][f]["model"])])).to(dev)
-            for f in mine]
-    u = torch.from_numpy(wl["u"]).to(dev)
-    prior = torch.empty(G, device=dev, dtype=torch.float32)
-    ctx.prior_pitman_yor(synth.PY_ALPHA, synth.PY_D, wl["sizes"], prior)
-    stream = torch.cuda.current_stream().cuda_stream
-    comm = torch.cuda.Stream(device=dev)
-    launches = [0]
-
-    def score_partial(lo, hi, out):
-        if feats:
-            ctx.score_batch(feats, [c[lo:hi] for c in cols], hi - lo, prior if rank == 0 else None, out, stream=stream)
-            launches[0] += 1
-        else:
-            out.zero_()
-
-    def sample_block(scores, ub, out):
-        ctx.sample_from_scores(scores, scores.shape[0], G, ub, out, stream=stream)
-        launches[0] += 1
-
-    peer = sharding.PeerFeatureShards(ctx, N, G) if args.shard_mode == "push" else None
-    lo_own, hi_own = peer.owned() if peer else (0, 0)
-    assign_own = torch.empty(max(hi_own - lo_own, 1), device=dev, dtype=torch.int32)
-
-    def step():
-        if peer is not None:  # reduction fused into the score kernel over NVLink peer memory
-            launches[0] += 2
-            return peer.step(feats, cols, prior, u, assign_own, stream=stream)
-        return sharding.feature_sharded_score_sample(score_partial, sample_block, N, G, u, dev, tile_rows=args.tile_rows,
-                                                     comm_stream=comm)
-
-    def barrier():
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches[0] = 0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for s0, s1 in ev:
-        s0.record()
-        step()
-        s1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = torch.tensor([float(sum(a.elapsed_time(b) for a, b in ev))], device=dev, dtype=torch.float64)
-    dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
-    if rank == 0:
-        value = float(N) * F * G / (ms_per_step * 1e-3)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "rows": N, "groups": G, "features": F,
-                       "parallelism": ("feature shards (%d per rank), partial rows pushed into the owner's slot over NVLink "
-                                       "peer memory from inside the score kernel, owner samples the slot sum" % len(mine))
-                       if peer is not None else
-                       ("feature shards (%d per rank) + NCCL reduce-scatter(sum) of [rows][G] partials, "
-                        "tiles of %d rows overlapped on a second stream" % (len(mine), args.tile_rows)),
-                       "l2": "inputs (640 MB of columns + 512 MB of partial scores per step) exceed the 126 MB L2"},
-            "clocks": clocks, "gpu_launches": launches[0],
-            "nvlink_bytes_per_step_per_rank": int(4 * N * G * (world - 1) / world),
-        }
-        print(json.dumps(line))
-    dist.destroy_process_group()
+    if b.dist is not None:
+        b.dist.destroy_process_group()
     return 0
 
 
@@ -458,19 +631,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2_nich", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--materialise", action="store_true", help="also write the [N][G] log scores (HBM-write-bound mode)")
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS),
+                    help="all (default): headline c2_nich + one sub-record per remaining BASELINE shape; or one shape alone")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--materialise", action="store_true", help="headline: also write the [N][G] log scores (HBM-write-bound mode)")
     ap.add_argument("--sweep", action="store_true",
-                    help="each step is a blocked Gibbs pass on the device: remove_value, score+sample, add_value, cache/prior refresh")
+                    help="headline: each step is a blocked Gibbs pass on the device: remove_value, score+sample, add_value, cache / prior refresh")
+    ap.add_argument("--feature-sharded", default=None, choices=["push", "rs"],
+                    help="N > 1 only: time just c3_crosscat feature-sharded in this mode (development runs)")
     ap.add_argument("--tile-rows", type=int, default=65536, help="row tile of the feature-sharded reduce-scatter")
-    ap.add_argument("--shard-mode", default="push", choices=["push", "rs"],
-                    help="c3 at N>1: fused NVLink peer push (default) or NCCL reduce-scatter")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "c3_crosscat" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        return run_b200_feature_sharded(args)
     return run_b200(args)
 
 

@@ -22,7 +22,13 @@ SOURCES = {
     "api.cu": [],
     "prep.cu": ["--fmad=false"],
     "score_rows.cu": [],
+    "score_rows_nich.cu": [],
+    "score_rows_gp.cu": [],
+    "score_rows_bnb.cu": [],
+    "score_rows_bb.cu": [],
+    "score_rows_dd.cu": [],
     "gather_rows.cu": [],
+    "table_rows.cu": [],
     "niw.cu": [],
     "niw_tc.cu": [],
     "microbench.cu": [],

@@ -12,6 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdist_b200.so")
 
 DD, DPD, BB, GP, NICH, NIW, BNB = 0, 1, 2, 3, 4, 5, 6
+# dist_b200_option
+OPT_VALUE_CDF, OPT_ROW_TILE, OPT_HOST_CHUNKS, OPT_NIW_PATH, OPT_TABLE_KERNEL, OPT_SMALL_TILE, OPT_NICH_PACKED = range(7)
 MODEL_NAMES = {DD: "dd", DPD: "dpd", BB: "bb", GP: "gp", NICH: "nich", NIW: "niw", BNB: "bnb"}
 COLUMN_DTYPE = {DD: np.int32, DPD: np.uint32, BB: np.uint8, GP: np.uint32, NICH: np.float32, NIW: np.float32, BNB: np.uint32}
 
@@ -24,6 +26,7 @@ SIGNATURES = {
     "dist_b200_ctx_destroy": (None, [c_p]),
     "dist_b200_last_error": (ctypes.c_char_p, [c_p]),
     "dist_b200_sm_count": (c_i, [c_p]),
+    "dist_b200_ctx_set_option": (c_i, [c_p, c_i, c_i]),
     "dist_b200_feature_create": (c_i, [c_p, c_i, ctypes.POINTER(c_p)]),
     "dist_b200_feature_destroy": (None, [c_p]),
     "dist_b200_feature_model": (c_i, [c_p]),
@@ -220,6 +223,10 @@ class Context:
             msg = self.L.dist_b200_last_error(self.h)
             raise DistB200Error("%s failed: status %d: %s" % (what, rc, msg.decode() if msg else ""))
 
+    def set_option(self, option, value):
+        """measurement knob (dist_b200_option); 0 restores the default"""
+        self.check(self.L.dist_b200_ctx_set_option(self.h, int(option), int(value)), "set_option")
+
     @property
     def sm_count(self):
         return self.L.dist_b200_sm_count(self.h)
@@ -380,7 +387,7 @@ class Context:
         return scores_accum
 
     def pipe_peak(self, which):
-        """lane-ops/s of the MUFU (0) or FP32-FMA (1) pipe, measured with a register-only kernel"""
+        """lane-ops/s of the MUFU (0) or FP32-FMA (1) pipe (register-only kernels); 2: L2 gather bytes/s"""
         out = ctypes.c_double()
         self.check(self.L.dist_b200_pipe_peak(self.h, which, ctypes.byref(out)), "pipe_peak")
         return out.value

@@ -178,6 +178,25 @@ struct Upload {
     }
 };
 
+// dpd caches: the canonical value-major table (dpd.hpp:471-497) and its lane-segment copy for table_rows.cu
+int dpd_rebuild(dist_b200_feature *f, const float *betas_dev, const int32_t *counts_dev, cudaStream_t s) {
+    dist_b200_ctx *ctx = f->ctx;
+    int rc = launch_dpd_prep(ctx, f->alpha, f->beta0, f->dim, betas_dev, f->G, counts_dev, static_cast<float *>(f->params), s);
+    if (rc || f->G < 1) return rc;
+    const size_t need = table_hot_floats(f->dim + 1, f->G);
+    if (need > f->dpd_hot_floats) {
+        if (f->dpd_hot) {
+            DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+            DISTB200_CUDA(ctx, cudaFree(f->dpd_hot));
+            f->dpd_hot = nullptr;
+            f->dpd_hot_floats = 0;
+        }
+        DISTB200_CUDA(ctx, cudaMalloc(&f->dpd_hot, need * sizeof(float)));
+        f->dpd_hot_floats = need;
+    }
+    return launch_table_hot(ctx, f->dim + 1, f->G, static_cast<const float *>(f->params), f->dpd_hot, s);
+}
+
 bool check_feature(const dist_b200_feature *f, int model) { return f && f->ctx && f->model == model; }
 
 // cache mutations are asynchronous on the caller's stream: mark their completion ...
@@ -263,6 +282,12 @@ void dist_b200_ctx_destroy(dist_b200_ctx *ctx) {
     delete ctx;
 }
 
+int dist_b200_ctx_set_option(dist_b200_ctx *ctx, int option, int value) {
+    if (!ctx || option < 0 || option >= DIST_B200_OPT_COUNT_) return DIST_B200_ERR_INVALID;
+    ctx->opt[option] = value;
+    return DIST_B200_OK;
+}
+
 const char *dist_b200_last_error(const dist_b200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 int dist_b200_sm_count(const dist_b200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
@@ -290,6 +315,8 @@ void dist_b200_feature_destroy(dist_b200_feature *f) {
     if (f->gp_table) cudaFree(f->gp_table);
     if (f->keys_dev) cudaFree(f->keys_dev);
     if (f->key_rows_dev) cudaFree(f->key_rows_dev);
+    if (f->dpd_hot) cudaFree(f->dpd_hot);
+    if (f->cdf_buf) cudaFree(f->cdf_buf);
     if (f->niw_buf) cudaFree(f->niw_buf);
     if (f->niw_tc) cudaFree(f->niw_tc);
     if (f->stats) cudaFree(f->stats);
@@ -468,7 +495,7 @@ int dist_b200_dpd_update_all(dist_b200_feature *f, float alpha, float beta0, int
         DISTB200_CUDA(ctx, cudaMemcpyAsync(f->stats, c, sizeof(int32_t) * static_cast<size_t>(G) * V, cudaMemcpyDeviceToDevice, as_stream(stream)));
         DISTB200_CUDA(ctx, cudaMemcpyAsync(f->stats + static_cast<size_t>(G) * V, b, sizeof(float) * V, cudaMemcpyDeviceToDevice, as_stream(stream)));
     }
-    return mark_ready(f, launch_dpd_prep(ctx, alpha, beta0, V, b, G, c, static_cast<float *>(f->params), as_stream(stream)), as_stream(stream));
+    return mark_ready(f, dpd_rebuild(f, b, c, as_stream(stream)), as_stream(stream));
 }
 
 int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float kappa, const float *psi,
@@ -725,8 +752,8 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
                 break;
             case DIST_B200_DPD:
                 if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, sign, s))) return rc;
-                if ((rc = launch_dpd_prep(ctx, f->alpha, f->beta0, f->dim, reinterpret_cast<const float *>(f->stats + static_cast<size_t>(G) * f->dim),
-                                          G, reinterpret_cast<const int32_t *>(f->stats), static_cast<float *>(f->params), s)))
+                if ((rc = dpd_rebuild(f, reinterpret_cast<const float *>(f->stats + static_cast<size_t>(G) * f->dim),
+                                      reinterpret_cast<const int32_t *>(f->stats), s)))
                     return rc;
                 break;
             default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: unsupported model");
@@ -1292,6 +1319,27 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
     auto solo = [](const dist_b200_feature *f) { return f->model == DIST_B200_DPD || f->model == DIST_B200_NIW; };
     int n_solo = 0;
     for (int f = 0; f < F; ++f) n_solo += solo(features[f]) ? 1 : 0;
+    // ONE table feature (dpd / dd / bb), sampling only: every row with the same value has the same likelihood
+    // vector, so it is evaluated once per distinct value (per-value CDF trees, table_rows.cu).  SURVEY 8(d)
+    // "algorithmic shortcut"; DIST_B200_OPT_VALUE_CDF = 1 keeps the per-cell kernels (what bench.py reports beside it)
+    if (F == 1 && assign && !scores && !accumulate && ctx->opt[DIST_B200_OPT_VALUE_CDF] == 0 &&
+        (features[0]->model == DIST_B200_DPD || features[0]->model == DIST_B200_DD || features[0]->model == DIST_B200_BB)) {
+        dist_b200_feature *f = const_cast<dist_b200_feature *>(features[0]);
+        const int R = f->model == DIST_B200_DPD ? f->dim + 1 : (f->model == DIST_B200_DD ? f->dim : 2);
+        const size_t need = value_cdf_floats(R, G);
+        if (need > f->cdf_floats) {
+            if (f->cdf_buf) {
+                DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+                DISTB200_CUDA(ctx, cudaFree(f->cdf_buf));
+                f->cdf_buf = nullptr;
+                f->cdf_floats = 0;
+            }
+            DISTB200_CUDA(ctx, cudaMalloc(&f->cdf_buf, need * sizeof(float)));
+            f->cdf_floats = need;
+        }
+        const int rc = launch_value_cdf(ctx, f, f->cdf_buf, columns[0], N, prior, u, assign, s);
+        if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;
+    }
     if (n_solo == 0) {
         if (F > kMaxFeatures) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score: more than 512 features in one call");
         FeatList fl;
@@ -1305,8 +1353,13 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
         if (int rc = launch_gp_table_batch(ctx, tb, s)) return rc;
         return launch_score_rows(ctx, fl, G, N, prior, u, assign, scores, accumulate, s);
     }
-    if (F == 1 && features[0]->model == DIST_B200_DPD)
+    if (F == 1 && features[0]->model == DIST_B200_DPD) {
+        if (assign && !scores && !accumulate && ctx->opt[DIST_B200_OPT_TABLE_KERNEL] == 0) {
+            const int rc = launch_table_rows(ctx, features[0], columns[0], N, prior, u, assign, s);
+            if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;
+        }
         return launch_gather_rows(ctx, features[0], columns[0], N, prior, u, assign, scores, accumulate, s);
+    }
     float *buf = scores;
     if (!buf) {
         int rc = ensure_scores_scratch(ctx, sizeof(float) * N * G);
@@ -1511,10 +1564,8 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
         prior_dev = reinterpret_cast<const float *>(dev + prior_off);
     }
     const size_t min_chunk = 32768;
-    static const size_t max_chunks = [] {
-        const char *e = getenv("DIST_B200_HOST_CHUNKS");
-        return e ? static_cast<size_t>(std::max(1, atoi(e))) : static_cast<size_t>(5);  // measured optimum at 1M rows
-    }();
+    // five chunks measured best at 1M rows (DIST_B200_OPT_HOST_CHUNKS overrides it for A/B runs)
+    const size_t max_chunks = ctx->opt[DIST_B200_OPT_HOST_CHUNKS] > 0 ? static_cast<size_t>(ctx->opt[DIST_B200_OPT_HOST_CHUNKS]) : 5;
     size_t nchunks = std::min<size_t>(max_chunks, std::max<size_t>(1, N / min_chunk));
     for (int f = 0; f < F; ++f)  // paths that materialise through the context's single scores buffer: no overlap
         if (features[f]->model == DIST_B200_NIW || (features[f]->model == DIST_B200_DPD && F > 1)) nchunks = 1;
@@ -1561,7 +1612,11 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
         }
         rc = score_dispatch(ctx, features, F, cols.data(), n, prior_dev, reinterpret_cast<const float *>(dev + u_off) + lo,
                             reinterpret_cast<int32_t *>(dev + assign_off) + lo, scores_dev ? scores_dev + lo * G : nullptr, 0, s);
-        if (rc) return rc;
+        if (rc) {  // copies of earlier chunks into the caller's buffers may still be in flight
+            cudaStreamSynchronize(st[0]);
+            cudaStreamSynchronize(st[1]);
+            return rc;
+        }
         int32_t *adst = assign_pinned ? assign_host + lo : reinterpret_cast<int32_t *>(pin + assign_off) + lo;
         DISTB200_CUDA(ctx, cudaMemcpyAsync(adst, dev + assign_off + 4 * lo, 4 * n, cudaMemcpyDeviceToHost, s));
         if (scores_host)

@@ -93,6 +93,7 @@ struct dist_b200_ctx {
     void *add_acc = nullptr;          // batched add_value: per-feature accumulators (stats.cu)
     size_t add_acc_bytes = 0;
     cudaEvent_t add_done = nullptr;   // recorded after the last merge that read add_acc
+    int opt[DIST_B200_OPT_COUNT_] = {0};  // dist_b200_ctx_set_option: A/B knobs of bench.py / the profiling scripts
 };
 
 struct dist_b200_feature {
@@ -126,6 +127,10 @@ struct dist_b200_feature {
     float *log_prod_dev = nullptr;    // gp: Group::log_prod per group (read by score_data only)
     int log_prod_cap = 0;
     bool log_prod_valid = false;      // cleared by every statistics mutation that does not maintain it
+    float *dpd_hot = nullptr;         // dpd: the table in the lane-segment layout of table_rows.cu
+    size_t dpd_hot_floats = 0;
+    float *cdf_buf = nullptr;         // dpd / dd / bb: per-value CDF trees (rebuilt per scoring call: they carry the prior)
+    size_t cdf_floats = 0;
     uint32_t *keys_dev = nullptr;     // dpd sorted keys
     int *key_rows_dev = nullptr;      // dpd: table row of sorted key i
     // niw
@@ -200,6 +205,14 @@ int launch_gather_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const voi
                        cudaStream_t s);
 int launch_sample_scores(dist_b200_ctx *ctx, const float *scores, size_t N, int G, const float *u,
                          int32_t *assign, cudaStream_t s, int n_slots = 1, size_t slot_stride = 0);
+// table_rows.cu: single table feature (dpd / dd / bb)
+size_t table_hot_floats(int R, int G);
+int launch_table_hot(dist_b200_ctx *ctx, int R, int G, const float *table, float *hot, cudaStream_t s);
+int launch_table_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *column, size_t N, const float *prior,
+                      const float *u, int32_t *assign, cudaStream_t s);
+size_t value_cdf_floats(int R, int G);
+int launch_value_cdf(dist_b200_ctx *ctx, const dist_b200_feature *f, float *buf, const void *column, size_t N,
+                     const float *prior, const float *u, int32_t *assign, cudaStream_t s);
 // niw.cu
 int niw_padded_dim(int d);
 int launch_niw_prep(dist_b200_ctx *ctx, int d, const float *mu, float kappa, const float *psi, float nu, int G,

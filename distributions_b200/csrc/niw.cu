@@ -263,24 +263,12 @@ int launch_niw_prep(dist_b200_ctx *ctx, int d, const float *mu, float kappa, con
     return DIST_B200_OK;
 }
 
-// DIST_B200_NIW_MODE: "tf32x3" (default; split-precision tensor-core path), "tf32" (single pass),
-// "fp32" (CUDA-core kernel).  Dimensions other than 32 always take the CUDA-core kernel.
-static int niw_mode() {
-    static const int mode = [] {
-        const char *e = getenv("DIST_B200_NIW_MODE");
-        if (!e) return 3;
-        if (!strcmp(e, "fp32")) return 0;
-        if (!strcmp(e, "tf32")) return 1;
-        return 3;
-    }();
-    return mode;
-}
-
 int launch_niw_scores(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *values, size_t N,
                       const float *prior, float *scores, int accumulate, cudaStream_t s) {
     if (N == 0 || f->G == 0) return DIST_B200_OK;
-    if (f->dim == 32 && f->niw_tc && niw_mode() != 0) {
-        const int rc = launch_niw_tc_scores(ctx, f->G, f->niw_tc, values, N, prior, scores, accumulate, niw_mode() == 3, s);
+    // d = 32: tcgen05 with split (3xTF32) operands; DIST_B200_OPT_NIW_PATH = 1 keeps the FP32 CUDA-core kernel for A/B runs
+    if (f->dim == 32 && f->niw_tc && ctx->opt[DIST_B200_OPT_NIW_PATH] == 0) {
+        const int rc = launch_niw_tc_scores(ctx, f->G, f->niw_tc, values, N, prior, scores, accumulate, true, s);
         if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;
     }
     NiwArgs a{};

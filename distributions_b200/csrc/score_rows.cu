@@ -1,541 +1,9 @@
-// score_rows.cu -- the row-mapped fused score(+prior)(+sample) kernel.
-//
-// Replaces, for N rows at once, the per-value stack of SURVEY.md §3.2:
-//   PitmanYor::Mixture::score_value (clustering.hpp:195-208, overwrite with the prior vector)
-//   -> Model::Mixture::score_value for every feature (accumulate; src/models/nich.cc:33-66,
-//      src/models/gp.cc:32-67, bb.hpp:303-313, dd.hpp:433-445)
-//   -> sample_from_scores_overwrite (random.hpp:360-366 = random.cc:94-106 + random.hpp:315-333).
-//
-// Mapping (B200): one ROW per lane, groups walked in register tiles of CHUNK.  The per-group caches
-// sit in shared memory and every lane of a warp reads the same group at the same time, so a cache
-// entry is one conflict-free broadcast LDS.128 shared by 32 rows; row values are read with coalesced
-// loads from feature-major columns.  Everything the reference does in three passes over a G-float
-// buffer (score, max/exp/sum, scan) happens in registers, in the reference's own left-to-right
-// order within a tile: no warp shuffles, and no [N][G] round trip through HBM unless the caller
-// asks for the scores.
-//
-//   G <= CHUNK  : the whole score row lives in registers; max, exp, running total and the
-//                 `t -= l[i]; t <= 0` walk are the reference's loops verbatim.
-//   G  > CHUNK  : per tile (negated scaled max, sum of exp) pairs are merged into at most kSlots
-//                 slots kept in shared memory; a walk over the slots finds the one holding
-//                 u * total, then each thread re-scores just that slot's tiles for its own row
-//                 (same code path as the main pass, with a per-lane group offset) and finishes with
-//                 the reference's walk.
-//
-// Group caches are staged with cp.async: resident for the whole kernel when all features fit in
-// shared memory, otherwise double-buffered per (feature, tile) behind the math of the previous
-// feature.  KIND >= 0 instantiates the single-feature kernels (model known at compile time, prior
-// folded into the resident caches); KIND = -1 is the cross-cat kernel (any feature list).
-#include "common.cuh"
+// score_rows.cu -- dispatch of the row-mapped fused score(+prior)(+sample) kernel (score_rows.cuh), the cross-cat
+// instantiations (KIND = -1: any feature list) and the GammaPoisson value-table builder.  The single-feature
+// instantiations live in score_rows_{nich,gp,bnb,bb,dd}.cu.
+#include "score_rows.cuh"
 
 namespace distb200 {
-
-constexpr int kSlots = 16;
-constexpr int kStages = 3;  // cp.async ring depth of the streaming mode
-constexpr size_t kResidentBudget = 96 * 1024;  // bytes of group caches kept resident in smem
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
-    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-
-__host__ __device__ __forceinline__ int kind_stride(int kind, int vdim) {  // floats of cache per group
-    return (kind == DIST_B200_DD || kind == kKindGpTable) ? vdim : 4;
-}
-
-// GammaPoisson term of one (value, group) cell -- the single definition shared by the direct path, the
-// table builder and the out-of-table fallback, so all three produce the same bits  (gp.cc:56-66)
-__device__ __forceinline__ float gp_term(const float4 q, uint32_t xb, const float *__restrict__ coeff,
-                                         const float *__restrict__ logfact) {
-    const float xf = static_cast<float>(xb);
-    const float lf = xb < 64 ? logfact[xb] : fast_lgamma_cell(static_cast<float>(xb + 1u), coeff);
-    const float lg = fast_lgamma_cell(q.x + xf, coeff);
-    return fmaf(q.y, xf, (q.z + lg) - lf);
-}
-
-// BetaNegativeBinomial term (bnb.hpp:308-319): q = {post_beta, alpha, score, -}
-__device__ __forceinline__ float bnb_term(const float4 q, uint32_t xb, const float *__restrict__ coeff) {
-    const float beta = q.x + static_cast<float>(xb);
-    return (q.z + fast_lgamma_cell(beta, coeff)) - fast_lgamma_cell(beta + q.y, coeff);
-}
-
-// raw 32-bit value of row `row` of a feature column
-__device__ __forceinline__ uint32_t load_value(int kind, const void *column, size_t row) {
-    if (kind == DIST_B200_BB) return static_cast<const uint8_t *>(column)[row];
-    return static_cast<const uint32_t *>(column)[row];
-}
-
-// one cell with caches behind a generic pointer: identical arithmetic to the tiled loop below
-__device__ __forceinline__ float cell_score(int kind, uint32_t xb, const float *__restrict__ p, int vdim,
-                                            const float *__restrict__ coeff, const float *__restrict__ logfact) {
-    switch (kind) {
-        case DIST_B200_NICH: {
-            const float4 q = *reinterpret_cast<const float4 *>(p);
-            const float d = __uint_as_float(xb) - q.x;
-            const float z = __fadd_rn(1.f, __fmul_rn(q.y, __fmul_rn(d, d)));
-            return fmaf(q.z, fast_log2_cell(z), q.w);  // q.z = log_coeff * ln 2
-        }
-        case DIST_B200_GP:
-            return gp_term(*reinterpret_cast<const float4 *>(p), xb, coeff, logfact);
-        case DIST_B200_BNB:
-            return bnb_term(*reinterpret_cast<const float4 *>(p), xb, coeff);
-        case DIST_B200_BB: {
-            const float2 q = *reinterpret_cast<const float2 *>(p);
-            return xb ? q.x : q.y;
-        }
-        case kKindGpTable:  // p points at this group's table row; out-of-table values handled by the caller
-            return p[min(xb, static_cast<uint32_t>(kGpTableX - 1))];
-        default: {  // DD
-            const int v = min(static_cast<int>(xb), vdim - 1);
-            return p[v];
-        }
-    }
-}
-
-// acc[j] (+)= model term of groups pb[0..CHUNK) for one row value.  kAssign: first feature of a
-// single-feature kernel, whose caches already carry the prior.
-template <int CHUNK, bool kAssign>
-__device__ __forceinline__ void accumulate_feature(int kind, uint32_t xb, const float *__restrict__ pb, int vdim,
-                                                   float (&acc)[CHUNK], const float *__restrict__ coeff,
-                                                   const float *__restrict__ logfact,
-                                                   const float4 *__restrict__ aux = nullptr) {
-    switch (kind) {
-        case kKindGpTable: {
-            // tabulated GammaPoisson: one conflict-free gather per cell (lanes differ only in the value
-            // column of a 32-wide row).  Counts beyond the table take the direct formula from `aux`.
-            if (xb < static_cast<uint32_t>(kGpTableX)) {
-#pragma unroll
-                for (int j = 0; j < CHUNK; ++j) {
-                    const float v = pb[j * kGpTableX + xb];
-                    acc[j] = kAssign ? v : acc[j] + v;
-                }
-            } else {
-#pragma unroll 1
-                for (int j = 0; j < CHUNK; ++j) {
-                    const float v = gp_term(aux[j], xb, coeff, logfact);
-#pragma unroll
-                    for (int jj = 0; jj < CHUNK; ++jj)
-                        if (jj == j) acc[jj] = kAssign ? v : acc[jj] + v;
-                }
-            }
-        } break;
-        case DIST_B200_NICH: {
-            // score + log_coeff * fast_log(1 + precision * (v - mean)^2)   (nich.cc:59-65)
-            const float4 *p4 = reinterpret_cast<const float4 *>(pb);
-            const float x = __uint_as_float(xb);
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-                const float4 q = p4[j];
-                const float d = x - q.x;
-                const float z = __fadd_rn(1.f, __fmul_rn(q.y, __fmul_rn(d, d)));
-                const float v = fmaf(q.z, fast_log2_cell(z), q.w);  // q.z = log_coeff * ln 2
-                acc[j] = kAssign ? v : acc[j] + v;
-            }
-        } break;
-        case DIST_B200_GP: {
-            // score + fast_lgamma(post_alpha + v) - fast_log_factorial(v) + score_coeff * v  (gp.cc:56-66)
-            const float4 *p4 = reinterpret_cast<const float4 *>(pb);
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-                const float v = gp_term(p4[j], xb, coeff, logfact);
-                acc[j] = kAssign ? v : acc[j] + v;
-            }
-        } break;
-        case DIST_B200_BNB: {
-            // score + fast_lgamma(post_beta + v) - fast_lgamma(post_beta + v + alpha)   (bnb.hpp:308-319)
-            const float4 *p4 = reinterpret_cast<const float4 *>(pb);
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-                const float v = bnb_term(p4[j], xb, coeff);
-                acc[j] = kAssign ? v : acc[j] + v;
-            }
-        } break;
-        case DIST_B200_BB: {
-            // value ? heads[g] : tails[g]   (bb.hpp:303-313)
-            const float4 *p4 = reinterpret_cast<const float4 *>(pb);
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-                const float2 q = *reinterpret_cast<const float2 *>(p4 + j);
-                const float v = xb ? q.x : q.y;
-                acc[j] = kAssign ? v : acc[j] + v;
-            }
-        } break;
-        default: {  // DD: scores_[value][g] - scores_shift_[g], pre-subtracted table (dd.hpp:433-445)
-            const int vi = min(static_cast<int>(xb), vdim - 1);
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-                const float v = pb[j * vdim + vi];
-                acc[j] = kAssign ? v : acc[j] + v;
-            }
-        } break;
-    }
-}
-
-struct RowsArgs {
-    int G;
-    int resident;        // all caches resident in smem
-    int stage_floats;    // floats per staging buffer (streaming mode)
-    int accumulate;
-    size_t N;
-    const float *prior;
-    const float *u;
-    int32_t *assign;
-    float *scores;
-    NumericTables t;
-    // peer push (feature shards): row r of this launch is global row row0 + r; it belongs to owner
-    // (row0 + r) / block_rows and is stored into that owner's slot for this rank, push[owner] (a peer
-    // device pointer mapped over NVLink), at local row (row0 + r) % block_rows
-    int n_push;
-    size_t row0, block_rows;
-    float *push[kMaxPushOwners];
-};
-
-template <int CHUNK, int KIND, bool kSample, bool kScores, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : (CHUNK <= 32 ? (KIND >= 0 ? 4 : 3) : (CHUNK <= 64 ? 2 : 1)))
-score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
-    constexpr int kThreads = THREADS;  // block size of this instantiation
-    extern __shared__ __align__(16) float smem[];
-    // layout: coeff[33*8] | logfact[64] | prior[Gpad] | tile[8 warps][32][33] (kScores) |
-    //         slots[kSlots][kThreads] float2 (kSample, multi-tile) | caches
-    constexpr bool kSingle = KIND >= 0;  // one feature of a known model; caches resident
-    // prior folded into the resident caches (first feature ASSIGNS): not for gp, whose score[g] cancels
-    // against lgamma(post_alpha + v) -- adding the prior before that cancellation would cost ~1e-5
-    constexpr bool kFold = kSingle && KIND != DIST_B200_GP && KIND != DIST_B200_BNB;
-    const int G = a.G;
-    const int nchunks = (G + CHUNK - 1) / CHUNK;
-    const int Gpad = nchunks * CHUNK;
-    const bool multi = nchunks > 1;
-    float *coeff = smem;
-    float *logfact = coeff + 33 * kLgammaRowStride;
-    float *prior_s = logfact + 64;
-    float *cursor = prior_s + Gpad;
-    float *tile = cursor;
-    if (kScores) cursor += (kThreads / 32) * 32 * 33;
-    float2 *slots = reinterpret_cast<float2 *>(cursor);
-    if (kSample && multi) cursor += 2 * kSlots * kThreads;
-    float *caches = cursor;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int F = kSingle ? 1 : feats.n;
-    const bool resident = kSingle ? true : (a.resident != 0);
-
-    for (int i = tid; i < 33 * kLgammaRowStride; i += kThreads) coeff[i] = a.t.lgamma5[i];
-    if (tid < 64) logfact[tid] = a.t.log_factorial[tid];
-    // the prior vector (clustering's overwrite) seeds every accumulator; padded groups get -inf
-    for (int g = tid; g < Gpad; g += kThreads)
-        prior_s[g] = g < G ? ((a.prior && !a.accumulate) ? a.prior[g] : 0.f) : -INFINITY;
-    if (resident) {
-        size_t off = 0;
-        for (int f = 0; f < F; ++f) {
-            const int n = Gpad * kind_stride(kSingle ? KIND : feats.f[f].kind, feats.f[f].vdim);
-            const float *src = static_cast<const float *>(feats.f[f].params);
-            for (int i = tid * 4; i < n; i += kThreads * 4) cp_async16(caches + off + i, src + i);
-            off += n;
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-    }
-    __syncthreads();
-    if (kFold) {
-        // fold the prior into this block's private copy of the caches: the first (only) feature then
-        // ASSIGNS prior + term in one FFMA instead of seeding accumulators and adding
-        const int vdim = feats.f[0].vdim;
-        // Padded groups (g >= G) become -inf for every row here, so the hot loop needs no per-cell mask:
-        // their prior is -inf, and nich borrows group 0's (mean, precision, coeff) so that the term is finite
-        // or -inf exactly when a real group's is (zeroed parameters would give 0 * inf = NaN for |x| > 1e19).
-        for (int g = tid; g < Gpad; g += kThreads) {
-            const float p = prior_s[g];
-            if (KIND == DIST_B200_NICH) {
-                if (g >= G) {
-                    caches[g * 4 + 0] = caches[0];
-                    caches[g * 4 + 1] = caches[1];
-                    caches[g * 4 + 2] = caches[2];
-                }
-                caches[g * 4 + 3] += p;
-            } else if (KIND == DIST_B200_GP) caches[g * 4 + 2] += p;
-            else if (KIND == DIST_B200_BB) {
-                caches[g * 4 + 0] += p;
-                caches[g * 4 + 1] += p;
-            } else {
-                for (int v = 0; v < vdim; ++v) caches[g * vdim + v] += p;
-            }
-        }
-        __syncthreads();
-    }
-
-    const int chunks_per_slot = (nchunks + kSlots - 1) / kSlots;
-    const int nslots = (nchunks + chunks_per_slot - 1) / chunks_per_slot;
-    // the selected slot is re-scored in-thread through the main loop body when caches are resident
-    const int extra = (kSample && multi && resident) ? chunks_per_slot : 0;
-    // Row tiles are strided over the blocks: neighbouring blocks stream neighbouring rows (DRAM / TLB
-    // locality for the many column streams of a cross-cat kind).  Splitting the last, partial round at
-    // warp granularity was measured and dropped: same-box A/B at c2 0.7315 ms plain vs 0.7380 ms balanced
-    // (blocks that finish early free MUFU issue slots for their neighbours on the SM), and the extra loop
-    // state cost the register-capped cross-cat kernel 8%.
-    const size_t ntiles = (a.N + kThreads - 1) / kThreads;
-    for (size_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
-        const size_t tile_base = tile_id * kThreads;
-        const size_t row_end = a.N;
-        size_t row = tile_base + tid;
-        const bool valid = row < row_end;
-        if (!valid) row = row_end - 1;  // clamp: compute on a real row, discard the result
-        float slot_m = INFINITY, slot_s = 0.f;  // slot being merged: negated scaled max, sum of exp
-        float nmax = 0.f, tres = 0.f;           // finalisation state: row's negated scaled max, remaining draw
-        int sel = 0, count = 0, result = 0;
-        const float urow = kSample ? a.u[row] : 0.f;
-
-        for (int it = 0; it < nchunks + extra; ++it) {
-            const bool fin = it >= nchunks;  // block-uniform: re-scoring the selected slot
-            // group offset of this thread's tile: uniform in the main pass, per lane when finalising
-            int g0 = it * CHUNK;
-            if (fin) g0 = min((sel * chunks_per_slot + (it - nchunks)) * CHUNK, Gpad - CHUNK);
-            // streaming mode: a kStages-deep cp.async ring; stage (f % kStages) holds feature f's caches for
-            // this tile of groups followed by this block's row values of feature f (one word per thread),
-            // so both arrive kStages-1 features ahead of their use
-            const int ring_floats = a.stage_floats + kThreads;
-            auto issue = [&](int f) {
-                const FeatDesc &fd = feats.f[f];
-                const int st = kind_stride(fd.kind, fd.vdim);
-                const float *src = static_cast<const float *>(fd.params) + static_cast<size_t>(g0) * st;
-                float *dst = caches + (f % kStages) * ring_floats;
-                for (int i = tid * 4; i < CHUNK * st; i += kThreads * 4) cp_async16(dst + i, src + i);
-                const char *xp = static_cast<const char *>(fd.column) + (fd.kind == DIST_B200_BB ? row : 4 * row);
-                cp_async4(dst + a.stage_floats + tid, reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(xp) & ~uintptr_t(3)));
-            };
-            if (!resident) {
-#pragma unroll
-                for (int f = 0; f < kStages - 1; ++f) {
-                    if (f < F) issue(f);
-                    cp_async_commit();
-                }
-            }
-
-            float acc[CHUNK];
-            if (!kFold) {
-#pragma unroll
-                for (int j = 0; j < CHUNK; j += 4) {
-                    const float4 p = *reinterpret_cast<const float4 *>(prior_s + g0 + j);
-                    acc[j] = p.x;
-                    acc[j + 1] = p.y;
-                    acc[j + 2] = p.z;
-                    acc[j + 3] = p.w;
-                }
-            }
-
-            if (kSingle) {
-                const uint32_t xb = load_value(KIND, feats.f[0].column, row);
-                const int vdim = feats.f[0].vdim;
-                accumulate_feature<CHUNK, kFold>(KIND, xb, caches + static_cast<size_t>(g0) * kind_stride(KIND, vdim), vdim,
-                                                 acc, coeff, logfact);
-            } else {
-                uint32_t xb = resident ? load_value(feats.f[0].kind, feats.f[0].column, row) : 0u;
-                size_t res_off = 0;
-                for (int f = 0; f < F; ++f) {
-                    const FeatDesc &fd = feats.f[f];
-                    const int st = kind_stride(fd.kind, fd.vdim);
-                    uint32_t xn = 0;
-                    const float *pb;
-                    if (resident) {
-                        if (f + 1 < F) xn = load_value(feats.f[f + 1].kind, feats.f[f + 1].column, row);
-                        pb = caches + res_off + static_cast<size_t>(g0) * st;
-                        res_off += static_cast<size_t>(Gpad) * st;
-                    } else {
-                        cp_async_wait<kStages - 2>();  // this thread's copies of feature f have landed
-                        __syncthreads();               // ... everyone's have, and stage (f-1) % kStages is free
-                        if (f + kStages - 1 < F) issue(f + kStages - 1);
-                        cp_async_commit();
-                        pb = caches + (f % kStages) * ring_floats;
-                        const uint32_t word = reinterpret_cast<const uint32_t *>(pb + a.stage_floats)[tid];
-                        if (fd.kind == DIST_B200_BB) {
-                            const uintptr_t addr = reinterpret_cast<uintptr_t>(fd.column) + row;
-                            xb = (word >> (8 * (addr & 3))) & 0xffu;
-                        } else {
-                            xb = word;
-                        }
-                    }
-                    accumulate_feature<CHUNK, false>(fd.kind, xb, pb, fd.vdim, acc, coeff, logfact,
-                                                     static_cast<const float4 *>(fd.aux) + g0);
-                    if (resident) xb = xn;
-                }
-                if (!resident) __syncthreads();  // the ring is refilled by the next tile's prologue
-            }
-
-            if (!kFold && g0 + CHUNK > G) {
-                // ragged last tile: padded groups carry zeroed caches, whose model terms may be inf/NaN
-                // (lgamma(0)); pin them to -inf so they vanish from max / exp / the walk.  With the prior
-                // folded into the caches (kFold) the padded entries are -inf by construction.
-#pragma unroll
-                for (int j = 0; j < CHUNK; ++j)
-                    if (g0 + j >= G) acc[j] = -INFINITY;
-            }
-
-            if (kScores && !fin) {
-                // [32 rows][32 groups] transposes through a padded per-warp tile -> every store instruction
-                // writes one full 128-byte line of a row.  Everything row-invariant is hoisted: the loop body
-                // is one LDS, one STG and a pointer step.
-                float *tw = tile + warp * 32 * 33;
-                const size_t wrow0 = tile_base + warp * 32;
-                const int nrows = wrow0 < row_end ? static_cast<int>(row_end - wrow0 < 32 ? row_end - wrow0 : 32) : 0;
-#pragma unroll
-                for (int sb = 0; sb < CHUNK / 32; ++sb) {
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) tw[lane * 33 + j] = acc[sb * 32 + j];
-                    __syncwarp();
-                    const int g = g0 + sb * 32 + lane;
-                    if (g >= G) continue;
-                    const float *src = tw + lane;
-                    if (a.n_push) {
-                        // rows of this warp tile land in at most two owners' slots
-                        const size_t grow0 = a.row0 + wrow0;
-                        int owner = static_cast<int>(grow0 / a.block_rows);
-                        size_t off = grow0 - static_cast<size_t>(owner) * a.block_rows;
-                        float *dst = a.push[owner] + off * G + g;
-                        for (int i = 0; i < nrows; ++i) {
-                            if (off == a.block_rows) {
-                                ++owner;
-                                off = 0;
-                                dst = a.push[owner] + g;
-                            }
-                            *dst = src[i * 33];
-                            dst += G;
-                            ++off;
-                        }
-                    } else {
-                        float *dst = a.scores + wrow0 * G + g;
-                        if (a.accumulate) {
-                            for (int i = 0; i < nrows; ++i, dst += G) *dst += src[i * 33];
-                        } else if (nrows == 32) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i, dst += G) *dst = src[i * 33];
-                        } else {
-                            for (int i = 0; i < nrows; ++i, dst += G) *dst = src[i * 33];
-                        }
-                    }
-                }
-            }
-
-            if (kSample) {
-                if (!multi) {
-                    // scores_to_likelihoods + sample_from_likelihoods, the reference's loops verbatim
-                    float m = acc[0];
-#pragma unroll
-                    for (int j = 1; j < CHUNK; ++j) m = fmaxf(m, acc[j]);
-                    const float nm = -m * kLog2e;  // exp(s - m) = 2^(s*log2e + nm): one FFMA + MUFU.EX2
-                    float total = 0.f;
-#pragma unroll
-                    for (int j = 0; j < CHUNK; ++j) {
-                        acc[j] = mufu_ex2(fmaf(acc[j], kLog2e, nm));
-                        total += acc[j];
-                    }
-                    float t = total * urow;
-                    int idx = 0;
-#pragma unroll
-                    for (int j = 0; j < CHUNK; ++j) {
-                        t -= acc[j];
-                        idx += (t > 0.f) ? 1 : 0;
-                    }
-                    result = min(idx, G - 1);
-                } else if (!fin) {
-                    float m = acc[0];
-#pragma unroll
-                    for (int j = 1; j < CHUNK; ++j) m = fmaxf(m, acc[j]);
-                    // slots carry nm = -(max * log2 e), rounded ONCE: every later rescale is a
-                    // difference of these rounded values, so tile sums stay mutually consistent
-                    const float nm = -m * kLog2e;
-                    float s = 0.f;
-#pragma unroll
-                    for (int j = 0; j < CHUNK; ++j) s += mufu_ex2(fmaf(acc[j], kLog2e, nm));
-                    // rescale to the smaller nm (the larger maximum): one of the two factors is 2^0 = 1, so a
-                    // single EX2 of -|difference| serves (slot_m = +inf on a fresh slot gives e = 0, slot_s = 0)
-                    const float dlt = slot_m - nm;
-                    const float e = mufu_ex2(-fabsf(dlt));
-                    slot_s = dlt > 0.f ? fmaf(slot_s, e, s) : fmaf(s, e, slot_s);
-                    slot_m = fminf(slot_m, nm);
-                    if ((it + 1) % chunks_per_slot == 0 || it + 1 == nchunks) {
-                        slots[(it / chunks_per_slot) * kThreads + tid] = make_float2(slot_m, slot_s);
-                        slot_m = INFINITY;
-                        slot_s = 0.f;
-                    }
-                    if (it + 1 == nchunks) {
-                        // total over slots, then the walk over slots to the one holding u * total
-                        float mm = INFINITY;
-                        for (int k = 0; k < nslots; ++k) mm = fminf(mm, slots[k * kThreads + tid].x);
-                        float total = 0.f;
-                        for (int k = 0; k < nslots; ++k) {
-                            const float2 ms = slots[k * kThreads + tid];
-                            const float w = ms.y * mufu_ex2(mm - ms.x);
-                            slots[k * kThreads + tid].y = w;  // the walk below reads the rescaled mass back: no second EX2
-                            total += w;
-                        }
-                        float t = total * urow;
-                        sel = nslots - 1;
-                        for (int k = 0; k < nslots; ++k) {
-                            const float w = slots[k * kThreads + tid].y;
-                            if (t <= w) {
-                                sel = k;
-                                break;
-                            }
-                            if (k + 1 < nslots) t -= w;
-                        }
-                        nmax = mm;
-                        tres = t;
-                        count = 0;
-                    }
-                } else {
-                    // finalisation: this tile belongs to the selected slot of this thread's row
-                    const bool live = (sel * chunks_per_slot + (it - nchunks)) * CHUNK < Gpad;
-#pragma unroll
-                    for (int j = 0; j < CHUNK; ++j) {
-                        tres -= live ? mufu_ex2(fmaf(acc[j], kLog2e, nmax)) : 0.f;
-                        count += (live && tres > 0.f) ? 1 : 0;
-                    }
-                }
-            }
-        }  // tiles of groups
-
-        if (kSample && multi) {
-            if (resident) {
-                result = min(sel * chunks_per_slot * CHUNK + count, G - 1);
-            } else {
-                // streaming caches: re-score the selected slot cell by cell from global memory
-                int idx = G - 1;
-                const int gb = sel * chunks_per_slot * CHUNK, ge = min(G, gb + chunks_per_slot * CHUNK);
-                float t = tres;
-                for (int g = gb; g < ge; ++g) {
-                    float s = prior_s[g];
-                    for (int f = 0; f < F; ++f) {
-                        const FeatDesc &fd = feats.f[f];
-                        const uint32_t xv = load_value(fd.kind, fd.column, row);
-                        if (fd.kind == kKindGpTable && xv >= static_cast<uint32_t>(kGpTableX))
-                            s += gp_term(static_cast<const float4 *>(fd.aux)[g], xv, coeff, logfact);
-                        else
-                            s += cell_score(fd.kind, xv,
-                                            static_cast<const float *>(fd.params) +
-                                                static_cast<size_t>(g) * kind_stride(fd.kind, fd.vdim),
-                                            fd.vdim, coeff, logfact);
-                    }
-                    t -= mufu_ex2(fmaf(s, kLog2e, nmax));
-                    if (t <= 0.f) {
-                        idx = g;
-                        break;
-                    }
-                }
-                result = idx;
-            }
-        }
-        if (kSample && valid) a.assign[row] = result;
-    }  // row tiles
-}
 
 // table[g][x] = GammaPoisson term of value x for group g, x < kGpTableX: built with gp_term itself (this
 // translation unit, same flags) so the tabulated and the direct path agree bit for bit
@@ -562,67 +30,6 @@ int launch_gp_table_batch(dist_b200_ctx *ctx, const GpTableBatch &b, cudaStream_
     return DIST_B200_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-template <int CHUNK, int KIND, bool kSample, bool kScores>
-static int launch_variant(dist_b200_ctx *ctx, const FeatList &feats, RowsArgs a, cudaStream_t s) {
-    // the cross-cat kernel at the widest register tile runs 128-thread blocks, three per SM (12 warps);
-    // everything else 256-thread blocks
-    constexpr int kThreads = (KIND < 0 && CHUNK == 128) ? 128 : 256;
-    const int G = a.G;
-    const int nchunks = (G + CHUNK - 1) / CHUNK;
-    const int Gpad = nchunks * CHUNK;
-    size_t cache_floats = 0;
-    int max_stride = 4;
-    for (int f = 0; f < feats.n; ++f) {
-        const int st = kind_stride(feats.f[f].kind, feats.f[f].vdim);
-        cache_floats += static_cast<size_t>(Gpad) * st;
-        if (st > max_stride) max_stride = st;
-    }
-    size_t fixed = (33 * kLgammaRowStride + 64 + Gpad) * sizeof(float);
-    if (kScores) fixed += (kThreads / 32) * 32 * 33 * sizeof(float);
-    if (kSample && nchunks > 1) fixed += sizeof(float2) * kSlots * kThreads;
-    a.resident = cache_floats * sizeof(float) <= kResidentBudget ? 1 : 0;
-    if (KIND >= 0 && !a.resident) return DIST_B200_ERR_UNSUPPORTED;  // caller falls back to the generic kernel
-    a.stage_floats = CHUNK * max_stride;
-    const size_t smem = fixed + (a.resident ? cache_floats : kStages * (static_cast<size_t>(a.stage_floats) + kThreads)) * sizeof(float);
-    if (smem > 227 * 1024) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_rows: group caches exceed shared memory");
-    auto kern = score_rows_kernel<CHUNK, KIND, kSample, kScores, kThreads>;
-    DISTB200_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int per_sm = 0;
-    DISTB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const size_t ntiles = (a.N + kThreads - 1) / kThreads;
-    const size_t max_blocks = static_cast<size_t>(ctx->sm_count) * per_sm;
-    const unsigned grid = static_cast<unsigned>(ntiles < max_blocks ? ntiles : max_blocks);
-    kern<<<grid, kThreads, smem, s>>>(feats, a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("score_rows launch: ") + cudaGetErrorString(e));
-    return DIST_B200_OK;
-}
-
-template <int CHUNK, int KIND>
-static int launch_modes(dist_b200_ctx *ctx, const FeatList &feats, const RowsArgs &a, cudaStream_t s) {
-    const bool sample = a.assign != nullptr, scores = a.scores != nullptr;
-    if (sample && scores) return launch_variant<CHUNK, KIND, true, true>(ctx, feats, a, s);
-    if (sample) return launch_variant<CHUNK, KIND, true, false>(ctx, feats, a, s);
-    return launch_variant<CHUNK, KIND, false, true>(ctx, feats, a, s);
-}
-
-// register tile: the whole row when it fits (the sampler is then the reference's loops verbatim),
-// 64-group tiles otherwise
-template <int KIND>
-static int launch_tiers(dist_b200_ctx *ctx, const FeatList &feats, const RowsArgs &a, cudaStream_t s) {
-    if (a.G <= 32) return launch_modes<32, KIND>(ctx, feats, a, s);
-    if (a.G <= 64) return launch_modes<64, KIND>(ctx, feats, a, s);
-    if (a.G <= 128) return launch_modes<128, KIND>(ctx, feats, a, s);
-    static const int tile = [] {  // tuning knob for profiling runs; measured at c2: 32 -> 0.748 ms, 64 -> 0.774 ms
-        const char *e = getenv("DIST_B200_TILE");
-        return e ? atoi(e) : 32;
-    }();
-    if (tile == 64) return launch_modes<64, KIND>(ctx, feats, a, s);
-    return launch_modes<32, KIND>(ctx, feats, a, s);
-}
-
 int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N, const float *prior,
                       const float *u, int32_t *assign, float *scores, int accumulate, cudaStream_t s,
                       const PushTargets *push) {
@@ -647,11 +54,11 @@ int launch_score_rows(dist_b200_ctx *ctx, const FeatList &feats, int G, size_t N
     if (feats.n == 1) {
         int rc = DIST_B200_ERR_UNSUPPORTED;
         switch (feats.f[0].kind) {
-            case DIST_B200_NICH: rc = launch_tiers<DIST_B200_NICH>(ctx, feats, a, s); break;
-            case DIST_B200_GP: rc = launch_tiers<DIST_B200_GP>(ctx, feats, a, s); break;
-            case DIST_B200_BNB: rc = launch_tiers<DIST_B200_BNB>(ctx, feats, a, s); break;
-            case DIST_B200_BB: rc = launch_tiers<DIST_B200_BB>(ctx, feats, a, s); break;
-            case DIST_B200_DD: rc = launch_tiers<DIST_B200_DD>(ctx, feats, a, s); break;
+            case DIST_B200_NICH: rc = launch_single_nich(ctx, feats, a, s); break;
+            case DIST_B200_GP: rc = launch_single_gp(ctx, feats, a, s); break;
+            case DIST_B200_BNB: rc = launch_single_bnb(ctx, feats, a, s); break;
+            case DIST_B200_BB: rc = launch_single_bb(ctx, feats, a, s); break;
+            case DIST_B200_DD: rc = launch_single_dd(ctx, feats, a, s); break;
         }
         if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;
     }

@@ -147,6 +147,8 @@ class PeerFeatureShards:
     slots (dist_b200_sample_from_slots).  Needs one process per GPU on one NVLink domain.
     """
 
+    launches_per_step = 2  # score + push kernel, slot-sum sampler
+
     def __init__(self, ctx, n_rows, n_groups, group=None):
         self.ctx, self.group = ctx, group
         self.world = dist.get_world_size(group)

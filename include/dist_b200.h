@@ -64,6 +64,22 @@ int dist_b200_ctx_create(int device, dist_b200_ctx **out);
 void dist_b200_ctx_destroy(dist_b200_ctx *ctx);
 const char *dist_b200_last_error(const dist_b200_ctx *ctx);
 int dist_b200_sm_count(const dist_b200_ctx *ctx);
+/* Measurement knobs (bench.py and the profiling scripts A/B kernels with them; a production caller never sets
+ * any: 0 = the library's default everywhere).  The library reads no environment variables. */
+typedef enum {
+    DIST_B200_OPT_VALUE_CDF = 0,   /* single dpd / dd / bb feature, sampling only: 0 = score once per distinct VALUE and
+                                      search per-value CDF trees per row (SURVEY.md 8d "algorithmic shortcut");
+                                      1 = evaluate every (row, group) cell (the no-shortcut kernels) */
+    DIST_B200_OPT_ROW_TILE = 1,    /* score_rows register tile for G > 128: 0 = default (32), else 32 / 64 */
+    DIST_B200_OPT_HOST_CHUNKS = 2, /* row chunks of the host-buffer entry: 0 = default (5) */
+    DIST_B200_OPT_NIW_PATH = 3,    /* d = 32: 0 = tcgen05 3xTF32 (default), 1 = FP32 CUDA-core kernel */
+    DIST_B200_OPT_TABLE_KERNEL = 4,/* dpd no-shortcut kernel: 0 = register kernel on the lane-segment layout, 1 = round-1 gather kernel */
+    DIST_B200_OPT_SMALL_TILE = 5,  /* score_rows, single feature, 64 < G <= 128: 0 = default, 1 = one 128-group tile x 256 threads
+                                      (round 1), 2 = 128 threads x 3 blocks / SM, 3 = four 32-group tiles */
+    DIST_B200_OPT_NICH_PACKED = 6, /* nich single feature: 0 = packed f32x2 loop (default), 1 = scalar loop (round 1) */
+    DIST_B200_OPT_COUNT_ = 16
+} dist_b200_option;
+int dist_b200_ctx_set_option(dist_b200_ctx *ctx, int option, int value);
 
 /* ---- features: MixtureValueScorer::{resize, update_all, update_group, add_group, remove_group}
  * All statistics arrays are host pointers holding the reference's Group fields as
@@ -326,7 +342,9 @@ int dist_b200_numerics_probe(dist_b200_ctx *ctx, int fn, size_t n, const float *
                              void *stream);
 
 /* Register-only pipe probes for roofline denominators that MEASURED_PEAKS.json does not carry:
- * which = 0: MUFU (ex2/lg2) lane-ops per second, 1: FP32 FMA lane-ops per second, whole device. */
+ * which = 0: MUFU (ex2/lg2) lane-ops per second, 1: FP32 FMA lane-ops per second, whole device;
+ * which = 2: L2 gather BYTES per second with the dpd table kernel's access pattern (random 2 KB rows of an
+ * L2-resident 8 MB table, LDG.128) -- the denominator of c4's gather bound. */
 int dist_b200_pipe_peak(dist_b200_ctx *ctx, int which, double *ops_per_s);
 
 #ifdef __cplusplus
