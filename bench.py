@@ -498,14 +498,17 @@ class Bench:
         return rec, clocks
 
     # ---- c3 at N > 1: the features of one cross-cat kind sharded over the ranks (strong scaling) -----------------
-    def run_feature_sharded(self, name, steps, warmup, mode):
-        torch, ctx, capi, dist = self.torch, self.ctx, self.capi, self.dist
+    def run_feature_sharded(self, name, steps, warmup, mode, row_shards=1):
+        """mode "push": NVLink peer push (row_shards > 1: the feature x row hybrid); "rs": NCCL reduce-scatter"""
+        torch, ctx, capi = self.torch, self.ctx, self.capi
         from distributions_b200 import sharding
-        wl = make_workload(name, 0)  # the same table on every rank; each rank keeps its features
+        wl = make_workload(name, 0)  # the same table on every rank; each rank keeps its (features, rows) block
         G, N, F = wl["G"], wl["N"], len(wl["feats"])
-        mine = sharding.feature_shard(F, self.rank, self.world)
+        peer = sharding.PeerFeatureShards(ctx, N, G, row_shards=row_shards) if mode == "push" else None
+        mine = peer.features(F) if peer else sharding.feature_shard(F, self.rank, self.world)
+        r0, r1 = peer.rows() if peer else (0, N)
         feats = [ctx.feature(model_id(capi, wl["feats"][f]["model"])).update_all(wl["feats"][f]) for f in mine]
-        cols = [torch.from_numpy(np.ascontiguousarray(wl["feats"][f]["values"],
+        cols = [torch.from_numpy(np.ascontiguousarray(wl["feats"][f]["values"][r0:r1],
                                                       dtype=capi.COLUMN_DTYPE[model_id(capi, wl["feats"][f]["model"])])).to(self.dev)
                 for f in mine]
         u = torch.from_numpy(wl["u"]).to(self.dev)
@@ -522,14 +525,14 @@ class Bench:
             ctx.sample_from_scores(scores, scores.shape[0], G, ub, out, stream=self.stream)
             launches[0] += 1
 
-        peer = sharding.PeerFeatureShards(ctx, N, G) if mode == "push" else None
         lo_own, hi_own = peer.owned() if peer else (0, 0)
         assign_own = torch.empty(max(hi_own - lo_own, 1), device=self.dev, dtype=torch.int32)
+        u_own = u[lo_own:hi_own]
 
         def step():
             if peer is not None:
                 launches[0] += peer.launches_per_step
-                return peer.step(feats, cols, prior, u, assign_own, stream=self.stream)
+                return peer.step(feats, cols, prior, u_own, assign_own, stream=self.stream)
             return sharding.feature_sharded_score_sample(score_partial, sample_block, N, G, u, self.dev, tile_rows=self.args.tile_rows,
                                                          comm_stream=comm)
 
@@ -538,17 +541,22 @@ class Bench:
         step()
         self.barrier()
         per_step = launches[0]
+        fs = peer.fs if peer else self.world
         if peer is not None:
             peer.close()
         cells = float(N) * F * G
-        rec = {"workload": name, "rows": N, "groups": G, "features": F, "features_per_rank": len(mine), "steps": steps,
+        rows_group = r1 - r0
+        rec = {"workload": name, "rows": N, "groups": G, "features": F, "features_per_rank": len(mine), "rows_per_group": rows_group,
+               "feature_shards": fs, "row_shards": self.world // fs, "steps": steps,
                "scaling": "strong", "ms_per_step": ms, "value": cells / (ms * 1e-3), "gpu_launches_per_step": per_step,
-               "parallelism": ("feature shards; partial rows stored into the owning rank's memory over NVLink from inside the score "
-                               "kernel, the owner samples the fixed-order sum of its slots" if mode == "push" else
+               "parallelism": ("feature shards" + (" x row shards (hybrid)" if fs != self.world else "") +
+                               "; partial rows stored into the owning rank's memory over NVLink from inside the score kernel "
+                               "(16-byte stores), device-side epoch flags instead of host barriers, the owner samples the "
+                               "fixed-order sum of its slots" if mode == "push" else
                                "feature shards + NCCL reduce-scatter(sum) of [rows][G] partials, tiles of %d rows overlapped on a "
                                "second stream" % self.args.tile_rows),
-               "nvlink_bytes_per_step_per_rank": int(4 * N * G * (self.world - 1) / self.world),
-               "l2": "inputs (640 MB of columns + 512 MB of partial scores per step) exceed the 126 MB L2"}
+               "nvlink_bytes_per_step_per_rank": int(4 * rows_group * G * (fs - 1) / fs),
+               "l2": "inputs (640 MB of columns + 512 MB of partial scores per step over the ranks) exceed the 126 MB L2"}
         del feats, cols
         torch.cuda.empty_cache()
         return rec
@@ -558,7 +566,7 @@ def run_b200(args):
     b = Bench(args)
     torch = b.torch
     if args.feature_sharded and b.world > 1:
-        r = b.run_feature_sharded("c3_crosscat", args.steps, args.warmup, args.feature_sharded)
+        r = b.run_feature_sharded("c3_crosscat", args.steps, args.warmup, "rs" if args.feature_sharded == "rs" else "push", args.row_shards)
         if b.rank == 0:
             print(json.dumps(r))
         b.dist.destroy_process_group()
@@ -578,8 +586,11 @@ def run_b200(args):
             r["scaling"] = "weak"
             r["parallelism"] = "row shards: caches and prior replicated, every rank scores its own 10M-row shard, no collective"
             configs["c4_dpd_row_sharded"] = r
-            for mode in ("push", "rs"):
-                configs["c3_crosscat_feature_sharded_" + mode] = b.run_feature_sharded("c3_crosscat", sub_steps, args.warmup, mode)
+            variants = [("push", "push", 1), ("rs", "rs", 1)]
+            if b.world >= 4:  # feature x row hybrid: 2 feature shards, world / 2 row shards
+                variants.append(("hybrid_2x%d" % (b.world // 2), "push", b.world // 2))
+            for label, mode, row_shards in variants:
+                configs["c3_crosscat_feature_sharded_" + label] = b.run_feature_sharded("c3_crosscat", sub_steps, args.warmup, mode, row_shards)
             # the same table on ONE GPU in the same run (rank 0 only, the others wait): the strong-scaling reference
             t1 = torch.zeros(1, device=b.dev, dtype=torch.float64)
             if b.rank == 0:
@@ -589,8 +600,8 @@ def run_b200(args):
                 t1[0] = r1["ms_per_step"]
             b.barrier()
             b.dist.broadcast(t1, 0)
-            for mode in ("push", "rs"):
-                r = configs["c3_crosscat_feature_sharded_" + mode]
+            for label, _, _ in variants:
+                r = configs["c3_crosscat_feature_sharded_" + label]
                 r["single_gpu_ms_same_run"] = float(t1.item())
                 r["strong_scaling_efficiency"] = float(t1.item()) / (b.world * r["ms_per_step"])
     if b.rank != 0:
@@ -639,6 +650,7 @@ def main():
                     help="headline: each step is a blocked Gibbs pass on the device: remove_value, score+sample, add_value, cache / prior refresh")
     ap.add_argument("--feature-sharded", default=None, choices=["push", "rs"],
                     help="N > 1 only: time just c3_crosscat feature-sharded in this mode (development runs)")
+    ap.add_argument("--row-shards", type=int, default=1, help="with --feature-sharded push: feature x row hybrid")
     ap.add_argument("--tile-rows", type=int, default=65536, help="row tile of the feature-sharded reduce-scatter")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -29,6 +29,7 @@ SOURCES = {
     "score_rows_dd.cu": [],
     "gather_rows.cu": [],
     "table_rows.cu": [],
+    "peer.cu": [],
     "niw.cu": [],
     "niw_tc.cu": [],
     "microbench.cu": [],

@@ -75,6 +75,8 @@ SIGNATURES = {
     "dist_b200_peer_close": (c_i, [c_p, c_p]),
     "dist_b200_peer_free": (c_i, [c_p, c_p]),
     "dist_b200_score_push_batch": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_sz, c_p, c_p, c_i, c_sz, c_p]),
+    "dist_b200_peer_signal": (c_i, [c_p, c_p, c_i, c_i, ctypes.c_uint32, c_p]),
+    "dist_b200_peer_wait": (c_i, [c_p, c_p, c_i, ctypes.c_uint32, c_p]),
     "dist_b200_sample_from_slots": (c_i, [c_p, c_p, c_i, c_sz, c_sz, c_i, c_p, c_p, c_p]),
     "dist_b200_score_sample_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_p, c_p]),
     "dist_b200_score_value_host": (c_i, [c_p, c_p, c_p, c_p]),
@@ -357,6 +359,13 @@ class Context:
         self.check(self.L.dist_b200_score_push_batch(self.h, fa, F, ca, n_rows, row0, _dev_ptr(prior), sp, len(slot_ptrs),
                                                      block_rows, stream), "score_push_batch")
 
+    def peer_signal(self, flag_ptrs, my_index, epoch, stream=None):
+        fp = (c_p * len(flag_ptrs))(*flag_ptrs)
+        self.check(self.L.dist_b200_peer_signal(self.h, fp, len(flag_ptrs), my_index, epoch, stream), "peer_signal")
+
+    def peer_wait(self, flags, n_peers, epoch, stream=None):
+        self.check(self.L.dist_b200_peer_wait(self.h, _dev_ptr(flags), n_peers, epoch, stream), "peer_wait")
+
     def sample_from_slots(self, slots, n_slots, slot_stride, n_rows, G, u, assign, stream=None):
         self.check(self.L.dist_b200_sample_from_slots(self.h, _dev_ptr(slots), n_slots, slot_stride, n_rows, G, _dev_ptr(u),
                                                       _dev_ptr(assign), stream), "sample_from_slots")
@@ -369,6 +378,8 @@ class Context:
         cols = [np.ascontiguousarray(c, dtype=COLUMN_DTYPE[f.model]) for f, c in zip(features, columns)]
         n = u.shape[0]
         G = features[0].groups
+        for f, c in zip(features, cols):
+            assert c.size == n or (f.model == NIW and c.size % n == 0), "column length != len(u)"
         fa = (c_p * F)(*[f.h for f in features])
         ca = (c_p * F)(*[c.ctypes.data for c in cols])
         prior = None if prior is None else np.ascontiguousarray(prior, dtype=np.float32)

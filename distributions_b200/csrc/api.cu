@@ -178,7 +178,38 @@ struct Upload {
     }
 };
 
-// dpd caches: the canonical value-major table (dpd.hpp:471-497) and its lane-segment copy for table_rows.cu
+// dpd storage: table (V + 2) x capacity floats (dense stride G inside it), statistics counts[capacity][V] | betas[V]
+uint32_t *dpd_betas(const dist_b200_feature *f) { return f->stats + static_cast<size_t>(f->capacity) * f->dim; }
+int dpd_reserve(dist_b200_feature *f, int G, int V, bool keep) {
+    dist_b200_ctx *ctx = f->ctx;
+    const int need = std::max(G, 1);
+    const bool fits = f->params && f->stats && need <= f->capacity &&
+                      f->params_bytes >= sizeof(float) * static_cast<size_t>(V + 2) * f->capacity &&
+                      f->stats_words >= static_cast<size_t>(f->capacity) * V + V;
+    if (fits) return DIST_B200_OK;
+    const int cap = static_cast<int>(round_up(static_cast<size_t>(need) + need / 4, 8));
+    void *params = nullptr;
+    uint32_t *stats = nullptr;
+    const size_t pbytes = sizeof(float) * static_cast<size_t>(V + 2) * cap, words = static_cast<size_t>(cap) * V + V;
+    DISTB200_CUDA(ctx, cudaMalloc(&params, pbytes));
+    DISTB200_CUDA(ctx, cudaMalloc(&stats, words * 4));
+    DISTB200_CUDA(ctx, cudaMemset(stats, 0, words * 4));
+    DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+    if (keep && f->stats && f->G > 0) {  // counts rows are contiguous; betas move with the capacity
+        DISTB200_CUDA(ctx, cudaMemcpy(stats, f->stats, sizeof(int32_t) * static_cast<size_t>(f->G) * V, cudaMemcpyDeviceToDevice));
+        DISTB200_CUDA(ctx, cudaMemcpy(stats + static_cast<size_t>(cap) * V, dpd_betas(f), sizeof(float) * V, cudaMemcpyDeviceToDevice));
+    }
+    if (f->params) DISTB200_CUDA(ctx, cudaFree(f->params));
+    if (f->stats) DISTB200_CUDA(ctx, cudaFree(f->stats));
+    f->params = params;
+    f->params_bytes = pbytes;
+    f->stats = stats;
+    f->stats_words = words;
+    f->capacity = cap;
+    return DIST_B200_OK;
+}
+
+// dpd caches: the canonical value-major table (dpd.hpp:471-497) + the scratch table_rows.cu re-lays it out into per call
 int dpd_rebuild(dist_b200_feature *f, const float *betas_dev, const int32_t *counts_dev, cudaStream_t s) {
     dist_b200_ctx *ctx = f->ctx;
     int rc = launch_dpd_prep(ctx, f->alpha, f->beta0, f->dim, betas_dev, f->G, counts_dev, static_cast<float *>(f->params), s);
@@ -194,7 +225,7 @@ int dpd_rebuild(dist_b200_feature *f, const float *betas_dev, const int32_t *cou
         DISTB200_CUDA(ctx, cudaMalloc(&f->dpd_hot, need * sizeof(float)));
         f->dpd_hot_floats = need;
     }
-    return launch_table_hot(ctx, f->dim + 1, f->G, static_cast<const float *>(f->params), f->dpd_hot, s);
+    return DIST_B200_OK;
 }
 
 bool check_feature(const dist_b200_feature *f, int model) { return f && f->ctx && f->model == model; }
@@ -472,8 +503,7 @@ int dist_b200_dpd_update_all(dist_b200_feature *f, float alpha, float beta0, int
     f->keys_dense = dense;
     f->dim = V;
     f->alphas.assign(betas, betas + V);
-    f->params_bytes = f->params_bytes;  // (table is reallocated by ensure_params when G or V grew)
-    int rc = ensure_params(f, G, false);
+    int rc = dpd_reserve(f, G, V, false);
     if (rc) return rc;
     if ((rc = ensure_scratch(ctx, round_up(sizeof(float) * V, 256) + round_up(sizeof(int32_t) * static_cast<size_t>(G) * V, 256) + 256))) return rc;
     Upload up{ctx, as_stream(stream)};
@@ -481,22 +511,12 @@ int dist_b200_dpd_update_all(dist_b200_feature *f, float alpha, float beta0, int
     const int32_t *c = up.put(counts, static_cast<size_t>(G) * V);
     if (up.err) return up.err;
     f->G = G;
-    {   // device-resident statistics: counts[G][V] | betas[V]
-        const size_t words = static_cast<size_t>(G) * V + V;
-        if (words > f->stats_words) {
-            if (f->stats) {
-                DISTB200_CUDA(ctx, cudaDeviceSynchronize());
-                DISTB200_CUDA(ctx, cudaFree(f->stats));
-                f->stats = nullptr;
-            }
-            DISTB200_CUDA(ctx, cudaMalloc(&f->stats, words * 4));
-            f->stats_words = words;
-        }
-        DISTB200_CUDA(ctx, cudaMemcpyAsync(f->stats, c, sizeof(int32_t) * static_cast<size_t>(G) * V, cudaMemcpyDeviceToDevice, as_stream(stream)));
-        DISTB200_CUDA(ctx, cudaMemcpyAsync(f->stats + static_cast<size_t>(G) * V, b, sizeof(float) * V, cudaMemcpyDeviceToDevice, as_stream(stream)));
-    }
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(f->stats, c, sizeof(int32_t) * static_cast<size_t>(G) * V, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(dpd_betas(f), b, sizeof(float) * V, cudaMemcpyDeviceToDevice, as_stream(stream)));
     return mark_ready(f, dpd_rebuild(f, b, c, as_stream(stream)), as_stream(stream));
 }
+
+static int niw_reserve(dist_b200_feature *f, int G, int keep);
 
 int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float kappa, const float *psi,
                              float nu, int G, const int32_t *count, const float *sum_x, const float *sum_xxT,
@@ -507,16 +527,10 @@ int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float
     if (d > 32) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "niw: d > 32");
     if (!(kappa > 0.f) || !(nu > static_cast<float>(d) - 1.f))
         return fail(ctx, DIST_B200_ERR_INVALID, "niw: need kappa > 0 and nu > d - 1 (niw.hpp:121,132)");
-    const size_t rec = static_cast<size_t>(niw_padded_dim(d)) * (niw_padded_dim(d) + 1) + 4;
-    const size_t bytes = sizeof(float) * rec * std::max(G, 1);
-    if (bytes > f->niw_bytes) {
-        if (f->niw_buf) {
-            DISTB200_CUDA(ctx, cudaDeviceSynchronize());
-            DISTB200_CUDA(ctx, cudaFree(f->niw_buf));
-            f->niw_buf = nullptr;
-        }
-        DISTB200_CUDA(ctx, cudaMalloc(&f->niw_buf, bytes));
-        f->niw_bytes = bytes;
+    f->dim = d;
+    {
+        int rcr = niw_reserve(f, G, 0);
+        if (rcr) return rcr;
     }
     const size_t dd = static_cast<size_t>(d) * d;
     int rc = ensure_scratch(ctx, round_up(4 * d, 256) + round_up(4 * dd, 256) + round_up(4 * static_cast<size_t>(G), 256) +
@@ -533,21 +547,67 @@ int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float
     f->G = G;
     f->kappa = kappa;
     f->nu = nu;
+    f->mu.assign(mu, mu + d);
+    f->psi.assign(psi, psi + dd);
     int rc2 = launch_niw_prep(ctx, d, mu_d, kappa, psi_d, nu, G, cnt_d, sx_d, sxx_d, f->niw_buf, as_stream(stream));
-    if (rc2 == DIST_B200_OK && d == 32 && G > 0) {  // operand images for the tensor-core path
-        const size_t tc_bytes = sizeof(float) * niw_tc_floats(G);
+    if (rc2 == DIST_B200_OK && d == 32 && G > 0) rc2 = launch_niw_tc_prep(ctx, G, f->niw_buf, f->niw_tc, as_stream(stream));
+    return mark_ready(f, rc2, as_stream(stream));
+}
+
+// NormalInverseWishart: one group's record (posterior, whitening matrix, constants) from its raw statistics
+// {int32 count; float sum_x[d]; float sum_xxT[d][d]} (niw.hpp:187-190, :247-276), then the tensor-core block records
+static int niw_update_group(dist_b200_feature *f, int groupid, const void *stats, cudaStream_t s) {
+    dist_b200_ctx *ctx = f->ctx;
+    const int d = f->dim;
+    const size_t dd = static_cast<size_t>(d) * d;
+    if (f->mu.size() != static_cast<size_t>(d) || f->psi.size() != dd) return fail(ctx, DIST_B200_ERR_STATE, "niw update_group: call update_all first");
+    int rc = ensure_scratch(ctx, round_up(4 * d, 256) * 2 + round_up(4 * dd, 256) * 2 + 512);
+    if (rc) return rc;
+    const char *p = static_cast<const char *>(stats);
+    Upload up{ctx, s};
+    const float *mu_d = up.put(f->mu.data(), d);
+    const float *psi_d = up.put(f->psi.data(), dd);
+    const int32_t *cnt_d = up.put(reinterpret_cast<const int32_t *>(p), 1);
+    const float *sx_d = up.put(reinterpret_cast<const float *>(p + 4), d);
+    const float *sxx_d = up.put(reinterpret_cast<const float *>(p + 4 + 4 * d), dd);
+    if (up.err) return up.err;
+    const size_t rec = static_cast<size_t>(niw_padded_dim(d)) * (niw_padded_dim(d) + 1) + 4;
+    rc = launch_niw_prep(ctx, d, mu_d, f->kappa, psi_d, f->nu, 1, cnt_d, sx_d, sxx_d, f->niw_buf + rec * groupid, s);
+    if (rc == DIST_B200_OK && d == 32 && f->niw_tc) rc = launch_niw_tc_prep(ctx, f->G, f->niw_buf, f->niw_tc, s);
+    return mark_ready(f, rc, s);
+}
+
+// (re)allocate the niw record buffers for G groups, keeping the first `keep` records
+static int niw_reserve(dist_b200_feature *f, int G, int keep) {
+    dist_b200_ctx *ctx = f->ctx;
+    const int d = f->dim;
+    const size_t rec = static_cast<size_t>(niw_padded_dim(d)) * (niw_padded_dim(d) + 1) + 4;
+    const size_t bytes = sizeof(float) * rec * std::max(G, 1);
+    if (bytes > f->niw_bytes) {
+        const size_t want = bytes + bytes / 4;
+        float *fresh = nullptr;
+        DISTB200_CUDA(ctx, cudaMalloc(&fresh, want));
+        DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+        if (f->niw_buf) {
+            if (keep > 0) DISTB200_CUDA(ctx, cudaMemcpy(fresh, f->niw_buf, sizeof(float) * rec * keep, cudaMemcpyDeviceToDevice));
+            DISTB200_CUDA(ctx, cudaFree(f->niw_buf));
+        }
+        f->niw_buf = fresh;
+        f->niw_bytes = want;
+    }
+    if (d == 32) {
+        const size_t tc_bytes = sizeof(float) * niw_tc_floats(std::max(G, 1));
         if (tc_bytes > f->niw_tc_bytes) {
             if (f->niw_tc) {
                 DISTB200_CUDA(ctx, cudaDeviceSynchronize());
                 DISTB200_CUDA(ctx, cudaFree(f->niw_tc));
                 f->niw_tc = nullptr;
             }
-            DISTB200_CUDA(ctx, cudaMalloc(&f->niw_tc, tc_bytes));
-            f->niw_tc_bytes = tc_bytes;
+            DISTB200_CUDA(ctx, cudaMalloc(&f->niw_tc, tc_bytes + tc_bytes / 4));
+            f->niw_tc_bytes = tc_bytes + tc_bytes / 4;
         }
-        rc2 = launch_niw_tc_prep(ctx, G, f->niw_buf, f->niw_tc, as_stream(stream));
     }
-    return mark_ready(f, rc2, as_stream(stream));
+    return DIST_B200_OK;
 }
 
 int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void *stats, void *stream) {
@@ -604,16 +664,45 @@ int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void
             if ((rc = mirror_stats(f, 0, c, groupid, 1, s))) return rc;
             return mark_ready(f, launch_dd_prep(ctx, f->dim, a, f->alpha_sum, groupid, 1, c, static_cast<float *>(f->params), s), s);
         }
+        case DIST_B200_DPD: {  // stats: the group's dense counts[V], in update_all's key order
+            const int V = f->dim;
+            if ((rc = ensure_scratch(ctx, round_up(sizeof(int32_t) * V, 256) + 256))) return rc;
+            Upload up2{ctx, s};
+            const int32_t *c = up2.put(static_cast<const int32_t *>(stats), V);
+            if (up2.err) return up2.err;
+            int32_t *row = reinterpret_cast<int32_t *>(f->stats) + static_cast<size_t>(groupid) * V;
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(row, c, sizeof(int32_t) * V, cudaMemcpyDeviceToDevice, s));
+            return mark_ready(f, launch_dpd_update_group(ctx, f->alpha, f->beta0, V, reinterpret_cast<const float *>(dpd_betas(f)), f->G, groupid,
+                                                         row, static_cast<float *>(f->params), s), s);
+        }
+        case DIST_B200_NIW: return niw_update_group(f, groupid, stats, s);
         default:
-            return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "update_group: use update_all for this model");
+            return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "update_group: unknown model");
     }
 }
 
 int dist_b200_feature_add_group(dist_b200_feature *f, void *stream) {
     if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
     dist_b200_ctx *ctx = f->ctx;
-    if (f->model == DIST_B200_DPD || f->model == DIST_B200_NIW)
-        return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_group: use update_all for this model");
+    if (f->model == DIST_B200_DPD) {
+        // a fresh empty group: one more zero counts row; the dense table's stride is G, so it is rebuilt (O(V G))
+        if (f->G < 1 && !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "add_group: call update_all first");
+        int rc = dpd_reserve(f, f->G + 1, f->dim, true);
+        if (rc) return rc;
+        cudaStream_t s = as_stream(stream);
+        DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
+        DISTB200_CUDA(ctx, cudaMemsetAsync(f->stats + static_cast<size_t>(f->G) * f->dim, 0, sizeof(int32_t) * f->dim, s));
+        f->G += 1;
+        return mark_ready(f, dpd_rebuild(f, reinterpret_cast<const float *>(dpd_betas(f)), reinterpret_cast<const int32_t *>(f->stats), s), s);
+    }
+    if (f->model == DIST_B200_NIW) {
+        if (f->mu.empty()) return fail(ctx, DIST_B200_ERR_STATE, "add_group: call update_all first");
+        int rc = niw_reserve(f, f->G + 1, f->G);
+        if (rc) return rc;
+        f->G += 1;
+        std::vector<float> zeros(1 + f->dim + static_cast<size_t>(f->dim) * f->dim, 0.f);  // Group::init: count = 0, sums = 0
+        return niw_update_group(f, f->G - 1, zeros.data(), as_stream(stream));
+    }
     int rc = ensure_params(f, f->G + 1, true);
     if (rc) return rc;
     f->G += 1;
@@ -626,9 +715,29 @@ int dist_b200_feature_add_group(dist_b200_feature *f, void *stream) {
 int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stream) {
     if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
     dist_b200_ctx *ctx = f->ctx;
-    if (f->model == DIST_B200_DPD || f->model == DIST_B200_NIW)
-        return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "remove_group: use update_all for this model");
     if (groupid < 0 || groupid >= f->G) return fail(ctx, DIST_B200_ERR_INVALID, "remove_group: bad groupid");
+    if (f->model == DIST_B200_DPD) {  // packed_remove on the counts rows, then the dense table again
+        cudaStream_t s = as_stream(stream);
+        DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
+        const int last = f->G - 1, V = f->dim;
+        if (groupid != last)
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(f->stats + static_cast<size_t>(groupid) * V, f->stats + static_cast<size_t>(last) * V,
+                                               sizeof(int32_t) * V, cudaMemcpyDeviceToDevice, s));
+        f->G = last;
+        return mark_ready(f, dpd_rebuild(f, reinterpret_cast<const float *>(dpd_betas(f)), reinterpret_cast<const int32_t *>(f->stats), s), s);
+    }
+    if (f->model == DIST_B200_NIW) {
+        cudaStream_t s = as_stream(stream);
+        DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
+        const size_t rec = static_cast<size_t>(niw_padded_dim(f->dim)) * (niw_padded_dim(f->dim) + 1) + 4;
+        const int last = f->G - 1;
+        if (groupid != last)
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(f->niw_buf + rec * groupid, f->niw_buf + rec * last, sizeof(float) * rec, cudaMemcpyDeviceToDevice, s));
+        f->G = last;
+        int rc = DIST_B200_OK;
+        if (f->dim == 32 && f->niw_tc && f->G > 0) rc = launch_niw_tc_prep(ctx, f->G, f->niw_buf, f->niw_tc, s);
+        return mark_ready(f, rc, s);
+    }
     const size_t gb = sizeof(float) * group_floats(f);
     char *base = static_cast<char *>(f->params);
     const int last = f->G - 1;
@@ -752,8 +861,7 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
                 break;
             case DIST_B200_DPD:
                 if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, sign, s))) return rc;
-                if ((rc = dpd_rebuild(f, reinterpret_cast<const float *>(f->stats + static_cast<size_t>(G) * f->dim),
-                                      reinterpret_cast<const int32_t *>(f->stats), s)))
+                if ((rc = dpd_rebuild(f, reinterpret_cast<const float *>(dpd_betas(f)), reinterpret_cast<const int32_t *>(f->stats), s)))
                     return rc;
                 break;
             default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: unsupported model");
@@ -901,7 +1009,7 @@ int dist_b200_score_data_grid(dist_b200_feature *f, const float *shareds_dev, si
     const float *betas = nullptr;
     if (f->model == DIST_B200_DPD) {
         st0 = f->stats;
-        betas = reinterpret_cast<const float *>(f->stats + static_cast<size_t>(f->G) * f->dim);
+        betas = reinterpret_cast<const float *>(dpd_betas(f));
     } else {
         st0 = stat_ptr(f, 0);
         if (stat_arrays(f) > 1) st1 = stat_ptr(f, 1);
@@ -1353,6 +1461,10 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
         if (int rc = launch_gp_table_batch(ctx, tb, s)) return rc;
         return launch_score_rows(ctx, fl, G, N, prior, u, assign, scores, accumulate, s);
     }
+    // one NIW<32> feature, sampling only: quadratic forms, scores and sample_from_scores in one tcgen05 kernel
+    if (F == 1 && features[0]->model == DIST_B200_NIW && features[0]->dim == 32 && features[0]->niw_tc && assign && !scores &&
+        !accumulate && ctx->opt[DIST_B200_OPT_NIW_PATH] == 0)
+        return launch_niw_tc(ctx, G, features[0]->niw_tc, columns[0], N, prior, nullptr, 0, u, assign, s);
     if (F == 1 && features[0]->model == DIST_B200_DPD) {
         if (assign && !scores && !accumulate && ctx->opt[DIST_B200_OPT_TABLE_KERNEL] == 0) {
             const int rc = launch_table_rows(ctx, features[0], columns[0], N, prior, u, assign, s);
@@ -1423,6 +1535,7 @@ int dist_b200_peer_alloc(dist_b200_ctx *ctx, size_t bytes, void **dev_ptr, unsig
     if (!ctx || !dev_ptr || !handle_out || bytes == 0) return DIST_B200_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     DISTB200_CUDA(ctx, cudaMalloc(dev_ptr, bytes));
+    DISTB200_CUDA(ctx, cudaMemset(*dev_ptr, 0, bytes));  // epoch flags start at 0
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
     if (e != cudaSuccess) {

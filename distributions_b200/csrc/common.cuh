@@ -127,7 +127,7 @@ struct dist_b200_feature {
     float *log_prod_dev = nullptr;    // gp: Group::log_prod per group (read by score_data only)
     int log_prod_cap = 0;
     bool log_prod_valid = false;      // cleared by every statistics mutation that does not maintain it
-    float *dpd_hot = nullptr;         // dpd: the table in the lane-segment layout of table_rows.cu
+    float *dpd_hot = nullptr;         // dpd: per-call scratch of table_rows.cu (the table with prior / row max folded in)
     size_t dpd_hot_floats = 0;
     float *cdf_buf = nullptr;         // dpd / dd / bb: per-value CDF trees (rebuilt per scoring call: they carry the prior)
     size_t cdf_floats = 0;
@@ -171,6 +171,8 @@ int launch_dd_prep(dist_b200_ctx *ctx, int dim, const float *alphas_dev, float a
                    const int32_t *counts_dev, float *table, cudaStream_t s);
 int launch_dpd_prep(dist_b200_ctx *ctx, float alpha, float beta0, int V, const float *betas_dev, int G,
                     const int32_t *counts_dev, float *table, cudaStream_t s);
+int launch_dpd_update_group(dist_b200_ctx *ctx, float alpha, float beta0, int V, const float *betas, int G, int g,
+                            const int32_t *counts_row, float *table, cudaStream_t s);
 int launch_prior_prep(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *sizes_dev, float *prior,
                       cudaStream_t s);
 int launch_low_entropy_prep(dist_b200_ctx *ctx, int dataset_size, int G, const int32_t *sizes_dev, float *prior,
@@ -207,7 +209,6 @@ int launch_sample_scores(dist_b200_ctx *ctx, const float *scores, size_t N, int 
                          int32_t *assign, cudaStream_t s, int n_slots = 1, size_t slot_stride = 0);
 // table_rows.cu: single table feature (dpd / dd / bb)
 size_t table_hot_floats(int R, int G);
-int launch_table_hot(dist_b200_ctx *ctx, int R, int G, const float *table, float *hot, cudaStream_t s);
 int launch_table_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *column, size_t N, const float *prior,
                       const float *u, int32_t *assign, cudaStream_t s);
 size_t value_cdf_floats(int R, int G);
@@ -222,8 +223,9 @@ int launch_niw_scores(dist_b200_ctx *ctx, const dist_b200_feature *f, const void
 // niw_tc.cu (tcgen05 / TMEM path, d = 32)
 size_t niw_tc_floats(int G);
 int launch_niw_tc_prep(dist_b200_ctx *ctx, int G, const float *recs, float *tc_buf, cudaStream_t s);
-int launch_niw_tc_scores(dist_b200_ctx *ctx, int G, const float *tc_buf, const void *values, size_t N, const float *prior,
-                         float *scores, int accumulate, bool split, cudaStream_t s);
+// scores != nullptr: [N][G] scores (optionally accumulated onto the buffer); scores == nullptr: the fused sampler writes assign[N]
+int launch_niw_tc(dist_b200_ctx *ctx, int G, const float *tc_buf, const void *values, size_t N, const float *prior,
+                  float *scores, int accumulate, const float *u, int32_t *assign, cudaStream_t s);
 
 // wire.cu: protobuf wire format of the reference (schema.proto) -> SoA.  Decoded feature: Shared floats
 // (+ dpd keys) and the statistics arrays in update_all's argument order.

@@ -266,9 +266,9 @@ int launch_niw_prep(dist_b200_ctx *ctx, int d, const float *mu, float kappa, con
 int launch_niw_scores(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *values, size_t N,
                       const float *prior, float *scores, int accumulate, cudaStream_t s) {
     if (N == 0 || f->G == 0) return DIST_B200_OK;
-    // d = 32: tcgen05 with split (3xTF32) operands; DIST_B200_OPT_NIW_PATH = 1 keeps the FP32 CUDA-core kernel for A/B runs
+    // d = 32: tcgen05 with split fp16 operands; DIST_B200_OPT_NIW_PATH = 1 keeps the FP32 CUDA-core kernel for A/B runs
     if (f->dim == 32 && f->niw_tc && ctx->opt[DIST_B200_OPT_NIW_PATH] == 0) {
-        const int rc = launch_niw_tc_scores(ctx, f->G, f->niw_tc, values, N, prior, scores, accumulate, true, s);
+        const int rc = launch_niw_tc(ctx, f->G, f->niw_tc, values, N, prior, scores, accumulate, nullptr, nullptr, s);
         if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;
     }
     NiwArgs a{};

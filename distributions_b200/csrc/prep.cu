@@ -593,6 +593,39 @@ int launch_dpd_prep(dist_b200_ctx *ctx, float alpha, float beta0, int V, const f
     return DIST_B200_OK;
 }
 
+// MixtureValueScorer::update_group for dpd (dpd.hpp:430-469 rebuild one group's entries): column g of the table
+// and shift[g], from that group's dense counts row.  One block.
+__global__ void dpd_update_group_kernel(float alpha, float beta0, int V, const float *__restrict__ betas, int G, int g,
+                                        const int32_t *__restrict__ counts_row, float *__restrict__ table, NumericTables t) {
+    __shared__ long long part[8];
+    __shared__ float s_shift;
+    long long total = 0;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) total += counts_row[v];
+    for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long all = 0;
+        for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) all += part[w];
+        s_shift = fast_log_table(alpha + static_cast<float>(all), t.log2_table);
+        table[static_cast<size_t>(V + 1) * G + g] = s_shift;
+    }
+    __syncthreads();
+    const float shift = s_shift;
+    for (int v = threadIdx.x; v <= V; v += blockDim.x) {
+        const float sc = v < V ? fast_log_table(alpha * betas[v] + static_cast<float>(counts_row[v]), t.log2_table)
+                               : fast_log_table(alpha * beta0, t.log2_table);
+        table[static_cast<size_t>(v) * G + g] = sc - shift;
+    }
+}
+
+int launch_dpd_update_group(dist_b200_ctx *ctx, float alpha, float beta0, int V, const float *betas, int G, int g,
+                            const int32_t *counts_row, float *table, cudaStream_t s) {
+    dpd_update_group_kernel<<<1, 256, 0, s>>>(alpha, beta0, V, betas, G, g, counts_row, table, ctx->tables);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
 int launch_prior_prep(dist_b200_ctx *ctx, float alpha, float d, int G, const int32_t *sizes, float *prior,
                       cudaStream_t s) {
     const int blocks = G <= 256 ? 1 : (G + 255) / 256 < 64 ? (G + 255) / 256 : 64;

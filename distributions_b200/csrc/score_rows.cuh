@@ -35,6 +35,11 @@ namespace distb200 {
 // {-mean_a, -mean_b, prec_a, prec_b | coef_a, coef_b, score_a, score_b}, so that the hot loop runs on packed
 // fp32x2 instructions (two cells per FADD2 / FMUL2 / FFMA2: 8 issue slots per cell instead of 11.5)
 constexpr int kKindNichPacked = 17;
+// internal single-feature kind: DirichletDiscrete, G <= 128, sampling only.  The block's cache copy holds, per
+// (group, value), (prior[g] + scores_[v][g] - shift[g] - m_v) * log2(e) with m_v the maximum over groups for that
+// value -- what scores_to_likelihoods would subtract for any row carrying v (random.cc:94-106) -- so a cell is one
+// shared-memory gather + MUFU.EX2, and the walk runs over pair sums (half the registers: five blocks per SM).
+constexpr int kKindDdScaled = 18;
 
 constexpr int kSlots = 16;
 constexpr int kStages = 3;  // cp.async ring depth of the streaming mode
@@ -81,7 +86,7 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
 }
 
 __host__ __device__ __forceinline__ int kind_stride(int kind, int vdim) {  // floats of cache per group
-    return (kind == DIST_B200_DD || kind == kKindGpTable) ? vdim : 4;
+    return (kind == DIST_B200_DD || kind == kKindGpTable || kind == kKindDdScaled) ? vdim : 4;
 }
 
 // GammaPoisson term of one (value, group) cell -- the single definition shared by the direct path, the
@@ -253,7 +258,7 @@ struct RowsArgs {
 };
 
 template <int CHUNK, int KIND, bool kSample, bool kScores, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : (CHUNK <= 32 ? (KIND >= 0 ? 4 : 3) : (CHUNK <= 64 ? 2 : 1)))
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? (KIND == kKindDdScaled ? 5 : 3) : (CHUNK <= 32 ? (KIND >= 0 ? 4 : 3) : (CHUNK <= 64 ? 2 : 1)))
 score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     constexpr int kThreads = THREADS;  // block size of this instantiation
     extern __shared__ __align__(16) float smem[];
@@ -324,6 +329,17 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
             }
         }
         __syncthreads();
+        if (KIND == kKindDdScaled) {
+            // per value: the maximum over groups, then (score - max) * log2e in place (a thread owns its value's column;
+            // padded groups stay -inf)
+            const int vdim = feats.f[0].vdim;
+            for (int v = tid; v < vdim; v += kThreads) {
+                float m = -INFINITY;
+                for (int g = 0; g < Gpad; ++g) m = fmaxf(m, caches[g * vdim + v]);
+                for (int g = 0; g < Gpad; ++g) caches[g * vdim + v] = (caches[g * vdim + v] - m) * kLog2e;
+            }
+            __syncthreads();
+        }
         if (KIND == kKindNichPacked) {
             // re-lay the private copy out in pairs of groups (in place: a thread owns its pair's eight floats)
             for (int p = tid; p < Gpad / 2; p += kThreads) {
@@ -395,7 +411,9 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                 }
             }
 
-            if (kSingle) {
+            if (KIND == kKindDdScaled) {
+                // gather + exp + pair sums fused below (the sampler of this kind reads the block's table itself)
+            } else if (kSingle) {
                 const uint32_t xb = load_value(KIND == kKindNichPacked ? DIST_B200_NICH : KIND, feats.f[0].column, row);
                 const int vdim = feats.f[0].vdim;
                 accumulate_feature<CHUNK, kFold>(KIND, xb, caches + static_cast<size_t>(g0) * kind_stride(KIND, vdim), vdim,
@@ -455,6 +473,31 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) tw[lane * 33 + j] = acc[sb * 32 + j];
                     __syncwarp();
+                    if (((G & 3) == 0) && g0 + sb * 32 + 32 <= G && !a.accumulate) {
+                        // 16-byte stores: lane (r, c) = (lane / 8, lane % 8) writes groups [4c, 4c + 4) of rows r, r + 4, ...
+                        // -- four conflict-free scalar LDS, one ST.128; a store instruction covers four 128-byte row
+                        // segments (a quarter of the store instructions, 16 B per lane on the NVLink path)
+                        const int r = lane >> 3, c = lane & 7;
+                        const int gq = g0 + sb * 32 + 4 * c;
+                        const size_t grow0 = a.row0 + wrow0;
+                        const int owner0 = a.n_push ? static_cast<int>(grow0 / a.block_rows) : 0;
+                        const size_t off0 = a.n_push ? grow0 - static_cast<size_t>(owner0) * a.block_rows : 0;
+                        const int first = a.n_push ? static_cast<int>(a.block_rows - off0 < 32 ? a.block_rows - off0 : 32) : 32;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = 4 * i + r;
+                            if (row >= nrows) continue;
+                            const float *sp = tw + row * 33 + 4 * c;
+                            const float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                            float *base;
+                            if (a.n_push)
+                                base = row < first ? a.push[owner0] + (off0 + row) * G : a.push[owner0 + 1] + static_cast<size_t>(row - first) * G;
+                            else
+                                base = a.scores + (wrow0 + row) * G;
+                            *reinterpret_cast<float4 *>(base + gq) = v;
+                        }
+                        continue;
+                    }
                     const int g = g0 + sb * 32 + lane;
                     if (g >= G) continue;
                     const float *src = tw + lane;
@@ -488,36 +531,101 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                 }
             }
 
-            if (kSample) {
+            if (kSample && KIND == kKindDdScaled) {
+                // One gather + MUFU.EX2 per cell; likelihoods are kept as PAIR sums, in four contiguous segments
+                // (four independent chains for the total and for the walk `t -= l; stop at t <= 0`, random.hpp:315-333).
+                // The walk stops on a pair; the pair's first likelihood is then recomputed (one more gather) to place the
+                // stop inside it.  Sign-bit counting as everywhere: an exact +0 continues (a near-tie).
+                const int vdim = feats.f[0].vdim;
+                const int vi = min(static_cast<int>(load_value(DIST_B200_DD, feats.f[0].column, row)), vdim - 1);
+                const float *pb = caches + vi;
+                constexpr int PAIRS = CHUNK / 2, SEGP = PAIRS / 4;
+                static_assert(CHUNK % 8 == 0, "register tile: four segments of whole pairs");
+                float p[PAIRS];
+                float seg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < SEGP; ++k) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = 2 * (q * SEGP + k);
+                        p[q * SEGP + k] = mufu_ex2(pb[j * vdim]) + mufu_ex2(pb[(j + 1) * vdim]);
+                        seg[q] += p[q * SEGP + k];
+                    }
+                }
+                const float p1 = seg[0], p2 = p1 + seg[1], p3 = p2 + seg[2];
+                const float t0 = (p3 + seg[3]) * urow;
+                float t[4] = {t0, t0 - p1, t0 - p2, t0 - p3};
+                float last[4] = {t[0], t[1], t[2], t[3]};  // the draw left in front of the first pair that is not passed
+                unsigned neg[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int k = 0; k < SEGP; ++k) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        t[q] -= p[q * SEGP + k];
+                        neg[q] += __float_as_uint(t[q]) >> 31;
+                        last[q] = (__float_as_uint(t[q]) >> 31) ? last[q] : t[q];
+                    }
+                }
+                // pairs passed in front of the stop; a segment after the stopping one starts at t <= 0 and passes none
+                int passed = 0, qs = 3;
+                bool open = true;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = SEGP - static_cast<int>(neg[q]);
+                    if (open) {
+                        passed += c;
+                        if (c < SEGP) {
+                            qs = q;
+                            open = false;
+                        }
+                    }
+                }
+                const float before = qs == 0 ? last[0] : (qs == 1 ? last[1] : (qs == 2 ? last[2] : last[3]));
+                const int kp = min(passed, PAIRS - 1);
+                const float first = mufu_ex2(pb[(2 * kp) * vdim]);
+                const int idx = 2 * kp + ((before - first > 0.f) ? 1 : 0);
+                result = min(open ? CHUNK - 1 : idx, G - 1);
+            } else if (kSample) {
                 if (!multi) {
                     // scores_to_likelihoods + sample_from_likelihoods (random.cc:94-106, random.hpp:315-333) on the
-                    // register row: exp(s - m) = 2^(s log2e - m log2e) as one packed FFMA2 per two cells + MUFU.EX2,
-                    // the total as an even and an odd chain (FADD2), the walk `t -= l[i]; stop at t <= 0` with the
-                    // stop counted from t's sign bit (one LEA.HI per cell; an exact +0 continues: a near-tie)
+                    // register row.  exp(s - m) = 2^(s log2e - m log2e): one packed FFMA2 per two cells + MUFU.EX2.
+                    // The row is cut into four contiguous segments: four independent partial sums, then four
+                    // independent walks `t -= l[i]` that start from the draw minus the mass of the segments before
+                    // (a thread's only parallelism is ILP here: one 128-deep dependent chain per phase would leave the
+                    // few resident warps waiting on FADD latency).  The stop `t <= 0` is counted from t's sign bit
+                    // (one LEA.HI per cell; an exact +0 continues: a near-tie); segments after the stop count 0.
                     float m = acc[0];
 #pragma unroll
                     for (int j = 1; j < CHUNK; ++j) m = fmaxf(m, acc[j]);
                     const float nm = -m * kLog2e;
                     const uint64_t l2e2 = f2_pack(kLog2e, kLog2e), nm2 = f2_pack(nm, nm);
-                    uint64_t tot2 = f2_pack(0.f, 0.f);
+                    constexpr int SEGLEN = CHUNK / 4;
+                    static_assert(CHUNK % 8 == 0, "register tile: four segments of an even number of groups");
+                    float seg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < CHUNK; j += 2) {
-                        float ea, eb;
-                        f2_unpack(f2_fma(f2_pack(acc[j], acc[j + 1]), l2e2, nm2), ea, eb);
-                        acc[j] = mufu_ex2(ea);
-                        acc[j + 1] = mufu_ex2(eb);
-                        tot2 = f2_add(tot2, f2_pack(acc[j], acc[j + 1]));
-                    }
-                    float te, to;
-                    f2_unpack(tot2, te, to);
-                    float t = (te + to) * urow;
-                    unsigned neg = 0;
+                    for (int j = 0; j < SEGLEN; j += 2) {
 #pragma unroll
-                    for (int j = 0; j < CHUNK; ++j) {
-                        t -= acc[j];
-                        neg += __float_as_uint(t) >> 31;
+                        for (int q = 0; q < 4; ++q) {
+                            float ea, eb;
+                            f2_unpack(f2_fma(f2_pack(acc[q * SEGLEN + j], acc[q * SEGLEN + j + 1]), l2e2, nm2), ea, eb);
+                            acc[q * SEGLEN + j] = mufu_ex2(ea);
+                            acc[q * SEGLEN + j + 1] = mufu_ex2(eb);
+                            seg[q] = (seg[q] + acc[q * SEGLEN + j]) + acc[q * SEGLEN + j + 1];
+                        }
                     }
-                    result = min(CHUNK - static_cast<int>(neg), G - 1);
+                    const float p1 = seg[0], p2 = p1 + seg[1], p3 = p2 + seg[2];
+                    const float t0 = (p3 + seg[3]) * urow;
+                    float t[4] = {t0, t0 - p1, t0 - p2, t0 - p3};
+                    unsigned neg[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int j = 0; j < SEGLEN; ++j) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            t[q] -= acc[q * SEGLEN + j];
+                            neg[q] += __float_as_uint(t[q]) >> 31;
+                        }
+                    }
+                    result = min(CHUNK - static_cast<int>((neg[0] + neg[1]) + (neg[2] + neg[3])), G - 1);
                 } else if (!fin) {
                     float m = acc[0];
 #pragma unroll
@@ -679,6 +787,13 @@ static int launch_tiers(dist_b200_ctx *ctx, const FeatList &feats, const RowsArg
         const int v = ctx->opt[DIST_B200_OPT_SMALL_TILE];
         if (v == 1) return launch_modes<128, KIND, 256>(ctx, feats, a, s);
         if (v == 3) return launch_modes<32, KIND, 256>(ctx, feats, a, s);
+        if (v != 2 && a.assign && !a.scores) {
+            // sampling only: the register tile is G rounded up to 16 groups (G = 100 pads to 112 instead of 128:
+            // every padded group is a wasted MUFU.EX2)
+            if (a.G <= 80) return launch_variant<80, KIND, true, false, 128>(ctx, feats, a, s);
+            if (a.G <= 96) return launch_variant<96, KIND, true, false, 128>(ctx, feats, a, s);
+            if (a.G <= 112) return launch_variant<112, KIND, true, false, 128>(ctx, feats, a, s);
+        }
         return launch_modes<128, KIND, 128>(ctx, feats, a, s);
     }
     // measured at c2: 32-group tiles 0.748 ms, 64-group tiles 0.774 ms (DIST_B200_OPT_ROW_TILE for A/B runs)

@@ -5,12 +5,15 @@
 // followed by sample_from_scores_overwrite (random.hpp:360-366, random.cc:94-106).
 //
 // (1) table_rows_kernel -- the full per-row evaluation, one WARP per row, everything in registers.
-//     The dpd table is kept in a second, "hot" layout whose physical order makes a coalesced LDG.128 hand
-//     every lane a CONTIGUOUS segment of logical groups (lane L owns groups [L*seg, (L+1)*seg)), so the
-//     reference's left-to-right walk needs no shared-memory transpose: per row 4 x LDG.128 per lane (G = 512),
-//     one CREDUX.MAX.F32 for the row maximum, one 5-step inclusive scan over the lane sums, one vote, and the
-//     owning lane's walk over its registers.  The 32 rows of a warp iteration load their values / uniforms with
-//     one coalesced load and store their indices with one coalesced store.
+//     Per call the dpd table is re-laid out (table_hot_fold_kernel, O(V G): a few us at c4) into a "hot" copy
+//       hot[v][p(g)] = (prior[g] + scores_[v][g] - shift[g] - m_v) * log2(e),   m_v = max_g of that row,
+//     i.e. with the clustering prior folded in (as score_rows folds it into its block-private caches) and the row
+//     maximum that scores_to_likelihoods subtracts (random.cc:94-106) already taken, so a cell is ONE MUFU.EX2.
+//     The physical order p(g) makes a coalesced LDG.128 hand every lane a CONTIGUOUS segment of logical groups
+//     (lane L owns groups [L*seg, (L+1)*seg)), so the reference's left-to-right walk needs no shared-memory
+//     transpose: per row 4 x LDG.128 per lane (G = 512), 16 MUFU.EX2, one 5-step inclusive scan over the lane
+//     sums, one vote, and the owning lane's walk over its registers.  The 32 rows of a warp iteration load their
+//     values / uniforms with one coalesced load and store their indices with one coalesced store.
 //     Bound: 1 MUFU.EX2 + 4 B of L2 gather per cell (the 8.4 MB table of c4 is L2-resident).
 //
 // (2) value_cdf_* -- SURVEY.md 8(d) "algorithmic shortcut": with frozen statistics and ONE table feature the
@@ -49,43 +52,38 @@ __host__ __device__ __forceinline__ int hot_pos(int g, int seg) {
     return 128 * (w >> 2) + 4 * L + (w & 3);
 }
 
-__global__ void table_hot_kernel(int R, int G, int seg, const float *__restrict__ table, float *__restrict__ hot) {
+// one warp per table row: row maximum of prior + score, then the scaled, max-relative hot row (pads -inf)
+__global__ void __launch_bounds__(256) table_hot_fold_kernel(int R, int G, int seg, const float *__restrict__ table,
+                                                             const float *__restrict__ prior, float *__restrict__ hot) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    const float *src = table + static_cast<size_t>(r) * G;
+    float m = -INFINITY;
+    for (int g = lane; g < G; g += 32) m = fmaxf(m, (prior ? prior[g] : 0.f) + src[g]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     const int stride = 32 * seg;
-    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= static_cast<size_t>(R) * stride) return;
-    const int r = static_cast<int>(i / stride), p = static_cast<int>(i - static_cast<size_t>(r) * stride);
-    // inverse of hot_pos: p = 128 k + 4 L + j
-    const int k = p >> 7, L = (p >> 2) & 31, j = p & 3;
-    const int g = L * seg + 4 * k + j;
-    hot[i] = (4 * k + j < seg && g < G) ? table[static_cast<size_t>(r) * G + g] : -INFINITY;
+    float *dst = hot + static_cast<size_t>(r) * stride;
+    for (int p = lane; p < stride; p += 32) {
+        // inverse of hot_pos: p = 128 k + 4 L + j
+        const int k = p >> 7, L = (p >> 2) & 31, j = p & 3;
+        const int g = L * seg + 4 * k + j;
+        dst[p] = (4 * k + j < seg && g < G) ? ((prior ? prior[g] : 0.f) + src[g] - m) * kLog2e : -INFINITY;
+    }
 }
 
-int launch_table_hot(dist_b200_ctx *ctx, int R, int G, const float *table, float *hot, cudaStream_t s) {
-    const size_t n = static_cast<size_t>(R) * 32 * hot_seg(G);
-    if (n == 0) return DIST_B200_OK;
-    table_hot_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(R, G, hot_seg(G), table, hot);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("table_hot launch: ") + cudaGetErrorString(e));
-    return DIST_B200_OK;
-}
 size_t table_hot_floats(int R, int G) { return static_cast<size_t>(R) * 32 * hot_seg(G); }
 
 struct TableRowsArgs {
     int G;
     KeyMap km;
     size_t N;
-    const float *hot;        // [(V+1)][32 * seg]
+    const float *hot;        // [(V+1)][32 * seg]: (prior + score - row max) * log2 e
     const uint32_t *values;
-    const float *prior;      // [G] or nullptr
     const float *u;
     int32_t *assign;
 };
-
-__device__ __forceinline__ float warp_max(float v) {
-    float m;
-    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));  // CREDUX.MAX.F32 (sm_100a)
-    return m;
-}
 
 constexpr int kTableWarps = 8;
 
@@ -95,12 +93,6 @@ __global__ void __launch_bounds__(kTableWarps * 32) table_rows_kernel(const Tabl
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = a.G;
     const unsigned full = 0xffffffffu;
-    float pr[SEG];
-#pragma unroll
-    for (int i = 0; i < SEG; ++i) {
-        const int g = lane * SEG + i;
-        pr[i] = (a.prior && g < G) ? a.prior[g] : 0.f;
-    }
     const size_t stride4 = 32 * K4;  // float4 per table row
     const float4 *hot4 = reinterpret_cast<const float4 *>(a.hot) + lane;
     const size_t step = static_cast<size_t>(gridDim.x) * kTableWarps * 32;
@@ -120,22 +112,14 @@ __global__ void __launch_bounds__(kTableWarps * 32) table_rows_kernel(const Tabl
 #pragma unroll
             for (int k = 0; k < K4; ++k) {
                 const float4 q = __ldg(src + 32 * k);
-                s[4 * k + 0] = q.x + pr[4 * k + 0];  // prior + (scores_[v][g] - shift[g])
-                s[4 * k + 1] = q.y + pr[4 * k + 1];
-                s[4 * k + 2] = q.z + pr[4 * k + 2];
-                s[4 * k + 3] = q.w + pr[4 * k + 3];
+                s[4 * k + 0] = mufu_ex2(q.x);  // exp(prior + scores_[v][g] - shift[g] - max)
+                s[4 * k + 1] = mufu_ex2(q.y);
+                s[4 * k + 2] = mufu_ex2(q.z);
+                s[4 * k + 3] = mufu_ex2(q.w);
             }
-            float m = s[0];
-#pragma unroll
-            for (int j = 1; j < SEG; ++j) m = fmaxf(m, s[j]);
-            m = warp_max(m);
-            const float nm = -m * kLog2e;
             float part = 0.f;
 #pragma unroll
-            for (int j = 0; j < SEG; ++j) {
-                s[j] = mufu_ex2(fmaf(s[j], kLog2e, nm));
-                part += s[j];
-            }
+            for (int j = 0; j < SEG; ++j) part += s[j];
             float incl = part;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -181,14 +165,18 @@ static int launch_table_rows_k(dist_b200_ctx *ctx, const TableRowsArgs &a, cudaS
 int launch_table_rows(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *column, size_t N, const float *prior,
                       const float *u, int32_t *assign, cudaStream_t s) {
     if (N == 0 || f->G == 0) return DIST_B200_OK;
-    if (!f->dpd_hot || f->G > 1024) return DIST_B200_ERR_UNSUPPORTED;
+    // the per-call re-layout costs O(V G): only worth it for batches well beyond the table itself
+    if (!f->dpd_hot || f->G > 1024 || N < 4 * static_cast<size_t>(f->dim + 1)) return DIST_B200_ERR_UNSUPPORTED;
+    {
+        const int R = f->dim + 1;
+        table_hot_fold_kernel<<<(R + 7) / 8, 256, 0, s>>>(R, f->G, hot_seg(f->G), static_cast<const float *>(f->params), prior, f->dpd_hot);
+    }
     TableRowsArgs a{};
     a.G = f->G;
     a.km = KeyMap{f->dim, f->keys_dense ? 1 : 0, f->keys_dev, f->key_rows_dev};
     a.N = N;
     a.hot = f->dpd_hot;
     a.values = static_cast<const uint32_t *>(column);
-    a.prior = prior;
     a.u = u;
     a.assign = assign;
     switch (hot_seg(f->G) / 4) {
@@ -344,6 +332,9 @@ int launch_value_cdf(dist_b200_ctx *ctx, const dist_b200_feature *f, float *buf,
     const int L = cdf_levels(G);
     if (L > 4) return DIST_B200_ERR_UNSUPPORTED;
     int R;
+    // the trees cost O(R G) per call: only worth it for batches well beyond the number of distinct values
+    if (N < 4 * static_cast<size_t>(f->model == DIST_B200_DPD ? f->dim + 1 : (f->model == DIST_B200_DD ? f->dim : 2)))
+        return DIST_B200_ERR_UNSUPPORTED;
     KeyMap km{};
     switch (f->model) {
         case DIST_B200_DPD:

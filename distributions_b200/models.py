@@ -331,6 +331,190 @@ class _DdMixture(_Mixture):
             g.counts = raw[i].copy()
 
 
+class _DpdShared(_Shared):
+    """DirichletProcessDiscrete::Shared (dpd.hpp:59-152) with a FIXED set of known values: `values` (the keys of
+    betas), `betas`, beta0 = max(0, 1 - sum betas) as Shared::protobuf_load computes it (dpd.hpp:104-125).  The
+    Hierarchical-DP part that invents values (Shared::add_value / realize, dpd.hpp:66-100) is off the scoring path:
+    change the value set with a new Shared and Mixture.init."""
+    FIELDS = (("gamma", 1.0), ("alpha", 0.5), ("values", None), ("betas", None))
+    OTHER = 0xFFFFFFFF  # dpd.hpp:55
+
+    def __init__(self, gamma=1.0, alpha=0.5, values=None, betas=None, dim=100):
+        self.gamma, self.alpha = float(gamma), float(alpha)
+        if values is None:  # EXAMPLE(): dim 100, betas 1 / dim, beta0 = 0 (dpd.hpp:141-152)
+            values, betas = np.arange(dim), np.full(dim, 1.0 / dim)
+        self.values = np.asarray(values, np.uint32)
+        self.betas = np.asarray(betas, np.float32)
+        assert self.values.size == self.betas.size and np.unique(self.values).size == self.values.size
+        self.beta0 = float(max(0.0, 1.0 - float(self.betas.astype(np.float64).sum())))
+        self.index = {int(v): i for i, v in enumerate(self.values)}
+
+
+class _DpdGroup(_Group):
+    """SparseCounter<Value, count_t> (dpd.hpp:157-215): value -> count, absent = 0"""
+    FIELDS = (("counts", None),)
+
+    def __init__(self):
+        self.counts = {}
+
+    def init(self, shared):
+        self.counts = {}
+
+    def add_value(self, shared, value):  # dpd.hpp:188-196
+        value = int(value)
+        assert value != shared.OTHER, "cannot add OTHER"
+        assert value in shared.index, "unknown value: %d" % value
+        self.counts[value] = self.counts.get(value, 0) + 1
+
+    def remove_value(self, shared, value):  # dpd.hpp:207-215
+        value = int(value)
+        assert value != shared.OTHER, "cannot remove OTHER"
+        assert value in shared.index, "unknown value: %d" % value
+        c = self.counts.get(value, 0) - 1
+        if c:
+            self.counts[value] = c
+        else:
+            self.counts.pop(value, None)
+
+    def dense(self, shared):
+        row = np.zeros(shared.values.size, np.int32)
+        for v, c in self.counts.items():
+            row[shared.index[v]] = c
+        return row
+
+
+class _DpdMixture(_Mixture):
+    model_id = capi.DPD
+    Group = _DpdGroup
+
+    def _pack_shared(self, s):
+        return [s.alpha]
+
+    def _workload(self, s):
+        counts = np.array([g.dense(s) for g in self.groups], np.int32).reshape(len(self.groups), s.values.size)
+        return dict(model="dpd", alpha=s.alpha, beta0=s.beta0, keys=s.values, betas=s.betas, counts=counts)
+
+    def _stats(self, s, g):
+        return g.dense(s)
+
+    def _pull_groups(self, s):
+        G, V = len(self.groups), s.values.size
+        raw = self.feature.download_stats(4 * G * V).view(np.int32).reshape(G, V)
+        for i, g in enumerate(self.groups):
+            g.counts = {int(s.values[v]): int(raw[i, v]) for v in np.nonzero(raw[i])[0]}
+
+
+class _NiwShared(_Shared):
+    """NormalInverseWishart::Shared (niw.hpp:52-170): mu[d], kappa, psi[d][d], nu"""
+    FIELDS = (("mu", None), ("kappa", 1.0), ("psi", None), ("nu", None))
+
+    def __init__(self, mu=None, kappa=1.0, psi=None, nu=None, dim=2):
+        self.mu = np.asarray(mu if mu is not None else np.zeros(dim), np.float32)  # EXAMPLE(): niw.hpp:160-170
+        d = self.mu.size
+        self.kappa = float(kappa)
+        self.psi = np.asarray(psi if psi is not None else np.eye(d), np.float32).reshape(d, d)
+        self.nu = float(nu if nu is not None else d + 1)
+
+    @property
+    def dim(self):
+        return self.mu.size
+
+
+class _NiwGroup(_Group):
+    """{count, sum_x, sum_xxT} (niw.hpp:187-190), float32 like the reference's Eigen Matrix<float>"""
+    FIELDS = (("count", 0), ("sum_x", None), ("sum_xxT", None))
+
+    def init(self, shared):  # niw.hpp:236-245
+        self.count = 0
+        self.sum_x = np.zeros(shared.dim, np.float32)
+        self.sum_xxT = np.zeros((shared.dim, shared.dim), np.float32)
+
+    def add_value(self, shared, value):  # niw.hpp:247-255: rank-1 updates
+        x = np.asarray(value, np.float32)
+        self.count += 1
+        self.sum_x += x
+        self.sum_xxT += np.outer(x, x)
+
+    def remove_value(self, shared, value):  # niw.hpp:267-276
+        x = np.asarray(value, np.float32)
+        self.count -= 1
+        self.sum_x -= x
+        self.sum_xxT -= np.outer(x, x)
+
+
+class _NiwMixture(_Mixture):
+    """The reference has no NIW Mixture (niw.hpp has Group / Scorer only); this is the batched form of looping
+    Group::score_value over the groups (mixture.hpp:321-337 semantics)."""
+    model_id = capi.NIW
+    Group = _NiwGroup
+
+    def _workload(self, s):
+        G, d = len(self.groups), s.dim
+        return dict(model="niw", mu=s.mu, kappa=s.kappa, psi=s.psi, nu=s.nu,
+                    count=np.array([g.count for g in self.groups], np.int32),
+                    sum_x=np.array([g.sum_x for g in self.groups], np.float32).reshape(G, d),
+                    sum_xxT=np.array([g.sum_xxT for g in self.groups], np.float32).reshape(G, d, d))
+
+    def _stats(self, s, g):
+        return np.concatenate([np.array([g.count], np.int32).view(np.float32), g.sum_x.ravel(), g.sum_xxT.ravel()]).astype(np.float32)
+
+    def score_value(self, shared, value, scores_accum):
+        assert len(scores_accum) == len(self.groups) and scores_accum.dtype == np.float32
+        self.ctx.score_value_host(self.feature, np.asarray(value, np.float32).reshape(1, -1), scores_accum)
+
+    def score_values(self, shared, values, prior, u, want_scores=False):
+        vals = np.ascontiguousarray(values, np.float32).reshape(-1, shared.dim)
+        return self.ctx.score_sample_batch_host([self.feature], [vals], prior, np.ascontiguousarray(u, np.float32), want_scores)
+
+    def score_data(self, shared):
+        raise NotImplementedError("niw score_data is not on the device (statistics stay on the host)")
+
+    score_data_grid = score_data
+    add_values = None
+
+
+class MixtureIdTracker:
+    """mixture.hpp:460-521: packed (contiguous, unstable under remove_group's swap-with-last) <-> global (fixed) group ids"""
+
+    def __init__(self, group_count=0):
+        self.init(group_count)
+
+    def init(self, group_count=0):
+        self.packed_to_global_ = []
+        self.global_to_packed_ = {}
+        self.global_size_ = 0
+        for _ in range(group_count):
+            self.add_group()
+
+    def add_group(self):
+        packed, glob = len(self.packed_to_global_), self.global_size_
+        self.global_size_ += 1
+        self.packed_to_global_.append(glob)
+        self.global_to_packed_[glob] = packed
+
+    def remove_group(self, packed):
+        assert packed < self.packed_size(), "bad packed id: %d" % packed
+        del self.global_to_packed_[self.packed_to_global_[packed]]
+        last = self.packed_to_global_.pop()
+        if packed != len(self.packed_to_global_):  # the last group moved into the hole
+            self.packed_to_global_[packed] = last
+            self.global_to_packed_[last] = packed
+
+    def packed_to_global(self, packed):
+        assert packed < self.packed_size(), "bad packed id: %d" % packed
+        return self.packed_to_global_[packed]
+
+    def global_to_packed(self, glob):
+        assert glob in self.global_to_packed_, "stale global id: %d" % glob
+        return self.global_to_packed_[glob]
+
+    def packed_size(self):
+        return len(self.packed_to_global_)
+
+    def global_size(self):
+        return self.global_size_
+
+
 class _Namespace:
     def __init__(self, name, Value, Shared, Group, Mixture):
         self.__name__, self.Value, self.Shared, self.Group, self.Mixture = name, Value, Shared, Group, Mixture
@@ -341,7 +525,9 @@ gp = _Namespace("gp", int, _GpShared, _CountSumGroup, _GpMixture)
 bnb = _Namespace("bnb", int, _BnbShared, _CountSumGroup, _BnbMixture)
 bb = _Namespace("bb", bool, _BbShared, _BbGroup, _BbMixture)
 dd = _Namespace("dd", int, _DdShared, _DdGroup, _DdMixture)
-MODELS = {m.__name__: m for m in (nich, gp, bnb, bb, dd)}
+dpd = _Namespace("dpd", int, _DpdShared, _DpdGroup, _DpdMixture)
+niw = _Namespace("niw", np.ndarray, _NiwShared, _NiwGroup, _NiwMixture)
+MODELS = {m.__name__: m for m in (nich, gp, bnb, bb, dd, dpd, niw)}
 
 
 # ------------------------------------------------------------------------------------------------------

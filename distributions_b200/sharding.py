@@ -140,49 +140,80 @@ def row_sharded_update(accumulate, merge, xchg, sign=+1, group=None):
 class PeerFeatureShards:
     """Feature shards with the reduction fused into the score kernel over NVLink peer memory.
 
-    Every rank owns the contiguous row block `rank` (block_rows(n_rows, world) rows) and holds `world`
-    slots [block][G]; rank r's score kernel stores its partial rows straight into slot r of the owning
-    rank (CUDA IPC mapping, dist_b200_score_push_batch), so the transfer overlaps the math tile by tile
-    and no partial [N][G] tile is written to local HBM.  The owner samples the fixed-order sum of its
-    slots (dist_b200_sample_from_slots).  Needs one process per GPU on one NVLink domain.
+    The `world` ranks form `row_shards` groups of `feature_shards = world / row_shards` ranks (pure feature
+    sharding: row_shards = 1).  A group scores the contiguous row range row_shard(n_rows, rs, row_shards); inside it
+    rank j holds the features feature_shard(F, j, feature_shards) and OWNS the row block j of the group's range.
+    Every owner has `feature_shards` slots [block][G] (x 2, alternating by step); rank j's score kernel stores its
+    partial rows straight into slot j of the owning rank (CUDA IPC mapping, dist_b200_score_push_batch, 16-byte
+    stores), so the transfer overlaps the math tile by tile and no partial [N][G] tile is written to local HBM.
+    Pushers then raise an epoch flag in the owners' memory and the owner's sampler waits on its flags ON THE DEVICE
+    (dist_b200_peer_signal / _wait): a step is four stream-ordered launches and never blocks the host.  Slot
+    buffers alternate between steps, which makes the flag chain sufficient: a pusher writing buffer b at step e + 2
+    has waited at e + 1 for every rank's e + 1 push, which each rank enqueued behind its own step-e sampler.
+    The owner samples the fixed-order sum of its slots (dist_b200_sample_from_slots; deterministic, unlike atomics).
+    Needs one process per GPU on one NVLink domain.
     """
+    launches_per_step = 4  # score + push kernel, signal, wait, slot-sum sampler
 
-    launches_per_step = 2  # score + push kernel, slot-sum sampler
-
-    def __init__(self, ctx, n_rows, n_groups, group=None):
+    def __init__(self, ctx, n_rows, n_groups, group=None, row_shards=1):
         self.ctx, self.group = ctx, group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.n_rows, self.G = n_rows, n_groups
-        self.block = block_rows(n_rows, self.world)
+        assert self.world % row_shards == 0
+        self.fs = self.world // row_shards           # feature shards = ranks per group
+        self.rs_index, self.index = divmod(self.rank, self.fs)
+        self.row_lo, self.row_hi = row_shard(n_rows, self.rs_index, row_shards)
+        self.n_rows, self.G = self.row_hi - self.row_lo, n_groups
+        self.block = block_rows(self.n_rows, self.fs)
         self.slot_floats = self.block * n_groups
-        self.mine, handle = ctx.peer_alloc(4 * self.world * self.slot_floats)
+        self.buf_floats = self.fs * self.slot_floats
+        flag_bytes = 256
+        self.mine, handle = ctx.peer_alloc(4 * 2 * self.buf_floats + flag_bytes)
         handles = [None] * self.world
         dist.all_gather_object(handles, handle, group=group)
-        self.bases = [self.mine if r == self.rank else ctx.peer_open(h) for r, h in enumerate(handles)]
-        # this rank's slot inside every owner's buffer
-        self.slot_ptrs = [b + 4 * self.rank * self.slot_floats for b in self.bases]
+        peers = range(self.rs_index * self.fs, (self.rs_index + 1) * self.fs)
+        self.bases = [self.mine if r == self.rank else ctx.peer_open(handles[r]) for r in peers]
+        # this rank's slot inside every owner's buffer, per alternating buffer; the owners' flag arrays
+        self.slot_ptrs = [[b + 4 * (k * self.buf_floats + self.index * self.slot_floats) for b in self.bases] for k in range(2)]
+        self.flag_ptrs = [b + 4 * 2 * self.buf_floats for b in self.bases]
+        self.epoch = 0
+        dist.barrier(group=group)  # every mapping exists before the first push
+
+    def features(self, n_features):
+        """indices of the features this rank scores"""
+        return feature_shard(n_features, self.index, self.fs)
+
+    def rows(self):
+        """global [lo, hi) of the rows this rank's GROUP scores (the rows its columns must cover)"""
+        return self.row_lo, self.row_hi
 
     def owned(self):
-        lo = min(self.rank * self.block, self.n_rows)
-        return lo, min(lo + self.block, self.n_rows)
+        """global [lo, hi) of the rows this rank samples"""
+        lo = min(self.index * self.block, self.n_rows)
+        return self.row_lo + lo, self.row_lo + min(lo + self.block, self.n_rows)
 
     def step(self, features, columns, prior, u, assign_out, stream=None):
-        """features / columns: this rank's shard (>= 1 feature); prior: device [G], applied by rank 0;
-        u: device [n_rows]; assign_out: device int32 [rows owned].  Returns the owned row range."""
+        """features / columns: this rank's shard (>= 1 feature), columns covering rows(); prior: device [G], applied by
+        the first rank of each group; u: device uniforms of the owned rows; assign_out: device int32 [rows owned].
+        Returns the owned row range.  Everything is enqueued on `stream`; nothing blocks the host."""
         assert len(features) >= 1, "every rank needs at least one feature of the kind"
-        self.ctx.score_push_batch(features, columns, self.n_rows, 0, prior if self.rank == 0 else None,
-                                  self.slot_ptrs, self.block, stream=stream)
-        dist.barrier(group=self.group)  # every rank's pushes have landed in the owners' slots
+        self.epoch += 1
+        k = self.epoch & 1
+        self.ctx.score_push_batch(features, columns, self.n_rows, 0, prior if self.index == 0 else None,
+                                  self.slot_ptrs[k], self.block, stream=stream)
+        self.ctx.peer_signal(self.flag_ptrs, self.index, self.epoch, stream=stream)
+        self.ctx.peer_wait(self.flag_ptrs[self.index], self.fs, self.epoch, stream=stream)
         lo, hi = self.owned()
         if hi > lo:
-            self.ctx.sample_from_slots(self.mine, self.world, self.slot_floats, hi - lo, self.G, u[lo:hi], assign_out,
-                                       stream=stream)
-        dist.barrier(group=self.group)  # owners are done reading before the next step overwrites the slots
+            self.ctx.sample_from_slots(self.mine + 4 * k * self.buf_floats, self.fs, self.slot_floats, hi - lo, self.G, u,
+                                       assign_out, stream=stream)
         return lo, hi
 
     def close(self):
+        import torch
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # nobody is still pushing into a buffer that is about to go away
         for r, b in enumerate(self.bases):
-            if r != self.rank:
+            if r != self.index:
                 self.ctx.peer_close(b)
         self.ctx.peer_free(self.mine)

@@ -72,11 +72,13 @@ typedef enum {
                                       1 = evaluate every (row, group) cell (the no-shortcut kernels) */
     DIST_B200_OPT_ROW_TILE = 1,    /* score_rows register tile for G > 128: 0 = default (32), else 32 / 64 */
     DIST_B200_OPT_HOST_CHUNKS = 2, /* row chunks of the host-buffer entry: 0 = default (5) */
-    DIST_B200_OPT_NIW_PATH = 3,    /* d = 32: 0 = tcgen05 3xTF32 (default), 1 = FP32 CUDA-core kernel */
+    DIST_B200_OPT_NIW_PATH = 3,    /* d = 32: 0 = tcgen05 kernel, split fp16 operands (default), 1 = FP32 CUDA-core kernel */
     DIST_B200_OPT_TABLE_KERNEL = 4,/* dpd no-shortcut kernel: 0 = register kernel on the lane-segment layout, 1 = round-1 gather kernel */
     DIST_B200_OPT_SMALL_TILE = 5,  /* score_rows, single feature, 64 < G <= 128: 0 = default, 1 = one 128-group tile x 256 threads
-                                      (round 1), 2 = 128 threads x 3 blocks / SM, 3 = four 32-group tiles */
+                                      (round 1), 2 = 128 threads x 3 blocks / SM with a 128-group tile, 3 = four 32-group tiles;
+                                      default: 128 threads x 3, tile = G rounded up to 16 when only sampling */
     DIST_B200_OPT_NICH_PACKED = 6, /* nich single feature: 0 = packed f32x2 loop (default), 1 = scalar loop (round 1) */
+    DIST_B200_OPT_NIW_DEBUG = 7,   /* profiling only, results are WRONG when set: 1 = skip the fused sampling walk, 2 = also the epilogue math */
     DIST_B200_OPT_COUNT_ = 16
 } dist_b200_option;
 int dist_b200_ctx_set_option(dist_b200_ctx *ctx, int option, int value);
@@ -124,14 +126,19 @@ int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float
                              const float *sum_xxT, void *stream);
 
 /* MixtureValueScorer::update_group after Group::add_value / remove_value touched one group
- * (nich.hpp:312-342, gp.hpp:262-291, bb.hpp:258-274, dd.hpp:381-397,458-467).  `stats` points at
- * that single group's statistics in the same order as the update_all arguments:
- *   nich {int32 count; float mean; float ctv}   gp {uint32 count; uint32 sum}
+ * (nich.hpp:312-342, gp.hpp:262-291, bb.hpp:258-274, dd.hpp:381-397,458-467, dpd.hpp:430-469; niw: the batched
+ * form of rebuilding one Group's Scorer, niw.hpp:247-276,343-361).  `stats` points at that single group's
+ * statistics in the same order as the update_all arguments:
+ *   nich {int32 count; float mean; float ctv}   gp / bnb {uint32 count; uint32 sum}
  *   bb {int32 heads; int32 tails}               dd int32 counts[dim]
- * The hyper-parameters are the ones given to the last update_all. */
+ *   dpd int32 counts[V] (dense, column v <-> keys[v] of the last update_all)
+ *   niw {int32 count; float sum_x[d]; float sum_xxT[d][d]} packed without padding
+ * The hyper-parameters are the ones given to the last update_all.  A dpd update rewrites the group's column of the
+ * value-major table (O(V)); new VALUES (Shared::add_value growing betas, dpd.hpp:66-84) need an update_all. */
 int dist_b200_feature_update_group(dist_b200_feature *f, int groupid, const void *stats, void *stream);
 /* packed_add of a fresh empty group / packed_remove = swap-with-last (vector.hpp:39-61,
- * mixture.hpp:361-375) on every per-group device array. */
+ * mixture.hpp:361-375) on every per-group device array.  dpd keeps its table dense with stride G, so both rebuild
+ * it from the device-resident counts (O(V G), a few microseconds at V = 4096, G = 512). */
 int dist_b200_feature_add_group(dist_b200_feature *f, void *stream);
 int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stream);
 
@@ -319,6 +326,15 @@ int dist_b200_peer_free(dist_b200_ctx *ctx, void *dev_ptr);
 int dist_b200_score_push_batch(dist_b200_ctx *ctx, const dist_b200_feature *const *features, int n_features,
                                const void *const *columns_dev, size_t n_rows, size_t row0, const float *prior_dev,
                                void *const *slot_ptrs, int n_owners, size_t block_rows, void *stream);
+/* Device-side signalling that replaces host barriers around the push.  Every owner holds one uint32 flag per
+ * pusher (zero-initialised: dist_b200_peer_alloc clears its buffer); epochs only grow.
+ *   dist_b200_peer_signal: after this rank's push kernel (same stream), raise flag[my_index] = epoch in every
+ *     owner's flag array (flag_ptrs[o] = peer-mapped base of owner o's flags) with a system-scope release.
+ *   dist_b200_peer_wait: stream-ordered wait until all n_peers local flags have reached `epoch` (system-scope
+ *     acquire; traps after ~13 s instead of hanging the device).  The sampler enqueued behind it then sees every push.
+ * Neither returns to the host: a step is push kernel, signal, wait, sampler on one stream. */
+int dist_b200_peer_signal(dist_b200_ctx *ctx, void *const *flag_ptrs, int n_peers, int my_index, uint32_t epoch, void *stream);
+int dist_b200_peer_wait(dist_b200_ctx *ctx, const void *flags_dev, int n_peers, uint32_t epoch, void *stream);
 /* sample_from_scores over the sum of n_slots partial score blocks, slot_stride floats apart. */
 int dist_b200_sample_from_slots(dist_b200_ctx *ctx, const float *slots_dev, int n_slots, size_t slot_stride,
                                 size_t n_rows, int G, const float *u_dev, int32_t *assign_dev, void *stream);

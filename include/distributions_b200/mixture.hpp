@@ -8,6 +8,8 @@
 //   Model::Shared / Model::Group {init, add_value, remove_value}
 //     NormalInverseChiSq  models/nich.hpp:52-165      GammaPoisson   models/gp.hpp:52-135
 //     BetaBernoulli       models/bb.hpp:52-122        DirichletDiscrete<max_dim>  models/dd.hpp:55-149
+//     DirichletProcessDiscrete  models/dpd.hpp:55-215 (fixed value set)    NormalInverseWishart<dim>  models/niw.hpp:52-276
+//   MixtureIdTracker                                        include/distributions/mixture.hpp:460-521
 //   Clustering<int>::PitmanYor::Mixture (CachedMixture over MixtureDriver)
 //                                                            clustering.hpp:126-234, mixture.hpp:48-163
 //     counts(), empty_groupids(), sample_size(), init, add_value / remove_value (return whether a group
@@ -28,6 +30,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <unordered_set>
 #include <utility>
 #include <vector>
@@ -280,6 +283,167 @@ struct DirichletDiscrete {
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), g.counts, nullptr);
     }
+};
+
+// DirichletProcessDiscrete (models/dpd.hpp:55-215) over a FIXED set of known values: Shared carries values / betas /
+// beta0 as Shared::protobuf_load leaves them (dpd.hpp:104-125); the Hierarchical-DP part that invents values
+// (Shared::add_value / realize, dpd.hpp:66-100) is off the scoring path -- change the value set with a new init().
+// Group = SparseCounter<Value, count_t> (dpd.hpp:157-158); unknown values are an error as in dpd.hpp:193.
+struct DirichletProcessDiscrete {
+    typedef uint32_t Value;
+    enum { model_id = DIST_B200_DPD };
+    static constexpr Value OTHER() { return 0xFFFFFFFFu; }  // dpd.hpp:55
+    struct Shared {
+        float gamma, alpha, beta0;
+        std::vector<Value> values;
+        std::vector<float> betas;
+        static Shared EXAMPLE() {  // dpd.hpp:141-152: dim 100, betas 1 / dim, beta0 = 0
+            Shared s;
+            s.gamma = 1.f; s.alpha = 0.5f; s.beta0 = 0.f;
+            for (Value v = 0; v < 100; ++v) { s.values.push_back(v); s.betas.push_back(0.01f); }
+            return s;
+        }
+        int index(Value v) const {
+            for (size_t i = 0; i < values.size(); ++i) if (values[i] == v) return static_cast<int>(i);
+            return -1;
+        }
+    };
+    struct Group {
+        std::unordered_map<Value, int32_t> counts;
+        void init(const Shared &, rng_t &) { counts.clear(); }
+        void add_value(const Shared & shared, const Value & value, rng_t &) {  // dpd.hpp:188-196
+            if (value == OTHER() || shared.index(value) < 0) throw std::runtime_error("dpd: unknown value");
+            counts[value] += 1;
+        }
+        void remove_value(const Shared & shared, const Value & value, rng_t &) {  // dpd.hpp:207-215
+            if (value == OTHER() || shared.index(value) < 0) throw std::runtime_error("dpd: unknown value");
+            if (--counts[value] == 0) counts.erase(value);
+        }
+        void dense(const Shared & shared, int32_t * row) const {
+            for (size_t v = 0; v < shared.values.size(); ++v) row[v] = 0;
+            for (const auto & kv : counts) row[shared.index(kv.first)] = kv.second;
+        }
+    };
+    static int update_all(dist_b200_feature * f, const Shared & s, const std::vector<Group> & groups) {
+        const size_t G = groups.size(), V = s.values.size();
+        std::vector<int32_t> counts(G * V);
+        for (size_t g = 0; g < G; ++g) groups[g].dense(s, counts.data() + g * V);
+        return dist_b200_dpd_update_all(f, s.alpha, s.beta0, static_cast<int>(V), s.values.data(), s.betas.data(),
+                                        static_cast<int>(G), counts.data(), nullptr);
+    }
+    static void load_groups(const unsigned char * raw, const Shared & s, std::vector<Group> & groups) {  // counts[G][V]
+        const int32_t * c = reinterpret_cast<const int32_t *>(raw);
+        const size_t V = s.values.size();
+        for (size_t g = 0; g < groups.size(); ++g) {
+            groups[g].counts.clear();
+            for (size_t v = 0; v < V; ++v) if (c[g * V + v]) groups[g].counts[s.values[v]] = c[g * V + v];
+        }
+    }
+    static size_t stats_bytes(const Shared & s, size_t G) { return 4 * G * s.values.size(); }
+    static void pack_shared(const Shared & s, std::vector<float> & out) { out.push_back(s.alpha); }
+    static int update_group(dist_b200_feature * f, const Shared & s, size_t groupid, const Group & g) {
+        std::vector<int32_t> row(s.values.size());
+        g.dense(s, row.data());
+        return dist_b200_feature_update_group(f, static_cast<int>(groupid), row.data(), nullptr);
+    }
+};
+
+// NormalInverseWishart<dim> (models/niw.hpp:52-276).  The reference has no NIW Mixture typedef; Mixture<NormalInverseWishart>
+// is the batched form of looping Group::score_value over the groups (mixture.hpp:321-337 semantics).  Group statistics
+// are the reference's {count, sum_x, sum_xxT} (niw.hpp:187-190) with its rank-1 updates (niw.hpp:247-276).
+template <int dim_>
+struct NormalInverseWishart {
+    enum { model_id = DIST_B200_NIW, dim = dim_ };
+    struct Value { float x[dim_]; };
+    struct Shared {
+        float mu[dim_];
+        float kappa;
+        float psi[dim_ * dim_];
+        float nu;
+        static Shared EXAMPLE() {  // niw.hpp:160-170
+            Shared s;
+            for (int i = 0; i < dim_; ++i) { s.mu[i] = 0.f; for (int j = 0; j < dim_; ++j) s.psi[i * dim_ + j] = i == j ? 1.f : 0.f; }
+            s.kappa = 1.f;
+            s.nu = dim_ + 1.f;
+            return s;
+        }
+    };
+    struct Group {  // also the packed layout dist_b200_feature_update_group takes for niw
+        int32_t count;
+        float sum_x[dim_];
+        float sum_xxT[dim_ * dim_];
+        void init(const Shared &, rng_t &) {
+            count = 0;
+            for (int i = 0; i < dim_; ++i) sum_x[i] = 0.f;
+            for (int i = 0; i < dim_ * dim_; ++i) sum_xxT[i] = 0.f;
+        }
+        void add_value(const Shared &, const Value & v, rng_t &) {  // niw.hpp:247-255
+            ++count;
+            for (int i = 0; i < dim_; ++i) { sum_x[i] += v.x[i]; for (int j = 0; j < dim_; ++j) sum_xxT[i * dim_ + j] += v.x[i] * v.x[j]; }
+        }
+        void remove_value(const Shared &, const Value & v, rng_t &) {  // niw.hpp:267-276
+            --count;
+            for (int i = 0; i < dim_; ++i) { sum_x[i] -= v.x[i]; for (int j = 0; j < dim_; ++j) sum_xxT[i * dim_ + j] -= v.x[i] * v.x[j]; }
+        }
+    };
+    static_assert(sizeof(Group) == 4 + 4 * dim_ + 4 * dim_ * dim_, "Group must be packed: it is passed to update_group as is");
+    static int update_all(dist_b200_feature * f, const Shared & s, const std::vector<Group> & groups) {
+        const size_t G = groups.size();
+        std::vector<int32_t> count(G);
+        std::vector<float> sx(G * dim_), sxx(G * dim_ * dim_);
+        for (size_t g = 0; g < G; ++g) {
+            count[g] = groups[g].count;
+            for (int i = 0; i < dim_; ++i) sx[g * dim_ + i] = groups[g].sum_x[i];
+            for (int i = 0; i < dim_ * dim_; ++i) sxx[g * dim_ * dim_ + i] = groups[g].sum_xxT[i];
+        }
+        return dist_b200_niw_update_all(f, dim_, s.mu, s.kappa, s.psi, s.nu, static_cast<int>(G), count.data(), sx.data(), sxx.data(), nullptr);
+    }
+    static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
+        return dist_b200_feature_update_group(f, static_cast<int>(groupid), &g, nullptr);
+    }
+};
+// ---------------------------------------------------------------------------------------------
+// MixtureIdTracker (mixture.hpp:460-521): packed (contiguous; they move under remove_group's swap-with-last) <-> global
+// (fixed, never reused) group ids
+struct MixtureIdTracker {
+    typedef uint32_t Id;
+    void init(size_t group_count = 0) {
+        packed_to_global_.clear();
+        global_to_packed_.clear();
+        global_size_ = 0;
+        for (size_t i = 0; i < group_count; ++i) add_group();
+    }
+    void add_group() {
+        const Id packed = static_cast<Id>(packed_to_global_.size()), global = static_cast<Id>(global_size_++);
+        packed_to_global_.push_back(global);
+        global_to_packed_[global] = packed;
+    }
+    void remove_group(Id packed) {
+        if (packed >= packed_size()) throw std::runtime_error("bad packed id");
+        global_to_packed_.erase(packed_to_global_[packed]);
+        const Id last = packed_to_global_.back();
+        packed_to_global_.pop_back();
+        if (packed != packed_to_global_.size()) {  // the last group moved into the hole
+            packed_to_global_[packed] = last;
+            global_to_packed_[last] = packed;
+        }
+    }
+    Id packed_to_global(Id packed) const {
+        if (packed >= packed_size()) throw std::runtime_error("bad packed id");
+        return packed_to_global_[packed];
+    }
+    Id global_to_packed(Id global) const {
+        auto i = global_to_packed_.find(global);
+        if (i == global_to_packed_.end()) throw std::runtime_error("stale global id");
+        return i->second;
+    }
+    size_t packed_size() const { return packed_to_global_.size(); }
+    size_t global_size() const { return global_size_; }
+
+  private:
+    std::vector<Id> packed_to_global_;
+    std::unordered_map<Id, Id> global_to_packed_;
+    size_t global_size_ = 0;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -73,7 +73,31 @@ def build_ref(force=False):
     return out
 
 
+def build_dropin(force=False):
+    """tests/cpp/dropin_mixture_slave.cc: the reference's own MixtureSlave instantiated with the B200 ValueScorers
+    (include/distributions_b200/reference_value_scorers.hpp), linked against the reference objects of _ref and
+    libdist_b200.so.  Container only; the binary travels to the GPU box (tests/test_dropin.py runs it there)."""
+    out = os.path.join(REF_OUT, "dropin_mixture_slave")
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tests", "cpp", "dropin_mixture_slave.cc")
+    hdr = os.path.join(root, "include", "distributions_b200", "reference_value_scorers.hpp")
+    lib_dir = os.path.join(root, "distributions_b200", "lib")
+    if not os.path.isdir(os.path.join(REF, "include", "distributions")):
+        return out if os.path.exists(out) else None
+    if build_ref() is None or not os.path.exists(os.path.join(lib_dir, "libdist_b200.so")):
+        return None
+    if not (force or _stale(out, [src, hdr, os.path.join(root, "include", "dist_b200.h")])):
+        return out
+    inc = ["-I" + os.path.join(REF, "include"), "-I" + os.path.join(HERE, "stub"), "-I" + os.path.join(root, "include")]
+    objs = [os.path.join(REF_OUT, s.replace("/", "_") + ".o") for s in REF_SOURCES]
+    # DIST_THROW_ON_ERROR: a failed DIST_ASSERT raises instead of abort(), like the reference's Python build (CMakeLists.txt:33)
+    _run(["g++"] + REF_FLAGS + ["-DDIST_THROW_ON_ERROR"] + inc + [src] + objs +
+         ["-L" + lib_dir, "-ldist_b200", "-Wl,-rpath,$ORIGIN/../../distributions_b200/lib", "-o", out, "-lm"])
+    return out
+
+
 if __name__ == "__main__":
     force = "--force" in sys.argv
     print("oracle :", build_oracle(force))
     print("ref    :", build_ref(force))
+    print("dropin :", build_dropin(force))

@@ -121,6 +121,68 @@ static void run_script(std::shared_ptr<Context> ctx, std::istream & in, const ty
     }
 }
 
+// dpd / niw through the mirror: after every incremental operation (update_group via add_value / remove_value,
+// add_group, remove_group with its swap-with-last) the per-value scores must equal those of a FRESH mixture that
+// update_all()s the same groups -- bit for bit for dpd (table gathers), to rounding for niw.  MixtureIdTracker follows
+// the same group churn.
+template <class Model, class MakeValue>
+static int incremental_equals_update_all(std::shared_ptr<Context> ctx, const typename Model::Shared & shared, MakeValue make_value,
+                                         float tol, const char * name) {
+    rng_t rng;
+    Mixture<Model> mixture(ctx);
+    MixtureIdTracker ids;
+    unsigned state = 12345u;
+    auto next = [&]() { state = state * 1664525u + 1013904223u; return state >> 8; };
+    mixture.groups().resize(5);
+    for (auto & g : mixture.groups()) g.init(shared, rng);
+    for (int i = 0; i < 20; ++i) mixture.groups(next() % 5).add_value(shared, make_value(next()), rng);
+    mixture.init(shared, rng);
+    ids.init(5);
+    int bad = 0;
+    std::vector<std::pair<size_t, typename Model::Value>> history;
+    for (int step = 0; step < 40; ++step) {
+        const unsigned op = next() % 10;
+        const size_t G = mixture.groups().size();
+        if (op < 5) {
+            const size_t gid = next() % G;
+            const auto v = make_value(next());
+            mixture.add_value(shared, gid, v, rng);
+            history.push_back(std::make_pair(static_cast<size_t>(ids.packed_to_global(gid)), v));
+        } else if (op < 7 && !history.empty()) {
+            const auto h = history.back();
+            history.pop_back();
+            mixture.remove_value(shared, ids.global_to_packed(h.first), h.second, rng);
+        } else if (op < 9) {
+            mixture.add_group(shared, rng);
+            ids.add_group();
+        } else if (G > 3) {
+            const size_t gid = next() % G;
+            const unsigned global = ids.packed_to_global(gid);
+            for (size_t i = history.size(); i-- > 0;)
+                if (history[i].first == global) history.erase(history.begin() + i);
+            mixture.remove_group(shared, gid);
+            ids.remove_group(gid);
+        }
+        Mixture<Model> fresh(ctx);
+        fresh.groups() = mixture.groups();
+        fresh.init(shared, rng);
+        const auto v = make_value(next());
+        std::vector<float> a(mixture.groups().size(), 0.f), b(a);
+        mixture.score_value(shared, v, Floats(a), rng);
+        fresh.score_value(shared, v, Floats(b), rng);
+        for (size_t g = 0; g < a.size(); ++g) {
+            const float d = a[g] > b[g] ? a[g] - b[g] : b[g] - a[g];
+            const float mag = (b[g] < 0 ? -b[g] : b[g]) + 1.f;
+            if (!(d <= tol * mag)) {
+                ++bad;
+                std::printf("selfcheck %s step %d group %zu: incremental %.9g vs update_all %.9g\n", name, step, g, a[g], b[g]);
+            }
+        }
+        if (ids.packed_size() != mixture.groups().size()) ++bad;
+    }
+    return bad;
+}
+
 int main(int argc, char ** argv) {
     if (argc < 2) return 2;
     std::ifstream in(argv[1]);
@@ -159,6 +221,18 @@ int main(int argc, char ** argv) {
                 std::printf("model bb\n");
                 run_script<BetaBernoulli>(ctx, in, BetaBernoulli::Shared::EXAMPLE(),
                                           [](std::istream & s) { int v; s >> v; return v != 0; });
+            } else if (line == "selfcheck") {
+                int bad = incremental_equals_update_all<DirichletProcessDiscrete>(
+                    ctx, DirichletProcessDiscrete::Shared::EXAMPLE(), [](unsigned r) { return static_cast<uint32_t>(r % 100); }, 0.f, "dpd");
+                typedef NormalInverseWishart<3> Niw;
+                Niw::Shared sh = Niw::Shared::EXAMPLE();
+                sh.nu = 6.f;
+                bad += incremental_equals_update_all<Niw>(ctx, sh, [](unsigned r) {
+                    Niw::Value v;
+                    for (int i = 0; i < 3; ++i) v.x[i] = static_cast<float>((r >> (5 * i)) % 32) * 0.25f - 4.f;
+                    return v;
+                }, 1e-5f, "niw3");
+                std::printf(bad ? "selfcheck FAILED %d\n" : "selfcheck ok%.0d\n", bad);
             } else if (line == "model dd") {
                 std::printf("model dd\n");
                 run_script<DirichletDiscrete<16>>(ctx, in, DirichletDiscrete<16>::Shared::EXAMPLE(),

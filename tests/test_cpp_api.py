@@ -199,6 +199,7 @@ def test_cpp_mixture_choreography(tmp_path, oracle):
     le_sizes = [3, 0, 17, 1, 250, 0, 42]
     lines.append("lowentropy")
     lines.append("5000 %d %s" % (len(le_sizes), " ".join(str(c) for c in le_sizes)))
+    lines.append("selfcheck")  # dpd / niw<3> / MixtureIdTracker: incremental group operations == update_all of the same groups
     script = tmp_path / "script.txt"
     script.write_text("\n".join(lines) + "\n")
     out = subprocess.run([exe, str(script)], capture_output=True, text=True, timeout=300)
@@ -250,3 +251,4 @@ def test_cpp_mixture_choreography(tmp_path, oracle):
     row = next(it)
     assert row[0] == "low_entropy"
     assert np.array_equal(np.array(row[1:], np.float32), oracle.low_entropy_prior(5000, le_sizes))
+    assert next(it) == ["selfcheck", "ok"], out.stdout[-2000:]

@@ -31,6 +31,10 @@ def _value(rng, name):
         return int(rng.poisson(6))
     if name == "bb":
         return bool(rng.random() < 0.4)
+    if name == "dpd":
+        return int(rng.integers(0, 100))
+    if name == "niw":
+        return (rng.normal(0, 2, 2) + np.array([1.0, -0.5])).astype(np.float32)
     return int(rng.integers(0, 16))
 
 
@@ -51,11 +55,35 @@ def _workload(name, shared, groups):
     if name == "bb":
         return dict(model=name, sizes=sizes, shared=np.array([shared.alpha, shared.beta], np.float32),
                     heads=np.array([g.heads for g in groups], np.int32), tails=np.array([g.tails for g in groups], np.int32))
+    if name == "dpd":
+        return dict(model=name, sizes=sizes, gamma=shared.gamma, alpha=shared.alpha, beta0=shared.beta0, keys=shared.values,
+                    betas=shared.betas, counts=np.array([g.dense(shared) for g in groups], np.int32).reshape(len(groups), -1))
+    if name == "niw":
+        G, d = len(groups), shared.dim
+        return dict(model=name, sizes=sizes, mu=shared.mu, kappa=shared.kappa, psi=shared.psi, nu=shared.nu,
+                    count=np.array([g.count for g in groups], np.int32),
+                    sum_x=np.array([g.sum_x for g in groups], np.float32).reshape(G, d),
+                    sum_xxT=np.array([g.sum_xxT for g in groups], np.float32).reshape(G, d, d))
     return dict(model=name, sizes=sizes, alphas=shared.alphas, counts=np.array([g.counts for g in groups], np.int32))
 
 
+def _oracle_rows(oracle, name, w, values):
+    """oracle scores [n][G] of the values against the workload's groups (no prior)"""
+    n, G = len(values), w["sizes"].size
+    if name == "niw":
+        want = np.zeros((n, G), np.float32)
+        oracle.niw_score_rows(w["mu"], w["kappa"], w["psi"], w["nu"], w["count"], w["sum_x"], w["sum_xxT"],
+                              np.ascontiguousarray(np.array(values, np.float32).reshape(n, -1)), want)
+        return want
+    ww = dict(w)
+    ww["values"] = np.array(values)
+    return cases.oracle_scores(oracle, [ww])
+
+
 def _tol(name, want):
-    extra = 25 * LOG_STEP if name == "nich" else (1e-4 if name in ("gp", "bnb") else 0.0)
+    extra = 25 * LOG_STEP if name in ("nich", "niw") else (1e-4 if name in ("gp", "bnb") else 0.0)
+    if name == "niw":  # float32 rank-1 statistics -> float32 Cholesky: the reference's own cross-flavour bar
+        return 1e-3 * (1 + 2 * np.abs(want)) + extra
     return 4e-6 * (1 + np.abs(want)) + extra
 
 
@@ -76,8 +104,7 @@ def test_mixture_choreography(ctx, oracle, name):
     def check():
         v = _value(rng, name)
         w = _workload(name, shared, mixture.groups)
-        want = np.zeros((1, len(mixture)), np.float32)
-        oracle.score_rows(cases.MODEL_ID[name], cases.oracle_caches(oracle, w), np.array([v]), want)
+        want = _oracle_rows(oracle, name, w, [v])
         noise = rng.standard_normal(len(mixture)).astype(np.float32)
         scores = noise.copy()
         mixture.score_value(shared, v, scores)  # accumulates (test_models.py:552-557)
@@ -112,23 +139,29 @@ def test_mixture_choreography(ctx, oracle, name):
     n = 80
     vals = [_value(rng, name) for _ in range(n)]
     gids = rng.integers(0, len(mixture), n).astype(np.int32)
-    expect = [model.Group().load(g.dump()) for g in mixture.groups]
-    for g in expect:
-        if name == "dd":
-            g.counts = g.counts.copy()
-    for gid, v in zip(gids, vals):
-        expect[gid].add_value(shared, v)
-    mixture.add_values(shared, np.array(vals), gids)
-    for got, exp in zip(mixture.groups, expect):
-        for k, _ in got.FIELDS:
-            a, b = np.asarray(getattr(got, k), np.float64), np.asarray(getattr(exp, k), np.float64)
-            assert np.allclose(a, b, rtol=1e-5, atol=1e-4), (name, k, a, b)
-    check()
-    if name != "gp":  # gp's score_data needs Group::log_prod, which this mirror does not carry
+    if name != "niw":  # niw statistics stay on the host: no batched add_value
+        expect = [model.Group().load(g.dump()) for g in mixture.groups]
+        for g in expect:
+            if name in ("dd", "dpd"):
+                g.counts = g.counts.copy()
+        for gid, v in zip(gids, vals):
+            expect[gid].add_value(shared, v)
+        mixture.add_values(shared, np.array(vals), gids)
+        for got, exp in zip(mixture.groups, expect):
+            for k, _ in got.FIELDS:
+                if name == "dpd":
+                    assert getattr(got, k) == getattr(exp, k), (name, k)
+                    continue
+                a, b = np.asarray(getattr(got, k), np.float64), np.asarray(getattr(exp, k), np.float64)
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-4), (name, k, a, b)
+        check()
+    if name not in ("gp", "niw"):  # gp's score_data needs Group::log_prod, which this mirror does not carry
         w = _workload(name, shared, mixture.groups)
         _, scale, want64 = oracle.score_data(w)
         assert abs(mixture.score_data(shared) - want64) <= 2e-7 * scale + 1e-5
     u = rng.random(n, dtype=np.float32)
     assign, scores = mixture.score_values(shared, np.array(vals), None, u, want_scores=True)
+    want = _oracle_rows(oracle, name, _workload(name, shared, mixture.groups), vals)
+    assert np.all(np.abs(scores - want) <= _tol(name, want))
     a_orc = oracle.sample_rows(scores.copy(), u)
     assert cases.explained_mismatch(scores.astype(np.float64), u, assign, a_orc, 2e-5).all()

@@ -60,7 +60,27 @@ def test_bb_dd_groups_and_containers():
     d.remove_value(sd, 3)
     assert d.counts.tolist() == [1, 1, 0, 1]
     assert models.nich.Shared(mu=1.5).dump() == {"mu": 1.5, "kappa": 1.0, "sigmasq": 1.0, "nu": 1.0}
-    assert set(models.MODELS) == {"nich", "gp", "bnb", "bb", "dd"}
+    assert set(models.MODELS) == {"nich", "gp", "bnb", "bb", "dd", "dpd", "niw"}
+    # dpd: sparse counters over a fixed value set (dpd.hpp:157-215); niw: rank-1 statistics (niw.hpp:247-276)
+    sp = models.dpd.Shared(values=[5, 9, 42], betas=[0.2, 0.3, 0.4])
+    assert abs(sp.beta0 - 0.1) < 1e-6
+    p = models.dpd.Group()
+    p.init(sp)
+    for v in (5, 42, 42, 9):
+        p.add_value(sp, v)
+    p.remove_value(sp, 9)
+    assert p.counts == {5: 1, 42: 2} and p.dense(sp).tolist() == [1, 0, 2]
+    import pytest
+    with pytest.raises(AssertionError):
+        p.add_value(sp, 7)  # unknown value, dpd.hpp:193
+    sw = models.niw.Shared(dim=3)
+    assert sw.nu == 4.0 and sw.psi.shape == (3, 3)
+    w = models.niw.Group()
+    w.init(sw)
+    w.add_value(sw, [1.0, 2.0, 3.0])
+    w.add_value(sw, [0.5, 0.0, -1.0])
+    w.remove_value(sw, [1.0, 2.0, 3.0])
+    assert w.count == 1 and w.sum_x.tolist() == [0.5, 0.0, -1.0] and w.sum_xxT[2, 2] == 1.0
 
 
 def test_clustering_driver_bookkeeping():
@@ -80,3 +100,33 @@ def test_clustering_driver_bookkeeping():
     le = models.LowEntropy.Mixture(ctx=None)
     le.init(models.LowEntropy(100), [0, 7])
     assert le.add_value(models.LowEntropy(100), 0, 2) is True and le.counts == [2, 7, 0] and le.empty_groupids == {2}
+
+
+def test_mixture_id_tracker():
+    """MixtureIdTracker (mixture.hpp:460-521): packed ids move under remove_group's swap-with-last, global ids never do"""
+    from distributions_b200.models import MixtureIdTracker
+    t = MixtureIdTracker(4)
+    assert [t.packed_to_global(i) for i in range(4)] == [0, 1, 2, 3]
+    t.remove_group(1)  # the last group (global 3) moves into packed slot 1
+    assert t.packed_size() == 3 and t.global_size() == 4
+    assert [t.packed_to_global(i) for i in range(3)] == [0, 3, 2]
+    assert t.global_to_packed(3) == 1 and t.global_to_packed(2) == 2
+    t.add_group()
+    assert t.packed_to_global(3) == 4 and t.global_size() == 5
+    t.remove_group(3)  # removing the last packed id moves nothing
+    assert [t.packed_to_global(i) for i in range(3)] == [0, 3, 2]
+    import pytest
+    with pytest.raises(AssertionError):
+        t.global_to_packed(1)  # stale global id
+    rng = __import__("numpy").random.default_rng(3)
+    live = {t.packed_to_global(i) for i in range(t.packed_size())}
+    for _ in range(200):  # random churn keeps the two maps inverse of each other
+        if rng.random() < 0.5 or t.packed_size() < 2:
+            t.add_group()
+            live.add(t.global_size() - 1)
+        else:
+            p = int(rng.integers(0, t.packed_size()))
+            live.discard(t.packed_to_global(p))
+            t.remove_group(p)
+        assert {t.packed_to_global(i) for i in range(t.packed_size())} == live
+        assert all(t.global_to_packed(t.packed_to_global(i)) == i for i in range(t.packed_size()))

@@ -14,7 +14,7 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n, G, F, out_dir):
+def _worker(rank, world, port, n, G, F, out_dir, row_shards):
     import torch.distributed as dist
     from distributions_b200 import capi, sharding, synth
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -25,22 +25,30 @@ def _worker(rank, world, port, n, G, F, out_dir):
     cc = synth.crosscat(911, G, n, n_gp=F // 2, n_bb=F - F // 2)
     ids = {"gp": capi.GP, "bb": capi.BB}
     ctx = capi.Context(rank)
-    mine = sharding.feature_shard(F, rank, world)
-    feats = [ctx.feature(ids[cc["features"][f]["model"]]).update_all(cc["features"][f]) for f in mine]
-    cols = [torch.from_numpy(np.ascontiguousarray(cc["features"][f]["values"],
-                                                  dtype=capi.COLUMN_DTYPE[ids[cc["features"][f]["model"]]])).to(dev) for f in mine]
     u = torch.from_numpy(cc["u"]).to(dev)
     prior = torch.empty(G, device=dev)
     ctx.prior_pitman_yor(synth.PY_ALPHA, synth.PY_D, cc["sizes"], prior)
-    # (1) fused peer push
-    shards = sharding.PeerFeatureShards(ctx, n, G)
+
+    def load(features, r0, r1):
+        feats = [ctx.feature(ids[cc["features"][f]["model"]]).update_all(cc["features"][f]) for f in features]
+        cols = [torch.from_numpy(np.ascontiguousarray(cc["features"][f]["values"][r0:r1],
+                                                      dtype=capi.COLUMN_DTYPE[ids[cc["features"][f]["model"]]])).to(dev) for f in features]
+        return feats, cols
+
+    # (1) fused peer push: pure feature shards (row_shards = 1) or the feature x row hybrid
+    shards = sharding.PeerFeatureShards(ctx, n, G, row_shards=row_shards)
+    r0, r1 = shards.rows()
+    feats, cols = load(shards.features(F), r0, r1)
     lo, hi = shards.owned()
     a_push = torch.full((hi - lo,), -1, device=dev, dtype=torch.int32)
-    for _ in range(2):  # twice: slots are reused across steps
-        shards.step(feats, cols, prior, u, a_push)
+    for _ in range(3):  # three steps: the two slot buffers alternate and are reused, flags advance by epoch
+        a_push.fill_(-1)
+        shards.step(feats, cols, prior, u[lo:hi], a_push)
     torch.cuda.synchronize()
 
-    # (2) NCCL reduce-scatter orchestration
+    # (2) NCCL reduce-scatter orchestration (pure feature shards over the whole world)
+    feats, cols = load(sharding.feature_shard(F, rank, world), 0, n)
+
     def score_partial(l, h, out):
         ctx.score_batch(feats, [c[l:h] for c in cols], h - l, prior if rank == 0 else None, out)
 
@@ -57,15 +65,16 @@ def _worker(rank, world, port, n, G, F, out_dir):
     dist.destroy_process_group()
 
 
-def test_feature_shards_two_gpus(tmp_path, oracle):
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 CUDA devices")
+@pytest.mark.parametrize("world,row_shards", [(2, 1), (4, 1), (4, 2), (8, 1), (8, 4)])
+def test_feature_shards_multi_gpu(tmp_path, oracle, world, row_shards):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip("needs %d CUDA devices" % world)
     import torch.multiprocessing as mp
     import cases
     from distributions_b200 import synth
-    world, n, G, F = 2, 5000, 40, 6
-    port = 29600 + os.getpid() % 1000
-    mp.spawn(_worker, args=(world, port, n, G, F, str(tmp_path)), nprocs=world, join=True)
+    n, G, F = 5003, 40, 2 * world + 2
+    port = 29600 + (os.getpid() + 17 * world + row_shards) % 1000
+    mp.spawn(_worker, args=(world, port, n, G, F, str(tmp_path), row_shards), nprocs=world, join=True)
     cc = synth.crosscat(911, G, n, n_gp=F // 2, n_bb=F - F // 2)
     prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, cc["sizes"])
     full = cases.oracle_scores(oracle, cc["features"], prior=prior)
