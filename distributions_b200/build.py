@@ -23,6 +23,7 @@ SOURCES = {
     "prep.cu": ["--fmad=false"],
     "score_rows.cu": [],
     "score_rows_nich.cu": [],
+    "nich_rows.cu": [],
     "score_rows_gp.cu": [],
     "score_rows_bnb.cu": [],
     "score_rows_bb.cu": [],

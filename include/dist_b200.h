@@ -77,7 +77,8 @@ typedef enum {
     DIST_B200_OPT_SMALL_TILE = 5,  /* score_rows, single feature, 64 < G <= 128: 0 = default, 1 = one 128-group tile x 256 threads
                                       (round 1), 2 = 128 threads x 3 blocks / SM with a 128-group tile, 3 = four 32-group tiles;
                                       default: 128 threads x 3, tile = G rounded up to 16 when only sampling */
-    DIST_B200_OPT_NICH_PACKED = 6, /* nich single feature: 0 = packed f32x2 loop (default), 1 = scalar loop (round 1) */
+    DIST_B200_OPT_NICH_PACKED = 6, /* nich single feature: 0 = default (packed fp32x2; sampling-only G > 128: two rows per thread),
+                                      1 = scalar loop (round 1), 2 = packed fp32x2 loop with one row per thread */
     DIST_B200_OPT_NIW_DEBUG = 7,   /* profiling only, results are WRONG when set: 1 = skip the fused sampling walk, 2 = also the epilogue math */
     DIST_B200_OPT_COUNT_ = 16
 } dist_b200_option;

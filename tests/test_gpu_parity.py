@@ -62,6 +62,7 @@ FUSED_VARIANTS = {
     "small_tile_256": {0: 1, 5: 1},                 # 64 < G <= 128: one 256-thread block / SM
     "small_tile_4x32": {0: 1, 5: 3},                # 64 < G <= 128: four 32-group tiles
     "nich_scalar": {6: 1},                          # nich: scalar loop instead of packed fp32x2
+    "nich_packed_one_row": {6: 2},                  # nich: packed loop, one row per thread (default: two rows for G > 128)
 }
 
 
