@@ -47,10 +47,13 @@ constexpr int kTcDim = 32;                 // d
 constexpr int kTcK = 48;                   // K of the GEMM: d + the b column, padded to the k-step of 16
 constexpr int kTcGroupsPerBlock = 8;       // groups per B tile (N = 256)
 constexpr int kTcRows = 128;               // rows per tile (M)
-constexpr int kAImageBytes = kTcRows * kTcK * 2;            // one fp16 A image: 12 KB
-constexpr int kATileBytes = 2 * kAImageBytes;               // hi + lo
-constexpr int kBImageBytes = 256 * kTcK * 2;                // one fp16 B image of a block: 24 KB
-constexpr int kBlockRecBytes = 2 * kBImageBytes + kTcGroupsPerBlock * 4 * 4;  // W_hi | W_lo | consts[8][4]
+constexpr int kAImageBytes = kTcRows * kTcK * 2;            // the hi image of a row tile (K = 48): 12 KB
+constexpr int kALoBytes = kTcRows * kTcDim * 2;             // its lo image (K = 32: the augmented columns have no low part): 8 KB
+constexpr int kATileBytes = kAImageBytes + kALoBytes;       // hi | lo
+constexpr int kBImageBytes = 256 * kTcK * 2;                // the hi image of a block (K = 48): 24 KB
+constexpr int kBLoBytes = 256 * kTcDim * 2;                 // its lo image (K = 32): 16 KB
+constexpr int kBImagesBytes = kBImageBytes + kBLoBytes;
+constexpr int kBlockRecBytes = kBImagesBytes + kTcGroupsPerBlock * 4 * 4;  // W_hi | W_lo | consts[8][4]
 constexpr int kChunkTiles = 4;             // resident row tiles per chunk (512 rows)
 constexpr int kBStages = 2;
 constexpr int kFusedThreads = 320;
@@ -184,17 +187,21 @@ __global__ void __launch_bounds__(256) niw_tc_prep_kernel(int G, const float *__
     __syncthreads();
     unsigned char *rec_out = blockrecs + static_cast<size_t>(blk) * kBlockRecBytes;
     __half *w_hi = reinterpret_cast<__half *>(rec_out), *w_lo = w_hi + 256 * kTcK;
-    float *consts = reinterpret_cast<float *>(rec_out + 2 * kBImageBytes);
+    float *consts = reinterpret_cast<float *>(rec_out + kBImagesBytes);
     for (int e = tid; e < 256 * kTcK; e += blockDim.x) {
         const int n = e / kTcK, k = e - n * kTcK;  // B row n = (group in block) * 32 + i, column k
         const int g = blk * kTcGroupsPerBlock + (n >> 5), i = n & 31;
-        float w = 0.f;
-        if (g < G && k < kTcDim) w = recs[static_cast<size_t>(g) * REC + kTcDim + i * kTcDim + k] * scale[n >> 5];
-        else if (g < G && k == kTcDim) w = nb[n] * scale[n >> 5];
-        const __half hi = __float2half_rn(w);
         const int off = core_offset_halves(n, k, 32);
-        w_hi[off] = hi;
-        w_lo[off] = __float2half_rn(w - __half2float(hi));
+        if (k < kTcDim) {
+            const float w = g < G ? recs[static_cast<size_t>(g) * REC + kTcDim + i * kTcDim + k] * scale[n >> 5] : 0.f;
+            const __half hi = __float2half_rn(w);
+            w_hi[off] = hi;
+            w_lo[off] = __float2half_rn(w - __half2float(hi));
+        } else {  // augmented columns of the hi image: -b's high term in column 32, its low term in column 33, zeros after
+            const float w = g < G ? nb[n] * scale[n >> 5] : 0.f;
+            const __half hi = __float2half_rn(w);
+            w_hi[off] = k == kTcDim ? hi : k == kTcDim + 1 ? __float2half_rn(w - __half2float(hi)) : __float2half_rn(0.f);
+        }
     }
     if (tid < kTcGroupsPerBlock) {
         const int g = blk * kTcGroupsPerBlock + tid;
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(256) niw_tc_pack_x_kernel(size_t N, const floa
     }
     __syncthreads();
     const float sc = s_scale;
-    __half *hi_img = xpack + tile * (2 * kTcRows * kTcK), *lo_img = hi_img + kTcRows * kTcK;
+    __half *hi_img = xpack + tile * (kATileBytes / 2), *lo_img = hi_img + kTcRows * kTcK;
     const float *xf = reinterpret_cast<const float *>(x);
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {  // one 16-byte core row (8 halves) per store
@@ -250,15 +257,13 @@ __global__ void __launch_bounds__(256) niw_tc_pack_x_kernel(size_t N, const floa
         *reinterpret_cast<uint4 *>(hi_img + off) = *reinterpret_cast<const uint4 *>(hi);
         *reinterpret_cast<uint4 *>(lo_img + off) = *reinterpret_cast<const uint4 *>(lo);
     }
-    {   // columns 32..47: the scaled constant 1 (exact in fp16: a power of two), then zeros; the lo image is all zero
+    {   // columns 32..47 of the hi image: the scaled constant 1 (exact in fp16: a power of two) twice, then zeros
         __align__(16) __half aug[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) aug[i] = __float2half_rn(0.f);
-        const uint4 zero = *reinterpret_cast<const uint4 *>(aug);
-        if ((tid & 1) == 0) aug[0] = __float2half_rn(row < N ? sc : 0.f);
+        if ((tid & 1) == 0) aug[0] = aug[1] = __float2half_rn(row < N ? sc : 0.f);  // one for -b's high term, one for its low term
         const int off = core_offset_halves(r, kTcDim + 8 * (tid & 1), kTcRows / 8);
         *reinterpret_cast<uint4 *>(hi_img + off) = *reinterpret_cast<const uint4 *>(aug);
-        *reinterpret_cast<uint4 *>(lo_img + off) = zero;
     }
 }
 
@@ -271,7 +276,7 @@ struct NiwTcArgs {
     const float *sx;                 // [ntiles]
     const float *prior;              // [G] or nullptr
     float *scores;                   // materialising mode: [N][G]
-    float *scratch;                  // fused mode: [grid][kChunkTiles * 128][Gpad]
+    float *scratch;                  // fused mode: [grid][Gpad / 4][kChunkTiles * 128] float4 (four groups of one row)
     const float *u;                  // fused mode
     int32_t *assign;                 // fused mode
 };
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                 auto load_a = [&](int t) {
                     mbar_wait(&a_empty[t], aphase ^ 1);  // the previous chunk's MMAs on this tile have retired
                     mbar_expect_tx(&a_full[t], kATileBytes);
-                    bulk_g2s(As + t * kATileBytes, a.xpack + (t0 + t) * (2 * kTcRows * kTcK), kATileBytes, &a_full[t]);
+                    bulk_g2s(As + t * kATileBytes, a.xpack + (t0 + t) * (kATileBytes / 2), kATileBytes, &a_full[t]);
                 };
                 // in consumption order: tile 0, block 0, the remaining tiles, the remaining blocks
                 load_a(0);
@@ -370,9 +375,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                             const uint32_t ao = ks * 2 * (kTcRows / 8) * 128, bo = ks * 2 * 32 * 128;
                             umma_f16(d_addr, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, acc);
                             acc = 1;
-                            // the augmented k-step's lo image of A is all zero: its lo x hi product is skipped
-                            if (ks < kTcDim / 16)
-                                umma_f16(d_addr, make_smem_desc(a_lo + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, 1);
+                            // the augmented k-step carries both terms of -b in the hi images: one MMA
+                            if (a.debug >= 5 || ks == kTcDim / 16) continue;  // (debug 5: hi x hi only)
+                            umma_f16(d_addr, make_smem_desc(a_lo + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, 1);
                             umma_f16(d_addr, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_lo + bo, 32 * 128, 128), idesc, 1);
                         }
                         if (blk == nb - 1) umma_commit(&a_empty[t]);  // tile reusable by the next chunk once these retire
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
             }
             for (int blk = 0; blk < nb; ++blk) {
                 mbar_wait(&b_full[bstage], bphase);
-                const float *cs = reinterpret_cast<const float *>(Bs + bstage * kBlockRecBytes + 2 * kBImageBytes);
+                const float *cs = reinterpret_cast<const float *>(Bs + bstage * kBlockRecBytes + kBImagesBytes);
                 float pr[kPer];
 #pragma unroll
                 for (int jj = 0; jj < kPer; ++jj) {
@@ -422,6 +427,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                     mbar_wait(&t_full[tb], fphase[tb]);
                     fphase[tb] ^= 1;
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    if (a.debug >= 4) {  // barrier hand-offs only: the rate of the loader + MMA stream alone
+                        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                        if (lane == 0) mbar_arrive(&t_empty[tb]);
+                        tb ^= 1;
+                        continue;
+                    }
                     uint32_t yr[2][64];
                     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tb * 256 + h * kPer * 32;
                     if (a.debug >= 3) {
@@ -460,8 +471,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                     }
                     const size_t row = (t0 + t) * kTcRows + r_in_tile;
                     if (kFused) {
-                        // the chunk's scores stay on chip (L2): [row in chunk][Gpad]; online (max, sum exp) of this row x half
-                        *reinterpret_cast<float4 *>(scratch + static_cast<size_t>(t * kTcRows + r_in_tile) * a.Gpad + blk * kTcGroupsPerBlock + h * kPer) =
+                        // the chunk's scores stay on chip (L2), quad-major so that a warp stores / walks whole lines; online (max, sum exp) of this row x half
+                        reinterpret_cast<float4 *>(scratch)[static_cast<size_t>(blk * 2 + h) * (kChunkTiles * kTcRows) + t * kTcRows + r_in_tile] =
                             make_float4(out[0], out[1], out[2], out[3]);
                         const float m4 = fmaxf(fmaxf(out[0], out[1]), fmaxf(out[2], out[3])) * kLog2e;
                         const float mn = fmaxf(fmaxf(om[t], m4), -3.0e38f);  // finite even when all four groups are padding
@@ -510,12 +521,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                     const float mm = fmaxf(m0, m1);  // max score * log2e
                     const float total = half_s[rc] * mufu_ex2(m0 - mm) + half_s[kChunkTiles * kTcRows + rc] * mufu_ex2(m1 - mm);
                     float tt = total * __ldg(a.u + row);
-                    const float4 *src = reinterpret_cast<const float4 *>(scratch + static_cast<size_t>(rc) * a.Gpad);
+                    const float4 *src = reinterpret_cast<const float4 *>(scratch) + rc;  // quad j of this row: src[j * rows per chunk]
                     unsigned neg = 0;
                     for (int j4 = 0; j4 < a.Gpad / 4; j4 += 8) {  // Gpad is a multiple of 8: 32 cells per step, eight loads in flight
                         float4 v[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = j4 + k < a.Gpad / 4 ? src[j4 + k] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                        for (int k = 0; k < 8; ++k)
+                            v[k] = j4 + k < a.Gpad / 4 ? src[static_cast<size_t>(j4 + k) * (kChunkTiles * kTcRows)] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             tt -= mufu_ex2(fmaf(v[k].x, kLog2e, -mm));
