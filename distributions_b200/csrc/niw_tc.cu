@@ -23,20 +23,28 @@
 // epilogue issued 32 broadcast LDS.128 per thread per tile, and a warp-wide LDS.128 occupies the shared-memory pipe for
 // four wavefronts even when every lane reads the same address -- 1 000 of the pipe's cycles per (tile, block), on top
 // of the 600 the tensor core needs for its own operand reads: the kernel sat at 35 % tensor-pipe activity
-// (profiles/r02_c5_niw_v1_lds_bound.txt).  8 MMAs per (tile, block): two k-steps x {hi hi, lo hi, hi lo}, and the
-// augmented k-step without its all-zero lo hi product; 3xTF32 (round 1) needed 12 at twice the operand bytes.
+// (profiles/r02_c5_niw_v1_lds_bound.txt).  -b is split like W, and both of its terms sit in the hi image (columns 32 and
+// 33, against two copies of the constant in A), so the augmented k-step is ONE MMA: 7 MMAs per (tile, block) = two k-steps x
+// {hi hi, lo hi, hi lo} + the augmented hi hi; the lo images stop at K = 32.  3xTF32 (round 1) needed 12 at twice the bytes.
 //
-// Schedule (per CTA, one per SM, persistent over chunks of kChunkTiles row tiles; 10 warps):
+// Schedule (per CTA, one per SM, persistent over chunks of kChunkTiles row tiles; 18 warps):
 //   warp 0 (one lane)  loader   -- cp.async.bulk of the chunk's A images (resident for the whole chunk) and of the
-//                                  32 block records {W_hi, W_lo, -b, constants} through a 3-stage ring
-//   warp 1 (one lane)  issuer   -- for every block, for every resident tile: 6 x tcgen05.mma, tcgen05.commit
-//   warps 2..9         epilogue -- tcgen05.ld, (y c - b)^2 sums on packed fp32x2, MUFU.LG2, the score; per row an ONLINE
+//                                  32 block records {W_hi, W_lo, constants} through a 2-stage ring
+//   warp 1 (one lane)  issuer   -- for every block, for every resident tile: 7 x tcgen05.mma, tcgen05.commit
+//   warps 2..17        epilogue -- four warps per TMEM lane quarter, each owns 64 accumulator columns (two groups):
+//                                  tcgen05.ld, sums of squares on packed fp32x2, MUFU.LG2, the score; per row an ONLINE
 //                                  (max, sum of exp) pair; the chunk's scores go to a per-CTA scratch block
-//                                  (512 KB, reused every chunk: it lives in L2), and after the last block the same warps
-//                                  walk their rows: t = u * total, first group with t - sum exp <= 0 (random.hpp:315-333).
-// L2 -> SM traffic: the A images once (128 MB) + 1 MB of block records per chunk (2 GB at c5) -- round 1 re-streamed the
-// rows for every block (8 GB) and round-tripped 2 GB of scores through HBM for a separate sampler.
+//                                  (512 KB, reused every chunk: it lives in L2; pair-major, so a warp stores and later
+//                                  walks whole lines), and after the last block the same warps walk one row each:
+//                                  t = u * total, first group with t - sum exp <= 0 (random.hpp:315-333).
+// L2 -> SM traffic: the A images once (160 MB) + 1.3 MB of block records per chunk (2.5 GB at c5) -- round 1 re-streamed
+// the rows for every block (8 GB) and round-tripped 2 GB of scores through HBM for a separate sampler.
 // Without a sampler request (score_batch, accumulate, mixed feature lists) the same kernel writes [N][G] scores.
+//
+// What bounds it (profiles/r02_c5_power.txt): the board's 1 000 W power cap.  nvidia-smi during back-to-back launches shows
+// sw_power_cap active and the SM clock at 1.65 - 1.73 GHz instead of 1.965; with the MMAs alone (debug 4) the kernel runs at
+// the tensor pipe's rate for 7 MMAs per (tile, block).  Every removed MMA, shared-memory operand read or L2 round trip is
+// therefore time: 8 -> 7 MMAs, K = 32 lo images and whole-line scratch accesses took the kernel from 1.97 to 1.55 ms.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -56,7 +64,8 @@ constexpr int kBImagesBytes = kBImageBytes + kBLoBytes;
 constexpr int kBlockRecBytes = kBImagesBytes + kTcGroupsPerBlock * 4 * 4;  // W_hi | W_lo | consts[8][4]
 constexpr int kChunkTiles = 4;             // resident row tiles per chunk (512 rows)
 constexpr int kBStages = 2;
-constexpr int kFusedThreads = 320;
+constexpr int kEpiWarps = 16;            // epilogue warps: four per TMEM lane quarter, each owns a quarter of the columns
+constexpr int kFusedThreads = 64 + 32 * kEpiWarps;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -286,9 +295,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *As = smem_raw;                                        // [kChunkTiles][hi | lo]  64 KB
     unsigned char *Bs = As + kChunkTiles * kATileBytes;                  // [kBStages][block record]
-    float *half_m = reinterpret_cast<float *>(Bs + kBStages * kBlockRecBytes);   // [2][kChunkTiles * 128] online max per column half
-    float *half_s = half_m + 2 * kChunkTiles * kTcRows;                          // [2][kChunkTiles * 128] online sum
-    uint64_t *bars = reinterpret_cast<uint64_t *>(half_s + 2 * kChunkTiles * kTcRows);
+    constexpr int kParts = kEpiWarps / 4;                                        // column parts of a block (one per epilogue warp of a lane quarter)
+    float *half_m = reinterpret_cast<float *>(Bs + kBStages * kBlockRecBytes);   // [kParts][kChunkTiles * 128] online max per column part
+    float *half_s = half_m + kParts * kChunkTiles * kTcRows;                     // [kParts][kChunkTiles * 128] online sum
+    uint64_t *bars = reinterpret_cast<uint64_t *>(half_s + kParts * kChunkTiles * kTcRows);
     uint64_t *a_full = bars, *a_empty = a_full + kChunkTiles, *b_full = a_empty + kChunkTiles, *b_empty = b_full + kBStages;
     uint64_t *t_full = b_empty + kBStages, *t_empty = t_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
@@ -302,11 +312,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
         }
         for (int i = 0; i < kBStages; ++i) {
             mbar_init(&b_full[i], 1);
-            mbar_init(&b_empty[i], 8);  // one arrival per epilogue warp: the record also carries their -b / constants
+            mbar_init(&b_empty[i], kEpiWarps);  // one arrival per epilogue warp: the record also carries their constants
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&t_full[i], 1);
-            mbar_init(&t_empty[i], 8);
+            mbar_init(&t_empty[i], kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -393,12 +403,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
             }
         }
     } else {
-        // ===================== epilogue + sampler (8 warps) =====================
-        const int e = warp - 2;        // 0..7
+        // ===================== epilogue + sampler (kEpiWarps warps) =====================
+        const int e = warp - 2;
         const int q = warp & 3;        // TMEM lane quarter this warp may access
-        const int h = e >> 2;          // column half: groups [4h, 4h + 4) of the block
+        const int h = e >> 2;          // column part: groups [kPer h, kPer h + kPer) of the block
         const int r_in_tile = q * 32 + lane;
-        constexpr int kPer = kTcGroupsPerBlock / 2;
+        constexpr int kPer = kTcGroupsPerBlock / kParts;
+        static_assert(kPer == 2, "the epilogue below loads 64 columns (two cells) per thread");
         uint32_t bstage = 0, bphase = 0, fphase[2] = {0, 0};
         int tb = 0;
         float *scratch = kFused ? a.scratch + static_cast<size_t>(blockIdx.x) * kChunkTiles * kTcRows * a.Gpad : nullptr;
@@ -433,14 +444,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                         tb ^= 1;
                         continue;
                     }
-                    uint32_t yr[2][64];
+                    uint32_t yr[64];
                     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tb * 256 + h * kPer * 32;
                     if (a.debug >= 3) {
 #pragma unroll
-                        for (int i = 0; i < 64; ++i) yr[0][i] = yr[1][i] = 0x3f800000u + i;
+                        for (int i = 0; i < 64; ++i) yr[i] = 0x3f800000u + i;
                     } else {
-                        tmem_ld64_nowait(t_row, yr[0]);
-                        tmem_ld64_nowait(t_row + 64, yr[1]);
+                        tmem_ld64_nowait(t_row, yr);
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -449,12 +459,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                     float out[kPer];
                     if (a.debug >= 2) {
 #pragma unroll
-                        for (int jj = 0; jj < kPer; ++jj) out[jj] = __uint_as_float(yr[jj >> 1][(jj & 1) * 32]);
+                        for (int jj = 0; jj < kPer; ++jj) out[jj] = __uint_as_float(yr[jj * 32]);
                     } else
 #pragma unroll
                     for (int jj = 0; jj < kPer; ++jj) {
                         const int j = h * kPer + jj;
-                        const uint32_t *y = &yr[jj >> 1][(jj & 1) * 32];  // (y - b) 2^(ex + ew)
+                        const uint32_t *y = &yr[jj * 32];  // (y - b) 2^(ex + ew)
                         const float4 c = *reinterpret_cast<const float4 *>(cs + j * 4);
                         const float unscale = sxt[t] * c.w;  // 2^-(ex + ew): exact
                         uint64_t qa = 0ull, qb = 0ull;
@@ -472,10 +482,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                     const size_t row = (t0 + t) * kTcRows + r_in_tile;
                     if (kFused) {
                         // the chunk's scores stay on chip (L2), quad-major so that a warp stores / walks whole lines; online (max, sum exp) of this row x half
-                        reinterpret_cast<float4 *>(scratch)[static_cast<size_t>(blk * 2 + h) * (kChunkTiles * kTcRows) + t * kTcRows + r_in_tile] =
-                            make_float4(out[0], out[1], out[2], out[3]);
-                        const float m4 = fmaxf(fmaxf(out[0], out[1]), fmaxf(out[2], out[3])) * kLog2e;
-                        const float mn = fmaxf(fmaxf(om[t], m4), -3.0e38f);  // finite even when all four groups are padding
+                        reinterpret_cast<float2 *>(scratch)[static_cast<size_t>(blk * kParts + h) * (kChunkTiles * kTcRows) + t * kTcRows + r_in_tile] =
+                            make_float2(out[0], out[1]);
+                        const float m4 = fmaxf(out[0], out[1]) * kLog2e;
+                        const float mn = fmaxf(fmaxf(om[t], m4), -3.0e38f);  // finite even when both groups are padding
                         float s4 = 0.f;
 #pragma unroll
                         for (int jj = 0; jj < kPer; ++jj) s4 += mufu_ex2(fmaf(out[jj], kLog2e, -mn));
@@ -484,13 +494,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                     } else if (row < a.N) {
                         const int gbase = blk * kTcGroupsPerBlock + h * kPer;
                         float *dst = a.scores + row * a.G + gbase;
-                        if (gbase + kPer <= a.G && (a.G & 3) == 0) {
-                            float4 o0 = make_float4(out[0], out[1], out[2], out[3]);
+                        if (gbase + kPer <= a.G && (a.G & 1) == 0) {
+                            float2 o0 = make_float2(out[0], out[1]);
                             if (a.accumulate) {
-                                const float4 p0 = *reinterpret_cast<float4 *>(dst);
-                                o0 = make_float4(o0.x + p0.x, o0.y + p0.y, o0.z + p0.z, o0.w + p0.w);
+                                const float2 p0 = *reinterpret_cast<float2 *>(dst);
+                                o0 = make_float2(o0.x + p0.x, o0.y + p0.y);
                             }
-                            *reinterpret_cast<float4 *>(dst) = o0;
+                            *reinterpret_cast<float2 *>(dst) = o0;
                         } else {
 #pragma unroll
                             for (int jj = 0; jj < kPer; ++jj)
@@ -506,44 +516,45 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                 }
             }
             if (kFused) {
-                // ---- sample_from_scores for the chunk's rows: combine the two column halves, then every thread walks two rows
+                // ---- sample_from_scores for the chunk's rows: combine the column parts, then every thread walks one row
 #pragma unroll
                 for (int t = 0; t < kChunkTiles; ++t) {
                     half_m[h * kChunkTiles * kTcRows + t * kTcRows + r_in_tile] = om[t];
                     half_s[h * kChunkTiles * kTcRows + t * kTcRows + r_in_tile] = os[t];
                 }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");  // scratch and the half pairs are complete (CTA-scope visibility)
+                asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kEpiWarps) : "memory");  // scratch and the part pairs are complete (CTA-scope visibility)
                 const int et = tid - 64;
-                for (int rc = et; rc < nt * kTcRows; rc += 256) {
+                for (int rc = et; rc < nt * kTcRows; rc += 32 * kEpiWarps) {
                     const size_t row = t0 * kTcRows + rc;
                     if (row >= a.N || a.debug >= 1) continue;
-                    const float m0 = half_m[rc], m1 = half_m[kChunkTiles * kTcRows + rc];
-                    const float mm = fmaxf(m0, m1);  // max score * log2e
-                    const float total = half_s[rc] * mufu_ex2(m0 - mm) + half_s[kChunkTiles * kTcRows + rc] * mufu_ex2(m1 - mm);
+                    float mm = half_m[rc];  // max score * log2e
+#pragma unroll
+                    for (int p = 1; p < kParts; ++p) mm = fmaxf(mm, half_m[p * kChunkTiles * kTcRows + rc]);
+                    float total = 0.f;
+#pragma unroll
+                    for (int p = 0; p < kParts; ++p)
+                        total = fmaf(half_s[p * kChunkTiles * kTcRows + rc], mufu_ex2(half_m[p * kChunkTiles * kTcRows + rc] - mm), total);
                     float tt = total * __ldg(a.u + row);
-                    const float4 *src = reinterpret_cast<const float4 *>(scratch) + rc;  // quad j of this row: src[j * rows per chunk]
+                    const float2 *src = reinterpret_cast<const float2 *>(scratch) + rc;  // pair j of this row: src[j * rows per chunk]
+                    const float2 ninf = make_float2(-INFINITY, -INFINITY);
+                    const int npairs = a.Gpad / 2;
                     unsigned neg = 0;
-                    for (int j4 = 0; j4 < a.Gpad / 4; j4 += 8) {  // Gpad is a multiple of 8: 32 cells per step, eight loads in flight
-                        float4 v[8];
+                    for (int j2 = 0; j2 < npairs; j2 += 16) {  // 32 cells per step, sixteen loads in flight
+                        float2 v[16];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            v[k] = j4 + k < a.Gpad / 4 ? src[static_cast<size_t>(j4 + k) * (kChunkTiles * kTcRows)] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                        for (int k = 0; k < 16; ++k) v[k] = j2 + k < npairs ? src[static_cast<size_t>(j2 + k) * (kChunkTiles * kTcRows)] : ninf;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
+                        for (int k = 0; k < 16; ++k) {
                             tt -= mufu_ex2(fmaf(v[k].x, kLog2e, -mm));
                             neg += __float_as_uint(tt) >> 31;
                             tt -= mufu_ex2(fmaf(v[k].y, kLog2e, -mm));
                             neg += __float_as_uint(tt) >> 31;
-                            tt -= mufu_ex2(fmaf(v[k].z, kLog2e, -mm));
-                            neg += __float_as_uint(tt) >> 31;
-                            tt -= mufu_ex2(fmaf(v[k].w, kLog2e, -mm));
-                            neg += __float_as_uint(tt) >> 31;
                         }
                     }
-                    const int walked = (a.Gpad / 4 + 7) / 8 * 32;  // cells walked, incl. the -inf fill of a ragged last step
+                    const int walked = (npairs + 15) / 16 * 32;  // cells walked, incl. the -inf fill of a ragged last step
                     a.assign[row] = min(walked - static_cast<int>(neg), a.G - 1);
                 }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");  // nobody overwrites the scratch while a row is still being walked
+                asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kEpiWarps) : "memory");  // nobody overwrites the scratch while a row is still being walked
             }
         }
     }
@@ -613,7 +624,7 @@ int launch_niw_tc(dist_b200_ctx *ctx, int G, const float *tc_buf, const void *va
     niw_tc_pack_x_kernel<<<static_cast<unsigned>(ntiles), 256, 0, s>>>(N, static_cast<const float *>(values), reinterpret_cast<__half *>(base),
                                                                    reinterpret_cast<float *>(base + xbytes));
     const size_t smem = static_cast<size_t>(kChunkTiles) * kATileBytes + static_cast<size_t>(kBStages) * kBlockRecBytes +
-                        4 * kChunkTiles * kTcRows * sizeof(float) + 32 * sizeof(uint64_t) + 1024;
+                        2 * (kEpiWarps / 4) * kChunkTiles * kTcRows * sizeof(float) + 32 * sizeof(uint64_t) + 1024;
     cudaError_t e;
     if (fused) {
         e = cudaFuncSetAttribute(niw_tc_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
