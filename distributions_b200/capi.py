@@ -47,6 +47,7 @@ SIGNATURES = {
     "dist_b200_remove_rows_batch": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz, c_p]),
     "dist_b200_rows_accumulate": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz, c_p, c_p]),
     "dist_b200_rows_merge": (c_i, [c_p, c_p, c_i, c_p, c_i, c_p]),
+    "dist_b200_rows_xchg_doubles": (c_i, [c_p, c_i, c_p]),
     "dist_b200_remove_rows_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_p, c_sz]),
     "dist_b200_gp_set_log_prod": (c_i, [c_p, c_p, c_p]),
     "dist_b200_score_data_grid": (c_i, [c_p, c_p, c_sz, c_sz, c_p, c_p]),
@@ -253,8 +254,16 @@ class Context:
         F, fa, ca = self._lists(features, columns)
         self.check(self.L.dist_b200_add_rows_batch(self.h, fa, F, ca, _dev_ptr(assign_dev), n_rows, stream), "add_rows_batch")
 
+    def rows_xchg_doubles(self, features):
+        """size (float64 elements) of the row-shard exchange buffer: [4][G] per pooled feature, then [G][dim] per dd / dpd table"""
+        F = len(features)
+        fa = (c_p * F)(*[f.h for f in features])
+        n = ctypes.c_size_t(0)
+        self.check(self.L.dist_b200_rows_xchg_doubles(fa, F, ctypes.byref(n)), "rows_xchg_doubles")
+        return int(n.value)
+
     def rows_accumulate(self, features, columns, assign_dev, n_rows, xchg_dev, stream=None):
-        """row shards: this rank's accumulators into xchg_dev [F][4][G] float64 (then all-reduce, then rows_merge)"""
+        """row shards: this rank's accumulators into xchg_dev (rows_xchg_doubles float64; then all-reduce, then rows_merge)"""
         F, fa, ca = self._lists(features, columns)
         self.check(self.L.dist_b200_rows_accumulate(self.h, fa, F, ca, _dev_ptr(assign_dev), n_rows, _dev_ptr(xchg_dev), stream),
                    "rows_accumulate")

@@ -767,6 +767,10 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
 // ([n_features][4][G] doubles) for an all-reduce; kRowsMerge = merge from the (all-reduced) `xchg`
 enum { kRowsBoth = 0, kRowsAccumulate = 1, kRowsMerge = 2 };
 
+static bool pooled_model(int model) {
+    return model == DIST_B200_NICH || model == DIST_B200_GP || model == DIST_B200_BB || model == DIST_B200_BNB;
+}
+
 static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
                       const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, int sign, void *stream,
                       int phase = kRowsBoth, double *xchg = nullptr) {
@@ -778,21 +782,30 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
         for (int i = 0; i < n_features; ++i) {
             const dist_b200_feature *f = features[i];
             if (!f) return fail(ctx, DIST_B200_ERR_INVALID, "rows exchange: null feature");
-            if (f->model == DIST_B200_DD || f->model == DIST_B200_DPD || f->model == DIST_B200_NIW)
-                return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "rows exchange: pooled-statistics models only (nich / gp / bb / bnb)");
+            if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "rows exchange: niw statistics stay on the host");
             if (f->G != features[0]->G) return fail(ctx, DIST_B200_ERR_INVALID, "rows exchange: features disagree on the number of groups");
         }
     }
     cudaStream_t s = as_stream(stream);
-    size_t acc_need = 0;
+    size_t acc_need = 0, table_tmp = 0;  // pooled accumulators | (exchange) one count table of delta counts
+    int n_pooled = 0;
     for (int i = 0; i < n_features; ++i) {
         dist_b200_feature *f = features[i];
         if (!f || f->ctx != ctx || (phase != kRowsMerge && !columns_dev[i])) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows: bad feature / column");
         if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: niw statistics stay on the host");
         if (f->G < 1 || !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: call update_all first");
-        if (f->model == DIST_B200_NICH || f->model == DIST_B200_GP || f->model == DIST_B200_BB || f->model == DIST_B200_BNB)
+        if (pooled_model(f->model)) {
             acc_need = std::max(acc_need, add_rows_acc_bytes(f->G) * std::min(n_features, kAddBatch));
+            ++n_pooled;
+        } else if (phase == kRowsAccumulate) {
+            table_tmp = std::max(table_tmp, round_up(sizeof(int32_t) * static_cast<size_t>(f->G) * f->dim, 256));
+        }
     }
+    acc_need = round_up(acc_need, 256);
+    const size_t pooled_bytes = acc_need;
+    acc_need += table_tmp;
+    // exchange layout: the pooled features' [4][G] blocks first (list order), then the count tables (list order)
+    size_t table_off = phase == kRowsBoth ? 0 : static_cast<size_t>(n_pooled) * 4 * features[0]->G;
     if (acc_need > ctx->add_acc_bytes) {
         if (ctx->add_acc) {
             DISTB200_CUDA(ctx, cudaDeviceSynchronize());
@@ -827,6 +840,24 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
         b.n = 0;
         return r;
     };
+    // count tables (dd / dpd).  Single GPU: the rows go straight into the feature's table.  Exchange: accumulate = this
+    // rank's delta counts as doubles into the feature's block of xchg, merge = the summed deltas into the table.
+    auto table_counts = [&](dist_b200_feature *f, int i) -> int {
+        const size_t cells = static_cast<size_t>(f->G) * f->dim;
+        int r = DIST_B200_OK;
+        if (phase == kRowsBoth) {
+            r = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, sign, s);
+        } else if (phase == kRowsAccumulate) {
+            int32_t *tmp = reinterpret_cast<int32_t *>(static_cast<char *>(ctx->add_acc) + pooled_bytes);
+            DISTB200_CUDA(ctx, cudaMemsetAsync(tmp, 0, sizeof(int32_t) * cells, s));
+            r = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, +1, s, tmp);
+            if (!r) r = launch_counts_to_doubles(ctx, tmp, xchg + table_off, cells, s);
+        } else {
+            r = launch_merge_counts(ctx, reinterpret_cast<int32_t *>(f->stats), xchg + table_off, cells, sign, s);
+        }
+        table_off += cells;
+        return r;
+    };
     for (int i = 0; i < n_features; ++i) {
         dist_b200_feature *f = features[i];
         const int G = f->G;
@@ -854,13 +885,15 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
             } break;
             case DIST_B200_DD:
                 if (!f->alphas_dev) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: dd alphas not resident (update_all first)");
-                if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, sign, s))) return rc;
+                if ((rc = table_counts(f, i))) return rc;
+                if (phase == kRowsAccumulate) break;
                 if ((rc = launch_dd_prep(ctx, f->dim, f->alphas_dev, f->alpha_sum, 0, G, reinterpret_cast<const int32_t *>(stat_ptr(f, 0)),
                                          static_cast<float *>(f->params), s)))
                     return rc;
                 break;
             case DIST_B200_DPD:
-                if ((rc = launch_add_rows_counts(ctx, f, columns_dev[i], assign_dev, n_rows, sign, s))) return rc;
+                if ((rc = table_counts(f, i))) return rc;
+                if (phase == kRowsAccumulate) break;
                 if ((rc = dpd_rebuild(f, reinterpret_cast<const float *>(dpd_betas(f)), reinterpret_cast<const int32_t *>(f->stats), s)))
                     return rc;
                 break;
@@ -881,6 +914,19 @@ int dist_b200_rows_accumulate(dist_b200_ctx *ctx, dist_b200_feature *const *feat
                               const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, double *xchg_dev,
                               void *stream) {
     return rows_batch(ctx, features, n_features, columns_dev, assign_dev, n_rows, +1, stream, kRowsAccumulate, xchg_dev);
+}
+
+int dist_b200_rows_xchg_doubles(dist_b200_feature *const *features, int n_features, size_t *n_doubles) {
+    if (n_features < 0 || (n_features && !features) || !n_doubles) return DIST_B200_ERR_INVALID;
+    size_t n = 0;
+    for (int i = 0; i < n_features; ++i) {
+        const dist_b200_feature *f = features[i];
+        if (!f) return DIST_B200_ERR_INVALID;
+        if (f->model == DIST_B200_NIW) return fail(f->ctx, DIST_B200_ERR_UNSUPPORTED, "rows exchange: niw statistics stay on the host");
+        n += pooled_model(f->model) ? static_cast<size_t>(4) * f->G : static_cast<size_t>(f->G) * f->dim;
+    }
+    *n_doubles = n;
+    return DIST_B200_OK;
 }
 
 int dist_b200_rows_merge(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features, const double *xchg_dev,

@@ -196,7 +196,9 @@ int launch_merge_prep_batch(dist_b200_ctx *ctx, const AddBatch &b, cudaStream_t 
 int launch_pack_accumulators(dist_b200_ctx *ctx, const AddBatch &b, double *xchg, cudaStream_t s);  // prep.cu
 // dd / dpd: counts updated in place
 int launch_add_rows_counts(dist_b200_ctx *ctx, dist_b200_feature *f, const void *column, const int32_t *assign, size_t N,
-                           int sign, cudaStream_t s);
+                           int sign, cudaStream_t s, int32_t *dst = nullptr);
+int launch_counts_to_doubles(dist_b200_ctx *ctx, const int32_t *src, double *dst, size_t n, cudaStream_t s);
+int launch_merge_counts(dist_b200_ctx *ctx, int32_t *counts, const double *delta, size_t n, int sign, cudaStream_t s);
 size_t add_rows_acc_bytes(int G);
 int launch_count_assignments(dist_b200_ctx *ctx, const int32_t *assign, size_t N, int G, int32_t *counts, int accumulate,
                              cudaStream_t s);

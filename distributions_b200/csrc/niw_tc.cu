@@ -111,6 +111,32 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 eviction policies: the per-CTA score scratch and the block records are re-used (evict last), the row images stream
+// through once (evict first) -- without them the streaming rows push dirty scratch lines out to HBM
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void st_f2_hint(float2 *p, float2 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;\n" ::"l"(p), "f"(v.x), "f"(v.y), "l"(policy) : "memory");
+}
+__device__ __forceinline__ float2 ld_f2_hint(const float2 *p, uint64_t policy) {
+    float2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;\n" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(policy) : "memory");
+    return v;
+}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
@@ -337,20 +363,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
         // ===================== loader =====================
         if (lane == 0) {
             uint32_t bstage = 0, bphase = 0, aphase = 0;
+            const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
             for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
                 const size_t t0 = chunk * kChunkTiles;
                 const int nt = static_cast<int>(a.ntiles - t0 < kChunkTiles ? a.ntiles - t0 : kChunkTiles);
                 auto load_a = [&](int t) {
                     mbar_wait(&a_empty[t], aphase ^ 1);  // the previous chunk's MMAs on this tile have retired
                     mbar_expect_tx(&a_full[t], kATileBytes);
-                    bulk_g2s(As + t * kATileBytes, a.xpack + (t0 + t) * (kATileBytes / 2), kATileBytes, &a_full[t]);
+                    bulk_g2s_hint(As + t * kATileBytes, a.xpack + (t0 + t) * (kATileBytes / 2), kATileBytes, &a_full[t], pol_stream);
                 };
                 // in consumption order: tile 0, block 0, the remaining tiles, the remaining blocks
                 load_a(0);
                 for (int blk = 0; blk < nb; ++blk) {
                     mbar_wait(&b_empty[bstage], bphase ^ 1);
                     mbar_expect_tx(&b_full[bstage], kBlockRecBytes);
-                    bulk_g2s(Bs + bstage * kBlockRecBytes, a.blockrecs + static_cast<size_t>(blk) * kBlockRecBytes, kBlockRecBytes, &b_full[bstage]);
+                    bulk_g2s_hint(Bs + bstage * kBlockRecBytes, a.blockrecs + static_cast<size_t>(blk) * kBlockRecBytes, kBlockRecBytes, &b_full[bstage], pol_keep);
                     if (++bstage == kBStages) {
                         bstage = 0;
                         bphase ^= 1;
@@ -413,6 +440,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
         uint32_t bstage = 0, bphase = 0, fphase[2] = {0, 0};
         int tb = 0;
         float *scratch = kFused ? a.scratch + static_cast<size_t>(blockIdx.x) * kChunkTiles * kTcRows * a.Gpad : nullptr;
+        const uint64_t pol_keep = l2_policy_evict_last();
         for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
             const size_t t0 = chunk * kChunkTiles;
             const int nt = static_cast<int>(a.ntiles - t0 < kChunkTiles ? a.ntiles - t0 : kChunkTiles);
@@ -482,8 +510,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                     const size_t row = (t0 + t) * kTcRows + r_in_tile;
                     if (kFused) {
                         // the chunk's scores stay on chip (L2), quad-major so that a warp stores / walks whole lines; online (max, sum exp) of this row x half
-                        reinterpret_cast<float2 *>(scratch)[static_cast<size_t>(blk * kParts + h) * (kChunkTiles * kTcRows) + t * kTcRows + r_in_tile] =
-                            make_float2(out[0], out[1]);
+                        st_f2_hint(reinterpret_cast<float2 *>(scratch) + static_cast<size_t>(blk * kParts + h) * (kChunkTiles * kTcRows) + t * kTcRows + r_in_tile,
+                                   make_float2(out[0], out[1]), pol_keep);
                         const float m4 = fmaxf(out[0], out[1]) * kLog2e;
                         const float mn = fmaxf(fmaxf(om[t], m4), -3.0e38f);  // finite even when both groups are padding
                         float s4 = 0.f;
@@ -542,7 +570,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                     for (int j2 = 0; j2 < npairs; j2 += 16) {  // 32 cells per step, sixteen loads in flight
                         float2 v[16];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) v[k] = j2 + k < npairs ? src[static_cast<size_t>(j2 + k) * (kChunkTiles * kTcRows)] : ninf;
+                        for (int k = 0; k < 16; ++k) v[k] = j2 + k < npairs ? ld_f2_hint(src + static_cast<size_t>(j2 + k) * (kChunkTiles * kTcRows), pol_keep) : ninf;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
                             tt -= mufu_ex2(fmaf(v[k].x, kLog2e, -mm));

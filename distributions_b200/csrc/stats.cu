@@ -288,8 +288,9 @@ int launch_add_rows_pooled(dist_b200_ctx *ctx, const AddBatch &b_in, cudaStream_
     return DIST_B200_OK;
 }
 
+// dst: the count table to update (nullptr = the feature's own statistics)
 int launch_add_rows_counts(dist_b200_ctx *ctx, dist_b200_feature *f, const void *column, const int32_t *assign, size_t N,
-                           int sign, cudaStream_t s) {
+                           int sign, cudaStream_t s, int32_t *dst) {
     if (N == 0 || f->G == 0) return DIST_B200_OK;
     CountArgs a{};
     a.model = f->model;
@@ -300,7 +301,7 @@ int launch_add_rows_counts(dist_b200_ctx *ctx, dist_b200_feature *f, const void 
     a.N = N;
     a.column = column;
     a.assign = assign;
-    a.counts = reinterpret_cast<int32_t *>(f->stats);  // dd: counts[G][dim]; dpd: counts[G][V]
+    a.counts = dst ? dst : reinterpret_cast<int32_t *>(f->stats);  // dd: counts[G][dim]; dpd: counts[G][V]
     a.keys = f->keys_dev;
     a.key_rows = f->key_rows_dev;
     const size_t cells = static_cast<size_t>(f->G) * f->dim;
@@ -316,6 +317,37 @@ int launch_add_rows_counts(dist_b200_ctx *ctx, dist_b200_feature *f, const void 
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("add_rows launch: ") + cudaGetErrorString(e));
+    return DIST_B200_OK;
+}
+
+// Row-shard exchange of a count table (dd / dpd): the rank's delta counts travel as doubles (integers are exact in
+// them), so that one float64 all-reduce carries the pooled accumulators and the tables alike.
+__global__ void counts_to_doubles_kernel(const int32_t *__restrict__ src, double *__restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = static_cast<double>(src[i]);
+}
+__global__ void merge_counts_kernel(int32_t *__restrict__ counts, const double *__restrict__ delta, size_t n, int sign) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const long long d = llrint(delta[i]);
+        if (d) counts[i] += static_cast<int32_t>(sign > 0 ? d : -d);
+    }
+}
+
+int launch_counts_to_doubles(dist_b200_ctx *ctx, const int32_t *src, double *dst, size_t n, cudaStream_t s) {
+    if (n == 0) return DIST_B200_OK;
+    const size_t want = (n + 255) / 256, cap = static_cast<size_t>(ctx->sm_count) * 8;
+    counts_to_doubles_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, s>>>(src, dst, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("counts_to_doubles launch: ") + cudaGetErrorString(e));
+    return DIST_B200_OK;
+}
+
+int launch_merge_counts(dist_b200_ctx *ctx, int32_t *counts, const double *delta, size_t n, int sign, cudaStream_t s) {
+    if (n == 0) return DIST_B200_OK;
+    const size_t want = (n + 255) / 256, cap = static_cast<size_t>(ctx->sm_count) * 8;
+    merge_counts_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, s>>>(counts, delta, n, sign);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("merge_counts launch: ") + cudaGetErrorString(e));
     return DIST_B200_OK;
 }
 

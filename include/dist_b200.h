@@ -169,11 +169,14 @@ int dist_b200_remove_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *fe
 int dist_b200_remove_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
                                      const void *const *columns_host, const int32_t *assign_host, size_t n_rows);
 /* Row shards (one process per GPU, rows partitioned, statistics replicated): the update has a real exchange
- * step.  Every rank accumulates its own rows into xchg_dev -- [n_features][4][G] doubles per feature:
- * count-like a, count-like b, sum x, sum x^2 (integers exact) --, the caller sums the buffers over the ranks
- * (one NCCL all-reduce of float64), and every rank merges the global sums into its replica (sign +1 add_value,
- * -1 remove_value), leaving all replicas bit-identical.  Pooled-statistics models only (nich / gp / bb / bnb),
- * all features with the same G. */
+ * step.  Every rank accumulates its own rows into xchg_dev, the caller sums the buffers over the ranks (one NCCL
+ * all-reduce of float64), and every rank merges the global sums into its replica (sign +1 add_value, -1
+ * remove_value), leaving all replicas bit-identical.  Layout of xchg_dev (doubles; dist_b200_rows_xchg_doubles
+ * returns the total): first one [4][G] block per pooled-statistics feature (nich / gp / bb / bnb: count-like a,
+ * count-like b, sum x, sum x^2; integers exact) in list order, then one [G][dim] block of delta counts per
+ * count-table feature (dd: dd.hpp:123-149; dpd: dpd.hpp:188-214, dim = number of known values) in list order.
+ * All features with the same G.  niw: unsupported. */
+int dist_b200_rows_xchg_doubles(dist_b200_feature *const *features, int n_features, size_t *n_doubles);
 int dist_b200_rows_accumulate(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
                               const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, double *xchg_dev,
                               void *stream);

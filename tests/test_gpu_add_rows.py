@@ -262,3 +262,53 @@ def test_remove_rows_empties_group(ctx, oracle):
     raw = f.download_stats(12 * G)
     assert not raw.any()
     np.testing.assert_array_equal(f.download_caches(4), cases.oracle_caches(oracle, w))
+
+
+def test_row_shard_exchange_with_count_tables(ctx, oracle):
+    """the row-shard exchange on one device: two 'ranks' accumulate their halves of the rows into two exchange buffers,
+    the buffers are summed (the all-reduce) and merged -- pooled models and the dd / dpd count tables in one buffer;
+    the result must equal add_rows_batch over all rows, bit for bit, and a -1 merge must restore the original"""
+    from distributions_b200 import capi
+    G, n = 17, 4001
+    names = ["gp", "dd", "nich", "dpd", "bb"]
+    ids = {"bb": capi.BB, "gp": capi.GP, "nich": capi.NICH, "dd": capi.DD, "dpd": capi.DPD}
+    kw = {"dd": dict(dim=8), "dpd": dict(V=53)}
+    ws = [getattr(synth, m)(1300 + i, G, n, **kw.get(m, {})) for i, m in enumerate(names)]
+    assign = np.random.default_rng(77).integers(0, G, n).astype(np.int32)
+    cols_h = [w["values"].astype(capi.COLUMN_DTYPE[ids[m]]) for m, w in zip(names, ws)]
+    stat_bytes = {"gp": 8 * G, "dd": 4 * G * 8, "nich": 12 * G, "dpd": 4 * G * 53, "bb": 8 * G}
+
+    single = [ctx.feature(ids[m]).update_all(w) for m, w in zip(names, ws)]
+    before = [f.download_stats(stat_bytes[m]) for m, f in zip(names, single)]
+    ctx.add_rows_batch(single, [dev(c) for c in cols_h], dev(assign), n)
+
+    shard = [ctx.feature(ids[m]).update_all(w) for m, w in zip(names, ws)]
+    nd = ctx.rows_xchg_doubles(shard)
+    assert nd == 3 * 4 * G + G * 8 + G * 53
+    total = torch.zeros(nd, dtype=torch.float64, device="cuda")
+    for lo, hi in ((0, n // 3), (n // 3, n)):
+        x = torch.full((nd,), 123.0, dtype=torch.float64, device="cuda")  # stale contents must not leak
+        ctx.rows_accumulate(shard, [dev(c[lo:hi]) for c in cols_h], dev(assign[lo:hi]), hi - lo, x)
+        total += x
+    # an empty shard contributes zeros
+    x = torch.full((nd,), 5.0, dtype=torch.float64, device="cuda")
+    ctx.rows_accumulate(shard, [dev(c[:1]) for c in cols_h], dev(assign[:1]), 0, x)
+    assert float(x.abs().sum()) == 0.0
+    ctx.rows_merge(shard, total, +1)
+    for m, a, b in zip(names, single, shard):
+        sa, sb = a.download_stats(stat_bytes[m]), b.download_stats(stat_bytes[m])
+        if m == "nich":  # the pooled merge is the same arithmetic on the same sums up to the order of the double additions
+            np.testing.assert_allclose(sa.view(np.float32)[G:], sb.view(np.float32)[G:], rtol=1e-6, atol=1e-6)
+            assert np.array_equal(sa.view(np.int32)[:G], sb.view(np.int32)[:G])
+        else:
+            assert np.array_equal(sa, sb), m
+        rows = {"nich": 4, "gp": 3, "bb": 2, "dd": 8, "dpd": 53 + 1}[m]
+        ca, cb = a.download_caches(rows), b.download_caches(rows)
+        if m == "nich":
+            np.testing.assert_allclose(ca, cb, rtol=1e-5, atol=1e-5)
+        else:
+            assert np.array_equal(ca, cb), m
+    ctx.rows_merge(shard, total, -1)
+    for m, f, b0 in zip(names, shard, before):
+        if m != "nich":
+            assert np.array_equal(f.download_stats(stat_bytes[m]), b0), m
