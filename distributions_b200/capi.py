@@ -158,7 +158,7 @@ def wire_encode_shared(model, shared, keys=None):
     L = lib()
     shared = np.ascontiguousarray(shared, dtype=np.float32)
     keys = np.ascontiguousarray(keys if keys is not None else [], dtype=np.uint32)
-    buf = np.empty(16 + 5 * shared.size, np.uint8)
+    buf = np.empty(16 + 5 * shared.size + 11 * keys.size, np.uint8)
     n = c_sz()
     rc = L.dist_b200_wire_encode_shared(None, model, _np_ptr(shared), shared.size, _np_ptr(keys) if keys.size else None, keys.size,
                                         _np_ptr(buf), buf.size, ctypes.byref(n))

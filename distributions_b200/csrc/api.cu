@@ -1133,6 +1133,12 @@ int dist_b200_update_all_wire(dist_b200_feature *f, const void *shared_msg, size
         case DIST_B200_DPD:
             return dist_b200_dpd_update_all(f, w.shared[1], w.shared[2], w.dim, w.keys.data(), w.shared.data() + 3, G,
                                             reinterpret_cast<const int32_t *>(st), stream);
+        case DIST_B200_NIW: {
+            const size_t d = static_cast<size_t>(w.dim);
+            return dist_b200_niw_update_all(f, w.dim, w.shared.data() + 2, w.shared[0], w.shared.data() + 2 + d, w.shared[1], G,
+                                            reinterpret_cast<const int32_t *>(st), reinterpret_cast<const float *>(st + g),
+                                            reinterpret_cast<const float *>(st + g + g * d), stream);
+        }
         default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "update_all_wire: unsupported model");
     }
 }

@@ -7,6 +7,7 @@
 // accepted.  Unknown fields are skipped, as protobuf readers do.  Counts are uint64 on the wire and 32-bit
 // in the reference's Groups (e.g. nich.hpp:98-101, gp.hpp:84-87): a value that does not fit is an error.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "common.cuh"
@@ -105,6 +106,34 @@ bool parse(const void *msg, size_t len, const char kinds[6], Fields &out) {
 bool fits32(uint64_t v) { return v <= 0xFFFFFFFFull; }
 
 }  // namespace
+
+// Eigen's isApprox(m, m^T) (niw.hpp:45-50): |m - m^T|_F <= 1e-5 min(|m|_F, |m^T|_F)
+static bool symmetric(const float *m, size_t d) {
+    double diff = 0, norm = 0;
+    for (size_t i = 0; i < d; ++i)
+        for (size_t j = 0; j < d; ++j) {
+            const double a = m[i * d + j], b = m[j * d + i];
+            diff += (a - b) * (a - b);
+            norm += a * a;
+        }
+    return diff <= 1e-10 * norm;
+}
+// LDLT with a positive diagonal (niw.hpp:52-61), as a Cholesky factorisation in double
+static bool positive_definite(const float *m, size_t d) {
+    std::vector<double> L(d * d, 0.0);
+    for (size_t j = 0; j < d; ++j) {
+        double s = m[j * d + j];
+        for (size_t k = 0; k < j; ++k) s -= L[j * d + k] * L[j * d + k];
+        if (!(s > 0.0)) return false;
+        L[j * d + j] = std::sqrt(s);
+        for (size_t i = j + 1; i < d; ++i) {
+            double t = m[i * d + j];
+            for (size_t k = 0; k < j; ++k) t -= L[i * d + k] * L[j * d + k];
+            L[i * d + j] = t / L[j * d + j];
+        }
+    }
+    return true;
+}
 
 static uint32_t fbits(float f) {
     uint32_t u;
@@ -237,7 +266,37 @@ int wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg, size_t sh
                 }
             }
         } break;
-        default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: model has no wire loader (niw statistics stay on the host)");
+        case DIST_B200_NIW: {  // schema.proto:147-161; Shared::protobuf_load niw.hpp:105-134, Group::protobuf_load :192-216
+            if (!parse(shared_msg, shared_len, "\0ffff", sh)) return bad("malformed NormalInverseWishart.Shared");
+            const size_t d = sh.f[1].size();
+            if (d < 1 || d > 32) return bad("NormalInverseWishart.Shared: dim must be 1..32");
+            if (sh.f[2].empty() || sh.f[4].empty()) return bad("NormalInverseWishart.Shared: missing required field");
+            if (sh.f[3].size() != d * d) return bad("NormalInverseWishart.Shared: psi is not dim x dim (niw.hpp:92-94)");
+            const float kappa = sh.f[2].back(), nu = sh.f[4].back();
+            if (!(kappa > 0.f)) return bad("NormalInverseWishart.Shared: kappa must be positive (niw.hpp:115)");
+            if (!(nu > static_cast<float>(d) - 1.f)) return bad("NormalInverseWishart.Shared: nu must exceed dim - 1 (niw.hpp:132)");
+            if (!symmetric(sh.f[3].data(), d) || !positive_definite(sh.f[3].data(), d))
+                return bad("NormalInverseWishart.Shared: psi is not symmetric positive definite (niw.hpp:127)");
+            // packed Shared: kappa, nu, mu[d], psi[d][d]
+            out.shared = {kappa, nu};
+            out.shared.insert(out.shared.end(), sh.f[1].begin(), sh.f[1].end());
+            out.shared.insert(out.shared.end(), sh.f[3].begin(), sh.f[3].end());
+            out.dim = static_cast<int>(d);
+            // statistics: count[G] | sum_x[G][d] | sum_xxT[G][d][d]
+            out.stats.assign(g * (1 + d + d * d), 0);
+            for (size_t i = 0; i < g; ++i) {
+                Fields m;
+                if (!parse(group_msgs[i], group_lens[i], "\0vff\0", m)) return bad("malformed NormalInverseWishart.Group");
+                if (m.v[1].empty()) return bad("NormalInverseWishart.Group: missing required field");
+                if (m.v[1].back() > 0x7FFFFFFFull) return bad("NormalInverseWishart.Group: count is negative or exceeds 31 bits");
+                if (m.f[2].size() != d || m.f[3].size() != d * d) return bad("NormalInverseWishart.Group: sum_x / sum_xxT sizes differ from Shared's dim");
+                if (!symmetric(m.f[3].data(), d)) return bad("NormalInverseWishart.Group: sum_xxT is not symmetric (niw.hpp:214)");
+                out.stats[i] = static_cast<uint32_t>(m.v[1].back());
+                for (size_t k = 0; k < d; ++k) out.stats[g + i * d + k] = fbits(m.f[2][k]);
+                for (size_t k = 0; k < d * d; ++k) out.stats[g + g * d + i * d * d + k] = fbits(m.f[3][k]);
+            }
+        } break;
+        default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: model has no wire loader");
     }
     return DIST_B200_OK;
 }
@@ -303,6 +362,7 @@ int wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint
         case DIST_B200_NICH: case DIST_B200_GP: need = 3 * g; break;
         case DIST_B200_BNB: case DIST_B200_BB: need = 2 * g; break;
         case DIST_B200_DD: case DIST_B200_DPD: need = g * static_cast<size_t>(dim); break;
+        case DIST_B200_NIW: need = g * (1 + static_cast<size_t>(dim) + static_cast<size_t>(dim) * dim); break;
         default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: model has no Group writer");
     }
     if (G < 0 || stats_words < need || (G && !stats) || (model == DIST_B200_DPD && G && !keys))
@@ -330,6 +390,12 @@ int wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint
             case DIST_B200_DD:
                 for (int v = 0; v < dim; ++v) put_u(out, 1, stats[i * dim + v]);
                 break;
+            case DIST_B200_NIW: {  // count (int32: negative values sign-extend to 64 bits), sum_x, sum_xxT row-major
+                const size_t d = static_cast<size_t>(dim);
+                put_u(out, 1, static_cast<uint64_t>(static_cast<int64_t>(static_cast<int32_t>(stats[i]))));
+                for (size_t k = 0; k < d; ++k) put_f(out, 2, stats[g + i * d + k]);
+                for (size_t k = 0; k < d * d; ++k) put_f(out, 3, stats[g + g * d + i * d * d + k]);
+            } break;
             default:  // dpd: sparse (keys, values), non-zero counts in Shared order
                 for (int v = 0; v < dim; ++v)
                     if (stats[i * dim + v]) put_u(out, 1, keys[v]);
@@ -342,8 +408,9 @@ int wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint
     return DIST_B200_OK;
 }
 
-// Shared message of a model from the packed floats wire_decode returns (dpd: not written -- its Shared also
-// carries per-value totals the feature does not track)
+// Shared message of a model from the packed floats wire_decode returns.  dpd: keys = values[V] followed by the
+// per-value totals Shared::counts[V] (dpd.hpp:64, :126-138 -- the sum of the groups' counts of the value when every
+// add_value went through both, as the mixture drivers do); niw: kappa, nu, mu[d], psi[d][d].
 int wire_encode_shared(dist_b200_ctx *ctx, int model, const float *shared, size_t n_shared, const uint32_t *keys,
                        size_t n_keys, std::vector<uint8_t> &out) {
     auto need = [&](size_t n) { return n_shared == n && shared; };
@@ -374,6 +441,27 @@ int wire_encode_shared(dist_b200_ctx *ctx, int model, const float *shared, size_
             if (!shared || n_shared < 1 || n_shared > 256) break;
             for (size_t v = 0; v < n_shared; ++v) put_float(1, shared[v]);
             return DIST_B200_OK;
+        case DIST_B200_DPD: {  // gamma, alpha, values, betas, counts (dpd.hpp:126-138)
+            if (!shared || n_shared < 4 || !keys) break;
+            const size_t V = n_shared - 3;
+            if (n_keys != 2 * V) break;
+            put_float(1, shared[0]);
+            put_float(2, shared[1]);
+            for (size_t v = 0; v < V; ++v) put_u(out, 3, keys[v]);
+            for (size_t v = 0; v < V; ++v) put_float(4, shared[3 + v]);
+            for (size_t v = 0; v < V; ++v) put_u(out, 5, keys[V + v]);
+            return DIST_B200_OK;
+        }
+        case DIST_B200_NIW: {  // mu, kappa, psi, nu (niw.hpp:136-156)
+            size_t d = 1;
+            while (d <= 32 && 2 + d + d * d != n_shared) ++d;
+            if (!shared || d > 32) break;
+            for (size_t k = 0; k < d; ++k) put_float(1, shared[2 + k]);
+            put_float(2, shared[0]);
+            for (size_t k = 0; k < d * d; ++k) put_float(3, shared[2 + d + k]);
+            put_float(4, shared[1]);
+            return DIST_B200_OK;
+        }
         default:
             return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "wire: model has no Shared writer");
     }

@@ -208,7 +208,8 @@ int dist_b200_score_data_grid_host(dist_b200_feature *f, const float *shareds_ho
  * max(0, 1 - sum betas) as Shared::protobuf_load, dpd.hpp:104-125; gp: log_prod is kept for score_data_grid).
  * Packed and unpacked repeated scalars are accepted, unknown fields skipped; a malformed message is
  * DIST_B200_ERR_INVALID, a uint64 count that does not fit the reference's 32-bit Group fields
- * DIST_B200_ERR_UNSUPPORTED.  niw: unsupported. */
+ * DIST_B200_ERR_UNSUPPORTED.  niw (schema.proto:147-161): Shared.psi must be symmetric positive definite and every
+ * Group.sum_xxT symmetric, as Shared / Group::protobuf_load assert (niw.hpp:105-134, :192-216). */
 int dist_b200_update_all_wire(dist_b200_feature *f, const void *shared_msg, size_t shared_len,
                               const void *const *group_msgs, const size_t *group_lens, int G, void *stream);
 /* The same with the Groups as one record stream of the reference's dumps (distributions/io/stream.py:141-153,
@@ -220,8 +221,9 @@ int dist_b200_update_all_stream(dist_b200_feature *f, const void *shared_msg, si
 int dist_b200_wire_split_stream(dist_b200_ctx *ctx, const void *stream_bytes, size_t stream_len, size_t *offsets_out,
                                 size_t *lens_out, size_t capacity, size_t *n_records);
 /* The decode step alone (no device): shared_out = Shared floats (nich 4; gp 2; bb 2; bnb alpha, beta, r;
- * dd alphas; dpd gamma, alpha, beta0, betas[V]), keys_out = dpd Shared.values (bnb: r), stats_out = the
- * update_all arrays back to back, floats as bit patterns (gp: count | sum | log_prod).  counts_out receives the
+ * dd alphas; dpd gamma, alpha, beta0, betas[V]; niw kappa, nu, mu[d], psi[d][d]), keys_out = dpd Shared.values
+ * (bnb: r), stats_out = the update_all arrays back to back, floats as bit patterns (gp: count | sum | log_prod;
+ * niw: count[G] | sum_x[G][d] | sum_xxT[G][d][d]).  counts_out receives the
  * three lengths (also when a buffer is too small).  ctx may be NULL (no error text is recorded then). */
 int dist_b200_wire_decode(dist_b200_ctx *ctx, int model, const void *shared_msg, size_t shared_len,
                           const void *const *group_msgs, const size_t *group_lens, int G, float *shared_out,
@@ -237,8 +239,9 @@ int dist_b200_feature_dump_groups_wire(dist_b200_feature *f, void *out, size_t c
 /* the encode step alone (no device; ctx may be NULL): stats = the arrays dist_b200_wire_decode returns */
 int dist_b200_wire_encode_groups(dist_b200_ctx *ctx, int model, int G, int dim, const uint32_t *keys, const uint32_t *stats,
                                  size_t stats_words, void *out, size_t capacity, size_t *lens_out, size_t *n_bytes);
-/* Shared message from the packed values dist_b200_wire_decode returns (nich, gp, bb, bnb with keys[0] = r,
- * dd; dpd's Shared also carries per-value totals the library does not track: ERR_UNSUPPORTED) */
+/* Shared message from the packed values dist_b200_wire_decode returns (nich, gp, bb, bnb with keys[0] = r, dd, niw;
+ * dpd: keys = Shared.values[V] followed by the per-value totals Shared.counts[V] (dpd.hpp:64, :126-138), i.e. the
+ * column sums of the groups' counts when every add_value went through Shared and a Group, as the drivers do) */
 int dist_b200_wire_encode_shared(dist_b200_ctx *ctx, int model, const float *shared, size_t n_shared, const uint32_t *keys,
                                  size_t n_keys, void *out, size_t capacity, size_t *n_bytes);
 /* Clustering message (pitman_yor = 1 | low_entropy = 2, schema.proto:36-53) -> the prior vector */

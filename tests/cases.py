@@ -113,6 +113,7 @@ WIRE = {
     "bb": (9404, 10, {}),
     "dd": (9405, 8, dict(dim=16)),
     "dpd": (9406, 6, dict(V=40, other_frac=0.05)),
+    "niw": (9407, 5, dict(d=4)),
 }
 
 # score_data golden cases: model -> (seed, G, synth kwargs, grid points); tests/golden/make_golden_score_data.py

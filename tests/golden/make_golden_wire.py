@@ -67,6 +67,11 @@ def encode(cls, w):
             nz = np.nonzero(w["counts"][g])[0][::-1]  # sparse, and not in Shared's order
             gs.append(cls("DirichletProcessDiscrete.Group")(keys=[int(w["keys"][v]) for v in nz], values=[int(w["counts"][g][v]) for v in nz]))
         assert V == w["betas"].size
+    elif m == "niw":
+        sh = cls("NormalInverseWishart.Shared")(mu=[float(x) for x in w["mu"]], kappa=float(w["kappa"]),
+                                               psi=[float(x) for x in w["psi"].ravel()], nu=float(w["nu"]))
+        gs = [cls("NormalInverseWishart.Group")(count=int(w["count"][g]), sum_x=[float(x) for x in w["sum_x"][g]],
+                                               sum_xxT=[float(x) for x in w["sum_xxT"][g].ravel()]) for g in range(G)]
     else:
         raise ValueError(m)
     return sh.SerializeToString(), [g.SerializeToString() for g in gs]

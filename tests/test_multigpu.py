@@ -88,13 +88,28 @@ def test_feature_shards_multi_gpu(tmp_path, oracle, world, row_shards):
         for lo, hi in d["rows"]:
             got_rs[lo:hi] = d["a_rs"][off:off + hi - lo]
             off += hi - lo
-    for got in (got_push, got_rs):
-        assert got.min() >= 0
-        assert cases.explained_mismatch(full.astype(np.float64), cc["u"], got, want, 2e-5).all()
-        assert np.mean(got == want) > 0.995
+    # fp32 sums of F feature terms in another association than the oracle's (per-rank partials, then the slots / NCCL's
+    # reduction order): each addition may differ by half an ulp of |score| <= 64, i.e. 4e-6 relative to the row's total
+    eps = 4e-6 * F
+    for label, got in (("push", got_push), ("reduce-scatter", got_rs)):
+        assert got.min() >= 0, label
+        ok = cases.explained_mismatch(full.astype(np.float64), cc["u"], got, want, eps)
+        assert ok.all(), "%s: %d of %d mismatching rows are not near-ties at eps %.1e (rows %s)" % (
+            label, int((~ok).sum()), int((got != want).sum()), eps, np.nonzero(~ok)[0][:8])
+        assert np.mean(got == want) > 0.995, label
 
 
 # ---- row shards: the update row (batched add_value) with its all-reduce -----------------------------
+def _update_case(capi, synth, G, n):
+    """pooled models and the dd / dpd count tables in one exchange buffer"""
+    ws = [synth.nich(701, G, n), synth.gp(702, G, n), synth.dd(705, G, n, dim=8), synth.bb(703, G, n), synth.bnb(704, G, n, r=2),
+          synth.dpd(706, G, n, V=61)]
+    ids = [capi.NICH, capi.GP, capi.DD, capi.BB, capi.BNB, capi.DPD]
+    stat_bytes = (12 * G, 8 * G, 4 * G * 8, 8 * G, 8 * G, 4 * G * 61)
+    cache_rows = (4, 3, 8, 2, 3, 62)
+    return ws, ids, stat_bytes, cache_rows
+
+
 def _update_worker(rank, world, port, n, G, out_dir):
     import torch.distributed as dist
     from distributions_b200 import capi, sharding, synth
@@ -103,20 +118,19 @@ def _update_worker(rank, world, port, n, G, out_dir):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    ws = [synth.nich(701, G, n), synth.gp(702, G, n), synth.bb(703, G, n), synth.bnb(704, G, n, r=2)]
-    ids = [capi.NICH, capi.GP, capi.BB, capi.BNB]
+    ws, ids, stat_bytes, cache_rows = _update_case(capi, synth, G, n)
     assign = np.random.default_rng(12).integers(0, G, n).astype(np.int32)
     lo, hi = sharding.row_shard(n, rank, world)
     ctx = capi.Context(rank)
     feats = [ctx.feature(i).update_all(w) for i, w in zip(ids, ws)]
     cols = [torch.from_numpy(np.ascontiguousarray(w["values"][lo:hi], dtype=capi.COLUMN_DTYPE[i])).to(dev) for i, w in zip(ids, ws)]
     a_dev = torch.from_numpy(assign[lo:hi].copy()).to(dev)
-    xchg = torch.zeros((len(feats), 4, G), dtype=torch.float64, device=dev)
+    xchg = torch.zeros(ctx.rows_xchg_doubles(feats), dtype=torch.float64, device=dev)
     sharding.row_sharded_update(lambda x: ctx.rows_accumulate(feats, cols, a_dev, hi - lo, x),
                                 lambda x, sign: ctx.rows_merge(feats, x, sign), xchg, +1)
     torch.cuda.synchronize()
     out = {}
-    for k, (f, nb, rows) in enumerate(zip(feats, (12 * G, 8 * G, 8 * G, 8 * G), (4, 3, 2, 3))):
+    for k, (f, nb, rows) in enumerate(zip(feats, stat_bytes, cache_rows)):
         out["stats%d" % k] = f.download_stats(nb)
         out["caches%d" % k] = f.download_caches(rows)
     np.savez(os.path.join(out_dir, "upd%d.npz" % rank), **out)
@@ -134,15 +148,14 @@ def test_row_sharded_update_two_gpus(tmp_path):
     world, n, G = 2, 6001, 33
     port = 29700 + os.getpid() % 1000
     mp.spawn(_update_worker, args=(world, port, n, G, str(tmp_path)), nprocs=world, join=True)
-    ws = [synth.nich(701, G, n), synth.gp(702, G, n), synth.bb(703, G, n), synth.bnb(704, G, n, r=2)]
-    ids = [capi.NICH, capi.GP, capi.BB, capi.BNB]
+    ws, ids, stat_bytes, cache_rows = _update_case(capi, synth, G, n)
     assign = np.random.default_rng(12).integers(0, G, n).astype(np.int32)
     ctx = capi.Context(0)
     feats = [ctx.feature(i).update_all(w) for i, w in zip(ids, ws)]
     cols = [torch.from_numpy(np.ascontiguousarray(w["values"], dtype=capi.COLUMN_DTYPE[i])).cuda() for i, w in zip(ids, ws)]
     ctx.add_rows_batch(feats, cols, torch.from_numpy(assign).cuda(), n)
     d = [np.load(os.path.join(str(tmp_path), "upd%d.npz" % r)) for r in range(world)]
-    for k, (f, nb, rows) in enumerate(zip(feats, (12 * G, 8 * G, 8 * G, 8 * G), (4, 3, 2, 3))):
+    for k, (f, nb, rows) in enumerate(zip(feats, stat_bytes, cache_rows)):
         single = f.download_stats(nb)
         assert np.array_equal(d[0]["stats%d" % k], d[1]["stats%d" % k])          # replicas bit-identical
         assert np.array_equal(d[0]["caches%d" % k], d[1]["caches%d" % k])

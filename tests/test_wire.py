@@ -11,7 +11,7 @@ import cases
 from distributions_b200 import capi, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-IDS = {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH, "bnb": capi.BNB}
+IDS = {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH, "bnb": capi.BNB, "niw": capi.NIW}
 
 
 @pytest.fixture(scope="module")
@@ -41,6 +41,9 @@ def expected(name):
         return w, np.asarray(w["shared"], np.float32), np.zeros(0, np.uint32), np.concatenate([u32(w["heads"]), u32(w["tails"])])
     if name == "dd":
         return w, np.asarray(w["alphas"], np.float32), np.zeros(0, np.uint32), u32(w["counts"])
+    if name == "niw":
+        sh = np.concatenate([[w["kappa"], w["nu"]], w["mu"], w["psi"].ravel()]).astype(np.float32)
+        return w, sh, np.zeros(0, np.uint32), np.concatenate([u32(w["count"]), f32(w["sum_x"]), f32(w["sum_xxT"])])
     beta0 = np.float32(max(0.0, 1.0 - float(np.sum(w["betas"].astype(np.float64)))))
     sh = np.concatenate([[np.float32(w["gamma"]), np.float32(w["alpha"]), beta0], w["betas"]]).astype(np.float32)
     return w, sh, w["keys"].astype(np.uint32), u32(w["counts"])
@@ -62,13 +65,16 @@ def test_encode_is_the_reference_writers_bytes(wire, name):
     sparse groups were written in another key order; equal after decoding again)"""
     sh_msg, g_msgs = messages(wire, name)
     _, keys, stats = capi.wire_decode(IDS[name], sh_msg, g_msgs)
-    dim = {"dd": 16, "dpd": 40}.get(name, 0)
+    dim = {"dd": 16, "dpd": 40, "niw": 4}.get(name, 0)
     out = capi.wire_encode_groups(IDS[name], len(g_msgs), dim, keys, stats)
     if name == "dpd":
-        _, _, again = capi.wire_decode(IDS[name], sh_msg, out)
+        sh, _, again = capi.wire_decode(IDS[name], sh_msg, out)
         assert np.array_equal(again, stats)
-        with pytest.raises(ValueError):  # its Shared carries per-value totals the library does not track
-            capi.wire_encode_shared(IDS[name], [1.0, 0.5, 0.1], None)
+        # Shared: values, betas and the per-value totals (the column sums of the groups' counts, dpd.hpp:126-138)
+        totals = stats.reshape(len(g_msgs), dim).sum(axis=0).astype(np.uint32)
+        assert capi.wire_encode_shared(IDS[name], sh, np.concatenate([keys, totals])) == sh_msg
+        with pytest.raises(ValueError):  # the totals are part of the message
+            capi.wire_encode_shared(IDS[name], sh, keys)
     else:
         assert out == g_msgs
         sh, keys, _ = capi.wire_decode(IDS[name], sh_msg, g_msgs)
