@@ -33,6 +33,7 @@ SOURCES = {
     "peer.cu": [],
     "niw.cu": [],
     "niw_tc.cu": [],
+    "niw_stats.cu": [],
     "microbench.cu": [],
     "stats.cu": [],
     "wire.cu": [],

@@ -58,7 +58,6 @@ int ensure_pinned(dist_b200_ctx *ctx, size_t bytes) {
     return DIST_B200_OK;
 }
 
-size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
 // per-group floats of the hot layout
 size_t group_floats(const dist_b200_feature *f) {
@@ -350,6 +349,8 @@ void dist_b200_feature_destroy(dist_b200_feature *f) {
     if (f->cdf_buf) cudaFree(f->cdf_buf);
     if (f->niw_buf) cudaFree(f->niw_buf);
     if (f->niw_tc) cudaFree(f->niw_tc);
+    if (f->niw_stats) cudaFree(f->niw_stats);
+    if (f->niw_shared_dev) cudaFree(f->niw_shared_dev);
     if (f->stats) cudaFree(f->stats);
     if (f->alphas_dev) cudaFree(f->alphas_dev);
     if (f->log_prod_dev) cudaFree(f->log_prod_dev);
@@ -517,6 +518,22 @@ int dist_b200_dpd_update_all(dist_b200_feature *f, float alpha, float beta0, int
 }
 
 static int niw_reserve(dist_b200_feature *f, int G, int keep);
+static int32_t *niw_count(const dist_b200_feature *f) { return reinterpret_cast<int32_t *>(f->niw_stats); }
+static float *niw_sum_x(const dist_b200_feature *f) { return reinterpret_cast<float *>(f->niw_stats) + f->niw_cap; }
+static float *niw_sum_xxT(const dist_b200_feature *f) {
+    return reinterpret_cast<float *>(f->niw_stats) + f->niw_cap + static_cast<size_t>(f->niw_cap) * f->dim;
+}
+// records of groups [g0, g0 + n) (and the tensor-core images) from the resident statistics
+static int niw_rebuild(dist_b200_feature *f, int g0, int n, cudaStream_t s) {
+    dist_b200_ctx *ctx = f->ctx;
+    const int d = f->dim;
+    const size_t dd = static_cast<size_t>(d) * d;
+    const size_t rec = static_cast<size_t>(niw_padded_dim(d)) * (niw_padded_dim(d) + 1) + 4;
+    int rc = launch_niw_prep(ctx, d, f->niw_shared_dev, f->kappa, f->niw_shared_dev + d, f->nu, n, niw_count(f) + g0,
+                             niw_sum_x(f) + static_cast<size_t>(g0) * d, niw_sum_xxT(f) + g0 * dd, f->niw_buf + rec * g0, s);
+    if (rc == DIST_B200_OK && d == 32 && f->niw_tc && f->G > 0) rc = launch_niw_tc_prep(ctx, f->G, f->niw_buf, f->niw_tc, s);
+    return rc;
+}
 
 int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float kappa, const float *psi,
                              float nu, int G, const int32_t *count, const float *sum_x, const float *sum_xxT,
@@ -527,6 +544,12 @@ int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float
     if (d > 32) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "niw: d > 32");
     if (!(kappa > 0.f) || !(nu > static_cast<float>(d) - 1.f))
         return fail(ctx, DIST_B200_ERR_INVALID, "niw: need kappa > 0 and nu > d - 1 (niw.hpp:121,132)");
+    if (f->niw_stats && f->dim != d) {  // the statistics layout depends on d
+        DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+        DISTB200_CUDA(ctx, cudaFree(f->niw_stats));
+        f->niw_stats = nullptr;
+        f->niw_cap = 0;
+    }
     f->dim = d;
     {
         int rcr = niw_reserve(f, G, 0);
@@ -549,9 +572,15 @@ int dist_b200_niw_update_all(dist_b200_feature *f, int d, const float *mu, float
     f->nu = nu;
     f->mu.assign(mu, mu + d);
     f->psi.assign(psi, psi + dd);
-    int rc2 = launch_niw_prep(ctx, d, mu_d, kappa, psi_d, nu, G, cnt_d, sx_d, sxx_d, f->niw_buf, as_stream(stream));
-    if (rc2 == DIST_B200_OK && d == 32 && G > 0) rc2 = launch_niw_tc_prep(ctx, G, f->niw_buf, f->niw_tc, as_stream(stream));
-    return mark_ready(f, rc2, as_stream(stream));
+    cudaStream_t s = as_stream(stream);
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(f->niw_shared_dev, mu_d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(f->niw_shared_dev + d, psi_d, sizeof(float) * dd, cudaMemcpyDeviceToDevice, s));
+    if (G > 0) {
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(niw_count(f), cnt_d, sizeof(int32_t) * G, cudaMemcpyDeviceToDevice, s));
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(niw_sum_x(f), sx_d, sizeof(float) * G * d, cudaMemcpyDeviceToDevice, s));
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(niw_sum_xxT(f), sxx_d, sizeof(float) * G * dd, cudaMemcpyDeviceToDevice, s));
+    }
+    return mark_ready(f, niw_rebuild(f, 0, G, s), s);
 }
 
 // NormalInverseWishart: one group's record (posterior, whitening matrix, constants) from its raw statistics
@@ -561,20 +590,20 @@ static int niw_update_group(dist_b200_feature *f, int groupid, const void *stats
     const int d = f->dim;
     const size_t dd = static_cast<size_t>(d) * d;
     if (f->mu.size() != static_cast<size_t>(d) || f->psi.size() != dd) return fail(ctx, DIST_B200_ERR_STATE, "niw update_group: call update_all first");
-    int rc = ensure_scratch(ctx, round_up(4 * d, 256) * 2 + round_up(4 * dd, 256) * 2 + 512);
+    if (!f->niw_stats || groupid >= f->niw_cap) return fail(ctx, DIST_B200_ERR_STATE, "niw update_group: call update_all first");
+    int rc = ensure_scratch(ctx, round_up(4 * d, 256) + round_up(4 * dd, 256) + 512);
     if (rc) return rc;
     const char *p = static_cast<const char *>(stats);
     Upload up{ctx, s};
-    const float *mu_d = up.put(f->mu.data(), d);
-    const float *psi_d = up.put(f->psi.data(), dd);
     const int32_t *cnt_d = up.put(reinterpret_cast<const int32_t *>(p), 1);
     const float *sx_d = up.put(reinterpret_cast<const float *>(p + 4), d);
     const float *sxx_d = up.put(reinterpret_cast<const float *>(p + 4 + 4 * d), dd);
     if (up.err) return up.err;
-    const size_t rec = static_cast<size_t>(niw_padded_dim(d)) * (niw_padded_dim(d) + 1) + 4;
-    rc = launch_niw_prep(ctx, d, mu_d, f->kappa, psi_d, f->nu, 1, cnt_d, sx_d, sxx_d, f->niw_buf + rec * groupid, s);
-    if (rc == DIST_B200_OK && d == 32 && f->niw_tc) rc = launch_niw_tc_prep(ctx, f->G, f->niw_buf, f->niw_tc, s);
-    return mark_ready(f, rc, s);
+    DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(niw_count(f) + groupid, cnt_d, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(niw_sum_x(f) + static_cast<size_t>(groupid) * d, sx_d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
+    DISTB200_CUDA(ctx, cudaMemcpyAsync(niw_sum_xxT(f) + groupid * dd, sxx_d, sizeof(float) * dd, cudaMemcpyDeviceToDevice, s));
+    return mark_ready(f, niw_rebuild(f, groupid, 1, s), s);
 }
 
 // (re)allocate the niw record buffers for G groups, keeping the first `keep` records
@@ -594,6 +623,25 @@ static int niw_reserve(dist_b200_feature *f, int G, int keep) {
         }
         f->niw_buf = fresh;
         f->niw_bytes = want;
+    }
+    if (!f->niw_shared_dev) DISTB200_CUDA(ctx, cudaMalloc(&f->niw_shared_dev, sizeof(float) * (32 + 32 * 32)));
+    if (G > f->niw_cap || !f->niw_stats) {
+        const int cap = std::max(G, 1) + std::max(G, 1) / 4 + 8;
+        const size_t dd = static_cast<size_t>(d) * d;
+        uint32_t *fresh = nullptr;
+        DISTB200_CUDA(ctx, cudaMalloc(&fresh, sizeof(uint32_t) * static_cast<size_t>(cap) * (1 + d + dd)));
+        DISTB200_CUDA(ctx, cudaMemset(fresh, 0, sizeof(uint32_t) * static_cast<size_t>(cap) * (1 + d + dd)));
+        DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+        if (f->niw_stats) {
+            if (keep > 0) {
+                DISTB200_CUDA(ctx, cudaMemcpy(fresh, niw_count(f), sizeof(int32_t) * keep, cudaMemcpyDeviceToDevice));
+                DISTB200_CUDA(ctx, cudaMemcpy(fresh + cap, niw_sum_x(f), sizeof(float) * keep * d, cudaMemcpyDeviceToDevice));
+                DISTB200_CUDA(ctx, cudaMemcpy(fresh + cap + static_cast<size_t>(cap) * d, niw_sum_xxT(f), sizeof(float) * keep * dd, cudaMemcpyDeviceToDevice));
+            }
+            DISTB200_CUDA(ctx, cudaFree(f->niw_stats));
+        }
+        f->niw_stats = fresh;
+        f->niw_cap = cap;
     }
     if (d == 32) {
         const size_t tc_bytes = sizeof(float) * niw_tc_floats(std::max(G, 1));
@@ -731,8 +779,15 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
         DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
         const size_t rec = static_cast<size_t>(niw_padded_dim(f->dim)) * (niw_padded_dim(f->dim) + 1) + 4;
         const int last = f->G - 1;
-        if (groupid != last)
+        if (groupid != last) {
+            const int d = f->dim;
+            const size_t dd = static_cast<size_t>(d) * d;
             DISTB200_CUDA(ctx, cudaMemcpyAsync(f->niw_buf + rec * groupid, f->niw_buf + rec * last, sizeof(float) * rec, cudaMemcpyDeviceToDevice, s));
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(niw_count(f) + groupid, niw_count(f) + last, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(niw_sum_x(f) + static_cast<size_t>(groupid) * d, niw_sum_x(f) + static_cast<size_t>(last) * d,
+                                               sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
+            DISTB200_CUDA(ctx, cudaMemcpyAsync(niw_sum_xxT(f) + groupid * dd, niw_sum_xxT(f) + last * dd, sizeof(float) * dd, cudaMemcpyDeviceToDevice, s));
+        }
         f->G = last;
         int rc = DIST_B200_OK;
         if (f->dim == 32 && f->niw_tc && f->G > 0) rc = launch_niw_tc_prep(ctx, f->G, f->niw_buf, f->niw_tc, s);
@@ -782,28 +837,28 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
         for (int i = 0; i < n_features; ++i) {
             const dist_b200_feature *f = features[i];
             if (!f) return fail(ctx, DIST_B200_ERR_INVALID, "rows exchange: null feature");
-            if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "rows exchange: niw statistics stay on the host");
             if (f->G != features[0]->G) return fail(ctx, DIST_B200_ERR_INVALID, "rows exchange: features disagree on the number of groups");
         }
     }
     cudaStream_t s = as_stream(stream);
-    size_t acc_need = 0, table_tmp = 0;  // pooled accumulators | (exchange) one count table of delta counts
+    size_t acc_need = 0, table_tmp = 0, niw_tmp = 0;  // pooled accumulators | (exchange) one count table of delta counts | niw work area
     int n_pooled = 0;
     for (int i = 0; i < n_features; ++i) {
         dist_b200_feature *f = features[i];
         if (!f || f->ctx != ctx || (phase != kRowsMerge && !columns_dev[i])) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows: bad feature / column");
-        if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: niw statistics stay on the host");
-        if (f->G < 1 || !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: call update_all first");
+        if (f->G < 1 || !(f->model == DIST_B200_NIW ? f->niw_stats : f->stats)) return fail(ctx, DIST_B200_ERR_STATE, "add_rows: call update_all first");
         if (pooled_model(f->model)) {
             acc_need = std::max(acc_need, add_rows_acc_bytes(f->G) * std::min(n_features, kAddBatch));
             ++n_pooled;
+        } else if (f->model == DIST_B200_NIW) {
+            if (phase != kRowsMerge) niw_tmp = std::max(niw_tmp, niw_add_rows_bytes(f->G, f->dim, n_rows));
         } else if (phase == kRowsAccumulate) {
             table_tmp = std::max(table_tmp, round_up(sizeof(int32_t) * static_cast<size_t>(f->G) * f->dim, 256));
         }
     }
     acc_need = round_up(acc_need, 256);
     const size_t pooled_bytes = acc_need;
-    acc_need += table_tmp;
+    acc_need += table_tmp + niw_tmp;
     // exchange layout: the pooled features' [4][G] blocks first (list order), then the count tables (list order)
     size_t table_off = phase == kRowsBoth ? 0 : static_cast<size_t>(n_pooled) * 4 * features[0]->G;
     if (acc_need > ctx->add_acc_bytes) {
@@ -897,6 +952,18 @@ static int rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *features, in
                 if ((rc = dpd_rebuild(f, reinterpret_cast<const float *>(dpd_betas(f)), reinterpret_cast<const int32_t *>(f->stats), s)))
                     return rc;
                 break;
+            case DIST_B200_NIW: {  // per-group SYRK into a [G][1 + d + d^2] double block (niw_stats.cu), then the records again
+                const int d = f->dim;
+                const size_t per = 1 + static_cast<size_t>(d) + static_cast<size_t>(d) * d;
+                char *area = static_cast<char *>(ctx->add_acc) + pooled_bytes + table_tmp;
+                double *acc = phase == kRowsBoth ? reinterpret_cast<double *>(area) : xchg + table_off;
+                void *work = area + round_up(sizeof(double) * G * per, 256);
+                if (phase != kRowsMerge && (rc = launch_niw_accumulate(ctx, G, d, columns_dev[i], assign_dev, n_rows, acc, work, s))) return rc;
+                table_off += G * per;
+                if (phase == kRowsAccumulate) break;
+                if ((rc = launch_niw_apply(ctx, G, d, sign, acc, niw_count(f), niw_sum_x(f), niw_sum_xxT(f), s))) return rc;
+                if ((rc = niw_rebuild(f, 0, G, s))) return rc;
+            } break;
             default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: unsupported model");
         }
     }
@@ -922,8 +989,9 @@ int dist_b200_rows_xchg_doubles(dist_b200_feature *const *features, int n_featur
     for (int i = 0; i < n_features; ++i) {
         const dist_b200_feature *f = features[i];
         if (!f) return DIST_B200_ERR_INVALID;
-        if (f->model == DIST_B200_NIW) return fail(f->ctx, DIST_B200_ERR_UNSUPPORTED, "rows exchange: niw statistics stay on the host");
-        n += pooled_model(f->model) ? static_cast<size_t>(4) * f->G : static_cast<size_t>(f->G) * f->dim;
+        n += pooled_model(f->model) ? static_cast<size_t>(4) * f->G
+             : f->model == DIST_B200_NIW ? static_cast<size_t>(f->G) * (1 + f->dim + static_cast<size_t>(f->dim) * f->dim)
+                                         : static_cast<size_t>(f->G) * f->dim;
     }
     *n_doubles = n;
     return DIST_B200_OK;
@@ -945,6 +1013,11 @@ int dist_b200_remove_rows_batch(dist_b200_ctx *ctx, dist_b200_feature *const *fe
     return rows_batch(ctx, features, n_features, columns_dev, assign_dev, n_rows, -1, stream);
 }
 
+// bytes of one value of the feature's column: bool as uint8, niw a row of d floats, everything else 4 bytes
+static size_t column_bytes(const dist_b200_feature *f) {
+    return f->model == DIST_B200_BB ? 1 : f->model == DIST_B200_NIW ? 4 * static_cast<size_t>(f->dim) : 4;
+}
+
 // host buffers: stage columns + assignments through the context scratch, run the device batch, drain
 static int rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
                            const void *const *columns_host, const int32_t *assign_host, size_t n_rows, int sign) {
@@ -955,9 +1028,8 @@ static int rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *feature
     size_t total = 0;
     for (int i = 0; i < n_features; ++i) {
         if (!features[i] || !columns_host[i]) return fail(ctx, DIST_B200_ERR_INVALID, "add_rows_host: null feature / column");
-        if (features[i]->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "add_rows: niw statistics stay on the host");
         off[i] = total;
-        total += round_up((features[i]->model == DIST_B200_BB ? 1 : 4) * n_rows, 256);
+        total += round_up(column_bytes(features[i]) * n_rows, 256);
     }
     const size_t assign_off = total;
     total += round_up(sizeof(int32_t) * n_rows, 256);
@@ -967,7 +1039,7 @@ static int rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *feature
     char *dev = static_cast<char *>(ctx->scratch_dev);
     std::vector<const void *> cols(n_features);
     for (int i = 0; i < n_features; ++i) {
-        const size_t vb = features[i]->model == DIST_B200_BB ? 1 : 4;
+        const size_t vb = column_bytes(features[i]);
         DISTB200_CUDA(ctx, cudaMemcpyAsync(dev + off[i], columns_host[i], vb * n_rows, cudaMemcpyHostToDevice, s));
         cols[i] = dev + off[i];
     }
@@ -1000,6 +1072,7 @@ static size_t shared_stride(const dist_b200_feature *f) {
         case DIST_B200_GP: case DIST_B200_BB: case DIST_B200_BNB: return 2;
         case DIST_B200_DD: return static_cast<size_t>(f->dim);
         case DIST_B200_DPD: return 1;
+        case DIST_B200_NIW: return 2 + static_cast<size_t>(f->dim) + static_cast<size_t>(f->dim) * f->dim;  // kappa, nu, mu[d], psi[d][d]
         default: return 0;
     }
 }
@@ -1029,8 +1102,7 @@ int dist_b200_score_data_grid(dist_b200_feature *f, const float *shareds_dev, si
     if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
     dist_b200_ctx *ctx = f->ctx;
     if (!shareds_dev || !out_dev) return fail(ctx, DIST_B200_ERR_INVALID, "score_data_grid: null argument");
-    if (f->model == DIST_B200_NIW) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_data_grid: niw statistics stay on the host");
-    if (f->G < 1 || !f->stats) return fail(ctx, DIST_B200_ERR_STATE, "score_data_grid: call update_all first");
+    if (f->G < 1 || !(f->model == DIST_B200_NIW ? f->niw_stats : f->stats)) return fail(ctx, DIST_B200_ERR_STATE, "score_data_grid: call update_all first");
     if (stride < shared_stride(f)) return fail(ctx, DIST_B200_ERR_INVALID, "score_data_grid: stride shorter than the model's packed Shared");
     if (f->model == DIST_B200_GP && !f->log_prod_valid)
         return fail(ctx, DIST_B200_ERR_STATE, "score_data_grid: gp needs Group::log_prod (dist_b200_gp_set_log_prod) after the last statistics change");
@@ -1051,6 +1123,15 @@ int dist_b200_score_data_grid(dist_b200_feature *f, const float *shareds_dev, si
     }
     if (!ctx->add_done) DISTB200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->add_done, cudaEventDisableTiming));
     DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, ctx->add_done, 0));
+    if (f->model == DIST_B200_NIW) {
+        DISTB200_CUDA(ctx, cudaMemsetAsync(ctx->add_acc, 0, sizeof(double) * n_grid, s));
+        int rcn = launch_niw_score_data(ctx, f->G, f->dim, niw_count(f), niw_sum_x(f), niw_sum_xxT(f), shareds_dev, n_grid, stride,
+                                        static_cast<double *>(ctx->add_acc), s);
+        if (!rcn) rcn = launch_score_data_finish(ctx, n_grid, static_cast<const double *>(ctx->add_acc), out_dev, s);
+        if (rcn) return rcn;
+        DISTB200_CUDA(ctx, cudaEventRecord(ctx->add_done, s));
+        return DIST_B200_OK;
+    }
     const uint32_t *st0, *st1 = nullptr, *st2 = nullptr;
     const float *betas = nullptr;
     if (f->model == DIST_B200_DPD) {
@@ -1231,13 +1312,15 @@ int dist_b200_feature_dump_groups_wire(dist_b200_feature *f, void *out, size_t c
                                        void *stream) {
     if (!f || !f->ctx) return DIST_B200_ERR_INVALID;
     dist_b200_ctx *ctx = f->ctx;
-    if (!f->stats || f->G < 1) return fail(ctx, DIST_B200_ERR_STATE, "dump_groups_wire: no device statistics (update_all first)");
+    if (!(f->model == DIST_B200_NIW ? f->niw_stats : f->stats) || f->G < 1)
+        return fail(ctx, DIST_B200_ERR_STATE, "dump_groups_wire: no device statistics (update_all first)");
     const size_t g = static_cast<size_t>(f->G);
     size_t words;
     switch (f->model) {
         case DIST_B200_NICH: case DIST_B200_GP: words = 3 * g; break;
         case DIST_B200_BNB: case DIST_B200_BB: words = 2 * g; break;
         case DIST_B200_DD: case DIST_B200_DPD: words = g * f->dim; break;
+        case DIST_B200_NIW: words = g * (1 + f->dim + static_cast<size_t>(f->dim) * f->dim); break;
         default: return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "dump_groups_wire: unsupported model");
     }
     std::vector<uint32_t> st(words, 0);
@@ -1264,12 +1347,21 @@ int dist_b200_feature_download_stats(const dist_b200_feature *f, void *out_host,
                                      void *stream) {
     if (!f || !f->ctx || !out_host) return DIST_B200_ERR_INVALID;
     dist_b200_ctx *ctx = f->ctx;
-    if (!f->stats) return fail(ctx, DIST_B200_ERR_STATE, "download_stats: no device statistics (update_all first)");
+    if (!(f->model == DIST_B200_NIW ? f->niw_stats : f->stats))
+        return fail(ctx, DIST_B200_ERR_STATE, "download_stats: no device statistics (update_all first)");
     cudaStream_t s = as_stream(stream);
     DISTB200_CUDA(ctx, cudaStreamWaitEvent(s, f->ready, 0));
     char *out = static_cast<char *>(out_host);
     size_t total = 0;
-    if (f->model == DIST_B200_DPD) {
+    if (f->model == DIST_B200_NIW) {  // count[G] | sum_x[G][d] | sum_xxT[G][d][d]
+        const size_t g = static_cast<size_t>(f->G), d = static_cast<size_t>(f->dim);
+        total = 4 * g * (1 + d + d * d);
+        if (n_bytes) *n_bytes = total;
+        if (total > capacity_bytes) return fail(ctx, DIST_B200_ERR_INVALID, "download_stats: buffer too small");
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(out, niw_count(f), 4 * g, cudaMemcpyDeviceToHost, s));
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(out + 4 * g, niw_sum_x(f), 4 * g * d, cudaMemcpyDeviceToHost, s));
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(out + 4 * g * (1 + d), niw_sum_xxT(f), 4 * g * d * d, cudaMemcpyDeviceToHost, s));
+    } else if (f->model == DIST_B200_DPD) {
         total = sizeof(int32_t) * static_cast<size_t>(f->G) * f->dim;
         if (n_bytes) *n_bytes = total;
         if (total > capacity_bytes) return fail(ctx, DIST_B200_ERR_INVALID, "download_stats: buffer too small");

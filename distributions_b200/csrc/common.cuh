@@ -140,6 +140,11 @@ struct dist_b200_feature {
     size_t niw_tc_bytes = 0;
     float kappa = 0, nu = 0;
     std::vector<float> mu, psi;
+    // niw: device-resident raw statistics over niw_cap groups (the state batched add_value updates in place):
+    // count[niw_cap] | sum_x[niw_cap][d] | sum_xxT[niw_cap][d][d]; and the Shared's mu[d] | psi[d][d]
+    uint32_t *niw_stats = nullptr;
+    int niw_cap = 0;
+    float *niw_shared_dev = nullptr;
 };
 
 namespace distb200 {
@@ -222,6 +227,16 @@ int launch_niw_prep(dist_b200_ctx *ctx, int d, const float *mu, float kappa, con
                     const int32_t *count, const float *sum_x, const float *sum_xxT, float *recs, cudaStream_t s);
 int launch_niw_scores(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *values, size_t N,
                       const float *prior, float *scores, int accumulate, cudaStream_t s);
+int launch_score_data_finish(dist_b200_ctx *ctx, size_t n_grid, const double *acc, float *out_dev, cudaStream_t s);  // prep.cu
+// niw_stats.cu (batched add_value / remove_value and score_data on the resident statistics)
+inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+size_t niw_add_rows_bytes(int G, int d, size_t N);
+int launch_niw_accumulate(dist_b200_ctx *ctx, int G, int d, const void *values, const int32_t *assign, size_t N, double *acc,
+                          void *work, cudaStream_t s);
+int launch_niw_apply(dist_b200_ctx *ctx, int G, int d, int sign, const double *acc, int32_t *count, float *sum_x, float *sum_xxT,
+                     cudaStream_t s);
+int launch_niw_score_data(dist_b200_ctx *ctx, int G, int d, const int32_t *count, const float *sum_x, const float *sum_xxT,
+                          const float *shareds_dev, size_t n_grid, size_t stride, double *acc, cudaStream_t s);
 // niw_tc.cu (tcgen05 / TMEM path, d = 32)
 size_t niw_tc_floats(int G);
 int launch_niw_tc_prep(dist_b200_ctx *ctx, int G, const float *recs, float *tc_buf, cudaStream_t s);

@@ -674,6 +674,13 @@ int launch_score_data(dist_b200_ctx *ctx, const dist_b200_feature *f, const uint
     return DIST_B200_OK;
 }
 
+int launch_score_data_finish(dist_b200_ctx *ctx, size_t n_grid, const double *acc, float *out_dev, cudaStream_t s) {
+    if (n_grid == 0) return DIST_B200_OK;
+    score_data_finish_kernel<<<blocks_for(n_grid, 256), 256, 0, s>>>(n_grid, acc, out_dev);
+    LAUNCH_CHECK(ctx);
+    return DIST_B200_OK;
+}
+
 int launch_low_entropy_prep(dist_b200_ctx *ctx, int dataset_size, int G, const int32_t *sizes, float *prior, cudaStream_t s) {
     const int blocks = G <= 256 ? 1 : (G + 255) / 256 < 64 ? (G + 255) / 256 : 64;
     low_entropy_prep_kernel<<<blocks, 256, 0, s>>>(dataset_size, G, sizes, prior, ctx->tables);

@@ -530,8 +530,10 @@ void orc_dpd_score_rows(size_t V, size_t G, const float *cache, size_t n, const 
 /* inverse and determinant of an SPD-ish d x d matrix by Gauss-Jordan with partial pivoting in
  * double (the reference calls Eigen's float inverse()/determinant(), random.hpp:171-172; Eigen
  * is absent here, hence "parity unpinned" for this step). a is destroyed. */
+static double g_logabsdet; /* sum of log |pivot| of the last invert() call: the determinant's log when det overflows a float */
 static double invert(int d, double *a, double *inv) {
     double det = 1.0;
+    g_logabsdet = 0.0;
     for (int i = 0; i < d; ++i)
         for (int j = 0; j < d; ++j) inv[i * d + j] = (i == j);
     for (int c = 0; c < d; ++c) {
@@ -547,6 +549,7 @@ static double invert(int d, double *a, double *inv) {
         }
         double piv = a[c * d + c];
         det *= piv;
+        g_logabsdet += log(fabs(piv));
         for (int j = 0; j < d; ++j) {
             a[c * d + j] /= piv;
             inv[c * d + j] /= piv;
@@ -617,6 +620,68 @@ void orc_niw_score_rows(int d, const float *mu, float kappa, const float *psi, f
         }
     }
     free(post_mu); free(sig_inv); free(konst); free(a); free(inv); free(xbar); free(diff);
+}
+
+/* Group::score_data (niw.hpp:296-308) summed over the groups, as SmallMixtureSlave's data scorer does for a model
+ * without a FastMixture (mixture.hpp:300-319); lmultigamma is special.hpp:278-286.  The determinants are taken by
+ * the Gauss-Jordan above in double (the reference: Eigen's float determinant(); Eigen is absent here). */
+/* fast_log(det) as the reference writes it, while det is a normal float; beyond that (the reference's float determinant()
+ * has overflowed to inf or flushed to 0 -- at d = 32 it always does -- and its score_data is meaningless) the log of the
+ * determinant itself, as the reference's exact-math Python flavour computes it (dbg/models/niw.py:213,216) */
+static float log_det(double det, double logabsdet) {
+    const float f = (float)det;
+    if (isfinite(f) && f >= 1.17549435e-38f) return orc_fast_log(f);
+    return (float)logabsdet;
+}
+
+static float orc_lmultigamma(int d, float a) {
+    const float log_pi = 1.1447298858494002f;
+    const float term1 = (float)(0.25 * (float)(d * (d - 1))) * log_pi;
+    float term2 = 0.f;
+    for (int j = 1; j <= d; ++j) term2 += orc_fast_lgamma((float)(a + 0.5 * (float)(1 - j)));
+    return term1 + term2;
+}
+
+float orc_niw_score_data(int d, const float *mu, float kappa, const float *psi, float nu, size_t G, const int32_t *count,
+                         const float *sum_x, const float *sum_xxT) {
+    const size_t dd = (size_t)d * d;
+    double *a = (double *)malloc(sizeof(double) * dd), *inv = (double *)malloc(sizeof(double) * dd);
+    float *xbar = (float *)malloc(sizeof(float) * d), *diff = (float *)malloc(sizeof(float) * d);
+    const float log_pi = 1.1447298858494002f;
+    for (size_t k = 0; k < dd; ++k) a[k] = psi[k];
+    const double det_prior_d = invert(d, a, inv);
+    const float log_det_prior = log_det(det_prior_d, g_logabsdet);
+    float total = 0.f;
+    for (size_t g = 0; g < G; ++g) {
+        const float cnt = (float)count[g];
+        const float *sx = sum_x + g * d, *sxx = sum_xxT + g * dd;
+        for (int i = 0; i < d; ++i) xbar[i] = count[g] ? sx[i] / cnt : 0.f;
+        for (int i = 0; i < d; ++i) diff[i] = xbar[i] - mu[i];
+        const float post_kappa = kappa + cnt, post_nu = nu + cnt;
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) {
+                float c_n = sxx[i * d + j] - sx[i] * xbar[j] - xbar[i] * sx[j] + cnt * xbar[i] * xbar[j];
+                a[i * d + j] = psi[i * d + j] + c_n + kappa * cnt / (kappa + cnt) * (diff[i] * diff[j]);
+            }
+        const double det_post_d = invert(d, a, inv);
+        const float log_det_post = log_det(det_post_d, g_logabsdet);
+        total += orc_lmultigamma(d, (float)(post_nu * 0.5)) + (float)(nu * 0.5) * log_det_prior -
+                 (float)((float)(count[g] * d) * 0.5) * log_pi - orc_lmultigamma(d, (float)(nu * 0.5)) -
+                 (float)(post_nu * 0.5) * log_det_post + (float)((float)d * 0.5) * orc_fast_log(kappa / post_kappa);
+    }
+    free(a); free(inv); free(xbar); free(diff);
+    return total;
+}
+
+/* Group::add_value / remove_value (niw.hpp:247-276), one value at a time in float as the reference's Eigen expressions */
+void orc_niw_group_update(int sign, int d, int32_t *count, float *sum_x, float *sum_xxT, size_t n, const float *values) {
+    for (size_t r = 0; r < n; ++r) {
+        const float *x = values + r * d;
+        *count += sign;
+        for (int i = 0; i < d; ++i) sum_x[i] += sign > 0 ? x[i] : -x[i];
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) sum_xxT[i * d + j] += sign > 0 ? x[i] * x[j] : -(x[i] * x[j]);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */

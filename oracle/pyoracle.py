@@ -175,6 +175,22 @@ class Oracle:
                                   _ptr(sum_xxT), n, _ptr(values), _ptr(scores))
         return scores
 
+    def niw_score_data(self, mu, kappa, psi, nu, count, sum_x, sum_xxT):
+        """sum over the groups of Group::score_data (niw.hpp:296-308)"""
+        mu, psi, count, sum_x, sum_xxT = _f32(mu), _f32(psi), _i32(count), _f32(sum_x), _f32(sum_xxT)
+        self.L.orc_niw_score_data.restype = ctypes.c_float
+        self.L.orc_niw_score_data.argtypes = [c_i, c_p, c_f, c_p, c_f, c_sz, c_p, c_p, c_p]
+        return float(self.L.orc_niw_score_data(mu.size, _ptr(mu), kappa, _ptr(psi), nu, count.size, _ptr(count), _ptr(sum_x), _ptr(sum_xxT)))
+
+    def niw_group_update(self, sign, count, sum_x, sum_xxT, values):
+        """Group::add_value (+1) / remove_value (-1) of the rows `values` [n][d], sequentially in float; returns the new statistics"""
+        sum_x, sum_xxT, values = _f32(sum_x).copy(), _f32(sum_xxT).copy(), _f32(values)
+        cnt = np.array([count], np.int32)
+        self.L.orc_niw_group_update.restype = None
+        self.L.orc_niw_group_update.argtypes = [c_i, c_i, c_p, c_p, c_p, c_sz, c_p]
+        self.L.orc_niw_group_update(sign, sum_x.size, _ptr(cnt), _ptr(sum_x), _ptr(sum_xxT), values.shape[0], _ptr(values))
+        return int(cnt[0]), sum_x, sum_xxT
+
     def sample_rows(self, scores, u):
         """scores [n][G] is overwritten with likelihoods (reference semantic). Returns assign."""
         assert scores.dtype == np.float32 and scores.flags.c_contiguous

@@ -186,7 +186,30 @@ def niw_golden_case(gd, name):
     g = lambda k: gd["%s_%s" % (name, k)]  # noqa: E731
     return dict(mu=g("mu").astype(np.float32), kappa=float(g("kappa")), psi=g("psi").astype(np.float32), nu=float(g("nu")),
                 count=g("count").astype(np.int32), sum_x=g("sum_x").astype(np.float32), sum_xxT=g("sum_xxT").astype(np.float32),
-                values=g("values").astype(np.float32), scores=g("scores"), post_mu=g("post_mu"), const_scores=g("const_scores"))
+                values=g("values").astype(np.float32), scores=g("scores"), post_mu=g("post_mu"), const_scores=g("const_scores"),
+                score_data=g("score_data"))
+
+
+def niw_score_data_tolerance(o, c):
+    """|implementation - reference python| allowed for sum_g Group.score_data: the implementation evaluates the
+    reference C++ expression (niw.hpp:296-308) with fast_lgamma / fast_log, whose deviations from lgamma / log are
+    known from the pinned oracle functions -- so return (correction, tolerance): want + correction is what an
+    implementation with exact linear algebra would give, up to fast_log(det)'s table step and float rounding"""
+    from scipy.special import gammaln
+    d = c["mu"].size
+    fl = lambda x: np.asarray(o.fast_lgamma(np.asarray(x, np.float32)), np.float64)  # noqa: E731
+    corr, tol = 0.0, 0.0
+    for n in c["count"].astype(np.float64):
+        for a in (0.5 * (c["nu"] + n), 0.5 * c["nu"]):
+            j = np.arange(1, d + 1)
+            arg = a + 0.5 * (1 - j)
+            dev = float(np.sum(fl(arg) - gammaln(arg)))
+            corr += dev if a != 0.5 * c["nu"] else -dev
+            tol += 3e-6 * float(np.sum(np.abs(gammaln(arg)))) + 1e-6 * d
+        # three fast_log terms, coefficients nu / 2, post.nu / 2, d / 2: a table step each (biased low, not corrected)
+        tol += LOG_STEP * (0.5 * c["nu"] + 0.5 * (c["nu"] + n) + 0.5 * d)
+        tol += 1e-5 * (0.5 * (c["nu"] + n))  # det of a float32 d x d posterior: relative 1e-5 in the log
+    return corr, tol
 
 
 def check_niw_golden(score_fn, o, c):

@@ -435,6 +435,32 @@ def test_niw_oracle_matches_reference_python(oracle, golden_niw, name):
     cases.check_niw_golden(score, oracle, c)
 
 
+@pytest.mark.parametrize("name", cases.NIW_GOLDEN_CASES)
+def test_niw_score_data_oracle_matches_reference_python(oracle, golden_niw, name):
+    """Group.score_data of the reference's exact-math Python (dbg/models/niw.py:202-217) summed over the groups vs the
+    C restatement of niw.hpp:296-308: at the reference's cross-flavour bar, and tightly once the KNOWN deviations of
+    fast_lgamma are taken out"""
+    c = cases.niw_golden_case(golden_niw, name)
+    got = oracle.niw_score_data(c["mu"], c["kappa"], c["psi"], c["nu"], c["count"], c["sum_x"], c["sum_xxT"])
+    want = float(np.sum(c["score_data"]))
+    assert abs(got - want) <= 1e-3 * (1 + abs(got) + abs(want))
+    corr, tol = cases.niw_score_data_tolerance(oracle, c)
+    assert abs(got - (want + corr)) <= tol + 2e-6 * abs(want), (got, want, corr, tol)
+
+
+def test_niw_group_update_oracle_matches_reference_python(oracle, golden_niw):
+    """Group.add_value one value at a time (niw.hpp:247-255) reproduces the statistics the reference's Python accumulated"""
+    c = cases.niw_golden_case(golden_niw, "ex1")
+    d = c["mu"].size
+    vals = c["values"]
+    cnt, sx, sxx = oracle.niw_group_update(+1, 0, np.zeros(d, np.float32), np.zeros((d, d), np.float32), vals)
+    assert cnt == len(vals)
+    np.testing.assert_allclose(sx, vals.astype(np.float64).sum(0), rtol=1e-5)
+    np.testing.assert_allclose(sxx, vals.astype(np.float64).T @ vals.astype(np.float64), rtol=1e-5, atol=1e-4)
+    cnt, sx, sxx = oracle.niw_group_update(-1, cnt, sx, sxx, vals)
+    assert cnt == 0 and np.abs(sx).max() < 1e-3 and np.abs(sxx).max() < 1e-2
+
+
 def test_niw_golden_covers_reference_examples(golden_niw):
     """the fixtures include the reference's EXAMPLES verbatim (dbg/models/niw.py:39-102 = lp/models/niw.pyx EXAMPLES)"""
     assert golden_niw["ex0_values"].shape == (7, 2) and golden_niw["ex1_values"].shape == (9, 3) and golden_niw["ex2_values"].shape == (9, 4)
