@@ -150,7 +150,11 @@ int dist_b200_feature_remove_group(dist_b200_feature *f, int groupid, void *stre
  * Group::add_value + MixtureValueScorer::add_value (nich.hpp:125-133,326-333; gp.hpp:109-116,275-282;
  * bb.hpp:102-107,258-265; dd.hpp:123-130,381-388; dpd.hpp:188-196,430-447).  Counts are exact; nich's
  * mean / count_times_variance use the pairwise merge of Group::merge (nich.hpp:167-179) instead of N
- * sequential Welford steps (agreement ~1e-6 relative).  niw: not supported (statistics stay on the host). */
+ * sequential Welford steps (agreement ~1e-6 relative).  niw (niw.hpp:247-276; column = rows of d floats): the rows
+ * are bucketed by group and every group's count / sum_x / sum_xxT deltas are accumulated in double (a per-group
+ * SYRK), then folded into the resident float statistics -- the correctly rounded sums, where the reference's
+ * value-by-value float updates carry their accumulation error; the group records are rebuilt afterwards.  A group
+ * the batch empties is reset to exact zeros (Group::init). */
 int dist_b200_feature_add_rows(dist_b200_feature *f, const void *column_dev, const int32_t *assign_dev, size_t n_rows,
                                void *stream);
 /* The same for all features of one cross-cat kind at once (the reference loops the features of a kind per
@@ -174,8 +178,8 @@ int dist_b200_remove_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *cons
  * remove_value), leaving all replicas bit-identical.  Layout of xchg_dev (doubles; dist_b200_rows_xchg_doubles
  * returns the total): first one [4][G] block per pooled-statistics feature (nich / gp / bb / bnb: count-like a,
  * count-like b, sum x, sum x^2; integers exact) in list order, then one [G][dim] block of delta counts per
- * count-table feature (dd: dd.hpp:123-149; dpd: dpd.hpp:188-214, dim = number of known values) in list order.
- * All features with the same G.  niw: unsupported. */
+ * count-table feature (dd: dd.hpp:123-149; dpd: dpd.hpp:188-214, dim = number of known values) and one
+ * [G][1 + d + d * d] block {count, sum_x, sum_xxT} per niw feature, in list order.  All features with the same G. */
 int dist_b200_rows_xchg_doubles(dist_b200_feature *const *features, int n_features, size_t *n_doubles);
 int dist_b200_rows_accumulate(dist_b200_ctx *ctx, dist_b200_feature *const *features, int n_features,
                               const void *const *columns_dev, const int32_t *assign_dev, size_t n_rows, double *xchg_dev,
@@ -191,11 +195,14 @@ int dist_b200_add_rows_batch_host(dist_b200_ctx *ctx, dist_b200_feature *const *
  * MixtureSlave::score_data_grid / score_data (mixture.hpp:427-438; nich.hpp:262-288, gp.hpp:220-241,
  * bb.hpp:207-229, dd.hpp:250-324, dpd.hpp:344-374) on the device-resident group statistics.  shareds:
  * n_grid packed Shareds, `stride` floats apart -- nich (mu, kappa, sigmasq, nu); gp (alpha, inv_beta);
- * bb (alpha, beta); dd alphas[dim]; dpd (alpha), with beta0 / betas of the last update_all.  Every term is
+ * bb (alpha, beta); dd alphas[dim]; dpd (alpha), with beta0 / betas of the last update_all; niw (niw.hpp:296-308)
+ * kappa, nu, mu[d], psi[d][d].  Every term is
  * the reference's fp32 expression; the sum over groups is accumulated in double (the reference: fp32, group
  * order), so results agree to ~1e-6 of sum |term|.  gp reads Group::log_prod, which the hot path does not
  * carry: set it with dist_b200_gp_set_log_prod after update_all / any statistics change (ERR_STATE otherwise).
- * niw: unsupported. */
+ * niw: the determinants come from Cholesky factorisations in double; fast_log(det) is the reference's while det is a
+ * normal float -- beyond that (the reference's float determinant() overflows, always at d = 32, and its result is
+ * meaningless) the exact log determinant is used, as in the reference's Python flavour (dbg/models/niw.py:213,216). */
 int dist_b200_gp_set_log_prod(dist_b200_feature *f, const float *log_prod_host, void *stream);
 int dist_b200_score_data_grid(dist_b200_feature *f, const float *shareds_dev, size_t n_grid, size_t stride,
                               float *out_dev, void *stream);
