@@ -1893,19 +1893,21 @@ int dist_b200_score_value_host(dist_b200_ctx *ctx, const dist_b200_feature *feat
     const int G = feature->G;
     if (G < 1) return fail(ctx, DIST_B200_ERR_STATE, "score_value: no groups");
     const size_t vb = value_bytes(feature);
-    int rc = ensure_scratch(ctx, round_up(vb, 256) + sizeof(float) * G + 256);
+    // zero-copy through the context's page-locked area (device-accessible under unified addressing): the kernel reads
+    // the value from host memory and writes the G scores back to it, so a call is ONE launch + one synchronise instead
+    // of two H2D copies, a launch and a D2H copy; the accumulation into the caller's (pageable) buffer is done here
+    int rc = ensure_pinned(ctx, round_up(vb, 256) + sizeof(float) * G + 256);
     if (rc) return rc;
-    char *dev = static_cast<char *>(ctx->scratch_dev);
-    float *sc = reinterpret_cast<float *>(dev + round_up(vb, 256));
+    char *pin = static_cast<char *>(ctx->pinned);
+    float *sc = reinterpret_cast<float *>(pin + round_up(vb, 256));
     cudaStream_t s = ctx->own_stream;
     if ((rc = wait_ready(ctx, &feature, 1, s))) return rc;
-    DISTB200_CUDA(ctx, cudaMemcpyAsync(dev, value_host, vb, cudaMemcpyHostToDevice, s));
-    DISTB200_CUDA(ctx, cudaMemcpyAsync(sc, scores_accum_host, sizeof(float) * G, cudaMemcpyHostToDevice, s));
-    const void *col = dev;
-    rc = score_dispatch(ctx, &feature, 1, &col, 1, nullptr, nullptr, nullptr, sc, 1, s);
+    std::memcpy(pin, value_host, vb);
+    const void *col = pin;
+    rc = score_dispatch(ctx, &feature, 1, &col, 1, nullptr, nullptr, nullptr, sc, 0, s);
     if (rc) return rc;
-    DISTB200_CUDA(ctx, cudaMemcpyAsync(scores_accum_host, sc, sizeof(float) * G, cudaMemcpyDeviceToHost, s));
     DISTB200_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int g = 0; g < G; ++g) scores_accum_host[g] += sc[g];  // MixtureSlave::score_value accumulates (mixture.hpp:416-425)
     return DIST_B200_OK;
 }
 

@@ -84,31 +84,33 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;                                                      // layout type 0 = no swizzle
 }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+// mbarriers are addressed by their shared-space address, computed once per kernel (a generic -> shared conversion per
+// call shows up in an epilogue that hands over a TMEM buffer every few hundred cycles)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     uint32_t spins = 0;
     while (!done) {
         asm volatile(
             "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(bar), "r"(parity)
             : "memory");
         if (!done && ++spins > (1u << 26)) __trap();  // never hang the device on a protocol error
     }
 }
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                      smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
                  : "memory");
 }
 // L2 eviction policies: the per-CTA score scratch and the block records are re-used (evict last), the row images stream
@@ -123,10 +125,10 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+__device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
                      smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ void st_f2_hint(float2 *p, float2 v, uint64_t policy) {
@@ -143,25 +145,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
-// 64 columns = two cells per instruction, results left in flight (the caller issues tcgen05.wait::ld once)
-__device__ __forceinline__ void tmem_ld64_nowait(uint32_t taddr, uint32_t (&r)[64]) {
+// 32 columns: one half (16 dims) of two cells
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *r) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
-          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
-          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
-          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
-          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
 
@@ -226,7 +222,10 @@ __global__ void __launch_bounds__(256) niw_tc_prep_kernel(int G, const float *__
     for (int e = tid; e < 256 * kTcK; e += blockDim.x) {
         const int n = e / kTcK, k = e - n * kTcK;  // B row n = (group in block) * 32 + i, column k
         const int g = blk * kTcGroupsPerBlock + (n >> 5), i = n & 31;
-        const int off = core_offset_halves(n, k, 32);
+        // B row (= accumulator column) of (group, dim i): the low 16 dims of the 8 groups, then the high 16 dims -- W is lower
+        // triangular, so the k-step over x[16..32) only feeds the high half and its MMAs run with N = 128
+        const int brow = (i >> 4) * 128 + (n >> 5) * 16 + (i & 15);
+        const int off = core_offset_halves(brow, k, 32);
         if (k < kTcDim) {
             const float w = g < G ? recs[static_cast<size_t>(g) * REC + kTcDim + i * kTcDim + k] * scale[n >> 5] : 0.f;
             const __half hi = __float2half_rn(w);
@@ -304,7 +303,6 @@ __global__ void __launch_bounds__(256) niw_tc_pack_x_kernel(size_t N, const floa
 
 struct NiwTcArgs {
     int G, n_blocks, accumulate, Gpad;
-    int debug;  // profiling runs only (DIST_B200_OPT_NIW_DEBUG): 1 = skip the sampling walk, 2 = also skip the epilogue math
     size_t N, ntiles;
     const unsigned char *blockrecs;  // [n_blocks][kBlockRecBytes]
     const __half *xpack;             // [ntiles][2][128 * 48]
@@ -316,7 +314,11 @@ struct NiwTcArgs {
     int32_t *assign;                 // fused mode
 };
 
-template <bool kFused>
+// kDebug (DIST_B200_OPT_NIW_DEBUG, profiling builds of the same kernel whose results are WRONG by construction): 1 = no
+// sampling walk, 2 = also no epilogue math, 4 = barrier hand-offs only (loader + MMA stream alone), 5 = and 3 of the 7 MMAs.
+// A template parameter, not a runtime flag: as a runtime branch the debug paths cost the production kernel 64 register
+// initialisations per thread per tile (28 % of its instructions, profiles/r02_c5_niw_fused.txt)
+template <bool kFused, int kDebug>
 __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const NiwTcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *As = smem_raw;                                        // [kChunkTiles][hi | lo]  64 KB
@@ -325,24 +327,30 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
     float *half_m = reinterpret_cast<float *>(Bs + kBStages * kBlockRecBytes);   // [kParts][kChunkTiles * 128] online max per column part
     float *half_s = half_m + kParts * kChunkTiles * kTcRows;                     // [kParts][kChunkTiles * 128] online sum
     uint64_t *bars = reinterpret_cast<uint64_t *>(half_s + kParts * kChunkTiles * kTcRows);
-    uint64_t *a_full = bars, *a_empty = a_full + kChunkTiles, *b_full = a_empty + kChunkTiles, *b_empty = b_full + kBStages;
-    uint64_t *t_full = b_empty + kBStages, *t_empty = t_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+    // shared-space addresses of the mbarriers: X(i) = the i-th barrier of ring X
+    const uint32_t bars_s = smem_u32(bars);
+    auto a_full = [&](int i) { return bars_s + 8u * i; };
+    auto a_empty = [&](int i) { return bars_s + 8u * (kChunkTiles + i); };
+    auto b_full = [&](int i) { return bars_s + 8u * (2 * kChunkTiles + i); };
+    auto b_empty = [&](int i) { return bars_s + 8u * (2 * kChunkTiles + kBStages + i); };
+    auto t_full = [&](int i) { return bars_s + 8u * (2 * kChunkTiles + 2 * kBStages + i); };
+    auto t_empty = [&](int i) { return bars_s + 8u * (2 * kChunkTiles + 2 * kBStages + 2 + i); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kChunkTiles + 2 * kBStages + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nb = a.n_blocks;
     if (tid == 0) {
         for (int i = 0; i < kChunkTiles; ++i) {
-            mbar_init(&a_full[i], 1);
-            mbar_init(&a_empty[i], 1);
+            mbar_init(a_full(i), 1);
+            mbar_init(a_empty(i), 1);
         }
         for (int i = 0; i < kBStages; ++i) {
-            mbar_init(&b_full[i], 1);
-            mbar_init(&b_empty[i], kEpiWarps);  // one arrival per epilogue warp: the record also carries their constants
+            mbar_init(b_full(i), 1);
+            mbar_init(b_empty(i), kEpiWarps);  // one arrival per epilogue warp: the record also carries their constants
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&t_full[i], 1);
-            mbar_init(&t_empty[i], kEpiWarps);
+            mbar_init(t_full(i), 1);
+            mbar_init(t_empty(i), kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -354,8 +362,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // instruction descriptor: D = F32, A = B = F16, both K-major, N = 256, M = 128
+    // instruction descriptors: D = F32, A = B = F16, both K-major, M = 128, N = 256 / 128 (the high-dims half alone)
     const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_half = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
     const size_t nchunks = (a.ntiles + kChunkTiles - 1) / kChunkTiles;
 
@@ -368,16 +377,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                 const size_t t0 = chunk * kChunkTiles;
                 const int nt = static_cast<int>(a.ntiles - t0 < kChunkTiles ? a.ntiles - t0 : kChunkTiles);
                 auto load_a = [&](int t) {
-                    mbar_wait(&a_empty[t], aphase ^ 1);  // the previous chunk's MMAs on this tile have retired
-                    mbar_expect_tx(&a_full[t], kATileBytes);
-                    bulk_g2s_hint(As + t * kATileBytes, a.xpack + (t0 + t) * (kATileBytes / 2), kATileBytes, &a_full[t], pol_stream);
+                    mbar_wait(a_empty(t), aphase ^ 1);  // the previous chunk's MMAs on this tile have retired
+                    mbar_expect_tx(a_full(t), kATileBytes);
+                    bulk_g2s_hint(As + t * kATileBytes, a.xpack + (t0 + t) * (kATileBytes / 2), kATileBytes, a_full(t), pol_stream);
                 };
                 // in consumption order: tile 0, block 0, the remaining tiles, the remaining blocks
                 load_a(0);
                 for (int blk = 0; blk < nb; ++blk) {
-                    mbar_wait(&b_empty[bstage], bphase ^ 1);
-                    mbar_expect_tx(&b_full[bstage], kBlockRecBytes);
-                    bulk_g2s_hint(Bs + bstage * kBlockRecBytes, a.blockrecs + static_cast<size_t>(blk) * kBlockRecBytes, kBlockRecBytes, &b_full[bstage], pol_keep);
+                    mbar_wait(b_empty(bstage), bphase ^ 1);
+                    mbar_expect_tx(b_full(bstage), kBlockRecBytes);
+                    bulk_g2s_hint(Bs + bstage * kBlockRecBytes, a.blockrecs + static_cast<size_t>(blk) * kBlockRecBytes, kBlockRecBytes, b_full(bstage), pol_keep);
                     if (++bstage == kBStages) {
                         bstage = 0;
                         bphase ^= 1;
@@ -391,34 +400,39 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint32_t bstage = 0, bphase = 0, aphase = 0, tphase[2] = {0, 0};
+            uint32_t bstage = 0, bphase = 0, aphase = 0, tphase = 0;  // tphase / fphase: bit tb = phase of accumulator tb
             int tb = 0;
             for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
                 const size_t t0 = chunk * kChunkTiles;
                 const int nt = static_cast<int>(a.ntiles - t0 < kChunkTiles ? a.ntiles - t0 : kChunkTiles);
                 for (int blk = 0; blk < nb; ++blk) {
-                    mbar_wait(&b_full[bstage], bphase);
+                    mbar_wait(b_full(bstage), bphase);
                     const uint32_t b_hi = smem_u32(Bs + bstage * kBlockRecBytes), b_lo = b_hi + kBImageBytes;
                     for (int t = 0; t < nt; ++t) {
-                        if (blk == 0) mbar_wait(&a_full[t], aphase);
-                        mbar_wait(&t_empty[tb], tphase[tb] ^ 1);  // epilogue has drained this accumulator
-                        tphase[tb] ^= 1;
+                        if (blk == 0) mbar_wait(a_full(t), aphase);
+                        mbar_wait(t_empty(tb), ((tphase >> tb) & 1u) ^ 1u);  // epilogue has drained this accumulator
+                        tphase ^= 1u << tb;
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                         const uint32_t d_addr = tmem_base + tb * 256;
                         const uint32_t a_hi = smem_u32(As + t * kATileBytes), a_lo = a_hi + kAImageBytes;
                         uint32_t acc = 0;
 #pragma unroll
                         for (int ks = 0; ks < kTcK / 16; ++ks) {  // K = 16 per instruction = two 8-half cores
-                            const uint32_t ao = ks * 2 * (kTcRows / 8) * 128, bo = ks * 2 * 32 * 128;
-                            umma_f16(d_addr, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, acc);
+                            const uint32_t ao = ks * 2 * (kTcRows / 8) * 128;
+                            // k-step 1 (x[16..32)) meets zeros in the low-dims half of the lower-triangular W: N = 128, B rows and
+                            // accumulator columns [128, 256) only
+                            const bool half = ks == 1;
+                            const uint32_t bo = ks * 2 * 32 * 128 + (half ? 16 * 128 : 0), dd = d_addr + (half ? 128 : 0);
+                            const uint32_t id = half ? idesc_half : idesc;
+                            umma_f16(dd, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), id, acc);
                             acc = 1;
                             // the augmented k-step carries both terms of -b in the hi images: one MMA
-                            if (a.debug >= 5 || ks == kTcDim / 16) continue;  // (debug 5: hi x hi only)
-                            umma_f16(d_addr, make_smem_desc(a_lo + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), idesc, 1);
-                            umma_f16(d_addr, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_lo + bo, 32 * 128, 128), idesc, 1);
+                            if (kDebug >= 5 || ks == kTcDim / 16) continue;  // (debug 5: hi x hi only)
+                            umma_f16(dd, make_smem_desc(a_lo + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_hi + bo, 32 * 128, 128), id, 1);
+                            umma_f16(dd, make_smem_desc(a_hi + ao, (kTcRows / 8) * 128, 128), make_smem_desc(b_lo + bo, 32 * 128, 128), id, 1);
                         }
-                        if (blk == nb - 1) umma_commit(&a_empty[t]);  // tile reusable by the next chunk once these retire
-                        umma_commit(&t_full[tb]);                     // accumulator ready for the epilogue
+                        if (blk == nb - 1) umma_commit(a_empty(t));  // tile reusable by the next chunk once these retire
+                        umma_commit(t_full(tb));                     // accumulator ready for the epilogue
                         tb ^= 1;
                     }
                     if (++bstage == kBStages) {
@@ -437,7 +451,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
         const int r_in_tile = q * 32 + lane;
         constexpr int kPer = kTcGroupsPerBlock / kParts;
         static_assert(kPer == 2, "the epilogue below loads 64 columns (two cells) per thread");
-        uint32_t bstage = 0, bphase = 0, fphase[2] = {0, 0};
+        uint32_t bstage = 0, bphase = 0, fphase = 0;
         int tb = 0;
         float *scratch = kFused ? a.scratch + static_cast<size_t>(blockIdx.x) * kChunkTiles * kTcRows * a.Gpad : nullptr;
         const uint64_t pol_keep = l2_policy_evict_last();
@@ -452,7 +466,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                 os[t] = 0.f;
             }
             for (int blk = 0; blk < nb; ++blk) {
-                mbar_wait(&b_full[bstage], bphase);
+                mbar_wait(b_full(bstage), bphase);
                 const float *cs = reinterpret_cast<const float *>(Bs + bstage * kBlockRecBytes + kBImagesBytes);
                 float pr[kPer];
 #pragma unroll
@@ -463,43 +477,41 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
 #pragma unroll
                 for (int t = 0; t < kChunkTiles; ++t) {
                     if (t >= nt) break;
-                    mbar_wait(&t_full[tb], fphase[tb]);
-                    fphase[tb] ^= 1;
+                    mbar_wait(t_full(tb), (fphase >> tb) & 1u);
+                    fphase ^= 1u << tb;
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    if (a.debug >= 4) {  // barrier hand-offs only: the rate of the loader + MMA stream alone
+                    if (kDebug >= 4) {  // barrier hand-offs only: the rate of the loader + MMA stream alone
                         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                        if (lane == 0) mbar_arrive(&t_empty[tb]);
+                        if (lane == 0) mbar_arrive(t_empty(tb));
                         tb ^= 1;
                         continue;
                     }
                     uint32_t yr[64];
-                    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tb * 256 + h * kPer * 32;
-                    if (a.debug >= 3) {
-#pragma unroll
-                        for (int i = 0; i < 64; ++i) yr[i] = 0x3f800000u + i;
-                    } else {
-                        tmem_ld64_nowait(t_row, yr);
-                    }
+                    // this thread's two groups: their low 16 dims at columns [32 h, 32 h + 32), their high 16 dims 128 further
+                    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tb * 256 + h * kPer * 16;
+                    tmem_ld32_nowait(t_row, yr);
+                    tmem_ld32_nowait(t_row + 128, yr + 32);
                     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                    if (lane == 0) mbar_arrive(&t_empty[tb]);  // accumulator drained by this warp: one of the 8 arrivals
+                    if (lane == 0) mbar_arrive(t_empty(tb));  // accumulator drained by this warp: one of the 8 arrivals
                     tb ^= 1;
                     float out[kPer];
-                    if (a.debug >= 2) {
+                    if (kDebug >= 2) {
 #pragma unroll
-                        for (int jj = 0; jj < kPer; ++jj) out[jj] = __uint_as_float(yr[jj * 32]);
+                        for (int jj = 0; jj < kPer; ++jj) out[jj] = __uint_as_float(yr[jj * 16]);
                     } else
 #pragma unroll
                     for (int jj = 0; jj < kPer; ++jj) {
                         const int j = h * kPer + jj;
-                        const uint32_t *y = &yr[jj * 32];  // (y - b) 2^(ex + ew)
+                        const uint32_t *ylo = &yr[jj * 16], *yhi = &yr[32 + jj * 16];  // (y - b) 2^(ex + ew): dims [0, 16) and [16, 32)
                         const float4 c = *reinterpret_cast<const float4 *>(cs + j * 4);
                         const float unscale = sxt[t] * c.w;  // 2^-(ex + ew): exact
                         uint64_t qa = 0ull, qb = 0ull;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const uint64_t d0 = pack2(__uint_as_float(y[4 * i]), __uint_as_float(y[4 * i + 1]));
-                            const uint64_t d1 = pack2(__uint_as_float(y[4 * i + 2]), __uint_as_float(y[4 * i + 3]));
+                            const uint32_t *y = i < 4 ? ylo + 4 * i : yhi + 4 * (i - 4);
+                            const uint64_t d0 = pack2(__uint_as_float(y[0]), __uint_as_float(y[1]));
+                            const uint64_t d1 = pack2(__uint_as_float(y[2]), __uint_as_float(y[3]));
                             qa = fma2(d0, d0, qa);
                             qb = fma2(d1, d1, qb);
                         }
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&b_empty[bstage]);  // this warp is done with the record's -b / constants
+                if (lane == 0) mbar_arrive(b_empty(bstage));  // this warp is done with the record's -b / constants
                 if (++bstage == kBStages) {
                     bstage = 0;
                     bphase ^= 1;
@@ -554,7 +566,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) niw_tc_fused_kernel(const Ni
                 const int et = tid - 64;
                 for (int rc = et; rc < nt * kTcRows; rc += 32 * kEpiWarps) {
                     const size_t row = t0 * kTcRows + rc;
-                    if (row >= a.N || a.debug >= 1) continue;
+                    if (row >= a.N || kDebug >= 1) continue;
                     float mm = half_m[rc];  // max score * log2e
 #pragma unroll
                     for (int p = 1; p < kParts; ++p) mm = fmaxf(mm, half_m[p * kChunkTiles * kTcRows + rc]);
@@ -648,18 +660,26 @@ int launch_niw_tc(dist_b200_ctx *ctx, int G, const float *tc_buf, const void *va
     a.scratch = reinterpret_cast<float *>(base + xbytes + sxbytes);
     a.u = u;
     a.assign = assign;
-    a.debug = ctx->opt[DIST_B200_OPT_NIW_DEBUG];
     niw_tc_pack_x_kernel<<<static_cast<unsigned>(ntiles), 256, 0, s>>>(N, static_cast<const float *>(values), reinterpret_cast<__half *>(base),
                                                                    reinterpret_cast<float *>(base + xbytes));
     const size_t smem = static_cast<size_t>(kChunkTiles) * kATileBytes + static_cast<size_t>(kBStages) * kBlockRecBytes +
                         2 * (kEpiWarps / 4) * kChunkTiles * kTcRows * sizeof(float) + 32 * sizeof(uint64_t) + 1024;
     cudaError_t e;
+    auto launch = [&](auto kern) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (err == cudaSuccess) kern<<<grid, kFusedThreads, smem, s>>>(a);
+        return err;
+    };
     if (fused) {
-        e = cudaFuncSetAttribute(niw_tc_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess) niw_tc_fused_kernel<true><<<grid, kFusedThreads, smem, s>>>(a);
+        switch (ctx->opt[DIST_B200_OPT_NIW_DEBUG]) {  // profiling variants, see the kernel's comment
+            case 0: e = launch(niw_tc_fused_kernel<true, 0>); break;
+            case 1: e = launch(niw_tc_fused_kernel<true, 1>); break;
+            case 2: case 3: e = launch(niw_tc_fused_kernel<true, 2>); break;
+            case 4: e = launch(niw_tc_fused_kernel<true, 4>); break;
+            default: e = launch(niw_tc_fused_kernel<true, 5>); break;
+        }
     } else {
-        e = cudaFuncSetAttribute(niw_tc_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess) niw_tc_fused_kernel<false><<<grid, kFusedThreads, smem, s>>>(a);
+        e = launch(niw_tc_fused_kernel<false, 0>);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("niw_tc launch: ") + cudaGetErrorString(e));

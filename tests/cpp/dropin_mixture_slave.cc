@@ -141,7 +141,7 @@ struct Harness {
         const double us_stock = std::chrono::duration<double, std::micro>(t1 - t0).count() / iters;
         const double us_b200 = std::chrono::duration<double, std::micro>(t2 - t1).count() / iters;
         std::printf("LATENCY %s G=%zu per-value score_value: stock FastMixture %.3f us, B200 ValueScorer %.1f us "
-                    "(2 H2D + 1 launch + 1 D2H + sync per call)\n", name, stock.groups().size(), us_stock, us_b200);
+                    "(zero-copy value and scores: 1 launch + 1 synchronise per call)\n", name, stock.groups().size(), us_stock, us_b200);
     }
 };
 
