@@ -40,6 +40,10 @@ constexpr int kKindNichPacked = 17;
 // value -- what scores_to_likelihoods would subtract for any row carrying v (random.cc:94-106) -- so a cell is one
 // shared-memory gather + MUFU.EX2, and the walk runs over pair sums (half the registers: five blocks per SM).
 constexpr int kKindDdScaled = 18;
+// the same with dim = 16 known at compile time (DirichletDiscrete<16>, the c1 shape): the per-cell gather address
+// becomes base + immediate, which takes an IMAD and a LEA out of a 7.6-instruction cell (profiles/r02_c1_dd_steady.txt)
+constexpr int kKindDdScaled16 = 19;
+__host__ __device__ constexpr bool is_dd_scaled(int kind) { return kind == kKindDdScaled || kind == kKindDdScaled16; }
 
 constexpr int kSlots = 16;
 constexpr int kStages = 3;  // cp.async ring depth of the streaming mode
@@ -86,7 +90,7 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
 }
 
 __host__ __device__ __forceinline__ int kind_stride(int kind, int vdim) {  // floats of cache per group
-    return (kind == DIST_B200_DD || kind == kKindGpTable || kind == kKindDdScaled) ? vdim : 4;
+    return (kind == DIST_B200_DD || kind == kKindGpTable || is_dd_scaled(kind)) ? vdim : 4;
 }
 
 // GammaPoisson term of one (value, group) cell -- the single definition shared by the direct path, the
@@ -258,7 +262,7 @@ struct RowsArgs {
 };
 
 template <int CHUNK, int KIND, bool kSample, bool kScores, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 128 ? (KIND == kKindDdScaled ? 5 : 3) : (CHUNK <= 32 ? (KIND >= 0 ? 4 : 3) : (CHUNK <= 64 ? 2 : 1)))
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? (is_dd_scaled(KIND) ? 5 : 3) : (CHUNK <= 32 ? (KIND >= 0 ? 4 : 3) : (CHUNK <= 64 ? 2 : 1)))
 score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     constexpr int kThreads = THREADS;  // block size of this instantiation
     extern __shared__ __align__(16) float smem[];
@@ -329,7 +333,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
             }
         }
         __syncthreads();
-        if (KIND == kKindDdScaled) {
+        if (is_dd_scaled(KIND)) {
             // per value: the maximum over groups, then (score - max) * log2e in place (a thread owns its value's column;
             // padded groups stay -inf)
             const int vdim = feats.f[0].vdim;
@@ -411,7 +415,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                 }
             }
 
-            if (KIND == kKindDdScaled) {
+            if (is_dd_scaled(KIND)) {
                 // gather + exp + pair sums fused below (the sampler of this kind reads the block's table itself)
             } else if (kSingle) {
                 const uint32_t xb = load_value(KIND == kKindNichPacked ? DIST_B200_NICH : KIND, feats.f[0].column, row);
@@ -531,12 +535,12 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                 }
             }
 
-            if (kSample && KIND == kKindDdScaled) {
+            if (kSample && is_dd_scaled(KIND)) {
                 // One gather + MUFU.EX2 per cell; likelihoods are kept as PAIR sums, in four contiguous segments
                 // (four independent chains for the total and for the walk `t -= l; stop at t <= 0`, random.hpp:315-333).
                 // The walk stops on a pair; the pair's first likelihood is then recomputed (one more gather) to place the
                 // stop inside it.  Sign-bit counting as everywhere: an exact +0 continues (a near-tie).
-                const int vdim = feats.f[0].vdim;
+                const int vdim = KIND == kKindDdScaled16 ? 16 : feats.f[0].vdim;
                 const int vi = min(static_cast<int>(load_value(DIST_B200_DD, feats.f[0].column, row)), vdim - 1);
                 const float *pb = caches + vi;
                 constexpr int PAIRS = CHUNK / 2, SEGP = PAIRS / 4;

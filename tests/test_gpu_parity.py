@@ -232,7 +232,7 @@ def test_accumulate_semantic(ctx, oracle, golden, name):
     np.testing.assert_array_equal(acc, got[0])
 
 
-@pytest.mark.parametrize("G", [1, 2, 31, 32, 33, 64, 100, 128, 129, 257, 1000])
+@pytest.mark.parametrize("G", [1, 2, 31, 32, 33, 64, 70, 90, 100, 110, 128, 129, 257, 1000])
 @pytest.mark.parametrize("name", ["nich", "gp", "bb", "dd"])
 def test_group_count_tiers(ctx, oracle, name, G):
     """ragged group counts across every register-tile / multi-chunk tier, ragged row counts"""
