@@ -339,6 +339,9 @@ class Bench:
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
         self.ctx = capi.Context(self.local_rank)
+        for kv in getattr(args, "option", None) or []:  # A/B runs only: dist_b200_ctx_set_option
+            k, v = kv.split("=")
+            self.ctx.set_option(int(k), int(v))
         self.flush = torch.empty(256 * 1024 * 1024 // 4, device=self.dev, dtype=torch.float32)  # > 126 MB L2
         self.stream = torch.cuda.current_stream().cuda_stream
         self.peaks = Peaks(self.ctx)
@@ -654,6 +657,7 @@ def main():
                     help="N > 1 only: time just c3_crosscat feature-sharded in this mode (development runs)")
     ap.add_argument("--row-shards", type=int, default=1, help="with --feature-sharded push: feature x row hybrid")
     ap.add_argument("--tile-rows", type=int, default=65536, help="row tile of the feature-sharded reduce-scatter")
+    ap.add_argument("--option", action="append", metavar="K=V", help="A/B runs: dist_b200_ctx_set_option(K, V) before anything runs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

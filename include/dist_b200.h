@@ -80,6 +80,8 @@ typedef enum {
     DIST_B200_OPT_NICH_PACKED = 6, /* nich single feature: 0 = default (packed fp32x2; sampling-only G > 128: two rows per thread),
                                       1 = scalar loop (round 1), 2 = packed fp32x2 loop with one row per thread */
     DIST_B200_OPT_NIW_DEBUG = 7,   /* profiling only, results are WRONG when set: 1 = skip the fused sampling walk, 2 = also the epilogue math */
+    DIST_B200_OPT_HOST_ZEROCOPY = 8, /* host-buffer entry with page-locked caller buffers: 0 = kernels read / write the host buffers
+                                      directly (one launch, no staging), 1 = staged row chunks over two streams (round 1) */
     DIST_B200_OPT_COUNT_ = 16
 } dist_b200_option;
 int dist_b200_ctx_set_option(dist_b200_ctx *ctx, int option, int value);
