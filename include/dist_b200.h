@@ -356,8 +356,12 @@ int dist_b200_sample_from_slots(dist_b200_ctx *ctx, const float *slots_dev, int 
                                 size_t n_rows, int G, const float *u_dev, int32_t *assign_dev, void *stream);
 
 /* ---- host-buffer forms: the call a reference-side binding makes.  Same
- * semantics with HOST pointers; inputs are staged through pinned memory, copied to the device,
- * scored there, and results copied back before returning. */
+ * semantics with HOST pointers, results on the host before returning.  Pageable buffers are staged through the
+ * context's page-locked area in row chunks over two streams (H2D of chunk k+1 and D2H of chunk k-1 under the kernel of
+ * chunk k).  Buffers that are ALL page-locked already (cudaHostAlloc / cudaHostRegister / torch pin_memory) are not
+ * copied at all: the kernels read the rows from and write the assignments to host memory directly (one launch; the
+ * PCIe transfers overlap the math row tile by row tile) -- except with a niw feature, whose pack kernel has no math to
+ * hide the reads behind.  dist_b200_score_value_host (per value) always goes through page-locked memory this way. */
 int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_feature *const *features,
                                       int n_features, const void *const *columns_host, size_t n_rows,
                                       const float *prior_host, const float *u_host, int32_t *assign_host,
