@@ -1859,8 +1859,12 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
     // five chunks measured best at 1M rows (DIST_B200_OPT_HOST_CHUNKS overrides it for A/B runs)
     const size_t max_chunks = ctx->opt[DIST_B200_OPT_HOST_CHUNKS] > 0 ? static_cast<size_t>(ctx->opt[DIST_B200_OPT_HOST_CHUNKS]) : 5;
     size_t nchunks = std::min<size_t>(max_chunks, std::max<size_t>(1, N / min_chunk));
-    for (int f = 0; f < F; ++f)  // paths that materialise through the context's single scores buffer: no overlap
-        if (features[f]->model == DIST_B200_NIW || (features[f]->model == DIST_B200_DPD && F > 1)) nchunks = 1;
+    // niw launches share the context's packed-row buffer and mixed dpd lists its single scores buffer: their kernels stay
+    // on ONE stream in chunk order; only the H2D copies of the later chunks run ahead on the second stream
+    bool one_compute_stream = false;
+    for (int f = 0; f < F; ++f)
+        if (features[f]->model == DIST_B200_NIW || (features[f]->model == DIST_B200_DPD && F > 1)) one_compute_stream = true;
+    if (one_compute_stream && scores_host) nchunks = 1;
     // chunk boundaries: equal interior chunks, half-size first and last ones -- the first H2D copy and the
     // last D2H copy are the only transfers no kernel hides
     std::vector<size_t> bounds(1, 0);
@@ -1880,6 +1884,53 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
     bounds.push_back(N);
     std::vector<const void *> cols(F);
     float *scores_dev = scores_host ? reinterpret_cast<float *>(dev + scores_off) : nullptr;
+    if (one_compute_stream && bounds.size() > 2) {
+        // copies of all chunks on the second stream, one event each; the kernels follow on the first stream
+        std::vector<cudaEvent_t> ready(bounds.size() - 1, nullptr);
+        auto cleanup = [&]() {
+            cudaStreamSynchronize(st[0]);
+            cudaStreamSynchronize(st[1]);
+            for (cudaEvent_t e : ready)
+                if (e) cudaEventDestroy(e);
+        };
+        cudaError_t ce = cudaSuccess;
+        for (size_t k = 0; k + 1 < bounds.size() && ce == cudaSuccess; ++k) {
+            const size_t lo = bounds[k], n = bounds[k + 1] - lo;
+            for (int f = 0; f < F && ce == cudaSuccess; ++f) {
+                const size_t vb = value_bytes(features[f]);
+                const char *src = static_cast<const char *>(columns_host[f]) + vb * lo;
+                if (!col_pinned[f]) {
+                    std::memcpy(pin + col_off[f] + vb * lo, src, vb * n);
+                    src = pin + col_off[f] + vb * lo;
+                }
+                ce = cudaMemcpyAsync(dev + col_off[f] + vb * lo, src, vb * n, cudaMemcpyHostToDevice, st[1]);
+            }
+            const char *src = reinterpret_cast<const char *>(u_host + lo);
+            if (!u_pinned) {
+                std::memcpy(pin + u_off + 4 * lo, src, 4 * n);
+                src = pin + u_off + 4 * lo;
+            }
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(dev + u_off + 4 * lo, src, 4 * n, cudaMemcpyHostToDevice, st[1]);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventRecord(ready[k], st[1]);
+        }
+        for (size_t k = 0; k + 1 < bounds.size() && ce == cudaSuccess && rc == DIST_B200_OK; ++k) {
+            const size_t lo = bounds[k], n = bounds[k + 1] - lo;
+            if (n == 0) continue;
+            ce = cudaStreamWaitEvent(st[0], ready[k], 0);
+            for (int f = 0; f < F; ++f) cols[f] = dev + col_off[f] + value_bytes(features[f]) * lo;
+            if (ce == cudaSuccess)
+                rc = score_dispatch(ctx, features, F, cols.data(), n, prior_dev, reinterpret_cast<const float *>(dev + u_off) + lo,
+                                    reinterpret_cast<int32_t *>(dev + assign_off) + lo, nullptr, 0, st[0]);
+        }
+        int32_t *adst = assign_pinned ? assign_host : reinterpret_cast<int32_t *>(pin + assign_off);
+        if (ce == cudaSuccess && rc == DIST_B200_OK) ce = cudaMemcpyAsync(adst, dev + assign_off, 4 * N, cudaMemcpyDeviceToHost, st[0]);
+        cleanup();
+        if (rc) return rc;
+        if (ce != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("score_sample_host: ") + cudaGetErrorString(ce));
+        if (!assign_pinned) std::memcpy(assign_host, pin + assign_off, sizeof(int32_t) * N);
+        return DIST_B200_OK;
+    }
     for (size_t k = 0; k + 1 < bounds.size(); ++k) {
         const size_t lo = bounds[k], n = bounds[k + 1] - lo;
         if (n == 0) continue;

@@ -42,7 +42,7 @@ def dev(a):
 
 def model_id(name):
     from distributions_b200 import capi
-    return {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH}[name]
+    return {"dd": capi.DD, "dpd": capi.DPD, "bb": capi.BB, "gp": capi.GP, "nich": capi.NICH, "niw": capi.NIW, "bnb": capi.BNB}[name]
 
 
 def envelope(oracle, w):
@@ -626,6 +626,45 @@ def test_host_entry_pinned_and_chunked(ctx, oracle):
     assert np.array_equal(assign, a_dev)
     assign2, _ = ctx.score_sample_batch_host([f], [w["values"]], prior, w["u"])  # pageable: staged
     assert np.array_equal(assign2, a_dev)
+
+
+def test_host_entry_niw_chunked(ctx, oracle):
+    """niw through the host-buffer entry: the H2D copies of later row chunks run ahead on the second stream while the
+    kernels stay on one (they share the context's packed-row buffer) -- pinned and pageable buffers, staged option too;
+    identical to the device-pointer path"""
+    from distributions_b200 import capi
+    n, G = 200_000, 24
+    w = synth.niw(16, G, n, d=32)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    f = ctx.feature(capi.NIW).update_all(w)
+    a_dev, _ = run_cuda(ctx, [w], prior, w["u"], n, want_scores=False)
+    pv = torch.from_numpy(w["values"]).pin_memory()
+    pu = torch.from_numpy(w["u"]).pin_memory()
+    pa = torch.empty(n, dtype=torch.int32).pin_memory()
+    assign, _ = ctx.score_sample_batch_host([f], [pv.numpy()], prior, pu.numpy(), assign_out=pa.numpy())
+    assert np.array_equal(assign, a_dev)
+    assign2, _ = ctx.score_sample_batch_host([f], [w["values"]], prior, w["u"])
+    assert np.array_equal(assign2, a_dev)
+
+
+def test_host_entry_staged_option(ctx, oracle):
+    """DIST_B200_OPT_HOST_ZEROCOPY = 1 (A/B runs): page-locked caller buffers through the staged chunk pipeline == zero-copy"""
+    from distributions_b200 import capi
+    n, G = 150_000, 200
+    w = synth.nich(17, G, n)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    f = ctx.feature(capi.NICH).update_all(w)
+    pv = torch.from_numpy(w["values"]).pin_memory()
+    pu = torch.from_numpy(w["u"]).pin_memory()
+    pa = torch.empty(n, dtype=torch.int32).pin_memory()
+    zc, _ = ctx.score_sample_batch_host([f], [pv.numpy()], prior, pu.numpy(), assign_out=pa.numpy())
+    zc = zc.copy()
+    ctx.set_option(capi.OPT_HOST_ZEROCOPY, 1)
+    try:
+        staged, _ = ctx.score_sample_batch_host([f], [pv.numpy()], prior, pu.numpy(), assign_out=pa.numpy())
+    finally:
+        ctx.set_option(capi.OPT_HOST_ZEROCOPY, 0)
+    assert np.array_equal(zc, staged)
 
 
 def test_crosscat_gp_table_and_fallback(ctx, oracle):
