@@ -26,12 +26,15 @@
 // (profiles/r02_c5_niw_v1_lds_bound.txt).  -b is split like W, and both of its terms sit in the hi image (columns 32 and
 // 33, against two copies of the constant in A), so the augmented k-step is ONE MMA: 7 MMAs per (tile, block) = two k-steps x
 // {hi hi, lo hi, hi lo} + the augmented hi hi; the lo images stop at K = 32.  3xTF32 (round 1) needed 12 at twice the bytes.
+// W = L^-1 is LOWER TRIANGULAR: the k-step over x[16..32) only feeds the upper 16 dims of every group.  The B rows
+// (= accumulator columns) are ordered (low dims of the 8 groups | high dims of the 8 groups), and that k-step's three
+// MMAs run with N = 128 on columns [128, 256): 5.5 MMA-equivalents per (tile, block).
 //
 // Schedule (per CTA, one per SM, persistent over chunks of kChunkTiles row tiles; 18 warps):
 //   warp 0 (one lane)  loader   -- cp.async.bulk of the chunk's A images (resident for the whole chunk) and of the
 //                                  32 block records {W_hi, W_lo, constants} through a 2-stage ring
-//   warp 1 (one lane)  issuer   -- for every block, for every resident tile: 7 x tcgen05.mma, tcgen05.commit
-//   warps 2..17        epilogue -- four warps per TMEM lane quarter, each owns 64 accumulator columns (two groups):
+//   warp 1 (one lane)  issuer   -- for every block, for every resident tile: 7 x tcgen05.mma (three of them N = 128), tcgen05.commit
+//   warps 2..17        epilogue -- four warps per TMEM lane quarter, each owns two groups (2 x 32 accumulator columns):
 //                                  tcgen05.ld, sums of squares on packed fp32x2, MUFU.LG2, the score; per row an ONLINE
 //                                  (max, sum of exp) pair; the chunk's scores go to a per-CTA scratch block
 //                                  (512 KB, reused every chunk: it lives in L2; pair-major, so a warp stores and later
@@ -41,10 +44,12 @@
 // the rows for every block (8 GB) and round-tripped 2 GB of scores through HBM for a separate sampler.
 // Without a sampler request (score_batch, accumulate, mixed feature lists) the same kernel writes [N][G] scores.
 //
-// What bounds it (profiles/r02_c5_power.txt): the board's 1 000 W power cap.  nvidia-smi during back-to-back launches shows
-// sw_power_cap active and the SM clock at 1.65 - 1.73 GHz instead of 1.965; with the MMAs alone (debug 4) the kernel runs at
-// the tensor pipe's rate for 7 MMAs per (tile, block).  Every removed MMA, shared-memory operand read or L2 round trip is
-// therefore time: 8 -> 7 MMAs, K = 32 lo images and whole-line scratch accesses took the kernel from 1.97 to 1.55 ms.
+// What bounds it (profiles/r02_c5_power.txt): launched back to back, the board's 1 000 W power cap -- nvidia-smi shows
+// sw_power_cap active and the SM clock at 1.65 - 1.8 GHz instead of 1.965; with the MMAs alone (debug 4) the kernel runs at
+// the tensor pipe's rate.  Every removed MMA, shared-memory operand read, L2 round trip or instruction is therefore time:
+// 8 -> 7 -> 5.5 MMAs, K = 32 lo images, whole-line scratch accesses, and an epilogue without per-tile overhead (the profiling
+// modes are template instantiations: as runtime branches they cost 27 % of all executed instructions) took the kernel from
+// 1.97 to 1.22 ms (profiles/r02_c5_niw_fused.txt).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
