@@ -466,11 +466,23 @@ class _NiwMixture(_Mixture):
         vals = np.ascontiguousarray(values, np.float32).reshape(-1, shared.dim)
         return self.ctx.score_sample_batch_host([self.feature], [vals], prior, np.ascontiguousarray(u, np.float32), want_scores)
 
-    def score_data(self, shared):
-        raise NotImplementedError("niw score_data is not on the device (statistics stay on the host)")
+    def _pack_shared(self, s):  # kappa, nu, mu[d], psi[d][d]
+        return np.concatenate([[s.kappa, s.nu], np.asarray(s.mu, np.float32).ravel(), np.asarray(s.psi, np.float32).ravel()]).astype(np.float32)
 
-    score_data_grid = score_data
-    add_values = None
+    def add_values(self, shared, values, groupids):
+        """batched add_value (niw.hpp:247-255) as a per-group SYRK on the device, then the Groups are read back"""
+        vals = np.ascontiguousarray(values, np.float32).reshape(-1, shared.dim)
+        self.ctx.add_rows_batch_host([self.feature], [vals], groupids)
+        self._pull_groups(shared)
+
+    def _pull_groups(self, s):
+        G, d = len(self.groups), s.dim
+        raw = self.feature.download_stats(4 * G * (1 + d + d * d))
+        cnt = raw[:4 * G].view(np.int32)
+        sx = raw[4 * G:4 * G * (1 + d)].view(np.float32).reshape(G, d)
+        sxx = raw[4 * G * (1 + d):].view(np.float32).reshape(G, d, d)
+        for i, g in enumerate(self.groups):
+            g.count, g.sum_x, g.sum_xxT = int(cnt[i]), sx[i].copy(), sxx[i].copy()
 
 
 class MixtureIdTracker:

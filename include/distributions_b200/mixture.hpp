@@ -21,7 +21,7 @@
 // bookkeeping); every score -- per value or batched -- is computed by the sm_100a
 // kernels behind the C-ABI.  There is no CPU scoring path here: a failed C-ABI call throws
 // std::runtime_error (the reference's DIST_THROW_ON_ERROR behaviour, common.hpp:49-67).
-// Not mirrored (off the path): Sampler, sample_value, score_data, protobuf, Group::merge, gp log_prod.
+// Not mirrored (off the path): Sampler, sample_value, protobuf, Group::merge, gp log_prod.
 #pragma once
 
 #include <dist_b200.h>
@@ -400,6 +400,25 @@ struct NormalInverseWishart {
     }
     static int update_group(dist_b200_feature * f, const Shared &, size_t groupid, const Group & g) {
         return dist_b200_feature_update_group(f, static_cast<int>(groupid), &g, nullptr);
+    }
+    static void pack_shared(const Shared & s, std::vector<float> & out) {  // score_data_grid layout: kappa, nu, mu[d], psi[d][d]
+        out.push_back(s.kappa);
+        out.push_back(s.nu);
+        out.insert(out.end(), s.mu, s.mu + dim_);
+        out.insert(out.end(), s.psi, s.psi + dim_ * dim_);
+    }
+    // device-resident statistics: count[G] | sum_x[G][d] | sum_xxT[G][d][d]
+    static size_t stats_bytes(const Shared &, size_t G) { return 4 * G * (1 + dim_ + dim_ * dim_); }
+    static void load_groups(const unsigned char * raw, const Shared &, std::vector<Group> & groups) {
+        const size_t G = groups.size();
+        const int32_t * cnt = reinterpret_cast<const int32_t *>(raw);
+        const float * sx = reinterpret_cast<const float *>(raw) + G;
+        const float * sxx = sx + G * dim_;
+        for (size_t g = 0; g < G; ++g) {
+            groups[g].count = cnt[g];
+            for (int i = 0; i < dim_; ++i) groups[g].sum_x[i] = sx[g * dim_ + i];
+            for (int i = 0; i < dim_ * dim_; ++i) groups[g].sum_xxT[i] = sxx[g * dim_ * dim_ + i];
+        }
     }
 };
 // ---------------------------------------------------------------------------------------------

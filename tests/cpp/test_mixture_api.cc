@@ -232,6 +232,35 @@ int main(int argc, char ** argv) {
                     for (int i = 0; i < 3; ++i) v.x[i] = static_cast<float>((r >> (5 * i)) % 32) * 0.25f - 4.f;
                     return v;
                 }, 1e-5f, "niw3");
+                {   // niw: batched add_values (per-group SYRK on the device) == the same add_value calls one by one, and
+                    // score_data (niw.hpp:296-308) over the device-resident statistics agrees between the two
+                    rng_t rng;
+                    Mixture<Niw> batched(ctx), single(ctx);
+                    batched.groups().resize(4);
+                    for (auto & g : batched.groups()) g.init(sh, rng);
+                    single.groups() = batched.groups();
+                    batched.init(sh, rng);
+                    single.init(sh, rng);
+                    std::vector<Niw::Value> vals(60);
+                    std::vector<int32_t> gid(60);
+                    unsigned state = 777u;
+                    for (size_t i = 0; i < vals.size(); ++i) {
+                        state = state * 1664525u + 1013904223u;
+                        for (int k = 0; k < 3; ++k) vals[i].x[k] = static_cast<float>((state >> (8 + 5 * k)) % 32) * 0.25f - 4.f;
+                        gid[i] = static_cast<int32_t>((state >> 4) % 3);  // the last group stays empty
+                        single.add_value(sh, gid[i], vals[i], rng);
+                    }
+                    batched.add_values(sh, vals.data(), gid.data(), vals.size());
+                    for (size_t g = 0; g < 4; ++g) {
+                        if (batched.groups(g).count != single.groups(g).count) ++bad;
+                        for (int k = 0; k < 9; ++k) {
+                            const float d = batched.groups(g).sum_xxT[k] - single.groups(g).sum_xxT[k];
+                            if (!(d < 1e-3f && d > -1e-3f)) ++bad;
+                        }
+                    }
+                    const float sa = batched.score_data(sh, rng), sb = single.score_data(sh, rng);
+                    if (!(sa == sa) || !(sa - sb < 1e-2f && sb - sa < 1e-2f) || !(sa < 0.f)) ++bad;
+                }
                 std::printf(bad ? "selfcheck FAILED %d\n" : "selfcheck ok%.0d\n", bad);
             } else if (line == "model dd") {
                 std::printf("model dd\n");
