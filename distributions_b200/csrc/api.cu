@@ -1811,15 +1811,7 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
     cudaStream_t st[2] = {ctx->own_stream, ctx->own_stream2};
     if ((rc = wait_ready(ctx, features, F, st[0]))) return rc;
     if ((rc = refresh_gp_tables(ctx, features, F, st[0]))) return rc;  // before the second stream starts reading them
-    if ((rc = wait_ready(ctx, features, F, st[1]))) return rc;
     const float *prior_dev = nullptr;
-    if (prior_host) {
-        std::memcpy(pin + prior_off, prior_host, sizeof(float) * G);
-        DISTB200_CUDA(ctx, cudaMemcpyAsync(dev + prior_off, pin + prior_off, sizeof(float) * G, cudaMemcpyHostToDevice, st[0]));
-        DISTB200_CUDA(ctx, cudaEventRecord(ctx->ev, st[0]));
-        DISTB200_CUDA(ctx, cudaStreamWaitEvent(st[1], ctx->ev, 0));
-        prior_dev = reinterpret_cast<const float *>(dev + prior_off);
-    }
     // Zero-copy: when every caller buffer is page-locked, the kernels read the rows straight from host memory and write
     // the assignments straight back (device-accessible under unified addressing): ONE launch, the PCIe transfers overlap
     // the math row tile by row tile with no chunking, no staging copies and no second stream.
@@ -1846,7 +1838,14 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
             if (ok) ok = cudaHostGetDevicePointer(&dp, assign_host, 0) == cudaSuccess;
             assign_zc = static_cast<int32_t *>(dp);
             if (ok) {
-                rc = score_dispatch(ctx, features, F, zc_cols.data(), N, prior_dev, u_zc, assign_zc, nullptr, 0, st[0]);
+                const float *prior_zc = nullptr;
+                if (prior_host) {  // the prior vector is re-read per table row by the dpd / dd kernels: it goes to the device
+                    std::memcpy(pin + prior_off, prior_host, sizeof(float) * G);
+                    if (cudaMemcpyAsync(dev + prior_off, pin + prior_off, sizeof(float) * G, cudaMemcpyHostToDevice, st[0]) != cudaSuccess)
+                        return fail(ctx, DIST_B200_ERR_CUDA, "score_sample_host: prior upload");
+                    prior_zc = reinterpret_cast<const float *>(dev + prior_off);
+                }
+                rc = score_dispatch(ctx, features, F, zc_cols.data(), N, prior_zc, u_zc, assign_zc, nullptr, 0, st[0]);
                 cudaError_t e = cudaStreamSynchronize(st[0]);
                 if (rc) return rc;
                 if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("score_sample_host: ") + cudaGetErrorString(e));
@@ -1854,6 +1853,14 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
             }
             cudaGetLastError();  // not mappable: fall through to the staged path
         }
+    }
+    if ((rc = wait_ready(ctx, features, F, st[1]))) return rc;
+    if (prior_host) {
+        std::memcpy(pin + prior_off, prior_host, sizeof(float) * G);
+        DISTB200_CUDA(ctx, cudaMemcpyAsync(dev + prior_off, pin + prior_off, sizeof(float) * G, cudaMemcpyHostToDevice, st[0]));
+        DISTB200_CUDA(ctx, cudaEventRecord(ctx->ev, st[0]));
+        DISTB200_CUDA(ctx, cudaStreamWaitEvent(st[1], ctx->ev, 0));
+        prior_dev = reinterpret_cast<const float *>(dev + prior_off);
     }
     const size_t min_chunk = 32768;
     // five chunks measured best at 1M rows (DIST_B200_OPT_HOST_CHUNKS overrides it for A/B runs)

@@ -62,6 +62,19 @@ __global__ void __launch_bounds__(kNrThreads, 2) nich_rows_kernel(const NichRows
     const uint64_t one2 = f2_pack(1.f, 1.f), l2e2 = f2_pack(kLog2e, kLog2e);
     const size_t tile_rows = static_cast<size_t>(kNrThreads) * kNrRows;
     const size_t ntiles = (a.N + tile_rows - 1) / tile_rows;
+    // the next tile's rows are requested while the current tile is evaluated (2 048 cells per row: the load latency --
+    // HBM, or PCIe when the host entry hands the kernel page-locked host buffers -- disappears behind them)
+    float xnext[kNrRows], unext[kNrRows];
+    auto fetch = [&](size_t tile) {
+#pragma unroll
+        for (int r = 0; r < kNrRows; ++r) {
+            const size_t rw = tile * tile_rows + static_cast<size_t>(r) * kNrThreads + tid;
+            const size_t rr = rw < a.N ? rw : a.N - 1;  // clamp: compute on a real row, discard the result
+            xnext[r] = __ldg(a.values + rr);
+            unext[r] = __ldg(a.u + rr);
+        }
+    };
+    if (blockIdx.x < ntiles) fetch(blockIdx.x);
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         size_t row[kNrRows];
         uint64_t x2[kNrRows];
@@ -69,11 +82,10 @@ __global__ void __launch_bounds__(kNrThreads, 2) nich_rows_kernel(const NichRows
 #pragma unroll
         for (int r = 0; r < kNrRows; ++r) {
             row[r] = tile * tile_rows + static_cast<size_t>(r) * kNrThreads + tid;
-            const size_t rr = row[r] < a.N ? row[r] : a.N - 1;  // clamp: compute on a real row, discard the result
-            const float x = a.values[rr];
-            x2[r] = f2_pack(x, x);
-            urow[r] = a.u[rr];
+            x2[r] = f2_pack(xnext[r], xnext[r]);
+            urow[r] = unext[r];
         }
+        if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
         float slot_m[kNrRows], slot_s[kNrRows];
 #pragma unroll
         for (int r = 0; r < kNrRows; ++r) {
