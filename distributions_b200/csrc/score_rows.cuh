@@ -559,7 +559,10 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                 const float p1 = seg[0], p2 = p1 + seg[1], p3 = p2 + seg[2];
                 const float t0 = (p3 + seg[3]) * urow;
                 float t[4] = {t0, t0 - p1, t0 - p2, t0 - p3};
-                float last[4] = {t[0], t[1], t[2], t[3]};  // the draw left in front of the first pair that is not passed
+                // the draw left in front of the first pair that is not passed = the smallest t >= +0 seen so far.  As unsigned
+                // integers the non-negative floats keep their order and every negative one is larger than all of them: one
+                // unsigned min per pair (a segment that starts at t < 0 is never the stopping one, its value is unused)
+                unsigned last[4] = {__float_as_uint(t[0]), __float_as_uint(t[1]), __float_as_uint(t[2]), __float_as_uint(t[3])};
                 unsigned neg[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int k = 0; k < SEGP; ++k) {
@@ -567,7 +570,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                     for (int q = 0; q < 4; ++q) {
                         t[q] -= p[q * SEGP + k];
                         neg[q] += __float_as_uint(t[q]) >> 31;
-                        last[q] = (__float_as_uint(t[q]) >> 31) ? last[q] : t[q];
+                        last[q] = min(last[q], __float_as_uint(t[q]));
                     }
                 }
                 // pairs passed in front of the stop; a segment after the stopping one starts at t <= 0 and passes none
@@ -584,7 +587,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                         }
                     }
                 }
-                const float before = qs == 0 ? last[0] : (qs == 1 ? last[1] : (qs == 2 ? last[2] : last[3]));
+                const float before = __uint_as_float(qs == 0 ? last[0] : (qs == 1 ? last[1] : (qs == 2 ? last[2] : last[3])));
                 const int kp = min(passed, PAIRS - 1);
                 const float first = mufu_ex2(pb[(2 * kp) * vdim]);
                 const int idx = 2 * kp + ((before - first > 0.f) ? 1 : 0);
