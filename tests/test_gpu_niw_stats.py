@@ -140,6 +140,29 @@ def test_niw_remove_rows_and_emptied_group(ctx, oracle):
     assert np.array_equal(f.download_stats(4 * G * (1 + d + d * d)), before)
 
 
+def test_niw_add_rows_skips_negative_ids_and_many_groups(ctx, oracle):
+    """negative / out-of-range group ids are skipped (as in every add_rows path); G beyond one scan thread per group"""
+    from distributions_b200 import capi
+    d, G, n = 4, 2500, 9000
+    w = synth.niw(3500, G, n, d=d)
+    rng = np.random.default_rng(9)
+    assign = rng.integers(0, G, n).astype(np.int32)
+    assign[::7] = -1
+    assign[3::11] = G + 5
+    f = ctx.feature(capi.NIW).update_all(w)
+    ctx.add_rows_batch([f], [dev(w["values"])], dev(assign), n)
+    count, sum_x, sum_xxT = stats_of(f, G, d)
+    valid = (assign >= 0) & (assign < G)
+    assert np.array_equal(count, w["count"] + np.bincount(assign[valid], minlength=G).astype(np.int32))
+    xs = w["sum_x"].astype(np.float64)
+    np.add.at(xs, assign[valid], w["values"][valid].astype(np.float64))
+    np.testing.assert_allclose(sum_x, xs, rtol=1e-6, atol=1e-4)
+    xx = w["sum_xxT"].astype(np.float64)
+    v = w["values"][valid].astype(np.float64)
+    np.add.at(xx, assign[valid], v[:, :, None] * v[:, None, :])
+    np.testing.assert_allclose(sum_xxT, xx, rtol=1e-6, atol=1e-3)
+
+
 def test_niw_row_shard_exchange(ctx, oracle):
     """two 'ranks' on one device: accumulate halves -> summed exchange block -> merge == add_rows over all rows"""
     from distributions_b200 import capi
