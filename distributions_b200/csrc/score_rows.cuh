@@ -803,8 +803,11 @@ static int launch_tiers(dist_b200_ctx *ctx, const FeatList &feats, const RowsArg
         }
         return launch_modes<128, KIND, 128>(ctx, feats, a, s);
     }
-    // measured at c2: 32-group tiles 0.748 ms, 64-group tiles 0.774 ms (DIST_B200_OPT_ROW_TILE for A/B runs)
-    if (ctx->opt[DIST_B200_OPT_ROW_TILE] == 64) return launch_modes<64, KIND, 256>(ctx, feats, a, s);
+    // measured at c2, sampling only: 32-group tiles 0.748 ms, 64-group tiles 0.774 ms; with the [N][G] scores also written
+    // (HBM-store bound): 32-group tiles 1.215 ms, 64-group tiles 1.098 ms -- a store instruction then covers 256-byte runs of
+    // a row instead of 128-byte ones (DIST_B200_OPT_ROW_TILE = 32 / 64 forces either for A/B runs)
+    const int tile = ctx->opt[DIST_B200_OPT_ROW_TILE] ? ctx->opt[DIST_B200_OPT_ROW_TILE] : (a.scores ? 64 : 32);
+    if (tile == 64) return launch_modes<64, KIND, 256>(ctx, feats, a, s);
     return launch_modes<32, KIND, 256>(ctx, feats, a, s);
 }
 
