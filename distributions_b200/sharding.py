@@ -137,6 +137,14 @@ def row_sharded_update(accumulate, merge, xchg, sign=+1, group=None):
     return xchg
 
 
+def recommended_row_shards(world):
+    """row_shards for PeerFeatureShards on `world` GPUs of one NVLink domain, from the measured c3 strong scaling
+    (profiles/r02_bench/bench_n{2,4,8}.json): two feature shards per group hide the push completely (0.96 at 2 GPUs) and
+    send (world / 2) x fewer bytes than pure feature sharding, whose per-lane remote stores top out at 210-340 GB/s
+    (0.69 at 4 GPUs, 0.34 at 8); 2 x 2 reaches 0.88, 2 x 4 0.83."""
+    return max(1, world // 2)
+
+
 class PeerFeatureShards:
     """Feature shards with the reduction fused into the score kernel over NVLink peer memory.
 

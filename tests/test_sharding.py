@@ -135,3 +135,8 @@ def test_row_sharded_update_replicas_agree(tmp_path):
     for r in range(world):
         d = np.load(os.path.join(str(tmp_path), "upd%d.npz" % r))
         assert np.array_equal(d["count"], count) and np.array_equal(d["sum"], total)
+
+
+def test_recommended_row_shards():
+    from distributions_b200 import sharding
+    assert [sharding.recommended_row_shards(w) for w in (1, 2, 4, 8)] == [1, 1, 2, 4]
