@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdist_b200.so")
 
 DD, DPD, BB, GP, NICH, NIW, BNB = 0, 1, 2, 3, 4, 5, 6
 # dist_b200_option
-OPT_VALUE_CDF, OPT_ROW_TILE, OPT_HOST_CHUNKS, OPT_NIW_PATH, OPT_TABLE_KERNEL, OPT_SMALL_TILE, OPT_NICH_PACKED, OPT_NIW_DEBUG, OPT_HOST_ZEROCOPY = range(9)
+OPT_VALUE_CDF, OPT_ROW_TILE, OPT_HOST_CHUNKS, OPT_NIW_PATH, OPT_TABLE_KERNEL, OPT_SMALL_TILE, OPT_NICH_PACKED, OPT_NIW_DEBUG, OPT_HOST_ZEROCOPY, OPT_EXP_OFFLOAD = range(10)
 MODEL_NAMES = {DD: "dd", DPD: "dpd", BB: "bb", GP: "gp", NICH: "nich", NIW: "niw", BNB: "bnb"}
 COLUMN_DTYPE = {DD: np.int32, DPD: np.uint32, BB: np.uint8, GP: np.uint32, NICH: np.float32, NIW: np.float32, BNB: np.uint32}
 

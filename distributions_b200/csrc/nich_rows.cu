@@ -9,7 +9,11 @@
 // read with up to 32-way bank conflicts (every lane its own slot, all slots at the same bank offset).  Here
 //   * every thread carries TWO rows, so a group's parameters are loaded once per two cells (half the wavefronts);
 //   * the block's parameter copy is skewed by 16 bytes per slot, so the lanes of the re-score pass, which sit in
-//     different slots, mostly hit different banks.
+//     different slots, mostly hit different banks;
+//   * 6 of every 16 pairs of softmax exponentials are evaluated on the FMA pipe (poly_ex2_pair, numerics.cuh): with two
+//     MUFU per cell (LG2 + EX2) the kernel sat at 89 % XU-pipe activity while the FMA pipe idled at 20 %
+//     (profiles/r02_c2_nich_rows.txt); same-box A/B 0.571 -> 0.521 ms;
+//   * rows are dealt to the blocks in half-tiles, so the per-SM loads differ by half a tile (see the kernel).
 // Cell arithmetic is the packed fp32x2 form of nich.cc:59-65 (see accumulate_feature, kKindNichPacked): two groups per
 // FADD2 / FMUL2 / FFMA2, every product and sum rounded as the reference's unfused expression.
 #include "score_rows.cuh"
@@ -19,6 +23,7 @@ namespace distb200 {
 constexpr int kNrThreads = 256;
 constexpr int kNrChunk = 32;
 constexpr int kNrRows = 2;  // rows per thread
+constexpr int kNrPolyDefault = 6;  // pairs of every 16 whose exp2 runs on the FMA pipe (poly_ex2_pair)
 
 struct NichRowsArgs {
     int G;
@@ -30,17 +35,146 @@ struct NichRowsArgs {
     int32_t *assign;
 };
 
+// geometry of the block-private parameter copy and the per-row slot pairs
+struct NichGeom {
+    int G, nchunks, cps, nslots, slot_groups;
+    const float4 *caches;  // pair p of groups at float4 index 2 p + (2 p) / slot_groups (one float4 of skew per slot)
+    float2 *slots;         // [R][kSlots][kNrThreads] {negated scaled max, sum}
+};
+
+// R rows per thread (row r of the thread = half-tile r of the tile: 256 consecutive rows) against all groups, then the
+// draw.  R = 2 is the steady state; R = 1 evaluates a block's odd last half-tile at half the cost (see the kernel).
+template <int kPoly, int R>
+__device__ __forceinline__ void nich_tile(const NichGeom &g, const float (&xrow)[R], const float (&urow)[R], const size_t (&row)[R],
+                                          size_t N, int32_t *__restrict__ assign) {
+    const int tid = threadIdx.x;
+    const uint64_t one2 = f2_pack(1.f, 1.f), l2e2 = f2_pack(kLog2e, kLog2e);
+    uint64_t x2[R];
+    float slot_m[R], slot_s[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        x2[r] = f2_pack(xrow[r], xrow[r]);
+        slot_m[r] = INFINITY;  // negated scaled max of the slot being merged
+        slot_s[r] = 0.f;
+    }
+    // one 32-group tile of one row: acc[j] = prior + score + log_coeff * fast_log(1 + precision * (x - mean)^2)
+    auto score_tile = [&](const float4 *p4, int r, float (&acc)[kNrChunk]) {
+#pragma unroll
+        for (int j = 0; j < kNrChunk; j += 2) {
+            const float4 qa = p4[j], qb = p4[j + 1];
+            const uint64_t d2 = f2_add(x2[r], f2_pack(qa.x, qa.y));
+            const uint64_t z2 = f2_fma(f2_mul(f2_pack(qa.z, qa.w), f2_mul(d2, d2)), one2, one2);  // unfused 1 + w (see score_rows.cuh)
+            float za, zb;
+            f2_unpack(z2, za, zb);
+            f2_unpack(f2_fma(f2_pack(qb.x, qb.y), f2_pack(fast_log2_cell(za), fast_log2_cell(zb)), f2_pack(qb.z, qb.w)), acc[j], acc[j + 1]);
+        }
+    };
+    for (int c = 0; c < g.nchunks; ++c) {
+        const float4 *p4 = g.caches + c * kNrChunk + c / g.cps;
+        float acc[R][kNrChunk];
+#pragma unroll
+        for (int j = 0; j < kNrChunk; j += 2) {  // parameters once, all rows
+            const float4 qa = p4[j], qb = p4[j + 1];
+            const uint64_t nm2 = f2_pack(qa.x, qa.y), pr2 = f2_pack(qa.z, qa.w), co2 = f2_pack(qb.x, qb.y), sc2 = f2_pack(qb.z, qb.w);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint64_t d2 = f2_add(x2[r], nm2);
+                const uint64_t z2 = f2_fma(f2_mul(pr2, f2_mul(d2, d2)), one2, one2);
+                float za, zb;
+                f2_unpack(z2, za, zb);
+                f2_unpack(f2_fma(co2, f2_pack(fast_log2_cell(za), fast_log2_cell(zb)), sc2), acc[r][j], acc[r][j + 1]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float m = acc[r][0];
+#pragma unroll
+            for (int j = 1; j < kNrChunk; ++j) m = fmaxf(m, acc[r][j]);
+            const float nm = -m * kLog2e;  // rounded once: every later rescale is a difference of these values
+            const uint64_t nm2 = f2_pack(nm, nm);
+            uint64_t s2 = f2_pack(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < kNrChunk; j += 2) {
+                const uint64_t e2 = f2_fma(f2_pack(acc[r][j], acc[r][j + 1]), l2e2, nm2);
+                if (((j / 2) * kPoly) % 16 < kPoly) {  // kPoly of 16 pairs, evenly spread between the MUFU pairs
+                    s2 = f2_add(s2, poly_ex2_pair(e2));
+                } else {
+                    float ea, eb;
+                    f2_unpack(e2, ea, eb);
+                    s2 = f2_add(s2, f2_pack(mufu_ex2(ea), mufu_ex2(eb)));
+                }
+            }
+            float se, so;
+            f2_unpack(s2, se, so);
+            const float s = se + so;
+            const float dlt = slot_m[r] - nm;
+            const float e = mufu_ex2(-fabsf(dlt));
+            slot_s[r] = dlt > 0.f ? fmaf(slot_s[r], e, s) : fmaf(s, e, slot_s[r]);
+            slot_m[r] = fminf(slot_m[r], nm);
+            if ((c + 1) % g.cps == 0 || c + 1 == g.nchunks) {
+                g.slots[(r * kSlots + c / g.cps) * kNrThreads + tid] = make_float2(slot_m[r], slot_s[r]);
+                slot_m[r] = INFINITY;
+                slot_s[r] = 0.f;
+            }
+        }
+    }
+    // per row: total over the slots, walk to the slot holding u * total, re-score that slot, walk its cells
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float2 *sl = g.slots + (r * kSlots) * kNrThreads + tid;
+        float mm = INFINITY;
+        for (int k = 0; k < g.nslots; ++k) mm = fminf(mm, sl[k * kNrThreads].x);
+        float total = 0.f;
+        for (int k = 0; k < g.nslots; ++k) {
+            const float2 ms = sl[k * kNrThreads];
+            const float w = ms.y * mufu_ex2(mm - ms.x);
+            sl[k * kNrThreads].y = w;
+            total += w;
+        }
+        float t = total * urow[r];
+        int sel = g.nslots - 1;
+        for (int k = 0; k < g.nslots; ++k) {
+            const float w = sl[k * kNrThreads].y;
+            if (t <= w) {
+                sel = k;
+                break;
+            }
+            if (k + 1 < g.nslots) t -= w;
+        }
+        int count = 0;
+        for (int cc = 0; cc < g.cps; ++cc) {
+            const int c = sel * g.cps + cc;
+            if (c >= g.nchunks) break;
+            float acc[kNrChunk];
+            score_tile(g.caches + c * kNrChunk + sel, r, acc);
+#pragma unroll
+            for (int j = 0; j < kNrChunk; ++j) {
+                t -= mufu_ex2(fmaf(acc[j], kLog2e, mm));
+                count += 1 - static_cast<int>(__float_as_uint(t) >> 31);  // t >= +0 continues (an exact 0: a near-tie)
+            }
+        }
+        if (row[r] < N) assign[row[r]] = min(sel * g.slot_groups + count, g.G - 1);
+    }
+}
+
+// Work split: the rows are cut into HALF-TILES of 256 (one row per thread) and every block takes a contiguous run of
+// them, as even as the count allows (the runs differ by at most one half-tile).  A block evaluates its run two
+// half-tiles at a time (two rows per thread) and an odd last one alone at half the cost, so the blocks' loads differ by
+// half a tile at most instead of a whole one: at c2 (1M rows, 296 blocks: 13.2 half-tiles per block) the slowest SM
+// runs 13.5 tile-halves instead of 14.
+template <int kPoly>
 __global__ void __launch_bounds__(kNrThreads, 2) nich_rows_kernel(const NichRowsArgs a) {
     extern __shared__ __align__(16) float smem[];
-    const int G = a.G;
-    const int nchunks = (G + kNrChunk - 1) / kNrChunk;
-    const int Gpad = nchunks * kNrChunk;
-    const int cps = (nchunks + kSlots - 1) / kSlots;           // chunks per slot
-    const int nslots = (nchunks + cps - 1) / cps;
-    const int slot_groups = cps * kNrChunk;
-    // caches: pair p of groups at float4 index 2 p + (2 p) / slot_groups (one float4 of skew per slot)
+    NichGeom g;
+    g.G = a.G;
+    g.nchunks = (a.G + kNrChunk - 1) / kNrChunk;
+    const int Gpad = g.nchunks * kNrChunk;
+    g.cps = (g.nchunks + kSlots - 1) / kSlots;  // chunks per slot
+    g.nslots = (g.nchunks + g.cps - 1) / g.cps;
+    g.slot_groups = g.cps * kNrChunk;
     float4 *caches = reinterpret_cast<float4 *>(smem);
-    float2 *slots = reinterpret_cast<float2 *>(caches + Gpad + nslots);
+    g.caches = caches;
+    g.slots = reinterpret_cast<float2 *>(caches + Gpad + g.nslots);
     const int tid = threadIdx.x;
 
     // block-private parameter copy: prior folded into the score, padded groups -inf (they borrow group 0's mean /
@@ -49,143 +183,66 @@ __global__ void __launch_bounds__(kNrThreads, 2) nich_rows_kernel(const NichRows
         float4 q[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const int g = 2 * p + k;
-            q[k] = a.params[g < G ? g : 0];
-            q[k].w = g < G ? q[k].w + (a.prior ? a.prior[g] : 0.f) : -INFINITY;
+            const int gi = 2 * p + k;
+            q[k] = a.params[gi < a.G ? gi : 0];
+            q[k].w = gi < a.G ? q[k].w + (a.prior ? a.prior[gi] : 0.f) : -INFINITY;
         }
-        const int at = 2 * p + (2 * p) / slot_groups;
+        const int at = 2 * p + (2 * p) / g.slot_groups;
         caches[at] = make_float4(-q[0].x, -q[1].x, q[0].y, q[1].y);
         caches[at + 1] = make_float4(q[0].z, q[1].z, q[0].w, q[1].w);
     }
     __syncthreads();
 
-    const uint64_t one2 = f2_pack(1.f, 1.f), l2e2 = f2_pack(kLog2e, kLog2e);
-    const size_t tile_rows = static_cast<size_t>(kNrThreads) * kNrRows;
-    const size_t ntiles = (a.N + tile_rows - 1) / tile_rows;
+    const size_t nhalf = (a.N + kNrThreads - 1) / kNrThreads;
+    const size_t base = nhalf / gridDim.x, rem = nhalf % gridDim.x;
+    const size_t h0 = blockIdx.x * base + (blockIdx.x < rem ? blockIdx.x : rem);
+    const size_t h1 = h0 + base + (blockIdx.x < rem ? 1 : 0);
     // the next tile's rows are requested while the current tile is evaluated (2 048 cells per row: the load latency --
     // HBM, or PCIe when the host entry hands the kernel page-locked host buffers -- disappears behind them)
     float xnext[kNrRows], unext[kNrRows];
-    auto fetch = [&](size_t tile) {
+    auto fetch = [&](size_t h) {
 #pragma unroll
         for (int r = 0; r < kNrRows; ++r) {
-            const size_t rw = tile * tile_rows + static_cast<size_t>(r) * kNrThreads + tid;
+            const size_t rw = (h + r) * kNrThreads + tid;
             const size_t rr = rw < a.N ? rw : a.N - 1;  // clamp: compute on a real row, discard the result
             xnext[r] = __ldg(a.values + rr);
             unext[r] = __ldg(a.u + rr);
         }
     };
-    if (blockIdx.x < ntiles) fetch(blockIdx.x);
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (h0 < h1) fetch(h0);
+    size_t h = h0;
+    for (; h + kNrRows <= h1; h += kNrRows) {
         size_t row[kNrRows];
-        uint64_t x2[kNrRows];
-        float urow[kNrRows];
+        float xrow[kNrRows], urow[kNrRows];
 #pragma unroll
         for (int r = 0; r < kNrRows; ++r) {
-            row[r] = tile * tile_rows + static_cast<size_t>(r) * kNrThreads + tid;
-            x2[r] = f2_pack(xnext[r], xnext[r]);
+            row[r] = (h + r) * kNrThreads + tid;
+            xrow[r] = xnext[r];
             urow[r] = unext[r];
         }
-        if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
-        float slot_m[kNrRows], slot_s[kNrRows];
-#pragma unroll
-        for (int r = 0; r < kNrRows; ++r) {
-            slot_m[r] = INFINITY;  // negated scaled max of the slot being merged
-            slot_s[r] = 0.f;
-        }
-        // one 32-group tile for both rows: acc[r][j] = prior + score + log_coeff * fast_log(1 + precision * (x - mean)^2)
-        auto score_tile = [&](const float4 *p4, int r, float (&acc)[kNrChunk]) {
-#pragma unroll
-            for (int j = 0; j < kNrChunk; j += 2) {
-                const float4 qa = p4[j], qb = p4[j + 1];
-                const uint64_t d2 = f2_add(x2[r], f2_pack(qa.x, qa.y));
-                const uint64_t z2 = f2_fma(f2_mul(f2_pack(qa.z, qa.w), f2_mul(d2, d2)), one2, one2);  // unfused 1 + w (see score_rows.cuh)
-                float za, zb;
-                f2_unpack(z2, za, zb);
-                f2_unpack(f2_fma(f2_pack(qb.x, qb.y), f2_pack(fast_log2_cell(za), fast_log2_cell(zb)), f2_pack(qb.z, qb.w)), acc[j], acc[j + 1]);
-            }
-        };
-        for (int c = 0; c < nchunks; ++c) {
-            const float4 *p4 = caches + c * kNrChunk + c / cps;
-            float acc[kNrRows][kNrChunk];
-#pragma unroll
-            for (int j = 0; j < kNrChunk; j += 2) {  // parameters once, both rows
-                const float4 qa = p4[j], qb = p4[j + 1];
-                const uint64_t nm2 = f2_pack(qa.x, qa.y), pr2 = f2_pack(qa.z, qa.w), co2 = f2_pack(qb.x, qb.y), sc2 = f2_pack(qb.z, qb.w);
-#pragma unroll
-                for (int r = 0; r < kNrRows; ++r) {
-                    const uint64_t d2 = f2_add(x2[r], nm2);
-                    const uint64_t z2 = f2_fma(f2_mul(pr2, f2_mul(d2, d2)), one2, one2);
-                    float za, zb;
-                    f2_unpack(z2, za, zb);
-                    f2_unpack(f2_fma(co2, f2_pack(fast_log2_cell(za), fast_log2_cell(zb)), sc2), acc[r][j], acc[r][j + 1]);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < kNrRows; ++r) {
-                float m = acc[r][0];
-#pragma unroll
-                for (int j = 1; j < kNrChunk; ++j) m = fmaxf(m, acc[r][j]);
-                const float nm = -m * kLog2e;  // rounded once: every later rescale is a difference of these values
-                const uint64_t nm2 = f2_pack(nm, nm);
-                uint64_t s2 = f2_pack(0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < kNrChunk; j += 2) {
-                    float ea, eb;
-                    f2_unpack(f2_fma(f2_pack(acc[r][j], acc[r][j + 1]), l2e2, nm2), ea, eb);
-                    s2 = f2_add(s2, f2_pack(mufu_ex2(ea), mufu_ex2(eb)));
-                }
-                float se, so;
-                f2_unpack(s2, se, so);
-                const float s = se + so;
-                const float dlt = slot_m[r] - nm;
-                const float e = mufu_ex2(-fabsf(dlt));
-                slot_s[r] = dlt > 0.f ? fmaf(slot_s[r], e, s) : fmaf(s, e, slot_s[r]);
-                slot_m[r] = fminf(slot_m[r], nm);
-                if ((c + 1) % cps == 0 || c + 1 == nchunks) {
-                    slots[(r * kSlots + c / cps) * kNrThreads + tid] = make_float2(slot_m[r], slot_s[r]);
-                    slot_m[r] = INFINITY;
-                    slot_s[r] = 0.f;
-                }
-            }
-        }
-        // per row: total over the slots, walk to the slot holding u * total, re-score that slot, walk its cells
-#pragma unroll
-        for (int r = 0; r < kNrRows; ++r) {
-            float2 *sl = slots + (r * kSlots) * kNrThreads + tid;
-            float mm = INFINITY;
-            for (int k = 0; k < nslots; ++k) mm = fminf(mm, sl[k * kNrThreads].x);
-            float total = 0.f;
-            for (int k = 0; k < nslots; ++k) {
-                const float2 ms = sl[k * kNrThreads];
-                const float w = ms.y * mufu_ex2(mm - ms.x);
-                sl[k * kNrThreads].y = w;
-                total += w;
-            }
-            float t = total * urow[r];
-            int sel = nslots - 1;
-            for (int k = 0; k < nslots; ++k) {
-                const float w = sl[k * kNrThreads].y;
-                if (t <= w) {
-                    sel = k;
-                    break;
-                }
-                if (k + 1 < nslots) t -= w;
-            }
-            int count = 0;
-            for (int cc = 0; cc < cps; ++cc) {
-                const int c = sel * cps + cc;
-                if (c >= nchunks) break;
-                float acc[kNrChunk];
-                score_tile(caches + c * kNrChunk + sel, r, acc);
-#pragma unroll
-                for (int j = 0; j < kNrChunk; ++j) {
-                    t -= mufu_ex2(fmaf(acc[j], kLog2e, mm));
-                    count += 1 - static_cast<int>(__float_as_uint(t) >> 31);  // t >= +0 continues (an exact 0: a near-tie)
-                }
-            }
-            if (row[r] < a.N) a.assign[row[r]] = min(sel * slot_groups + count, G - 1);
-        }
+        if (h + kNrRows < h1) fetch(h + kNrRows);
+        nich_tile<kPoly, kNrRows>(g, xrow, urow, row, a.N, a.assign);
     }
+    if (h < h1) {  // odd half-tile left: one row per thread
+        const size_t row[1] = {h * kNrThreads + tid};
+        const float xrow[1] = {xnext[0]}, urow[1] = {unext[0]};
+        nich_tile<kPoly, 1>(g, xrow, urow, row, a.N, a.assign);
+    }
+}
+
+template <int kPoly>
+static int launch_nich_rows_t(dist_b200_ctx *ctx, const NichRowsArgs &a, size_t smem, cudaStream_t s) {
+    DISTB200_CUDA(ctx, cudaFuncSetAttribute(nich_rows_kernel<kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    DISTB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nich_rows_kernel<kPoly>, kNrThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const size_t tile_rows = static_cast<size_t>(kNrThreads) * kNrRows;
+    const size_t ntiles = (a.N + tile_rows - 1) / tile_rows;
+    const size_t cap = static_cast<size_t>(ctx->sm_count) * per_sm;
+    nich_rows_kernel<kPoly><<<static_cast<unsigned>(ntiles < cap ? ntiles : cap), kNrThreads, smem, s>>>(a);  // N > 0: the callers return early on an empty batch
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("nich_rows launch: ") + cudaGetErrorString(e));
+    return DIST_B200_OK;
 }
 
 // DIST_B200_ERR_UNSUPPORTED: the caller takes the generic kernel
@@ -206,17 +263,17 @@ int launch_nich_rows(dist_b200_ctx *ctx, const float4 *params, const void *colum
     a.values = static_cast<const float *>(column);
     a.u = u;
     a.assign = assign;
-    DISTB200_CUDA(ctx, cudaFuncSetAttribute(nich_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int per_sm = 0;
-    DISTB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nich_rows_kernel, kNrThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const size_t tile_rows = static_cast<size_t>(kNrThreads) * kNrRows;
-    const size_t ntiles = (N + tile_rows - 1) / tile_rows;
-    const size_t cap = static_cast<size_t>(ctx->sm_count) * per_sm;
-    nich_rows_kernel<<<static_cast<unsigned>(ntiles < cap ? ntiles : cap), kNrThreads, smem, s>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("nich_rows launch: ") + cudaGetErrorString(e));
-    return DIST_B200_OK;
+    // DIST_B200_OPT_EXP_OFFLOAD (A/B runs): 0 = default, 1 = every exp2 on the MUFU pipe, 1 + k = k of 16 pairs on the FMA pipe
+    switch (ctx->opt[DIST_B200_OPT_EXP_OFFLOAD]) {
+        case 1: return launch_nich_rows_t<0>(ctx, a, smem, s);
+        case 3: return launch_nich_rows_t<2>(ctx, a, smem, s);
+        case 5: return launch_nich_rows_t<4>(ctx, a, smem, s);
+        case 6: return launch_nich_rows_t<5>(ctx, a, smem, s);
+        case 7: return launch_nich_rows_t<6>(ctx, a, smem, s);
+        case 8: return launch_nich_rows_t<7>(ctx, a, smem, s);
+        case 9: return launch_nich_rows_t<8>(ctx, a, smem, s);
+        default: return launch_nich_rows_t<kNrPolyDefault>(ctx, a, smem, s);
+    }
 }
 
 }  // namespace distb200

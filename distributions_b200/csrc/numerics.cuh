@@ -123,4 +123,55 @@ __device__ inline float fast_lgamma_nu(float nu, const float *__restrict__ coeff
     return r;
 }
 
+// Blackwell packed fp32 pairs (one issue slot, two lanes of the FMA pipe); every element is IEEE-rounded like
+// the scalar __fadd_rn / __fmul_rn / fmaf it replaces
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// exp2 of a pair on the FMA pipe (Cody-Waite split + degree-5 minimax polynomial, 2.1e-7 relative: the accuracy class of
+// MUFU.EX2's 2^-22), for arguments <= ~0.  The sampling kernels are bound by the MUFU pipe (16 lanes / clock / SM) while the
+// FMA pipe idles: a share of their exp2 takes this route instead of MUFU.EX2 (the softmax trick of recent attention
+// kernels; nich_rows.cu: kPoly of every 16 pairs).  x + 1.5 * 2^23 rounds x to the nearest integer n in the low mantissa bits, f = x - n lies
+// in [-0.5, 0.5], and 2^n is applied by adding n to the exponent field; below -125 the argument is clamped (2^-125 of
+// the row maximum: the MUFU route flushes those cells to 0, both are < 3e-38 of the total).
+__device__ __forceinline__ uint64_t poly_ex2_pair(uint64_t x2) {
+    float xa, xb;
+    f2_unpack(x2, xa, xb);
+    x2 = f2_pack(fmaxf(xa, -125.f), fmaxf(xb, -125.f));
+    const float magic = 12582912.f;
+    const uint64_t r2 = f2_add(x2, f2_pack(magic, magic));
+    const uint64_t f2 = f2_add(x2, f2_fma(r2, f2_pack(-1.f, -1.f), f2_pack(magic, magic)));  // x - n, exact
+    uint64_t p2 = f2_fma(f2_pack(0.0013276472454890609f, 0.0013276472454890609f), f2, f2_pack(0.009675540961325169f, 0.009675540961325169f));
+    p2 = f2_fma(p2, f2, f2_pack(0.05550713092088699f, 0.05550713092088699f));
+    p2 = f2_fma(p2, f2, f2_pack(0.24022120237350464f, 0.24022120237350464f));
+    p2 = f2_fma(p2, f2, f2_pack(0.6931469440460205f, 0.6931469440460205f));
+    p2 = f2_fma(p2, f2, f2_pack(1.0000001192092896f, 1.0000001192092896f));
+    float pa, pb, ra, rb;
+    f2_unpack(p2, pa, pb);
+    f2_unpack(r2, ra, rb);
+    return f2_pack(__uint_as_float(__float_as_uint(pa) + (__float_as_uint(ra) << 23)),
+                   __uint_as_float(__float_as_uint(pb) + (__float_as_uint(rb) << 23)));
+}
+
 }  // namespace distb200

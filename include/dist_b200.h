@@ -82,6 +82,8 @@ typedef enum {
     DIST_B200_OPT_NIW_DEBUG = 7,   /* profiling only, results are WRONG when set: 1 = skip the fused sampling walk, 2 = also the epilogue math */
     DIST_B200_OPT_HOST_ZEROCOPY = 8, /* host-buffer entry with page-locked caller buffers: 0 = kernels read / write the host buffers
                                       directly (one launch, no staging), 1 = staged row chunks over two streams (round 1) */
+    DIST_B200_OPT_EXP_OFFLOAD = 9, /* nich sampling kernel (G > 128): share of the softmax exp2 evaluated on the FMA pipe (Cody-Waite +
+                                      degree-5 polynomial) instead of MUFU.EX2: 0 = default (6 of every 16 pairs), 1 = none, 1 + k = k of every 16 pairs (k = 2, 4 .. 8) */
     DIST_B200_OPT_COUNT_ = 16
 } dist_b200_option;
 int dist_b200_ctx_set_option(dist_b200_ctx *ctx, int option, int value);

@@ -63,6 +63,9 @@ FUSED_VARIANTS = {
     "small_tile_4x32": {0: 1, 5: 3},                # 64 < G <= 128: four 32-group tiles
     "nich_scalar": {6: 1},                          # nich: scalar loop instead of packed fp32x2
     "nich_packed_one_row": {6: 2},                  # nich: packed loop, one row per thread (default: two rows for G > 128)
+    "nich_exp_all_mufu": {9: 1},                    # nich G > 128: every softmax exp2 on the MUFU pipe
+    "nich_exp_offload_4": {9: 5},                   # ... 4 of 16 pairs on the FMA pipe (polynomial)
+    "nich_exp_offload_8": {9: 9},                   # ... 8 of 16
 }
 
 
