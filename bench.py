@@ -267,7 +267,7 @@ def binding_roofline(name, wl, ms, peaks, cdf_shortcut=False, materialise=False)
     traffic, traffic_src = ncu_traffic(NCU_SUMMARY.get(name))
     if cdf_shortcut or materialise:
         r = dict(hbm)
-        r["kernel"] = ("value_cdf_build_kernel + value_cdf_sample_kernel (per-value CDF trees)" if cdf_shortcut
+        r["kernel"] = ("value_guide_build_kernel + value_guide_sample_kernel (per-value CDF rows + guide tables, one thread per row)" if cdf_shortcut
                        else "score_rows_kernel (scores materialised)")
     elif model in ("dd", "nich", "dpd"):
         mufu_per_cell = 2.0 if model == "nich" else 1.0  # nich: lg2 + ex2; dd / dpd: ex2

@@ -1573,8 +1573,9 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
     for (int f = 0; f < F; ++f) n_solo += solo(features[f]) ? 1 : 0;
     // ONE table feature (dpd / dd / bb), sampling only: every row with the same value has the same likelihood
     // vector, so it is evaluated once per distinct value (per-value CDF trees, table_rows.cu).  SURVEY 8(d)
-    // "algorithmic shortcut"; DIST_B200_OPT_VALUE_CDF = 1 keeps the per-cell kernels (what bench.py reports beside it)
-    if (F == 1 && assign && !scores && !accumulate && ctx->opt[DIST_B200_OPT_VALUE_CDF] == 0 &&
+    // "algorithmic shortcut"; DIST_B200_OPT_VALUE_CDF = 1 keeps the per-cell kernels (what bench.py reports beside it),
+    // 2 = the round-2 tree search instead of the guide-table walk
+    if (F == 1 && assign && !scores && !accumulate && ctx->opt[DIST_B200_OPT_VALUE_CDF] != 1 &&
         (features[0]->model == DIST_B200_DPD || features[0]->model == DIST_B200_DD || features[0]->model == DIST_B200_BB)) {
         dist_b200_feature *f = const_cast<dist_b200_feature *>(features[0]);
         const int R = f->model == DIST_B200_DPD ? f->dim + 1 : (f->model == DIST_B200_DD ? f->dim : 2);

@@ -306,6 +306,152 @@ __global__ void __launch_bounds__(256) value_cdf_sample_kernel(const CdfSampleAr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// (2b) per-value CDF + guide table (the default of the shortcut for G <= 1024): same likelihoods and inclusive prefix
+// sums as the trees, stored as a plain row cdf[r][Gs], plus guide[r][k] = first group whose prefix reaches
+// (k / K) * total, K a power of two >= 2 G.  A data row is ONE THREAD: k = floor(u K) (exact: K is a power of two),
+// start at guide[r][k] and step forward while cdf < t -- on average G / K + 1 < 2 probes, no warp-wide votes, 32
+// independent rows per warp in flight where the tree search had 4.  Exactness of the start: u >= k / K, products by
+// `total` round monotonically, so t = fl(u total) >= fl((k / K) total) = the threshold the guide entry was built for,
+// and the first prefix >= t cannot lie before it.  Same result as the tree search (first g with cdf[g] >= t, clamped
+// to G - 1) wherever the prefix sums are monotone, i.e. up to near-ties.
+struct GuideArgs {
+    int model, G, R, Gs, K, vdim;
+    const void *params;
+    const float *prior;
+    float *cdf;        // [R][Gs]
+    float *total;      // [R]
+    uint16_t *guide;   // [R][K]
+};
+__device__ __forceinline__ float guide_table_score(const GuideArgs &a, int r, int g) {
+    CdfArgs c{};
+    c.model = a.model;
+    c.G = a.G;
+    c.vdim = a.vdim;
+    c.params = a.params;
+    return table_score(c, r, g);
+}
+
+constexpr int kGuideWarps = 8;
+
+// one warp per table row; the row's prefix sums stay in shared memory for the K binary searches of the guide
+__global__ void __launch_bounds__(kGuideWarps * 32) value_guide_build_kernel(const GuideArgs a) {
+    extern __shared__ float guide_smem[];  // [kGuideWarps][Gs]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * kGuideWarps + warp;
+    if (r >= a.R) return;
+    const unsigned full = 0xffffffffu;
+    const int G = a.G;
+    float *mine = guide_smem + warp * a.Gs;
+    float m = -INFINITY;
+    for (int g = lane; g < G; g += 32) m = fmaxf(m, (a.prior ? a.prior[g] : 0.f) + guide_table_score(a, r, g));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(full, m, o));
+    const float nm = -m * kLog2e;
+    float *row = a.cdf + static_cast<size_t>(r) * a.Gs;
+    float carry = 0.f;
+    for (int g0 = 0; g0 < a.Gs; g0 += 32) {  // identical arithmetic to value_cdf_build_kernel: same prefix sums
+        const int g = g0 + lane;
+        float l = 0.f;
+        if (g < G) l = mufu_ex2(fmaf((a.prior ? a.prior[g] : 0.f) + guide_table_score(a, r, g), kLog2e, nm));
+        float incl = l;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += v;
+        }
+        incl += carry;
+        carry = __shfl_sync(full, incl, 31);
+        const float p = g < G ? incl : INFINITY;
+        row[g] = p;
+        mine[g] = p;
+    }
+    if (lane == 0) a.total[r] = carry;
+    __syncwarp();
+    uint16_t *gd = a.guide + static_cast<size_t>(r) * a.K;
+    const float inv_k = 1.f / static_cast<float>(a.K);
+    for (int k = lane; k < a.K; k += 32) {
+        const float thr = (static_cast<float>(k) * inv_k) * carry;  // = fl(u total) at u = k / K
+        int lo = 0, hi = G - 1;  // first g in [0, G - 1] with cdf[g] >= thr, G - 1 when none
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (mine[mid] < thr) lo = mid + 1;
+            else hi = mid;
+        }
+        gd[k] = static_cast<uint16_t>(lo);
+    }
+}
+
+struct GuideSampleArgs {
+    int G, Gs, K;
+    KeyMap km;
+    size_t N;
+    const float *cdf, *total;
+    const uint16_t *guide;
+    const uint32_t *values;
+    int value_bytes;
+    const float *u;
+    int32_t *assign;
+};
+
+__device__ __forceinline__ int guide_draw(const GuideSampleArgs &a, uint32_t v, float uu, float kf) {
+    const int r = key_row(a.km, v);
+    const float t = uu * __ldg(a.total + r);
+    const int k = max(0, min(static_cast<int>(uu * kf), a.K - 1));
+    int g = __ldg(a.guide + static_cast<size_t>(r) * a.K + k);
+    const float *c = a.cdf + static_cast<size_t>(r) * a.Gs;
+    while (g < a.G - 1 && __ldg(c + g) < t) ++g;
+    return g;
+}
+
+// kVec = 4: four consecutive rows per thread (16-byte loads of the values / uniforms, one 16-byte store of the indices;
+// four independent gather chains in flight per thread); the last N % 4 rows and unaligned buffers take the scalar form
+template <int kVec>
+__global__ void __launch_bounds__(256) value_guide_sample_kernel(const GuideSampleArgs a) {
+    const size_t step = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const float kf = static_cast<float>(a.K);
+    const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (kVec == 4) {
+        const size_t nq = a.N / 4;
+        for (size_t q = first; q < nq; q += step) {
+            uint32_t v[4];
+            if (a.value_bytes == 1) {
+                const uchar4 b = reinterpret_cast<const uchar4 *>(a.values)[q];
+                v[0] = b.x ? 1u : 0u, v[1] = b.y ? 1u : 0u, v[2] = b.z ? 1u : 0u, v[3] = b.w ? 1u : 0u;
+            } else {
+                const uint4 w = reinterpret_cast<const uint4 *>(a.values)[q];
+                v[0] = w.x, v[1] = w.y, v[2] = w.z, v[3] = w.w;
+            }
+            const float4 u4 = reinterpret_cast<const float4 *>(a.u)[q];
+            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+            int g[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g[i] = guide_draw(a, v[i], uu[i], kf);
+            reinterpret_cast<int4 *>(a.assign)[q] = make_int4(g[0], g[1], g[2], g[3]);
+        }
+        const size_t n = nq * 4 + first;  // the ragged tail
+        if (n < a.N) {
+            const uint32_t v = a.value_bytes == 1 ? (reinterpret_cast<const uint8_t *>(a.values)[n] ? 1u : 0u) : a.values[n];
+            a.assign[n] = guide_draw(a, v, a.u[n], kf);
+        }
+    } else {
+        for (size_t n = first; n < a.N; n += step) {
+            const uint32_t v = a.value_bytes == 1 ? (reinterpret_cast<const uint8_t *>(a.values)[n] ? 1u : 0u) : a.values[n];
+            a.assign[n] = guide_draw(a, v, a.u[n], kf);
+        }
+    }
+}
+
+static int guide_k(int G) {
+    int K = 64;
+    while (K < 2 * G) K *= 2;
+    return K;
+}
+static int guide_gs(int G) { return (G + 31) / 32 * 32; }
+static size_t guide_floats(int R, int G) {
+    return static_cast<size_t>(R) * guide_gs(G) + static_cast<size_t>(R) + (static_cast<size_t>(R) * guide_k(G) + 1) / 2;
+}
+
 static int cdf_levels(int G) {
     int L = 1, cap = 8;
     while (cap < G) {
@@ -321,7 +467,18 @@ size_t value_cdf_floats(int R, int G) {
         per += w;
         w *= 8;
     }
-    return static_cast<size_t>(R) * per + static_cast<size_t>(R);  // trees + totals
+    const size_t trees = static_cast<size_t>(R) * per + static_cast<size_t>(R);  // trees + totals
+    const size_t guided = G <= 1024 ? guide_floats(R, G) : 0;                     // cdf rows + totals + guide tables
+    return trees > guided ? trees : guided;
+}
+static size_t value_cdf_tree_floats(int R, int G) {
+    const int L = cdf_levels(G);
+    size_t per = 0, w = 8;
+    for (int l = 0; l < L; ++l) {
+        per += w;
+        w *= 8;
+    }
+    return per;
 }
 
 // single table feature, sampling only.  `buf` holds value_cdf_floats(R, G) floats (feature-owned scratch).
@@ -351,13 +508,51 @@ int launch_value_cdf(dist_b200_ctx *ctx, const dist_b200_feature *f, float *buf,
             break;
         default: return DIST_B200_ERR_UNSUPPORTED;
     }
+    // DIST_B200_OPT_VALUE_CDF = 2 (A/B runs): the tree search also where the guide-table kernels apply
+    if (G <= 1024 && ctx->opt[DIST_B200_OPT_VALUE_CDF] != 2) {
+        GuideArgs b{};
+        b.model = f->model;
+        b.G = G;
+        b.R = R;
+        b.Gs = guide_gs(G);
+        b.K = guide_k(G);
+        b.vdim = f->dim;
+        b.params = f->params;
+        b.prior = prior;
+        b.cdf = buf;
+        b.total = buf + static_cast<size_t>(R) * b.Gs;
+        b.guide = reinterpret_cast<uint16_t *>(b.total + R);
+        value_guide_build_kernel<<<(R + kGuideWarps - 1) / kGuideWarps, kGuideWarps * 32, kGuideWarps * b.Gs * sizeof(float), s>>>(b);
+        GuideSampleArgs a{};
+        a.G = G;
+        a.Gs = b.Gs;
+        a.K = b.K;
+        a.km = km;
+        a.N = N;
+        a.cdf = b.cdf;
+        a.total = b.total;
+        a.guide = b.guide;
+        a.values = static_cast<const uint32_t *>(column);
+        a.value_bytes = f->model == DIST_B200_BB ? 1 : 4;
+        a.u = u;
+        a.assign = assign;
+        const bool vec = N >= 1024 && ((reinterpret_cast<uintptr_t>(column) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(assign)) & 15) == 0;
+        const size_t want = ((vec ? N / 4 : N) + 255) / 256;
+        const size_t cap = static_cast<size_t>(ctx->sm_count) * 8;
+        const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+        if (vec) value_guide_sample_kernel<4><<<grid, 256, 0, s>>>(a);
+        else value_guide_sample_kernel<1><<<grid, 256, 0, s>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("value_guide launch: ") + cudaGetErrorString(e));
+        return DIST_B200_OK;
+    }
     CdfArgs b{};
     b.model = f->model;
     b.G = G;
     b.R = R;
     b.L = L;
     b.vdim = f->dim;
-    b.tree_floats = (value_cdf_floats(R, G) - R) / R;
+    b.tree_floats = value_cdf_tree_floats(R, G);
     b.params = f->params;
     b.prior = prior;
     b.tree = buf;

@@ -57,6 +57,7 @@ def envelope(oracle, w):
 # every kernel variant behind the fused (sampling-only) entry: dist_b200_option settings
 FUSED_VARIANTS = {
     "default": {},                                  # per-value CDF trees for single dpd / dd / bb, packed nich, ...
+    "value_cdf_tree": {0: 2},                       # per-value CDFs searched as 8-ary trees (default: guide-table walk)
     "no_value_cdf": {0: 1},                         # per-cell kernels: table_rows (dpd), score_rows (dd / bb)
     "round1_gather": {0: 1, 4: 1},                  # dpd: round-1 warp-per-row gather kernel
     "small_tile_256": {0: 1, 5: 1},                 # 64 < G <= 128: one 256-thread block / SM
