@@ -1500,6 +1500,8 @@ static int fill_desc(dist_b200_ctx *ctx, const dist_b200_feature *cf, const void
     d.kind = f->model;
     d.vdim = f->dim;
     d.aux = nullptr;
+    d.cap = f->capacity;
+    d.pad_ = 0;
     if (multi && f->model == DIST_B200_GP) {
         if (f->gp_table_cap < f->capacity) {
             if (f->gp_table) {
@@ -1507,7 +1509,7 @@ static int fill_desc(dist_b200_ctx *ctx, const dist_b200_feature *cf, const void
                 DISTB200_CUDA(ctx, cudaFree(f->gp_table));
                 f->gp_table = nullptr;
             }
-            DISTB200_CUDA(ctx, cudaMalloc(&f->gp_table, sizeof(float) * kGpTableX * f->capacity));
+            DISTB200_CUDA(ctx, cudaMalloc(&f->gp_table, sizeof(float) * 2 * kGpTableX * f->capacity));  // [capacity][x] | [x][capacity]
             f->gp_table_cap = f->capacity;
             f->gp_table_dirty = true;
         }

@@ -12,7 +12,7 @@
 namespace distb200 {
 
 constexpr int kMaxPushOwners = 16;  // ranks of one NVLink domain a feature-sharded launch can push to
-constexpr int kMaxFeatures = 512;  // feature descriptors travel in kernel-parameter space (16 KB)
+constexpr int kMaxFeatures = 512;  // feature descriptors travel in kernel-parameter space (20 KB)
 
 // device view of one feature, consumed by the row-mapped score kernel
 struct FeatDesc {
@@ -21,6 +21,8 @@ struct FeatDesc {
     int kind;            // dist_b200_model, or kKindGpTable
     int vdim;            // dd: dim; gp table: kGpTableX
     const void *aux;     // gp table: the float4 caches, for values >= kGpTableX
+    int cap;             // gp table: groups allocated = row stride of the transposed copy [kGpTableX][cap] that follows the table
+    int pad_;
 };
 
 // internal kind: GammaPoisson scored through a per-(group, value) table for small counts

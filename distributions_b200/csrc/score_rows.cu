@@ -16,7 +16,11 @@ __global__ void gp_table_kernel(const GpTableBatch b, NumericTables t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n_groups[blockIdx.y] * kGpTableX) return;
     const int g = i / kGpTableX, x = i % kGpTableX;
-    b.table[blockIdx.y][i] = gp_term(b.params[blockIdx.y][g], static_cast<uint32_t>(x), coeff, logfact);
+    const float v = gp_term(b.params[blockIdx.y][g], static_cast<uint32_t>(x), coeff, logfact);
+    b.table[blockIdx.y][i] = v;
+    // transposed copy [x][capacity] behind the table: the kSub re-score reads 16 consecutive groups of one value
+    const int cap = b.n_groups[blockIdx.y];
+    b.table[blockIdx.y][static_cast<size_t>(kGpTableX + x) * cap + g] = v;
 }
 
 int launch_gp_table_batch(dist_b200_ctx *ctx, const GpTableBatch &b, cudaStream_t s) {

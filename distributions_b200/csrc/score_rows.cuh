@@ -235,10 +235,16 @@ struct RowsArgs {
     float *push[kMaxPushOwners];
 };
 
-template <int CHUNK, int KIND, bool kSample, bool kScores, int THREADS>
+// kSub (feature lists whose caches stream, more groups than one register tile, sampling only): per tile the row keeps
+// the tile's maximum and the sums of exp over SUB-SLOTS of 16 groups, so that the draw is located down to 16 groups
+// from the main pass and only those are re-scored (from global memory, through the transposed GammaPoisson tables).
+constexpr int kSubGroups = 16;
+template <int CHUNK, int KIND, bool kSample, bool kScores, int THREADS, bool kSub = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (is_dd_scaled(KIND) ? 5 : 3) : (CHUNK <= 32 ? (KIND >= 0 ? 4 : 3) : (CHUNK <= 64 ? 2 : 1)))
 score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     constexpr int kThreads = THREADS;  // block size of this instantiation
+    static_assert(!kSub || (KIND < 0 && kSample && !kScores && CHUNK % kSubGroups == 0), "kSub: streaming feature lists, sampling only");
+    constexpr int kSubPer = CHUNK / kSubGroups;  // sub-slots per tile
     extern __shared__ __align__(16) float smem[];
     // layout: coeff[33*8] | logfact[64] | prior[Gpad] | tile[8 warps][32][33] (kScores) |
     //         slots[kSlots][kThreads] float2 (kSample, multi-tile) | caches
@@ -258,7 +264,9 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     float *tile = cursor;
     if (kScores) cursor += (kThreads / 32) * 32 * 33;
     float2 *slots = reinterpret_cast<float2 *>(cursor);
-    if (kSample && multi) cursor += 2 * kSlots * kThreads;
+    float *subs = cursor;  // kSub: [nchunks][kSubPer + 1][kThreads] -- sub-slot sums, then the tile's negated scaled max
+    if (kSub) cursor += nchunks * (kSubPer + 1) * kThreads;
+    else if (kSample && multi) cursor += 2 * kSlots * kThreads;
     float *caches = cursor;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -607,6 +615,25 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                         }
                     }
                     result = min(CHUNK - static_cast<int>((neg[0] + neg[1]) + (neg[2] + neg[3])), G - 1);
+                } else if (kSub) {
+                    float m = acc[0];
+#pragma unroll
+                    for (int j = 1; j < CHUNK; ++j) m = fmaxf(m, acc[j]);
+                    const float nm = fmaxf(-m * kLog2e, -3.0e38f);  // finite also when every group of the tile is at -inf... (+inf max cannot occur)
+                    const uint64_t l2e2 = f2_pack(kLog2e, kLog2e), nm2 = f2_pack(nm, nm);
+#pragma unroll
+                    for (int k = 0; k < kSubPer; ++k) {
+                        float sk = 0.f;  // summed left to right, as the re-score walk subtracts
+#pragma unroll
+                        for (int j = 0; j < kSubGroups; j += 2) {
+                            float ea, eb;
+                            f2_unpack(f2_fma(f2_pack(acc[k * kSubGroups + j], acc[k * kSubGroups + j + 1]), l2e2, nm2), ea, eb);
+                            sk += mufu_ex2(ea);
+                            sk += mufu_ex2(eb);
+                        }
+                        subs[(it * (kSubPer + 1) + k) * kThreads + tid] = sk;
+                    }
+                    subs[(it * (kSubPer + 1) + kSubPer) * kThreads + tid] = nm;
                 } else if (!fin) {
                     float m = acc[0];
 #pragma unroll
@@ -675,16 +702,108 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
             }
         }  // tiles of groups
 
-        if (kSample && multi) {
+        if (kSub) {
+            // tiles -> the tile holding u * total -> its sub-slot -> re-score that sub-slot's 16 groups
+            float mm = INFINITY;
+            for (int c = 0; c < nchunks; ++c) mm = fminf(mm, subs[(c * (kSubPer + 1) + kSubPer) * kThreads + tid]);
+            float total = 0.f;
+            for (int c = 0; c < nchunks; ++c) {
+                float sc = 0.f;
+                for (int k = 0; k < kSubPer; ++k) sc += subs[(c * (kSubPer + 1) + k) * kThreads + tid];
+                total += sc * mufu_ex2(mm - subs[(c * (kSubPer + 1) + kSubPer) * kThreads + tid]);
+            }
+            float t = total * urow;
+            int csel = nchunks - 1;
+            float fsel = 1.f;
+            for (int c = 0; c < nchunks; ++c) {
+                float sc = 0.f;
+                for (int k = 0; k < kSubPer; ++k) sc += subs[(c * (kSubPer + 1) + k) * kThreads + tid];
+                const float fc = mufu_ex2(mm - subs[(c * (kSubPer + 1) + kSubPer) * kThreads + tid]);
+                const float w = sc * fc;
+                fsel = fc;
+                if (t <= w) {
+                    csel = c;
+                    break;
+                }
+                if (c + 1 < nchunks) t -= w;
+            }
+            t = fsel > 0.f ? t / fsel : 0.f;  // the remaining draw on the selected tile's own scale
+            int ksel = kSubPer - 1;
+            for (int k = 0; k < kSubPer; ++k) {
+                const float w = subs[(csel * (kSubPer + 1) + k) * kThreads + tid];
+                if (t <= w) {
+                    ksel = k;
+                    break;
+                }
+                if (k + 1 < kSubPer) t -= w;
+            }
+            const float nm = subs[(csel * (kSubPer + 1) + kSubPer) * kThreads + tid];
+            const int gb = csel * CHUNK + ksel * kSubGroups;
+            // the same sums in the same order as the main pass: prior, then the features left to right
+            float sc16[kSubGroups];
+#pragma unroll
+            for (int j = 0; j < kSubGroups; ++j) sc16[j] = prior_s[gb + j];
+            for (int f = 0; f < F; ++f) {
+                const FeatDesc &fd = feats.f[f];
+                const uint32_t xv = load_value(fd.kind, fd.column, row);
+                if (fd.kind == kKindGpTable && xv < static_cast<uint32_t>(kGpTableX)) {
+                    // transposed table [value][capacity] behind the [capacity][value] one: 64 contiguous bytes
+                    const float4 *tp = reinterpret_cast<const float4 *>(static_cast<const float *>(fd.params) +
+                                                                        static_cast<size_t>(kGpTableX + xv) * fd.cap + gb);
+#pragma unroll
+                    for (int q = 0; q < kSubGroups / 4; ++q) {
+                        const float4 v = __ldg(tp + q);
+                        sc16[4 * q] += v.x;
+                        sc16[4 * q + 1] += v.y;
+                        sc16[4 * q + 2] += v.z;
+                        sc16[4 * q + 3] += v.w;
+                    }
+                } else if (fd.kind == kKindGpTable) {
+#pragma unroll 1
+                    for (int j = 0; j < kSubGroups; ++j) {
+                        const float v = gp_term(static_cast<const float4 *>(fd.aux)[gb + j], xv, coeff, logfact);
+#pragma unroll
+                        for (int jj = 0; jj < kSubGroups; ++jj)
+                            if (jj == j) sc16[jj] += v;
+                    }
+                } else if (fd.kind == DIST_B200_BB) {
+                    const float2 *bp = reinterpret_cast<const float2 *>(static_cast<const float4 *>(fd.params) + gb);
+#pragma unroll
+                    for (int j = 0; j < kSubGroups; ++j) {
+                        const float2 q = __ldg(bp + 2 * j);
+                        sc16[j] += xv ? q.x : q.y;
+                    }
+                } else {
+                    const int st = kind_stride(fd.kind, fd.vdim);
+#pragma unroll
+                    for (int j = 0; j < kSubGroups; ++j)
+                        sc16[j] += cell_score(fd.kind, xv, static_cast<const float *>(fd.params) + static_cast<size_t>(gb + j) * st, fd.vdim, coeff, logfact);
+                }
+            }
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < kSubGroups; ++j) {
+                const float sj = gb + j < G ? sc16[j] : -INFINITY;  // padded groups: as in the main pass
+                t -= mufu_ex2(fmaf(sj, kLog2e, nm));
+                cnt += 1 - static_cast<int>(__float_as_uint(t) >> 31);  // t >= +0 continues (an exact 0: a near-tie)
+            }
+            result = min(gb + cnt, G - 1);
+        } else if (kSample && multi) {
             if (resident) {
                 result = min(sel * chunks_per_slot * CHUNK + count, G - 1);
             } else {
-                // streaming caches: re-score the selected slot cell by cell from global memory
+                // streaming caches: re-score the selected slot cell by cell from global memory -- or read the scores back
+                // where this launch has just written them (the row's scores were stored by lanes of this warp)
                 int idx = G - 1;
                 const int gb = sel * chunks_per_slot * CHUNK, ge = min(G, gb + chunks_per_slot * CHUNK);
                 float t = tres;
+                const bool readback = kScores && !a.accumulate && !a.n_push;
+                if (readback) __syncwarp();
                 for (int g = gb; g < ge; ++g) {
                     float s = prior_s[g];
+                    if (readback) {
+                        s = a.scores[row * static_cast<size_t>(G) + g];
+                    } else
                     for (int f = 0; f < F; ++f) {
                         const FeatDesc &fd = feats.f[f];
                         const uint32_t xv = load_value(fd.kind, fd.column, row);
@@ -712,7 +831,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // launchers (header templates: every score_rows_*.cu instantiates the variants of its own model)
-template <int CHUNK, int KIND, bool kSample, bool kScores, int THREADS>
+template <int CHUNK, int KIND, bool kSample, bool kScores, int THREADS, bool kSub = false>
 static int launch_variant(dist_b200_ctx *ctx, const FeatList &feats, RowsArgs a, cudaStream_t s) {
     constexpr int kThreads = THREADS;
     const int G = a.G;
@@ -727,13 +846,14 @@ static int launch_variant(dist_b200_ctx *ctx, const FeatList &feats, RowsArgs a,
     }
     size_t fixed = (33 * kLgammaRowStride + 64 + Gpad) * sizeof(float);
     if (kScores) fixed += (kThreads / 32) * 32 * 33 * sizeof(float);
-    if (kSample && nchunks > 1) fixed += sizeof(float2) * kSlots * kThreads;
-    a.resident = cache_floats * sizeof(float) <= kResidentBudget ? 1 : 0;
+    if (kSub) fixed += sizeof(float) * nchunks * (CHUNK / kSubGroups + 1) * kThreads;
+    else if (kSample && nchunks > 1) fixed += sizeof(float2) * kSlots * kThreads;
+    a.resident = (!kSub && cache_floats * sizeof(float) <= kResidentBudget) ? 1 : 0;
     if (KIND >= 0 && !a.resident) return DIST_B200_ERR_UNSUPPORTED;  // caller falls back to the generic kernel
     a.stage_floats = CHUNK * max_stride;
     const size_t smem = fixed + (a.resident ? cache_floats : kStages * (static_cast<size_t>(a.stage_floats) + kThreads)) * sizeof(float);
     if (smem > 227 * 1024) return fail(ctx, DIST_B200_ERR_UNSUPPORTED, "score_rows: group caches exceed shared memory");
-    auto kern = score_rows_kernel<CHUNK, KIND, kSample, kScores, kThreads>;
+    auto kern = score_rows_kernel<CHUNK, KIND, kSample, kScores, kThreads, kSub>;
     DISTB200_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
     DISTB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
@@ -780,6 +900,18 @@ static int launch_tiers(dist_b200_ctx *ctx, const FeatList &feats, const RowsArg
     // measured at c2, sampling only: 32-group tiles 0.748 ms, 64-group tiles 0.774 ms; with the [N][G] scores also written
     // (HBM-store bound): 32-group tiles 1.215 ms, 64-group tiles 1.098 ms -- a store instruction then covers 256-byte runs of
     // a row instead of 128-byte ones (DIST_B200_OPT_ROW_TILE = 32 / 64 forces either for A/B runs)
+    if constexpr (KIND < 0) if (a.assign && !a.scores && !a.n_push && ctx->opt[DIST_B200_OPT_ROW_TILE] == 0) {
+        // feature lists too large to keep resident (a cross-cat kind): the 128-group streaming tiles of the G <= 128 case
+        // with sub-slot bookkeeping (kSub); measured at 256 features against the 32-group tiles + per-cell re-score of a whole
+        // slot from global memory: G = 256, 200k rows 11.7 -> 3.74 ms; G = 1024, 100k rows 15.3 -> 7.63 ms, identical draws
+        size_t cache_bytes = 0;
+        for (int f = 0; f < feats.n; ++f)
+            cache_bytes += sizeof(float) * static_cast<size_t>((a.G + 31) / 32 * 32) * kind_stride(feats.f[f].kind, feats.f[f].vdim);
+        if (cache_bytes > kResidentBudget) {
+            const int rc = launch_variant<128, KIND, true, false, 128, true>(ctx, feats, a, s);
+            if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;  // (too many groups for the sub-slot sums in shared memory)
+        }
+    }
     const int tile = ctx->opt[DIST_B200_OPT_ROW_TILE] ? ctx->opt[DIST_B200_OPT_ROW_TILE] : (a.scores ? 64 : 32);
     if (tile == 64) return launch_modes<64, KIND, 256>(ctx, feats, a, s);
     return launch_modes<32, KIND, 256>(ctx, feats, a, s);

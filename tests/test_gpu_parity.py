@@ -58,6 +58,7 @@ def envelope(oracle, w):
 FUSED_VARIANTS = {
     "default": {},                                  # per-value CDF trees for single dpd / dd / bb, packed nich, ...
     "value_cdf_tree": {0: 2},                       # per-value CDFs searched as 8-ary trees (default: guide-table walk)
+    "row_tile_32": {1: 32},                         # G > 128: 32-group tiles + slots everywhere (also instead of the kSub streaming kernel)
     "no_value_cdf": {0: 1},                         # per-cell kernels: table_rows (dpd), score_rows (dd / bb)
     "round1_gather": {0: 1, 4: 1},                  # dpd: round-1 warp-per-row gather kernel
     "small_tile_256": {0: 1, 5: 1},                 # 64 < G <= 128: one 256-thread block / SM
@@ -327,7 +328,7 @@ def test_crosscat_golden(ctx, oracle, golden):
     assert cases.explained_mismatch(scores.astype(np.float64), u, assign, a_orc, EPS_TIE).all()
 
 
-@pytest.mark.parametrize("G,F", [(128, 24), (200, 10)])
+@pytest.mark.parametrize("G,F", [(128, 24), (200, 10), (300, 12), (1000, 8)])
 def test_crosscat_streaming(ctx, oracle, G, F):
     """enough features that the group caches do not fit in shared memory (double-buffered staging)"""
     n = 700
@@ -336,6 +337,12 @@ def test_crosscat_streaming(ctx, oracle, G, F):
     # widen the caches with dd features so the resident budget is exceeded
     for k in range(6):
         w = synth.dd(900 + k, G, n, dim=32)
+        feats.append(w)
+    if G > 128:  # a nich member: the generic per-cell branch of the sub-slot re-score (G > 128: kSub kernel)
+        w = synth.nich(950, G, n)
+        w["count"] = cc["sizes"].astype(w["count"].dtype)
+        w["mean"][cc["sizes"] == 0] = 0
+        w["ctv"][cc["sizes"] == 0] = 0
         feats.append(w)
     prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, cc["sizes"])
     assign, scores = run_cuda(ctx, feats, prior, cc["u"], n)
