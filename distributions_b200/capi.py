@@ -81,6 +81,8 @@ SIGNATURES = {
     "dist_b200_sample_from_slots": (c_i, [c_p, c_p, c_i, c_sz, c_sz, c_i, c_p, c_p, c_p]),
     "dist_b200_score_sample_batch_host": (c_i, [c_p, c_p, c_i, c_p, c_sz, c_p, c_p, c_p, c_p]),
     "dist_b200_score_value_host": (c_i, [c_p, c_p, c_p, c_p]),
+    "dist_b200_host_register": (c_i, [c_p, c_p, c_sz]),
+    "dist_b200_host_unregister": (c_i, [c_p, c_p]),
     "dist_b200_numerics_probe": (c_i, [c_p, c_i, c_sz, c_p, c_p, c_p]),
     "dist_b200_pipe_peak": (c_i, [c_p, c_i, ctypes.POINTER(ctypes.c_double)]),
 }
@@ -399,6 +401,15 @@ class Context:
         self.check(self.L.dist_b200_score_sample_batch_host(self.h, fa, F, ca, n, _np_ptr(prior), _np_ptr(u), _np_ptr(assign),
                                                             _np_ptr(scores)), "score_sample_batch_host")
         return assign, scores
+
+    def host_register(self, array):
+        """page-lock a numpy array in place (once): later host-entry calls on it are zero-copy"""
+        assert array.flags.c_contiguous
+        self.check(self.L.dist_b200_host_register(self.h, array.ctypes.data, array.nbytes), "host_register")
+        return array
+
+    def host_unregister(self, array):
+        self.check(self.L.dist_b200_host_unregister(self.h, array.ctypes.data), "host_unregister")
 
     def score_value_host(self, feature, value, scores_accum):
         v = np.ascontiguousarray(value, dtype=COLUMN_DTYPE[feature.model])

@@ -1983,6 +1983,30 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
     return DIST_B200_OK;
 }
 
+int dist_b200_host_register(dist_b200_ctx *ctx, void *ptr, size_t bytes) {
+    if (!ctx || !ptr || bytes == 0) return DIST_B200_ERR_INVALID;
+    DISTB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return DIST_B200_OK;
+    }
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    return DIST_B200_OK;
+}
+
+int dist_b200_host_unregister(dist_b200_ctx *ctx, void *ptr) {
+    if (!ctx || !ptr) return DIST_B200_ERR_INVALID;
+    DISTB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    DISTB200_CUDA(ctx, cudaDeviceSynchronize());  // no kernel may still be reading the range
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, DIST_B200_ERR_INVALID, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+    }
+    return DIST_B200_OK;
+}
+
 int dist_b200_score_value_host(dist_b200_ctx *ctx, const dist_b200_feature *feature, const void *value_host,
                                float *scores_accum_host) {
     if (!ctx || !feature || !value_host || !scores_accum_host) return DIST_B200_ERR_INVALID;

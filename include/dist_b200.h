@@ -369,6 +369,12 @@ int dist_b200_score_sample_batch_host(dist_b200_ctx *ctx, const dist_b200_featur
                                       int n_features, const void *const *columns_host, size_t n_rows,
                                       const float *prior_host, const float *u_host, int32_t *assign_host,
                                       float *scores_host);
+/* Page-lock a caller-owned host buffer once (cudaHostRegister, portable + mapped), so that every later host-entry call
+ * on it takes the zero-copy route -- the data columns of a Gibbs sampler are the same arrays sweep after sweep (the
+ * reference keeps them in std::vector / numpy storage, which is pageable).  Registering an already registered range is
+ * OK.  The caller unregisters before freeing the buffer. */
+int dist_b200_host_register(dist_b200_ctx *ctx, void *ptr, size_t bytes);
+int dist_b200_host_unregister(dist_b200_ctx *ctx, void *ptr);
 /* per-value MixtureSlave::score_value (mixture.hpp:416-425): scores_accum_host[G] += model term. */
 int dist_b200_score_value_host(dist_b200_ctx *ctx, const dist_b200_feature *feature, const void *value_host,
                                float *scores_accum_host);

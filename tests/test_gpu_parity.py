@@ -639,6 +639,30 @@ def test_host_entry_pinned_and_chunked(ctx, oracle):
     assert np.array_equal(assign2, a_dev)
 
 
+def test_host_register(ctx, oracle):
+    """dist_b200_host_register: plain numpy arrays page-locked in place take the zero-copy route; same draws as the
+    device-pointer path; registering twice is fine, unregistering an unknown pointer is an error, not a crash"""
+    from distributions_b200 import capi
+    n, G = 120_001, 300
+    w = synth.nich(18, G, n)
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    f = ctx.feature(capi.NICH).update_all(w)
+    a_dev, _ = run_cuda(ctx, [w], prior, w["u"], n, want_scores=False)
+    vals, uu, out = w["values"].copy(), w["u"].copy(), np.full(n, -7, np.int32)
+    for arr in (vals, uu, out, vals):
+        ctx.host_register(arr)
+    try:
+        assign, _ = ctx.score_sample_batch_host([f], [vals], prior, uu, assign_out=out)
+        assert assign is out and np.array_equal(out, a_dev)
+    finally:
+        for arr in (vals, uu, out):
+            ctx.host_unregister(arr)
+    with pytest.raises(capi.DistB200Error):
+        ctx.host_unregister(np.zeros(16, np.float32))
+    assign2, _ = ctx.score_sample_batch_host([f], [vals], prior, uu)  # pageable again
+    assert np.array_equal(assign2, a_dev)
+
+
 def test_host_entry_niw_chunked(ctx, oracle):
     """niw through the host-buffer entry: the H2D copies of later row chunks run ahead on the second stream while the
     kernels stay on one (they share the context's packed-row buffer) -- pinned and pageable buffers, staged option too;
