@@ -297,6 +297,11 @@ def binding_roofline(name, wl, ms, peaks, cdf_shortcut=False, materialise=False)
                             "(7 kind::f16 MMAs of K = 16 per 128 x 256 tile = 3.4 x the counted flops) and runs at the board's power cap "
                             "(profiles/r02_c5_power.txt)",
              "kernel": "niw_tc_fused_kernel (tcgen05 kind::f16, split fp16 operands, fused sampler)", "hbm": hbm}
+        # what the tensor pipe actually executes: 5.5 MMA-equivalents of 128 x 256 x 16 per (128 rows, 8 groups) = 5 632 flop / cell
+        issued = cells * 5.5 * 128 * 256 * 16 * 2 / (128.0 * 8)
+        r["issued"] = {"flop_per_cell": 5632, "achieved": issued / t / 1e12, "unit": "TFLOP/s", "frac_of_peak": issued / t / 1e12 / peak,
+                       "note": "fp16 MMA flops issued (hi x hi, lo x hi, hi x lo terms; the k-step over x[16..32) at N = 128); the "
+                               "SURVEY 8(d) figure above counts 2 d^2 + 2 d"}
     else:  # cross-cat gp + bb: FP32 pipe per SURVEY 8(d): 10 FMA per gp cell, 1 per bb cell
         n_gp = sum(1 for w in wl["feats"] if w["model"] == "gp")
         fma_ops = float(N) * G * (10.0 * n_gp + 1.0 * (F - n_gp))
