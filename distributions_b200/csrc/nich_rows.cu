@@ -14,6 +14,8 @@
 //     MUFU per cell (LG2 + EX2) the kernel sat at 89 % XU-pipe activity while the FMA pipe idled at 20 %
 //     (profiles/r02_c2_nich_rows.txt); same-box A/B 0.571 -> 0.521 ms;
 //   * rows are dealt to the blocks in half-tiles, so the per-SM loads differ by half a tile (see the kernel).
+// The default is now nich_rows2_kernel below (static softmax reference, four rows per thread: 0.522 -> 0.482 ms);
+// nich_rows_kernel stays selectable (DIST_B200_OPT_NICH_PACKED = 3) and is what the paragraphs above describe.
 // Cell arithmetic is the packed fp32x2 form of nich.cc:59-65 (see accumulate_feature, kKindNichPacked): two groups per
 // FADD2 / FMUL2 / FFMA2, every product and sum rounded as the reference's unfused expression.
 #include "score_rows.cuh"
@@ -230,6 +232,245 @@ __global__ void __launch_bounds__(kNrThreads, 2) nich_rows_kernel(const NichRows
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// nich_rows2_kernel: the same cells against a STATIC reference instead of the row's running maximum.
+//   score_g(x) = sc_g + co_g ln z <= sc_g   (co_g < 0, z >= 1),   sc_g = prior_g + score_g of the group,
+// so M* = max_g sc_g bounds every score of every row, and the softmax weights can be formed directly as
+//   e_g = 2^(co_g lg2 z + (sc_g - M*) log2 e)  in (0, 1]
+// in the FFMA2 that used to produce the score: no per-tile maximum (FMNMX3), no second FFMA2 for the exponent, no
+// (max, sum) merges, no 64 live score registers -- a thread carries FOUR rows (a group's parameters are loaded once
+// per four cells) and a slot is a plain sum.  Ratios of weights do not depend on the reference, and for every term that
+// matters (exponent near 0) both summands of the FFMA2 are small, so it is rounded finer than a score near -50 was.
+// What a static reference cannot promise is range: a row whose best score lies far below M* (an outlier to every group)
+// would lose its small terms to underflow.  Rows whose total comes out below 2^-40 (flushed terms are then < 2^-86 of
+// the total) are therefore re-evaluated by nich2_row_exact with their own maximum; with the empty group a Pitman-Yor
+// mixture always carries (broad prior predictive), such rows do not occur in practice.
+constexpr int kN2Rows = 4;
+constexpr int kN2PolyDefault = 5;  // same-box sweep at c2: 0 / 3 / 4 / 5 / 6 / 8 / 10 / 12 of 16 -> 0.534 / 0.502 / 0.494 / 0.482 / 0.507 / 0.502 / 0.504 / 0.537 ms
+constexpr float kN2Redo = 9.094947e-13f;  // 2^-40
+
+struct Nich2Geom {
+    int G, nchunks, cps, nslots, slot_groups;
+    const float4 *caches;  // pair p at float4 index 2 p + (2 p) / slot_groups: {-mean a, -mean b, prec a, prec b}, {co a, co b, sc' a, sc' b}
+    float *slots;          // [R][kSlots][kNrThreads] sums of weights
+};
+
+// exponent of one cell: co lg2(fast_log argument) + sc'  (the unfused 1 + prec d^2 of nich.cc:59-65, table-step mantissa)
+__device__ __forceinline__ float nich2_arg(const Nich2Geom &g, int gi, float x) {
+    const int p = gi >> 1, at = 2 * p + (2 * p) / g.slot_groups;
+    const float4 qa = g.caches[at], qb = g.caches[at + 1];
+    const bool hi = gi & 1;
+    const float d = x + (hi ? qa.y : qa.x);
+    const float z = __fadd_rn(1.f, __fmul_rn(hi ? qa.w : qa.z, __fmul_rn(d, d)));
+    return fmaf(hi ? qb.y : qb.x, fast_log2_cell(z), hi ? qb.w : qb.z);
+}
+
+// scores_to_likelihoods + sample_from_likelihoods with the row's own maximum (random.cc:94-106, random.hpp:315-333)
+__device__ __noinline__ int nich2_row_exact(const Nich2Geom &g, float x, float u) {
+    float m = -INFINITY;
+    for (int gi = 0; gi < g.G; ++gi) m = fmaxf(m, nich2_arg(g, gi, x));
+    float total = 0.f;
+    for (int gi = 0; gi < g.G; ++gi) total += mufu_ex2(nich2_arg(g, gi, x) - m);
+    float t = total * u;
+    int count = 0;
+    for (int gi = 0; gi < g.G; ++gi) {
+        t -= mufu_ex2(nich2_arg(g, gi, x) - m);
+        count += 1 - static_cast<int>(__float_as_uint(t) >> 31);
+    }
+    return min(count, g.G - 1);
+}
+
+template <int kPoly, int R>
+__device__ __forceinline__ void nich2_tile(const Nich2Geom &g, const float (&xrow)[R], const float (&urow)[R], const size_t (&row)[R],
+                                           size_t N, int32_t *__restrict__ assign) {
+    const int tid = threadIdx.x;
+    const uint64_t one2 = f2_pack(1.f, 1.f);
+    uint64_t x2[R], sa[R], sb[R];  // two partial sums per row: even / odd pairs
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        x2[r] = f2_pack(xrow[r], xrow[r]);
+        sa[r] = sb[r] = f2_pack(0.f, 0.f);
+    }
+    // weights of one pair of groups for row r; kPoly of every 16 pairs on the FMA pipe (same choice in both passes)
+    auto pair_weights = [&](const float4 &qa, const float4 &qb, int r, int j) {
+        const uint64_t d2 = f2_add(x2[r], f2_pack(qa.x, qa.y));
+        const uint64_t z2 = f2_fma(f2_mul(f2_pack(qa.z, qa.w), f2_mul(d2, d2)), one2, one2);  // unfused 1 + w (see score_rows.cuh)
+        float za, zb;
+        f2_unpack(z2, za, zb);
+        const uint64_t a2 = f2_fma(f2_pack(qb.x, qb.y), f2_pack(fast_log2_cell(za), fast_log2_cell(zb)), f2_pack(qb.z, qb.w));
+        if (((j / 2) * kPoly) % 16 < kPoly) return poly_ex2_pair(a2);
+        float ea, eb;
+        f2_unpack(a2, ea, eb);
+        return f2_pack(mufu_ex2(ea), mufu_ex2(eb));
+    };
+    for (int c = 0; c < g.nchunks; ++c) {
+        const float4 *p4 = g.caches + c * kNrChunk + c / g.cps;
+#pragma unroll
+        for (int j = 0; j < kNrChunk; j += 2) {  // parameters once, all rows
+            const float4 qa = p4[j], qb = p4[j + 1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint64_t e2 = pair_weights(qa, qb, r, j);
+                if (j & 2) sb[r] = f2_add(sb[r], e2);
+                else sa[r] = f2_add(sa[r], e2);
+            }
+        }
+        if ((c + 1) % g.cps == 0 || c + 1 == g.nchunks) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float a0, a1;
+                f2_unpack(f2_add(sa[r], sb[r]), a0, a1);
+                g.slots[(r * kSlots + c / g.cps) * kNrThreads + tid] = a0 + a1;
+                sa[r] = sb[r] = f2_pack(0.f, 0.f);
+            }
+        }
+    }
+    // per row: total over the slots, walk to the slot holding u * total, re-form that slot's weights, walk its cells
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float *sl = g.slots + (r * kSlots) * kNrThreads + tid;
+        float total = 0.f;
+        for (int k = 0; k < g.nslots; ++k) total += sl[k * kNrThreads];
+        int result;
+        if (!(total >= kN2Redo)) {
+            result = nich2_row_exact(g, xrow[r], urow[r]);  // an outlier to every group: its own maximum
+        } else {
+            float t = total * urow[r];
+            int sel = g.nslots - 1;
+            for (int k = 0; k < g.nslots; ++k) {
+                const float w = sl[k * kNrThreads];
+                if (t <= w) {
+                    sel = k;
+                    break;
+                }
+                if (k + 1 < g.nslots) t -= w;
+            }
+            int count = 0;
+            for (int cc = 0; cc < g.cps; ++cc) {
+                const int c = sel * g.cps + cc;
+                if (c >= g.nchunks) break;
+                const float4 *p4 = g.caches + c * kNrChunk + sel;
+#pragma unroll
+                for (int j = 0; j < kNrChunk; j += 2) {
+                    float ea, eb;
+                    f2_unpack(pair_weights(p4[j], p4[j + 1], r, j), ea, eb);
+                    t -= ea;
+                    count += 1 - static_cast<int>(__float_as_uint(t) >> 31);  // t >= +0 continues (an exact 0: a near-tie)
+                    t -= eb;
+                    count += 1 - static_cast<int>(__float_as_uint(t) >> 31);
+                }
+            }
+            result = min(sel * g.slot_groups + count, g.G - 1);
+        }
+        if (row[r] < N) assign[row[r]] = result;
+    }
+}
+
+// rows are dealt in units of 256 (one row per thread) as in nich_rows_kernel; a block evaluates its run four units at a
+// time and the remainder with the two- and one-row forms
+template <int kPoly, int RT, int kBlocks>
+__global__ void __launch_bounds__(kNrThreads, kBlocks) nich_rows2_kernel(const NichRowsArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float red[kNrThreads / 32];
+    Nich2Geom g;
+    g.G = a.G;
+    g.nchunks = (a.G + kNrChunk - 1) / kNrChunk;
+    const int Gpad = g.nchunks * kNrChunk;
+    g.cps = (g.nchunks + kSlots - 1) / kSlots;
+    g.nslots = (g.nchunks + g.cps - 1) / g.cps;
+    g.slot_groups = g.cps * kNrChunk;
+    float4 *caches = reinterpret_cast<float4 *>(smem);
+    g.caches = caches;
+    g.slots = reinterpret_cast<float *>(caches + Gpad + g.nslots);
+    const int tid = threadIdx.x;
+
+    // M* = max over the real groups of prior + score (the same value in every block)
+    float m = -INFINITY;
+    for (int gi = tid; gi < a.G; gi += kNrThreads) m = fmaxf(m, a.params[gi].w + (a.prior ? a.prior[gi] : 0.f));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < kNrThreads / 32; ++w) m = fmaxf(m, red[w]);
+    // block-private parameter copy: padded groups get sc' = -inf and borrow group 0's mean / precision / coefficient
+    for (int p = tid; p < Gpad / 2; p += kNrThreads) {
+        float4 q[2];
+        float sc[2], co[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int gi = 2 * p + k;
+            q[k] = a.params[gi < a.G ? gi : 0];
+            const float s = q[k].w + (a.prior ? a.prior[gi < a.G ? gi : 0] : 0.f);
+            sc[k] = gi < a.G ? (s - m) * kLog2e : -INFINITY;
+            co[k] = static_cast<float>(static_cast<double>(q[k].z) * 1.4426950408889634);  // log_coeff ln 2 -> log_coeff (lg2 scale)
+        }
+        const int at = 2 * p + (2 * p) / g.slot_groups;
+        caches[at] = make_float4(-q[0].x, -q[1].x, q[0].y, q[1].y);
+        caches[at + 1] = make_float4(co[0], co[1], sc[0], sc[1]);
+    }
+    __syncthreads();
+
+    const size_t nunits = (a.N + kNrThreads - 1) / kNrThreads;
+    const size_t base = nunits / gridDim.x, rem = nunits % gridDim.x;
+    const size_t h0 = blockIdx.x * base + (blockIdx.x < rem ? blockIdx.x : rem);
+    const size_t h1 = h0 + base + (blockIdx.x < rem ? 1 : 0);
+    float xnext[RT], unext[RT];
+    auto fetch = [&](size_t h) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const size_t rw = (h + r) * kNrThreads + tid;
+            const size_t rr = rw < a.N ? rw : a.N - 1;  // clamp: compute on a real row, discard the result
+            xnext[r] = __ldg(a.values + rr);
+            unext[r] = __ldg(a.u + rr);
+        }
+    };
+    if (h0 < h1) fetch(h0);
+    size_t h = h0;
+    for (; h + RT <= h1; h += RT) {
+        size_t row[RT];
+        float xrow[RT], urow[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            row[r] = (h + r) * kNrThreads + tid;
+            xrow[r] = xnext[r];
+            urow[r] = unext[r];
+        }
+        if (h + RT < h1) fetch(h + RT);
+        nich2_tile<kPoly, RT>(g, xrow, urow, row, a.N, a.assign);
+    }
+    int left = static_cast<int>(h1 - h), at = 0;  // 0..RT-1 units: xnext / unext hold their rows
+    if (RT >= 4 && left >= 2) {
+        const size_t row[2] = {h * kNrThreads + tid, (h + 1) * kNrThreads + tid};
+        const float xrow[2] = {xnext[0], xnext[1]}, urow[2] = {unext[0], unext[1]};
+        nich2_tile<kPoly, 2>(g, xrow, urow, row, a.N, a.assign);
+        left -= 2;
+        at = 2;
+    }
+    if (left) {
+        const size_t row[1] = {(h + at) * kNrThreads + tid};
+        const float xrow[1] = {at ? xnext[RT >= 4 ? 2 : 0] : xnext[0]}, urow[1] = {at ? unext[RT >= 4 ? 2 : 0] : unext[0]};
+        nich2_tile<kPoly, 1>(g, xrow, urow, row, a.N, a.assign);
+    }
+}
+
+template <int kPoly, int RT = kN2Rows, int kBlocks = 2>
+static int launch_nich_rows2_t(dist_b200_ctx *ctx, const NichRowsArgs &a, size_t smem, cudaStream_t s) {
+    smem -= sizeof(float) * (kN2Rows - RT) * kSlots * kNrThreads;
+    DISTB200_CUDA(ctx, cudaFuncSetAttribute(nich_rows2_kernel<kPoly, RT, kBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    DISTB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nich_rows2_kernel<kPoly, RT, kBlocks>, kNrThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const size_t tile_rows = static_cast<size_t>(kNrThreads) * RT;
+    const size_t ntiles = (a.N + tile_rows - 1) / tile_rows;
+    const size_t cap = static_cast<size_t>(ctx->sm_count) * per_sm;
+    nich_rows2_kernel<kPoly, RT, kBlocks><<<static_cast<unsigned>(ntiles < cap ? ntiles : cap), kNrThreads, smem, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("nich_rows2 launch: ") + cudaGetErrorString(e));
+    return DIST_B200_OK;
+}
+
 template <int kPoly>
 static int launch_nich_rows_t(dist_b200_ctx *ctx, const NichRowsArgs &a, size_t smem, cudaStream_t s) {
     DISTB200_CUDA(ctx, cudaFuncSetAttribute(nich_rows_kernel<kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -254,7 +495,6 @@ int launch_nich_rows(dist_b200_ctx *ctx, const float4 *params, const void *colum
     const int cps = (nchunks + kSlots - 1) / kSlots;
     const int nslots = (nchunks + cps - 1) / cps;
     const size_t smem = sizeof(float4) * (Gpad + nslots) + sizeof(float2) * kNrRows * kSlots * kNrThreads;
-    if (smem > 110 * 1024) return DIST_B200_ERR_UNSUPPORTED;  // two blocks per SM
     NichRowsArgs a{};
     a.G = G;
     a.N = N;
@@ -263,14 +503,25 @@ int launch_nich_rows(dist_b200_ctx *ctx, const float4 *params, const void *colum
     a.values = static_cast<const float *>(column);
     a.u = u;
     a.assign = assign;
+    // default: the static-reference kernel, four rows per thread (nich_rows2_kernel); DIST_B200_OPT_NICH_PACKED = 3 (A/B runs):
+    // the two-row kernel with per-tile maxima it replaced.  DIST_B200_OPT_EXP_OFFLOAD: 0 = default, 1 = every exp2 on the
+    // MUFU pipe, 1 + k = k of every 16 pairs on the FMA pipe
+    if (ctx->opt[DIST_B200_OPT_NICH_PACKED] != 3) {
+        const size_t smem2 = sizeof(float4) * (Gpad + nslots) + sizeof(float) * kN2Rows * kSlots * kNrThreads;
+        if (smem2 > 220 * 1024) return DIST_B200_ERR_UNSUPPORTED;  // (one block per SM beyond ~2 800 groups)
+        switch (ctx->opt[DIST_B200_OPT_EXP_OFFLOAD]) {
+            case 1: return launch_nich_rows2_t<0>(ctx, a, smem2, s);
+            case 5: return launch_nich_rows2_t<4>(ctx, a, smem2, s);
+            case 7: return launch_nich_rows2_t<6>(ctx, a, smem2, s);
+            case 9: return launch_nich_rows2_t<8>(ctx, a, smem2, s);
+            default: return launch_nich_rows2_t<kN2PolyDefault>(ctx, a, smem2, s);
+        }
+    }
+    if (smem > 110 * 1024) return DIST_B200_ERR_UNSUPPORTED;  // two blocks per SM
     // DIST_B200_OPT_EXP_OFFLOAD (A/B runs): 0 = default, 1 = every exp2 on the MUFU pipe, 1 + k = k of 16 pairs on the FMA pipe
     switch (ctx->opt[DIST_B200_OPT_EXP_OFFLOAD]) {
         case 1: return launch_nich_rows_t<0>(ctx, a, smem, s);
-        case 3: return launch_nich_rows_t<2>(ctx, a, smem, s);
         case 5: return launch_nich_rows_t<4>(ctx, a, smem, s);
-        case 6: return launch_nich_rows_t<5>(ctx, a, smem, s);
-        case 7: return launch_nich_rows_t<6>(ctx, a, smem, s);
-        case 8: return launch_nich_rows_t<7>(ctx, a, smem, s);
         case 9: return launch_nich_rows_t<8>(ctx, a, smem, s);
         default: return launch_nich_rows_t<kNrPolyDefault>(ctx, a, smem, s);
     }

@@ -78,13 +78,14 @@ typedef enum {
     DIST_B200_OPT_SMALL_TILE = 5,  /* score_rows, single feature, 64 < G <= 128: 0 = default, 1 = one 128-group tile x 256 threads
                                       (round 1), 2 = 128 threads x 3 blocks / SM with a 128-group tile, 3 = four 32-group tiles;
                                       default: 128 threads x 3, tile = G rounded up to 16 when only sampling */
-    DIST_B200_OPT_NICH_PACKED = 6, /* nich single feature: 0 = default (packed fp32x2; sampling-only G > 128: two rows per thread),
-                                      1 = scalar loop (round 1), 2 = packed fp32x2 loop with one row per thread */
+    DIST_B200_OPT_NICH_PACKED = 6, /* nich single feature: 0 = default (packed fp32x2; sampling-only G > 128: static softmax reference,
+                                      four rows per thread), 1 = scalar loop (round 1), 2 = packed fp32x2 loop with one row per thread,
+                                      3 = sampling-only G > 128 with per-tile maxima, two rows per thread (the kernel the default replaced) */
     DIST_B200_OPT_NIW_DEBUG = 7,   /* profiling only, results are WRONG when set: 1 = skip the fused sampling walk, 2 = also the epilogue math */
     DIST_B200_OPT_HOST_ZEROCOPY = 8, /* host-buffer entry with page-locked caller buffers: 0 = kernels read / write the host buffers
                                       directly (one launch, no staging), 1 = staged row chunks over two streams (round 1) */
     DIST_B200_OPT_EXP_OFFLOAD = 9, /* nich sampling kernel (G > 128): share of the softmax exp2 evaluated on the FMA pipe (Cody-Waite +
-                                      degree-5 polynomial) instead of MUFU.EX2: 0 = default (6 of every 16 pairs), 1 = none, 1 + k = k of every 16 pairs (k = 2, 4 .. 8) */
+                                      degree-5 polynomial) instead of MUFU.EX2: 0 = default (5 of every 16 pairs), 1 = none, 1 + k = k of every 16 pairs (k = 4, 6, 8) */
     DIST_B200_OPT_COUNT_ = 16
 } dist_b200_option;
 int dist_b200_ctx_set_option(dist_b200_ctx *ctx, int option, int value);

@@ -65,6 +65,8 @@ FUSED_VARIANTS = {
     "small_tile_4x32": {0: 1, 5: 3},                # 64 < G <= 128: four 32-group tiles
     "nich_scalar": {6: 1},                          # nich: scalar loop instead of packed fp32x2
     "nich_packed_one_row": {6: 2},                  # nich: packed loop, one row per thread (default: two rows for G > 128)
+    "nich_online_max_two_rows": {6: 3},             # nich G > 128: the two-row kernel with per-tile maxima (default: static reference, four rows)
+    "nich_online_max_mufu": {6: 3, 9: 1},           # ... every exp2 on the MUFU pipe
     "nich_exp_all_mufu": {9: 1},                    # nich G > 128: every softmax exp2 on the MUFU pipe
     "nich_exp_offload_4": {9: 5},                   # ... 4 of 16 pairs on the FMA pipe (polynomial)
     "nich_exp_offload_8": {9: 9},                   # ... 8 of 16
@@ -637,6 +639,29 @@ def test_host_entry_pinned_and_chunked(ctx, oracle):
     assert np.array_equal(assign, a_dev)
     assign2, _ = ctx.score_sample_batch_host([f], [w["values"]], prior, w["u"])  # pageable: staged
     assert np.array_equal(assign2, a_dev)
+
+
+def test_nich_outlier_rows(ctx, oracle):
+    """rows far from every group (no broad empty group to catch them): every score lies hundreds of nats below the best
+    group constant, the regime where a static softmax reference would underflow -- the sampling kernels must still agree
+    with the oracle's sampler on the materialised scores (nich_rows2: rows re-evaluated with their own maximum)"""
+    n, G = 40_000, 300
+    w = synth.nich(77, G, n)
+    # every group well populated (steep Student-t tails, no empty group), a third of the rows thousands of sigmas away
+    rng = np.random.default_rng(78)
+    w["count"] = np.maximum(w["count"], 60).astype(w["count"].dtype)
+    w["sizes"] = w["count"].astype(w["sizes"].dtype)
+    w["mean"] = rng.normal(0.0, 5.0, G).astype(np.float32)
+    w["ctv"] = (w["count"] * rng.uniform(0.5, 2.0, G)).astype(np.float32)
+    far = np.arange(n) % 3 == 0
+    w["values"] = rng.normal(0.0, 5.0, n).astype(np.float32)
+    w["values"][far] = np.where(np.arange(far.sum()) % 2 == 0, 3e4, -7e5).astype(np.float32) + w["values"][far]
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    assign, scores = run_cuda(ctx, [w], prior, w["u"], n)
+    assert scores[far].max(axis=1).max() < scores[~far].max(axis=1).min() - 100.0  # they really are outliers
+    a_orc = oracle.sample_rows(scores.copy(), w["u"])
+    assert cases.explained_mismatch(scores.astype(np.float64), w["u"], assign, a_orc, EPS_TIE).all()
+    check_fused_variants(ctx, [w], prior, w["u"], n, scores, assign)
 
 
 def test_host_register(ctx, oracle):
