@@ -44,6 +44,7 @@ WORKLOADS = {
     "c5_niw": dict(model="niw", G=256, N=1_000_000, seed=20245, d=32),
     # beyond BASELINE.json (A/B harness only, --workload): the cross-cat kind with more groups than one register tile
     "x_crosscat_g256": dict(model="crosscat", G=256, N=200_000, seed=20246, n_gp=128, n_bb=128),
+    "x_crosscat_g256_1m": dict(model="crosscat", G=256, N=1_000_000, seed=20246, n_gp=128, n_bb=128),
     "x_crosscat_g1024": dict(model="crosscat", G=1024, N=100_000, seed=20247, n_gp=128, n_bb=128),
 }
 HEADLINE = "c2_nich"

@@ -305,6 +305,7 @@ void dist_b200_ctx_destroy(dist_b200_ctx *ctx) {
     if (ctx->add_done) cudaEventDestroy(ctx->add_done);
     if (ctx->scores_scratch) cudaFree(ctx->scores_scratch);
     if (ctx->xpack) cudaFree(ctx->xpack);
+    if (ctx->bbt) cudaFree(ctx->bbt);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->own_stream2) cudaStreamDestroy(ctx->own_stream2);

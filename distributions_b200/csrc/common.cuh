@@ -88,6 +88,8 @@ struct dist_b200_ctx {
     size_t scratch_bytes = 0;
     void *xpack = nullptr;            // niw tensor path: rows packed into A-operand images
     size_t xpack_bytes = 0;
+    float *bbt = nullptr;             // kSub cross-cat kernel: compact [heads | tails] rows of the list's BetaBernoulli features
+    size_t bbt_floats = 0;
     void *scores_scratch = nullptr;   // [N][G] buffer of the materialising dispatch paths
     size_t scores_scratch_bytes = 0;
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;

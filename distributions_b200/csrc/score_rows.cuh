@@ -767,11 +767,15 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                             if (jj == j) sc16[jj] += v;
                     }
                 } else if (fd.kind == DIST_B200_BB) {
-                    const float2 *bp = reinterpret_cast<const float2 *>(static_cast<const float4 *>(fd.params) + gb);
+                    // compact copy [heads[Gpad] | tails[Gpad]] made for this launch (bb_compact_kernel): 64 contiguous bytes
+                    const float4 *bp = reinterpret_cast<const float4 *>(static_cast<const float *>(fd.aux) + (xv ? 0 : fd.cap) + gb);
 #pragma unroll
-                    for (int j = 0; j < kSubGroups; ++j) {
-                        const float2 q = __ldg(bp + 2 * j);
-                        sc16[j] += xv ? q.x : q.y;
+                    for (int q = 0; q < kSubGroups / 4; ++q) {
+                        const float4 v = __ldg(bp + q);
+                        sc16[4 * q] += v.x;
+                        sc16[4 * q + 1] += v.y;
+                        sc16[4 * q + 2] += v.z;
+                        sc16[4 * q + 3] += v.w;
                     }
                 } else {
                     const int st = kind_stride(fd.kind, fd.vdim);
@@ -875,6 +879,19 @@ static int launch_modes(dist_b200_ctx *ctx, const FeatList &feats, const RowsArg
     return launch_variant<CHUNK, KIND, false, true, THREADS>(ctx, feats, a, s);
 }
 
+// kSub launches: heads / tails of every BetaBernoulli feature of the list as two contiguous rows (the float4 caches hold
+// them 16 bytes apart: the 16-group re-score would touch eight sectors per feature instead of two)
+static __global__ void __launch_bounds__(256) bb_compact_kernel(const __grid_constant__ FeatList feats, int Gpad) {
+    const FeatDesc &fd = feats.f[blockIdx.y];
+    if (fd.kind != DIST_B200_BB) return;
+    float *out = const_cast<float *>(static_cast<const float *>(fd.aux));
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < Gpad; g += gridDim.x * blockDim.x) {
+        const float4 q = static_cast<const float4 *>(fd.params)[g];
+        out[g] = q.x;
+        out[Gpad + g] = q.y;
+    }
+}
+
 // Register tile.  G <= 128: the whole row in one tile (the sampler is then the reference's loops on registers);
 // 64 < G <= 128 of a single feature runs 128-thread blocks, three per SM (12 warps instead of the 8 of one
 // 256-thread block: the row-wide dependent chains of max / total / walk need the extra warps to hide their
@@ -903,12 +920,37 @@ static int launch_tiers(dist_b200_ctx *ctx, const FeatList &feats, const RowsArg
     if constexpr (KIND < 0) if (a.assign && !a.scores && !a.n_push && ctx->opt[DIST_B200_OPT_ROW_TILE] == 0) {
         // feature lists too large to keep resident (a cross-cat kind): the 128-group streaming tiles of the G <= 128 case
         // with sub-slot bookkeeping (kSub); measured at 256 features against the 32-group tiles + per-cell re-score of a whole
-        // slot from global memory: G = 256, 200k rows 11.7 -> 3.74 ms; G = 1024, 100k rows 15.3 -> 7.63 ms, identical draws
+        // slot from global memory: G = 256, 1M rows 53.4 -> 14.9 ms; G = 1024, 100k rows 15.3 -> 7.19 ms
         size_t cache_bytes = 0;
         for (int f = 0; f < feats.n; ++f)
             cache_bytes += sizeof(float) * static_cast<size_t>((a.G + 31) / 32 * 32) * kind_stride(feats.f[f].kind, feats.f[f].vdim);
         if (cache_bytes > kResidentBudget) {
-            const int rc = launch_variant<128, KIND, true, false, 128, true>(ctx, feats, a, s);
+            const int Gpad = (a.G + 127) / 128 * 128;  // <= every feature's capacity (ensure_params pads to 128 groups)
+            int n_bb = 0;
+            for (int f = 0; f < feats.n; ++f) n_bb += feats.f[f].kind == DIST_B200_BB ? 1 : 0;
+            const size_t need = static_cast<size_t>(n_bb) * 2 * Gpad;
+            if (need > ctx->bbt_floats) {
+                if (ctx->bbt) {
+                    DISTB200_CUDA(ctx, cudaDeviceSynchronize());
+                    DISTB200_CUDA(ctx, cudaFree(ctx->bbt));
+                    ctx->bbt = nullptr;
+                    ctx->bbt_floats = 0;
+                }
+                DISTB200_CUDA(ctx, cudaMalloc(&ctx->bbt, need * sizeof(float)));
+                ctx->bbt_floats = need;
+            }
+            FeatList local = feats;
+            for (int f = 0, k = 0; f < local.n; ++f)
+                if (local.f[f].kind == DIST_B200_BB) {
+                    local.f[f].aux = ctx->bbt + static_cast<size_t>(k++) * 2 * Gpad;
+                    local.f[f].cap = Gpad;
+                }
+            if (n_bb) {
+                bb_compact_kernel<<<dim3((Gpad + 255) / 256, local.n), 256, 0, s>>>(local, Gpad);
+                cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("bb_compact launch: ") + cudaGetErrorString(e));
+            }
+            const int rc = launch_variant<128, KIND, true, false, 128, true>(ctx, local, a, s);
             if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;  // (too many groups for the sub-slot sums in shared memory)
         }
     }
