@@ -1613,6 +1613,12 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
     if (F == 1 && features[0]->model == DIST_B200_NIW && features[0]->dim == 32 && features[0]->niw_tc && assign && !scores &&
         !accumulate && ctx->opt[DIST_B200_OPT_NIW_PATH] == 0)
         return launch_niw_tc(ctx, G, features[0]->niw_tc, columns[0], N, prior, nullptr, 0, u, assign, s);
+    // one NIW feature with d <= 8, sampling only: the fused FP32 kernel (DIST_B200_OPT_NIW_PATH = 1 keeps the materialising route)
+    if (F == 1 && features[0]->model == DIST_B200_NIW && features[0]->dim <= 8 && assign && !scores && !accumulate &&
+        ctx->opt[DIST_B200_OPT_NIW_PATH] == 0) {
+        const int rc = launch_niw_rows_small(ctx, features[0], columns[0], N, prior, u, assign, s);
+        if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;
+    }
     if (F == 1 && features[0]->model == DIST_B200_DPD) {
         if (assign && !scores && !accumulate && ctx->opt[DIST_B200_OPT_TABLE_KERNEL] == 0) {
             const int rc = launch_table_rows(ctx, features[0], columns[0], N, prior, u, assign, s);

@@ -229,6 +229,8 @@ int launch_value_cdf(dist_b200_ctx *ctx, const dist_b200_feature *f, float *buf,
 int niw_padded_dim(int d);
 int launch_niw_prep(dist_b200_ctx *ctx, int d, const float *mu, float kappa, const float *psi, float nu, int G,
                     const int32_t *count, const float *sum_x, const float *sum_xxT, float *recs, cudaStream_t s);
+int launch_niw_rows_small(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *values, size_t N, const float *prior,
+                          const float *u, int32_t *assign, cudaStream_t s);
 int launch_niw_scores(dist_b200_ctx *ctx, const dist_b200_feature *f, const void *values, size_t N,
                       const float *prior, float *scores, int accumulate, cudaStream_t s);
 int launch_score_data_finish(dist_b200_ctx *ctx, size_t n_grid, const double *acc, float *out_dev, cudaStream_t s);  // prep.cu

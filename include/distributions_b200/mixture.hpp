@@ -71,6 +71,16 @@ class Context {
         if (rc != DIST_B200_OK)
             throw std::runtime_error(std::string(what) + ": " + dist_b200_last_error(ctx_));
     }
+    // page-lock a caller-owned array once (e.g. the std::vector<Value> a sampler keeps its column in): every later
+    // host-buffer call on it is zero-copy.  Unregister before the storage is freed or reallocated.
+    template <class T>
+    void host_register(std::vector<T> & v) const {
+        if (!v.empty()) check(dist_b200_host_register(ctx_, v.data(), v.size() * sizeof(T)), "host_register");
+    }
+    template <class T>
+    void host_unregister(std::vector<T> & v) const {
+        if (!v.empty()) check(dist_b200_host_unregister(ctx_, v.data()), "host_unregister");
+    }
 
   private:
     dist_b200_ctx * ctx_ = nullptr;

@@ -526,6 +526,38 @@ def test_niw_vs_oracle(ctx, oracle, d, G):
     assert assign.min() >= 0 and assign.max() < G
 
 
+@pytest.mark.parametrize("d,G", [(1, 40), (2, 9), (3, 64), (4, 300), (5, 33), (8, 256)])
+def test_niw_small_d_fused(ctx, oracle, d, G):
+    """d <= 8, sampling only: niw_rows_kernel (scores never materialised, static softmax reference) against the oracle's
+    sampler on the materialising route's scores -- every mismatch a near-tie -- incl. a ragged last tile, rows far
+    from every group (re-evaluated with their own maximum) and the materialising route selected by option"""
+    from distributions_b200 import capi
+    n = 20_011
+    w = synth.niw(700 + d + G, G, n, d=d)
+    w["values"] = w["values"].copy()
+    w["values"][::7] *= 300.0  # outliers to every group
+    prior = oracle.py_prior(synth.PY_ALPHA, synth.PY_D, w["sizes"])
+    assign, scores = _niw_cuda(ctx, w, n, prior)
+    a_orc = oracle.sample_rows(scores.copy(), w["u"][:n])
+    assert cases.explained_mismatch(scores.astype(np.float64), w["u"][:n], assign, a_orc, EPS_TIE).all()
+    f = ctx.feature(capi.NIW).update_all(w)
+    col, u_d, prior_d = dev(np.ascontiguousarray(w["values"], dtype=np.float32)), dev(w["u"]), dev(prior)
+    for path in (0, 1):
+        ctx.set_option(capi.OPT_NIW_PATH, path)
+        try:
+            a_f = torch.full((n,), -3, device="cuda", dtype=torch.int32)
+            ctx.score_sample_batch([f], [col], n, prior_d, u_d, a_f, None)
+            torch.cuda.synchronize()
+        finally:
+            ctx.set_option(capi.OPT_NIW_PATH, 0)
+        a_f = a_f.cpu().numpy()
+        assert a_f.min() >= 0 and a_f.max() < G
+        diff = np.nonzero(a_f != assign)[0]
+        assert diff.size <= max(2, 2e-3 * n), (path, diff.size)
+        if diff.size:
+            assert cases.explained_mismatch(scores[diff].astype(np.float64), w["u"][:n][diff], assign[diff], a_f[diff], EPS_TIE).all(), path
+
+
 @pytest.fixture(scope="module")
 def golden_niw():
     import os
