@@ -55,7 +55,7 @@ NCU_SUMMARY = {
     "c2_nich": "r02_c2_nich_rows_v3_static_reference.txt",
     "c1_dd_steady": "r02_c1_dd_steady.txt",
     "c3_crosscat": "r02_c3_crosscat.txt",
-    "c4_dpd": "r02_c4_dpd_table_rows.txt",
+    "c4_dpd": "r02_c4_dpd_table_rows_v2_staged_walk.txt",
     "c5_niw": "r02_c5_niw_fused.txt",
 }
 
@@ -279,7 +279,7 @@ def binding_roofline(name, wl, ms, peaks, cdf_shortcut=False, materialise=False)
         r = {"bound": "sfu", "achieved": cells * mufu_per_cell / t / 1e9, "peak": peaks.mufu / 1e9, "unit": "G MUFU lane-ops/s",
              "frac": t_sfu / t, "mufu_per_cell": mufu_per_cell, "t_roof_ms": t_sfu * 1e3,
              "peak_source": "measured here (dist_b200_pipe_peak: register-only ex2 / lg2 chains)",
-             "kernel": {"dd": "score_rows_kernel<112, dd scaled table, 128 threads>", "nich": "nich_rows2_kernel<5> (packed fp32x2, static softmax reference, four rows per thread, 5 of 16 exp2 pairs on the FMA pipe)", "dpd": "table_rows_kernel<4>"}[model]}
+             "kernel": {"dd": "score_rows_kernel<112, dd scaled table, 128 threads>", "nich": "nich_rows2_kernel<5> (packed fp32x2, static softmax reference, four rows per thread, 5 of 16 exp2 pairs on the FMA pipe)", "dpd": "table_rows_kernel<4, staged walk, 1 of 4 quads on the FMA pipe>"}[model]}
         if model == "dpd":  # max(t_SFU, gathered bytes / measured L2 gather bandwidth)
             t_l2 = 4.0 * cells / peaks.l2_gather
             r["l2_gather"] = {"gathered_bytes": 4.0 * cells, "achieved_gbs": 4.0 * cells / t / 1e9, "peak_gbs": peaks.l2_gather / 1e9,

@@ -1620,7 +1620,7 @@ static int score_dispatch(dist_b200_ctx *ctx, const dist_b200_feature *const *fe
         if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;
     }
     if (F == 1 && features[0]->model == DIST_B200_DPD) {
-        if (assign && !scores && !accumulate && ctx->opt[DIST_B200_OPT_TABLE_KERNEL] == 0) {
+        if (assign && !scores && !accumulate && ctx->opt[DIST_B200_OPT_TABLE_KERNEL] != 1) {
             const int rc = launch_table_rows(ctx, features[0], columns[0], N, prior, u, assign, s);
             if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;
         }

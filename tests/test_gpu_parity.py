@@ -60,6 +60,8 @@ FUSED_VARIANTS = {
     "value_cdf_tree": {0: 2},                       # per-value CDFs searched as 8-ary trees (default: guide-table walk)
     "row_tile_32": {1: 32},                         # G > 128: 32-group tiles + slots everywhere (also instead of the kSub streaming kernel)
     "no_value_cdf": {0: 1},                         # per-cell kernels: table_rows (dpd), score_rows (dd / bb)
+    "table_rows_walk_in_loop": {0: 1, 4: 2},        # dpd G in (384, 512]: every lane walks inside the row loop (default: the owner's walk staged)
+    "table_rows_all_mufu": {0: 1, 9: 1},            # dpd G in (384, 512]: every exp2 on the MUFU pipe
     "round1_gather": {0: 1, 4: 1},                  # dpd: round-1 warp-per-row gather kernel
     "small_tile_256": {0: 1, 5: 1},                 # 64 < G <= 128: one 256-thread block / SM
     "small_tile_4x32": {0: 1, 5: 3},                # 64 < G <= 128: four 32-group tiles
