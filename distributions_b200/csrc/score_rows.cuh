@@ -348,6 +348,16 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     // (blocks that finish early free MUFU issue slots for their neighbours on the SM), and the extra loop
     // state cost the register-capped cross-cat kernel 8%.
     const size_t ntiles = (a.N + kThreads - 1) / kThreads;
+    // dd scaled-table kind (a tile of rows is ~3 us of work): the next tile's value and uniform are requested while the
+    // current tile is evaluated, so the load latency is not left to the other resident blocks
+    constexpr bool kPrefetch = kSample && is_dd_scaled(KIND);
+    uint32_t pre_v = 0;
+    float pre_u = 0.f;
+    if (kPrefetch && blockIdx.x < ntiles) {
+        const size_t r0 = min(static_cast<size_t>(blockIdx.x) * kThreads + tid, a.N - 1);
+        pre_v = load_value(DIST_B200_DD, feats.f[0].column, r0);
+        pre_u = a.u[r0];
+    }
     for (size_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
         const size_t tile_base = tile_id * kThreads;
         const size_t row_end = a.N;
@@ -357,7 +367,13 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
         float slot_m = INFINITY, slot_s = 0.f;  // slot being merged: negated scaled max, sum of exp
         float nmax = 0.f, tres = 0.f;           // finalisation state: row's negated scaled max, remaining draw
         int sel = 0, count = 0, result = 0;
-        const float urow = kSample ? a.u[row] : 0.f;
+        const float urow = kPrefetch ? pre_u : (kSample ? a.u[row] : 0.f);
+        const uint32_t vrow = pre_v;
+        if (kPrefetch && tile_id + gridDim.x < ntiles) {
+            const size_t rn = min((tile_id + gridDim.x) * kThreads + tid, a.N - 1);
+            pre_v = load_value(DIST_B200_DD, feats.f[0].column, rn);
+            pre_u = a.u[rn];
+        }
 
         for (int it = 0; it < nchunks + extra; ++it) {
             const bool fin = it >= nchunks;  // block-uniform: re-scoring the selected slot
@@ -523,7 +539,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                 // The walk stops on a pair; the pair's first likelihood is then recomputed (one more gather) to place the
                 // stop inside it.  Sign-bit counting as everywhere: an exact +0 continues (a near-tie).
                 const int vdim = KIND == kKindDdScaled16 ? 16 : feats.f[0].vdim;
-                const int vi = min(static_cast<int>(load_value(DIST_B200_DD, feats.f[0].column, row)), vdim - 1);
+                const int vi = min(static_cast<int>(vrow), vdim - 1);
                 const float *pb = caches + vi;
                 constexpr int PAIRS = CHUNK / 2, SEGP = PAIRS / 4;
                 static_assert(CHUNK % 8 == 0, "register tile: four segments of whole pairs");
