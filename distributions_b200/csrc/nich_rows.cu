@@ -384,6 +384,36 @@ __global__ void __launch_bounds__(kNrThreads, kBlocks) nich_rows2_kernel(const N
     g.slots = reinterpret_cast<float *>(caches + Gpad + g.nslots);
     const int tid = threadIdx.x;
 
+    // this block's run of 256-row units, and the request for its first piece before anything else
+    const size_t nunits = (a.N + kNrThreads - 1) / kNrThreads;
+    const size_t base = nunits / gridDim.x, rem = nunits % gridDim.x;
+    const size_t h0 = blockIdx.x * base + (blockIdx.x < rem ? blockIdx.x : rem);
+    const size_t h1 = h0 + base + (blockIdx.x < rem ? 1 : 0);
+    float xnext[RT], unext[RT];
+    auto fetch = [&](size_t hh, int cnt) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            if (r < cnt) {
+                const size_t rw = (hh + r) * kNrThreads + tid;
+                const size_t rr = rw < a.N ? rw : a.N - 1;  // clamp: compute on a real row, discard the result
+                xnext[r] = __ldg(a.values + rr);
+                unext[r] = __ldg(a.u + rr);
+            }
+        }
+    };
+    auto piece = [&](size_t hh, int lead_left) -> int {  // units of the next piece: 2 / 1 while leading units remain, then RT
+        if (hh >= h1) return 0;
+        if (RT >= 4 && lead_left >= 2) return 2;
+        if (lead_left >= 1) return 1;
+        return RT;
+    };
+    size_t h = h0;
+    int lead = static_cast<int>((h1 - h0) % RT);
+    int n = piece(h, lead);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) xnext[r] = unext[r] = 0.f;
+    if (n) fetch(h, n);
+
     // M* = max over the real groups of prior + score (the same value in every block)
     float m = -INFINITY;
     for (int gi = tid; gi < a.G; gi += kNrThreads) m = fmaxf(m, a.params[gi].w + (a.prior ? a.prior[gi] : 0.f));
@@ -412,23 +442,10 @@ __global__ void __launch_bounds__(kNrThreads, kBlocks) nich_rows2_kernel(const N
     }
     __syncthreads();
 
-    const size_t nunits = (a.N + kNrThreads - 1) / kNrThreads;
-    const size_t base = nunits / gridDim.x, rem = nunits % gridDim.x;
-    const size_t h0 = blockIdx.x * base + (blockIdx.x < rem ? blockIdx.x : rem);
-    const size_t h1 = h0 + base + (blockIdx.x < rem ? 1 : 0);
-    float xnext[RT], unext[RT];
-    auto fetch = [&](size_t h) {
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            const size_t rw = (h + r) * kNrThreads + tid;
-            const size_t rr = rw < a.N ? rw : a.N - 1;  // clamp: compute on a real row, discard the result
-            xnext[r] = __ldg(a.values + rr);
-            unext[r] = __ldg(a.u + rr);
-        }
-    };
-    if (h0 < h1) fetch(h0);
-    size_t h = h0;
-    for (; h + RT <= h1; h += RT) {
+    // the short leading pieces (run length mod RT: two units, then one) come FIRST: the block's first request for rows is
+    // small -- when the rows live in page-locked host memory every block's first fetch crosses PCIe with nothing to hide
+    // behind -- and the first full tile's rows arrive while the leading piece is evaluated
+    while (n) {
         size_t row[RT];
         float xrow[RT], urow[RT];
 #pragma unroll
@@ -437,21 +454,22 @@ __global__ void __launch_bounds__(kNrThreads, kBlocks) nich_rows2_kernel(const N
             xrow[r] = xnext[r];
             urow[r] = unext[r];
         }
-        if (h + RT < h1) fetch(h + RT);
-        nich2_tile<kPoly, RT>(g, xrow, urow, row, a.N, a.assign);
-    }
-    int left = static_cast<int>(h1 - h), at = 0;  // 0..RT-1 units: xnext / unext hold their rows
-    if (RT >= 4 && left >= 2) {
-        const size_t row[2] = {h * kNrThreads + tid, (h + 1) * kNrThreads + tid};
-        const float xrow[2] = {xnext[0], xnext[1]}, urow[2] = {unext[0], unext[1]};
-        nich2_tile<kPoly, 2>(g, xrow, urow, row, a.N, a.assign);
-        left -= 2;
-        at = 2;
-    }
-    if (left) {
-        const size_t row[1] = {(h + at) * kNrThreads + tid};
-        const float xrow[1] = {at ? xnext[RT >= 4 ? 2 : 0] : xnext[0]}, urow[1] = {at ? unext[RT >= 4 ? 2 : 0] : unext[0]};
-        nich2_tile<kPoly, 1>(g, xrow, urow, row, a.N, a.assign);
+        const int nc = n;
+        h += nc;
+        if (nc < RT) lead -= nc;
+        n = piece(h, lead);
+        if (n) fetch(h, n);
+        if (nc == RT) {
+            nich2_tile<kPoly, RT>(g, xrow, urow, row, a.N, a.assign);
+        } else if (nc == 2) {
+            const size_t row2[2] = {row[0], row[1]};
+            const float x2[2] = {xrow[0], xrow[1]}, u2[2] = {urow[0], urow[1]};
+            nich2_tile<kPoly, 2>(g, x2, u2, row2, a.N, a.assign);
+        } else {
+            const size_t row1[1] = {row[0]};
+            const float x1[1] = {xrow[0]}, u1[1] = {urow[0]};
+            nich2_tile<kPoly, 1>(g, x1, u1, row1, a.N, a.assign);
+        }
     }
 }
 
