@@ -273,8 +273,10 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
     const int F = kSingle ? 1 : feats.n;
     const bool resident = kSingle ? true : (a.resident != 0);
 
-    for (int i = tid; i < 33 * kLgammaRowStride; i += kThreads) coeff[i] = a.t.lgamma5[i];
-    if (tid < 64) logfact[tid] = a.t.log_factorial[tid];
+    if (!is_dd_scaled(KIND)) {  // (table lookups need neither; the dd kernel reuses the area as scratch)
+        for (int i = tid; i < 33 * kLgammaRowStride; i += kThreads) coeff[i] = a.t.lgamma5[i];
+        if (tid < 64) logfact[tid] = a.t.log_factorial[tid];
+    }
     // the prior vector (clustering's overwrite) seeds every accumulator; padded groups get -inf
     for (int g = tid; g < Gpad; g += kThreads)
         prior_s[g] = g < G ? ((a.prior && !a.accumulate) ? a.prior[g] : 0.f) : -INFINITY;
@@ -319,10 +321,31 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
             // per value: the maximum over groups, then (score - max) * log2e in place (a thread owns its value's column;
             // padded groups stay -inf)
             const int vdim = feats.f[0].vdim;
-            for (int v = tid; v < vdim; v += kThreads) {
-                float m = -INFINITY;
-                for (int g = 0; g < Gpad; ++g) m = fmaxf(m, caches[g * vdim + v]);
-                for (int g = 0; g < Gpad; ++g) caches[g * vdim + v] = (caches[g * vdim + v] - m) * kLog2e;
+            // threads cover (value, slice of the groups): with one thread per value the 2 x Gpad dependent shared-memory
+            // accesses of 16 threads were most of a small launch's time (c1 at 1e5 rows: ~9 us of prologue in a 17 us kernel).
+            // Partial maxima go through the lgamma coefficient area, which a dd kernel never reads.
+            const int nsl = vdim <= kThreads ? min(kThreads / vdim, (33 * kLgammaRowStride) / vdim) : 1;
+            if (nsl > 1) {
+                float *part = coeff;
+                const int v = tid % vdim, sl = tid / vdim;
+                const int per = (Gpad + nsl - 1) / nsl, ga = sl * per, gb = min(Gpad, ga + per);
+                if (sl < nsl) {
+                    float m = -INFINITY;
+                    for (int g = ga; g < gb; ++g) m = fmaxf(m, caches[g * vdim + v]);
+                    part[sl * vdim + v] = m;
+                }
+                __syncthreads();
+                if (sl < nsl) {
+                    float m = part[v];
+                    for (int k = 1; k < nsl; ++k) m = fmaxf(m, part[k * vdim + v]);
+                    for (int g = ga; g < gb; ++g) caches[g * vdim + v] = (caches[g * vdim + v] - m) * kLog2e;
+                }
+            } else {
+                for (int v = tid; v < vdim; v += kThreads) {
+                    float m = -INFINITY;
+                    for (int g = 0; g < Gpad; ++g) m = fmaxf(m, caches[g * vdim + v]);
+                    for (int g = 0; g < Gpad; ++g) caches[g * vdim + v] = (caches[g * vdim + v] - m) * kLog2e;
+                }
             }
             __syncthreads();
         }
