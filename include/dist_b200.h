@@ -68,7 +68,7 @@ int dist_b200_sm_count(const dist_b200_ctx *ctx);
  * any: 0 = the library's default everywhere).  The library reads no environment variables. */
 typedef enum {
     DIST_B200_OPT_VALUE_CDF = 0,   /* single dpd / dd / bb feature, sampling only: 0 = score once per distinct VALUE and
-                                      search per-value CDF trees per row (SURVEY.md 8d "algorithmic shortcut");
+                                      search per-value CDFs (guide tables; 8-ary trees for G > 1024) per row (SURVEY.md 8d "algorithmic shortcut");
                                       1 = evaluate every (row, group) cell (the no-shortcut kernels),
                                       2 = the shortcut with 8-ary tree search instead of the guide-table walk (G <= 1024) */
     DIST_B200_OPT_ROW_TILE = 1,    /* score_rows register tile for G > 128: 0 = default (32; 64 when the [N][G] scores are written), else 32 / 64 */
