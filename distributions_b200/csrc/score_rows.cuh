@@ -658,7 +658,7 @@ score_rows_kernel(const __grid_constant__ FeatList feats, const RowsArgs a) {
                     float m = acc[0];
 #pragma unroll
                     for (int j = 1; j < CHUNK; ++j) m = fmaxf(m, acc[j]);
-                    const float nm = fmaxf(-m * kLog2e, -3.0e38f);  // finite also when every group of the tile is at -inf... (+inf max cannot occur)
+                    const float nm = fminf(-m * kLog2e, 3.0e38f);  // finite also when every group of the tile sits at -inf (a masked-out prior): its weights are then 0, not NaN
                     const uint64_t l2e2 = f2_pack(kLog2e, kLog2e), nm2 = f2_pack(nm, nm);
 #pragma unroll
                     for (int k = 0; k < kSubPer; ++k) {
