@@ -22,6 +22,8 @@ SOURCES = {
     "api.cu": [],
     "prep.cu": ["--fmad=false"],
     "score_rows.cu": [],
+    "score_rows_cc32.cu": [],
+    "score_rows_cc64.cu": [],
     "score_rows_nich.cu": [],
     "nich_rows.cu": [],
     "score_rows_gp.cu": [],

@@ -935,15 +935,31 @@ static __global__ void __launch_bounds__(256) bb_compact_kernel(const __grid_con
 // 64 < G <= 128 of a single feature runs 128-thread blocks, three per SM (12 warps instead of the 8 of one
 // 256-thread block: the row-wide dependent chains of max / total / walk need the extra warps to hide their
 // latency) -- DIST_B200_OPT_SMALL_TILE selects the alternatives for A/B runs.  G > 128: 32-group tiles.
+// the feature-list (KIND = -1) instantiations are the heaviest to compile: they live in three translation units
+// (score_rows.cu: 128-group tiles; score_rows_cc32.cu: 32-group tiles + kSub; score_rows_cc64.cu: 64-group tiles)
+int launch_crosscat_tile32(dist_b200_ctx *ctx, const FeatList &feats, const RowsArgs &a, cudaStream_t s);
+int launch_crosscat_tile64(dist_b200_ctx *ctx, const FeatList &feats, const RowsArgs &a, cudaStream_t s);
+int launch_crosscat_ksub(dist_b200_ctx *ctx, const FeatList &feats, const RowsArgs &a, cudaStream_t s);
+template <int KIND>
+static int launch_tile32(dist_b200_ctx *ctx, const FeatList &feats, const RowsArgs &a, cudaStream_t s) {
+    if constexpr (KIND < 0) return launch_crosscat_tile32(ctx, feats, a, s);
+    else return launch_modes<32, KIND, 256>(ctx, feats, a, s);
+}
+template <int KIND>
+static int launch_tile64(dist_b200_ctx *ctx, const FeatList &feats, const RowsArgs &a, cudaStream_t s) {
+    if constexpr (KIND < 0) return launch_crosscat_tile64(ctx, feats, a, s);
+    else return launch_modes<64, KIND, 256>(ctx, feats, a, s);
+}
+
 template <int KIND>
 static int launch_tiers(dist_b200_ctx *ctx, const FeatList &feats, const RowsArgs &a, cudaStream_t s) {
-    if (a.G <= 32) return launch_modes<32, KIND, 256>(ctx, feats, a, s);
-    if (a.G <= 64) return launch_modes<64, KIND, 256>(ctx, feats, a, s);
+    if (a.G <= 32) return launch_tile32<KIND>(ctx, feats, a, s);
+    if (a.G <= 64) return launch_tile64<KIND>(ctx, feats, a, s);
     if (a.G <= 128) {
         if (KIND < 0) return launch_modes<128, KIND, 128>(ctx, feats, a, s);
         const int v = ctx->opt[DIST_B200_OPT_SMALL_TILE];
         if (v == 1) return launch_modes<128, KIND, 256>(ctx, feats, a, s);
-        if (v == 3) return launch_modes<32, KIND, 256>(ctx, feats, a, s);
+        if (v == 3) return launch_tile32<KIND>(ctx, feats, a, s);
         if (v != 2 && a.assign && !a.scores) {
             // sampling only: the register tile is G rounded up to 16 groups (G = 100 pads to 112 instead of 128:
             // every padded group is a wasted MUFU.EX2)
@@ -989,13 +1005,13 @@ static int launch_tiers(dist_b200_ctx *ctx, const FeatList &feats, const RowsArg
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return fail(ctx, DIST_B200_ERR_CUDA, std::string("bb_compact launch: ") + cudaGetErrorString(e));
             }
-            const int rc = launch_variant<128, KIND, true, false, 128, true>(ctx, local, a, s);
+            const int rc = launch_crosscat_ksub(ctx, local, a, s);
             if (rc != DIST_B200_ERR_UNSUPPORTED) return rc;  // (too many groups for the sub-slot sums in shared memory)
         }
     }
     const int tile = ctx->opt[DIST_B200_OPT_ROW_TILE] ? ctx->opt[DIST_B200_OPT_ROW_TILE] : (a.scores ? 64 : 32);
-    if (tile == 64) return launch_modes<64, KIND, 256>(ctx, feats, a, s);
-    return launch_modes<32, KIND, 256>(ctx, feats, a, s);
+    if (tile == 64) return launch_tile64<KIND>(ctx, feats, a, s);
+    return launch_tile32<KIND>(ctx, feats, a, s);
 }
 
 // one per model, each in its own translation unit (parallel compilation)
